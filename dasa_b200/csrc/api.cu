@@ -1,0 +1,37 @@
+// Library identification, error reporting and the dasa_gemm precision dispatcher.
+#include <stdio.h>
+#include <string.h>
+#include "common.cuh"
+#include "gemm_common.cuh"
+
+static thread_local char g_last_error[256] = "";
+
+void dasa_set_error(const char* what, cudaError_t e) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+}
+
+extern "C" int dasa_version(void) { return 101; }
+extern "C" const char* dasa_build_arch(void) { return "sm_100a"; }
+extern "C" const char* dasa_last_error(void) { return g_last_error; }
+
+extern "C" size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision) {
+  size_t a = dasa_gemm_simt_workspace(M, N, K);
+  size_t b = (precision == DASA_PREC_TF32) ? dasa_gemm_tc_workspace(M, N, K) : 0;
+  return a > b ? a : b;
+}
+
+extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                         const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue,
+                         const dasa_epilogue_t* epi, int precision, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (M < 0 || N < 0 || K < 0) return DASA_ERR_BAD_SHAPE;
+  if (A == nullptr || B == nullptr || C == nullptr) return DASA_ERR_BAD_SHAPE;
+  if (epilogue == DASA_EPI_GATE && (epi == nullptr || epi->gate_src == nullptr)) return DASA_ERR_BAD_SHAPE;
+  const EpiParams ep = make_epi(epi);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DASA_PREC_TF32 && dasa_gemm_tc_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc))
+    return dasa_gemm_tc(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
+                        workspace_bytes, st);
+  return dasa_gemm_simt(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
+                        workspace_bytes, st);
+}

@@ -1,0 +1,439 @@
+// Encoder-side kernels for DicEncoder / DicModel (r2rmodel.py:2272-2365, vilmodel.py:161-236, 479-506, 1083-1095):
+// embedding + LayerNorm, fused dropout/residual/LayerNorm, short-sequence multi-head attention (one CTA per
+// (sample, head), everything resident in shared memory), token reversal. The dense projections go through dasa_gemm.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_MAXV = 8;  // float4 per lane -> rows up to 1024 wide
+
+struct RowVec { float4 v[LN_MAXV]; };
+
+// mean / rstd over a row held in registers by one warp (two-pass, biased variance: torch.nn.LayerNorm)
+__device__ __forceinline__ void warp_row_stats(const RowVec& x, int n4, int Hd, float eps, float& mean, float& rstd) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (lane + 32 * i < n4) s += (x.v[i].x + x.v[i].y) + (x.v[i].z + x.v[i].w);
+  mean = warp_sum(s) / Hd;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (lane + 32 * i < n4) {
+      float a;
+      a = x.v[i].x - mean; q = fmaf(a, a, q); a = x.v[i].y - mean; q = fmaf(a, a, q);
+      a = x.v[i].z - mean; q = fmaf(a, a, q); a = x.v[i].w - mean; q = fmaf(a, a, q);
+    }
+  rstd = rsqrtf(warp_sum(q) / Hd + eps);
+}
+
+__device__ __forceinline__ float4 ln_apply(const float4& x, float mean, float rstd, const float4& g, const float4& b) {
+  return make_float4((x.x - mean) * rstd * g.x + b.x, (x.y - mean) * rstd * g.y + b.y, (x.z - mean) * rstd * g.z + b.z,
+                     (x.w - mean) * rstd * g.w + b.w);
+}
+
+__device__ __forceinline__ float4 mask_f4(const uint8_t* m, float scale) {
+  const uchar4 u = *reinterpret_cast<const uchar4*>(m);
+  return make_float4(u.x ? scale : 0.f, u.y ? scale : 0.f, u.z ? scale : 0.f, u.w ? scale : 0.f);
+}
+
+__global__ void __launch_bounds__(256) embed_layernorm_kernel(const int64_t* __restrict__ ids, int64_t ld_ids, int B, int L, int Hd,
+                                                              const float* __restrict__ word, const float* __restrict__ pos,
+                                                              const float* __restrict__ type0, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps,
+                                                              const uint8_t* __restrict__ mask, float scale, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B * L) return;
+  const int b = row / L, l = row % L;
+  const int64_t id = ids[(int64_t)b * ld_ids + l];
+  const int n4 = Hd >> 2;
+  RowVec x;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < n4) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(word + id * Hd) + j);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)l * Hd) + j);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(type0) + j);
+      x.v[i] = make_float4((w.x + p.x) + t.x, (w.y + p.y) + t.y, (w.z + p.z) + t.z, (w.w + p.w) + t.w);
+    }
+  }
+  float mean, rstd;
+  warp_row_stats(x, n4, Hd, eps, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < n4) {
+      float4 o = ln_apply(x.v[i], mean, rstd, __ldg(reinterpret_cast<const float4*>(gamma) + j),
+                          __ldg(reinterpret_cast<const float4*>(beta) + j));
+      if (mask != nullptr) {
+        const float4 m = mask_f4(mask + (int64_t)row * Hd + 4 * j, scale);
+        o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+      }
+      reinterpret_cast<float4*>(out + (int64_t)row * Hd)[j] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_residual_layernorm_kernel(
+    const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ mask, float scale, const float* __restrict__ resid,
+    int64_t ldr, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, const uint8_t* __restrict__ post_mask,
+    float post_scale, float* __restrict__ out, int64_t ldo, float* __restrict__ stats_out, float* __restrict__ z_out, int R, int Hd) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int n4 = Hd >> 2;
+  RowVec z;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < n4) {
+      float4 v = reinterpret_cast<const float4*>(x + (int64_t)row * ldx)[j];
+      if (mask != nullptr) {
+        const float4 m = mask_f4(mask + (int64_t)row * Hd + 4 * j, scale);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      }
+      if (resid != nullptr) {
+        const float4 r = reinterpret_cast<const float4*>(resid + (int64_t)row * ldr)[j];
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      z.v[i] = v;
+      if (z_out != nullptr) reinterpret_cast<float4*>(z_out + (int64_t)row * Hd)[j] = v;
+    }
+  }
+  float mean, rstd;
+  warp_row_stats(z, n4, Hd, eps, mean, rstd);
+  if (stats_out != nullptr && lane == 0) { stats_out[2 * row] = mean; stats_out[2 * row + 1] = rstd; }
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < n4) {
+      float4 o = ln_apply(z.v[i], mean, rstd, __ldg(reinterpret_cast<const float4*>(gamma) + j),
+                          __ldg(reinterpret_cast<const float4*>(beta) + j));
+      if (post_mask != nullptr) {
+        const float4 m = mask_f4(post_mask + (int64_t)row * Hd + 4 * j, post_scale);
+        o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+      }
+      reinterpret_cast<float4*>(out + (int64_t)row * ldo)[j] = o;
+    }
+  }
+}
+
+// dz = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma += sum_r g*xhat; dbeta += sum_r g
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dout, int64_t lddo, const float* __restrict__ z,
+                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                            const uint8_t* __restrict__ mask, float scale,
+                                                            const uint8_t* __restrict__ post_mask, float post_scale,
+                                                            float* __restrict__ dx, int64_t lddx, float* __restrict__ dresid,
+                                                            int64_t lddr, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int R, int Hd) {
+  extern __shared__ float sm_acc[];  // [2*Hd] per-CTA dgamma/dbeta partials
+  for (int i = threadIdx.x; i < 2 * Hd; i += blockDim.x) sm_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int n4 = Hd >> 2;
+  for (int row = blockIdx.x * nwarp + (threadIdx.x >> 5); row < R; row += gridDim.x * nwarp) {
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    RowVec g, xh;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) {
+        float4 d = reinterpret_cast<const float4*>(dout + (int64_t)row * lddo)[j];
+        if (post_mask != nullptr) {
+          const float4 m = mask_f4(post_mask + (int64_t)row * Hd + 4 * j, post_scale);
+          d.x *= m.x; d.y *= m.y; d.z *= m.z; d.w *= m.w;
+        }
+        const float4 zz = reinterpret_cast<const float4*>(z + (int64_t)row * Hd)[j];
+        const float4 xhat = make_float4((zz.x - mean) * rstd, (zz.y - mean) * rstd, (zz.z - mean) * rstd, (zz.w - mean) * rstd);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + j);
+        atomicAdd(&sm_acc[4 * j + 0], d.x * xhat.x); atomicAdd(&sm_acc[4 * j + 1], d.y * xhat.y);
+        atomicAdd(&sm_acc[4 * j + 2], d.z * xhat.z); atomicAdd(&sm_acc[4 * j + 3], d.w * xhat.w);
+        atomicAdd(&sm_acc[Hd + 4 * j + 0], d.x); atomicAdd(&sm_acc[Hd + 4 * j + 1], d.y);
+        atomicAdd(&sm_acc[Hd + 4 * j + 2], d.z); atomicAdd(&sm_acc[Hd + 4 * j + 3], d.w);
+        const float4 dg = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        g.v[i] = dg; xh.v[i] = xhat;
+        s1 += (dg.x + dg.y) + (dg.z + dg.w);
+        s2 += (dg.x * xhat.x + dg.y * xhat.y) + (dg.z * xhat.z + dg.w * xhat.w);
+      }
+    }
+    s1 = warp_sum(s1) / Hd;
+    s2 = warp_sum(s2) / Hd;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) {
+        float4 dz = make_float4(rstd * (g.v[i].x - s1 - xh.v[i].x * s2), rstd * (g.v[i].y - s1 - xh.v[i].y * s2),
+                                rstd * (g.v[i].z - s1 - xh.v[i].z * s2), rstd * (g.v[i].w - s1 - xh.v[i].w * s2));
+        if (dresid != nullptr) reinterpret_cast<float4*>(dresid + (int64_t)row * lddr)[j] = dz;
+        if (dx != nullptr) {
+          if (mask != nullptr) {
+            const float4 m = mask_f4(mask + (int64_t)row * Hd + 4 * j, scale);
+            dz.x *= m.x; dz.y *= m.y; dz.z *= m.z; dz.w *= m.w;
+          }
+          reinterpret_cast<float4*>(dx + (int64_t)row * lddx)[j] = dz;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Hd; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, sm_acc[i]);
+    if (dbeta) atomicAdd(dbeta + i, sm_acc[Hd + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- multi-head attention
+struct MhaArgs {
+  const float *q, *k, *v; int64_t ldq, sq, ldk, sk, ldv, sv;
+  const uint8_t* key_pad; int64_t ld_pad; const uint8_t* drop_mask; float drop_scale;
+  float* out; int64_t ldo, so; float* probs_out;
+  int B, heads, Lq, Lk, dh;
+};
+
+__global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
+  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh, dhp = dh + 1;
+  float* Qs = smem;                    // [Lq][dh]
+  float* Ks = Qs + Lq * dh;            // [Lk][dh+1]  (padded: conflict-free column reads)
+  float* Vs = Ks + Lk * dhp;           // [Lk][dh]
+  float* Ss = Vs + Lk * dh;            // [Lq][Lk]
+  const float* qb = a.q + (int64_t)b * a.sq + h * dh;
+  const float* kb = a.k + (int64_t)b * a.sk + h * dh;
+  const float* vb = a.v + (int64_t)b * a.sv + h * dh;
+  for (int i = threadIdx.x; i < Lq * dh; i += blockDim.x) Qs[i] = qb[(int64_t)(i / dh) * a.ldq + (i % dh)];
+  for (int i = threadIdx.x; i < Lk * dh; i += blockDim.x) {
+    const int r = i / dh, c = i % dh;
+    Ks[r * dhp + c] = kb[(int64_t)r * a.ldk + c];
+    Vs[i] = vb[(int64_t)r * a.ldv + c];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)dh);
+  for (int idx = threadIdx.x; idx < Lq * Lk; idx += blockDim.x) {
+    const int i = idx / Lk, j = idx % Lk;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < dh; ++d) acc = fmaf(Qs[i * dh + d], Ks[j * dhp + d], acc);
+    acc *= scale;   // reference: scores / sqrt(dh) then + mask (vilmodel.py:219-222)
+    if (a.key_pad != nullptr && a.key_pad[(int64_t)b * a.ld_pad + j]) acc += -10000.0f;
+    Ss[idx] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = wid; i < Lq; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, Ss[i * Lk + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) { const float e = expf(Ss[i * Lk + j] - mx); Ss[i * Lk + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < Lk; j += 32) {
+      float p = Ss[i * Lk + j] * inv;
+      const int64_t gi = (((int64_t)b * a.heads + h) * Lq + i) * Lk + j;
+      if (a.probs_out != nullptr) a.probs_out[gi] = p;
+      if (a.drop_mask != nullptr) p *= a.drop_mask[gi] ? a.drop_scale : 0.f;
+      Ss[i * Lk + j] = p;
+    }
+  }
+  __syncthreads();
+  float* ob = a.out + (int64_t)b * a.so + h * dh;
+  for (int idx = threadIdx.x; idx < Lq * dh; idx += blockDim.x) {
+    const int i = idx / dh, d = idx % dh;
+    float acc = 0.f;
+    for (int j = 0; j < Lk; ++j) acc = fmaf(Ss[i * Lk + j], Vs[j * dh + d], acc);
+    ob[(int64_t)i * a.ldo + d] = acc;
+  }
+}
+
+struct MhaBwdArgs {
+  const float *q, *k, *v; int64_t ldq, sq, ldk, sk, ldv, sv;
+  const float* probs; const uint8_t* drop_mask; float drop_scale;
+  const float* dout; int64_t ldo, so;
+  float *dq, *dk, *dv; int64_t lddq, sdq, lddk, sdk, lddv, sdv;
+  int B, heads, Lq, Lk, dh;
+};
+
+__global__ void __launch_bounds__(256) mha_bwd_kernel(MhaBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
+  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh, dhp = dh + 1;
+  float* Qs = smem;                     // [Lq][dh+1]
+  float* Ks = Qs + Lq * dhp;            // [Lk][dh+1]
+  float* Vs = Ks + Lk * dhp;            // [Lk][dh+1]
+  float* Os = Vs + Lk * dhp;            // dOut [Lq][dh+1]
+  float* Ps = Os + Lq * dhp;            // [Lq][Lk]  softmax probs -> dS
+  float* Pd = Ps + Lq * Lk;             // [Lq][Lk]  dropped probs
+  const float* qb = a.q + (int64_t)b * a.sq + h * dh;
+  const float* kb = a.k + (int64_t)b * a.sk + h * dh;
+  const float* vb = a.v + (int64_t)b * a.sv + h * dh;
+  const float* ob = a.dout + (int64_t)b * a.so + h * dh;
+  for (int i = threadIdx.x; i < Lq * dh; i += blockDim.x) {
+    const int r = i / dh, c = i % dh;
+    Qs[r * dhp + c] = qb[(int64_t)r * a.ldq + c];
+    Os[r * dhp + c] = ob[(int64_t)r * a.ldo + c];
+  }
+  for (int i = threadIdx.x; i < Lk * dh; i += blockDim.x) {
+    const int r = i / dh, c = i % dh;
+    Ks[r * dhp + c] = kb[(int64_t)r * a.ldk + c];
+    Vs[r * dhp + c] = vb[(int64_t)r * a.ldv + c];
+  }
+  const int64_t pbase = ((int64_t)b * a.heads + h) * Lq * Lk;
+  for (int i = threadIdx.x; i < Lq * Lk; i += blockDim.x) {
+    const float p = a.probs[pbase + i];
+    Ps[i] = p;
+    Pd[i] = (a.drop_mask != nullptr) ? (a.drop_mask[pbase + i] ? p * a.drop_scale : 0.f) : p;
+  }
+  __syncthreads();
+  // dV[j,d] = sum_i Pd[i,j] dO[i,d]
+  float* dvb = a.dv + (int64_t)b * a.sdv + h * dh;
+  for (int idx = threadIdx.x; idx < Lk * dh; idx += blockDim.x) {
+    const int j = idx / dh, d = idx % dh;
+    float acc = 0.f;
+    for (int i = 0; i < Lq; ++i) acc = fmaf(Pd[i * Lk + j], Os[i * dhp + d], acc);
+    dvb[(int64_t)j * a.lddv + d] = acc;
+  }
+  __syncthreads();
+  // dP[i,j] = (dO[i,:] . V[j,:]) * dropmask ; stored into Pd
+  for (int idx = threadIdx.x; idx < Lq * Lk; idx += blockDim.x) {
+    const int i = idx / Lk, j = idx % Lk;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < dh; ++d) acc = fmaf(Os[i * dhp + d], Vs[j * dhp + d], acc);
+    if (a.drop_mask != nullptr) acc *= a.drop_mask[pbase + idx] ? a.drop_scale : 0.f;
+    Pd[idx] = acc;
+  }
+  __syncthreads();
+  // dS = P * (dP - sum_j P dP), scaled by 1/sqrt(dh); stored into Ps
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float scale = rsqrtf((float)dh);
+  for (int i = wid; i < Lq; i += nw) {
+    float dot = 0.f;
+    for (int j = lane; j < Lk; j += 32) dot = fmaf(Ps[i * Lk + j], Pd[i * Lk + j], dot);
+    dot = warp_sum(dot);
+    for (int j = lane; j < Lk; j += 32) Ps[i * Lk + j] = Ps[i * Lk + j] * (Pd[i * Lk + j] - dot) * scale;
+  }
+  __syncthreads();
+  float* dqb = a.dq + (int64_t)b * a.sdq + h * dh;
+  for (int idx = threadIdx.x; idx < Lq * dh; idx += blockDim.x) {
+    const int i = idx / dh, d = idx % dh;
+    float acc = 0.f;
+    for (int j = 0; j < Lk; ++j) acc = fmaf(Ps[i * Lk + j], Ks[j * dhp + d], acc);
+    dqb[(int64_t)i * a.lddq + d] = acc;
+  }
+  float* dkb = a.dk + (int64_t)b * a.sdk + h * dh;
+  for (int idx = threadIdx.x; idx < Lk * dh; idx += blockDim.x) {
+    const int j = idx / dh, d = idx % dh;
+    float acc = 0.f;
+    for (int i = 0; i < Lq; ++i) acc = fmaf(Ps[i * Lk + j], Qs[i * dhp + d], acc);
+    dkb[(int64_t)j * a.lddk + d] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) reverse_tokens_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                             const int32_t* __restrict__ lengths, int B, int L, int Hd) {
+  const int n4 = Hd >> 2;
+  const int64_t total = (int64_t)B * L * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % n4);
+    const int64_t bl = i / n4;
+    const int l = (int)(bl % L), b = (int)(bl / L);
+    const int src = lengths[b] - 1 - l;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src >= 0) v = reinterpret_cast<const float4*>(x + ((int64_t)b * L + src) * Hd)[j];
+    reinterpret_cast<float4*>(out + ((int64_t)b * L + l) * Hd)[j] = v;
+  }
+}
+
+inline bool ln_shape_ok(int Hd) { return Hd % 4 == 0 && Hd >= 4 && Hd <= 32 * 4 * LN_MAXV; }
+
+}  // namespace
+
+extern "C" int dasa_embed_layernorm(const int64_t* ids, int64_t ld_ids, int B, int L, int Hd, const float* word, const float* pos,
+                                    const float* type0, const float* gamma, const float* beta, float eps,
+                                    const uint8_t* drop_mask, float drop_scale, float* out, void* stream) {
+  if (B <= 0 || L <= 0) return DASA_OK;
+  if (!ln_shape_ok(Hd)) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(word) || !dasa_aligned16(pos) || !dasa_aligned16(type0) || !dasa_aligned16(gamma) || !dasa_aligned16(beta) ||
+      !dasa_aligned16(out) || (drop_mask && reinterpret_cast<uintptr_t>(drop_mask) % 4))
+    return DASA_ERR_BAD_ALIGN;
+  embed_layernorm_kernel<<<(unsigned)dasa_cdiv((int64_t)B * L, 8), 256, 0, (cudaStream_t)stream>>>(
+      ids, ld_ids, B, L, Hd, word, pos, type0, gamma, beta, eps, drop_mask, drop_scale, out);
+  return dasa_check_launch("embed_layernorm_kernel");
+}
+
+extern "C" int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, const uint8_t* drop_mask, float drop_scale,
+                                               const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps,
+                                               const uint8_t* post_mask, float post_scale, float* out, int64_t ldo,
+                                               float* stats_out, float* z_out, int R, int Hd, void* stream) {
+  if (R <= 0) return DASA_OK;
+  if (!ln_shape_ok(Hd)) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(x) || ldx % 4 || (resid && (!dasa_aligned16(resid) || ldr % 4)) || !dasa_aligned16(out) || ldo % 4 ||
+      !dasa_aligned16(gamma) || !dasa_aligned16(beta) || (drop_mask && reinterpret_cast<uintptr_t>(drop_mask) % 4) ||
+      (post_mask && reinterpret_cast<uintptr_t>(post_mask) % 4) || (z_out && !dasa_aligned16(z_out)))
+    return DASA_ERR_BAD_ALIGN;
+  dropout_residual_layernorm_kernel<<<(unsigned)dasa_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, drop_mask, drop_scale, resid, ldr, gamma, beta, eps, post_mask, post_scale, out, ldo, stats_out, z_out, R, Hd);
+  return dasa_check_launch("dropout_residual_layernorm_kernel");
+}
+
+extern "C" int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* z, const float* gamma, const float* stats,
+                                  const uint8_t* drop_mask, float drop_scale, const uint8_t* post_mask, float post_scale,
+                                  float* dx, int64_t lddx, float* dresid, int64_t lddr, float* dgamma, float* dbeta, int R, int Hd,
+                                  void* stream) {
+  if (R <= 0) return DASA_OK;
+  if (!ln_shape_ok(Hd)) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(dout) || lddo % 4 || !dasa_aligned16(z) || !dasa_aligned16(gamma) || (dx && (!dasa_aligned16(dx) || lddx % 4)) ||
+      (dresid && (!dasa_aligned16(dresid) || lddr % 4)))
+    return DASA_ERR_BAD_ALIGN;
+  const unsigned grid = (unsigned)min((int64_t)DASA_NUM_SMS * 2, dasa_cdiv(R, 8));
+  layernorm_bwd_kernel<<<grid, 256, 2 * Hd * sizeof(float), (cudaStream_t)stream>>>(
+      dout, lddo, z, gamma, stats, drop_mask, drop_scale, post_mask, post_scale, dx, lddx, dresid, lddr, dgamma, dbeta, R, Hd);
+  return dasa_check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
+                            int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
+                            float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out, int B, int heads, int Lq,
+                            int Lk, int dh, void* stream) {
+  if (B <= 0 || heads <= 0) return DASA_OK;
+  if (Lq <= 0 || Lk <= 0 || dh <= 0) return DASA_ERR_BAD_SHAPE;
+  const size_t smem = sizeof(float) * ((size_t)Lq * dh + (size_t)Lk * (dh + 1) + (size_t)Lk * dh + (size_t)Lq * Lk);
+  if (smem > 227 * 1024) return DASA_ERR_BAD_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { dasa_set_error("mha_fwd attr", e); return DASA_ERR_CUDA; }
+  MhaArgs a{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh};
+  mha_fwd_kernel<<<(unsigned)(B * heads), 256, smem, (cudaStream_t)stream>>>(a);
+  return dasa_check_launch("mha_fwd_kernel");
+}
+
+extern "C" int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
+                            int64_t ldv, int64_t sv, const float* probs, const uint8_t* drop_mask, float drop_scale,
+                            const float* dout, int64_t ldo, int64_t so, float* dq, int64_t lddq, int64_t sdq, float* dk,
+                            int64_t lddk, int64_t sdk, float* dv, int64_t lddv, int64_t sdv, int B, int heads, int Lq, int Lk,
+                            int dh, void* stream) {
+  if (B <= 0 || heads <= 0) return DASA_OK;
+  if (Lq <= 0 || Lk <= 0 || dh <= 0 || probs == nullptr) return DASA_ERR_BAD_SHAPE;
+  const size_t smem = sizeof(float) * (2 * (size_t)Lq * (dh + 1) + 2 * (size_t)Lk * (dh + 1) + 2 * (size_t)Lq * Lk);
+  if (smem > 227 * 1024) return DASA_ERR_BAD_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { dasa_set_error("mha_bwd attr", e); return DASA_ERR_CUDA; }
+  MhaBwdArgs a{q, k, v, ldq, sq, ldk, sk, ldv, sv, probs, drop_mask, drop_scale, dout, ldo, so,
+               dq, dk, dv, lddq, sdq, lddk, sdk, lddv, sdv, B, heads, Lq, Lk, dh};
+  mha_bwd_kernel<<<(unsigned)(B * heads), 256, smem, (cudaStream_t)stream>>>(a);
+  return dasa_check_launch("mha_bwd_kernel");
+}
+
+extern "C" int dasa_reverse_tokens(const float* x, float* out, const int32_t* lengths, int B, int L, int Hd, void* stream) {
+  if (B <= 0 || L <= 0) return DASA_OK;
+  if (Hd % 4 != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(x) || !dasa_aligned16(out)) return DASA_ERR_BAD_ALIGN;
+  const int64_t total = (int64_t)B * L * (Hd / 4);
+  const unsigned grid = (unsigned)min((int64_t)DASA_NUM_SMS * 8, dasa_cdiv(total, 256));
+  reverse_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, lengths, B, L, Hd);
+  return dasa_check_launch("reverse_tokens_kernel");
+}

@@ -1,0 +1,56 @@
+// Epilogue shared by the FFMA and tcgen05 GEMM kernels.
+#pragma once
+#include "common.cuh"
+
+struct EpiParams {
+  const float* bias;
+  const float* gate_src;
+  int64_t ld_gate;
+  float* gate_out;
+  int64_t ld_gate_out;
+  const uint8_t* drop_mask;
+  float drop_scale;
+};
+
+static inline EpiParams make_epi(const dasa_epilogue_t* e) {
+  EpiParams p{};
+  if (e) {
+    p.bias = e->bias; p.gate_src = e->gate_src; p.ld_gate = e->ld_gate; p.gate_out = e->gate_out;
+    p.ld_gate_out = e->ld_gate_out; p.drop_mask = e->drop_mask; p.drop_scale = e->drop_scale;
+  }
+  return p;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// v = alpha*acc + beta*C already applied by the caller.
+__device__ __forceinline__ float apply_epilogue(float v, int m, int n, int N, int epilogue, const EpiParams& ep) {
+  if (epilogue != DASA_EPI_NONE && epilogue != DASA_EPI_TANH && ep.bias != nullptr) v += __ldg(ep.bias + n);
+  switch (epilogue) {
+    case DASA_EPI_BIAS_TANH:
+    case DASA_EPI_TANH: v = tanhf(v); break;
+    case DASA_EPI_BIAS_GELU: v = gelu_erf(v); break;
+    case DASA_EPI_BIAS_RELU: v = fmaxf(v, 0.f); break;
+    case DASA_EPI_GATE: {
+      const float s = sigmoidf_(v);
+      if (ep.gate_out != nullptr) ep.gate_out[(int64_t)m * ep.ld_gate_out + n] = s;
+      v = s * __ldg(ep.gate_src + (int64_t)m * ep.ld_gate + n);
+      break;
+    }
+    default: break;
+  }
+  if (ep.drop_mask != nullptr) v *= ep.drop_mask[(int64_t)m * N + n] ? ep.drop_scale : 0.f;
+  return v;
+}
+
+// implemented in gemm_simt.cu / gemm_tc.cu
+size_t dasa_gemm_simt_workspace(int M, int N, int K);
+int dasa_gemm_simt(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                   const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue, const EpiParams& ep,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st);
+bool dasa_gemm_tc_supported(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                            int64_t ldb, const float* C, int64_t ldc);
+size_t dasa_gemm_tc_workspace(int M, int N, int K);
+int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                 const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue, const EpiParams& ep,
+                 void* workspace, size_t workspace_bytes, cudaStream_t st);

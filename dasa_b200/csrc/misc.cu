@@ -1,0 +1,187 @@
+// Small elementwise / per-row kernels: dropout plumbing, activation backward, masked cross-entropy + action selection
+// (agent_dg.py:832-886), fused RMSprop + gradient clipping (agent_dg.py:1389-1405).
+#include "common.cuh"
+
+namespace {
+
+inline unsigned ew_grid(int64_t n, int threads = 256) {
+  int64_t g = dasa_cdiv(n, threads);
+  const int64_t cap = (int64_t)DASA_NUM_SMS * 8;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ mask,
+                                                            float scale, float* __restrict__ y, int64_t ldy, int R, int C) {
+  const int64_t total = (int64_t)R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i % C);
+    float v = x[(int64_t)r * ldx + c];
+    if (mask != nullptr) v *= mask[i] ? scale : 0.f;
+    y[(int64_t)r * ldy + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) act_backward_kernel(int act, const float* __restrict__ dy, int64_t lddy,
+                                                           const float* __restrict__ y, int64_t ldy, const uint8_t* __restrict__ mask,
+                                                           float scale, float* __restrict__ dx, int64_t lddx, int R, int C) {
+  const int64_t total = (int64_t)R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i % C);
+    float g = dy[(int64_t)r * lddy + c];
+    if (mask != nullptr) g *= mask[i] ? scale : 0.f;
+    const float yv = y[(int64_t)r * ldy + c];
+    dx[(int64_t)r * lddx + c] = (act == 0) ? g * (1.f - yv * yv) : (yv > 0.f ? g : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) axpy2d_kernel(float a, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+                                                     int64_t ldy, int accumulate, int R, int C) {
+  const int64_t total = (int64_t)R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i % C);
+    const float v = a * x[(int64_t)r * ldx + c];
+    float* dst = y + (int64_t)r * ldy + c;
+    *dst = accumulate ? *dst + v : v;
+  }
+}
+
+// splitmix64-style counter hash -> uniform in [0,1)
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = hash_uniform(seed, offset + (uint64_t)i) >= p ? 1 : 0;
+}
+
+// one warp per sample: log-softmax over the (masked) candidate logits, CE with ignore_index, gradient, argmax
+__global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict__ logit, int64_t ld, const int64_t* __restrict__ target,
+                                                        int ignore_index, int B, int Nc, float grad_scale, float* __restrict__ loss_acc,
+                                                        float* __restrict__ dlogit, int64_t* __restrict__ action,
+                                                        float* __restrict__ logprob_action, float* __restrict__ entropy) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* z = logit + (int64_t)b * ld;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int j = lane; j < Nc; j += 32) {
+    const float v = z[j];
+    if (v > mx) { mx = v; arg = j; }
+  }
+  // argmax with first-index tie-break (torch.max semantics)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  float sum = 0.f;
+  for (int j = lane; j < Nc; j += 32) sum += expf(z[j] - mx);
+  sum = warp_sum(sum);
+  const float lse = mx + logf(sum);
+  const int64_t t = target ? target[b] : (int64_t)ignore_index;
+  const bool valid = target && (t != (int64_t)ignore_index);
+  float ent = 0.f;
+  for (int j = lane; j < Nc; j += 32) {
+    const float lp = z[j] - lse;          // -inf for masked candidates
+    const float p = expf(lp);
+    if (p > 0.f) ent -= p * lp;
+    if (dlogit != nullptr) dlogit[(int64_t)b * Nc + j] = valid ? (p - (j == (int)t ? 1.f : 0.f)) * grad_scale : 0.f;
+  }
+  ent = warp_sum(ent);
+  if (lane == 0) {
+    if (valid && loss_acc != nullptr) atomicAdd(loss_acc, lse - z[t]);
+    if (action != nullptr) action[b] = arg;
+    if (logprob_action != nullptr) logprob_action[b] = z[arg] - lse;
+    if (entropy != nullptr) entropy[b] = ent;
+  }
+}
+
+__global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
+                                                      int64_t n, float lr, float alpha, float eps, float wd,
+                                                      const float* __restrict__ clip) {
+  const float c = clip ? clip[0] : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * c;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float s = alpha * sq[i] + (1.f - alpha) * gi * gi;
+    sq[i] = s;
+    p[i] = pi - lr * gi / (sqrtf(s) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fmaf(x[i], x[i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef) {
+  const float norm = sqrtf(sumsq[0]);
+  coef[0] = fminf(1.f, max_norm / (norm + 1e-6f));
+}
+
+}  // namespace
+
+extern "C" int dasa_dropout_apply(const float* x, int64_t ldx, const uint8_t* mask, float scale, float* y, int64_t ldy, int R, int C,
+                                  void* stream) {
+  if (R <= 0 || C <= 0) return DASA_OK;
+  dropout_apply_kernel<<<ew_grid((int64_t)R * C), 256, 0, (cudaStream_t)stream>>>(x, ldx, mask, scale, y, ldy, R, C);
+  return dasa_check_launch("dropout_apply_kernel");
+}
+
+extern "C" int dasa_act_backward(int act, const float* dy, int64_t lddy, const float* y, int64_t ldy, const uint8_t* mask, float scale,
+                                 float* dx, int64_t lddx, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return DASA_OK;
+  if (act != 0 && act != 1) return DASA_ERR_BAD_SHAPE;
+  act_backward_kernel<<<ew_grid((int64_t)R * C), 256, 0, (cudaStream_t)stream>>>(act, dy, lddy, y, ldy, mask, scale, dx, lddx, R, C);
+  return dasa_check_launch("act_backward_kernel");
+}
+
+extern "C" int dasa_axpy2d(float a, const float* x, int64_t ldx, float* y, int64_t ldy, int accumulate, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return DASA_OK;
+  axpy2d_kernel<<<ew_grid((int64_t)R * C), 256, 0, (cudaStream_t)stream>>>(a, x, ldx, y, ldy, accumulate, R, C);
+  return dasa_check_launch("axpy2d_kernel");
+}
+
+extern "C" int dasa_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  if (n <= 0) return DASA_OK;
+  dropout_mask_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset);
+  return dasa_check_launch("dropout_mask_kernel");
+}
+
+extern "C" int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* target, int ignore_index, int B, int Nc, float grad_scale,
+                              float* loss_acc, float* dlogit, int64_t* action, float* logprob_action, float* entropy, void* stream) {
+  if (B <= 0) return DASA_OK;
+  if (Nc <= 0) return DASA_ERR_BAD_SHAPE;
+  masked_ce_kernel<<<(unsigned)dasa_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(logit, ld, target, ignore_index, B, Nc, grad_scale,
+                                                                               loss_acc, dlogit, action, logprob_action, entropy);
+  return dasa_check_launch("masked_ce_kernel");
+}
+
+extern "C" int dasa_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha, float eps,
+                                 float weight_decay, const float* clip_coef, void* stream) {
+  if (n <= 0) return DASA_OK;
+  rmsprop_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, square_avg, n, lr, alpha, eps, weight_decay, clip_coef);
+  return dasa_check_launch("rmsprop_kernel");
+}
+
+extern "C" int dasa_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  if (n <= 0) return DASA_OK;
+  sumsq_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  return dasa_check_launch("sumsq_kernel");
+}
+
+extern "C" int dasa_clip_coef(const float* sumsq, float max_norm, float* clip_coef, void* stream) {
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, clip_coef);
+  return dasa_check_launch("clip_coef_kernel");
+}

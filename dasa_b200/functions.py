@@ -1,0 +1,319 @@
+"""torch.autograd.Function wrappers: forward AND backward of every trainable op of the hot path run on the
+hand-written kernels (closed forms: SURVEY.md Appendix A). Weight gradients are accumulated in place into
+`param.grad` by beta=1 GEMMs (no per-step temporary), which is why the Functions return None for parameters.
+"""
+import torch
+
+from . import ops
+from .ops import (EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_GATE, EPI_NONE, EPI_TANH, _acc_grad)
+
+
+def _zeros_like_grad(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) with act in {none, tanh, relu} fused in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        epi = {None: EPI_BIAS if bias is not None else EPI_NONE,
+               "tanh": EPI_BIAS_TANH if bias is not None else EPI_TANH,
+               "relu": EPI_BIAS_RELU}[act]
+        y = ops.linear_fwd(x, weight, bias, epi)
+        ctx.act, ctx.has_bias = act, bias is not None
+        ctx.save_for_backward(x, weight, bias if bias is not None else x.new_empty(0), y if act else x.new_empty(0))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.act:
+            dy = ops.act_backward(ctx.act, dy, y)
+        if weight.requires_grad:
+            ops.linear_bwd_weight(dy, x, _zeros_like_grad(weight), True)
+        if ctx.has_bias and bias.requires_grad:
+            ops.colsum(dy, _zeros_like_grad(bias), True)
+        dx = ops.linear_bwd_input(dy, weight) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None
+
+
+def linear(x, weight, bias=None, act=None):
+    return LinearFn.apply(x, weight, bias, act)
+
+
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, scale):
+        ctx.scale = scale
+        ctx.save_for_backward(mask)
+        return ops.dropout_apply(x, mask, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        return ops.dropout_apply(dy.contiguous(), mask, ctx.scale), None, None
+
+
+def dropout(x, mask, scale):
+    return x if mask is None else DropoutFn.apply(x, mask, scale)
+
+
+class AdaINGateFn(torch.autograd.Function):
+    """DGAdaChannel (ab_type=a, sigmoid) over the RGB slice of a feature tensor, fused with the decoder's drop_env mask:
+    out[..., :C] = sigmoid(d[..., :C] W^T + b) * f[..., :C] (* mask*scale);  out[..., C:] = f[..., C:]  (angle part).
+    One GEMM with the gate epilogue reading f / writing out in place at row stride F (no clones, no copy-backs)."""
+
+    @staticmethod
+    def forward(ctx, f, d, weight, bias, mask, scale, C):
+        F_all = f.shape[-1]
+        out = torch.empty(f.shape, device=f.device, dtype=torch.float32)
+        f2, R, _, ldf = ops._rows(f)
+        d2, _, _, ldd = ops._rows(d)
+        o2, _, _, ldo = ops._rows_out(out)
+        s = torch.empty(R, C, device=f.device, dtype=torch.float32)
+        ops.gemm(d2, ldd, 1, weight, C, 1, o2, ldo, R, C, C, epilogue=EPI_GATE, bias=bias, gate_src=f2, ld_gate=ldf,
+                 gate_out=s, ld_gate_out=C, drop_mask=mask, drop_scale=scale)
+        if F_all > C:
+            ops.axpy2d(1.0, f2[:, C:], o2[:, C:], accumulate=False)
+        ctx.C, ctx.scale = C, scale
+        ctx.save_for_backward(f, d, weight, bias, s, mask if mask is not None else f.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f, d, weight, bias, s, mask = ctx.saved_tensors
+        C = ctx.C
+        mask = mask if mask.numel() else None
+        dout = dout.contiguous()
+        f2, R, _, ldf = ops._rows(f)
+        d2, _, _, ldd = ops._rows(d)
+        g2, _, _, ldg = ops._rows(dout)
+        dg = torch.empty(R, C, device=f.device, dtype=torch.float32)
+        ops.call("dasa_gate_backward", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
+                 None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, R, C, ops._stream())
+        # dW[C,C] += dg^T d ; db += colsum(dg)
+        ops.gemm(dg, C, 0, d2, ldd, 0, _zeros_like_grad(weight), C, C, C, R, beta=1.0)
+        ops.colsum(dg, _zeros_like_grad(bias), True)
+        return None, None, None, None, None, None, None
+
+
+class ShiftAttnFn(torch.autograd.Function):
+    """ShiftSoftDotAttention, output_tilde=False (model.py:318-353): returns (weighted_context, pre-shift softmax)."""
+
+    @staticmethod
+    def forward(ctx, h, context, w_in, w_shift, b_shift, headings):
+        t = ops.linear_fwd(h, w_in)
+        kl = ops.linear_fwd(h, w_shift, b_shift)
+        k = w_shift.shape[0]
+        wc, p, q, kappa = ops.row_attention_fwd(context, t, None, k, headings, kl)
+        ctx.k, ctx.headings = k, headings
+        ctx.save_for_backward(h, context, w_in, w_shift, b_shift, t, p, q, kappa)
+        ctx.mark_non_differentiable(p)
+        return wc, p
+
+    @staticmethod
+    def backward(ctx, dwc, _dp):
+        h, context, w_in, w_shift, b_shift, t, p, q, kappa = ctx.saved_tensors
+        need_dctx = ctx.needs_input_grad[1]
+        dctx, dt, dkl = ops.row_attention_bwd(context, t, p, q, kappa, dwc.contiguous(), ctx.k, ctx.headings, need_dctx)
+        if w_in.requires_grad:
+            ops.linear_bwd_weight(dt, h, _zeros_like_grad(w_in), True)
+        if w_shift.requires_grad:
+            ops.linear_bwd_weight(dkl, h, _zeros_like_grad(w_shift), True)
+            ops.colsum(dkl, _zeros_like_grad(b_shift), True)
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dh = ops.linear_bwd_input(dt, w_in)
+            ops.linear_bwd_input(dkl, w_shift, out=dh, beta=1.0)
+        return dh, dctx, None, None, None, None
+
+
+class SoftDotAttnFn(torch.autograd.Function):
+    """SoftDotAttention with output_tilde=True (model.py:268-296): returns (h_tilde, alpha)."""
+
+    @staticmethod
+    def forward(ctx, h, context, mask, w_in, w_out):
+        B, Hq = h.shape
+        D = context.shape[2]
+        t = ops.linear_fwd(h, w_in)
+        cat = torch.empty(B, D + Hq, device=h.device, dtype=torch.float32)     # [wc ; h]  (model.py:291)
+        _, alpha, _, _ = ops.row_attention_fwd(context, t, mask, 0, 1, None, wc=cat)
+        ops.axpy2d(1.0, h, cat[:, D:], accumulate=False)
+        h_tilde = ops.linear_fwd(cat, w_out, None, EPI_TANH)
+        ctx.D = D
+        ctx.save_for_backward(h, context, w_in, w_out, t, alpha, cat, h_tilde)
+        ctx.mark_non_differentiable(alpha)
+        return h_tilde, alpha
+
+    @staticmethod
+    def backward(ctx, dht, _da):
+        h, context, w_in, w_out, t, alpha, cat, h_tilde = ctx.saved_tensors
+        D = ctx.D
+        du = ops.act_backward("tanh", dht.contiguous(), h_tilde)
+        if w_out.requires_grad:
+            ops.linear_bwd_weight(du, cat, _zeros_like_grad(w_out), True)
+        dcat = ops.linear_bwd_input(du, w_out)
+        need_dctx = ctx.needs_input_grad[1]
+        dctx, dt, _ = ops.row_attention_bwd(context, t, alpha, alpha, None, dcat[:, :D], 0, 1, need_dctx)
+        if w_in.requires_grad:
+            ops.linear_bwd_weight(dt, h, _zeros_like_grad(w_in), True)
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dh = dcat[:, D:].contiguous()
+            ops.linear_bwd_input(dt, w_in, out=dh, beta=1.0)
+        return dh, dctx, None, None, None
+
+
+class CandLogitsFn(torch.autograd.Function):
+    """candidate_att_layer with output_prob=False (model.py:559) + the agent's -inf masking (agent_dg.py:832-841)."""
+
+    @staticmethod
+    def forward(ctx, h, cand, leng, w_in, rgb_channels):
+        t = ops.linear_fwd(h, w_in)
+        logit = ops.cand_logits_fwd(cand, t, leng)
+        ctx.rgb = rgb_channels
+        ctx.save_for_backward(h, cand, leng if leng is not None else h.new_empty(0), w_in, t)
+        return logit
+
+    @staticmethod
+    def backward(ctx, dlogit):
+        h, cand, leng, w_in, t = ctx.saved_tensors
+        leng = leng if leng.numel() else None
+        need_dcand = ctx.needs_input_grad[1]
+        dcand_rgb, dt = ops.cand_logits_bwd(cand, t, leng, dlogit, ctx.rgb, need_dcand)
+        dcand = None
+        if need_dcand:
+            # only the AdaIN'd RGB slice carries gradient; the angle part is environment data
+            dcand = torch.zeros(cand.shape, device=cand.device, dtype=torch.float32)
+            ops.axpy2d(1.0, dcand_rgb, dcand[..., :ctx.rgb], accumulate=False)
+        if w_in.requires_grad:
+            ops.linear_bwd_weight(dt, h, _zeros_like_grad(w_in), True)
+        dh = ops.linear_bwd_input(dt, w_in) if ctx.needs_input_grad[0] else None
+        return dh, dcand, None, None, None
+
+
+class LSTMCellFn(torch.autograd.Function):
+    """nn.LSTMCell (model.py:437,514): two gate GEMMs (x W_ih^T, h W_hh^T accumulated) + fused pointwise."""
+
+    @staticmethod
+    def forward(ctx, x, h, c, w_ih, w_hh, b_ih, b_hh):
+        B, H = h.shape
+        gates = ops.linear_fwd(x, w_ih)
+        ops.linear_fwd(h, w_hh, out=gates, beta=1.0)
+        h1 = torch.empty(B, H, device=h.device, dtype=torch.float32)
+        c1 = torch.empty(B, H, device=h.device, dtype=torch.float32)
+        acts = torch.empty(B, 4 * H, device=h.device, dtype=torch.float32)
+        ops.lstm_pointwise_fwd(gates, None, b_ih, b_hh, c.contiguous(), None, h1, c1, None, acts)
+        ctx.save_for_backward(x, h, c, w_ih, w_hh, b_ih, b_hh, acts, c1)
+        return h1, c1
+
+    @staticmethod
+    def backward(ctx, dh1, dc1):
+        x, h, c, w_ih, w_hh, b_ih, b_hh, acts, c1 = ctx.saved_tensors
+        B, H = h.shape
+        dgates = torch.empty(B, 4 * H, device=h.device, dtype=torch.float32)
+        dc0 = torch.empty(B, H, device=h.device, dtype=torch.float32)
+        ops.lstm_pointwise_bwd(None if dh1 is None else dh1.contiguous(), None, None if dc1 is None else dc1.contiguous(),
+                               acts, c.contiguous(), c1, dgates, dc0)
+        if w_ih.requires_grad:
+            ops.linear_bwd_weight(dgates, x, _zeros_like_grad(w_ih), True)
+            ops.linear_bwd_weight(dgates, h, _zeros_like_grad(w_hh), True)
+            ops.colsum(dgates, _zeros_like_grad(b_ih), True)
+            ops.colsum(dgates, _zeros_like_grad(b_hh), True)
+        dx = ops.linear_bwd_input(dgates, w_ih) if ctx.needs_input_grad[0] else None
+        dh = ops.linear_bwd_input(dgates, w_hh) if ctx.needs_input_grad[1] else None
+        return dx, dh, (dc0 if ctx.needs_input_grad[2] else None), None, None, None, None
+
+
+class BiLSTMFn(torch.autograd.Function):
+    """Packed one-layer bidirectional nn.LSTM over the reversed token sequence (r2rmodel.py:2339-2357).
+    x [B, L, In]; lengths int32 [B]. Returns ctx [B, L, 2H] (zero rows past each length), h_fin [2,B,H], c_fin [2,B,H]
+    (index 0 = forward direction, 1 = reverse direction)."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        B, L, In = x.shape
+        H = w_hh_f.shape[1]
+        dev = x.device
+        x = x.contiguous()
+        out = torch.empty(B, L, 2 * H, device=dev, dtype=torch.float32)
+        hs = torch.zeros(2, L + 1, B, H, device=dev, dtype=torch.float32)     # state BEFORE step s at index s
+        cs = torch.zeros(2, L + 1, B, H, device=dev, dtype=torch.float32)
+        acts = torch.empty(2, L, B, 4 * H, device=dev, dtype=torch.float32)
+        gh = torch.empty(B, 4 * H, device=dev, dtype=torch.float32)
+        params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
+        for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
+            xp = ops.linear_fwd(x, w_ih)                        # [B, L, 4H] all time steps at once
+            order = range(L) if d == 0 else range(L - 1, -1, -1)
+            for s, l in enumerate(order):
+                ops.linear_fwd(hs[d, s], w_hh, out=gh)
+                ops.lstm_pointwise_fwd(xp[:, l], gh, b_ih, b_hh, cs[d, s], hs[d, s], hs[d, s + 1], cs[d, s + 1],
+                                       out[:, l, d * H:(d + 1) * H], acts[d, s], lengths, l)
+        h_fin = torch.stack((hs[0, L], hs[1, L]))
+        c_fin = torch.stack((cs[0, L], cs[1, L]))
+        ctx.save_for_backward(x, lengths, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hs, cs, acts)
+        return out, h_fin, c_fin
+
+    @staticmethod
+    def backward(ctx, dout, dh_fin, dc_fin):
+        (x, lengths, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hs, cs, acts) = ctx.saved_tensors
+        B, L, In = x.shape
+        H = w_hh_f.shape[1]
+        dev = x.device
+        dout = dout.contiguous() if dout is not None else torch.zeros(B, L, 2 * H, device=dev)
+        params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.zeros(B, L, In, device=dev, dtype=torch.float32) if need_dx else None
+        for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
+            dgates = torch.empty(L, B, 4 * H, device=dev, dtype=torch.float32)     # indexed by step s
+            dh = dh_fin[d].contiguous() if dh_fin is not None else torch.zeros(B, H, device=dev)
+            dc = dc_fin[d].contiguous() if dc_fin is not None else torch.zeros(B, H, device=dev)
+            dh_rec = torch.empty(B, H, device=dev, dtype=torch.float32)
+            dh_pass = torch.empty(B, H, device=dev, dtype=torch.float32)
+            dc_prev = torch.empty(B, H, device=dev, dtype=torch.float32)
+            order = list(range(L)) if d == 0 else list(range(L - 1, -1, -1))
+            for s in range(L - 1, -1, -1):
+                l = order[s]
+                # dh (carried) + dout[:, l] -> dgates ; inactive rows pass dh/dc through untouched
+                ops.lstm_pointwise_bwd(dh, dout[:, l, d * H:(d + 1) * H], dc, acts[d, s], cs[d, s], cs[d, s + 1], dgates[s],
+                                       dc_prev, dh_pass, lengths, l)
+                ops.linear_bwd_input(dgates[s], w_hh, out=dh_rec)
+                # next carried dh = recurrent gradient (active rows) + passthrough (inactive rows; dout rows there are 0)
+                ops.axpy2d(1.0, dh_pass, dh_rec, accumulate=True)
+                dh, dh_rec = dh_rec, dh
+                dc, dc_prev = dc_prev, dc
+            # weight gradients: one GEMM each over all L*B rows
+            # x rows for step s are x[:, order[s]] -> gather once
+            xs = x if d == 0 else x.flip(1)
+            xs = xs.transpose(0, 1).contiguous()                       # [L, B, In] in step order
+            if w_ih.requires_grad:
+                ops.linear_bwd_weight(dgates.view(L * B, 4 * H), xs.view(L * B, In), _zeros_like_grad(w_ih), True)
+                ops.linear_bwd_weight(dgates.view(L * B, 4 * H), hs[d, :L].reshape(L * B, H), _zeros_like_grad(w_hh), True)
+                ops.colsum(dgates.view(L * B, 4 * H), _zeros_like_grad(b_ih), True)
+                ops.colsum(dgates.view(L * B, 4 * H), _zeros_like_grad(b_hh), True)
+            if need_dx:
+                dxs = ops.linear_bwd_input(dgates.view(L * B, 4 * H), w_ih).view(L, B, In).transpose(0, 1)
+                dx += dxs if d == 0 else dxs.flip(1)
+        return (dx, None) + (None,) * 8
+
+
+class MaskedCEFn(torch.autograd.Function):
+    """sum-reduced cross entropy with ignore_index over candidate logits that already carry -inf (agent_dg.py:850).
+    Returns (loss[1], greedy action[B])."""
+
+    @staticmethod
+    def forward(ctx, logit, target, ignore_index):
+        loss = torch.zeros(1, device=logit.device, dtype=torch.float32)
+        dlogit, action, _, _ = ops.masked_ce(logit.contiguous(), target, ignore_index, 1.0, loss)
+        ctx.save_for_backward(dlogit)
+        ctx.mark_non_differentiable(action)
+        return loss, action
+
+    @staticmethod
+    def backward(ctx, dloss, _da):
+        (dlogit,) = ctx.saved_tensors
+        return dlogit * dloss, None, None

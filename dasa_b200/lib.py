@@ -1,0 +1,105 @@
+"""ctypes loader for libdasa_b200.so — the C-ABI library declared in include/dasa_b200.h.
+
+The product path has no CPU or library fallback: if the shared object is missing or a call returns an error code,
+this module raises. `check_exports()` is what the CPU test tier uses to verify that every symbol the header declares
+is exported (no compute call is made without a GPU).
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdasa_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dasa_b200.h")
+
+ERRORS = {-1: "BAD_SHAPE", -2: "BAD_ALIGN", -3: "WORKSPACE", -4: "CUDA", -5: "UNSUPPORTED"}
+
+P, I, L, F, Z, U = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
+
+
+class DasaError(RuntimeError):
+    pass
+
+
+class Epilogue(ctypes.Structure):
+    """dasa_epilogue_t"""
+    _fields_ = [("bias", P), ("gate_src", P), ("ld_gate", L), ("gate_out", P), ("ld_gate_out", L),
+                ("drop_mask", P), ("drop_scale", F)]
+
+
+def _parse_header():
+    """Derive every prototype (ctypes restype/argtypes) from include/dasa_b200.h, so the binding cannot drift from
+    the declared ABI."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    sig = {}
+    for m in re.finditer(r"(const\s+char\s*\*|size_t|int)\s+(dasa_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, params = m.group(1), m.group(2), m.group(3).strip()
+        res = ctypes.c_char_p if "char" in ret else (Z if ret == "size_t" else I)
+        args = []
+        if params and params != "void":
+            for prm in params.split(","):
+                prm = prm.strip()
+                if "dasa_epilogue_t" in prm:
+                    args.append(ctypes.POINTER(Epilogue))
+                elif "*" in prm:
+                    args.append(P)
+                elif re.match(r"(const\s+)?int64_t\b", prm):
+                    args.append(L)
+                elif re.match(r"(const\s+)?uint64_t\b", prm):
+                    args.append(U)
+                elif re.match(r"(const\s+)?size_t\b", prm):
+                    args.append(Z)
+                elif re.match(r"(const\s+)?float\b", prm):
+                    args.append(F)
+                elif re.match(r"(const\s+)?int\b", prm):
+                    args.append(I)
+                else:
+                    raise DasaError("cannot map parameter %r of %s" % (prm, name))
+        sig[name] = (res, args)
+    return sig
+
+
+_lib = None
+launches = 0          # number of kernel-launching C-ABI calls made through `call` (bench.py reports it)
+
+
+def header_symbols():
+    """Names of every function declared in include/dasa_b200.h."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dasa_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DasaError("libdasa_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                        "there is no fallback path" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _parse_header().items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check_exports():
+    lib = load()
+    names = header_symbols()
+    missing = [s for s in names if not hasattr(lib, s)]
+    unparsed = [s for s in names if s not in _parse_header()]
+    return missing, unparsed
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; raise on a non-zero status."""
+    global launches
+    fn = getattr(load(), name)
+    rc = fn(*args)
+    launches += 1
+    if rc != 0:
+        raise DasaError("%s failed: %s (%s)" % (name, ERRORS.get(rc, rc), load().dasa_last_error().decode()))
+    return rc

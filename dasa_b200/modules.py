@@ -1,0 +1,496 @@
+"""Drop-in torch.nn modules for the agent_dg hot path: same constructor arguments, forward signatures, return values
+and state_dict keys/shapes as the reference, computed by the sm_100a kernels of libdasa_b200.
+
+Reference classes mirrored here (paths relative to /root/reference/r2r_src):
+  DGAdaChannel / DGAdaStatChannel / DGAdaMeanChannel   agent_dg.py:1513-1661
+  adaptive_instance_normalization                      model.py:1822-1840
+  SoftDotAttention / ShiftSoftDotAttention             model.py:253-353
+  BAttnDecoderLSTM                                     model.py:422-574
+  Critic                                               model.py:970-982
+  DicEncoder (+ DicModel, LXRTXLayer, BertLayer ...)   r2rmodel.py:2199-2365, vilmodel.py:1245-1423
+
+The reference reads a module-global `args`; here the same fields are explicit keyword arguments whose defaults are the
+README "train" command's values (README.md:82-96). nn.Linear / nn.LayerNorm / nn.Embedding / nn.LSTM / nn.LSTMCell
+objects are used ONLY as parameter containers (identical state_dict keys and default initialisation); their forward()
+is never called. Modules raise if fed CPU tensors: there is no fallback path.
+
+Dropout: the reference uses nn.Dropout with torch's Philox stream, which custom kernels cannot reproduce. Every dropout
+site therefore draws an explicit keep mask from the ambient `DropoutSource` (see below): generated on the device by a
+counter-based RNG kernel in normal training, or injected by tag for parity tests (same tags as oracle/restated.py).
+"""
+import contextlib
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functions as Fn
+from . import ops
+from .config import FULL, PolicyConfig
+
+
+# ------------------------------------------------------------------------------------------------- dropout source
+class DropoutSource:
+    """Provides keep masks for dropout sites. tag -> uint8 keep mask (or None in eval)."""
+
+    def __init__(self, seed=0, injected=None, prefix=""):
+        self.seed, self.injected, self.prefix, self.counter = int(seed), injected, prefix, 0
+
+    def mask(self, tag, shape, p, training, device):
+        if not training or p <= 0.0:
+            return None, 1.0
+        scale = 1.0 / (1.0 - p)
+        if self.injected is not None:
+            m = self.injected.get(self.prefix + tag)
+            if m is None:
+                return None, 1.0
+            m = ops.as_keep_mask(m.to(device))
+            assert tuple(m.shape) == tuple(shape), (tag, m.shape, shape)
+            return m, scale
+        n = 1
+        for s in shape:
+            n *= s
+        m = ops.dropout_mask(tuple(shape), p, self.seed, self.counter, device)
+        self.counter += n
+        return m, scale
+
+
+_source = DropoutSource()
+
+
+def dropout_source():
+    return _source
+
+
+@contextlib.contextmanager
+def use_dropout_source(src):
+    global _source
+    old, _source = _source, src
+    try:
+        yield src
+    finally:
+        _source = old
+
+
+def _drop(x, tag, p, training):
+    m, scale = _source.mask(tag, x.shape, p, training, x.device)
+    return Fn.dropout(x, m, scale)
+
+
+# -------------------------------------------------------------------------------------------------- AdaIN family
+class DGAdaChannel(nn.Module):
+    """agent_dg.py:1513-1547 with ab_type in {a}, a_type='sigmoid' (the README configuration)."""
+
+    def __init__(self, channel, eps=1e-6, ab_type="a", a_type="sigmoid"):
+        super().__init__()
+        if ab_type != "a" or a_type != "sigmoid":
+            raise NotImplementedError("only --ab_type a --a_type sigmoid is on the hot path (README.md:86)")
+        self.a_fc = nn.Linear(channel, channel)
+        self.eps, self.channel = eps, channel
+
+    def forward(self, f_t, d_t):
+        """f_t, d_t: [N, L, C] (strided slices of [N, L, C+A] buffers are read in place) -> [N, L, C]."""
+        return Fn.AdaINGateFn.apply(f_t, d_t, self.a_fc.weight, self.a_fc.bias, None, 1.0, self.channel)
+
+    def gate_features(self, feat, dfeat, drop_mask=None, drop_scale=1.0):
+        """Fused form used by the rollout: feat/dfeat [N, L, C+A] -> AdaIN'd copy with the angle part carried over and
+        the decoder's drop_env mask folded into the GEMM epilogue (agent_dg.py:764-768 + model.py:506-508)."""
+        return Fn.AdaINGateFn.apply(feat, dfeat, self.a_fc.weight, self.a_fc.bias, drop_mask, drop_scale, self.channel)
+
+
+class DGAdaStatChannel(nn.Module):
+    """agent_dg.py:1639-1661 (forward; these variants are not in the named training configuration)."""
+
+    def __init__(self, channel, eps=1e-6):
+        super().__init__()
+        self.a_fc = nn.Linear(4 * channel, channel)
+        self.b_fc = nn.Linear(4 * channel, channel)
+        self.eps = eps
+
+    def forward(self, f_t, d_t):
+        stats = ops.view_stats(d_t)
+        a = ops.linear_fwd(stats, self.a_fc.weight, self.a_fc.bias)
+        b = ops.linear_fwd(stats, self.b_fc.weight, self.b_fc.bias)
+        return ops.channel_modulate(f_t, a, b)
+
+
+class DGAdaMeanChannel(nn.Module):
+    """agent_dg.py:1620-1636 (forward)."""
+
+    def __init__(self, channel, eps=1e-6):
+        super().__init__()
+        self.a_fc = nn.Linear(channel, channel)
+        self.b_fc = nn.Linear(channel, channel)
+        self.eps, self.channel = eps, channel
+
+    def forward(self, f_t, d_t):
+        mean = ops.view_stats(d_t)[:, :self.channel]
+        a = ops.linear_fwd(mean, self.a_fc.weight, self.a_fc.bias)
+        b = ops.linear_fwd(mean, self.b_fc.weight, self.b_fc.bias)
+        return ops.channel_modulate(f_t, a, b)
+
+
+def adaptive_instance_normalization(content_feat, style_feat):
+    """model.py:1831-1840."""
+    assert content_feat.size() == style_feat.size()
+    return ops.adain_rows(content_feat, style_feat, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------------ attention
+class SoftDotAttention(nn.Module):
+    """model.py:253-296."""
+
+    def __init__(self, query_dim, ctx_dim):
+        super().__init__()
+        self.linear_in = nn.Linear(query_dim, ctx_dim, bias=False)
+        self.linear_out = nn.Linear(query_dim + ctx_dim, query_dim, bias=False)
+
+    def forward(self, h, context, mask=None, output_tilde=True, output_prob=True, cand_leng=None, rgb_channels=None):
+        if output_tilde and output_prob:
+            return Fn.SoftDotAttnFn.apply(h, context, mask, self.linear_in.weight, self.linear_out.weight)
+        if not output_prob:
+            # candidate_att_layer call (model.py:559): only the raw logits are consumed; the softmax / weighted sum /
+            # linear_out tail of the reference is dead work and is skipped.
+            leng = cand_leng
+            if leng is None and mask is not None:
+                leng = (~mask.bool()).sum(1).to(torch.int32)
+            rgb = context.shape[2] if rgb_channels is None else rgb_channels
+            logit = Fn.CandLogitsFn.apply(h, context, leng, self.linear_in.weight, rgb)
+            return None, logit
+        raise NotImplementedError("SoftDotAttention(output_tilde=False, output_prob=True) is not used by agent_dg")
+
+
+class ShiftSoftDotAttention(nn.Module):
+    """model.py:300-353 (used with mask=None, output_tilde=False: model.py:511)."""
+
+    def __init__(self, query_dim, ctx_dim, kernel_size=3, headings=12):
+        super().__init__()
+        self.linear_in = nn.Linear(query_dim, ctx_dim, bias=False)
+        self.linear_shift = nn.Linear(query_dim, kernel_size)
+        self.linear_out = nn.Linear(query_dim + ctx_dim, query_dim, bias=False)   # unused by the decoder; kept for state_dict
+        self.kernel_size, self.padding_size, self.headings = kernel_size, kernel_size // 2, headings
+
+    def forward(self, h, context, mask=None, output_tilde=True, output_prob=True):
+        if mask is not None or output_tilde or not output_prob:
+            raise NotImplementedError("agent_dg calls feat_att_layer(h, feature, output_tilde=False) only (model.py:511)")
+        return Fn.ShiftAttnFn.apply(h, context, self.linear_in.weight, self.linear_shift.weight, self.linear_shift.bias,
+                                    self.headings)
+
+
+# -------------------------------------------------------------------------------------------------------- decoder
+class BAttnDecoderLSTM(nn.Module):
+    """model.py:422-574."""
+
+    def __init__(self, embedding_size, hidden_size, dropout_ratio, feature_size=2048 + 4, pred_back=False,
+                 angle_feat_size=128, featdropout=0.4, use_shift=True, shift_kernel_size=5):
+        super().__init__()
+        if pred_back:
+            raise NotImplementedError("--pred_back is not part of the agent_dg README configuration")
+        self.embedding_size, self.feature_size, self.hidden_size = embedding_size, feature_size, hidden_size
+        self.angle_feat_size, self.dropout_ratio, self.featdropout = angle_feat_size, dropout_ratio, featdropout
+        self.embedding = nn.Sequential(nn.Linear(angle_feat_size, embedding_size), nn.Tanh())
+        self.drop = nn.Dropout(p=dropout_ratio)          # attribute kept: the agent pokes decoder.drop_env (agent_dg.py:657)
+        self.drop_env = nn.Dropout(p=featdropout)
+        self.lstm = nn.LSTMCell(embedding_size + feature_size, hidden_size)
+        if use_shift:
+            self.feat_att_layer = ShiftSoftDotAttention(hidden_size, feature_size, shift_kernel_size)
+        else:
+            raise NotImplementedError("--use_shift is part of the hot-path configuration")
+        self.attention_layer = SoftDotAttention(hidden_size, hidden_size * 2)
+        self.candidate_att_layer = SoftDotAttention(hidden_size, feature_size)
+        self.pred_back = pred_back
+
+    def forward(self, action, feature, cand_feat, h_0, prev_h1, c_0, ctx, ctx_mask=None, already_dropfeat=False,
+                cand_leng=None):
+        """Same contract as the reference; h_0 is ignored there too (model.py:472-474, 514). When not already_dropfeat
+        and in training mode the dropped features are written back into the caller's tensors like the reference does
+        (model.py:508, 557). `cand_leng` (int32 [B], optional extension) lets the logits come out already -inf-masked."""
+        A, p, tr = self.angle_feat_size, self.dropout_ratio, self.training
+        emb = Fn.linear(action, self.embedding[0].weight, self.embedding[0].bias, "tanh")
+        emb = _drop(emb, "dec.act", p, tr)
+        if not already_dropfeat and tr:
+            m, s = _source.mask("dec.feat", feature[..., :-A].shape, self.featdropout, tr, feature.device)
+            if m is not None:
+                dropped = torch.cat([Fn.dropout(feature[..., :-A], m, s), feature[..., -A:]], -1)
+                with torch.no_grad():
+                    feature.copy_(dropped)
+                feature = dropped
+        h_prev_drop = _drop(prev_h1, "dec.h_prev", p, tr)
+        attn_feat, _ = self.feat_att_layer(h_prev_drop, feature, output_tilde=False)
+        x = torch.cat((emb, attn_feat), 1)
+        h_1, c_1 = Fn.LSTMCellFn.apply(x, prev_h1, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih,
+                                       self.lstm.bias_hh)
+        h_1_drop = _drop(h_1, "dec.h1", p, tr)
+        h_tilde, alpha = self.attention_layer(h_1_drop, ctx, ctx_mask)
+        h_tilde_drop = _drop(h_tilde, "dec.htilde", p, tr)
+        if not already_dropfeat and tr:
+            m, s = _source.mask("dec.cand", cand_feat[..., :-A].shape, self.featdropout, tr, cand_feat.device)
+            if m is not None:
+                dropped = torch.cat([Fn.dropout(cand_feat[..., :-A], m, s), cand_feat[..., -A:]], -1)
+                with torch.no_grad():
+                    cand_feat.copy_(dropped)
+                cand_feat = dropped
+        _, logit = self.candidate_att_layer(h_tilde_drop, cand_feat, output_prob=False, cand_leng=cand_leng,
+                                            rgb_channels=self.feature_size - A)
+        return h_1, c_1, logit, h_tilde, {}
+
+
+class Critic(nn.Module):
+    """model.py:970-982."""
+
+    def __init__(self, critic_dim=1024, dropout=0.5):
+        super().__init__()
+        self.dim, self.p = critic_dim, dropout
+        self.state2value = nn.Sequential(nn.Linear(critic_dim, critic_dim), nn.ReLU(), nn.Dropout(dropout),
+                                         nn.Linear(critic_dim, 1))
+
+    def forward(self, state):
+        x = Fn.linear(state, self.state2value[0].weight, self.state2value[0].bias, "relu")
+        x = _drop(x, "critic", self.p, self.training)
+        return Fn.linear(x, self.state2value[3].weight, self.state2value[3].bias).squeeze()
+
+
+# -------------------------------------------------------------------------------------------------------- encoder
+class _BertSelfAttention(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(hid, hid), nn.Linear(hid, hid), nn.Linear(hid, hid)
+
+
+class _BertSelfOutput(nn.Module):
+    def __init__(self, hid, eps, in_dim=None):
+        super().__init__()
+        self.dense = nn.Linear(in_dim or hid, hid)
+        self.LayerNorm = nn.LayerNorm(hid, eps=eps)
+
+
+class _BertAttention(nn.Module):
+    def __init__(self, hid, eps):
+        super().__init__()
+        self.self = _BertSelfAttention(hid)
+        self.output = _BertSelfOutput(hid, eps)
+
+
+class _BertXAttention(nn.Module):
+    def __init__(self, hid, eps):
+        super().__init__()
+        self.att = _BertSelfAttention(hid)
+        self.output = _BertSelfOutput(hid, eps)
+
+
+class _BertIntermediate(nn.Module):
+    def __init__(self, hid, inter):
+        super().__init__()
+        self.dense = nn.Linear(hid, inter)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, hid, inter, eps):
+        super().__init__()
+        self.attention = _BertAttention(hid, eps)
+        self.intermediate = _BertIntermediate(hid, inter)
+        self.output = _BertSelfOutput(hid, eps, in_dim=inter)
+
+
+class _LXRTXLayer(nn.Module):
+    def __init__(self, hid, inter, eps):
+        super().__init__()
+        self.lang_self_att = _BertAttention(hid, eps)
+        self.lang_inter = _BertIntermediate(hid, inter)
+        self.lang_output = _BertSelfOutput(hid, eps, in_dim=inter)
+        self.visn_self_att = _BertAttention(hid, eps)
+        self.visn_inter = _BertIntermediate(hid, inter)
+        self.visn_output = _BertSelfOutput(hid, eps, in_dim=inter)
+        self.visual_attention = _BertXAttention(hid, eps)
+
+
+class _BertEmbeddings(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(cfg.vocab, cfg.bert_hidden, padding_idx=0)
+        self.position_embeddings = nn.Embedding(cfg.max_pos, cfg.bert_hidden)
+        self.token_type_embeddings = nn.Embedding(cfg.type_vocab, cfg.bert_hidden)
+        self.LayerNorm = nn.LayerNorm(cfg.bert_hidden, eps=cfg.bert_eps)
+
+
+class _BertPooler(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        self.dense = nn.Linear(hid, hid)
+
+
+class _VisionEncoder(nn.Module):
+    def __init__(self, vision_size, hid):
+        super().__init__()
+        self.visn_fc = nn.Linear(vision_size, hid)
+        self.visn_layer_norm = nn.LayerNorm(hid, eps=1e-12)
+
+
+class DicModel(nn.Module):
+    """vilmodel.py:1245-1423, forward-only kernels (train config: every output is detached, vilmodel.py:1377-1410)."""
+
+    def __init__(self, cfg: PolicyConfig, vision_size):
+        super().__init__()
+        self.cfg = cfg
+        hid, inter, eps = cfg.bert_hidden, cfg.bert_inter, cfg.bert_eps
+        self.embeddings = _BertEmbeddings(cfg)
+        self.pooler = _BertPooler(hid)
+        self.lalayer = nn.ModuleList([_BertLayer(hid, inter, eps) for _ in range(cfg.la_layers)])
+        self.addlayer = nn.ModuleList([_LXRTXLayer(hid, inter, eps) for _ in range(cfg.vl_layers)])
+        self.vision_encoder = _VisionEncoder(vision_size, hid)
+        self.update_lang_bert, self.update_add_layer = False, cfg.update_add_layer
+        self._qkv_cache = {}
+
+    # fused [3*hid, hid] QKV weights (one GEMM instead of three); rebuilt when the parameters change version
+    def _qkv(self, att, which="qkv"):
+        key = (id(att), which)
+        ver = (att.query.weight._version, att.key.weight._version, att.value.weight._version,
+               att.query.weight.data_ptr())
+        hit = self._qkv_cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        mods = {"qkv": (att.query, att.key, att.value), "kv": (att.key, att.value)}[which]
+        with torch.no_grad():
+            w = torch.cat([m.weight for m in mods], 0).contiguous()
+            b = torch.cat([m.bias for m in mods], 0).contiguous()
+        self._qkv_cache[key] = (ver, w, b)
+        return w, b
+
+    def _out_ln(self, out_mod, x, resid, tag, training):
+        p = self.cfg.bert_dropout
+        y = ops.linear_fwd(x, out_mod.dense.weight, out_mod.dense.bias)
+        m, s = _source.mask(tag, y.shape, p, training, y.device)
+        return ops.dropout_residual_layernorm(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias,
+                                              out_mod.LayerNorm.eps, m, s)
+
+    def _self_att(self, att_mod, x, key_pad, tag, training):
+        cfg = self.cfg
+        hid = cfg.bert_hidden
+        w, b = self._qkv(att_mod.self)
+        qkv = ops.linear_fwd(x, w, b)
+        B, L = x.shape[0], x.shape[1]
+        m, s = _source.mask(tag + ".probs", (B, cfg.bert_heads, L, L), cfg.bert_dropout, training, x.device)
+        o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s)
+        return self._out_ln(att_mod.output, o, x, tag + ".out", training)
+
+    def _cross_att(self, xatt, x, ctx, key_pad, tag, training):
+        cfg = self.cfg
+        hid = cfg.bert_hidden
+        q = ops.linear_fwd(x, xatt.att.query.weight, xatt.att.query.bias)
+        w, b = self._qkv(xatt.att, "kv")
+        kv = ops.linear_fwd(ctx, w, b)
+        B, Lq, Lk = x.shape[0], x.shape[1], ctx.shape[1]
+        m, s = _source.mask(tag + ".probs", (B, cfg.bert_heads, Lq, Lk), cfg.bert_dropout, training, x.device)
+        o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s)
+        return self._out_ln(xatt.output, o, x, tag + ".out", training)
+
+    def _ffn(self, inter_mod, out_mod, x, tag, training):
+        y = ops.linear_fwd(x, inter_mod.dense.weight, inter_mod.dense.bias, ops.EPI_BIAS_GELU)
+        return self._out_ln(out_mod, y, x, tag, training)
+
+    @torch.no_grad()
+    def language_stack(self, input_ids, pad_mask, training):
+        """BertEmbeddings + la_layers x BertLayer (vilmodel.py:1366-1378). pad_mask: uint8 [B, L], 1 = padding."""
+        cfg, e = self.cfg, self.embeddings
+        B, L = input_ids.shape
+        m, s = _source.mask("enc.emb", (B, L, cfg.bert_hidden), cfg.bert_dropout, training, input_ids.device)
+        x = ops.embed_layernorm(input_ids, e.word_embeddings.weight, e.position_embeddings.weight,
+                                e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps, m, s)
+        for i, layer in enumerate(self.lalayer):
+            a = self._self_att(layer.attention, x, pad_mask, "enc.la%d.att" % i, training)
+            x = self._ffn(layer.intermediate, layer.output, a, "enc.la%d.ffn" % i, training)
+        return x
+
+    @torch.no_grad()
+    def cross_modal(self, lang, pad_mask, img_feats, training):
+        """VisionEncoder + vl_layers x LXRTXLayer (vilmodel.py:1383-1410)."""
+        cfg, ve = self.cfg, self.vision_encoder
+        v = ops.linear_fwd(img_feats, ve.visn_fc.weight, ve.visn_fc.bias)
+        m, s = _source.mask("enc.visn", v.shape, cfg.bert_dropout, training, v.device)
+        visn = ops.dropout_residual_layernorm(v, None, ve.visn_layer_norm.weight, ve.visn_layer_norm.bias, 1e-12,
+                                              None, 1.0, m, s)
+        for i, layer in enumerate(self.addlayer):
+            t = "enc.vl%d" % i
+            l1 = self._cross_att(layer.visual_attention, lang, visn, None, t + ".x_lv", training)
+            v1 = self._cross_att(layer.visual_attention, visn, lang, pad_mask, t + ".x_vl", training)
+            l2 = self._self_att(layer.lang_self_att, l1, pad_mask, t + ".ls", training)
+            v2 = self._self_att(layer.visn_self_att, v1, None, t + ".vs", training)
+            lang = self._ffn(layer.lang_inter, layer.lang_output, l2, t + ".lo", training)
+            visn = self._ffn(layer.visn_inter, layer.visn_output, v2, t + ".vo", training)
+        return lang, visn
+
+
+class DicEncoder(nn.Module):
+    """r2rmodel.py:2199-2365. Constructor signature as the reference; `cfg` (optional) shrinks the transformer for tests."""
+
+    lstm_num_layers = 1
+
+    def __init__(self, vision_size, hidden_size, dec_hidden_size, dropout_ratio, bidirectional, update, bert_n_layers,
+                 reverse_input, top_lstm, vl_layers, la_layers, bert_type="small", update_add_layer=True, cfg=None):
+        super().__init__()
+        if not (bidirectional and reverse_input and top_lstm and bert_n_layers == 1 and bert_type == "small" and not update):
+            raise NotImplementedError("agent_dg constructs DicEncoder(.., True, False, 1, True, True, ..) (agent_dg.py:161)")
+        from dataclasses import replace
+        cfg = replace(cfg or FULL, vl_layers=vl_layers, la_layers=la_layers, enc_hidden=hidden_size, hidden=dec_hidden_size,
+                      enc_dropout=dropout_ratio, update_add_layer=bool(update_add_layer))
+        if cfg.update_add_layer:
+            raise NotImplementedError("finetune (--d_update_add_layer) backward through the VL layers lands in a later round")
+        self.cfg = cfg
+        self.hidden_size, self.dec_hidden_size, self.dropout_ratio = hidden_size, dec_hidden_size, dropout_ratio
+        self.drop = nn.Dropout(p=dropout_ratio)
+        self.num_directions = 2
+        self.bert = DicModel(cfg, vision_size)
+        self.lstm = nn.LSTM(cfg.bert_hidden, hidden_size, 1, batch_first=True, bidirectional=True)
+        n_in = hidden_size * 2
+        self.encoder2decoder_ht = nn.Linear(n_in, dec_hidden_size)     # unused when top_lstm; kept for state_dict
+        self.encoder2decoder_ct = nn.Linear(n_in, dec_hidden_size)
+        self.encoder_lstm2decoder_ht = nn.Linear(n_in, dec_hidden_size)
+        self.encoder_lstm2decoder_ct = nn.Linear(n_in, dec_hidden_size)
+        self.cache_language = False     # exact in eval mode; opt-in
+        self._lang_cache = None
+
+    def forward(self, inputs, mask, lengths, f_t_all=None):
+        """inputs [B, maxInput] int64, mask [B, Lmax] bool (True = pad), lengths [B] (sorted desc), f_t_all [B, 36, F]
+        -> (ctx [B, Lmax, 2H], decoder_init [B, Hd], c_t [B, Hd], mask, vision_outputs [B, 36, 768])."""
+        tr = self.training
+        L = mask.size(1)
+        pad = mask.to(torch.uint8).contiguous()
+        ids = inputs[:, :L]
+        key = (inputs.data_ptr(), L, inputs._version)
+        if self.cache_language and not tr and self._lang_cache is not None and self._lang_cache[0] == key:
+            lang0 = self._lang_cache[1]
+        else:
+            lang0 = self.bert.language_stack(ids, pad, tr)
+            if self.cache_language and not tr:
+                self._lang_cache = (key, lang0)
+        lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr)
+        len32 = torch.as_tensor(lengths, device=lang.device).to(torch.int32)
+        rev = ops.reverse_tokens(lang, len32)
+        l = self.lstm
+        ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0,
+                                              l.weight_ih_l0_reverse, l.weight_hh_l0_reverse, l.bias_ih_l0_reverse,
+                                              l.bias_hh_l0_reverse)
+        # h_t = cat(enc_h_t[-1], enc_h_t[-2]): reverse-direction final state first (r2rmodel.py:2345-2346)
+        h_cat = torch.cat((h_fin[1], h_fin[0]), 1)
+        c_cat = torch.cat((c_fin[1], c_fin[0]), 1)
+        decoder_init = Fn.linear(h_cat, self.encoder_lstm2decoder_ht.weight, self.encoder_lstm2decoder_ht.bias, "tanh")
+        c_t = Fn.linear(c_cat, self.encoder_lstm2decoder_ct.weight, self.encoder_lstm2decoder_ct.bias)
+        ctx = _drop(ctx, "enc.ctx", self.dropout_ratio, tr)
+        return ctx, decoder_init, c_t, mask, visn
+
+
+def build_policy(cfg: PolicyConfig = FULL, state=None, device="cuda"):
+    """Construct (encoder, decoder, critic, adaIn) the way Seq2SeqAgent.__init__ does (agent_dg.py:161-201) and
+    optionally load seeded / checkpoint state dicts (keys as in the reference)."""
+    enc = DicEncoder(cfg.feat, cfg.enc_hidden, cfg.hidden, cfg.enc_dropout, True, False, 1, True, True, cfg.vl_layers,
+                     cfg.la_layers, "small", cfg.update_add_layer, cfg=cfg)
+    dec = BAttnDecoderLSTM(cfg.action_emb, cfg.hidden, cfg.dropout, feature_size=cfg.feat, angle_feat_size=cfg.angle_size,
+                           featdropout=cfg.featdropout, shift_kernel_size=cfg.shift_kernel)
+    cri = Critic(cfg.critic_dim, cfg.dropout)
+    ada = DGAdaChannel(cfg.rgb_size)
+    if state is not None:
+        enc.load_state_dict(state["encoder"], strict=True)
+        dec.load_state_dict(state["decoder"], strict=True)
+        cri.load_state_dict(state["critic"], strict=True)
+        ada.load_state_dict(state["adaIn"], strict=True)
+    return tuple(m.to(device) for m in (enc, dec, cri, ada))

@@ -1,0 +1,390 @@
+"""Tensor-level wrappers over the C ABI (include/dasa_b200.h) and the autograd Functions built from them.
+
+PyTorch is plumbing here (device memory, streams, the autograd tape); every numeric step of the hot path is one of
+the hand-written sm_100a kernels in dasa_b200/csrc. There is no CPU / eager fallback: tensors must be CUDA fp32.
+"""
+import ctypes
+
+import torch
+
+from . import lib
+from .lib import Epilogue, call
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_TANH, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_GATE, EPI_TANH = range(7)
+PREC_FP32, PREC_TF32 = 0, 1
+
+_precision = PREC_FP32
+_workspaces = {}
+
+
+def set_precision(name):
+    """'fp32' (FFMA, exact fp32 products) or 'tf32' (tcgen05 tensor cores for the dense projections)."""
+    global _precision
+    _precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}[name]
+
+
+def get_precision():
+    return "tf32" if _precision == PREC_TF32 else "fp32"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise lib.DasaError("dasa_b200 ops need CUDA tensors (no CPU fallback)")
+            if t.dtype != torch.float32:
+                raise lib.DasaError("expected float32, got %s" % t.dtype)
+
+
+def _rows(t):
+    """[.., C] tensor -> (tensor, R, C, ld): rows addressed as base + r*ld, unit inner stride. Strided slices such as
+    feat[..., :2048] of a [B, V, 2176] buffer are passed through in place; anything irregular is made contiguous
+    (inputs only — callers allocate outputs themselves, so outputs are always regular)."""
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        t = t.contiguous()
+    if t.dim() == 2:
+        return t, t.shape[0], t.shape[1], (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+    uniform = all(t.shape[i] == 1 or t.stride(i) == t.stride(i + 1) * t.shape[i + 1] for i in range(t.dim() - 2))
+    if not uniform or t.shape[-2] == 1:
+        t = t.contiguous()
+    return t, t.numel() // t.shape[-1], t.shape[-1], t.stride(-2)
+
+
+def _rows_out(t):
+    """Like _rows, for OUTPUT tensors: the kernel must write the caller's storage, so a copy is an error."""
+    t2, R, C, ld = _rows(t)
+    if t2.data_ptr() != t.data_ptr():
+        raise lib.DasaError("output tensor is not row-regular (shape %s strides %s)" % (tuple(t.shape), t.stride()))
+    return t2, R, C, ld
+
+
+def workspace(nbytes):
+    dev = torch.cuda.current_device()
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 64 << 20), dtype=torch.uint8, device="cuda")
+        _workspaces[dev] = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------------------------------- GEMM
+def gemm(A, lda, a_kmajor, Bm, ldb, b_kmajor, C, ldc, M, N, K, alpha=1.0, beta=0.0, epilogue=EPI_NONE, bias=None,
+         gate_src=None, ld_gate=0, gate_out=None, ld_gate_out=0, drop_mask=None, drop_scale=1.0, precision=None):
+    prec = _precision if precision is None else precision
+    nbytes = lib.load().dasa_gemm_workspace_bytes(M, N, K, prec)
+    ws = workspace(nbytes) if nbytes else None
+    epi = Epilogue(_p(bias), _p(gate_src), ld_gate, _p(gate_out), ld_gate_out, _p(drop_mask), float(drop_scale))
+    call("dasa_gemm", int(a_kmajor), int(b_kmajor), M, N, K, float(alpha), _p(A), lda, _p(Bm), ldb, float(beta), _p(C), ldc,
+         epilogue, ctypes.byref(epi), prec, _p(ws), ws.numel() if ws is not None else 0, _stream())
+
+
+def linear_fwd(x, w, bias=None, epilogue=None, out=None, beta=0.0, precision=None):
+    """y[.., N] = epi(x[.., K] @ w[N, K]^T (+ bias)) ; x rows may be strided."""
+    _chk(x, w, bias, out)
+    x2, M, K, lda = _rows(x)
+    N = w.shape[0]
+    assert w.shape[1] == K and w.is_contiguous(), (w.shape, K)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32) if x.dim() > 1 else \
+            torch.empty(N, device=x.device, dtype=torch.float32)
+    o2, Mo, No, ldc = _rows_out(out)
+    assert Mo == M and No == N
+    if epilogue is None:
+        epilogue = EPI_BIAS if bias is not None else EPI_NONE
+    gemm(x2, lda, 1, w, K, 1, o2, ldc, M, N, K, beta=beta, epilogue=epilogue, bias=bias, precision=precision)
+    return out
+
+
+def linear_bwd_input(dy, w, out=None, beta=0.0, precision=None):
+    """dx[.., K] (+)= dy[.., N] @ w[N, K]"""
+    _chk(dy, w, out)
+    d2, M, N, lda = _rows(dy)
+    K = w.shape[1]
+    if out is None:
+        out = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=torch.float32)
+    o2, _, _, ldc = _rows_out(out)
+    gemm(d2, lda, 1, w, K, 0, o2, ldc, M, K, N, beta=beta, precision=precision)
+    return out
+
+
+def linear_bwd_weight(dy, x, dw, accumulate=True, precision=None):
+    """dw[N, K] (+)= dy[.., N]^T @ x[.., K]   (reduction over the rows)"""
+    _chk(dy, x, dw)
+    d2, M, N, ldd = _rows(dy)
+    x2, Mx, K, ldx = _rows(x)
+    assert M == Mx and dw.shape == (N, K) and dw.is_contiguous()
+    gemm(d2, ldd, 0, x2, ldx, 0, dw, K, N, K, M, beta=1.0 if accumulate else 0.0, precision=precision)
+    return dw
+
+
+def colsum(x, out, accumulate=True):
+    x2, M, N, ld = _rows(x)
+    call("dasa_colsum", _p(x2), ld, M, N, _p(out), int(accumulate), _stream())
+    return out
+
+
+def _acc_grad(param, fn_new):
+    """Accumulate a parameter gradient in place (param.grad is created zero-filled on first use)."""
+    if param.grad is None:
+        param.grad = torch.zeros_like(param)
+    fn_new(param.grad)
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def dropout_apply(x, mask, scale, out=None):
+    x2, R, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    o2, _, _, ldo = _rows_out(out)
+    call("dasa_dropout_apply", _p(x2), ldx, _p(mask), float(scale), _p(o2), ldo, R, C, _stream())
+    return out
+
+
+def act_backward(act, dy, y, mask=None, scale=1.0):
+    d2, R, C, ldd = _rows(dy)
+    y2, _, _, ldy = _rows(y)
+    dx = torch.empty(dy.shape, device=dy.device, dtype=torch.float32)
+    x2, _, _, ldx = _rows_out(dx)
+    call("dasa_act_backward", 0 if act == "tanh" else 1, _p(d2), ldd, _p(y2), ldy, _p(mask), float(scale), _p(x2), ldx, R, C,
+         _stream())
+    return dx
+
+
+def axpy2d(a, x, y, accumulate=True):
+    x2, R, C, ldx = _rows(x)
+    y2, _, _, ldy = _rows_out(y)
+    call("dasa_axpy2d", float(a), _p(x2), ldx, _p(y2), ldy, int(accumulate), R, C, _stream())
+    return y
+
+
+def dropout_mask(shape, p, seed, offset=0, device="cuda"):
+    m = torch.empty(shape, dtype=torch.uint8, device=device)
+    call("dasa_dropout_mask", _p(m), m.numel(), float(p), int(seed), int(offset), _stream())
+    return m
+
+
+def as_keep_mask(m):
+    """Accept bool / float (pre-scaled) / uint8 masks from tests; return contiguous uint8 keep flags."""
+    if m is None:
+        return None
+    if m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    return m.contiguous()
+
+
+# -------------------------------------------------------------------------------------------------- AdaIN family
+def gate_modulate(g, f, out, mask=None, scale=1.0):
+    g2, R, C, ldg = _rows(g)
+    f2, _, _, ldf = _rows(f)
+    o2, _, _, ldo = _rows_out(out)
+    call("dasa_gate_modulate", _p(g2), ldg, _p(f2), ldf, _p(o2), ldo, _p(mask), float(scale), R, C, _stream())
+    return out
+
+
+def view_stats(d):
+    """d [N, V, C] (rows may be strided) -> [N, 4C] mean/std/max/min over views."""
+    N, V, C = d.shape
+    assert d.stride(2) == 1
+    stats = torch.empty(N, 4 * C, device=d.device, dtype=torch.float32)
+    call("dasa_view_stats", _p(d), d.stride(1), d.stride(0), N, V, C, _p(stats), _stream())
+    return stats
+
+
+def channel_modulate(f, a, b, out=None):
+    N, V, C = f.shape
+    assert f.stride(2) == 1
+    if out is None:
+        out = torch.empty(N, V, C, device=f.device, dtype=torch.float32)
+    call("dasa_channel_modulate", _p(f), f.stride(1), f.stride(0), _p(a.contiguous()), _p(None if b is None else b.contiguous()),
+         _p(out), out.stride(1), out.stride(0), N, V, C, _stream())
+    return out
+
+
+def adain_rows(f, d, eps=1e-5, out=None):
+    f2, R, C, ldf = _rows(f)
+    d2, _, _, ldd = _rows(d)
+    if out is None:
+        out = torch.empty(f.shape, device=f.device, dtype=torch.float32)
+    o2, _, _, ldo = _rows_out(out)
+    call("dasa_adain_rows", _p(f2), ldf, _p(d2), ldd, _p(o2), ldo, R, C, float(eps), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------- attention kernels
+def row_attention_fwd(ctx, t, mask=None, shift_k=0, headings=12, kappa_logits=None, wc=None, want_q=False):
+    B, rows, D = ctx.shape
+    assert ctx.stride(2) == 1
+    if wc is None:
+        wc = torch.empty(B, D, device=ctx.device, dtype=torch.float32)
+    attn = torch.empty(B, rows, device=ctx.device, dtype=torch.float32)
+    q = torch.empty(B, rows, device=ctx.device, dtype=torch.float32) if (want_q or shift_k > 0) else None
+    kappa = torch.empty(B, shift_k, device=ctx.device, dtype=torch.float32) if shift_k > 0 else None
+    if mask is not None:
+        mask = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+        assert mask.stride(1) == 1
+    call("dasa_row_attention_fwd", _p(ctx), ctx.stride(1), ctx.stride(0), B, rows, D, _p(t), t.stride(0), _p(mask),
+         mask.stride(0) if mask is not None else 0, shift_k, headings, _p(kappa_logits),
+         kappa_logits.stride(0) if kappa_logits is not None else 0, _p(wc), wc.stride(0), _p(attn), _p(q), _p(kappa), _stream())
+    return wc, attn, q, kappa
+
+
+def row_attention_bwd(ctx, t, attn, q, kappa, dwc, shift_k=0, headings=12, need_dctx=True, dctx=None, accumulate=False):
+    B, rows, D = ctx.shape
+    if need_dctx and dctx is None:
+        dctx = torch.empty(B, rows, D, device=ctx.device, dtype=torch.float32)
+    dt = torch.empty(B, D, device=ctx.device, dtype=torch.float32)
+    dkl = torch.empty(B, shift_k, device=ctx.device, dtype=torch.float32) if shift_k > 0 else None
+    assert dwc.stride(1) == 1
+    call("dasa_row_attention_bwd", _p(ctx), ctx.stride(1), ctx.stride(0), B, rows, D, _p(t), t.stride(0), _p(attn), _p(q),
+         _p(kappa), shift_k, headings, _p(dwc), dwc.stride(0), _p(dctx), dctx.stride(1) if dctx is not None else 0,
+         dctx.stride(0) if dctx is not None else 0, int(accumulate), _p(dt), dt.stride(0), _p(dkl),
+         dkl.stride(0) if dkl is not None else 0, _stream())
+    return dctx, dt, dkl
+
+
+def cand_logits_fwd(cand, t, leng):
+    B, Nc, D = cand.shape
+    assert cand.stride(2) == 1
+    logit = torch.empty(B, Nc, device=cand.device, dtype=torch.float32)
+    call("dasa_cand_logits_fwd", _p(cand), cand.stride(1), cand.stride(0), B, Nc, D, _p(t), t.stride(0), _p(leng), _p(logit),
+         _stream())
+    return logit
+
+
+def cand_logits_bwd(cand, t, leng, dlogit, Dc, need_dcand=True):
+    B, Nc, D = cand.shape
+    dcand = torch.empty(B, Nc, Dc, device=cand.device, dtype=torch.float32) if need_dcand else None
+    dt = torch.empty(B, D, device=cand.device, dtype=torch.float32)
+    call("dasa_cand_logits_bwd", _p(cand), cand.stride(1), cand.stride(0), B, Nc, D, _p(t), t.stride(0), _p(leng),
+         _p(dlogit.contiguous()), _p(dcand), dcand.stride(1) if need_dcand else 0, dcand.stride(0) if need_dcand else 0, Dc,
+         _p(dt), dt.stride(0), _stream())
+    return dcand, dt
+
+
+# -------------------------------------------------------------------------------------------------------- LSTM
+def lstm_pointwise_fwd(ga, gb, bias_a, bias_b, c_prev, h_prev, h_out, c_out, seq_out=None, acts_out=None, active=None, pos=0):
+    B, H = h_out.shape
+
+    def ld(t):
+        return 0 if t is None else t.stride(0)
+    call("dasa_lstm_pointwise_fwd", _p(ga), ld(ga), _p(gb), ld(gb), _p(bias_a), _p(bias_b), _p(c_prev), ld(c_prev), _p(h_prev),
+         ld(h_prev), _p(h_out), ld(h_out), _p(c_out), ld(c_out), _p(seq_out), ld(seq_out), _p(acts_out), ld(acts_out),
+         _p(active), int(pos), B, H, _stream())
+
+
+def lstm_pointwise_bwd(dh, dh2, dc, acts, c_prev, c_new, dgates, dc_prev, dh_pass=None, active=None, pos=0):
+    B, H = c_new.shape
+
+    def ld(t):
+        return 0 if t is None else t.stride(0)
+    call("dasa_lstm_pointwise_bwd", _p(dh), ld(dh), _p(dh2), ld(dh2), _p(dc), ld(dc), _p(acts), ld(acts), _p(c_prev), ld(c_prev),
+         _p(c_new), ld(c_new), _p(dgates), ld(dgates), _p(dc_prev), ld(dc_prev), _p(dh_pass), ld(dh_pass), _p(active), int(pos),
+         B, H, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ encoder pieces
+def embed_layernorm(ids, word, pos, type0, gamma, beta, eps, mask=None, scale=1.0):
+    B, L = ids.shape
+    Hd = word.shape[1]
+    assert ids.dtype == torch.int64 and ids.stride(1) == 1
+    out = torch.empty(B, L, Hd, device=word.device, dtype=torch.float32)
+    call("dasa_embed_layernorm", _p(ids), ids.stride(0), B, L, Hd, _p(word), _p(pos), _p(type0), _p(gamma), _p(beta), float(eps),
+         _p(mask), float(scale), _p(out), _stream())
+    return out
+
+
+def dropout_residual_layernorm(x, resid, gamma, beta, eps, mask=None, scale=1.0, post_mask=None, post_scale=1.0,
+                               save=False):
+    x2, R, Hd, ldx = _rows(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    o2, _, _, ldo = _rows_out(out)
+    r2, ldr = None, 0
+    if resid is not None:
+        r2, _, _, ldr = _rows(resid)
+    stats = torch.empty(R, 2, device=x.device, dtype=torch.float32) if save else None
+    z = torch.empty(R, Hd, device=x.device, dtype=torch.float32) if save else None
+    call("dasa_dropout_residual_layernorm", _p(x2), ldx, _p(mask), float(scale), _p(r2), ldr, _p(gamma), _p(beta), float(eps),
+         _p(post_mask), float(post_scale), _p(o2), ldo, _p(stats), _p(z), R, Hd, _stream())
+    return (out, stats, z) if save else out
+
+
+def layernorm_bwd(dout, z, gamma, stats, dgamma, dbeta, mask=None, scale=1.0, post_mask=None, post_scale=1.0, need_dx=True):
+    d2, R, Hd, ldd = _rows(dout)
+    dresid = torch.empty(dout.shape, device=dout.device, dtype=torch.float32)
+    dx = torch.empty(dout.shape, device=dout.device, dtype=torch.float32) if (need_dx and mask is not None) else None
+    call("dasa_layernorm_bwd", _p(d2), ldd, _p(z), _p(gamma), _p(stats), _p(mask), float(scale), _p(post_mask), float(post_scale),
+         _p(dx), Hd, _p(dresid), Hd, _p(dgamma), _p(dbeta), R, Hd, _stream())
+    return (dx if dx is not None else dresid), dresid
+
+
+def mha_fwd(q, k, v, heads, key_pad=None, drop_mask=None, drop_scale=1.0, save_probs=False):
+    """q [B,Lq,Hd] / k,v [B,Lk,Hd] views with unit inner stride (slices of a fused QKV buffer are fine)."""
+    B, Lq, Hd = q.shape
+    Lk = k.shape[1]
+    dh = Hd // heads
+    out = torch.empty(B, Lq, Hd, device=q.device, dtype=torch.float32)
+    probs = torch.empty(B, heads, Lq, Lk, device=q.device, dtype=torch.float32) if save_probs else None
+    if key_pad is not None and key_pad.dtype != torch.uint8:
+        key_pad = key_pad.to(torch.uint8)
+    call("dasa_mha_fwd", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0),
+         _p(key_pad), key_pad.stride(0) if key_pad is not None else 0, _p(drop_mask), float(drop_scale), _p(out), out.stride(1),
+         out.stride(0), _p(probs), B, heads, Lq, Lk, dh, _stream())
+    return (out, probs) if save_probs else out
+
+
+def mha_bwd(q, k, v, probs, dout, heads, drop_mask=None, drop_scale=1.0):
+    B, Lq, Hd = q.shape
+    Lk = k.shape[1]
+    dh = Hd // heads
+    dq = torch.empty(B, Lq, Hd, device=q.device, dtype=torch.float32)
+    dk = torch.empty(B, Lk, Hd, device=q.device, dtype=torch.float32)
+    dv = torch.empty(B, Lk, Hd, device=q.device, dtype=torch.float32)
+    dout = dout.contiguous()
+    call("dasa_mha_bwd", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0),
+         _p(probs), _p(drop_mask), float(drop_scale), _p(dout), dout.stride(1), dout.stride(0), _p(dq), dq.stride(1), dq.stride(0),
+         _p(dk), dk.stride(1), dk.stride(0), _p(dv), dv.stride(1), dv.stride(0), B, heads, Lq, Lk, dh, _stream())
+    return dq, dk, dv
+
+
+def reverse_tokens(x, lengths_i32):
+    B, L, Hd = x.shape
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    call("dasa_reverse_tokens", _p(x), _p(out), _p(lengths_i32), B, L, Hd, _stream())
+    return out
+
+
+# -------------------------------------------------------------------------------------------------- loss / optim
+def masked_ce(logit, target, ignore_index, grad_scale, loss_acc, want_grad=True, want_action=True, want_stats=False):
+    B, Nc = logit.shape
+    assert logit.stride(1) == 1
+    dlogit = torch.empty(B, Nc, device=logit.device, dtype=torch.float32) if want_grad else None
+    action = torch.empty(B, device=logit.device, dtype=torch.int64) if want_action else None
+    lp = torch.empty(B, device=logit.device, dtype=torch.float32) if want_stats else None
+    ent = torch.empty(B, device=logit.device, dtype=torch.float32) if want_stats else None
+    call("dasa_masked_ce", _p(logit), logit.stride(0), _p(target), int(ignore_index), B, Nc, float(grad_scale), _p(loss_acc),
+         _p(dlogit), _p(action), _p(lp), _p(ent), _stream())
+    return dlogit, action, lp, ent
+
+
+def rmsprop_step(param, grad, square_avg, lr, alpha=0.99, eps=1e-8, weight_decay=0.0, clip_coef=None):
+    call("dasa_rmsprop_step", _p(param), _p(grad), _p(square_avg), param.numel(), float(lr), float(alpha), float(eps),
+         float(weight_decay), _p(clip_coef), _stream())
+
+
+def sumsq(x, out):
+    call("dasa_sumsq", _p(x), x.numel(), _p(out), _stream())
+
+
+def clip_coef(sumsq_t, max_norm, coef):
+    call("dasa_clip_coef", _p(sumsq_t), float(max_norm), _p(coef), _stream())

@@ -1,0 +1,149 @@
+"""The agent_dg rollout loop around the drop-in modules (agent_dg.py:633-1033, the teacher-forced / greedy branches),
+with a device-resident synthetic stand-in for the environment (there is no simulator offline) and the optimizer step
+of Seq2SeqAgent.optim_step (agent_dg.py:1389-1405) on fused kernels.
+
+Differences from the reference loop that do not change the numbers:
+  * the 4 clone()s + 2 strided copy-backs per step around adaIn (agent_dg.py:764-768) disappear: the gate GEMM reads the
+    stride-2176 slices in place and its epilogue writes the AdaIN'd copy directly;
+  * the decoder's per-element drop_env masks (model.py:506-508, 556-557) are folded into that epilogue, so the decoder is
+    called with already_dropfeat=True on tensors that are already dropped (same values);
+  * no per-step host synchronisation: losses/actions stay on the device (the reference syncs at agent_dg.py:890).
+"""
+import torch
+
+from . import functions as Fn
+from . import modules as M
+from . import ops
+from .config import FULL, PolicyConfig
+
+
+class DeviceEpisodes:
+    """synth.Episodes moved to the GPU (optionally re-uploaded from pinned host memory each step for the e2e metric)."""
+
+    FIELDS = ("input_a_t", "f_t", "d_t", "cand_feat", "cand_dfeat", "cand_leng", "target")
+
+    def __init__(self, ep, device="cuda", resident=True):
+        self.B, self.T, self.cfg = ep.B, ep.T, ep.cfg
+        self.host = ep
+        self.device = device
+        self.seq = ep.seq.to(device)
+        self.seq_mask = ep.seq_mask.to(device)
+        self.seq_lengths = ep.seq_lengths.to(device).to(torch.int32)
+        self.resident = resident
+        if resident:
+            for k in self.FIELDS:
+                setattr(self, k, getattr(ep, k).to(device))
+        else:
+            self.stage = {k: torch.empty_like(getattr(ep, k)[0], device=device) for k in self.FIELDS}
+
+    def step(self, t):
+        if self.resident:
+            return tuple(getattr(self, k)[t] for k in self.FIELDS)
+        out = []
+        for k in self.FIELDS:                       # host -> device copy of this step's inputs (pinned source)
+            self.stage[k].copy_(getattr(self.host, k)[t], non_blocking=True)
+            out.append(self.stage[k])
+        return tuple(out)
+
+
+class NavPolicy:
+    """encoder + decoder + critic + adaIn, built like Seq2SeqAgent.__init__ (agent_dg.py:149-201)."""
+
+    def __init__(self, cfg: PolicyConfig = FULL, state=None, device="cuda"):
+        self.cfg, self.device = cfg, device
+        self.encoder, self.decoder, self.critic, self.adaIn = M.build_policy(cfg, state, device)
+        self.models = (self.encoder, self.decoder, self.critic, self.adaIn)
+        self._opt = None
+
+    def train(self):
+        for m in self.models:
+            m.train()
+        return self
+
+    def eval(self):
+        for m in self.models:
+            m.eval()
+        return self
+
+    def zero_grad(self):
+        for m in self.models:
+            for p in m.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    # ------------------------------------------------------------------------------------------------ one nav step
+    def step(self, ep, t, carry):
+        """Loop body of vl_rollout up to the masked logits (agent_dg.py:727-841). carry = None at t == 0."""
+        cfg, tr = self.cfg, self.decoder.training
+        a_t, f_t, d_t, cand, cand_d, leng, _ = ep.step(t)
+        src = M.dropout_source()
+        B, V, _ = f_t.shape
+        C = cfg.rgb_size
+        m_f, s_f = src.mask("dec.feat", (B, V, C), cfg.featdropout, tr, f_t.device)
+        m_c, s_c = src.mask("dec.cand", (B, cand.shape[1], C), cfg.featdropout, tr, f_t.device)
+        df_t = self.adaIn.gate_features(f_t, d_t, m_f, s_f)                 # K1 views
+        cand_g = self.adaIn.gate_features(cand, cand_d, m_c, s_c)           # K1 candidates
+        ctx, en_h, en_c, _, _ = self.encoder(ep.seq, ep.seq_mask, ep.seq_lengths, f_t_all=f_t)   # sees the RAW f_t
+        prev_h1, c_0 = (en_h, en_c) if carry is None else carry
+        h_t, c_t, logit, h1, _ = self.decoder(a_t, df_t, cand_g, prev_h1, prev_h1, c_0, ctx, ep.seq_mask,
+                                              already_dropfeat=True, cand_leng=leng)
+        return logit, h_t, (h1, c_t)
+
+    # ------------------------------------------------------------------------------------------- teacher-forced rollout
+    def teacher_rollout(self, ep, T=None, ml_weight=0.4, tag_steps=True):
+        """feedback='teacher', train_rl=False (agent_dg.py:1368-1370): returns (loss tensor [1], logits list, actions list).
+        loss = sum_t CE_sum(logit_t, target_t) * ml_weight / B  (agent_dg.py:850, 1024)."""
+        T = ep.T if T is None else T
+        carry, total, logits, actions = None, None, [], []
+        src = M.dropout_source()
+        base_prefix = src.prefix
+        for t in range(T):
+            if tag_steps:
+                src.prefix = base_prefix + "t%d." % t
+            logit, h_t, carry = self.step(ep, t, carry)
+            loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.step(t)[6] if ep.resident else ep.stage["target"], self.cfg.ignore_id)
+            total = loss_t if total is None else total + loss_t
+            logits.append(logit)
+            actions.append(a_t)
+        src.prefix = base_prefix
+        return total * (ml_weight / ep.B), logits, actions
+
+    @torch.no_grad()
+    def greedy_rollout(self, ep, T=None):
+        """feedback='argmax' decode (agent_dg.py:871-875) over pre-generated observations: per-step greedy actions."""
+        T = ep.T if T is None else T
+        carry, actions, logits = None, [], []
+        for t in range(T):
+            logit, h_t, carry = self.step(ep, t, carry)
+            _, a_t, _, _ = ops.masked_ce(logit, None, self.cfg.ignore_id, 0.0, None, want_grad=False)
+            actions.append(a_t)
+            logits.append(logit)
+        return actions, logits
+
+    # ------------------------------------------------------------------------------------------------- optimizer (a12)
+    def _build_optimizer(self, lr):
+        groups = []
+        for name, m, clip in (("encoder", self.encoder, 40.0), ("decoder", self.decoder, 40.0), ("critic", self.critic, None),
+                              ("adaIn", self.adaIn, None)):
+            ps = [p for p in m.parameters() if p.requires_grad]
+            groups.append({"name": name, "params": ps, "clip": clip, "sq": [torch.zeros_like(p) for p in ps]})
+        self._opt = {"groups": groups, "lr": lr, "sumsq": torch.zeros(1, device=self.device),
+                     "coef": torch.ones(1, device=self.device)}
+
+    def optim_step(self, lr=1e-4):
+        """clip_grad_norm_(encoder, 40), clip_grad_norm_(decoder, 40), RMSprop on all four groups (agent_dg.py:1389-1405).
+        Parameters that never received a gradient are skipped, like torch.optim does for grad=None."""
+        if self._opt is None:
+            self._build_optimizer(lr)
+        o = self._opt
+        for g in o["groups"]:
+            coef = None
+            live = [(p, sq) for p, sq in zip(g["params"], g["sq"]) if p.grad is not None]
+            if g["clip"] is not None:
+                o["sumsq"].zero_()
+                for p, _ in live:
+                    ops.sumsq(p.grad, o["sumsq"])
+                ops.clip_coef(o["sumsq"], g["clip"], o["coef"])
+                coef = o["coef"]
+            for p, sq in live:
+                ops.rmsprop_step(p.data, p.grad, sq, lr, 0.99, 1e-8, 0.0, coef)

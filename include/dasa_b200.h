@@ -1,0 +1,220 @@
+/*
+ * dasa_b200 — C ABI of the B200-native kernels behind DASA's agent_dg navigation-policy hot path.
+ *
+ * The reference (sunqiang85/DASA) has no FFI layer: its boundary for this path is the torch.nn.Module surface
+ * that r2r_src/agent_dg.py touches. The Python drop-in modules in dasa_b200/modules.py keep
+ * that surface; underneath they call this library through ctypes with raw device pointers. Every entry point
+ * below names the reference code it replaces (paths relative to r2r_src/).
+ *
+ * Conventions
+ *   - all tensors are device pointers, fp32 row-major unless stated; `ld*` are leading dimensions in ELEMENTS
+ *     so strided slices (e.g. feature[..., :2048] of a [.., 2176] row) are read/written in place;
+ *   - caller owns every buffer (incl. workspaces); kernels never allocate, free or retain pointers;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation inside, so
+ *     every call is CUDA-graph capturable;
+ *   - return value: 0 = ok, negative = DASA_ERR_* below; asynchronous CUDA faults surface at the next sync;
+ *   - dropout is always an explicit, caller-provided keep mask (uint8, 1 = keep) plus the scale 1/(1-p);
+ *     a NULL mask means "no dropout" (eval mode).
+ */
+#ifndef DASA_B200_H
+#define DASA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DASA_OK 0
+#define DASA_ERR_BAD_SHAPE (-1)
+#define DASA_ERR_BAD_ALIGN (-2)
+#define DASA_ERR_WORKSPACE (-3)
+#define DASA_ERR_CUDA (-4)
+#define DASA_ERR_UNSUPPORTED (-5)
+
+/* library / build identification */
+int dasa_version(void);                 /* 100*major + minor */
+const char* dasa_build_arch(void);      /* "sm_100a" */
+const char* dasa_last_error(void);      /* text of the last CUDA error seen by a launch wrapper */
+
+/* ------------------------------------------------------------------------------------------------ GEMM
+ * C[M,N] = epilogue( alpha * opA(A)[M,K] * opB(B)[K,N] + beta * C ), row-major C with leading dim ldc.
+ *   a_kmajor=1: A stored [M,K] (k contiguous, lda >= K);  a_kmajor=0: A stored [K,M] (m contiguous, lda >= M)
+ *   b_kmajor=1: B stored [N,K] (k contiguous, ldb >= K) — the nn.Linear weight layout;  b_kmajor=0: B stored [K,N]
+ * epilogue: DASA_EPI_* applied after alpha/beta; `bias` is [N] (may be NULL); for DASA_EPI_GATE the result is
+ *   sigmoid(acc + bias) * gate_src[m*ld_gate + n], optionally multiplied by drop_mask*drop_scale, and the sigmoid
+ *   itself is stored to `gate_out` (ld = ld_gate_out) when non-NULL (needed by the backward pass).
+ * precision: DASA_PREC_FP32 = FFMA (exact fp32 products); DASA_PREC_TF32 = tcgen05 kind::tf32 tensor cores
+ *   (fp32 storage, 10-bit mantissa products, fp32 accumulate in TMEM) — falls back to FP32 when the operands do
+ *   not satisfy the TMA alignment rules (16-byte base/stride). Never a CPU fallback.
+ * workspace: split-K partial sums; size from dasa_gemm_workspace_bytes (may be 0).
+ * Replaces nn.Linear / torch.bmm / torch.matmul call sites: agent_dg.py:1538 (a_fc), model.py:277,315 (linear_in),
+ * model.py:292 (linear_out), model.py:501, 514 (LSTMCell gates), vilmodel.py:210-212,233,247,293,306 (BERT), 1088.
+ */
+enum { DASA_EPI_NONE = 0, DASA_EPI_BIAS = 1, DASA_EPI_BIAS_TANH = 2, DASA_EPI_BIAS_GELU = 3, DASA_EPI_BIAS_RELU = 4,
+       DASA_EPI_GATE = 5, DASA_EPI_TANH = 6 };
+enum { DASA_PREC_FP32 = 0, DASA_PREC_TF32 = 1 };
+
+typedef struct {
+  const float* bias;          /* [N] or NULL */
+  const float* gate_src;      /* EPI_GATE: f, [M, ld_gate] */
+  int64_t ld_gate;
+  float* gate_out;            /* EPI_GATE: sigmoid(acc+bias) saved here when non-NULL, [M, ld_gate_out] */
+  int64_t ld_gate_out;
+  const uint8_t* drop_mask;   /* optional keep mask [M, N] contiguous, applied to the final value */
+  float drop_scale;
+} dasa_epilogue_t;
+
+size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
+int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue,
+              const dasa_epilogue_t* epi, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* column sums: out[n] (+)= sum_m X[m*ldx + n]   (bias gradients) */
+int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------ AdaIN family
+ * a1: DGAdaChannel ab_type=a, a_type=sigmoid (agent_dg.py:1534-1547) = dasa_gemm(..., DASA_EPI_GATE) for the fused
+ *     path, or this elementwise epilogue when the pre-activation g is already in memory:
+ *     out[r, c] = sigmoid(g[r, c]) * f[r, c] (* mask * scale);  r < R, c < C.                                   */
+int dasa_gate_modulate(const float* g, int64_t ldg, const float* f, int64_t ldf, float* out, int64_t ldo,
+                       const uint8_t* drop_mask, float drop_scale, int R, int C, void* stream);
+/* backward of the gate: dg[r,c] = dout[r,c] * mask*scale * f[r,c] * s(1-s), s = saved sigmoid (Appendix A, K1) */
+int dasa_gate_backward(const float* dout, int64_t lddo, const float* f, int64_t ldf, const float* s, int64_t lds,
+                       const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, int R, int C, void* stream);
+
+/* a2: per-channel statistics over the views of one panorama (agent_dg.py:1651-1656):
+ *     stats[n, 0:C]=mean, [C:2C]=unbiased std, [2C:3C]=max, [3C:4C]=min of d[n, :, c] over V views.            */
+int dasa_view_stats(const float* d, int64_t ld_row, int64_t ld_sample, int N, int V, int C, float* stats, void* stream);
+/* a2: out[n,v,c] = a[n,c] * f[n,v,c] + b[n,c]  (agent_dg.py:1636, 1661); b may be NULL                          */
+int dasa_channel_modulate(const float* f, int64_t ldf_row, int64_t ldf_sample, const float* a, const float* b,
+                          float* out, int64_t ldo_row, int64_t ldo_sample, int N, int V, int C, void* stream);
+/* a2: model.adaptive_instance_normalization (model.py:1822-1840): per (n, view) row statistics over the C channels,
+ *     unbiased variance + eps; out = (f - mu_f) / sd_f * sd_d + mu_d. One pass: read f, read d, write out.      */
+int dasa_adain_rows(const float* f, int64_t ldf, const float* d, int64_t ldd, float* out, int64_t ldo,
+                    int R, int C, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------- decoder attention (a3-a5)
+ * Single-pass "row attention": for each sample b, rows r < nrows[b] (or `rows` if nrows==NULL) of ctx[b] (row
+ * stride ld_row, sample stride ld_sample, D channels) are staged ONCE in shared memory by bulk-async (TMA) copies,
+ * split across the CTAs of a thread-block cluster by channel; partial logits z_r = ctx_r . t are reduced across the
+ * cluster through distributed shared memory, then
+ *   shift_k == 0 : alpha = softmax(z masked to -inf where mask[b,r] != 0)            (model.py:276-288, SoftDotAttention)
+ *   shift_k  > 0 : p = softmax(z); kappa = softmax(W_s h + b_s);
+ *                  q[e,l] = sum_j kappa_j p[e,(l+j-k/2) mod headings]                 (model.py:327-345, ShiftSoftDotAttention)
+ * and wc = sum_r w_r ctx_r is produced from the same shared-memory tile. attn_out receives the PRE-shift softmax
+ * (model.py:336,351-353); q_out (optional) the shifted weights (needed by backward).
+ * wc is written with leading dim ld_wc so it can land directly in the [wc ; h] concat buffer of linear_out.
+ */
+int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
+                           const float* t, int64_t ld_t, const uint8_t* mask, int64_t ld_mask,
+                           int shift_k, int headings, const float* kappa_logits, int64_t ld_kappa,
+                           float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, void* stream);
+/* backward (Appendix A, K3 / K4): given dwc -> dctx (may be NULL), dt, dkappa_logits (shift only).
+ * dctx_accumulate != 0 adds into dctx instead of overwriting it.                                                  */
+int dasa_row_attention_bwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
+                           const float* t, int64_t ld_t, const float* attn, const float* q, const float* kappa,
+                           int shift_k, int headings, const float* dwc, int64_t ld_dwc,
+                           float* dctx, int64_t ldd_row, int64_t ldd_sample, int dctx_accumulate,
+                           float* dt, int64_t ld_dt, float* dkappa_logits, int64_t ld_dkappa, void* stream);
+
+/* a5: candidate logits (model.py:559 with output_prob=False; masking agent_dg.py:832-841):
+ *     logit[b,c] = cand[b,c,:] . t[b,:] for c < cand_leng[b], -inf otherwise.                                     */
+int dasa_cand_logits_fwd(const float* cand, int64_t ld_row, int64_t ld_sample, int B, int Nc, int D,
+                         const float* t, int64_t ld_t, const int32_t* cand_leng, float* logit, void* stream);
+/* backward: dcand[b,c,:] = dlogit[b,c] * t[b,:] (zero rows for c >= leng; only the first Dc channels are written),
+ *           dt[b,:] = sum_c dlogit[b,c] * cand[b,c,:]                                                              */
+int dasa_cand_logits_bwd(const float* cand, int64_t ld_row, int64_t ld_sample, int B, int Nc, int D,
+                         const float* t, int64_t ld_t, const int32_t* cand_leng, const float* dlogit,
+                         float* dcand, int64_t ldd_row, int64_t ldd_sample, int Dc, float* dt, int64_t ld_dt, void* stream);
+
+/* --------------------------------------------------------------------------------------------- LSTM (a6, a9)
+ * Pointwise part of an LSTM step, gate order i,f,g,o (nn.LSTMCell model.py:437,514; nn.LSTM r2rmodel.py:2342).
+ * gates = ga (+ gb) (+ bias_a + bias_b), each [B, 4H] with its own leading dim; gb / biases may be NULL.
+ * `active` (optional, [B] int32 lengths) with `pos`: rows with pos >= active[b] keep (h_prev, c_prev) and write zeros
+ * to `seq_out` (packed-sequence semantics). acts_out (optional, [B,4H]) receives the post-nonlinearity gates for
+ * the backward pass.                                                                                               */
+int dasa_lstm_pointwise_fwd(const float* ga, int64_t ld_ga, const float* gb, int64_t ld_gb, const float* bias_a,
+                            const float* bias_b, const float* c_prev, int64_t ld_cp, const float* h_prev, int64_t ld_hp,
+                            float* h_out, int64_t ld_h, float* c_out, int64_t ld_c, float* seq_out, int64_t ld_seq,
+                            float* acts_out, int64_t ld_acts, const int32_t* active, int pos, int B, int H, void* stream);
+/* backward: (dh, dc_in, saved acts, c_prev, c_new) -> dgates [B,4H], dc_prev. dh2 (optional) is added to dh.
+ * Inactive rows (pos >= active[b]) pass dh/dc straight through into dh_pass/dc_prev and produce zero dgates.       */
+int dasa_lstm_pointwise_bwd(const float* dh, int64_t ld_dh, const float* dh2, int64_t ld_dh2, const float* dc,
+                            int64_t ld_dc, const float* acts, int64_t ld_acts, const float* c_prev, int64_t ld_cp,
+                            const float* c_new, int64_t ld_cn, float* dgates, int64_t ld_dg, float* dc_prev,
+                            int64_t ld_dcp, float* dh_pass, int64_t ld_dhp, const int32_t* active, int pos,
+                            int B, int H, void* stream);
+
+/* ------------------------------------------------------------------------------------------- encoder pieces (a9)
+ * BertEmbeddings (vilmodel.py:161-176): out[b,l,:] = LN(word[ids[b,l]] + pos[l] + type[0]) (* mask*scale).          */
+int dasa_embed_layernorm(const int64_t* ids, int64_t ld_ids, int B, int L, int Hd, const float* word, const float* pos,
+                         const float* type0, const float* gamma, const float* beta, float eps,
+                         const uint8_t* drop_mask, float drop_scale, float* out, void* stream);
+/* BertSelfOutput / BertOutput / VisionEncoder tail (vilmodel.py:246-250, 305-309, 1089-1094):
+ *   z = x (* mask*scale) (+ resid);  out = LN(z) * gamma + beta (* post_mask*post_scale); rows R, width Hd <= 1024.
+ *   stats_out (optional, [R,2]) receives (mean, rstd) and z_out (optional, [R,Hd] contiguous) the LN input, both
+ *   only needed by the backward pass (finetune config).                                                             */
+int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, const uint8_t* drop_mask, float drop_scale,
+                                    const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps,
+                                    const uint8_t* post_mask, float post_scale, float* out, int64_t ldo,
+                                    float* stats_out, float* z_out, int R, int Hd, void* stream);
+/* backward of the above (finetune config): given dout -> dresid (gradient w.r.t. z, i.e. w.r.t. the residual input) and
+ * dx (gradient w.r.t. x, = dresid * mask*scale); ACCUMULATES dgamma/dbeta (atomics).                                */
+int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* z, const float* gamma, const float* stats,
+                       const uint8_t* drop_mask, float drop_scale, const uint8_t* post_mask, float post_scale,
+                       float* dx, int64_t lddx, float* dresid, int64_t lddr, float* dgamma, float* dbeta,
+                       int R, int Hd, void* stream);
+/* Multi-head attention for short sequences (vilmodel.py:203-236, 479-506): one CTA per (batch, head).
+ *   q [B,Lq,*], k/v [B,Lk,*] with row strides ldq/ldk/ldv and sample strides sq/sk/sv (so fused QKV buffers are
+ *   addressed in place); scores = q k^T / sqrt(dh) + (key_pad[b,j] ? -10000 : 0); softmax; optional keep mask on the
+ *   probabilities [B,heads,Lq,Lk]; out[b,i,head*dh:(head+1)*dh] = P v. probs_out optional (for backward).          */
+int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
+                 int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
+                 float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out,
+                 int B, int heads, int Lq, int Lk, int dh, void* stream);
+int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
+                 int64_t ldv, int64_t sv, const float* probs, const uint8_t* drop_mask, float drop_scale,
+                 const float* dout, int64_t ldo, int64_t so, float* dq, int64_t lddq, int64_t sdq, float* dk,
+                 int64_t lddk, int64_t sdk, float* dv, int64_t lddv, int64_t sdv,
+                 int B, int heads, int Lq, int Lk, int dh, void* stream);
+/* token reversal (r2rmodel.py:2326-2330): out[b,i,:] = x[b, len_b-1-i, :] for i < len_b else 0. Self-inverse, so
+ * the same call maps gradients back.                                                                                */
+int dasa_reverse_tokens(const float* x, float* out, const int32_t* lengths, int B, int L, int Hd, void* stream);
+
+/* ----------------------------------------------------------------------------------------- elementwise helpers */
+/* y = x * mask * scale (mask may be NULL -> copy); strided rows                                                     */
+int dasa_dropout_apply(const float* x, int64_t ldx, const uint8_t* mask, float scale, float* y, int64_t ldy,
+                       int R, int C, void* stream);
+/* dx = dy * (1 - y*y) (tanh), dx = dy * (y > 0) (relu), optional keep mask folded in front (dy*mask*scale)        */
+int dasa_act_backward(int act /*0 tanh, 1 relu*/, const float* dy, int64_t lddy, const float* y, int64_t ldy,
+                      const uint8_t* mask, float scale, float* dx, int64_t lddx, int R, int C, void* stream);
+/* y (+)= a*x   elementwise over [R,C] strided                                                                      */
+int dasa_axpy2d(float a, const float* x, int64_t ldx, float* y, int64_t ldy, int accumulate, int R, int C, void* stream);
+/* keep-mask generator (counter-based hash RNG): mask[i] = u(seed, offset+i) >= p                                   */
+int dasa_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* --------------------------------------------------------------------------------------- loss / action (a10, a13)
+ * nn.CrossEntropyLoss(ignore_index, sum) over masked logits + argmax (agent_dg.py:850, 870-873):
+ *   loss_acc[0] += sum_b CE(logit[b,:], target[b]) ; dlogit = (softmax - onehot) * grad_scale for valid targets, 0
+ *   for ignored rows; action[b] = argmax (first maximal index, like torch.max).                                    */
+int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* target, int ignore_index, int B, int Nc,
+                   float grad_scale, float* loss_acc, float* dlogit, int64_t* action, float* logprob_action,
+                   float* entropy, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- optimizer (a12)
+ * torch.optim.RMSprop step (alpha=0.99, eps=1e-8, no momentum, not centered; agent_dg.py:214-241) fused over one
+ * flat parameter group, with the clip coefficient of clip_grad_norm (agent_dg.py:1392-1393) folded in:
+ *   g = grad * clip_coef[0] (clip_coef on device, may be NULL); sq = alpha*sq + (1-alpha) g^2; p -= lr * g/(sqrt(sq)+eps) */
+int dasa_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha, float eps,
+                      float weight_decay, const float* clip_coef, void* stream);
+/* sum of squares of a flat buffer, accumulated into out[0] (for the global grad norm)                              */
+int dasa_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* clip_coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))                                                         */
+int dasa_clip_coef(const float* sumsq, float max_norm, float* clip_coef, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASA_B200_H */

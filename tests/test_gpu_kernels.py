@@ -1,0 +1,276 @@
+"""GPU tier (B200): every C-ABI kernel against the CPU oracle (oracle/restated.py) or a float64 torch restatement on
+identical seeded inputs. Bars: fp32 paths 1e-4 relative (north_star); index outputs bit-exact."""
+import math
+
+import pytest
+import torch
+
+from dasa_b200 import synth
+from dasa_b200.config import FULL, SMALL
+from oracle import restated as R
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from dasa_b200 import functions as Fn
+    from dasa_b200 import modules as M
+    from dasa_b200 import ops
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def assert_close(a, b, tol=1e-4, what=""):
+    e = rel_err(a, b)
+    assert e <= tol, "%s: relative error %.3e > %.1e" % (what, e, tol)
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(20, 4096, 3264), (20, 2176, 1024), (1, 5, 1024), (720, 768, 2176), (1600, 3072, 768),
+                                   (37, 53, 29), (128, 128, 8), (257, 130, 1000), (1000, 2048, 2048)])
+@pytest.mark.parametrize("layout", [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_gemm_fp32(M, N, K, layout):
+    ak, bk = layout
+    if (M * N * K > 3e9 / 4) and layout != (1, 1):
+        pytest.skip("large shapes only in the Linear layout")
+    gen = g(M + N + K)
+    A = torch.randn((M, K) if ak else (K, M), generator=gen)
+    Bm = torch.randn((N, K) if bk else (K, N), generator=gen)
+    C0 = torch.randn(M, N, generator=gen)
+    bias = torch.randn(N, generator=gen)
+    ref = (A if ak else A.t()).double() @ (Bm.t() if bk else Bm).double()
+    Ad, Bd = A.to(DEV), Bm.to(DEV)
+    C = C0.to(DEV).clone()
+    ops.gemm(Ad, Ad.stride(0), ak, Bd, Bd.stride(0), bk, C, N, M, N, K, alpha=0.5, beta=2.0, epilogue=ops.EPI_BIAS,
+             bias=bias.to(DEV), precision=ops.PREC_FP32)
+    assert_close(C, 0.5 * ref + 2.0 * C0.double() + bias.double(), 2e-5, "gemm")
+
+
+@pytest.mark.parametrize("epi", ["tanh", "gelu", "relu", "bias_tanh"])
+def test_gemm_epilogues(epi):
+    gen = g(5)
+    M, N, K = 70, 200, 300
+    A, W, b = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) / math.sqrt(K), torch.randn(N, generator=gen)
+    z = A.double() @ W.double().t()
+    code, ref = {"tanh": (ops.EPI_TANH, torch.tanh(z)), "gelu": (ops.EPI_BIAS_GELU, R.gelu_erf(z + b.double())),
+                 "relu": (ops.EPI_BIAS_RELU, torch.relu(z + b.double())),
+                 "bias_tanh": (ops.EPI_BIAS_TANH, torch.tanh(z + b.double()))}[epi]
+    y = ops.linear_fwd(A.to(DEV), W.to(DEV), None if epi == "tanh" else b.to(DEV), code, precision=ops.PREC_FP32)
+    assert_close(y, ref, 2e-5, epi)
+
+
+def test_linear_backward_helpers():
+    gen = g(6)
+    M, N, K = 45, 96, 130
+    x, w, dy = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen), torch.randn(M, N, generator=gen)
+    dx = ops.linear_bwd_input(dy.to(DEV), w.to(DEV), precision=ops.PREC_FP32)
+    assert_close(dx, dy.double() @ w.double(), 2e-5, "dx")
+    dw0 = torch.randn(N, K, generator=gen)
+    dw = dw0.to(DEV).clone()
+    ops.linear_bwd_weight(dy.to(DEV), x.to(DEV), dw, True, precision=ops.PREC_FP32)
+    assert_close(dw, dw0.double() + dy.double().t() @ x.double(), 2e-5, "dw")
+    out = torch.zeros(N, device=DEV)
+    ops.colsum(dy.to(DEV), out, False)
+    assert_close(out, dy.double().sum(0), 2e-5, "colsum")
+
+
+# ------------------------------------------------------------------------------------------------ AdaIN family
+@pytest.mark.parametrize("cfg,B", [(SMALL, 3), (FULL, 2)])
+def test_adain_gate_fused_and_epilogue(cfg, B):
+    st = synth.adain_state(cfg, 0)
+    ep = synth.Episodes(B, 1, cfg, seed=2)
+    C = cfg.rgb_size
+    f, d = ep.f_t[0], ep.d_t[0]
+    want = R.adain_channel_gate(st, f[..., :C], d[..., :C])
+    mod = M.DGAdaChannel(C).to(DEV)
+    mod.load_state_dict(st)
+    fd, dd = f.to(DEV), d.to(DEV)
+    got = mod(fd[..., :C], dd[..., :C])                        # strided slices, read in place
+    assert_close(got, want, 1e-4, "DGAdaChannel")
+    full = mod.gate_features(fd, dd)
+    assert_close(full[..., :C], want, 1e-4, "gate_features rgb")
+    assert torch.equal(full[..., C:].cpu(), f[..., C:])          # angle part carried over bit-exactly
+    # epilogue-only form given the pre-activation
+    gpre = torch.nn.functional.linear(d[..., :C], st["a_fc.weight"], st["a_fc.bias"]).to(DEV)
+    out = torch.empty_like(gpre)
+    ops.gate_modulate(gpre, fd[..., :C], out)
+    assert_close(out, want, 1e-5, "gate_modulate")
+    # with an injected drop_env mask
+    keep = torch.rand(B, cfg.views, C, generator=g(3)) >= 0.4
+    full2 = mod.gate_features(fd, dd, keep.to(torch.uint8).to(DEV), 1 / 0.6)
+    assert_close(full2[..., :C], want * keep / 0.6, 1e-4, "gate + mask")
+
+
+@pytest.mark.parametrize("cfg,B", [(SMALL, 4), (FULL, 2)])
+def test_adain_stat_mean_default(cfg, B):
+    ep = synth.Episodes(B, 1, cfg, seed=4, stress=True)
+    C = cfg.rgb_size
+    f, d = ep.f_t[0][..., :C], ep.d_t[0][..., :C]
+    fd, dd = ep.f_t[0].to(DEV)[..., :C], ep.d_t[0].to(DEV)[..., :C]
+    assert_close(ops.view_stats(dd), R.view_stats(d), 1e-5, "view_stats")
+    for kind, cls, fn in (("stat", M.DGAdaStatChannel, R.adain_stat_channel), ("mean", M.DGAdaMeanChannel, R.adain_mean_channel)):
+        st = synth.adain_state(cfg, 0, kind)
+        mod = cls(C).to(DEV)
+        mod.load_state_dict(st)
+        assert_close(mod(fd, dd), fn(st, f, d), 1e-4, kind)
+    assert_close(M.adaptive_instance_normalization(fd, dd), R.adain_default(f, d), 1e-4, "adain default")
+
+
+# ------------------------------------------------------------------------------------------- decoder attention
+@pytest.mark.parametrize("cfg,B", [(SMALL, 5), (FULL, 3), (FULL, 40)])
+def test_shift_attention_fwd_bwd(cfg, B):
+    st = {k: v.clone().requires_grad_(True) for k, v in synth.decoder_state(cfg, 0).items()}
+    ep = synth.Episodes(B, 1, cfg, seed=8)
+    gen = g(9)
+    h = torch.tanh(torch.randn(B, cfg.hidden, generator=gen)).requires_grad_(True)
+    ctxt = ep.f_t[0].clone().requires_grad_(True)
+    wc, p = R.shift_soft_dot_attention(st, "feat_att_layer.", h, ctxt, cfg.headings)
+    dwc = torch.randn(wc.shape, generator=gen)
+    wc.backward(dwc)
+    mod = M.ShiftSoftDotAttention(cfg.hidden, cfg.feat, cfg.shift_kernel).to(DEV)
+    mod.load_state_dict({k.split(".", 1)[1]: v.detach() for k, v in st.items() if k.startswith("feat_att_layer.")})
+    hd = h.detach().to(DEV).requires_grad_(True)
+    cd = ctxt.detach().to(DEV).requires_grad_(True)
+    wc2, p2 = mod(hd, cd, output_tilde=False)
+    assert_close(p2, p, 1e-4, "view softmax")
+    assert_close(wc2, wc, 1e-4, "weighted context")
+    wc2.backward(dwc.to(DEV))
+    assert_close(hd.grad, h.grad, 2e-4, "dh")
+    assert_close(cd.grad, ctxt.grad, 2e-4, "dctx")
+    assert_close(mod.linear_in.weight.grad, st["feat_att_layer.linear_in.weight"].grad, 2e-4, "dW_in")
+    assert_close(mod.linear_shift.weight.grad, st["feat_att_layer.linear_shift.weight"].grad, 2e-4, "dW_shift")
+    assert_close(mod.linear_shift.bias.grad, st["feat_att_layer.linear_shift.bias"].grad, 2e-4, "db_shift")
+
+
+@pytest.mark.parametrize("cfg,B", [(SMALL, 5), (FULL, 3), (FULL, 24)])
+def test_soft_dot_attention_fwd_bwd(cfg, B):
+    st = {k: v.clone().requires_grad_(True) for k, v in synth.decoder_state(cfg, 0).items()}
+    gen = g(10)
+    seq, mask, lens = synth.instructions(B, cfg, seed=3)
+    L = mask.shape[1]
+    h = torch.tanh(torch.randn(B, cfg.hidden, generator=gen)).requires_grad_(True)
+    ctxt = (torch.randn(B, L, cfg.ctx_dim, generator=gen) * 0.3 * (~mask).unsqueeze(-1)).requires_grad_(True)
+    ht, alpha = R.soft_dot_attention(st, "attention_layer.", h, ctxt, mask)
+    dht = torch.randn(ht.shape, generator=gen)
+    ht.backward(dht)
+    mod = M.SoftDotAttention(cfg.hidden, cfg.ctx_dim).to(DEV)
+    mod.load_state_dict({k.split(".", 1)[1]: v.detach() for k, v in st.items() if k.startswith("attention_layer.")})
+    hd = h.detach().to(DEV).requires_grad_(True)
+    cd = ctxt.detach().to(DEV).requires_grad_(True)
+    ht2, alpha2 = mod(hd, cd, mask.to(DEV))
+    assert_close(alpha2, alpha, 1e-4, "alpha")
+    assert float(alpha2[mask.to(DEV)].abs().max()) == 0.0
+    assert_close(ht2, ht, 1e-4, "h_tilde")
+    ht2.backward(dht.to(DEV))
+    assert_close(hd.grad, h.grad, 2e-4, "dh")
+    assert_close(cd.grad, ctxt.grad, 2e-4, "dctx")
+    assert_close(mod.linear_in.weight.grad, st["attention_layer.linear_in.weight"].grad, 2e-4, "dW_in")
+    assert_close(mod.linear_out.weight.grad, st["attention_layer.linear_out.weight"].grad, 2e-4, "dW_out")
+
+
+@pytest.mark.parametrize("cfg,B", [(SMALL, 5), (FULL, 6)])
+def test_candidate_logits_fwd_bwd(cfg, B):
+    st = {k: v.clone().requires_grad_(True) for k, v in synth.decoder_state(cfg, 0).items()}
+    ep = synth.Episodes(B, 1, cfg, seed=12)
+    gen = g(13)
+    h = torch.tanh(torch.randn(B, cfg.hidden, generator=gen)).requires_grad_(True)
+    cand = ep.cand_feat[0].clone().requires_grad_(True)
+    leng = ep.cand_leng[0]
+    lg = R.candidate_logits(st, "candidate_att_layer.", h, cand)
+    lg = lg.masked_fill(R.length2mask(leng, lg.shape[1]), -float("inf"))
+    dl = torch.randn(lg.shape, generator=gen) * torch.isfinite(lg)
+    torch.where(torch.isfinite(lg), lg, torch.zeros_like(lg)).backward(dl)
+    mod = M.SoftDotAttention(cfg.hidden, cfg.feat).to(DEV)
+    mod.load_state_dict({k.split(".", 1)[1]: v.detach() for k, v in st.items() if k.startswith("candidate_att_layer.")})
+    hd = h.detach().to(DEV).requires_grad_(True)
+    cd = cand.detach().to(DEV).requires_grad_(True)
+    _, lg2 = mod(hd, cd, output_prob=False, cand_leng=leng.to(DEV), rgb_channels=cfg.rgb_size)
+    fin = torch.isfinite(lg)
+    assert torch.equal(torch.isfinite(lg2).cpu(), fin)
+    assert_close(lg2.cpu()[fin], lg[fin], 1e-4, "logits")
+    lg2.backward(dl.to(DEV))
+    assert_close(hd.grad, h.grad, 2e-4, "dh")
+    assert_close(cd.grad[..., :cfg.rgb_size], cand.grad[..., :cfg.rgb_size], 2e-4, "dcand rgb")
+    assert_close(mod.linear_in.weight.grad, st["candidate_att_layer.linear_in.weight"].grad, 2e-4, "dW_in")
+
+
+# ------------------------------------------------------------------------------------------------------- LSTM
+@pytest.mark.parametrize("cfg,B", [(SMALL, 5), (FULL, 20)])
+def test_lstm_cell_fwd_bwd(cfg, B):
+    st = {k: v.clone().requires_grad_(True) for k, v in synth.decoder_state(cfg, 0).items() if k.startswith("lstm.")}
+    gen = g(14)
+    x = torch.randn(B, cfg.action_emb + cfg.feat, generator=gen).requires_grad_(True)
+    h = torch.tanh(torch.randn(B, cfg.hidden, generator=gen)).requires_grad_(True)
+    c = torch.randn(B, cfg.hidden, generator=gen).requires_grad_(True)
+    h1, c1 = R.lstm_cell(st["lstm.weight_ih"], st["lstm.weight_hh"], st["lstm.bias_ih"], st["lstm.bias_hh"], x, h, c)
+    dh1, dc1 = torch.randn(h1.shape, generator=gen), torch.randn(c1.shape, generator=gen)
+    (h1 * dh1).sum().add((c1 * dc1).sum()).backward()
+    P = {k: v.detach().to(DEV).requires_grad_(True) for k, v in st.items()}
+    xd, hd, cd = (t.detach().to(DEV).requires_grad_(True) for t in (x, h, c))
+    h2, c2 = Fn.LSTMCellFn.apply(xd, hd, cd, P["lstm.weight_ih"], P["lstm.weight_hh"], P["lstm.bias_ih"], P["lstm.bias_hh"])
+    assert_close(h2, h1, 1e-4, "h1")
+    assert_close(c2, c1, 1e-4, "c1")
+    torch.autograd.backward([h2, c2], [dh1.to(DEV), dc1.to(DEV)])
+    for a, b, n in ((xd, x, "dx"), (hd, h, "dh"), (cd, c, "dc")):
+        assert_close(a.grad, b.grad, 2e-4, n)
+    for k in st:
+        assert_close(P[k].grad, st[k].grad, 2e-4, k)
+
+
+def test_masked_ce_and_argmax():
+    gen = g(15)
+    B, Nc = 37, 11
+    lg = torch.randn(B, Nc, generator=gen) * 3
+    leng = torch.randint(2, Nc + 1, (B,), generator=gen)
+    lg = lg.masked_fill(R.length2mask(leng, Nc), -float("inf"))
+    lg[3, :2] = 1.25                                              # exact tie -> first index wins
+    tgt = torch.stack([torch.randint(0, int(n), (1,), generator=gen)[0] for n in leng])
+    tgt[::5] = -100
+    lgr = lg.clone().requires_grad_(True)
+    want = torch.nn.functional.cross_entropy(lgr, tgt, ignore_index=-100, reduction="sum")
+    want.backward()
+    lgd = lg.to(DEV).requires_grad_(True)
+    loss, act = Fn.MaskedCEFn.apply(lgd, tgt.to(DEV), -100)
+    assert_close(loss, want, 1e-5, "ce")
+    loss.backward()
+    assert_close(lgd.grad, lgr.grad, 1e-5, "dlogit")
+    assert torch.equal(act.cpu(), lg.argmax(1))
+    _, a2, lp, ent = ops.masked_ce(lg.to(DEV), None, -100, 0.0, None, want_grad=False, want_stats=True)
+    dist = torch.distributions.Categorical(logits=lg)
+    assert_close(ent, dist.entropy(), 1e-4, "entropy")
+    assert_close(lp, torch.log_softmax(lg, 1).gather(1, lg.argmax(1, keepdim=True)).squeeze(1), 1e-4, "logprob")
+
+
+def test_rmsprop_and_clip_match_torch():
+    gen = g(16)
+    p0, g0 = torch.randn(1000, 33, generator=gen), torch.randn(1000, 33, generator=gen) * 3
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.RMSprop([ref], lr=1e-4)
+    pd, sq = p0.to(DEV).clone(), torch.zeros_like(p0, device=DEV)
+    ssq, coef = torch.zeros(1, device=DEV), torch.ones(1, device=DEV)
+    for it in range(3):
+        ref.grad = g0.clone() * (it + 1)
+        torch.nn.utils.clip_grad_norm_([ref], 40.0)
+        opt.step()
+        gd = (g0 * (it + 1)).to(DEV)
+        ssq.zero_()
+        ops.sumsq(gd, ssq)
+        ops.clip_coef(ssq, 40.0, coef)
+        ops.rmsprop_step(pd, gd, sq, 1e-4, 0.99, 1e-8, 0.0, coef)
+    assert_close(pd, ref.detach(), 1e-5, "rmsprop")
+
+
+def test_dropout_mask_rate_and_determinism():
+    m1 = ops.dropout_mask((1 << 20,), 0.4, 7, 0)
+    m2 = ops.dropout_mask((1 << 20,), 0.4, 7, 0)
+    assert torch.equal(m1, m2)
+    assert abs(float(m1.float().mean()) - 0.6) < 5e-3
+    assert not torch.equal(m1, ops.dropout_mask((1 << 20,), 0.4, 8, 0))

@@ -1,0 +1,223 @@
+"""GPU tier (B200): the drop-in modules and the rollout against the CPU oracle and the committed golden fixtures
+(outputs of the real reference modules). Everything below calls the C-ABI kernels through dasa_b200.modules."""
+import os
+
+import pytest
+import torch
+
+from dasa_b200 import synth
+from dasa_b200.config import FULL, SMALL
+from oracle import restated as R
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from dasa_b200 import modules as M
+    from dasa_b200.rollout import DeviceEpisodes, NavPolicy
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def assert_close(a, b, tol=1e-4, what=""):
+    e = rel_err(a, b)
+    assert e <= tol, "%s: relative error %.3e > %.1e" % (what, e, tol)
+
+
+@pytest.mark.parametrize("cfg,B,seed", [(SMALL, 5, 3), (SMALL, 2, 4)])
+def test_encoder_matches_oracle(cfg, B, seed):
+    st = synth.policy_state(cfg, 0)
+    ep = synth.Episodes(B, 1, cfg, seed=seed)
+    with torch.no_grad():
+        ctx, h, c, vis = R.encoder_forward(st["encoder"], cfg, ep.seq, ep.seq_mask, ep.seq_lengths, ep.f_t[0])
+    pol = NavPolicy(cfg, st).eval()
+    dep = DeviceEpisodes(ep)
+    with torch.no_grad():
+        ctx2, h2, c2, _, vis2 = pol.encoder(dep.seq, dep.seq_mask, dep.seq_lengths, f_t_all=dep.f_t[0])
+    assert_close(vis2, vis, 1e-4, "vision stream")
+    assert_close(ctx2, ctx, 1e-4, "ctx")
+    assert_close(h2, h, 1e-4, "decoder_init")
+    assert_close(c2, c, 1e-4, "c_t")
+    assert float(ctx2[dep.seq_mask].abs().max()) == 0.0
+
+
+def test_small_golden_modules():
+    g = torch.load(os.path.join(GOLDEN, "small_eval.pt"))
+    cfg = SMALL
+    st = synth.policy_state(cfg, g["meta"]["seed"])
+    ep = synth.Episodes(cfg=cfg, **g["meta"]["episodes"])
+    dep = DeviceEpisodes(ep)
+    pol = NavPolicy(cfg, st).eval()
+    a_t, f_t, d_t, cand, cand_d, leng, tgt = dep.step(1)
+    with torch.no_grad():
+        ctx, eh, ec, _, vis = pol.encoder(dep.seq, dep.seq_mask, dep.seq_lengths, f_t_all=f_t)
+        assert_close(ctx, g["enc_ctx"], 1e-4, "enc ctx vs reference")
+        assert_close(eh, g["enc_h"], 1e-4, "enc h")
+        assert_close(ec, g["enc_c"], 1e-4, "enc c")
+        h = g["h_query"].to(DEV)
+        wc, p = pol.decoder.feat_att_layer(h, f_t, output_tilde=False)
+        assert_close(p, g["shift_attn"], 1e-4, "shift attn")
+        assert_close(wc, g["shift_wc"], 1e-4, "shift wc")
+        ht, alpha = pol.decoder.attention_layer(h, g["enc_ctx"].to(DEV), dep.seq_mask)
+        assert_close(ht, g["softdot_h"], 1e-4, "softdot h")
+        assert_close(alpha, g["softdot_alpha"], 1e-4, "softdot alpha")
+        h1, c1, lg, htl, _ = pol.decoder(a_t, f_t.clone(), cand.clone(), g["enc_h"].to(DEV), g["enc_h"].to(DEV),
+                                         g["enc_c"].to(DEV), g["enc_ctx"].to(DEV), dep.seq_mask)
+        assert_close(h1, g["dec_h1"], 1e-4, "dec h1")
+        assert_close(c1, g["dec_c1"], 1e-4, "dec c1")
+        assert_close(lg, g["dec_logit"], 1e-4, "dec logit")
+        assert_close(htl, g["dec_htilde"], 1e-4, "dec h_tilde")
+        assert_close(pol.critic(h1), g["critic"], 1e-4, "critic")
+        loss, logits, actions = pol.teacher_rollout(dep, 4)
+    lg = torch.stack(logits).cpu()
+    fin = torch.isfinite(g["rollout_eval_logits"])
+    assert torch.equal(torch.isfinite(lg), fin)
+    assert_close(lg[fin], g["rollout_eval_logits"][fin], 2e-4, "rollout logits")
+    assert_close(loss, g["rollout_eval_loss"], 1e-4, "rollout loss")
+    assert torch.equal(torch.stack(actions).cpu(), g["rollout_eval_logits"].argmax(-1))   # greedy actions bit-exact
+
+
+def test_full_geometry_golden_rollout():
+    g = torch.load(os.path.join(GOLDEN, "full_eval.pt"))
+    cfg = FULL
+    st = synth.policy_state(cfg, g["meta"]["seed"])
+    ep = synth.Episodes(cfg=cfg, **g["meta"]["episodes"])
+    dep = DeviceEpisodes(ep)
+    pol = NavPolicy(cfg, st).eval()
+    with torch.no_grad():
+        loss, logits, actions = pol.teacher_rollout(dep, 2)
+        ctx, eh, ec, _, vis = pol.encoder(dep.seq, dep.seq_mask, dep.seq_lengths, f_t_all=dep.f_t[0])
+    from oracle.make_golden import sample
+    lg = torch.stack(logits).cpu()
+    fin = torch.isfinite(g["logits"])
+    assert torch.equal(torch.isfinite(lg), fin)
+    assert_close(lg[fin], g["logits"][fin], 2e-4, "logits vs reference")
+    assert_close(loss, g["loss"], 1e-4, "loss")
+    assert_close(eh, g["enc_h"], 1e-4, "enc h")
+    assert_close(sample(ctx.cpu(), 4099), g["ctx_sample"], 1e-4, "ctx sample")
+    assert_close(sample(vis.cpu(), 4099), g["vis_sample"], 2e-4, "vis sample")
+    # greedy actions bit-exact wherever the top-2 margin exceeds the tolerance
+    ref = g["logits"]
+    top2 = ref.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 1e-3
+    assert torch.equal(torch.stack(actions).cpu()[safe], ref.argmax(-1)[safe])
+
+
+def _train_masks(cfg, B, T, L, nc, seed):
+    """Random keep masks for every dropout site of a T-step rollout, keyed like oracle/restated.py tags."""
+    gen = torch.Generator().manual_seed(seed)
+    Hb, hd, V, C = cfg.bert_hidden, cfg.bert_heads, cfg.views, cfg.rgb_size
+    keep = {}
+
+    def add(tag, shape, p):
+        keep[tag] = (torch.rand(*shape, generator=gen) >= p, p)
+    for t in range(T):
+        pre = "t%d." % t
+        add(pre + "enc.emb", (B, L, Hb), cfg.bert_dropout)
+        for i in range(cfg.la_layers):
+            add(pre + "enc.la%d.att.probs" % i, (B, hd, L, L), cfg.bert_dropout)
+            add(pre + "enc.la%d.att.out" % i, (B, L, Hb), cfg.bert_dropout)
+            add(pre + "enc.la%d.ffn" % i, (B, L, Hb), cfg.bert_dropout)
+        add(pre + "enc.visn", (B, V, Hb), cfg.bert_dropout)
+        for i in range(cfg.vl_layers):
+            v = pre + "enc.vl%d" % i
+            add(v + ".x_lv.probs", (B, hd, L, V), cfg.bert_dropout); add(v + ".x_lv.out", (B, L, Hb), cfg.bert_dropout)
+            add(v + ".x_vl.probs", (B, hd, V, L), cfg.bert_dropout); add(v + ".x_vl.out", (B, V, Hb), cfg.bert_dropout)
+            add(v + ".ls.probs", (B, hd, L, L), cfg.bert_dropout); add(v + ".ls.out", (B, L, Hb), cfg.bert_dropout)
+            add(v + ".vs.probs", (B, hd, V, V), cfg.bert_dropout); add(v + ".vs.out", (B, V, Hb), cfg.bert_dropout)
+            add(v + ".lo", (B, L, Hb), cfg.bert_dropout); add(v + ".vo", (B, V, Hb), cfg.bert_dropout)
+        add(pre + "enc.ctx", (B, L, cfg.ctx_dim), cfg.enc_dropout)
+        add(pre + "dec.act", (B, cfg.action_emb), cfg.dropout)
+        add(pre + "dec.feat", (B, V, C), cfg.featdropout)
+        add(pre + "dec.h_prev", (B, cfg.hidden), cfg.dropout)
+        add(pre + "dec.h1", (B, cfg.hidden), cfg.dropout)
+        add(pre + "dec.htilde", (B, cfg.hidden), cfg.dropout)
+        add(pre + "dec.cand", (B, nc, C), cfg.featdropout)
+    return keep
+
+
+@pytest.mark.parametrize("cfg,B,T", [(SMALL, 3, 3)])
+def test_train_rollout_loss_and_gradients(cfg, B, T):
+    """Train-mode teacher-forced rollout with injected dropout masks: loss, logits and every parameter gradient of the
+    train configuration (adaIn, decoder, bi-LSTM + init linears) against oracle autograd."""
+    st = synth.policy_state(cfg, 1)
+    ep = synth.Episodes(B, T, cfg, seed=31)
+    L, nc = ep.seq_mask.shape[1], ep.cand_feat.shape[2]
+    keep = _train_masks(cfg, B, T, L, nc, 77)
+    ost = {grp: {k: v.clone().requires_grad_(True) for k, v in d.items()} for grp, d in st.items()}
+    drops = R.MaskDrops({k: m.float() / (1 - p) for k, (m, p) in keep.items()})
+    loss, logits, _ = R.teacher_rollout(ost, cfg, ep, T, drops=drops)
+    loss.backward()
+
+    pol = NavPolicy(cfg, st).train()
+    dep = DeviceEpisodes(ep)
+    src = M.DropoutSource(injected={k: m for k, (m, p) in keep.items()})
+    with M.use_dropout_source(src):
+        loss2, logits2, _ = pol.teacher_rollout(dep, T)
+    assert_close(loss2, loss, 1e-4, "train loss")
+    lg, lg2 = torch.stack(logits).detach(), torch.stack(logits2).detach().cpu()
+    fin = torch.isfinite(lg)
+    assert_close(lg2[fin], lg[fin], 2e-4, "train logits")
+    loss2.backward()
+    checked = 0
+    for grp, mod in (("adaIn", pol.adaIn), ("decoder", pol.decoder), ("encoder", pol.encoder)):
+        for k, prm in mod.named_parameters():
+            want = ost[grp][k].grad
+            if want is None or float(want.abs().max()) == 0.0:
+                assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, "unexpected grad for %s.%s" % (grp, k)
+                continue
+            assert prm.grad is not None, "missing grad for %s.%s" % (grp, k)
+            assert_close(prm.grad, want, 1e-3, "grad %s.%s" % (grp, k))
+            checked += 1
+    assert checked >= 20
+
+
+def test_decoder_writes_back_dropped_features_in_train_mode():
+    """model.py:508,557: with already_dropfeat=False the decoder mutates the caller's feature / cand_feat in train mode
+    and leaves them bit-unchanged in eval mode."""
+    cfg = SMALL
+    st = synth.policy_state(cfg, 0)
+    ep = synth.Episodes(3, 1, cfg, seed=5)
+    dep = DeviceEpisodes(ep)
+    pol = NavPolicy(cfg, st)
+    a_t, f_t, d_t, cand, cand_d, leng, tgt = dep.step(0)
+    h = torch.zeros(3, cfg.hidden, device=DEV)
+    ctx = torch.randn(3, dep.seq_mask.shape[1], cfg.ctx_dim, device=DEV)
+    pol.eval()
+    f0, c0 = f_t.clone(), cand.clone()
+    with torch.no_grad():
+        pol.decoder(a_t, f0, c0, h, h, h, ctx, dep.seq_mask)
+    assert torch.equal(f0, f_t) and torch.equal(c0, cand)
+    pol.train()
+    with torch.no_grad():
+        pol.decoder(a_t, f0, c0, h, h, h, ctx, dep.seq_mask)
+    C = cfg.rgb_size
+    assert not torch.equal(f0[..., :C], f_t[..., :C])
+    assert torch.equal(f0[..., C:], f_t[..., C:])          # angle part never dropped
+    kept = f0[..., :C] != 0
+    assert_close(f0[..., :C][kept], (f_t[..., :C] / (1 - cfg.featdropout))[kept], 1e-6, "scaled survivors")
+
+
+def test_optimizer_step_matches_torch_rmsprop():
+    cfg = SMALL
+    st = synth.policy_state(cfg, 2)
+    ep = synth.Episodes(3, 2, cfg, seed=6)
+    dep = DeviceEpisodes(ep)
+    pol = NavPolicy(cfg, st).eval()
+    loss, _, _ = pol.teacher_rollout(dep, 2)
+    loss.backward()
+    import copy
+    dec_ref = copy.deepcopy(pol.decoder)
+    for p, q in zip(dec_ref.parameters(), pol.decoder.parameters()):
+        p.grad = None if q.grad is None else q.grad.clone()
+    opt = torch.optim.RMSprop(dec_ref.parameters(), lr=1e-4)
+    torch.nn.utils.clip_grad_norm_(dec_ref.parameters(), 40.0)
+    opt.step()
+    pol.optim_step(1e-4)
+    for (k, p), q in zip(dec_ref.named_parameters(), pol.decoder.parameters()):
+        assert_close(q, p, 1e-5, "param %s after step" % k)
