@@ -1,7 +1,296 @@
-// tcgen05 (TF32) GEMM — placeholder until the tensor-core kernel lands; reports "unsupported" so dasa_gemm uses FFMA.
+// tcgen05 (5th-gen tensor core) TF32 GEMM for the dense projections: C[M,N] = epi(alpha * A[M,K] * B[N,K]^T + beta*C).
+// fp32 operands stay fp32 in HBM; TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero fill) stages 128x32 / BNx32 tiles
+// in shared memory as TFLOAT32, one elected thread issues tcgen05.mma.kind::tf32 (UMMA 128 x BN x 8) with the fp32
+// accumulator living in TMEM, tcgen05.commit hands smem stages back to the TMA producer through mbarriers, and the
+// four warps read the accumulator back with tcgen05.ld for the fused epilogue (bias / tanh / GELU / ReLU / sigmoid-gate).
+// K-major ("Linear") operand layout only; the other layouts of dasa_gemm stay on the FFMA kernel.
+#include <cuda.h>
 #include "common.cuh"
 #include "gemm_common.cuh"
-bool dasa_gemm_tc_supported(int, int, int, int, int, const float*, int64_t, const float*, int64_t, const float*, int64_t) { return false; }
-size_t dasa_gemm_tc_workspace(int, int, int) { return 0; }
-int dasa_gemm_tc(int, int, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*, int64_t, int,
-                 const EpiParams&, void*, size_t, cudaStream_t) { return DASA_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;            // 32 fp32 = 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 8;         // tf32: 32 bytes per MMA along K
+constexpr int TC_THREADS = 128;
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+  int M, N, K;
+  float alpha, beta;
+  float* C; int64_t ldc;
+  int epilogue; EpiParams ep;
+  float* partial;        // split-K partial sums [S, M, N] or nullptr
+  int k_per_split;       // multiple of TC_BK
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  // 1024-byte alignment is required by the 128B swizzle; the dynamic smem base is aligned by the launch
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = min(p.K, kbeg + p.k_per_split);
+  const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);       // BN fp32 accumulator columns x 128 lanes
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+      unsigned char* a_dst = tiles + s * STAGE_BYTES;
+      tma_load_2d(a_dst, &tmA, kbeg + kb * TC_BK, m0, &full_bar[s]);
+      tma_load_2d(a_dst + A_BYTES, &tmB, kbeg + kb * TC_BK, n0, &full_bar[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (single thread)
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      unsigned char* a_src = tiles + s * STAGE_BYTES;
+      const uint64_t da = make_smem_desc_sw128(a_src);
+      const uint64_t db = make_smem_desc_sw128(a_src + A_BYTES);
+#pragma unroll
+      for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+        // advance the start address by k*32 bytes inside the 128-byte swizzled row (address field is in 16-byte units)
+        umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);      // smem stage free once these MMAs have consumed it
+    }
+    umma_commit(tmem_full);            // accumulator complete
+  }
+
+  // -------------------------------------------------------------------- epilogue: all four warps
+  __syncwarp();
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+  const int m = m0 + warp * 32 + lane;               // TMEM lane == tile row
+  const bool row_ok = m < p.M;
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    if (!row_ok) continue;
+    const int nb = n0 + c0;
+    if (p.partial != nullptr) {
+      float* dst = p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N + nb;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) dst[j] = __uint_as_float(r[j]);
+      continue;
+    }
+    float* crow = p.C + (int64_t)m * p.ldc + nb;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = p.alpha * __uint_as_float(r[j]);
+      if (nb + j < p.N) {
+        if (p.beta != 0.f) x += p.beta * crow[j];
+        x = apply_epilogue(x, m, nb + j, p.N, p.epilogue, p.ep);
+      }
+      v[j] = x;
+    }
+    if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) crow[j] = v[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N, float alpha, float beta,
+                                        float* __restrict__ C, int64_t ldc, int epilogue, EpiParams ep) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * N) return;
+  const int m = idx / N, n = idx % N;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += partial[(int64_t)z * M * N + idx];
+  float v = alpha * s;
+  if (beta != 0.f) v += beta * C[(int64_t)m * ldc + n];
+  C[(int64_t)m * ldc + n] = apply_epilogue(v, m, n, N, epilogue, ep);
+}
+
+struct TcPlan { int bn; int splits; int k_per_split; };
+
+TcPlan plan_tc(int M, int N, int K) {
+  TcPlan pl;
+  const int64_t tm = dasa_cdiv(M, TC_BM);
+  pl.bn = (tm * dasa_cdiv(N, 128) >= DASA_NUM_SMS || N <= 64) ? 128 : 64;
+  if (N <= 64) pl.bn = 64;
+  const int64_t tiles = tm * dasa_cdiv(N, pl.bn);
+  int s = 1;
+  const int nkb = (int)dasa_cdiv(K, TC_BK);
+  if (tiles < DASA_NUM_SMS && nkb >= 8) {
+    s = (int)dasa_cdiv(DASA_NUM_SMS, tiles);
+    s = s > nkb / 4 ? nkb / 4 : s;
+    s = s < 1 ? 1 : (s > 32 ? 32 : s);
+  }
+  int kps = (int)dasa_cdiv(nkb, s) * TC_BK;
+  pl.splits = (int)dasa_cdiv(K, kps);
+  pl.k_per_split = kps;
+  return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, K] with row stride ld (elements), K contiguous; box = [box_rows x 32]
+bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int splits, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { dasa_set_error("gemm_tf32 attr", e); return DASA_ERR_CUDA; }
+  dim3 grid((unsigned)dasa_cdiv(p.N, BN), (unsigned)dasa_cdiv(p.M, TC_BM), (unsigned)splits);
+  gemm_tf32_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tb, p);
+  return dasa_check_launch("gemm_tf32_kernel");
+}
+
+}  // namespace
+
+bool dasa_gemm_tc_supported(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                            int64_t ldb, const float* C, int64_t ldc) {
+  (void)C; (void)ldc;
+  if (!a_kmajor || !b_kmajor) return false;                 // Linear layout only (for now)
+  if (M <= 0 || N <= 0 || K < TC_BK) return false;
+  if (!dasa_aligned16(A) || !dasa_aligned16(B) || (lda % 4) != 0 || (ldb % 4) != 0) return false;   // TMA stride/base rules
+  return get_encode_fn() != nullptr;
+}
+
+size_t dasa_gemm_tc_workspace(int M, int N, int K) {
+  TcPlan pl = plan_tc(M, N, K);
+  return pl.splits > 1 ? (size_t)pl.splits * M * N * sizeof(float) : 0;
+}
+
+int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
+                 int64_t ldb, float beta, float* C, int64_t ldc, int epilogue, const EpiParams& ep, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st) {
+  (void)a_kmajor; (void)b_kmajor;
+  TcPlan pl = plan_tc(M, N, K);
+  float* partial = nullptr;
+  if (pl.splits > 1) {
+    const size_t need = (size_t)pl.splits * M * N * sizeof(float);
+    if (workspace == nullptr || workspace_bytes < need) { pl.splits = 1; pl.k_per_split = (int)dasa_cdiv(K, TC_BK) * TC_BK; }
+    else partial = static_cast<float*>(workspace);
+  }
+  CUtensorMap ta, tb;
+  if (!make_map(&ta, A, M, K, lda, TC_BM) || !make_map(&tb, B, N, K, ldb, pl.bn)) return DASA_ERR_UNSUPPORTED;
+  TcParams p{M, N, K, alpha, beta, C, ldc, epilogue, ep, partial, pl.k_per_split};
+  int rc = (pl.bn == 128) ? launch_tc<128, 6>(ta, tb, p, pl.splits, st) : launch_tc<64, 8>(ta, tb, p, pl.splits, st);
+  if (rc != DASA_OK) return rc;
+  if (partial != nullptr) {
+    const int64_t total = (int64_t)M * N;
+    tc_splitk_reduce_kernel<<<(unsigned)dasa_cdiv(total, 256), 256, 0, st>>>(partial, pl.splits, M, N, alpha, beta, C, ldc,
+                                                                              epilogue, ep);
+    rc = dasa_check_launch("tc_splitk_reduce_kernel");
+  }
+  return rc;
+}

@@ -26,8 +26,11 @@ struct RowAttnSmem {
   uint64_t* bar;
 };
 
+__host__ __device__ inline int ra_pad4(int rows) { return (rows + 3) & ~3; }
+
 __host__ __device__ inline size_t ra_smem_bytes(int rows, int chunk, int cs) {
-  return sizeof(float) * ((size_t)rows * chunk + 2 * (size_t)chunk + (size_t)cs * rows + 3 * (size_t)rows + 1024) + 16 + 16;
+  const size_t rp = (size_t)ra_pad4(rows);   // keep every sub-array 16-byte aligned (float4 access to red / tv / dv)
+  return sizeof(float) * ((size_t)rows * chunk + 2 * (size_t)chunk + (size_t)cs * rp + 3 * rp + 1024) + 16 + 16;
 }
 
 __device__ inline RowAttnSmem ra_carve(unsigned char* raw, int rows, int chunk, int cs) {
@@ -36,10 +39,11 @@ __device__ inline RowAttnSmem ra_carve(unsigned char* raw, int rows, int chunk, 
   s.tv = s.tile + (size_t)rows * chunk;
   s.dv = s.tv + chunk;
   s.zpart = s.dv + chunk;
-  s.w = s.zpart + (size_t)cs * rows;
-  s.p = s.w + rows;
-  s.aux = s.p + rows;
-  s.red = s.aux + rows;
+  const int rp = ra_pad4(rows);
+  s.w = s.zpart + (size_t)cs * rp;
+  s.p = s.w + rp;
+  s.aux = s.p + rp;
+  s.red = s.aux + rp;
   uintptr_t b = reinterpret_cast<uintptr_t>(s.red + 1024);
   b = (b + 15) & ~uintptr_t(15);
   s.bar = reinterpret_cast<uint64_t*>(b);

@@ -57,7 +57,8 @@ def _rows(t):
     uniform = all(t.shape[i] == 1 or t.stride(i) == t.stride(i + 1) * t.shape[i + 1] for i in range(t.dim() - 2))
     if not uniform or t.shape[-2] == 1:
         t = t.contiguous()
-    return t, t.numel() // t.shape[-1], t.shape[-1], t.stride(-2)
+    R, C, ld = t.numel() // t.shape[-1], t.shape[-1], t.stride(-2)
+    return t.as_strided((R, C), (ld, 1)), R, C, ld          # genuine 2-D view over the same storage
 
 
 def _rows_out(t):

@@ -43,7 +43,8 @@ def test_encoder_matches_oracle(cfg, B, seed):
     assert_close(ctx2, ctx, 1e-4, "ctx")
     assert_close(h2, h, 1e-4, "decoder_init")
     assert_close(c2, c, 1e-4, "c_t")
-    assert float(ctx2[dep.seq_mask].abs().max()) == 0.0
+    if bool(dep.seq_mask.any()):
+        assert float(ctx2[dep.seq_mask].abs().max()) == 0.0
 
 
 def test_small_golden_modules():
