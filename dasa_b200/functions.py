@@ -229,10 +229,25 @@ class LSTMCellFn(torch.autograd.Function):
         return dx, dh, (dc0 if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
+_wt_cache = {}
+
+
+def _transposed(w):
+    """W_hh^T for the backward recurrence, cached until the parameter changes (optimizer step bumps _version)."""
+    key = w.data_ptr()
+    hit = _wt_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    wt = w.detach().t().contiguous()
+    _wt_cache[key] = (w._version, wt)
+    return wt
+
+
 class BiLSTMFn(torch.autograd.Function):
     """Packed one-layer bidirectional nn.LSTM over the reversed token sequence (r2rmodel.py:2339-2357).
     x [B, L, In]; lengths int32 [B]. Returns ctx [B, L, 2H] (zero rows past each length), h_fin [2,B,H], c_fin [2,B,H]
-    (index 0 = forward direction, 1 = reverse direction)."""
+    (index 0 = forward direction, 1 = reverse direction). Small batches run the fused per-step kernels (one C call for
+    the whole sequence); larger ones the GEMM + pointwise path."""
 
     @staticmethod
     def forward(ctx, x, lengths, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
@@ -241,20 +256,33 @@ class BiLSTMFn(torch.autograd.Function):
         dev = x.device
         x = x.contiguous()
         out = torch.empty(B, L, 2 * H, device=dev, dtype=torch.float32)
-        hs = torch.zeros(2, L + 1, B, H, device=dev, dtype=torch.float32)     # state BEFORE step s at index s
-        cs = torch.zeros(2, L + 1, B, H, device=dev, dtype=torch.float32)
+        hs = torch.empty(2, L + 1, B, H, device=dev, dtype=torch.float32)     # state BEFORE step s at index s
+        cs = torch.empty(2, L + 1, B, H, device=dev, dtype=torch.float32)
+        hs[:, 0].zero_()
+        cs[:, 0].zero_()
         acts = torch.empty(2, L, B, 4 * H, device=dev, dtype=torch.float32)
-        gh = torch.empty(B, 4 * H, device=dev, dtype=torch.float32)
         params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
-        for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
-            xp = ops.linear_fwd(x, w_ih)                        # [B, L, 4H] all time steps at once
-            order = range(L) if d == 0 else range(L - 1, -1, -1)
-            for s, l in enumerate(order):
-                ops.linear_fwd(hs[d, s], w_hh, out=gh)
-                ops.lstm_pointwise_fwd(xp[:, l], gh, b_ih, b_hh, cs[d, s], hs[d, s], hs[d, s + 1], cs[d, s + 1],
-                                       out[:, l, d * H:(d + 1) * H], acts[d, s], lengths, l)
+        fused = B <= ops.lib.load().dasa_bilstm_max_batch() and H % 64 == 0
+        if fused:
+            xp = [ops.linear_fwd(x, w_ih) for (w_ih, _, _, _) in params]       # [B, L, 4H] all time steps at once
+            P2 = ops.lib.P * 2
+            a = ops.lib.BiLstmFwd(P2(xp[0].data_ptr(), xp[1].data_ptr()), P2(w_hh_f.data_ptr(), w_hh_r.data_ptr()),
+                                  P2(b_ih_f.data_ptr(), b_ih_r.data_ptr()), P2(b_hh_f.data_ptr(), b_hh_r.data_ptr()),
+                                  P2(hs[0].data_ptr(), hs[1].data_ptr()), P2(cs[0].data_ptr(), cs[1].data_ptr()),
+                                  P2(acts[0].data_ptr(), acts[1].data_ptr()), out.data_ptr(), lengths.data_ptr(), B, L, H)
+            ops.call("dasa_bilstm_seq_fwd", ops.ctypes.byref(a), ops._stream())
+        else:
+            gh = torch.empty(B, 4 * H, device=dev, dtype=torch.float32)
+            for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
+                xp = ops.linear_fwd(x, w_ih)
+                order = range(L) if d == 0 else range(L - 1, -1, -1)
+                for s, l in enumerate(order):
+                    ops.linear_fwd(hs[d, s], w_hh, out=gh)
+                    ops.lstm_pointwise_fwd(xp[:, l], gh, b_ih, b_hh, cs[d, s], hs[d, s], hs[d, s + 1], cs[d, s + 1],
+                                           out[:, l, d * H:(d + 1) * H], acts[d, s], lengths, l)
         h_fin = torch.stack((hs[0, L], hs[1, L]))
         c_fin = torch.stack((cs[0, L], cs[1, L]))
+        ctx.fused = fused
         ctx.save_for_backward(x, lengths, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hs, cs, acts)
         return out, h_fin, c_fin
 
@@ -268,26 +296,41 @@ class BiLSTMFn(torch.autograd.Function):
         params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
         need_dx = ctx.needs_input_grad[0]
         dx = torch.zeros(B, L, In, device=dev, dtype=torch.float32) if need_dx else None
+        dgates_all = torch.empty(2, L, B, 4 * H, device=dev, dtype=torch.float32)     # indexed by step s
+        if ctx.fused:
+            dhf = dh_fin.contiguous() if dh_fin is not None else None
+            dcf = dc_fin.contiguous() if dc_fin is not None else None
+            wt = (_transposed(w_hh_f), _transposed(w_hh_r))
+            work = torch.empty(2, 2, 2, B, H, device=dev, dtype=torch.float32)
+            P2 = ops.lib.P * 2
+
+            def pp(t, d):
+                return None if t is None else t[d].data_ptr()
+            a = ops.lib.BiLstmBwd(P2(wt[0].data_ptr(), wt[1].data_ptr()), P2(acts[0].data_ptr(), acts[1].data_ptr()),
+                                  P2(cs[0].data_ptr(), cs[1].data_ptr()), dout.data_ptr(), P2(pp(dhf, 0), pp(dhf, 1)),
+                                  P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates_all[0].data_ptr(), dgates_all[1].data_ptr()),
+                                  P2(work[0, 0].data_ptr(), work[0, 1].data_ptr()),
+                                  P2(work[1, 0].data_ptr(), work[1, 1].data_ptr()), lengths.data_ptr(), B, L, H)
+            ops.call("dasa_bilstm_seq_bwd", ops.ctypes.byref(a), ops._stream())
         for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
-            dgates = torch.empty(L, B, 4 * H, device=dev, dtype=torch.float32)     # indexed by step s
-            dh = dh_fin[d].contiguous() if dh_fin is not None else torch.zeros(B, H, device=dev)
-            dc = dc_fin[d].contiguous() if dc_fin is not None else torch.zeros(B, H, device=dev)
-            dh_rec = torch.empty(B, H, device=dev, dtype=torch.float32)
-            dh_pass = torch.empty(B, H, device=dev, dtype=torch.float32)
-            dc_prev = torch.empty(B, H, device=dev, dtype=torch.float32)
+            dgates = dgates_all[d]
             order = list(range(L)) if d == 0 else list(range(L - 1, -1, -1))
-            for s in range(L - 1, -1, -1):
-                l = order[s]
-                # dh (carried) + dout[:, l] -> dgates ; inactive rows pass dh/dc through untouched
-                ops.lstm_pointwise_bwd(dh, dout[:, l, d * H:(d + 1) * H], dc, acts[d, s], cs[d, s], cs[d, s + 1], dgates[s],
-                                       dc_prev, dh_pass, lengths, l)
-                ops.linear_bwd_input(dgates[s], w_hh, out=dh_rec)
-                # next carried dh = recurrent gradient (active rows) + passthrough (inactive rows; dout rows there are 0)
-                ops.axpy2d(1.0, dh_pass, dh_rec, accumulate=True)
-                dh, dh_rec = dh_rec, dh
-                dc, dc_prev = dc_prev, dc
-            # weight gradients: one GEMM each over all L*B rows
-            # x rows for step s are x[:, order[s]] -> gather once
+            if not ctx.fused:
+                dh = dh_fin[d].contiguous() if dh_fin is not None else torch.zeros(B, H, device=dev)
+                dc = dc_fin[d].contiguous() if dc_fin is not None else torch.zeros(B, H, device=dev)
+                dh_rec = torch.empty(B, H, device=dev, dtype=torch.float32)
+                dh_pass = torch.empty(B, H, device=dev, dtype=torch.float32)
+                dc_prev = torch.empty(B, H, device=dev, dtype=torch.float32)
+                for s in range(L - 1, -1, -1):
+                    l = order[s]
+                    # dh (carried) + dout[:, l] -> dgates ; inactive rows pass dh/dc through untouched
+                    ops.lstm_pointwise_bwd(dh, dout[:, l, d * H:(d + 1) * H], dc, acts[d, s], cs[d, s], cs[d, s + 1],
+                                           dgates[s], dc_prev, dh_pass, lengths, l)
+                    ops.linear_bwd_input(dgates[s], w_hh, out=dh_rec)
+                    ops.axpy2d(1.0, dh_pass, dh_rec, accumulate=True)
+                    dh, dh_rec = dh_rec, dh
+                    dc, dc_prev = dc_prev, dc
+            # weight gradients: one GEMM each over all L*B rows; x rows for step s are x[:, order[s]]
             xs = x if d == 0 else x.flip(1)
             xs = xs.transpose(0, 1).contiguous()                       # [L, B, In] in step order
             if w_ih.requires_grad:

@@ -21,6 +21,18 @@ class DasaError(RuntimeError):
     pass
 
 
+class BiLstmFwd(ctypes.Structure):
+    """dasa_bilstm_fwd_t"""
+    _fields_ = [("xp", P * 2), ("w_hh", P * 2), ("b_ih", P * 2), ("b_hh", P * 2), ("hs", P * 2), ("cs", P * 2),
+                ("acts", P * 2), ("out", P), ("lengths", P), ("B", I), ("L", I), ("H", I)]
+
+
+class BiLstmBwd(ctypes.Structure):
+    """dasa_bilstm_bwd_t"""
+    _fields_ = [("w_hh_t", P * 2), ("acts", P * 2), ("cs", P * 2), ("dout", P), ("dh_fin", P * 2), ("dc_fin", P * 2),
+                ("dgates", P * 2), ("dh_pass", P * 2), ("dc_work", P * 2), ("lengths", P), ("B", I), ("L", I), ("H", I)]
+
+
 class Epilogue(ctypes.Structure):
     """dasa_epilogue_t"""
     _fields_ = [("bias", P), ("gate_src", P), ("ld_gate", L), ("gate_out", P), ("ld_gate_out", L),

@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import lib
-from .lib import Epilogue, call
+from .lib import Epilogue, call  # noqa: F401
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_TANH, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_GATE, EPI_TANH = range(7)
 PREC_FP32, PREC_TF32 = 0, 1

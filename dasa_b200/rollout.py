@@ -34,16 +34,23 @@ class DeviceEpisodes:
             for k in self.FIELDS:
                 setattr(self, k, getattr(ep, k).to(device))
         else:
-            self.stage = {k: torch.empty_like(getattr(ep, k)[0], device=device) for k in self.FIELDS}
+            # one device buffer per (field, step): the tensors are saved for backward, so they cannot be recycled inside a
+            # rollout (and must not share an autograd version counter)
+            self.stage = {k: [torch.empty_like(getattr(ep, k)[0], device=device) for _ in range(ep.T)] for k in self.FIELDS}
 
     def step(self, t):
         if self.resident:
             return tuple(getattr(self, k)[t] for k in self.FIELDS)
         out = []
         for k in self.FIELDS:                       # host -> device copy of this step's inputs (pinned source)
-            self.stage[k].copy_(getattr(self.host, k)[t], non_blocking=True)
-            out.append(self.stage[k])
+            dst = self.stage[k][t]
+            dst.copy_(getattr(self.host, k)[t], non_blocking=True)
+            out.append(dst)
         return tuple(out)
+
+    def target_at(self, t):
+        """Teacher action of step t (device tensor; valid after step(t) in the non-resident mode)."""
+        return getattr(self, "target")[t] if self.resident else self.stage["target"][t]
 
 
 class NavPolicy:
@@ -101,7 +108,7 @@ class NavPolicy:
             if tag_steps:
                 src.prefix = base_prefix + "t%d." % t
             logit, h_t, carry = self.step(ep, t, carry)
-            loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.step(t)[6] if ep.resident else ep.stage["target"], self.cfg.ignore_id)
+            loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.target_at(t), self.cfg.ignore_id)
             total = loss_t if total is None else total + loss_t
             logits.append(logit)
             actions.append(a_t)

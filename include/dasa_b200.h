@@ -147,6 +147,30 @@ int dasa_lstm_pointwise_bwd(const float* dh, int64_t ld_dh, const float* dh2, in
                             int64_t ld_dcp, float* dh_pass, int64_t ld_dhp, const int32_t* active, int pos,
                             int B, int H, void* stream);
 
+/* Fused recurrence of the packed bidirectional encoder LSTM (r2rmodel.py:2339-2357) for small batches (B <= 20,
+ * H % 64 == 0): ONE call issues the whole time loop (one launch per step covering both directions; each CTA owns 16
+ * hidden units, streams its recurrent-weight rows from L2 and applies the pointwise cell in the same kernel).
+ * Index d = 0 is the forward direction, d = 1 the reverse direction; step s processes position l = s (d=0) or L-1-s (d=1).
+ *   fwd: xp[d] = x W_ih^T [B, L, 4H] (no bias); hs/cs[d] = [L+1, B, H] state BEFORE step s at index s (index 0 zero-filled
+ *        by the caller); acts[d] = [L, B, 4H] post-nonlinearity gates; out = [B, L, 2H] (zero rows past each length).
+ *   bwd: w_hh_t[d] = W_hh^T [H, 4H]; dout = grad of `out`; dh_fin/dc_fin[d] = grad of the final states [B, H] or NULL;
+ *        dgates[d] = [L, B, 4H] (output, step order); dh_pass/dc_work[d] = [2, B, H] scratch.                          */
+typedef struct {
+  const float* xp[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];
+  float* hs[2]; float* cs[2]; float* acts[2]; float* out; const int32_t* lengths;
+  int B, L, H;
+} dasa_bilstm_fwd_t;
+typedef struct {
+  const float* w_hh_t[2]; const float* acts[2]; const float* cs[2]; const float* dout;
+  const float* dh_fin[2]; const float* dc_fin[2];
+  float* dgates[2]; float* dh_pass[2]; float* dc_work[2];
+  const int32_t* lengths;
+  int B, L, H;
+} dasa_bilstm_bwd_t;
+int dasa_bilstm_max_batch(void);
+int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* args, void* stream);
+int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------- encoder pieces (a9)
  * BertEmbeddings (vilmodel.py:161-176): out[b,l,:] = LN(word[ids[b,l]] + pos[l] + type[0]) (* mask*scale).          */
 int dasa_embed_layernorm(const int64_t* ids, int64_t ld_ids, int B, int L, int Hd, const float* word, const float* pos,

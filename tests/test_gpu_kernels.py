@@ -274,3 +274,39 @@ def test_dropout_mask_rate_and_determinism():
     assert torch.equal(m1, m2)
     assert abs(float(m1.float().mean()) - 0.6) < 5e-3
     assert not torch.equal(m1, ops.dropout_mask((1 << 20,), 0.4, 8, 0))
+
+
+@pytest.mark.parametrize("B,L,In,H", [(3, 9, 96, 128), (20, 24, 768, 128), (20, 80, 768, 1024), (7, 33, 64, 64)])
+def test_bilstm_fused_fwd_bwd(B, L, In, H):
+    """Fused per-step bi-LSTM kernels (packed-sequence semantics, ragged lengths) against the oracle + autograd."""
+    gen = g(17 + B)
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    sd = {}
+    for sfx in ("", "_reverse"):
+        sd["lstm.weight_ih_l0" + sfx] = torch.randn(4 * H, In, generator=gen) / math.sqrt(In)
+        sd["lstm.weight_hh_l0" + sfx] = torch.randn(4 * H, H, generator=gen) / math.sqrt(H)
+        sd["lstm.bias_ih_l0" + sfx] = torch.randn(4 * H, generator=gen) * 0.1
+        sd["lstm.bias_hh_l0" + sfx] = torch.randn(4 * H, generator=gen) * 0.1
+    sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    lengths = torch.randint(1, L + 1, (B,), generator=gen).sort(descending=True).values
+    lengths[0] = L
+    x = torch.randn(B, L, In, generator=gen).requires_grad_(True)
+    out, ((hf, cf), (hb, cb)) = R.bilstm(sd, x, lengths, H)
+    wts = [torch.randn(t.shape, generator=gen) for t in (out, hf, cf, hb, cb)]
+    sum((t * w).sum() for t, w in zip((out, hf, cf, hb, cb), wts)).backward()
+    P = {k: v.detach().to(DEV).requires_grad_(True) for k, v in sd.items()}
+    xd = x.detach().to(DEV).requires_grad_(True)
+    l32 = lengths.to(DEV).to(torch.int32)
+    o2, hfin, cfin = Fn.BiLSTMFn.apply(xd, l32, *[P["lstm." + n] for n in names], *[P["lstm." + n + "_reverse"] for n in names])
+    assert_close(o2, out, 1e-4, "seq out")
+    assert_close(hfin[0], hf, 1e-4, "h fwd"); assert_close(hfin[1], hb, 1e-4, "h bwd")
+    assert_close(cfin[0], cf, 1e-4, "c fwd"); assert_close(cfin[1], cb, 1e-4, "c bwd")
+    pad = torch.arange(L)[None, :] >= lengths[:, None]
+    if bool(pad.any()):
+        assert float(o2[pad.to(DEV)].abs().max()) == 0.0
+    dhf = torch.stack((wts[1], wts[3])).to(DEV)
+    dcf = torch.stack((wts[2], wts[4])).to(DEV)
+    torch.autograd.backward([o2, hfin, cfin], [wts[0].to(DEV), dhf, dcf])
+    assert_close(xd.grad, x.grad, 3e-4, "dx")
+    for k in sd:
+        assert_close(P[k].grad, sd[k].grad, 3e-4, k)
