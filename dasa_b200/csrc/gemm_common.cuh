@@ -23,24 +23,36 @@ static inline EpiParams make_epi(const dasa_epilogue_t* e) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// v = alpha*acc + beta*C already applied by the caller.
-__device__ __forceinline__ float apply_epilogue(float v, int m, int n, int N, int epilogue, const EpiParams& ep) {
-  if (epilogue != DASA_EPI_NONE && epilogue != DASA_EPI_TANH && ep.bias != nullptr) v += __ldg(ep.bias + n);
-  switch (epilogue) {
-    case DASA_EPI_BIAS_TANH:
-    case DASA_EPI_TANH: v = tanhf(v); break;
-    case DASA_EPI_BIAS_GELU: v = gelu_erf(v); break;
-    case DASA_EPI_BIAS_RELU: v = fmaxf(v, 0.f); break;
-    case DASA_EPI_GATE: {
-      const float s = sigmoidf_(v);
-      if (ep.gate_out != nullptr) ep.gate_out[(int64_t)m * ep.ld_gate_out + n] = s;
-      v = s * __ldg(ep.gate_src + (int64_t)m * ep.ld_gate + n);
-      break;
-    }
-    default: break;
+// v = alpha*acc + beta*C already applied by the caller. Compile-time epilogue kind: each kernel instantiation carries
+// exactly one variant (a runtime switch inside the fully unrolled accumulator loops made the kernels instruction-fetch bound).
+template <int EPI>
+__device__ __forceinline__ float apply_epilogue_t(float v, int m, int n, int N, const EpiParams& ep) {
+  if constexpr (EPI != DASA_EPI_NONE && EPI != DASA_EPI_TANH) {
+    if (ep.bias != nullptr) v += __ldg(ep.bias + n);
+  }
+  if constexpr (EPI == DASA_EPI_BIAS_TANH || EPI == DASA_EPI_TANH) v = tanhf(v);
+  if constexpr (EPI == DASA_EPI_BIAS_GELU) v = gelu_erf(v);
+  if constexpr (EPI == DASA_EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+  if constexpr (EPI == DASA_EPI_GATE) {
+    const float s = sigmoidf_(v);
+    if (ep.gate_out != nullptr) ep.gate_out[(int64_t)m * ep.ld_gate_out + n] = s;
+    v = s * __ldg(ep.gate_src + (int64_t)m * ep.ld_gate + n);
   }
   if (ep.drop_mask != nullptr) v *= ep.drop_mask[(int64_t)m * N + n] ? ep.drop_scale : 0.f;
   return v;
+}
+
+// runtime-dispatched form for the small (non-unrolled) reduction kernels
+static __device__ __noinline__ float apply_epilogue(float v, int m, int n, int N, int epilogue, const EpiParams& ep) {
+  switch (epilogue) {
+    case DASA_EPI_BIAS: return apply_epilogue_t<DASA_EPI_BIAS>(v, m, n, N, ep);
+    case DASA_EPI_BIAS_TANH: return apply_epilogue_t<DASA_EPI_BIAS_TANH>(v, m, n, N, ep);
+    case DASA_EPI_BIAS_GELU: return apply_epilogue_t<DASA_EPI_BIAS_GELU>(v, m, n, N, ep);
+    case DASA_EPI_BIAS_RELU: return apply_epilogue_t<DASA_EPI_BIAS_RELU>(v, m, n, N, ep);
+    case DASA_EPI_GATE: return apply_epilogue_t<DASA_EPI_GATE>(v, m, n, N, ep);
+    case DASA_EPI_TANH: return apply_epilogue_t<DASA_EPI_TANH>(v, m, n, N, ep);
+    default: return apply_epilogue_t<DASA_EPI_NONE>(v, m, n, N, ep);
+  }
 }
 
 // implemented in gemm_simt.cu / gemm_tc.cu

@@ -121,9 +121,11 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int6
       if (partial != nullptr) {
         partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
       } else {
+        // direct store path: only the plain / bias epilogues (others are routed through the reduction kernel)
         float v = alpha * acc[i][j];
         if (beta != 0.f) v += beta * C[(int64_t)m * ldc + n];
-        C[(int64_t)m * ldc + n] = apply_epilogue(v, m, n, N, epilogue, ep);
+        if (epilogue == DASA_EPI_BIAS && ep.bias != nullptr) v += __ldg(ep.bias + n);
+        C[(int64_t)m * ldc + n] = v;
       }
     }
   }
@@ -199,7 +201,7 @@ int launch_simt(int a_k, int b_k, int M, int N, int K, float alpha, const float*
 
 size_t dasa_gemm_simt_workspace(int M, int N, int K) {
   SimtPlan p = plan_simt(M, N, K);
-  return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
+  return (size_t)p.splits * M * N * sizeof(float);          // also the staging buffer of the two-pass activation epilogues
 }
 
 int dasa_gemm_simt(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
@@ -209,10 +211,12 @@ int dasa_gemm_simt(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha,
   if (K <= 0) return DASA_ERR_BAD_SHAPE;
   SimtPlan p = plan_simt(M, N, K);
   float* partial = nullptr;
-  if (p.splits > 1) {
+  const bool simple = (epilogue == DASA_EPI_NONE || epilogue == DASA_EPI_BIAS) && ep.drop_mask == nullptr;
+  if (p.splits > 1 || !simple) {
     const size_t need = (size_t)p.splits * M * N * sizeof(float);
-    if (workspace == nullptr || workspace_bytes < need) {  // run unsplit rather than fail
-      p.splits = 1;
+    if (workspace == nullptr || workspace_bytes < need) {
+      if (!simple) return DASA_ERR_WORKSPACE;                 // fused activations need the staging buffer
+      p.splits = 1;                                           // run unsplit rather than fail
       p.k_per_split = K;
     } else {
       partial = static_cast<float*>(workspace);

@@ -73,7 +73,7 @@ struct TcParams {
   int k_per_split;       // multiple of TC_BK
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -164,7 +164,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float x = p.alpha * __uint_as_float(r[j]);
       if (nb + j < p.N) {
         if (p.beta != 0.f) x += p.beta * crow[j];
-        x = apply_epilogue(x, m, nb + j, p.N, p.epilogue, p.ep);
+        x = apply_epilogue_t<EPI>(x, m, nb + j, p.N, p.ep);
       }
       v[j] = x;
     }
@@ -244,14 +244,33 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int6
   return r == CUDA_SUCCESS;
 }
 
+template <int BN, int STAGES, int EPI>
+int launch_tc_e(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int splits, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { dasa_set_error("gemm_tf32 attr", e); return DASA_ERR_CUDA; }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)dasa_cdiv(p.N, BN), (unsigned)dasa_cdiv(p.M, TC_BM), (unsigned)splits);
+  gemm_tf32_kernel<BN, STAGES, EPI><<<grid, TC_THREADS, smem, st>>>(ta, tb, p);
+  return dasa_check_launch("gemm_tf32_kernel");
+}
+
 template <int BN, int STAGES>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int splits, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { dasa_set_error("gemm_tf32 attr", e); return DASA_ERR_CUDA; }
-  dim3 grid((unsigned)dasa_cdiv(p.N, BN), (unsigned)dasa_cdiv(p.M, TC_BM), (unsigned)splits);
-  gemm_tf32_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tb, p);
-  return dasa_check_launch("gemm_tf32_kernel");
+  // split-K launches only store raw partial sums: one (NONE) instantiation serves them all
+  const int epi = (p.partial != nullptr) ? DASA_EPI_NONE : p.epilogue;
+  switch (epi) {
+    case DASA_EPI_BIAS: return launch_tc_e<BN, STAGES, DASA_EPI_BIAS>(ta, tb, p, splits, st);
+    case DASA_EPI_BIAS_TANH: return launch_tc_e<BN, STAGES, DASA_EPI_BIAS_TANH>(ta, tb, p, splits, st);
+    case DASA_EPI_BIAS_GELU: return launch_tc_e<BN, STAGES, DASA_EPI_BIAS_GELU>(ta, tb, p, splits, st);
+    case DASA_EPI_BIAS_RELU: return launch_tc_e<BN, STAGES, DASA_EPI_BIAS_RELU>(ta, tb, p, splits, st);
+    case DASA_EPI_GATE: return launch_tc_e<BN, STAGES, DASA_EPI_GATE>(ta, tb, p, splits, st);
+    case DASA_EPI_TANH: return launch_tc_e<BN, STAGES, DASA_EPI_TANH>(ta, tb, p, splits, st);
+    default: return launch_tc_e<BN, STAGES, DASA_EPI_NONE>(ta, tb, p, splits, st);
+  }
 }
 
 }  // namespace
