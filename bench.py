@@ -212,6 +212,9 @@ def run_ours(args):
 
     cfg, B, T = FULL, args.batch, args.actions
     pol = NavPolicy(cfg, synth.policy_state(cfg, 0), dev).train()
+    pol.flatten_parameters()
+    from dasa_b200 import dist as ddist
+    ddist.broadcast_(pol.param_buffers(), world)
     host_ep = synth.Episodes(B, T, cfg, seed=100 + rank, pin=True)
     ep_res = DeviceEpisodes(host_ep, dev, resident=True)
     ep_e2e = DeviceEpisodes(host_ep, dev, resident=False)
@@ -221,13 +224,10 @@ def run_ours(args):
     def one_step(ep, read_back):
         pol.zero_grad()
         with M.use_dropout_source(src):
-            loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT, tag_steps=False)
+            # per-rank factor ml_weight / (B_local * world): summed gradients == one process running the global batch
+            loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT / world, tag_steps=False)
         loss.backward()
-        if world > 1:
-            for m in pol.models:
-                for p in m.parameters():
-                    if p.grad is not None:
-                        dist.all_reduce(p.grad)
+        ddist.allreduce_sum_(pol.grad_buffers(), world)     # NCCL over NVLink: 4 flat buffers, ~190 MB
         pol.optim_step(LR)
         if read_back:
             loss_host.copy_(loss.detach(), non_blocking=True)

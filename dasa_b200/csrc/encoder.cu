@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(const int64_t* __r
   }
 }
 
-__global__ void __launch_bounds__(256) dropout_residual_layernorm_kernel(
+__global__ void __launch_bounds__(128) dropout_residual_layernorm_kernel(
     const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ mask, float scale, const float* __restrict__ resid,
     int64_t ldr, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, const uint8_t* __restrict__ post_mask,
     float post_scale, float* __restrict__ out, int64_t ldo, float* __restrict__ stats_out, float* __restrict__ z_out, int R, int Hd) {
@@ -194,59 +194,144 @@ struct MhaArgs {
   int B, heads, Lq, Lk, dh;
 };
 
+// Register-tiled: a warp owns 4 query rows; lane l owns keys l, l+32, l+64 (scores) / head-dim columns l, l+32 (P.V).
+// Q/K rows are padded to dh+4 floats so 128-bit shared loads are conflict-free per quarter-warp.
 __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
-  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh, dhp = dh + 1;
-  float* Qs = smem;                    // [Lq][dh]
-  float* Ks = Qs + Lq * dh;            // [Lk][dh+1]  (padded: conflict-free column reads)
-  float* Vs = Ks + Lk * dhp;           // [Lk][dh]
-  float* Ss = Vs + Lk * dh;            // [Lq][Lk]
+  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh, dhp = dh + 4;
+  const int LqP = (Lq + 3) & ~3, LkP = (Lk + 3) & ~3;
+  float* Qs = smem;                      // [LqP][dhp]
+  float* Ks = Qs + LqP * dhp;            // [LkP][dhp]
+  float* Vs = Ks + LkP * dhp;            // [LkP][dh]
+  float* Ss = Vs + LkP * dh;             // [LqP][LkP]
   const float* qb = a.q + (int64_t)b * a.sq + h * dh;
   const float* kb = a.k + (int64_t)b * a.sk + h * dh;
   const float* vb = a.v + (int64_t)b * a.sv + h * dh;
-  for (int i = threadIdx.x; i < Lq * dh; i += blockDim.x) Qs[i] = qb[(int64_t)(i / dh) * a.ldq + (i % dh)];
-  for (int i = threadIdx.x; i < Lk * dh; i += blockDim.x) {
-    const int r = i / dh, c = i % dh;
-    Ks[r * dhp + c] = kb[(int64_t)r * a.ldk + c];
-    Vs[i] = vb[(int64_t)r * a.ldv + c];
+  const int d4n = dh >> 2;
+  for (int i = threadIdx.x; i < LqP * d4n; i += blockDim.x) {
+    const int r = i / d4n, c = i % d4n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < Lq) v = *reinterpret_cast<const float4*>(qb + (int64_t)r * a.ldq + 4 * c);
+    *reinterpret_cast<float4*>(Qs + r * dhp + 4 * c) = v;
   }
-  __syncthreads();
-  const float scale = rsqrtf((float)dh);
-  for (int idx = threadIdx.x; idx < Lq * Lk; idx += blockDim.x) {
-    const int i = idx / Lk, j = idx % Lk;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < dh; ++d) acc = fmaf(Qs[i * dh + d], Ks[j * dhp + d], acc);
-    acc *= scale;   // reference: scores / sqrt(dh) then + mask (vilmodel.py:219-222)
-    if (a.key_pad != nullptr && a.key_pad[(int64_t)b * a.ld_pad + j]) acc += -10000.0f;
-    Ss[idx] = acc;
+  for (int i = threadIdx.x; i < LkP * d4n; i += blockDim.x) {
+    const int r = i / d4n, c = i % d4n;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (r < Lk) {
+      kv = *reinterpret_cast<const float4*>(kb + (int64_t)r * a.ldk + 4 * c);
+      vv = *reinterpret_cast<const float4*>(vb + (int64_t)r * a.ldv + 4 * c);
+    }
+    *reinterpret_cast<float4*>(Ks + r * dhp + 4 * c) = kv;
+    *reinterpret_cast<float4*>(Vs + r * dh + 4 * c) = vv;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = wid; i < Lq; i += nw) {
-    float mx = -INFINITY;
-    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, Ss[i * Lk + j]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < Lk; j += 32) { const float e = expf(Ss[i * Lk + j] - mx); Ss[i * Lk + j] = e; sum += e; }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    for (int j = lane; j < Lk; j += 32) {
-      float p = Ss[i * Lk + j] * inv;
-      const int64_t gi = (((int64_t)b * a.heads + h) * Lq + i) * Lk + j;
-      if (a.probs_out != nullptr) a.probs_out[gi] = p;
-      if (a.drop_mask != nullptr) p *= a.drop_mask[gi] ? a.drop_scale : 0.f;
-      Ss[i * Lk + j] = p;
+  const float scale = rsqrtf((float)dh);
+  constexpr int JT = 3;                  // keys per lane (Lk <= 96)
+  for (int i0 = wid * 4; i0 < Lq; i0 += nw * 4) {
+    float acc[4][JT];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int t = 0; t < JT; ++t) acc[r][t] = 0.f;
+    for (int c = 0; c < d4n; ++c) {
+      float4 q[4], k[JT];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) q[r] = *reinterpret_cast<const float4*>(Qs + (i0 + r) * dhp + 4 * c);
+#pragma unroll
+      for (int t = 0; t < JT; ++t) {
+        const int j = lane + 32 * t;
+        k[t] = (j < LkP) ? *reinterpret_cast<const float4*>(Ks + j * dhp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int t = 0; t < JT; ++t) {
+          acc[r][t] = fmaf(q[r].x, k[t].x, acc[r][t]);
+          acc[r][t] = fmaf(q[r].y, k[t].y, acc[r][t]);
+          acc[r][t] = fmaf(q[r].z, k[t].z, acc[r][t]);
+          acc[r][t] = fmaf(q[r].w, k[t].w, acc[r][t]);
+        }
     }
-  }
-  __syncthreads();
-  float* ob = a.out + (int64_t)b * a.so + h * dh;
-  for (int idx = threadIdx.x; idx < Lq * dh; idx += blockDim.x) {
-    const int i = idx / dh, d = idx % dh;
-    float acc = 0.f;
-    for (int j = 0; j < Lk; ++j) acc = fmaf(Ss[i * Lk + j], Vs[j * dh + d], acc);
-    ob[(int64_t)i * a.ldo + d] = acc;
+    // softmax over keys for the 4 rows (scores / sqrt(dh) + additive -10000 padding mask, vilmodel.py:219-225)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r;
+      float v[JT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < JT; ++t) {
+        const int j = lane + 32 * t;
+        float x = -INFINITY;
+        if (j < Lk) {
+          x = acc[r][t] * scale;
+          if (a.key_pad != nullptr && a.key_pad[(int64_t)b * a.ld_pad + j]) x += -10000.0f;
+        }
+        v[t] = x;
+        mx = fmaxf(mx, x);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < JT; ++t) {
+        v[t] = (lane + 32 * t < Lk) ? expf(v[t] - mx) : 0.f;
+        sum += v[t];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      if (i < Lq) {
+#pragma unroll
+        for (int t = 0; t < JT; ++t) {
+          const int j = lane + 32 * t;
+          if (j < LkP) {
+            float p = 0.f;
+            if (j < Lk) {
+              p = v[t] * inv;
+              const int64_t gi = (((int64_t)b * a.heads + h) * Lq + i) * Lk + j;
+              if (a.probs_out != nullptr) a.probs_out[gi] = p;
+              if (a.drop_mask != nullptr) p *= a.drop_mask[gi] ? a.drop_scale : 0.f;
+            }
+            Ss[i * LkP + j] = p;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // O[i0..i0+3][d] = P V ; lane owns head-dim columns lane, lane+32
+    float o[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { o[r][0] = 0.f; o[r][1] = 0.f; }
+    for (int j4 = 0; j4 < LkP; j4 += 4) {
+      float4 p[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        p[r] = (i0 + r < Lq) ? *reinterpret_cast<const float4*>(Ss + (i0 + r) * LkP + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int d = lane + 32 * c;
+        if (d < dh) {
+          const float v0 = Vs[(j4 + 0) * dh + d], v1 = Vs[(j4 + 1) * dh + d], v2 = Vs[(j4 + 2) * dh + d], v3 = Vs[(j4 + 3) * dh + d];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            o[r][c] = fmaf(p[r].x, v0, o[r][c]);
+            o[r][c] = fmaf(p[r].y, v1, o[r][c]);
+            o[r][c] = fmaf(p[r].z, v2, o[r][c]);
+            o[r][c] = fmaf(p[r].w, v3, o[r][c]);
+          }
+        }
+      }
+    }
+    float* ob = a.out + (int64_t)b * a.so + h * dh;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (i0 + r < Lq) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int d = lane + 32 * c;
+          if (d < dh) ob[(int64_t)(i0 + r) * a.ldo + d] = o[r][c];
+        }
+      }
   }
 }
 
@@ -376,7 +461,7 @@ extern "C" int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, cons
       !dasa_aligned16(gamma) || !dasa_aligned16(beta) || (drop_mask && reinterpret_cast<uintptr_t>(drop_mask) % 4) ||
       (post_mask && reinterpret_cast<uintptr_t>(post_mask) % 4) || (z_out && !dasa_aligned16(z_out)))
     return DASA_ERR_BAD_ALIGN;
-  dropout_residual_layernorm_kernel<<<(unsigned)dasa_cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(
+  dropout_residual_layernorm_kernel<<<(unsigned)dasa_cdiv(R, 4), 128, 0, (cudaStream_t)stream>>>(
       x, ldx, drop_mask, drop_scale, resid, ldr, gamma, beta, eps, post_mask, post_scale, out, ldo, stats_out, z_out, R, Hd);
   return dasa_check_launch("dropout_residual_layernorm_kernel");
 }
@@ -402,7 +487,11 @@ extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float
                             int Lk, int dh, void* stream) {
   if (B <= 0 || heads <= 0) return DASA_OK;
   if (Lq <= 0 || Lk <= 0 || dh <= 0) return DASA_ERR_BAD_SHAPE;
-  const size_t smem = sizeof(float) * ((size_t)Lq * dh + (size_t)Lk * (dh + 1) + (size_t)Lk * dh + (size_t)Lq * Lk);
+  if (Lk > 96 || dh > 64 || dh % 4 != 0) return DASA_ERR_UNSUPPORTED;
+  if (!dasa_aligned16(q) || !dasa_aligned16(k) || !dasa_aligned16(v) || ldq % 4 || ldk % 4 || ldv % 4 || sq % 4 || sk % 4 || sv % 4)
+    return DASA_ERR_BAD_ALIGN;
+  const int LqP = (Lq + 3) & ~3, LkP = (Lk + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)LqP * (dh + 4) + (size_t)LkP * (dh + 4) + (size_t)LkP * dh + (size_t)LqP * LkP);
   if (smem > 227 * 1024) return DASA_ERR_BAD_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { dasa_set_error("mha_fwd attr", e); return DASA_ERR_CUDA; }

@@ -230,16 +230,28 @@ class LSTMCellFn(torch.autograd.Function):
 
 
 _wt_cache = {}
+_weights_epoch = 0
+
+
+def invalidate_weight_caches():
+    """Call after parameters were updated through raw pointers (the fused RMSprop kernel does not bump tensor versions)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def weights_epoch():
+    return _weights_epoch
 
 
 def _transposed(w):
-    """W_hh^T for the backward recurrence, cached until the parameter changes (optimizer step bumps _version)."""
+    """W_hh^T for the backward recurrence, cached until the parameter changes."""
     key = w.data_ptr()
+    tag = (w._version, _weights_epoch)
     hit = _wt_cache.get(key)
-    if hit is not None and hit[0] == w._version:
+    if hit is not None and hit[0] == tag:
         return hit[1]
     wt = w.detach().t().contiguous()
-    _wt_cache[key] = (w._version, wt)
+    _wt_cache[key] = (tag, wt)
     return wt
 
 

@@ -35,6 +35,7 @@ class DropoutSource:
 
     def __init__(self, seed=0, injected=None, prefix=""):
         self.seed, self.injected, self.prefix, self.counter = int(seed), injected, prefix, 0
+        self._pools = {}
 
     def mask(self, tag, shape, p, training, device):
         if not training or p <= 0.0:
@@ -50,9 +51,19 @@ class DropoutSource:
         n = 1
         for s in shape:
             n *= s
-        m = ops.dropout_mask(tuple(shape), p, self.seed, self.counter, device)
-        self.counter += n
-        return m, scale
+        # sub-allocate from a per-probability pool filled by ONE RNG launch (dozens of tiny launches per action otherwise)
+        pool = self._pools.get(p)
+        if pool is None or pool[1] + n > pool[0].numel():
+            size = max(self.POOL_BYTES, n)
+            buf = ops.dropout_mask((size,), p, self.seed, self.counter, device)
+            self.counter += size
+            pool = [buf, 0]
+            self._pools[p] = pool
+        off = pool[1]
+        pool[1] = (off + n + 15) & ~15
+        return pool[0][off:off + n].view(tuple(shape)), scale
+
+    POOL_BYTES = 16 << 20
 
 
 _source = DropoutSource()
@@ -345,7 +356,7 @@ class DicModel(nn.Module):
     def _qkv(self, att, which="qkv"):
         key = (id(att), which)
         ver = (att.query.weight._version, att.key.weight._version, att.value.weight._version,
-               att.query.weight.data_ptr())
+               att.query.weight.data_ptr(), Fn.weights_epoch())
         hit = self._qkv_cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]

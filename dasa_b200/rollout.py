@@ -61,6 +61,7 @@ class NavPolicy:
         self.encoder, self.decoder, self.critic, self.adaIn = M.build_policy(cfg, state, device)
         self.models = (self.encoder, self.decoder, self.critic, self.adaIn)
         self._opt = None
+        self._flat = None
 
     def train(self):
         for m in self.models:
@@ -73,6 +74,10 @@ class NavPolicy:
         return self
 
     def zero_grad(self):
+        if getattr(self, "_flat", None) is not None:
+            for g in self._flat:
+                g["flat_g"].zero_()
+            return
         for m in self.models:
             for p in m.parameters():
                 if p.grad is not None:
@@ -128,6 +133,42 @@ class NavPolicy:
         return actions, logits
 
     # ------------------------------------------------------------------------------------------------- optimizer (a12)
+    def flatten_parameters(self):
+        """Re-home the trainable parameters of each optimizer group (encoder / decoder / critic / adaIn, agent_dg.py:214-241)
+        in one flat fp32 buffer, with a matching flat gradient buffer that every `p.grad` views: zero_grad is one memset per
+        group, the data-parallel reduction one all-reduce per group, clip + RMSprop one launch per group. The frozen BERT stack
+        (detached in the train config, vilmodel.py:1377-1410) is excluded and marked requires_grad=False."""
+        groups = []
+        for name, m, clip in (("encoder", self.encoder, 40.0), ("decoder", self.decoder, 40.0), ("critic", self.critic, None),
+                              ("adaIn", self.adaIn, None)):
+            ps = []
+            for k, p in m.named_parameters():
+                if name == "encoder" and k.startswith("bert."):
+                    p.requires_grad_(False)
+                    continue
+                ps.append(p)
+            n = sum(p.numel() for p in ps)
+            flat_p = torch.empty(n, device=self.device, dtype=torch.float32)
+            flat_g = torch.zeros(n, device=self.device, dtype=torch.float32)
+            off = 0
+            for p in ps:
+                k = p.numel()
+                flat_p[off:off + k].copy_(p.data.reshape(-1))
+                p.data = flat_p[off:off + k].view_as(p)
+                p.grad = flat_g[off:off + k].view_as(p)
+                off += k
+            groups.append({"name": name, "params": ps, "clip": clip, "flat_p": flat_p, "flat_g": flat_g,
+                           "flat_sq": torch.zeros_like(flat_p)})
+        self._flat = groups
+        self._opt = {"sumsq": torch.zeros(1, device=self.device), "coef": torch.ones(1, device=self.device)}
+        return groups
+
+    def grad_buffers(self):
+        return [g["flat_g"] for g in self._flat]
+
+    def param_buffers(self):
+        return [g["flat_p"] for g in self._flat]
+
     def _build_optimizer(self, lr):
         groups = []
         for name, m, clip in (("encoder", self.encoder, 40.0), ("decoder", self.decoder, 40.0), ("critic", self.critic, None),
@@ -139,7 +180,20 @@ class NavPolicy:
 
     def optim_step(self, lr=1e-4):
         """clip_grad_norm_(encoder, 40), clip_grad_norm_(decoder, 40), RMSprop on all four groups (agent_dg.py:1389-1405).
-        Parameters that never received a gradient are skipped, like torch.optim does for grad=None."""
+        Parameters that never received a gradient are skipped, like torch.optim does for grad=None (in the flat layout they
+        carry an all-zero gradient, for which the RMSprop update is exactly zero)."""
+        if getattr(self, "_flat", None) is not None:
+            o = self._opt
+            for g in self._flat:
+                coef = None
+                if g["clip"] is not None:
+                    o["sumsq"].zero_()
+                    ops.sumsq(g["flat_g"], o["sumsq"])
+                    ops.clip_coef(o["sumsq"], g["clip"], o["coef"])
+                    coef = o["coef"]
+                ops.rmsprop_step(g["flat_p"], g["flat_g"], g["flat_sq"], lr, 0.99, 1e-8, 0.0, coef)
+            Fn.invalidate_weight_caches()       # parameters changed behind autograd's back (raw-pointer update)
+            return
         if self._opt is None:
             self._build_optimizer(lr)
         o = self._opt
@@ -154,3 +208,4 @@ class NavPolicy:
                 coef = o["coef"]
             for p, sq in live:
                 ops.rmsprop_step(p.data, p.grad, sq, lr, 0.99, 1e-8, 0.0, coef)
+        Fn.invalidate_weight_caches()
