@@ -202,6 +202,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
     lib.load()
     ops.set_precision(args.precision)
+    from dasa_b200 import functions as Fn
+    Fn.defer_weight_grads(True)      # one long-K weight-gradient GEMM per weight per rollout
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -226,7 +228,7 @@ def run_ours(args):
         with M.use_dropout_source(src):
             # per-rank factor ml_weight / (B_local * world): summed gradients == one process running the global batch
             loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT / world, tag_steps=False)
-        loss.backward()
+        pol.backward(loss)
         ddist.allreduce_sum_(pol.grad_buffers(), world)     # NCCL over NVLink: 4 flat buffers, ~190 MB
         pol.optim_step(LR)
         if read_back:
@@ -322,7 +324,7 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
         pol.zero_grad()
         with M.use_dropout_source(src):
             loss, _, _ = pol.teacher_rollout(ep, min(ep.T, 4), ML_WEIGHT, tag_steps=False)
-        loss.backward()
+        pol.backward(loss)
         torch.cuda.synchronize()
     finally:
         ops_mod.call = orig

@@ -5,6 +5,7 @@
 // four warps read the accumulator back with tcgen05.ld for the fused epilogue (bias / tanh / GELU / ReLU / sigmoid-gate).
 // K-major ("Linear") operand layout only; the other layouts of dasa_gemm stay on the FFMA kernel.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_common.cuh"
 
@@ -64,6 +65,10 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ unsigned long long g_tc_ts[64];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TC_STAMP(i) do { if ((p.debug & 2) && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == 0) g_tc_ts[i] = gtimer(); } while (0)
+
 struct TcParams {
   int M, N, K;
   float alpha, beta;
@@ -71,6 +76,7 @@ struct TcParams {
   int epilogue; EpiParams ep;
   float* partial;        // split-K partial sums [S, M, N] or nullptr
   int k_per_split;       // multiple of TC_BK
+  int debug;             // bit0: skip epilogue global stores (timing experiments only)
 };
 
 template <int BN, int STAGES, int EPI>
@@ -91,6 +97,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int kend = min(p.K, kbeg + p.k_per_split);
   const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
 
+  if (threadIdx.x == 0) TC_STAMP(0);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -103,6 +110,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0 && lane == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -114,7 +122,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       unsigned char* a_dst = tiles + s * STAGE_BYTES;
       tma_load_2d(a_dst, &tmA, kbeg + kb * TC_BK, m0, &full_bar[s]);
       tma_load_2d(a_dst + A_BYTES, &tmB, kbeg + kb * TC_BK, n0, &full_bar[s]);
+      if (kb == 0) TC_STAMP(2);
     }
+    TC_STAMP(3);
   } else if (warp == 1 && lane == 0) {
     // ---------------------------------------------------------------- MMA issuer (single thread)
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
@@ -123,6 +133,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
+      if (kb == 0) TC_STAMP(4);
       tc_fence_after();
       unsigned char* a_src = tiles + s * STAGE_BYTES;
       const uint64_t da = make_smem_desc_sw128(a_src);
@@ -135,51 +146,74 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       umma_commit(&empty_bar[s]);      // smem stage free once these MMAs have consumed it
     }
     umma_commit(tmem_full);            // accumulator complete
+    TC_STAMP(5);
   }
 
   // -------------------------------------------------------------------- epilogue: all four warps
   __syncwarp();
   mbar_wait(tmem_full, 0);
   tc_fence_after();
-  const int m = m0 + warp * 32 + lane;               // TMEM lane == tile row
-  const bool row_ok = m < p.M;
-  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  if (threadIdx.x == 64) TC_STAMP(6);
+  // Phase 1: TMEM -> shared. Thread = tile row (TMEM lane); the pipeline smem is idle now (all MMAs retired, all TMA
+  // loads consumed) and is reused as a [128][BN+4] fp32 staging tile (the +4 keeps the 128-bit row writes conflict-free).
+  constexpr int LDS = BN + 4;
+  float* stage = reinterpret_cast<float*>(tiles);
+  {
+    float* srow = stage + (warp * 32 + lane) * LDS;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    if (!row_ok) continue;
-    const int nb = n0 + c0;
-    if (p.partial != nullptr) {
-      float* dst = p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N + nb;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (nb + j < p.N) dst[j] = __uint_as_float(r[j]);
-      continue;
-    }
-    float* crow = p.C + (int64_t)m * p.ldc + nb;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = p.alpha * __uint_as_float(r[j]);
-      if (nb + j < p.N) {
-        if (p.beta != 0.f) x += p.beta * crow[j];
-        x = apply_epilogue_t<EPI>(x, m, nb + j, p.N, p.ep);
-      }
-      v[j] = x;
-    }
-    if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (nb + j < p.N) crow[j] = v[j];
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(srow + c0 + 4 * q) =
+            make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
     }
   }
+  __syncwarp();     // each warp re-reads only the 32 rows it staged itself
+  // Phase 2: shared -> global, one (or two) full tile rows per warp instruction: every global access of the epilogue
+  // (C, beta*C, bias, gate source / gate output, drop mask) is coalesced.
+  constexpr int LPR = BN / 4;          // lanes per row
+  constexpr int RPI = 32 / LPR;        // rows per warp instruction
+  const int col4 = lane % LPR, rsub = lane / LPR;
+  const int n = n0 + 4 * col4;
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (n + 3 < p.N);
+  if (!(p.debug & 1)) {
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr += RPI) {
+      const int r = warp * 32 + rr + rsub;
+      const int m = m0 + r;
+      if (m >= p.M || n >= p.N) continue;
+      const float4 a4 = *reinterpret_cast<const float4*>(stage + r * LDS + 4 * col4);
+      float v[4] = {a4.x, a4.y, a4.z, a4.w};
+      if (p.partial != nullptr) {
+        float* dst = p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N + n;
+        if (((p.N & 3) == 0) && (n + 3 < p.N)) *reinterpret_cast<float4*>(dst) = a4;
+        else
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = v[e];
+        continue;
+      }
+      float* crow = p.C + (int64_t)m * p.ldc + n;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (n + e < p.N) {
+          float x = p.alpha * v[e];
+          if (p.beta != 0.f) x += p.beta * crow[e];
+          v[e] = apply_epilogue_t<EPI>(x, m, n + e, p.N, p.ep);
+        }
+      }
+      if (vec_ok) *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+      else
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (n + e < p.N) crow[e] = v[e];
+    }
+  }
+  if (threadIdx.x == 64) TC_STAMP(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (threadIdx.x == 32) TC_STAMP(8);
 }
 
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N, float alpha, float beta,
@@ -197,17 +231,22 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int S
 struct TcPlan { int bn; int splits; int k_per_split; };
 
 TcPlan plan_tc(int M, int N, int K) {
+  // Measured on B200 (scripts/gemm_sweep.py, gemm_timeline.py): a launch costs ~14 us fixed, a k-block 0.1-0.3 us depending on
+  // how many CTAs share the L2 ports; a second wave or a split-K reduction pass costs more than it gains unless K is long.
   TcPlan pl;
   const int64_t tm = dasa_cdiv(M, TC_BM);
-  pl.bn = (tm * dasa_cdiv(N, 128) >= DASA_NUM_SMS || N <= 64) ? 128 : 64;
+  const int64_t t128 = tm * dasa_cdiv(N, 128), t64 = tm * dasa_cdiv(N, 64);
   if (N <= 64) pl.bn = 64;
+  else if (t128 >= 120) pl.bn = 128;
+  else if (t64 <= DASA_NUM_SMS) pl.bn = 64;
+  else pl.bn = 128;
   const int64_t tiles = tm * dasa_cdiv(N, pl.bn);
-  int s = 1;
   const int nkb = (int)dasa_cdiv(K, TC_BK);
-  if (tiles < DASA_NUM_SMS && nkb >= 8) {
-    s = (int)dasa_cdiv(DASA_NUM_SMS, tiles);
-    s = s > nkb / 4 ? nkb / 4 : s;
-    s = s < 1 ? 1 : (s > 32 ? 32 : s);
+  int s = 1;
+  if (tiles * 2 <= DASA_NUM_SMS && nkb >= 64) {
+    s = (int)(DASA_NUM_SMS / tiles);
+    s = s > nkb / 16 ? nkb / 16 : s;
+    s = s < 1 ? 1 : (s > 16 ? 16 : s);
   }
   int kps = (int)dasa_cdiv(nkb, s) * TC_BK;
   pl.splits = (int)dasa_cdiv(K, kps);
@@ -275,6 +314,10 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, i
 
 }  // namespace
 
+extern "C" int dasa_debug_tc_timestamps(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, g_tc_ts, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : DASA_ERR_CUDA;
+}
+
 bool dasa_gemm_tc_supported(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int64_t lda, const float* B,
                             int64_t ldb, const float* C, int64_t ldc) {
   (void)C; (void)ldc;
@@ -302,7 +345,9 @@ int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, c
   }
   CUtensorMap ta, tb;
   if (!make_map(&ta, A, M, K, lda, TC_BM) || !make_map(&tb, B, N, K, ldb, pl.bn)) return DASA_ERR_UNSUPPORTED;
-  TcParams p{M, N, K, alpha, beta, C, ldc, epilogue, ep, partial, pl.k_per_split};
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("DASA_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  TcParams p{M, N, K, alpha, beta, C, ldc, epilogue, ep, partial, pl.k_per_split, dbg};
   int rc = (pl.bn == 128) ? launch_tc<128, 6>(ta, tb, p, pl.splits, st) : launch_tc<64, 8>(ta, tb, p, pl.splits, st);
   if (rc != DASA_OK) return rc;
   if (partial != nullptr) {

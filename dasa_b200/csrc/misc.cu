@@ -103,6 +103,31 @@ __global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict_
   }
 }
 
+// out[c, r] = in[r, c] through a 32x33 shared tile (both sides coalesced)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols,
+                                                        float* __restrict__ out, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(int64_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void bump_counter_kernel(unsigned long long* ctr, unsigned long long inc) { ctr[0] += inc; }
+
+__global__ void __launch_bounds__(256) dropout_mask_dev_kernel(uint8_t* __restrict__ mask, int64_t n, float p,
+                                                               const unsigned long long* __restrict__ seed_dev, uint64_t offset) {
+  const uint64_t seed = seed_dev[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = hash_uniform(seed, offset + (uint64_t)i) >= p ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
                                                       int64_t n, float lr, float alpha, float eps, float wd,
                                                       const float* __restrict__ clip) {
@@ -157,6 +182,24 @@ extern "C" int dasa_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t see
   if (n <= 0) return DASA_OK;
   dropout_mask_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset);
   return dasa_check_launch("dropout_mask_kernel");
+}
+
+extern "C" int dasa_transpose(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, void* stream) {
+  if (rows <= 0 || cols <= 0) return DASA_OK;
+  dim3 grid((unsigned)dasa_cdiv(cols, 32), (unsigned)dasa_cdiv(rows, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, ld_in, rows, cols, out, ld_out);
+  return dasa_check_launch("transpose_kernel");
+}
+
+extern "C" int dasa_dropout_mask_dev(uint8_t* mask, int64_t n, float p, const uint64_t* seed_dev, uint64_t offset, void* stream) {
+  if (n <= 0) return DASA_OK;
+  dropout_mask_dev_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, n, p, reinterpret_cast<const unsigned long long*>(seed_dev), offset);
+  return dasa_check_launch("dropout_mask_dev_kernel");
+}
+
+extern "C" int dasa_bump_counter(uint64_t* counter, uint64_t inc, void* stream) {
+  bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter), inc);
+  return dasa_check_launch("bump_counter_kernel");
 }
 
 extern "C" int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* target, int ignore_index, int B, int Nc, float grad_scale,

@@ -14,6 +14,47 @@ def _zeros_like_grad(p):
     return p.grad
 
 
+# ---------------------------------------------------------------------------------------- deferred weight gradients
+# dW = dY^T X is a reduction over rows. Inside a rollout every step contributes only B (=20) rows to each decoder weight,
+# i.e. a rank-20 update that re-reads and re-writes the whole weight gradient. With deferral the (dY, X) row blocks of all
+# T steps are queued and ONE GEMM per weight with reduction length T*B (or T*L*B for the bi-LSTM) runs at flush time.
+_defer = False
+_queue = {}
+
+
+def defer_weight_grads(flag=True):
+    global _defer
+    _defer = bool(flag)
+
+
+def _wgrad(weight, dy, x, bias=None):
+    """dW += dy^T x ; db += colsum(dy) — immediately, or queued until flush_weight_grads()."""
+    if not weight.requires_grad:
+        return
+    if not _defer:
+        ops.linear_bwd_weight(dy, x, _zeros_like_grad(weight), True)
+        if bias is not None and bias.requires_grad:
+            ops.colsum(dy, _zeros_like_grad(bias), True)
+        return
+    ent = _queue.get(id(weight))
+    if ent is None:
+        ent = _queue[id(weight)] = [weight, bias, [], []]
+    d2, x2 = ops._rows(dy)[0], ops._rows(x)[0]
+    ent[2].append(d2)
+    ent[3].append(x2)
+
+
+def flush_weight_grads():
+    """Run the queued weight-gradient reductions (call once after loss.backward())."""
+    for weight, bias, dys, xs in _queue.values():
+        dY = dys[0] if len(dys) == 1 else torch.cat(dys, 0)
+        X = xs[0] if len(xs) == 1 else torch.cat(xs, 0)
+        ops.linear_bwd_weight(dY, X, _zeros_like_grad(weight), True)
+        if bias is not None and bias.requires_grad:
+            ops.colsum(dY, _zeros_like_grad(bias), True)
+    _queue.clear()
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) with act in {none, tanh, relu} fused in the GEMM epilogue."""
 
@@ -33,10 +74,7 @@ class LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         if ctx.act:
             dy = ops.act_backward(ctx.act, dy, y)
-        if weight.requires_grad:
-            ops.linear_bwd_weight(dy, x, _zeros_like_grad(weight), True)
-        if ctx.has_bias and bias.requires_grad:
-            ops.colsum(dy, _zeros_like_grad(bias), True)
+        _wgrad(weight, dy, x, bias if ctx.has_bias else None)
         dx = ops.linear_bwd_input(dy, weight) if ctx.needs_input_grad[0] else None
         return dx, None, None, None
 
@@ -95,9 +133,7 @@ class AdaINGateFn(torch.autograd.Function):
         dg = torch.empty(R, C, device=f.device, dtype=torch.float32)
         ops.call("dasa_gate_backward", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
                  None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, R, C, ops._stream())
-        # dW[C,C] += dg^T d ; db += colsum(dg)
-        ops.gemm(dg, C, 0, d2, ldd, 0, _zeros_like_grad(weight), C, C, C, R, beta=1.0)
-        ops.colsum(dg, _zeros_like_grad(bias), True)
+        _wgrad(weight, dg, d2[:, :C], bias)        # dW[C,C] += dg^T d ; db += colsum(dg)
         return None, None, None, None, None, None, None
 
 
@@ -120,11 +156,8 @@ class ShiftAttnFn(torch.autograd.Function):
         h, context, w_in, w_shift, b_shift, t, p, q, kappa = ctx.saved_tensors
         need_dctx = ctx.needs_input_grad[1]
         dctx, dt, dkl = ops.row_attention_bwd(context, t, p, q, kappa, dwc.contiguous(), ctx.k, ctx.headings, need_dctx)
-        if w_in.requires_grad:
-            ops.linear_bwd_weight(dt, h, _zeros_like_grad(w_in), True)
-        if w_shift.requires_grad:
-            ops.linear_bwd_weight(dkl, h, _zeros_like_grad(w_shift), True)
-            ops.colsum(dkl, _zeros_like_grad(b_shift), True)
+        _wgrad(w_in, dt, h)
+        _wgrad(w_shift, dkl, h, b_shift)
         dh = None
         if ctx.needs_input_grad[0]:
             dh = ops.linear_bwd_input(dt, w_in)
@@ -154,13 +187,11 @@ class SoftDotAttnFn(torch.autograd.Function):
         h, context, w_in, w_out, t, alpha, cat, h_tilde = ctx.saved_tensors
         D = ctx.D
         du = ops.act_backward("tanh", dht.contiguous(), h_tilde)
-        if w_out.requires_grad:
-            ops.linear_bwd_weight(du, cat, _zeros_like_grad(w_out), True)
+        _wgrad(w_out, du, cat)
         dcat = ops.linear_bwd_input(du, w_out)
         need_dctx = ctx.needs_input_grad[1]
         dctx, dt, _ = ops.row_attention_bwd(context, t, alpha, alpha, None, dcat[:, :D], 0, 1, need_dctx)
-        if w_in.requires_grad:
-            ops.linear_bwd_weight(dt, h, _zeros_like_grad(w_in), True)
+        _wgrad(w_in, dt, h)
         dh = None
         if ctx.needs_input_grad[0]:
             dh = dcat[:, D:].contiguous()
@@ -190,8 +221,7 @@ class CandLogitsFn(torch.autograd.Function):
             # only the AdaIN'd RGB slice carries gradient; the angle part is environment data
             dcand = torch.zeros(cand.shape, device=cand.device, dtype=torch.float32)
             ops.axpy2d(1.0, dcand_rgb, dcand[..., :ctx.rgb], accumulate=False)
-        if w_in.requires_grad:
-            ops.linear_bwd_weight(dt, h, _zeros_like_grad(w_in), True)
+        _wgrad(w_in, dt, h)
         dh = ops.linear_bwd_input(dt, w_in) if ctx.needs_input_grad[0] else None
         return dh, dcand, None, None, None
 
@@ -219,40 +249,24 @@ class LSTMCellFn(torch.autograd.Function):
         dc0 = torch.empty(B, H, device=h.device, dtype=torch.float32)
         ops.lstm_pointwise_bwd(None if dh1 is None else dh1.contiguous(), None, None if dc1 is None else dc1.contiguous(),
                                acts, c.contiguous(), c1, dgates, dc0)
-        if w_ih.requires_grad:
-            ops.linear_bwd_weight(dgates, x, _zeros_like_grad(w_ih), True)
-            ops.linear_bwd_weight(dgates, h, _zeros_like_grad(w_hh), True)
-            ops.colsum(dgates, _zeros_like_grad(b_ih), True)
-            ops.colsum(dgates, _zeros_like_grad(b_hh), True)
+        _wgrad(w_ih, dgates, x, b_ih)
+        _wgrad(w_hh, dgates, h, b_hh)
         dx = ops.linear_bwd_input(dgates, w_ih) if ctx.needs_input_grad[0] else None
         dh = ops.linear_bwd_input(dgates, w_hh) if ctx.needs_input_grad[1] else None
         return dx, dh, (dc0 if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
-_wt_cache = {}
-_weights_epoch = 0
-
-
 def invalidate_weight_caches():
     """Call after parameters were updated through raw pointers (the fused RMSprop kernel does not bump tensor versions)."""
-    global _weights_epoch
-    _weights_epoch += 1
+    ops.weights_epoch += 1
 
 
 def weights_epoch():
-    return _weights_epoch
+    return ops.weights_epoch
 
 
 def _transposed(w):
-    """W_hh^T for the backward recurrence, cached until the parameter changes."""
-    key = w.data_ptr()
-    tag = (w._version, _weights_epoch)
-    hit = _wt_cache.get(key)
-    if hit is not None and hit[0] == tag:
-        return hit[1]
-    wt = w.detach().t().contiguous()
-    _wt_cache[key] = (tag, wt)
-    return wt
+    return ops.transposed_weight(w)
 
 
 class BiLSTMFn(torch.autograd.Function):
@@ -345,11 +359,8 @@ class BiLSTMFn(torch.autograd.Function):
             # weight gradients: one GEMM each over all L*B rows; x rows for step s are x[:, order[s]]
             xs = x if d == 0 else x.flip(1)
             xs = xs.transpose(0, 1).contiguous()                       # [L, B, In] in step order
-            if w_ih.requires_grad:
-                ops.linear_bwd_weight(dgates.view(L * B, 4 * H), xs.view(L * B, In), _zeros_like_grad(w_ih), True)
-                ops.linear_bwd_weight(dgates.view(L * B, 4 * H), hs[d, :L].reshape(L * B, H), _zeros_like_grad(w_hh), True)
-                ops.colsum(dgates.view(L * B, 4 * H), _zeros_like_grad(b_ih), True)
-                ops.colsum(dgates.view(L * B, 4 * H), _zeros_like_grad(b_hh), True)
+            _wgrad(w_ih, dgates.view(L * B, 4 * H), xs.view(L * B, In), b_ih)
+            _wgrad(w_hh, dgates.view(L * B, 4 * H), hs[d, :L].reshape(L * B, H), b_hh)
             if need_dx:
                 dxs = ops.linear_bwd_input(dgates.view(L * B, 4 * H), w_ih).view(L, B, In).transpose(0, 1)
                 dx += dxs if d == 0 else dxs.flip(1)

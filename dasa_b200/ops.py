@@ -106,6 +106,36 @@ def linear_fwd(x, w, bias=None, epilogue=None, out=None, beta=0.0, precision=Non
     return out
 
 
+def transpose(x, out=None):
+    """x [R, C] (rows may be strided) -> [C, Rp] with Rp = R rounded up to 4 (row stride TMA-legal); returns out[:, :R]."""
+    x2, R, C, ld = _rows(x)
+    Rp = (R + 3) & ~3
+    if out is None:
+        out = torch.empty(C, Rp, device=x.device, dtype=torch.float32)
+    call("dasa_transpose", _p(x2), ld, R, C, _p(out), out.stride(0), _stream())
+    return out[:, :R]
+
+
+_wt_cache = {}
+weights_epoch = 0      # bumped by the optimizer step (raw-pointer updates do not bump tensor versions)
+
+
+def transposed_weight(w):
+    """W^T ([in, out], contiguous rows) cached until the parameter changes: lets dX = dY.W run as a K-major GEMM."""
+    key = w.data_ptr()
+    tag = (w._version, weights_epoch, tuple(w.shape))
+    hit = _wt_cache.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    wt = transpose(w.detach())
+    _wt_cache[key] = (tag, wt)
+    return wt
+
+
+def _tc_ok(*dims):
+    return _precision == PREC_TF32 and all(d >= 32 and d % 4 == 0 for d in dims)
+
+
 def linear_bwd_input(dy, w, out=None, beta=0.0, precision=None):
     """dx[.., K] (+)= dy[.., N] @ w[N, K]"""
     _chk(dy, w, out)
@@ -114,6 +144,10 @@ def linear_bwd_input(dy, w, out=None, beta=0.0, precision=None):
     if out is None:
         out = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=torch.float32)
     o2, _, _, ldc = _rows_out(out)
+    if precision is None and _tc_ok(N) and lda % 4 == 0 and d2.data_ptr() % 16 == 0:
+        wt = transposed_weight(w)                                  # [K, N] rows of stride Np
+        gemm(d2, lda, 1, wt, wt.stride(0), 1, o2, ldc, M, K, N, beta=beta)
+        return out
     gemm(d2, lda, 1, w, K, 0, o2, ldc, M, K, N, beta=beta, precision=precision)
     return out
 
@@ -124,6 +158,10 @@ def linear_bwd_weight(dy, x, dw, accumulate=True, precision=None):
     d2, M, N, ldd = _rows(dy)
     x2, Mx, K, ldx = _rows(x)
     assert M == Mx and dw.shape == (N, K) and dw.is_contiguous()
+    if precision is None and _tc_ok(M) and M >= 64:
+        dyt, xt = transpose(d2), transpose(x2)                    # [N, Mp], [K, Mp]: both K-major over the row index
+        gemm(dyt, dyt.stride(0), 1, xt, xt.stride(0), 1, dw, K, N, K, M, beta=1.0 if accumulate else 0.0)
+        return dw
     gemm(d2, ldd, 0, x2, ldx, 0, dw, K, N, K, M, beta=1.0 if accumulate else 0.0, precision=precision)
     return dw
 

@@ -120,6 +120,11 @@ class NavPolicy:
         src.prefix = base_prefix
         return total * (ml_weight / ep.B), logits, actions
 
+    def backward(self, loss):
+        """loss.backward() + the deferred, batched weight-gradient GEMMs (functions.defer_weight_grads)."""
+        loss.backward()
+        Fn.flush_weight_grads()
+
     @torch.no_grad()
     def greedy_rollout(self, ep, T=None):
         """feedback='argmax' decode (agent_dg.py:871-875) over pre-generated observations: per-step greedy actions."""

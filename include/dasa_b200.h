@@ -218,6 +218,12 @@ int dasa_act_backward(int act /*0 tanh, 1 relu*/, const float* dy, int64_t lddy,
 int dasa_axpy2d(float a, const float* x, int64_t ldx, float* y, int64_t ldy, int accumulate, int R, int C, void* stream);
 /* keep-mask generator (counter-based hash RNG): mask[i] = u(seed, offset+i) >= p                                   */
 int dasa_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* same, with the seed read from device memory at run time, so a captured CUDA graph draws fresh masks on every replay
+ * (dasa_bump_counter advances that seed inside the graph)                                                           */
+int dasa_dropout_mask_dev(uint8_t* mask, int64_t n, float p, const uint64_t* seed_dev, uint64_t offset, void* stream);
+int dasa_bump_counter(uint64_t* counter, uint64_t inc, void* stream);
+/* out[c*ld_out + r] = in[r*ld_in + c]  (operand re-layout for the K-major tensor-core GEMM in the backward pass)    */
+int dasa_transpose(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, void* stream);
 
 /* --------------------------------------------------------------------------------------- loss / action (a10, a13)
  * nn.CrossEntropyLoss(ignore_index, sum) over masked logits + argmax (agent_dg.py:850, 870-873):

@@ -9,6 +9,8 @@ from dasa_b200.rollout import DeviceEpisodes, NavPolicy
 prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ops.set_precision(prec)
+import dasa_b200.functions as Fn
+Fn.defer_weight_grads(True)
 cfg = FULL
 pol = NavPolicy(cfg, synth.policy_state(cfg, 0)).train()
 ep = DeviceEpisodes(synth.Episodes(20, T, cfg, seed=1))
@@ -18,7 +20,7 @@ def run():
     pol.zero_grad()
     with M.use_dropout_source(src):
         loss, _, _ = pol.teacher_rollout(ep, T, 0.4, tag_steps=False)
-    loss.backward()
+    pol.backward(loss)
     pol.optim_step(1e-4)
 
 run(); run()
