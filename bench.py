@@ -219,25 +219,53 @@ def run_ours(args):
     ddist.broadcast_(pol.param_buffers(), world)
     host_ep = synth.Episodes(B, T, cfg, seed=100 + rank, pin=True)
     ep_res = DeviceEpisodes(host_ep, dev, resident=True)
-    ep_e2e = DeviceEpisodes(host_ep, dev, resident=False)
-    src = M.DropoutSource(seed=1234 + rank)
+    src = M.DropoutSource(seed=1234 + rank, device_seed=True, device=dev)
     loss_host = torch.zeros(1).pin_memory()
+    state = {"graph": None, "loss": None, "launches": 0, "graph_error": None}
 
-    def one_step(ep, read_back):
+    def fwd_bwd(ep):
         pol.zero_grad()
+        src.advance()
         with M.use_dropout_source(src):
             # per-rank factor ml_weight / (B_local * world): summed gradients == one process running the global batch
             loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT / world, tag_steps=False)
         pol.backward(loss)
+        return loss
+
+    def finish():
         ddist.allreduce_sum_(pol.grad_buffers(), world)     # NCCL over NVLink: 4 flat buffers, ~190 MB
         pol.optim_step(LR)
+
+    def one_step(ep, read_back, upload=False):
+        if upload:                                          # e2e: this rollout's inputs come from pinned host memory
+            for k in DeviceEpisodes.FIELDS:
+                getattr(ep_res, k).copy_(getattr(host_ep, k), non_blocking=True)
+        if state["graph"] is not None:
+            state["graph"].replay()
+            loss = state["loss"]
+            if world > 1:
+                finish()
+        else:
+            loss = fwd_bwd(ep_res)
+            finish()
         if read_back:
             loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
 
-    def timed(ep, read_back, steps, warmup):
+    def capture():
+        """Whole rollout (forward, backward, deferred weight grads, and for N=1 clip + RMSprop) as ONE CUDA graph."""
+        Fn.invalidate_weight_caches()                       # cached transposes must be rebuilt INSIDE the graph every replay
+        g = torch.cuda.CUDAGraph()
+        l0 = lib.launches
+        with torch.cuda.graph(g):
+            loss = fwd_bwd(ep_res)
+            if world == 1:
+                finish()
+        state["graph"], state["loss"], state["launches"] = g, loss, lib.launches - l0
+
+    def timed(read_back, upload, steps, warmup):
         for _ in range(warmup):
-            one_step(ep, read_back)
+            one_step(ep_res, read_back, upload)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -246,7 +274,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            one_step(ep, read_back)
+            one_step(ep_res, read_back, upload)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -254,14 +282,27 @@ def run_ours(args):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps, (lib.launches - l0) // steps
+        n = (lib.launches - l0) // steps
+        return float(ms) / steps, (n + state["launches"] if state["graph"] is not None else n)
+
+    for _ in range(2):                                      # eager warm-up (allocator, caches, autotuned smem attributes)
+        one_step(ep_res, False)
+    torch.cuda.synchronize()
+    if not args.no_graph:
+        try:
+            capture()
+        except Exception as e:                              # stay on eager launches, say so in the JSON line
+            state["graph"], state["graph_error"] = None, repr(e)[:200]
+            torch.cuda.synchronize()
+            Fn.invalidate_weight_caches()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step, launches = timed(ep_res, False, args.steps, args.warmup)
+    ms_step, launches = timed(False, False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(ep_e2e, True, max(1, args.steps // 2), 1)
+    ms_e2e, _ = timed(True, True, max(1, args.steps // 2), 1)
+    Fn.invalidate_weight_caches()
 
     nav = B * T * world
     value = nav / (ms_step * 1e-3)
@@ -289,7 +330,9 @@ def run_ours(args):
         "config": {"workload": "agent_dg teacher-forced vl_rollout fwd+bwd+RMSprop, B=%d/GPU, T=%d, 36x2176 views, 80-token "
                                "instructions, 9 la + 3 vl layers recomputed per action (BASELINE.json configs[1])" % (B, T),
                    "precision": args.precision, "l2": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2",
-                   "parallelism": "dp%d" % world},
+                   "parallelism": "dp%d" % world,
+                   "launch": "cuda-graph replay of the whole rollout" if state["graph"] is not None else
+                             "eager launches (%s)" % (state["graph_error"] or "--no-graph")},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "nav steps/s", "h2d_bytes_per_step": host_ep.h2d_bytes_per_step() * T,
                 "d2h_bytes_per_step": 4},
@@ -322,6 +365,7 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
     ops_mod.call = hooked
     try:
         pol.zero_grad()
+        src.advance()
         with M.use_dropout_source(src):
             loss, _, _ = pol.teacher_rollout(ep, min(ep.T, 4), ML_WEIGHT, tag_steps=False)
         pol.backward(loss)

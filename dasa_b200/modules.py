@@ -33,9 +33,19 @@ from .config import FULL, PolicyConfig
 class DropoutSource:
     """Provides keep masks for dropout sites. tag -> uint8 keep mask (or None in eval)."""
 
-    def __init__(self, seed=0, injected=None, prefix=""):
+    def __init__(self, seed=0, injected=None, prefix="", device_seed=False, device="cuda"):
         self.seed, self.injected, self.prefix, self.counter = int(seed), injected, prefix, 0
         self._pools = {}
+        # device_seed: the RNG seed lives in device memory and is advanced by a kernel (`advance()`), so a captured CUDA graph
+        # draws different masks on every replay
+        self.seed_dev = torch.tensor([int(seed)], dtype=torch.int64, device=device) if device_seed else None
+
+    def advance(self):
+        """Start a new iteration: fresh masks (device-seed mode) and recycled pools."""
+        self._pools = {}
+        if self.seed_dev is not None:
+            self.counter = 0
+            ops.bump_counter(self.seed_dev)
 
     def mask(self, tag, shape, p, training, device):
         if not training or p <= 0.0:
@@ -55,7 +65,10 @@ class DropoutSource:
         pool = self._pools.get(p)
         if pool is None or pool[1] + n > pool[0].numel():
             size = max(self.POOL_BYTES, n)
-            buf = ops.dropout_mask((size,), p, self.seed, self.counter, device)
+            if self.seed_dev is not None:
+                buf = ops.dropout_mask_dev((size,), p, self.seed_dev, self.counter, device)
+            else:
+                buf = ops.dropout_mask((size,), p, self.seed, self.counter, device)
             self.counter += size
             pool = [buf, 0]
             self._pools[p] = pool

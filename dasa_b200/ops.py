@@ -212,6 +212,17 @@ def dropout_mask(shape, p, seed, offset=0, device="cuda"):
     return m
 
 
+def dropout_mask_dev(shape, p, seed_dev, offset=0, device="cuda"):
+    """Keep mask whose seed is read from device memory at run time (fresh masks on every CUDA-graph replay)."""
+    m = torch.empty(shape, dtype=torch.uint8, device=device)
+    call("dasa_dropout_mask_dev", _p(m), m.numel(), float(p), _p(seed_dev), int(offset), _stream())
+    return m
+
+
+def bump_counter(counter, inc=0x9E3779B97F4A7C15):
+    call("dasa_bump_counter", _p(counter), int(inc) & 0xFFFFFFFFFFFFFFFF, _stream())
+
+
 def as_keep_mask(m):
     """Accept bool / float (pre-scaled) / uint8 masks from tests; return contiguous uint8 keep flags."""
     if m is None:
