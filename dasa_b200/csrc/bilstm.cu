@@ -218,6 +218,272 @@ __global__ void __launch_bounds__(THREADS) bilstm_step_bwd_kernel(SeqBwd p, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TF32 tensor-core variants (precision mode tf32). Same CTA = 16 hidden units decomposition, but the 64 x H (fwd) /
+// 16 x 4H (bwd) weight slice is streamed from L2 straight into mma.sync.m16n8k8 A-fragments with 128-bit loads (the k
+// index inside each 16-wide group is permuted identically for A and B, so one float4 per row feeds two MMAs), the
+// batch side (h / dgates, <= 24 rows) is loaded the same way, the 8 warps split the reduction dimension and combine
+// their partial tiles through shared memory. No operand staging, no per-chunk barriers; fp32 accumulate.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int NB = 24;          // padded batch (3 n-tiles of 8)
+
+__global__ void __launch_bounds__(THREADS) bilstm_step_fwd_tc_kernel(SeqFwd p, int s) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  float (*part)[64][NB + 1] = reinterpret_cast<float (*)[64][NB + 1]>(smem_dyn);   // [8] per-warp partial gate tiles
+  float (*gbuf)[NB + 1] = part[0];                 // the reduced tile overwrites warp 0's partials in place
+  const int d = blockIdx.y, j0 = blockIdx.x * UNITS;
+  const int B = p.B, L = p.L, H = p.H;
+  const int l = d == 0 ? s : L - 1 - s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* h_prev = p.hs[d] + (size_t)s * B * H;
+  const float* W = p.w_hh[d];
+  const int kspan = H >> 3, kw0 = warp * kspan;    // this warp's slice of the reduction dimension
+  // local row r = unit*4 + gate  ->  global W row gate*H + j0 + unit ; m-tile mt covers local rows 16mt .. 16mt+15
+  const float* rowA[4];
+  const float* rowB[4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int ra = 16 * mt + g, rb = ra + 8;
+    rowA[mt] = W + ((size_t)(ra & 3) * H + j0 + (ra >> 2)) * H + kw0 + 4 * t;
+    rowB[mt] = W + ((size_t)(rb & 3) * H + j0 + (rb >> 2)) * H + kw0 + 4 * t;
+  }
+  const float* hrow[3];
+  bool hok[3];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) {
+    const int b = 8 * nt + g;
+    hok[nt] = b < B;
+    hrow[nt] = h_prev + (size_t)(hok[nt] ? b : 0) * H + kw0 + 4 * t;
+  }
+  float acc[4][3][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+  const int groups = kspan >> 4;
+  float4 wa[4], wb[4], hv[3];
+  auto load = [&](int gi) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      wa[mt] = __ldg(reinterpret_cast<const float4*>(rowA[mt] + 16 * gi));
+      wb[mt] = __ldg(reinterpret_cast<const float4*>(rowB[mt] + 16 * gi));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+      hv[nt] = hok[nt] ? *reinterpret_cast<const float4*>(hrow[nt] + 16 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  load(0);
+  for (int gi = 0; gi < groups; ++gi) {
+    float4 ca[4], cb[4], ch[3];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) { ca[mt] = wa[mt]; cb[mt] = wb[mt]; }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) ch[nt] = hv[nt];
+    if (gi + 1 < groups) load(gi + 1);             // next group's loads are in flight during these MMAs
+    uint32_t b0[3], b1[3], b2[3], b3[3];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) { b0[nt] = to_tf32(ch[nt].x); b1[nt] = to_tf32(ch[nt].y); b2[nt] = to_tf32(ch[nt].z); b3[nt] = to_tf32(ch[nt].w); }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const uint32_t a0 = to_tf32(ca[mt].x), a1 = to_tf32(cb[mt].x), a2 = to_tf32(ca[mt].y), a3 = to_tf32(cb[mt].y);
+      const uint32_t e0 = to_tf32(ca[mt].z), e1 = to_tf32(cb[mt].z), e2 = to_tf32(ca[mt].w), e3 = to_tf32(cb[mt].w);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        mma_tf32(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+        mma_tf32(acc[mt][nt], e0, e1, e2, e3, b2[nt], b3[nt]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      part[warp][16 * mt + g][8 * nt + 2 * t] = acc[mt][nt][0];
+      part[warp][16 * mt + g][8 * nt + 2 * t + 1] = acc[mt][nt][1];
+      part[warp][16 * mt + g + 8][8 * nt + 2 * t] = acc[mt][nt][2];
+      part[warp][16 * mt + g + 8][8 * nt + 2 * t + 1] = acc[mt][nt][3];
+    }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 64 * NB; o += THREADS) {
+    const int r = o / NB, c = o % NB;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += part[w][r][c];
+    gbuf[r][c] = v;
+  }
+  __syncthreads();
+  for (int tt = threadIdx.x; tt < UNITS * B; tt += THREADS) {
+    const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+    const size_t sb = (size_t)b * H + j;
+    const float cp = p.cs[d][(size_t)s * B * H + sb];
+    float* hn = p.hs[d] + (size_t)(s + 1) * B * H;
+    float* cn = p.cs[d] + (size_t)(s + 1) * B * H;
+    float* a = p.acts[d] + ((size_t)s * B + b) * 4 * H;
+    float* o = p.out + ((size_t)b * L + l) * 2 * H + (size_t)d * H + j;
+    if (l >= p.lengths[b]) {
+      hn[sb] = h_prev[sb];
+      cn[sb] = cp;
+      *o = 0.f;
+      a[j] = 0.f; a[H + j] = 0.f; a[2 * H + j] = 0.f; a[3 * H + j] = 0.f;
+      continue;
+    }
+    const float* xrow = p.xp[d] + ((size_t)b * L + l) * 4 * H;
+    float gt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      gt[q] = gbuf[u * 4 + q][b] + xrow[q * H + j] + __ldg(p.b_ih[d] + q * H + j) + __ldg(p.b_hh[d] + q * H + j);
+    const float ig = sigmoidf_(gt[0]), fg = sigmoidf_(gt[1]), gg = tanhf(gt[2]), og = sigmoidf_(gt[3]);
+    const float c1 = fg * cp + ig * gg;
+    const float h1 = og * tanhf(c1);
+    hn[sb] = h1;
+    cn[sb] = c1;
+    *o = h1;
+    a[j] = ig; a[H + j] = fg; a[2 * H + j] = gg; a[3 * H + j] = og;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) bilstm_step_bwd_tc_kernel(SeqBwd p, int s) {
+  __shared__ float part[8][UNITS][NB + 1];
+  __shared__ float red[UNITS][NB];
+  const int d = blockIdx.y, j0 = blockIdx.x * UNITS;
+  const int B = p.B, L = p.L, H = p.H, G = 4 * H;
+  const int l = d == 0 ? s : L - 1 - s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const bool last = (s == L - 1);
+  if (!last) {
+    // rec[b, unit] = dgates_{s+1}[b, :] . W_hh^T[unit, :] : one 16-row m-tile, 3 n-tiles, reduction 4H split over the warps
+    const float* dg_next = p.dgates[d] + (size_t)(s + 1) * B * G;
+    const int kspan = G >> 3, kw0 = warp * kspan;
+    const float* rowA = p.w_hh_t[d] + (size_t)(j0 + g) * G + kw0 + 4 * t;
+    const float* rowB = rowA + (size_t)8 * G;
+    const float* brow[3];
+    bool bok[3];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      const int b = 8 * nt + g;
+      bok[nt] = b < B;
+      brow[nt] = dg_next + (size_t)(bok[nt] ? b : 0) * G + kw0 + 4 * t;
+    }
+    float acc[3][4];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    const int groups = kspan >> 4;
+    constexpr int PF = 4;                               // groups of loads kept in flight
+    float4 wa[PF], wb[PF], bv[PF][3];
+    auto load = [&](int gi, int slot) {
+      wa[slot] = __ldg(reinterpret_cast<const float4*>(rowA + 16 * gi));
+      wb[slot] = __ldg(reinterpret_cast<const float4*>(rowB + 16 * gi));
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+        bv[slot][nt] = bok[nt] ? *reinterpret_cast<const float4*>(brow[nt] + 16 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+      if (i < groups) load(i, i);
+    for (int g0 = 0; g0 < groups; g0 += PF) {
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int gi = g0 + i;
+        if (gi >= groups) break;
+        const float4 ca = wa[i], cb = wb[i];
+        float4 ch[3];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) ch[nt] = bv[i][nt];
+        if (gi + PF < groups) load(gi + PF, i);
+        const uint32_t a0 = to_tf32(ca.x), a1 = to_tf32(cb.x), a2 = to_tf32(ca.y), a3 = to_tf32(cb.y);
+        const uint32_t e0 = to_tf32(ca.z), e1 = to_tf32(cb.z), e2 = to_tf32(ca.w), e3 = to_tf32(cb.w);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          mma_tf32(acc[nt], a0, a1, a2, a3, to_tf32(ch[nt].x), to_tf32(ch[nt].y));
+          mma_tf32(acc[nt], e0, e1, e2, e3, to_tf32(ch[nt].z), to_tf32(ch[nt].w));
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      part[warp][g][8 * nt + 2 * t] = acc[nt][0];
+      part[warp][g][8 * nt + 2 * t + 1] = acc[nt][1];
+      part[warp][g + 8][8 * nt + 2 * t] = acc[nt][2];
+      part[warp][g + 8][8 * nt + 2 * t + 1] = acc[nt][3];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < UNITS * NB; o += THREADS) {
+      const int r = o / NB, c = o % NB;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][r][c];
+      red[r][c] = v;
+    }
+  }
+  __syncthreads();
+  const int par = s & 1;
+  for (int tt = threadIdx.x; tt < UNITS * B; tt += THREADS) {
+    const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+    const size_t sb = (size_t)b * H + j;
+    float dh, dc;
+    if (last) {
+      dh = p.dh_fin[d] ? p.dh_fin[d][sb] : 0.f;
+      dc = p.dc_fin[d] ? p.dc_fin[d][sb] : 0.f;
+    } else {
+      dh = red[u][b] + p.dh_pass[d][(size_t)(par ^ 1) * B * H + sb];
+      dc = p.dc_work[d][(size_t)(par ^ 1) * B * H + sb];
+    }
+    float* dg = p.dgates[d] + ((size_t)s * B + b) * G;
+    float* dh_pass = p.dh_pass[d] + (size_t)par * B * H;
+    float* dc_out = p.dc_work[d] + (size_t)par * B * H;
+    if (l >= p.lengths[b]) {
+      dg[j] = 0.f; dg[H + j] = 0.f; dg[2 * H + j] = 0.f; dg[3 * H + j] = 0.f;
+      dh_pass[sb] = dh;
+      dc_out[sb] = dc;
+      continue;
+    }
+    dh += p.dout[((size_t)b * L + l) * 2 * H + (size_t)d * H + j];
+    const float* a = p.acts[d] + ((size_t)s * B + b) * G;
+    const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
+    const float cp = p.cs[d][(size_t)s * B * H + sb];
+    const float tc = tanhf(p.cs[d][(size_t)(s + 1) * B * H + sb]);
+    const float dct = dc + dh * og * (1.f - tc * tc);
+    dg[j] = dct * gg * ig * (1.f - ig);
+    dg[H + j] = dct * cp * fg * (1.f - fg);
+    dg[2 * H + j] = dct * ig * (1.f - gg * gg);
+    dg[3 * H + j] = dh * tc * og * (1.f - og);
+    dh_pass[sb] = 0.f;
+    dc_out[sb] = dct * fg;
+  }
+}
+
+int run_fwd_tc(const SeqFwd& p, cudaStream_t st) {
+  dim3 grid((unsigned)(p.H / UNITS), 2);
+  constexpr size_t smem = sizeof(float) * 8 * 64 * (NB + 1);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(bilstm_step_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { dasa_set_error("bilstm fwd tc attr", e); return DASA_ERR_CUDA; }
+    attr = true;
+  }
+  for (int s = 0; s < p.L; ++s) bilstm_step_fwd_tc_kernel<<<grid, THREADS, smem, st>>>(p, s);
+  return dasa_check_launch("bilstm_step_fwd_tc_kernel");
+}
+
+int run_bwd_tc(const SeqBwd& p, cudaStream_t st) {
+  dim3 grid((unsigned)(p.H / UNITS), 2);
+  for (int s = p.L - 1; s >= 0; --s) bilstm_step_bwd_tc_kernel<<<grid, THREADS, 0, st>>>(p, s);
+  return dasa_check_launch("bilstm_step_bwd_tc_kernel");
+}
+
 template <int BT>
 int run_fwd(const SeqFwd& p, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)BT * p.H + 64 * BT);
@@ -243,7 +509,7 @@ int run_bwd(const SeqBwd& p, cudaStream_t st) {
 
 extern "C" int dasa_bilstm_max_batch(void) { return 20; }
 
-extern "C" int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* a, void* stream) {
+extern "C" int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* a, int precision, void* stream) {
   if (a == nullptr || a->B <= 0 || a->L <= 0) return DASA_ERR_BAD_SHAPE;
   if (a->B > 20 || a->H % 64 != 0) return DASA_ERR_UNSUPPORTED;
   SeqFwd p;
@@ -254,6 +520,7 @@ extern "C" int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* a, void* stream) {
   }
   p.out = a->out; p.lengths = a->lengths; p.B = a->B; p.L = a->L; p.H = a->H;
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DASA_PREC_TF32 && p.H % 128 == 0) return run_fwd_tc(p, st);
   if (p.B <= 4) return run_fwd<4>(p, st);
   if (p.B <= 8) return run_fwd<8>(p, st);
   if (p.B <= 12) return run_fwd<12>(p, st);
@@ -261,7 +528,7 @@ extern "C" int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* a, void* stream) {
   return run_fwd<20>(p, st);
 }
 
-extern "C" int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* a, void* stream) {
+extern "C" int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* a, int precision, void* stream) {
   if (a == nullptr || a->B <= 0 || a->L <= 0) return DASA_ERR_BAD_SHAPE;
   if (a->B > 20 || a->H % 64 != 0) return DASA_ERR_UNSUPPORTED;
   SeqBwd p;
@@ -273,6 +540,7 @@ extern "C" int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* a, void* stream) {
   }
   p.dout = a->dout; p.lengths = a->lengths; p.B = a->B; p.L = a->L; p.H = a->H;
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DASA_PREC_TF32 && p.H % 128 == 0) return run_bwd_tc(p, st);
   if (p.B <= 4) return run_bwd<4>(p, st);
   if (p.B <= 8) return run_bwd<8>(p, st);
   if (p.B <= 12) return run_bwd<12>(p, st);

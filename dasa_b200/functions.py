@@ -296,7 +296,7 @@ class BiLSTMFn(torch.autograd.Function):
                                   P2(b_ih_f.data_ptr(), b_ih_r.data_ptr()), P2(b_hh_f.data_ptr(), b_hh_r.data_ptr()),
                                   P2(hs[0].data_ptr(), hs[1].data_ptr()), P2(cs[0].data_ptr(), cs[1].data_ptr()),
                                   P2(acts[0].data_ptr(), acts[1].data_ptr()), out.data_ptr(), lengths.data_ptr(), B, L, H)
-            ops.call("dasa_bilstm_seq_fwd", ops.ctypes.byref(a), ops._stream())
+            ops.call("dasa_bilstm_seq_fwd", ops.ctypes.byref(a), ops._precision, ops._stream())
         else:
             gh = torch.empty(B, 4 * H, device=dev, dtype=torch.float32)
             for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
@@ -337,7 +337,7 @@ class BiLSTMFn(torch.autograd.Function):
                                   P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates_all[0].data_ptr(), dgates_all[1].data_ptr()),
                                   P2(work[0, 0].data_ptr(), work[0, 1].data_ptr()),
                                   P2(work[1, 0].data_ptr(), work[1, 1].data_ptr()), lengths.data_ptr(), B, L, H)
-            ops.call("dasa_bilstm_seq_bwd", ops.ctypes.byref(a), ops._stream())
+            ops.call("dasa_bilstm_seq_bwd", ops.ctypes.byref(a), ops._precision, ops._stream())
         for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
             dgates = dgates_all[d]
             order = list(range(L)) if d == 0 else list(range(L - 1, -1, -1))

@@ -4,6 +4,7 @@ PyTorch is plumbing here (device memory, streams, the autograd tape); every nume
 the hand-written sm_100a kernels in dasa_b200/csrc. There is no CPU / eager fallback: tensors must be CUDA fp32.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -122,13 +123,16 @@ weights_epoch = 0      # bumped by the optimizer step (raw-pointer updates do no
 
 def transposed_weight(w):
     """W^T ([in, out], contiguous rows) cached until the parameter changes: lets dX = dY.W run as a K-major GEMM."""
-    key = w.data_ptr()
-    tag = (w._version, weights_epoch, tuple(w.shape))
+    key = id(w)
+    tag = (w._version, weights_epoch, w.data_ptr())
     hit = _wt_cache.get(key)
-    if hit is not None and hit[0] == tag:
+    if hit is not None and hit[0] == tag and hit[2]() is w:      # the weakref guards against id()/address reuse
         return hit[1]
+    if len(_wt_cache) > 256:
+        for k in [k for k, v in _wt_cache.items() if v[2]() is None]:
+            del _wt_cache[k]
     wt = transpose(w.detach())
-    _wt_cache[key] = (tag, wt)
+    _wt_cache[key] = (tag, wt, weakref.ref(w))
     return wt
 
 

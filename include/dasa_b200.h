@@ -168,8 +168,9 @@ typedef struct {
   int B, L, H;
 } dasa_bilstm_bwd_t;
 int dasa_bilstm_max_batch(void);
-int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* args, void* stream);
-int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, void* stream);
+/* precision: DASA_PREC_FP32 = FFMA kernels (exact fp32); DASA_PREC_TF32 = mma.sync TF32 tensor-core kernels (H % 128 == 0) */
+int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* args, int precision, void* stream);
+int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------- encoder pieces (a9)
  * BertEmbeddings (vilmodel.py:161-176): out[b,l,:] = LN(word[ids[b,l]] + pos[l] + type[0]) (* mask*scale).          */

@@ -310,3 +310,39 @@ def test_bilstm_fused_fwd_bwd(B, L, In, H):
     assert_close(xd.grad, x.grad, 3e-4, "dx")
     for k in sd:
         assert_close(P[k].grad, sd[k].grad, 3e-4, k)
+
+
+@pytest.mark.parametrize("B,L,In,H", [(20, 45, 768, 1024), (5, 12, 64, 128)])
+def test_bilstm_tf32_tensor_core_path(B, L, In, H):
+    """mma.sync TF32 recurrence kernels (tf32 precision mode): stated bound 1e-2 relative against the fp32 oracle."""
+    gen = g(23 + B)
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    sd = {}
+    for sfx in ("", "_reverse"):
+        sd["lstm.weight_ih_l0" + sfx] = torch.randn(4 * H, In, generator=gen) / math.sqrt(In)
+        sd["lstm.weight_hh_l0" + sfx] = torch.randn(4 * H, H, generator=gen) / math.sqrt(H)
+        sd["lstm.bias_ih_l0" + sfx] = torch.randn(4 * H, generator=gen) * 0.1
+        sd["lstm.bias_hh_l0" + sfx] = torch.randn(4 * H, generator=gen) * 0.1
+    sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    lengths = torch.randint(1, L + 1, (B,), generator=gen).sort(descending=True).values
+    lengths[0] = L
+    x = torch.randn(B, L, In, generator=gen).requires_grad_(True)
+    out, ((hf, cf), (hb, cb)) = R.bilstm(sd, x, lengths, H)
+    wts = [torch.randn(t.shape, generator=gen) for t in (out, hf, cf, hb, cb)]
+    sum((t * w).sum() for t, w in zip((out, hf, cf, hb, cb), wts)).backward()
+    P = {k: v.detach().to(DEV).requires_grad_(True) for k, v in sd.items()}
+    xd = x.detach().to(DEV).requires_grad_(True)
+    l32 = lengths.to(DEV).to(torch.int32)
+    ops.set_precision("tf32")
+    try:
+        o2, hfin, cfin = Fn.BiLSTMFn.apply(xd, l32, *[P["lstm." + n] for n in names], *[P["lstm." + n + "_reverse"] for n in names])
+        dhf = torch.stack((wts[1], wts[3])).to(DEV)
+        dcf = torch.stack((wts[2], wts[4])).to(DEV)
+        torch.autograd.backward([o2, hfin, cfin], [wts[0].to(DEV), dhf, dcf])
+    finally:
+        ops.set_precision("fp32")
+    errs = {"out": rel_err(o2, out), "h_f": rel_err(hfin[0], hf), "h_b": rel_err(hfin[1], hb), "dx": rel_err(xd.grad, x.grad)}
+    for k in sd:
+        errs[k] = rel_err(P[k].grad, sd[k].grad)
+    print("tf32 bilstm errors:", {k: "%.2e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-2, errs
