@@ -272,36 +272,44 @@ __global__ void __launch_bounds__(THREADS) bilstm_step_fwd_tc_kernel(SeqFwd p, i
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
   const int groups = kspan >> 4;
-  float4 wa[4], wb[4], hv[3];
-  auto load = [&](int gi) {
+  constexpr int PF = 2;                              // 16-wide k groups of operand loads kept in flight per lane
+  float4 wa[PF][4], wb[PF][4], hv[PF][3];
+  auto load = [&](int gi, int slot) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      wa[mt] = __ldg(reinterpret_cast<const float4*>(rowA[mt] + 16 * gi));
-      wb[mt] = __ldg(reinterpret_cast<const float4*>(rowB[mt] + 16 * gi));
+      wa[slot][mt] = __ldg(reinterpret_cast<const float4*>(rowA[mt] + 16 * gi));
+      wb[slot][mt] = __ldg(reinterpret_cast<const float4*>(rowB[mt] + 16 * gi));
     }
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt)
-      hv[nt] = hok[nt] ? *reinterpret_cast<const float4*>(hrow[nt] + 16 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      hv[slot][nt] = hok[nt] ? *reinterpret_cast<const float4*>(hrow[nt] + 16 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  load(0);
-  for (int gi = 0; gi < groups; ++gi) {
-    float4 ca[4], cb[4], ch[3];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) { ca[mt] = wa[mt]; cb[mt] = wb[mt]; }
+  for (int i = 0; i < PF; ++i)
+    if (i < groups) load(i, i);
+  for (int g0 = 0; g0 < groups; g0 += PF) {
 #pragma unroll
-    for (int nt = 0; nt < 3; ++nt) ch[nt] = hv[nt];
-    if (gi + 1 < groups) load(gi + 1);             // next group's loads are in flight during these MMAs
-    uint32_t b0[3], b1[3], b2[3], b3[3];
+    for (int i = 0; i < PF; ++i) {
+      const int gi = g0 + i;
+      if (gi >= groups) break;
+      float4 ca[4], cb[4], ch[3];
 #pragma unroll
-    for (int nt = 0; nt < 3; ++nt) { b0[nt] = to_tf32(ch[nt].x); b1[nt] = to_tf32(ch[nt].y); b2[nt] = to_tf32(ch[nt].z); b3[nt] = to_tf32(ch[nt].w); }
+      for (int mt = 0; mt < 4; ++mt) { ca[mt] = wa[i][mt]; cb[mt] = wb[i][mt]; }
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const uint32_t a0 = to_tf32(ca[mt].x), a1 = to_tf32(cb[mt].x), a2 = to_tf32(ca[mt].y), a3 = to_tf32(cb[mt].y);
-      const uint32_t e0 = to_tf32(ca[mt].z), e1 = to_tf32(cb[mt].z), e2 = to_tf32(ca[mt].w), e3 = to_tf32(cb[mt].w);
+      for (int nt = 0; nt < 3; ++nt) ch[nt] = hv[i][nt];
+      if (gi + PF < groups) load(gi + PF, i);        // refill this slot while the MMAs below run
+      uint32_t b0[3], b1[3], b2[3], b3[3];
 #pragma unroll
-      for (int nt = 0; nt < 3; ++nt) {
-        mma_tf32(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
-        mma_tf32(acc[mt][nt], e0, e1, e2, e3, b2[nt], b3[nt]);
+      for (int nt = 0; nt < 3; ++nt) { b0[nt] = to_tf32(ch[nt].x); b1[nt] = to_tf32(ch[nt].y); b2[nt] = to_tf32(ch[nt].z); b3[nt] = to_tf32(ch[nt].w); }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const uint32_t a0 = to_tf32(ca[mt].x), a1 = to_tf32(cb[mt].x), a2 = to_tf32(ca[mt].y), a3 = to_tf32(cb[mt].y);
+        const uint32_t e0 = to_tf32(ca[mt].z), e1 = to_tf32(cb[mt].z), e2 = to_tf32(ca[mt].w), e3 = to_tf32(cb[mt].w);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          mma_tf32(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+          mma_tf32(acc[mt][nt], e0, e1, e2, e3, b2[nt], b3[nt]);
+        }
       }
     }
   }

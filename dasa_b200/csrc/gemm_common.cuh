@@ -26,6 +26,24 @@ __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + e
 // v = alpha*acc + beta*C already applied by the caller. Compile-time epilogue kind: each kernel instantiation carries
 // exactly one variant (a runtime switch inside the fully unrolled accumulator loops made the kernels instruction-fetch bound).
 template <int EPI>
+__device__ __forceinline__ constexpr bool epi_has_bias() { return EPI != DASA_EPI_NONE && EPI != DASA_EPI_TANH; }
+
+// everything after the bias add (callers that loop over rows hoist the per-column bias load out of the loop)
+template <int EPI>
+__device__ __forceinline__ float apply_activation_t(float v, int m, int n, int N, const EpiParams& ep) {
+  if constexpr (EPI == DASA_EPI_BIAS_TANH || EPI == DASA_EPI_TANH) v = tanhf(v);
+  if constexpr (EPI == DASA_EPI_BIAS_GELU) v = gelu_erf(v);
+  if constexpr (EPI == DASA_EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+  if constexpr (EPI == DASA_EPI_GATE) {
+    const float s = sigmoidf_(v);
+    if (ep.gate_out != nullptr) ep.gate_out[(int64_t)m * ep.ld_gate_out + n] = s;
+    v = s * __ldg(ep.gate_src + (int64_t)m * ep.ld_gate + n);
+  }
+  if (ep.drop_mask != nullptr) v *= ep.drop_mask[(int64_t)m * N + n] ? ep.drop_scale : 0.f;
+  return v;
+}
+
+template <int EPI>
 __device__ __forceinline__ float apply_epilogue_t(float v, int m, int n, int N, const EpiParams& ep) {
   if constexpr (EPI != DASA_EPI_NONE && EPI != DASA_EPI_TANH) {
     if (ep.bias != nullptr) v += __ldg(ep.bias + n);

@@ -80,12 +80,12 @@ struct TcParams {
 };
 
 template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, (STAGES <= 4 ? 2 : 1))
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   // 1024-byte alignment is required by the 128B swizzle; the dynamic smem base is aligned by the launch
-  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps shared-space provenance (LDS/STS, not generic)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -95,7 +95,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * p.k_per_split;
   const int kend = min(p.K, kbeg + p.k_per_split);
-  const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
+  const int nkb = (p.debug & 4) ? 0 : (kend - kbeg + TC_BK - 1) / TC_BK;   // debug bit2: skip TMA + MMA
 
   if (threadIdx.x == 0) TC_STAMP(0);
   if (threadIdx.x == 0) {
@@ -158,7 +158,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // loads consumed) and is reused as a [128][BN+4] fp32 staging tile (the +4 keeps the 128-bit row writes conflict-free).
   constexpr int LDS = BN + 4;
   float* stage = reinterpret_cast<float*>(tiles);
-  {
+  if (!(p.debug & 8)) {   // debug bit3: skip the whole epilogue
     float* srow = stage + (warp * 32 + lane) * LDS;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -178,7 +178,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int col4 = lane % LPR, rsub = lane / LPR;
   const int n = n0 + 4 * col4;
   const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (n + 3 < p.N);
-  if (!(p.debug & 1)) {
+  float bias4[4] = {0.f, 0.f, 0.f, 0.f};      // per-column, loop invariant: loaded once (not once per row)
+  if constexpr (epi_has_bias<EPI>()) {
+    if (p.ep.bias != nullptr && p.partial == nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (n + e < p.N) bias4[e] = __ldg(p.ep.bias + n + e);
+    }
+  }
+  const float alpha = p.alpha, beta = p.beta;
+  if (!(p.debug & 9)) {
 #pragma unroll 4
     for (int rr = 0; rr < 32; rr += RPI) {
       const int r = warp * 32 + rr + rsub;
@@ -198,9 +206,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (n + e < p.N) {
-          float x = p.alpha * v[e];
-          if (p.beta != 0.f) x += p.beta * crow[e];
-          v[e] = apply_epilogue_t<EPI>(x, m, n + e, p.N, p.ep);
+          float x = alpha * v[e];
+          if (beta != 0.f) x += beta * crow[e];
+          v[e] = apply_activation_t<EPI>(x + bias4[e], m, n + e, p.N, p.ep);
         }
       }
       if (vec_ok) *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
@@ -238,7 +246,7 @@ TcPlan plan_tc(int M, int N, int K) {
   const int64_t t128 = tm * dasa_cdiv(N, 128), t64 = tm * dasa_cdiv(N, 64);
   if (N <= 64) pl.bn = 64;
   else if (t128 >= 120) pl.bn = 128;
-  else if (t64 <= DASA_NUM_SMS) pl.bn = 64;
+  else if (t64 <= 2 * DASA_NUM_SMS) pl.bn = 64;     // two CTAs are resident per SM
   else pl.bn = 128;
   const int64_t tiles = tm * dasa_cdiv(N, pl.bn);
   const int nkb = (int)dasa_cdiv(K, TC_BK);
@@ -348,7 +356,15 @@ int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, c
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("DASA_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   TcParams p{M, N, K, alpha, beta, C, ldc, epilogue, ep, partial, pl.k_per_split, dbg};
-  int rc = (pl.bn == 128) ? launch_tc<128, 6>(ta, tb, p, pl.splits, st) : launch_tc<64, 8>(ta, tb, p, pl.splits, st);
+  // 3 x 32 KB / 4 x 24 KB stages = 96 KB of pipeline per CTA: two CTAs co-reside on an SM, so one CTA's epilogue and
+  // prologue overlap the other's main loop and a 192-tile problem needs no second wave.
+  // otherwise (one CTA per SM anyway) the deep 6/8-stage ring keeps 192 KB of loads in flight per SM.
+  const int64_t ctas = dasa_cdiv(M, TC_BM) * dasa_cdiv(N, pl.bn) * pl.splits;
+  int rc;
+  if (ctas > DASA_NUM_SMS)
+    rc = (pl.bn == 128) ? launch_tc<128, 3>(ta, tb, p, pl.splits, st) : launch_tc<64, 4>(ta, tb, p, pl.splits, st);
+  else
+    rc = (pl.bn == 128) ? launch_tc<128, 6>(ta, tb, p, pl.splits, st) : launch_tc<64, 8>(ta, tb, p, pl.splits, st);
   if (rc != DASA_OK) return rc;
   if (partial != nullptr) {
     const int64_t total = (int64_t)M * N;
