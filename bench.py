@@ -328,7 +328,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products in the dense projections)" if args.precision == "tf32" else "f32",
         "data": "synthetic",
         "config": {"workload": "agent_dg teacher-forced vl_rollout fwd+bwd+RMSprop, B=%d/GPU, T=%d, 36x2176 views, 80-token "
-                               "instructions, 9 la + 3 vl layers recomputed per action (BASELINE.json configs[1])" % (B, T),
+                               "instructions, 9 la + 3 vl layers evaluated for every action (the instruction-only la stack of the T actions batched "
+                               "into one pass, own dropout masks per action; nothing cached) (BASELINE.json configs[1])" % (B, T),
                    "precision": args.precision, "l2": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2",
                    "parallelism": "dp%d" % world,
                    "launch": "cuda-graph replay of the whole rollout" if state["graph"] is not None else

@@ -40,6 +40,19 @@ class DropoutSource:
         # draws different masks on every replay
         self.seed_dev = torch.tensor([int(seed)], dtype=torch.int64, device=device) if device_seed else None
 
+    def mask_steps(self, tag, shape, p, training, device, steps):
+        """Keep mask for `steps` consecutive rollout steps stacked along dim 0 (shape = per-step shape). With injected masks
+        the per-step tags 't<i>.<tag>' are concatenated, so batched and per-step evaluation see identical masks."""
+        if not training or p <= 0.0:
+            return None, 1.0
+        if self.injected is not None:
+            parts = [self.injected.get("%st%d.%s" % (self.prefix, i, tag)) for i in range(steps)]
+            if any(m is None for m in parts):
+                return None, 1.0
+            m = ops.as_keep_mask(torch.cat([x.to(device) for x in parts], 0))
+            return m, 1.0 / (1.0 - p)
+        return self.mask(tag, (shape[0] * steps,) + tuple(shape[1:]), p, training, device)
+
     def advance(self):
         """Start a new iteration: fresh masks (device-seed mode) and recycled pools."""
         self._pools = {}
@@ -383,7 +396,7 @@ class DicModel(nn.Module):
     def _out_ln(self, out_mod, x, resid, tag, training):
         p = self.cfg.bert_dropout
         y = ops.linear_fwd(x, out_mod.dense.weight, out_mod.dense.bias)
-        m, s = _source.mask(tag, y.shape, p, training, y.device)
+        m, s = self._mask(tag, (y.shape[0] // self._steps,) + tuple(y.shape[1:]), training, y.device)
         return ops.dropout_residual_layernorm(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias,
                                               out_mod.LayerNorm.eps, m, s)
 
@@ -393,7 +406,7 @@ class DicModel(nn.Module):
         w, b = self._qkv(att_mod.self)
         qkv = ops.linear_fwd(x, w, b)
         B, L = x.shape[0], x.shape[1]
-        m, s = _source.mask(tag + ".probs", (B, cfg.bert_heads, L, L), cfg.bert_dropout, training, x.device)
+        m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, L, L), training, x.device)
         o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s)
         return self._out_ln(att_mod.output, o, x, tag + ".out", training)
 
@@ -413,17 +426,33 @@ class DicModel(nn.Module):
         return self._out_ln(out_mod, y, x, tag, training)
 
     @torch.no_grad()
-    def language_stack(self, input_ids, pad_mask, training):
-        """BertEmbeddings + la_layers x BertLayer (vilmodel.py:1366-1378). pad_mask: uint8 [B, L], 1 = padding."""
+    def language_stack(self, input_ids, pad_mask, training, steps=1):
+        """BertEmbeddings + la_layers x BertLayer (vilmodel.py:1366-1378). pad_mask: uint8 [B, L], 1 = padding.
+        steps > 1 evaluates the stack for `steps` rollout actions at once: the instruction does not depend on the action
+        taken, so the T per-action evaluations of the reference (agent_dg.py:789-797, each with its own dropout masks) are
+        batched along dim 0 -> [steps*B, L, hid]. Same arithmetic per (action, episode); nothing is cached or skipped."""
         cfg, e = self.cfg, self.embeddings
+        if steps > 1:
+            input_ids = input_ids.repeat(steps, 1)
+            pad_mask = pad_mask.repeat(steps, 1)
         B, L = input_ids.shape
-        m, s = _source.mask("enc.emb", (B, L, cfg.bert_hidden), cfg.bert_dropout, training, input_ids.device)
+        self._steps = steps
+        m, s = self._mask("enc.emb", (B // steps, L, cfg.bert_hidden), training, input_ids.device)
         x = ops.embed_layernorm(input_ids, e.word_embeddings.weight, e.position_embeddings.weight,
                                 e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps, m, s)
         for i, layer in enumerate(self.lalayer):
             a = self._self_att(layer.attention, x, pad_mask, "enc.la%d.att" % i, training)
             x = self._ffn(layer.intermediate, layer.output, a, "enc.la%d.ffn" % i, training)
+        self._steps = 1
         return x
+
+    _steps = 1
+
+    def _mask(self, tag, shape, training, device):
+        """Dropout mask for one step, or for `self._steps` stacked steps while the batched language stack runs."""
+        if self._steps > 1:
+            return _source.mask_steps(tag, shape, self.cfg.bert_dropout, training, device, self._steps)
+        return _source.mask(tag, shape, self.cfg.bert_dropout, training, device)
 
     @torch.no_grad()
     def cross_modal(self, lang, pad_mask, img_feats, training):
@@ -473,15 +502,25 @@ class DicEncoder(nn.Module):
         self.cache_language = False     # exact in eval mode; opt-in
         self._lang_cache = None
 
-    def forward(self, inputs, mask, lengths, f_t_all=None):
+    def language_for_rollout(self, inputs, mask, steps):
+        """The language stack for `steps` actions in one batched pass -> [steps, B, L, hid] (see DicModel.language_stack)."""
+        L = mask.size(1)
+        pad = mask.to(torch.uint8).contiguous()
+        out = self.bert.language_stack(inputs[:, :L].contiguous(), pad, self.training, steps)
+        return out.view(steps, inputs.shape[0], L, -1)
+
+    def forward(self, inputs, mask, lengths, f_t_all=None, lang_out=None):
         """inputs [B, maxInput] int64, mask [B, Lmax] bool (True = pad), lengths [B] (sorted desc), f_t_all [B, 36, F]
-        -> (ctx [B, Lmax, 2H], decoder_init [B, Hd], c_t [B, Hd], mask, vision_outputs [B, 36, 768])."""
+        -> (ctx [B, Lmax, 2H], decoder_init [B, Hd], c_t [B, Hd], mask, vision_outputs [B, 36, 768]).
+        lang_out (optional extension): this action's language-stack output from language_for_rollout()."""
         tr = self.training
         L = mask.size(1)
         pad = mask.to(torch.uint8).contiguous()
         ids = inputs[:, :L]
         key = (inputs.data_ptr(), L, inputs._version)
-        if self.cache_language and not tr and self._lang_cache is not None and self._lang_cache[0] == key:
+        if lang_out is not None:
+            lang0 = lang_out
+        elif self.cache_language and not tr and self._lang_cache is not None and self._lang_cache[0] == key:
             lang0 = self._lang_cache[1]
         else:
             lang0 = self.bert.language_stack(ids, pad, tr)

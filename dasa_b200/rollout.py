@@ -62,6 +62,7 @@ class NavPolicy:
         self.models = (self.encoder, self.decoder, self.critic, self.adaIn)
         self._opt = None
         self._flat = None
+        self.batch_language = True     # evaluate the 9 language layers for all T actions of a rollout in one batched pass
 
     def train(self):
         for m in self.models:
@@ -84,7 +85,7 @@ class NavPolicy:
                     p.grad.zero_()
 
     # ------------------------------------------------------------------------------------------------ one nav step
-    def step(self, ep, t, carry):
+    def step(self, ep, t, carry, lang_out=None):
         """Loop body of vl_rollout up to the masked logits (agent_dg.py:727-841). carry = None at t == 0."""
         cfg, tr = self.cfg, self.decoder.training
         a_t, f_t, d_t, cand, cand_d, leng, _ = ep.step(t)
@@ -95,7 +96,7 @@ class NavPolicy:
         m_c, s_c = src.mask("dec.cand", (B, cand.shape[1], C), cfg.featdropout, tr, f_t.device)
         df_t = self.adaIn.gate_features(f_t, d_t, m_f, s_f)                 # K1 views
         cand_g = self.adaIn.gate_features(cand, cand_d, m_c, s_c)           # K1 candidates
-        ctx, en_h, en_c, _, _ = self.encoder(ep.seq, ep.seq_mask, ep.seq_lengths, f_t_all=f_t)   # sees the RAW f_t
+        ctx, en_h, en_c, _, _ = self.encoder(ep.seq, ep.seq_mask, ep.seq_lengths, f_t_all=f_t, lang_out=lang_out)   # RAW f_t
         prev_h1, c_0 = (en_h, en_c) if carry is None else carry
         h_t, c_t, logit, h1, _ = self.decoder(a_t, df_t, cand_g, prev_h1, prev_h1, c_0, ctx, ep.seq_mask,
                                               already_dropfeat=True, cand_leng=leng)
@@ -109,10 +110,12 @@ class NavPolicy:
         carry, total, logits, actions = None, None, [], []
         src = M.dropout_source()
         base_prefix = src.prefix
+        # the instruction-only language stack of all T actions in one batched pass (per-action dropout masks preserved)
+        lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T) if self.batch_language else None
         for t in range(T):
             if tag_steps:
                 src.prefix = base_prefix + "t%d." % t
-            logit, h_t, carry = self.step(ep, t, carry)
+            logit, h_t, carry = self.step(ep, t, carry, None if lang_all is None else lang_all[t])
             loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.target_at(t), self.cfg.ignore_id)
             total = loss_t if total is None else total + loss_t
             logits.append(logit)
