@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-micro", action="store_true")
+    ap.add_argument("--schedule", default="batched", choices=["batched", "sequential"],
+                    help="batched: AdaIN + encoder of all T teacher-forced actions as one batch; sequential: per action")
+    ap.add_argument("--skip-sequential", action="store_true", help="do not also time the per-action schedule")
     return ap.parse_args()
 
 
@@ -214,6 +217,7 @@ def run_ours(args):
 
     cfg, B, T = FULL, args.batch, args.actions
     pol = NavPolicy(cfg, synth.policy_state(cfg, 0), dev).train()
+    pol.schedule = args.schedule
     pol.flatten_parameters()
     from dasa_b200 import dist as ddist
     ddist.broadcast_(pol.param_buffers(), world)
@@ -303,6 +307,25 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(True, True, max(1, args.steps // 2), 1)
     Fn.invalidate_weight_caches()
+    # the same workload on the per-action schedule (the order a sampled / greedy rollout is forced to use)
+    ms_seq = None
+    if args.schedule == "batched" and not args.skip_sequential:
+        state["graph"], state["loss"] = None, None
+        pol.schedule = "sequential"
+        torch.cuda.synchronize()
+        try:
+            for _ in range(2):
+                one_step(ep_res, False)
+            torch.cuda.synchronize()
+            if not args.no_graph:
+                capture()
+            ms_seq, _ = timed(False, False, max(1, args.steps // 2), 1)
+        except Exception as e:
+            ms_seq = None
+            state["graph_error"] = repr(e)[:200]
+        state["graph"] = None
+        pol.schedule = args.schedule
+        Fn.invalidate_weight_caches()
 
     nav = B * T * world
     value = nav / (ms_step * 1e-3)
@@ -332,12 +355,17 @@ def run_ours(args):
                                "into one pass, own dropout masks per action; nothing cached) (BASELINE.json configs[1])" % (B, T),
                    "precision": args.precision, "l2": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2",
                    "parallelism": "dp%d" % world,
+                   "schedule": ("batched: the agent follows the teacher, so all T observations are known up front and AdaIN + "
+                                "cross-modal layers + bi-LSTM of the T actions run as one batch; decoder sequential"
+                                if args.schedule == "batched" else "sequential: AdaIN -> encoder -> decoder per action"),
                    "launch": "cuda-graph replay of the whole rollout" if state["graph"] is not None else
                              "eager launches (%s)" % (state["graph_error"] or "--no-graph")},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "nav steps/s", "h2d_bytes_per_step": host_ep.h2d_bytes_per_step() * T,
                 "d2h_bytes_per_step": 4},
         "roofline": roof, "kernels": extra, "cpu_baseline": cpu,
+        "sequential_schedule": None if ms_seq is None else {"value": nav / (ms_seq * 1e-3), "unit": "nav steps/s",
+                                                             "ms_per_step": ms_seq},
     }
     print(json.dumps(line))
     if world > 1:

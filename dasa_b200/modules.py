@@ -417,7 +417,7 @@ class DicModel(nn.Module):
         w, b = self._qkv(xatt.att, "kv")
         kv = ops.linear_fwd(ctx, w, b)
         B, Lq, Lk = x.shape[0], x.shape[1], ctx.shape[1]
-        m, s = _source.mask(tag + ".probs", (B, cfg.bert_heads, Lq, Lk), cfg.bert_dropout, training, x.device)
+        m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
         o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s)
         return self._out_ln(xatt.output, o, x, tag + ".out", training)
 
@@ -455,11 +455,20 @@ class DicModel(nn.Module):
         return _source.mask(tag, shape, self.cfg.bert_dropout, training, device)
 
     @torch.no_grad()
-    def cross_modal(self, lang, pad_mask, img_feats, training):
-        """VisionEncoder + vl_layers x LXRTXLayer (vilmodel.py:1383-1410)."""
+    def cross_modal(self, lang, pad_mask, img_feats, training, steps=1):
+        """VisionEncoder + vl_layers x LXRTXLayer (vilmodel.py:1383-1410). steps > 1: the inputs hold `steps` rollout actions
+        stacked along dim 0 (teacher-forced rollouts know every observation up front); per-action dropout masks are kept."""
+        cfg, ve = self.cfg, self.vision_encoder
+        self._steps = steps
+        try:
+            return self._cross_modal(lang, pad_mask, img_feats, training)
+        finally:
+            self._steps = 1
+
+    def _cross_modal(self, lang, pad_mask, img_feats, training):
         cfg, ve = self.cfg, self.vision_encoder
         v = ops.linear_fwd(img_feats, ve.visn_fc.weight, ve.visn_fc.bias)
-        m, s = _source.mask("enc.visn", v.shape, cfg.bert_dropout, training, v.device)
+        m, s = self._mask("enc.visn", (v.shape[0] // self._steps,) + tuple(v.shape[1:]), training, v.device)
         visn = ops.dropout_residual_layernorm(v, None, ve.visn_layer_norm.weight, ve.visn_layer_norm.bias, 1e-12,
                                               None, 1.0, m, s)
         for i, layer in enumerate(self.addlayer):
@@ -508,6 +517,32 @@ class DicEncoder(nn.Module):
         pad = mask.to(torch.uint8).contiguous()
         out = self.bert.language_stack(inputs[:, :L].contiguous(), pad, self.training, steps)
         return out.view(steps, inputs.shape[0], L, -1)
+
+    def encode_rollout(self, inputs, mask, lengths, f_all, steps, lang_all=None):
+        """Encoder for `steps` actions of a TEACHER-FORCED rollout in one batch (the trajectory, hence every panorama, is
+        independent of the policy's outputs): f_all [steps*B, 36, F] -> (ctx [steps*B, L, 2H], decoder_init [B, Hd], c_t [B, Hd])
+        where the decoder initial state comes from action 0 (agent_dg.py:812-815). Per-action dropout masks are preserved."""
+        tr = self.training
+        B, L = inputs.shape[0], mask.size(1)
+        pad = mask.to(torch.uint8).contiguous()
+        if lang_all is None:
+            lang_all = self.bert.language_stack(inputs[:, :L].contiguous(), pad, tr, steps)
+        lang_all = lang_all.reshape(steps * B, L, -1)
+        pad_all = pad.repeat(steps, 1)
+        lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps)
+        len32 = torch.as_tensor(lengths, device=lang.device).to(torch.int32).repeat(steps)
+        rev = ops.reverse_tokens(lang, len32)
+        l = self.lstm
+        ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0,
+                                              l.weight_ih_l0_reverse, l.weight_hh_l0_reverse, l.bias_ih_l0_reverse,
+                                              l.bias_hh_l0_reverse)
+        h_cat = torch.cat((h_fin[1, :B], h_fin[0, :B]), 1)
+        c_cat = torch.cat((c_fin[1, :B], c_fin[0, :B]), 1)
+        decoder_init = Fn.linear(h_cat, self.encoder_lstm2decoder_ht.weight, self.encoder_lstm2decoder_ht.bias, "tanh")
+        c_t = Fn.linear(c_cat, self.encoder_lstm2decoder_ct.weight, self.encoder_lstm2decoder_ct.bias)
+        m, sc = _source.mask_steps("enc.ctx", (B,) + tuple(ctx.shape[1:]), self.dropout_ratio, tr, ctx.device, steps)
+        ctx = Fn.dropout(ctx, m, sc)
+        return ctx, decoder_init, c_t
 
     def forward(self, inputs, mask, lengths, f_t_all=None, lang_out=None):
         """inputs [B, maxInput] int64, mask [B, Lmax] bool (True = pad), lengths [B] (sorted desc), f_t_all [B, 36, F]

@@ -62,6 +62,7 @@ class NavPolicy:
         self.models = (self.encoder, self.decoder, self.critic, self.adaIn)
         self._opt = None
         self._flat = None
+        self.schedule = "batched"      # teacher-forced rollouts: see teacher_rollout()
         self.batch_language = True     # evaluate the 9 language layers for all T actions of a rollout in one batched pass
 
     def train(self):
@@ -103,13 +104,52 @@ class NavPolicy:
         return logit, h_t, (h1, c_t)
 
     # ------------------------------------------------------------------------------------------- teacher-forced rollout
-    def teacher_rollout(self, ep, T=None, ml_weight=0.4, tag_steps=True):
+    def teacher_rollout(self, ep, T=None, ml_weight=0.4, tag_steps=True, schedule=None):
         """feedback='teacher', train_rl=False (agent_dg.py:1368-1370): returns (loss tensor [1], logits list, actions list).
-        loss = sum_t CE_sum(logit_t, target_t) * ml_weight / B  (agent_dg.py:850, 1024)."""
+        loss = sum_t CE_sum(logit_t, target_t) * ml_weight / B  (agent_dg.py:850, 1024).
+
+        schedule 'sequential': every action runs AdaIN -> encoder -> decoder in turn, as the reference loop does (the only
+          order possible when the next observation depends on the sampled / greedy action).
+        schedule 'batched' (default for teacher forcing): the agent follows the teacher, so the trajectory and all T
+          observations are known up front; AdaIN gates, the cross-modal layers and the bi-LSTM of all T actions run as ONE
+          batch of T*B sequences (identical per-(action, episode) arithmetic and dropout masks), only the recurrent decoder
+          stays sequential."""
         T = ep.T if T is None else T
-        carry, total, logits, actions = None, None, [], []
+        schedule = schedule or self.schedule
         src = M.dropout_source()
         base_prefix = src.prefix
+        cfg, tr = self.cfg, self.decoder.training
+        carry, total, logits, actions = None, None, [], []
+        if schedule == "batched" and ep.resident:
+            B, C = ep.B, cfg.rgb_size
+            f_all = ep.f_t[:T].reshape(T * B, cfg.views, cfg.feat)
+            d_all = ep.d_t[:T].reshape(T * B, cfg.views, cfg.feat)
+            nc = ep.cand_feat.shape[2]
+            cand_all = ep.cand_feat[:T].reshape(T * B, nc, cfg.feat)
+            candd_all = ep.cand_dfeat[:T].reshape(T * B, nc, cfg.feat)
+            dev = f_all.device
+            m_f, s_f = src.mask_steps("dec.feat", (B, cfg.views, C), cfg.featdropout, tr, dev, T)
+            m_c, s_c = src.mask_steps("dec.cand", (B, nc, C), cfg.featdropout, tr, dev, T)
+            df_all = self.adaIn.gate_features(f_all, d_all, m_f, s_f)                 # K1, all actions
+            candg_all = self.adaIn.gate_features(cand_all, candd_all, m_c, s_c)
+            ctx_all, en_h, en_c = self.encoder.encode_rollout(ep.seq, ep.seq_mask, ep.seq_lengths, f_all, T)
+            L = ctx_all.shape[1]
+            ctx_steps = ctx_all.view(T, B, L, -1).unbind(0)          # unbind: one stacked gradient instead of T zero-filled ones
+            df_steps = df_all.view(T, B, cfg.views, cfg.feat).unbind(0)
+            cand_steps = candg_all.view(T, B, nc, cfg.feat).unbind(0)
+            for t in range(T):
+                if tag_steps:
+                    src.prefix = base_prefix + "t%d." % t
+                prev_h1, c_0 = (en_h, en_c) if carry is None else carry
+                h_t, c_t, logit, h1, _ = self.decoder(ep.input_a_t[t], df_steps[t], cand_steps[t], prev_h1, prev_h1, c_0,
+                                                      ctx_steps[t], ep.seq_mask, already_dropfeat=True, cand_leng=ep.cand_leng[t])
+                carry = (h1, c_t)
+                loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.target_at(t), cfg.ignore_id)
+                total = loss_t if total is None else total + loss_t
+                logits.append(logit)
+                actions.append(a_t)
+            src.prefix = base_prefix
+            return total * (ml_weight / ep.B), logits, actions
         # the instruction-only language stack of all T actions in one batched pass (per-action dropout masks preserved)
         lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T) if self.batch_language else None
         for t in range(T):

@@ -276,7 +276,7 @@ def test_dropout_mask_rate_and_determinism():
     assert not torch.equal(m1, ops.dropout_mask((1 << 20,), 0.4, 8, 0))
 
 
-@pytest.mark.parametrize("B,L,In,H", [(3, 9, 96, 128), (20, 24, 768, 128), (20, 80, 768, 1024), (7, 33, 64, 64)])
+@pytest.mark.parametrize("B,L,In,H", [(3, 9, 96, 128), (20, 24, 768, 128), (20, 80, 768, 1024), (7, 33, 64, 64), (45, 11, 96, 128)])
 def test_bilstm_fused_fwd_bwd(B, L, In, H):
     """Fused per-step bi-LSTM kernels (packed-sequence semantics, ragged lengths) against the oracle + autograd."""
     gen = g(17 + B)

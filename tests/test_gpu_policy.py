@@ -75,6 +75,9 @@ def test_small_golden_modules():
         assert_close(htl, g["dec_htilde"], 1e-4, "dec h_tilde")
         assert_close(pol.critic(h1), g["critic"], 1e-4, "critic")
         loss, logits, actions = pol.teacher_rollout(dep, 4)
+        loss_s, logits_s, actions_s = pol.teacher_rollout(dep, 4, schedule="sequential")
+    assert_close(loss_s, g["rollout_eval_loss"], 1e-4, "sequential-schedule loss")
+    assert torch.equal(torch.stack(actions_s), torch.stack(actions))
     lg = torch.stack(logits).cpu()
     fin = torch.isfinite(g["rollout_eval_logits"])
     assert torch.equal(torch.isfinite(lg), fin)
@@ -142,8 +145,9 @@ def _train_masks(cfg, B, T, L, nc, seed):
     return keep
 
 
+@pytest.mark.parametrize("schedule", ["batched", "sequential"])
 @pytest.mark.parametrize("cfg,B,T", [(SMALL, 3, 3)])
-def test_train_rollout_loss_and_gradients(cfg, B, T):
+def test_train_rollout_loss_and_gradients(cfg, B, T, schedule):
     """Train-mode teacher-forced rollout with injected dropout masks: loss, logits and every parameter gradient of the
     train configuration (adaIn, decoder, bi-LSTM + init linears) against oracle autograd."""
     st = synth.policy_state(cfg, 1)
@@ -159,7 +163,7 @@ def test_train_rollout_loss_and_gradients(cfg, B, T):
     dep = DeviceEpisodes(ep)
     src = M.DropoutSource(injected={k: m for k, (m, p) in keep.items()})
     with M.use_dropout_source(src):
-        loss2, logits2, _ = pol.teacher_rollout(dep, T)
+        loss2, logits2, _ = pol.teacher_rollout(dep, T, schedule=schedule)
     assert_close(loss2, loss, 1e-4, "train loss")
     lg, lg2 = torch.stack(logits).detach(), torch.stack(logits2).detach().cpu()
     fin = torch.isfinite(lg)
