@@ -335,6 +335,159 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
   }
 }
 
+// ---- tensor-core variant (precision mode tf32): S = Q K^T and O = P V on mma.sync.m16n8k8 TF32, fp32 accumulate ----------
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int MHA_TC_THREADS = 128;
+constexpr int MHA_TC_MAXNT = 12;     // key tiles of 8 -> Lk <= 96
+
+__host__ __device__ inline int mha_tc_pstride(int LkP) { return LkP + ((36 - (LkP & 31)) & 31); }   // stride % 32 == 4
+
+// one CTA per (sample, head); warp w owns query m-tiles w, w+4, ... (16 rows each)
+__global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
+  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh;
+  const int LqP = (Lq + 15) & ~15, LkP = (Lk + 7) & ~7;
+  const int QS = dh + 4, VS = dh + 8, PS = mha_tc_pstride(LkP);
+  uint32_t* Qs = reinterpret_cast<uint32_t*>(smem);          // [LqP][QS]  tf32 bit patterns
+  uint32_t* Ks = Qs + LqP * QS;                              // [LkP][QS]
+  uint32_t* Vs = Ks + LkP * QS;                              // [LkP][VS]
+  uint32_t* Ps = Vs + LkP * VS;                              // [LqP][PS]
+  const float* qb = a.q + (int64_t)b * a.sq + h * dh;
+  const float* kb = a.k + (int64_t)b * a.sk + h * dh;
+  const float* vb = a.v + (int64_t)b * a.sv + h * dh;
+  const int d4n = dh >> 2;
+  for (int i = threadIdx.x; i < LqP * d4n; i += MHA_TC_THREADS) {
+    const int r = i / d4n, c = i % d4n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < Lq) v = *reinterpret_cast<const float4*>(qb + (int64_t)r * a.ldq + 4 * c);
+    *reinterpret_cast<uint4*>(Qs + r * QS + 4 * c) = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
+  }
+  for (int i = threadIdx.x; i < LkP * d4n; i += MHA_TC_THREADS) {
+    const int r = i / d4n, c = i % d4n;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (r < Lk) {
+      kv = *reinterpret_cast<const float4*>(kb + (int64_t)r * a.ldk + 4 * c);
+      vv = *reinterpret_cast<const float4*>(vb + (int64_t)r * a.ldv + 4 * c);
+    }
+    *reinterpret_cast<uint4*>(Ks + r * QS + 4 * c) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
+    *reinterpret_cast<uint4*>(Vs + r * VS + 4 * c) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nkt = LkP >> 3;                                  // key tiles
+  const float scale = rsqrtf((float)dh);
+  const uint8_t* pad = a.key_pad ? a.key_pad + (int64_t)b * a.ld_pad : nullptr;
+  for (int mt = warp; mt * 16 < Lq; mt += MHA_TC_THREADS / 32) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    float acc[MHA_TC_MAXNT][4];
+#pragma unroll
+    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    for (int k0 = 0; k0 < dh; k0 += 8) {
+      const uint32_t a0 = Qs[r0 * QS + k0 + t], a1 = Qs[r1 * QS + k0 + t], a2 = Qs[r0 * QS + k0 + t + 4], a3 = Qs[r1 * QS + k0 + t + 4];
+#pragma unroll
+      for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+        if (nt < nkt) {
+          const uint32_t b0 = Ks[(nt * 8 + g) * QS + k0 + t], b1 = Ks[(nt * 8 + g) * QS + k0 + t + 4];
+          mma_m16n8k8_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+    // scores -> masked softmax per row; a row lives in the 4 lanes sharing g (cols 2t, 2t+1 of every key tile)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+      if (nt < nkt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          float add = 0.f;
+          const bool ok = j < Lk;
+          if (ok && pad != nullptr && pad[j]) add = -10000.0f;
+          acc[nt][e] = ok ? acc[nt][e] * scale + add : -INFINITY;
+          acc[nt][2 + e] = ok ? acc[nt][2 + e] * scale + add : -INFINITY;
+          mx0 = fmaxf(mx0, acc[nt][e]);
+          mx1 = fmaxf(mx1, acc[nt][2 + e]);
+        }
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+      if (nt < nkt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          acc[nt][e] = (acc[nt][e] == -INFINITY) ? 0.f : expf(acc[nt][e] - mx0);
+          acc[nt][2 + e] = (acc[nt][2 + e] == -INFINITY) ? 0.f : expf(acc[nt][2 + e] - mx1);
+          s0 += acc[nt][e];
+          s1 += acc[nt][2 + e];
+        }
+      }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float inv0 = 1.f / s0, inv1 = 1.f / s1;
+    const int64_t pb0 = (((int64_t)b * a.heads + h) * Lq + r0) * Lk, pb1 = (((int64_t)b * a.heads + h) * Lq + r1) * Lk;
+#pragma unroll
+    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+      if (nt < nkt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          float p0 = acc[nt][e] * inv0, p1 = acc[nt][2 + e] * inv1;
+          if (j < Lk) {
+            if (r0 < Lq) {
+              if (a.probs_out != nullptr) a.probs_out[pb0 + j] = p0;
+              if (a.drop_mask != nullptr) p0 *= a.drop_mask[pb0 + j] ? a.drop_scale : 0.f;
+            }
+            if (r1 < Lq) {
+              if (a.probs_out != nullptr) a.probs_out[pb1 + j] = p1;
+              if (a.drop_mask != nullptr) p1 *= a.drop_mask[pb1 + j] ? a.drop_scale : 0.f;
+            }
+          } else { p0 = 0.f; p1 = 0.f; }
+          Ps[r0 * PS + j] = f2tf32(p0);
+          Ps[r1 * PS + j] = f2tf32(p1);
+        }
+      }
+    }
+    __syncwarp();
+    // O = P V for this m-tile: 8 head-dim tiles of 8
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+    for (int k0 = 0; k0 < LkP; k0 += 8) {
+      const uint32_t a0 = Ps[r0 * PS + k0 + t], a1 = Ps[r1 * PS + k0 + t], a2 = Ps[r0 * PS + k0 + t + 4], a3 = Ps[r1 * PS + k0 + t + 4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (nt * 8 < dh) {
+          const uint32_t b0 = Vs[(k0 + t) * VS + nt * 8 + g], b1 = Vs[(k0 + t + 4) * VS + nt * 8 + g];
+          mma_m16n8k8_tf32(o[nt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+    float* ob = a.out + (int64_t)b * a.so + h * dh;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt * 8 < dh) {
+        const int d = nt * 8 + 2 * t;
+        if (r0 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r0 * a.ldo + d) = make_float2(o[nt][0], o[nt][1]);
+        if (r1 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r1 * a.ldo + d) = make_float2(o[nt][2], o[nt][3]);
+      }
+    }
+  }
+}
+
 struct MhaBwdArgs {
   const float *q, *k, *v; int64_t ldq, sq, ldk, sk, ldv, sv;
   const float* probs; const uint8_t* drop_mask; float drop_scale;
@@ -484,8 +637,22 @@ extern "C" int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* 
 extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                             int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
                             float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out, int B, int heads, int Lq,
-                            int Lk, int dh, void* stream) {
+                            int Lk, int dh, int precision, void* stream) {
   if (B <= 0 || heads <= 0) return DASA_OK;
+  if (precision == DASA_PREC_TF32 && Lq > 0 && Lk > 0 && Lk <= 8 * MHA_TC_MAXNT && dh % 8 == 0 && dh <= 64 && dasa_aligned16(q) &&
+      dasa_aligned16(k) && dasa_aligned16(v) && !(ldq % 4 || ldk % 4 || ldv % 4 || sq % 4 || sk % 4 || sv % 4) &&
+      dasa_aligned16(out) && !(ldo % 2 || so % 2)) {
+    const int LqP = (Lq + 15) & ~15, LkP = (Lk + 7) & ~7;
+    const size_t smem_tc = sizeof(float) * ((size_t)LqP * (dh + 4) + (size_t)LkP * (dh + 4) + (size_t)LkP * (dh + 8) +
+                                            (size_t)LqP * mha_tc_pstride(LkP));
+    if (smem_tc <= 227 * 1024) {
+      cudaError_t e2 = cudaFuncSetAttribute(mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+      if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc attr", e2); return DASA_ERR_CUDA; }
+      MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh};
+      mha_fwd_tc_kernel<<<(unsigned)(B * heads), MHA_TC_THREADS, smem_tc, (cudaStream_t)stream>>>(at);
+      return dasa_check_launch("mha_fwd_tc_kernel");
+    }
+  }
   if (Lq <= 0 || Lk <= 0 || dh <= 0) return DASA_ERR_BAD_SHAPE;
   if (Lk > 96 || dh > 64 || dh % 4 != 0) return DASA_ERR_UNSUPPORTED;
   if (!dasa_aligned16(q) || !dasa_aligned16(k) || !dasa_aligned16(v) || ldq % 4 || ldk % 4 || ldv % 4 || sq % 4 || sk % 4 || sv % 4)

@@ -143,21 +143,27 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, i
   C[(int64_t)m * ldc + n] = apply_epilogue(v, m, n, N, epilogue, ep);
 }
 
-__global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out, int accumulate) {
-  // one warp-column-group per 32 columns; 8 row-lanes per block reduce through shared memory
+// out[n] (+)= sum_m X[m, n]: grid (N/32 column groups, row slabs); 32x8 threads; slabs combine with one atomicAdd per column
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out, int rows_per_slab) {
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
   float s = 0.f;
   if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += X[(int64_t)m * ldx + n];
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) s += X[(int64_t)m * ldx + n];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[n] = accumulate ? out[n] + t : t;
+    atomicAdd(out + n, t);
   }
+}
+
+__global__ void zero_kernel(float* __restrict__ p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
 }
 
 struct SimtPlan { bool skinny; int splits; int k_per_split; };
@@ -241,6 +247,18 @@ int dasa_gemm_simt(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha,
 
 extern "C" int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out, int accumulate, void* stream) {
   if (N <= 0) return DASA_OK;
-  colsum_kernel<<<(unsigned)dasa_cdiv(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, N, out, accumulate);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    zero_kernel<<<(unsigned)dasa_cdiv(N, 256), 256, 0, st>>>(out, N);
+    if (dasa_check_launch("zero_kernel") != DASA_OK) return DASA_ERR_CUDA;
+  }
+  if (M <= 0) return DASA_OK;
+  const int col_groups = (int)dasa_cdiv(N, 32);
+  int slabs = (int)dasa_cdiv(4 * DASA_NUM_SMS, col_groups);          // ~4 CTAs per SM in total
+  const int max_slabs = (int)dasa_cdiv(M, 64);
+  slabs = slabs < 1 ? 1 : (slabs > max_slabs ? max_slabs : slabs);
+  const int rows_per_slab = (int)dasa_cdiv(M, slabs);
+  dim3 grid((unsigned)col_groups, (unsigned)dasa_cdiv(M, rows_per_slab));
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(X, ldx, M, N, out, rows_per_slab);
   return dasa_check_launch("colsum_kernel");
 }

@@ -251,8 +251,8 @@ TcPlan plan_tc(int M, int N, int K) {
   const int64_t tiles = tm * dasa_cdiv(N, pl.bn);
   const int nkb = (int)dasa_cdiv(K, TC_BK);
   int s = 1;
-  if (tiles * 2 <= DASA_NUM_SMS && nkb >= 64) {
-    s = (int)(DASA_NUM_SMS / tiles);
+  if (tiles * 2 <= 2 * DASA_NUM_SMS && nkb >= 64) {     // two CTAs are resident per SM (4-stage variant)
+    s = (int)(2 * DASA_NUM_SMS / tiles);
     s = s > nkb / 16 ? nkb / 16 : s;
     s = s < 1 ? 1 : (s > 16 ? 16 : s);
   }

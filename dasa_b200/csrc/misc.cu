@@ -54,9 +54,34 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// 16 keep flags per thread: four 64-bit hashes, one byte lane each 16 bits -> one 128-bit store
+__device__ __forceinline__ uint64_t hash64(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ void mask_fill(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+  const uint32_t thr = (uint32_t)(p * 65536.0f);                       // keep iff 16-bit uniform >= p
+  const int64_t n16 = n >> 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t h = hash64(seed, offset + (uint64_t)(4 * i + q));
+      w[q] = ((uint32_t)(h & 0xFFFF) >= thr ? 1u : 0u) | (((uint32_t)((h >> 16) & 0xFFFF) >= thr ? 1u : 0u) << 8) |
+             (((uint32_t)((h >> 32) & 0xFFFF) >= thr ? 1u : 0u) << 16) | (((uint32_t)(h >> 48) >= thr ? 1u : 0u) << 24);
+    }
+    reinterpret_cast<uint4*>(mask)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // tail (n not a multiple of 16)
+  for (int64_t i = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = (uint32_t)(hash64(seed ^ 0x5bd1e995u, offset + (uint64_t)i) & 0xFFFF) >= thr ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    mask[i] = hash_uniform(seed, offset + (uint64_t)i) >= p ? 1 : 0;
+  mask_fill(mask, n, p, seed, offset);
 }
 
 // one warp per sample: log-softmax over the (masked) candidate logits, CE with ignore_index, gradient, argmax
@@ -123,9 +148,7 @@ __global__ void bump_counter_kernel(unsigned long long* ctr, unsigned long long 
 
 __global__ void __launch_bounds__(256) dropout_mask_dev_kernel(uint8_t* __restrict__ mask, int64_t n, float p,
                                                                const unsigned long long* __restrict__ seed_dev, uint64_t offset) {
-  const uint64_t seed = seed_dev[0];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    mask[i] = hash_uniform(seed, offset + (uint64_t)i) >= p ? 1 : 0;
+  mask_fill(mask, n, p, seed_dev[0], offset);
 }
 
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
@@ -180,7 +203,8 @@ extern "C" int dasa_axpy2d(float a, const float* x, int64_t ldx, float* y, int64
 
 extern "C" int dasa_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
   if (n <= 0) return DASA_OK;
-  dropout_mask_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset);
+  if (reinterpret_cast<uintptr_t>(mask) & 15) return DASA_ERR_BAD_ALIGN;
+  dropout_mask_kernel<<<ew_grid(n / 16 + 1), 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset);
   return dasa_check_launch("dropout_mask_kernel");
 }
 
@@ -193,7 +217,8 @@ extern "C" int dasa_transpose(const float* in, int64_t ld_in, int rows, int cols
 
 extern "C" int dasa_dropout_mask_dev(uint8_t* mask, int64_t n, float p, const uint64_t* seed_dev, uint64_t offset, void* stream) {
   if (n <= 0) return DASA_OK;
-  dropout_mask_dev_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, n, p, reinterpret_cast<const unsigned long long*>(seed_dev), offset);
+  if (reinterpret_cast<uintptr_t>(mask) & 15) return DASA_ERR_BAD_ALIGN;
+  dropout_mask_dev_kernel<<<ew_grid(n / 16 + 1), 256, 0, (cudaStream_t)stream>>>(mask, n, p, reinterpret_cast<const unsigned long long*>(seed_dev), offset);
   return dasa_check_launch("dropout_mask_dev_kernel");
 }
 

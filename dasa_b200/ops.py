@@ -392,7 +392,7 @@ def mha_fwd(q, k, v, heads, key_pad=None, drop_mask=None, drop_scale=1.0, save_p
         key_pad = key_pad.to(torch.uint8)
     call("dasa_mha_fwd", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0),
          _p(key_pad), key_pad.stride(0) if key_pad is not None else 0, _p(drop_mask), float(drop_scale), _p(out), out.stride(1),
-         out.stride(0), _p(probs), B, heads, Lq, Lk, dh, _stream())
+         out.stride(0), _p(probs), B, heads, Lq, Lk, dh, _precision, _stream())
     return (out, probs) if save_probs else out
 
 

@@ -194,11 +194,12 @@ int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* z, const fl
 /* Multi-head attention for short sequences (vilmodel.py:203-236, 479-506): one CTA per (batch, head).
  *   q [B,Lq,*], k/v [B,Lk,*] with row strides ldq/ldk/ldv and sample strides sq/sk/sv (so fused QKV buffers are
  *   addressed in place); scores = q k^T / sqrt(dh) + (key_pad[b,j] ? -10000 : 0); softmax; optional keep mask on the
- *   probabilities [B,heads,Lq,Lk]; out[b,i,head*dh:(head+1)*dh] = P v. probs_out optional (for backward).          */
+ *   probabilities [B,heads,Lq,Lk]; out[b,i,head*dh:(head+1)*dh] = P v. probs_out optional (for backward).
+ *   precision DASA_PREC_TF32 runs Q K^T and P V on mma.sync TF32 tensor cores (softmax in fp32).                   */
 int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                  int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
                  float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out,
-                 int B, int heads, int Lq, int Lk, int dh, void* stream);
+                 int B, int heads, int Lq, int Lk, int dh, int precision, void* stream);
 int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                  int64_t ldv, int64_t sv, const float* probs, const uint8_t* drop_mask, float drop_scale,
                  const float* dout, int64_t ldo, int64_t so, float* dq, int64_t lddq, int64_t sdq, float* dk,

@@ -8,11 +8,13 @@ from dasa_b200.rollout import DeviceEpisodes, NavPolicy
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+SCHED = sys.argv[3] if len(sys.argv) > 3 else "batched"
 ops.set_precision(prec)
 import dasa_b200.functions as Fn
 Fn.defer_weight_grads(True)
 cfg = FULL
 pol = NavPolicy(cfg, synth.policy_state(cfg, 0)).train()
+pol.schedule = SCHED
 ep = DeviceEpisodes(synth.Episodes(20, T, cfg, seed=1))
 src = M.DropoutSource(seed=3)
 

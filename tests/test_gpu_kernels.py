@@ -346,3 +346,33 @@ def test_bilstm_tf32_tensor_core_path(B, L, In, H):
         errs[k] = rel_err(P[k].grad, sd[k].grad)
     print("tf32 bilstm errors:", {k: "%.2e" % v for k, v in errs.items()})
     assert max(errs.values()) <= 1e-2, errs
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("B,Lq,Lk", [(3, 45, 45), (2, 80, 36), (4, 36, 80), (2, 23, 23)])
+def test_mha_forward_both_precisions(prec, tol, B, Lq, Lk):
+    """BertSelfAttention / BertOutAttention core (vilmodel.py:203-236): padding mask (-10000), dropout keep mask, P.V."""
+    gen = g(31 + Lq + Lk)
+    heads, dh = 12, 64
+    Hd = heads * dh
+    q = torch.randn(B, Lq, Hd, generator=gen)
+    kv = torch.randn(B, Lk, 2 * Hd, generator=gen)          # fused K|V buffer: strided views
+    k, v = kv[..., :Hd], kv[..., Hd:]
+    lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), generator=gen)
+    pad = torch.arange(Lk)[None, :] >= lens[:, None]
+    keep = torch.rand(B, heads, Lq, Lk, generator=gen) >= 0.1
+    qh = q.view(B, Lq, heads, dh).permute(0, 2, 1, 3).double()
+    kh = k.reshape(B, Lk, heads, dh).permute(0, 2, 1, 3).double()
+    vh = v.reshape(B, Lk, heads, dh).permute(0, 2, 1, 3).double()
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh) + (pad.double() * -10000.0)[:, None, None, :]
+    p = torch.softmax(s, -1)
+    want = ((p * keep / 0.9) @ vh).permute(0, 2, 1, 3).reshape(B, Lq, Hd)
+    kvd = kv.to(DEV)
+    ops.set_precision(prec)
+    try:
+        out, probs = ops.mha_fwd(q.to(DEV), kvd[..., :Hd], kvd[..., Hd:], heads, pad.to(DEV), keep.to(torch.uint8).to(DEV), 1 / 0.9,
+                                 save_probs=True)
+    finally:
+        ops.set_precision("fp32")
+    assert_close(probs, p, tol, "probs")
+    assert_close(out, want, tol, "attention output")

@@ -261,6 +261,11 @@ def test_tf32_deferred_training_step_close_to_oracle():
             if want is None or float(want.abs().max()) == 0.0 or not prm.requires_grad:
                 continue
             e = rel_err(prm.grad, want)
-            worst = max(worst, e)
-            assert e <= 2e-2, "tf32 grad %s.%s rel err %.3e" % (grp, k, e)
-    print("worst tf32 gradient rel err %.3e" % worst)
+            gd, wd = prm.grad.detach().double().cpu(), want.double()
+            e2 = float((gd - wd).norm() / wd.norm())
+            worst = max(worst, e2)
+            # TF32 products (10-bit mantissa) through ~15 stacked GEMM/attention layers: gradients are held to 1e-2 in the
+            # L2 norm and 5e-2 element-wise (relative to the largest entry); forward outputs to 1e-2 element-wise.
+            assert e2 <= 1e-2, "tf32 grad %s.%s L2 rel err %.3e" % (grp, k, e2)
+            assert e <= 5e-2, "tf32 grad %s.%s max rel err %.3e" % (grp, k, e)
+    print("worst tf32 gradient L2 rel err %.3e" % worst)
