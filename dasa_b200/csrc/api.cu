@@ -10,6 +10,19 @@ void dasa_set_error(const char* what, cudaError_t e) {
   snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
 }
 
+void* dasa_tensormap_encoder() {
+  static void* fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = ptr;
+  }
+  return fn;
+}
+
 extern "C" int dasa_version(void) { return 101; }
 extern "C" const char* dasa_build_arch(void) { return "sm_100a"; }
 extern "C" const char* dasa_last_error(void) { return g_last_error; }

@@ -9,6 +9,8 @@
 #define DASA_NUM_SMS 148
 
 void dasa_set_error(const char* what, cudaError_t e);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no direct libcuda link dependency); nullptr if unavailable
+void* dasa_tensormap_encoder();
 
 static inline int dasa_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -4,6 +4,7 @@
 // dot products are exchanged through distributed shared memory, every CTA then owns the full 36/80-entry distribution
 // and produces its channel slice of the weighted sum from the tile it already holds. One read of ctx, no re-read.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -56,7 +57,13 @@ struct RowAttnArgs {
   int shift_k, headings; const float* kappa_logits; int64_t ld_kappa;
   float* wc; int64_t ld_wc; float* attn_out; float* q_out; float* kappa_out;
   int chunk;
+  int nbox, boxw;        // the channel slice is staged as nbox TMA boxes of [rows x boxw] floats (boxw <= 256, chunk = nbox*boxw)
 };
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 
 // stage the rows of this CTA's channel slice: warp 0 issues one bulk copy per unmasked row
 __device__ __forceinline__ void ra_issue_loads(const RowAttnSmem& s, const float* ctx_b, int64_t ld_row, int rows, int chunk,
@@ -132,8 +139,15 @@ __device__ __forceinline__ void ra_softmax_rows(const RowAttnSmem& s, int rows, 
   }
 }
 
-template <int CS>
-__global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(RowAttnArgs a) {
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Forward. Per CTA: (1) bulk-async stage the [rows x chunk] context slice and the target slice, (2) partial row dots into
+// LOCAL smem, (3) ONE full cluster barrier, (4) pull the peers' partials through DSMEM (fixed rank order => identical sums
+// everywhere), (5) arrive on the exit barrier (peers may still read our partials), softmax / shift, weighted sum from the
+// resident tile, (6) wait on the exit barrier. Only step (3) sits on the critical path.
+template <int CS, bool SHIFT>
+__global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap, RowAttnArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (CS == 1) ? 0 : (int)cluster.block_rank();
@@ -142,35 +156,99 @@ __global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(RowAttnAr
   const RowAttnSmem s = ra_carve(smem_raw, rows, chunk, CS);
   const int c0 = rank * chunk;
   const int cn = max(0, min(chunk, a.D - c0));
-  const uint8_t* mask_b = a.mask ? a.mask + (int64_t)b * a.ld_mask : nullptr;
+  const uint8_t* mask_b = (!SHIFT && a.mask) ? a.mask + (int64_t)b * a.ld_mask : nullptr;
   const float* ctx_b = a.ctx + (int64_t)b * a.ld_sample;
+  const float* t_b = a.t + (int64_t)b * a.ld_t + c0;
+  const bool t_bulk = ((reinterpret_cast<uintptr_t>(t_b) & 15) == 0) && cn > 0;
 
-  if (threadIdx.x == 0) { mbar_init(s.bar, 1); mbar_fence_init(); }
-  __syncthreads();
-  ra_issue_loads(s, ctx_b, a.ld_row, rows, chunk, c0, cn, mask_b);
-  for (int c = threadIdx.x; c < cn; c += RA_THREADS) s.tv[c] = a.t[(int64_t)b * a.ld_t + c0 + c];
-  if (CS > 1) cluster.sync(); else __syncthreads();     // every CTA of the cluster is running before DSMEM traffic
+  const int nbox = a.nbox, boxw = a.boxw;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    mbar_init(s.bar, 1);
+    mbar_fence_init();
+    // one TMA box load per [rows x boxw] sub-tile (out-of-range channels are zero-filled) + the target slice
+    mbar_expect_tx(s.bar, (uint32_t)nbox * (uint32_t)rows * (uint32_t)boxw * 4u + (t_bulk ? (uint32_t)cn * 4u : 0u));
+    for (int sb = 0; sb < nbox; ++sb) tma_load_3d(s.tile + (size_t)sb * rows * boxw, &tmap, c0 + sb * boxw, 0, b, s.bar);
+    if (t_bulk) bulk_g2s(s.tv, t_b, (uint32_t)cn * 4u, s.bar);
+  }
+  __syncthreads();                               // barrier initialised before anybody waits on it
+  if (!t_bulk) {
+    for (int c = threadIdx.x; c < cn; c += RA_THREADS) s.tv[c] = t_b[c];
+    __syncthreads();
+  }
   mbar_wait(s.bar, 0);
 
-  ra_partial_dots(cluster, s, s.tv, rows, chunk, cn, mask_b, CS, rank);
+  // partial dots of this channel slice -> local smem (aux doubles as the local partial array)
+  {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b4 = boxw >> 2;
+    for (int r = wid; r < rows; r += RA_THREADS / 32) {
+      float acc = 0.f;
+      if (mask_b == nullptr || mask_b[r] == 0) {
+        for (int sb = 0; sb < nbox; ++sb) {
+          const float4* row = reinterpret_cast<const float4*>(s.tile + ((size_t)sb * rows + r) * boxw);
+          const float4* v4 = reinterpret_cast<const float4*>(s.tv + sb * boxw);
+          const int lim = min(b4, (cn - sb * boxw + 3) >> 2);          // columns past cn: tile is zero-filled but tv is not staged
+          for (int j = lane; j < lim; j += 32) {
+            const float4 x = row[j], y = v4[j];
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+          }
+        }
+        acc = warp_sum(acc);
+      }
+      if (lane == 0) s.aux[r] = acc;
+    }
+  }
   if (CS > 1) cluster.sync(); else __syncthreads();
-  ra_softmax_rows<false>(s, rows, CS, mask_b);
+  // pull: z[r] = sum over ranks (fixed order) of their partials
+  for (int r = threadIdx.x; r < rows; r += RA_THREADS) {
+    float z = 0.f;
+#pragma unroll
+    for (int k = 0; k < CS; ++k) z += (CS == 1) ? s.aux[r] : cluster.map_shared_rank(s.aux, k)[r];
+    s.zpart[r] = (mask_b != nullptr && mask_b[r]) ? -INFINITY : z;
+  }
+  if (CS > 1) cluster_arrive();                  // exit barrier, arrive half: done reading the peers' shared memory
   __syncthreads();
-
-  // shift (circular cross-correlation along the heading axis) or plain weights
-  if (a.shift_k > 0) {
-    const int k = a.shift_k, half = k / 2, Hn = a.headings;
-    if (threadIdx.x < 32) {
-      float kl = (threadIdx.x < k) ? a.kappa_logits[(int64_t)b * a.ld_kappa + threadIdx.x] : -INFINITY;
-      const float mx = warp_max(kl);
-      float e = (threadIdx.x < k) ? expf(kl - mx) : 0.f;
-      const float sum = warp_sum(e);
-      if (threadIdx.x < k) {
-        s.red[threadIdx.x] = e / sum;
-        if (rank == 0 && a.kappa_out) a.kappa_out[(int64_t)b * k + threadIdx.x] = e / sum;
+  // softmax over rows (warp 0)
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float z[RA_MAX_ROWS / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < RA_MAX_ROWS / 32; ++i) {
+      const int r = lane + 32 * i;
+      z[i] = (r < rows) ? s.zpart[r] : -INFINITY;
+      mx = fmaxf(mx, z[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < RA_MAX_ROWS / 32; ++i) {
+      z[i] = (z[i] == -INFINITY) ? 0.f : expf(z[i] - mx);
+      sum += z[i];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < RA_MAX_ROWS / 32; ++i) {
+      const int r = lane + 32 * i;
+      if (r < rows) s.p[r] = z[i] * inv;
+    }
+    if (SHIFT) {
+      const int k = a.shift_k;
+      float kl = (lane < k) ? a.kappa_logits[(int64_t)b * a.ld_kappa + lane] : -INFINITY;
+      const float kmx = warp_max(kl);
+      const float e = (lane < k) ? expf(kl - kmx) : 0.f;
+      const float ksum = warp_sum(e);
+      if (lane < k) {
+        s.red[lane] = e / ksum;
+        if (rank == 0 && a.kappa_out) a.kappa_out[(int64_t)b * k + lane] = e / ksum;
       }
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  if (SHIFT) {
+    const int k = a.shift_k, half = k / 2, Hn = a.headings;
     for (int r = threadIdx.x; r < rows; r += RA_THREADS) {
       const int e = r / Hn, l = r % Hn;
       float q = 0.f;
@@ -203,16 +281,19 @@ __global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(RowAttnAr
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool act = (col < n4) && (grp < G);
       if (act) {
+        const int b4w = boxw >> 2, sbi = col / b4w, cin = col % b4w;
+        const float4* tp = reinterpret_cast<const float4*>(s.tile + (size_t)sbi * rows * boxw) + cin;
+        const int stride4 = b4w;
+#pragma unroll 4
         for (int r = grp; r < rows; r += G) {
           const float wr = s.w[r];
-          if (wr != 0.f) {
-            const float4 v = reinterpret_cast<const float4*>(s.tile + (size_t)r * chunk)[col];
+          {
+            const float4 v = tp[(size_t)r * stride4];
             acc.x = fmaf(wr, v.x, acc.x); acc.y = fmaf(wr, v.y, acc.y); acc.z = fmaf(wr, v.z, acc.z); acc.w = fmaf(wr, v.w, acc.w);
           }
         }
       }
       if (G > 1) {
-        // G*n4 <= 256 float4 = 1024 floats of scratch
         __syncthreads();
         if (act) reinterpret_cast<float4*>(s.red)[grp * n4 + col] = acc;
         __syncthreads();
@@ -225,10 +306,12 @@ __global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(RowAttnAr
       }
       if (act && grp == 0) {
         float* dst = a.wc + (int64_t)b * a.ld_wc + c0 + 4 * col;
-        dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = acc;
+        else { dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w; }
       }
     }
   }
+  if (CS > 1) cluster_wait();                    // exit barrier, wait half: nobody is still reading our partials
 }
 
 struct RowAttnBwdArgs {
@@ -404,14 +487,17 @@ __global__ void __launch_bounds__(128) cand_logits_bwd_kernel(const float* __res
 int pick_cluster(int B, int rows, int D, int* chunk_out) {
   int cs = 1;
   auto chunk_of = [&](int c) { return (int)(dasa_cdiv(dasa_cdiv(D, 4), c) * 4); };
+  // small channel slices => several CTAs per SM overlap their load / barrier / compute phases (measured: 2 CTAs/SM with
+  // 88 KB slices reached 25 % of HBM peak); never below 64 floats per row slice
+  while (cs < 8 && (ra_smem_bytes(rows, chunk_of(cs), cs) > 48 * 1024) && chunk_of(cs * 2) >= 64) cs *= 2;
   while (cs < 8 && ra_smem_bytes(rows, chunk_of(cs), cs) > 100 * 1024) cs *= 2;
   while (cs < 8 && (int64_t)B * cs * 2 <= 2 * DASA_NUM_SMS) cs *= 2;   // small batches: more CTAs in flight per sample
   *chunk_out = chunk_of(cs);
   return cs;
 }
 
-template <typename Kern, typename Args>
-int launch_cluster(Kern kern, const Args& a, int B, int cs, size_t smem, cudaStream_t st, const char* name) {
+template <typename Kern, typename... Args>
+int launch_cluster(Kern kern, int B, int cs, size_t smem, cudaStream_t st, const char* name, Args... args) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
   cudaLaunchConfig_t cfg{};
@@ -426,7 +512,7 @@ int launch_cluster(Kern kern, const Args& a, int B, int cs, size_t smem, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, a);
+  e = cudaLaunchKernelEx(&cfg, kern, args...);
   if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
   return DASA_OK;
 }
@@ -443,17 +529,47 @@ extern "C" int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t 
     return DASA_ERR_BAD_SHAPE;
   if (!dasa_aligned16(ctx) || ld_row % 4 != 0 || ld_sample % 4 != 0) return DASA_ERR_BAD_ALIGN;
   RowAttnArgs a{ctx, ld_row, ld_sample, B, rows, D, t, ld_t, mask, ld_mask, shift_k, headings, kappa_logits, ld_kappa,
-                wc, ld_wc, attn_out, q_out, kappa_out, 0};
+                wc, ld_wc, attn_out, q_out, kappa_out, 0, 1, 0};
   const int cs = pick_cluster(B, rows, D, &a.chunk);
+  // TMA boxes: inner extent <= 256 elements; widen the slice so that it is a whole number of equal boxes
+  a.nbox = (int)dasa_cdiv(a.chunk, 256);
+  a.boxw = (int)(dasa_cdiv(dasa_cdiv(a.chunk, a.nbox), 4) * 4);
+  if (a.nbox > 1) {                              // every sub-tile must start 128-byte aligned: rows*boxw*4 % 128 == 0
+    int g = 32;
+    while (g > 1 && (rows % g) != 0) g >>= 1;    // g = gcd(rows, 32)
+    const int q = 32 / g;
+    a.boxw = (int)(dasa_cdiv(a.boxw, q) * q);
+    if (a.boxw > 256) return DASA_ERR_BAD_SHAPE;
+  }
+  a.chunk = a.nbox * a.boxw;
   const size_t smem = ra_smem_bytes(rows, a.chunk, cs);
   if (smem > 227 * 1024) return DASA_ERR_BAD_SHAPE;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (cs) {
-    case 1: return launch_cluster(row_attention_fwd_kernel<1>, a, B, 1, smem, st, "row_attention_fwd<1>");
-    case 2: return launch_cluster(row_attention_fwd_kernel<2>, a, B, 2, smem, st, "row_attention_fwd<2>");
-    case 4: return launch_cluster(row_attention_fwd_kernel<4>, a, B, 4, smem, st, "row_attention_fwd<4>");
-    default: return launch_cluster(row_attention_fwd_kernel<8>, a, B, 8, smem, st, "row_attention_fwd<8>");
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeFn enc = reinterpret_cast<EncodeFn>(dasa_tensormap_encoder());
+  if (enc == nullptr) return DASA_ERR_UNSUPPORTED;
+  CUtensorMap tmap;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld_row * 4, (cuuint64_t)ld_sample * 4};
+    cuuint32_t box[3] = {(cuuint32_t)a.boxw, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ctx), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DASA_ERR_UNSUPPORTED;
   }
+  cudaStream_t st = (cudaStream_t)stream;
+#define DASA_RA_FWD(CSV)                                                                                                  \
+  (shift_k > 0 ? launch_cluster(row_attention_fwd_kernel<CSV, true>, B, CSV, smem, st, "row_attention_fwd<shift>", tmap, a) \
+               : launch_cluster(row_attention_fwd_kernel<CSV, false>, B, CSV, smem, st, "row_attention_fwd<softdot>", tmap, a))
+  switch (cs) {
+    case 1: return DASA_RA_FWD(1);
+    case 2: return DASA_RA_FWD(2);
+    case 4: return DASA_RA_FWD(4);
+    default: return DASA_RA_FWD(8);
+  }
+#undef DASA_RA_FWD
 }
 
 extern "C" int dasa_row_attention_bwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
@@ -475,10 +591,10 @@ extern "C" int dasa_row_attention_bwd(const float* ctx, int64_t ld_row, int64_t 
   if (smem > 227 * 1024) return DASA_ERR_BAD_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   switch (cs) {
-    case 1: return launch_cluster(row_attention_bwd_kernel<1>, a, B, 1, smem, st, "row_attention_bwd<1>");
-    case 2: return launch_cluster(row_attention_bwd_kernel<2>, a, B, 2, smem, st, "row_attention_bwd<2>");
-    case 4: return launch_cluster(row_attention_bwd_kernel<4>, a, B, 4, smem, st, "row_attention_bwd<4>");
-    default: return launch_cluster(row_attention_bwd_kernel<8>, a, B, 8, smem, st, "row_attention_bwd<8>");
+    case 1: return launch_cluster(row_attention_bwd_kernel<1>, B, 1, smem, st, "row_attention_bwd<1>", a);
+    case 2: return launch_cluster(row_attention_bwd_kernel<2>, B, 2, smem, st, "row_attention_bwd<2>", a);
+    case 4: return launch_cluster(row_attention_bwd_kernel<4>, B, 4, smem, st, "row_attention_bwd<4>", a);
+    default: return launch_cluster(row_attention_bwd_kernel<8>, B, 8, smem, st, "row_attention_bwd<8>", a);
   }
 }
 

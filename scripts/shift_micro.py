@@ -1,0 +1,16 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dasa_b200 import ops
+B, V, F = int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 36, 2176
+f = torch.rand(B, V, F, device="cuda"); t = torch.randn(B, F, device="cuda") * 0.05; kl = torch.randn(B, 5, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+ts = []
+for i in range(8):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(); ops.row_attention_fwd(f, t, None, 5, 12, kl); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts.sort(); ms = ts[len(ts) // 2]
+byt = 4 * (B * V * F + 2 * B * F + B * V + B * 5)
+print("B=%d shift_attention_fwd: %.3f ms  %.1f GB/s" % (B, ms, byt / ms / 1e6))
