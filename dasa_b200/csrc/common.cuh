@@ -12,6 +12,11 @@ void dasa_set_error(const char* what, cudaError_t e);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no direct libcuda link dependency); nullptr if unavailable
 void* dasa_tensormap_encoder();
 
+// persistent pipelined forward of the (shift) view attention for large batches (row_attention_pipe.cu)
+int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D, const float* t,
+                                     int64_t ld_t, int shift_k, int headings, const float* kappa_logits, int64_t ld_kappa,
+                                     float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, cudaStream_t st);
+
 static inline int dasa_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { dasa_set_error(what, e); return DASA_ERR_CUDA; }

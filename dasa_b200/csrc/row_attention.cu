@@ -5,6 +5,7 @@
 // and produces its channel slice of the weighted sum from the tile it already holds. One read of ctx, no re-read.
 #include <cooperative_groups.h>
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -496,6 +497,17 @@ int pick_cluster(int B, int rows, int D, int* chunk_out) {
   return cs;
 }
 
+// batches at or above this size use the persistent pipelined kernel (DASA_RA_PIPE_MIN_B overrides, for the sweep)
+int ra_pipe_min_batch() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DASA_RA_PIPE_MIN_B");
+    v = e ? atoi(e) : 64;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 template <typename Kern, typename... Args>
 int launch_cluster(Kern kern, int B, int cs, size_t smem, cudaStream_t st, const char* name, Args... args) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -528,6 +540,11 @@ extern "C" int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t 
   if (shift_k < 0 || shift_k > RA_MAX_K || (shift_k > 0 && (headings <= 0 || rows % headings != 0 || kappa_logits == nullptr)))
     return DASA_ERR_BAD_SHAPE;
   if (!dasa_aligned16(ctx) || ld_row % 4 != 0 || ld_sample % 4 != 0) return DASA_ERR_BAD_ALIGN;
+  if (mask == nullptr && B >= ra_pipe_min_batch()) {
+    const int rc = dasa_row_attention_fwd_pipelined(ctx, ld_row, ld_sample, B, rows, D, t, ld_t, shift_k, headings, kappa_logits,
+                                                    ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out, (cudaStream_t)stream);
+    if (rc != DASA_ERR_UNSUPPORTED) return rc;
+  }
   RowAttnArgs a{ctx, ld_row, ld_sample, B, rows, D, t, ld_t, mask, ld_mask, shift_k, headings, kappa_logits, ld_kappa,
                 wc, ld_wc, attn_out, q_out, kappa_out, 0, 1, 0};
   const int cs = pick_cluster(B, rows, D, &a.chunk);

@@ -1,0 +1,415 @@
+// Large-batch forward of the view attention (ShiftSoftDotAttention, model.py:307-353; plain soft-dot when shift_k == 0,
+// no mask): PERSISTENT thread-block clusters, one sample per cluster per iteration, warp-specialised and pipelined through
+// mbarriers so that the HBM loads never stop while earlier samples are being reduced.
+//
+//   * cluster of CS CTAs (1 CTA / SM); CTA `rank` owns the channel slice [rank*chunk, (rank+1)*chunk) of every sample its
+//     cluster processes and keeps a ring of NS shared-memory stages. A stage = the [rows x chunk] context slice, staged as
+//     nbox TMA boxes [rows x boxw] (boxw*4 bytes is an odd multiple of 16 when the shape allows it, so that 8 consecutive
+//     rows fall into 8 different 16-byte bank groups) + the target slice (bulk copy), completing on the stage's `full`.
+//   * producer warp : waits `empty[stage]`, issues the TMA loads of the next sample;
+//   * dot warps     : lane = (row of an 8-row group, box): one box-row dot product per lane, 2 shuffles to add the boxes,
+//                     partial sums PUSHED into every CTA of the cluster with st.async (data + complete_tx on the receiver's
+//                     `zfull` mbarrier - no cluster-wide barrier anywhere in the loop);
+//   * softmax warps : (4, round-robin over samples) wait `zfull`, add the CS partials in fixed rank order (all CTAs get
+//                     bit-identical weights), softmax over the rows, circular shift along the heading axis, publish the
+//                     weights, arrive `wready[stage]`;
+//   * weighted-sum warps: warp = box, lane = float4 column: sum_r w_r * slice[r, :] from the still-resident stage, store,
+//                     arrive `empty[stage]`.
+#include <cooperative_groups.h>
+#include <cuda.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int RP_DWARPS = 8;          // dot-product warps (ceil(rows/8) of them are active)
+constexpr int RP_MAX_BOX = 4;         // boxes per slice = weighted-sum warps
+constexpr int RP_SWARPS = 4;          // softmax warps
+constexpr int RP_WARPS = RP_DWARPS + RP_MAX_BOX + RP_SWARPS + 1;
+constexpr int RP_THREADS = RP_WARPS * 32;
+constexpr int RP_MAX_ROWS = 64;       // two rows per lane in a softmax warp
+constexpr int RP_MAX_K = 15;
+
+struct PipeArgs {
+  const float* t; int64_t ld_t;
+  const float* kappa_logits; int64_t ld_kappa;
+  float* wc; int64_t ld_wc; float* attn_out; float* q_out; float* kappa_out;
+  int B, rows, D, chunk, nbox, boxw, box_stride, shift_k, headings, nstages, nclusters;   // box_stride in floats
+};
+
+// Shared memory of one CTA. NS stages; the partial-dot exchange ring is 2*NS deep: a peer can push sample j only after this
+// CTA's softmax warps have consumed sample j - 2*NS (its load of j waits for its own weighted sum of j-NS, which waited for
+// our dots of j-NS, whose load waited for our weighted sum - hence softmax - of j-2*NS).
+struct PipeSmem {
+  float* tile;      // [NS][nbox][box_stride]
+  float* tv;        // [NS][chunk]            target slice
+  float* wts;       // [NS][RPAD]             final weights of the stage's sample
+  float* zbuf;      // [2*NS][CS][RPAD]       partial dots pushed by every CTA of the cluster
+  float* pscr;      // [SWARPS][RPAD + 16]    softmax-warp scratch: p, kappa
+  uint8_t* tab;     // [rows][k]              circular-shift source rows
+  uint64_t* full;   // [NS]   TMA landed
+  uint64_t* empty;  // [NS]   weighted-sum warps are done with the stage
+  uint64_t* wready; // [NS]   weights published
+  uint64_t* zfull;  // [2*NS] all partial dots of a sample arrived
+  size_t stage_floats;
+};
+
+__host__ __device__ inline int rp_rpad(int rows) { return (rows + 3) & ~3; }
+
+__host__ __device__ inline size_t rp_smem_bytes(int rows, int chunk, int nbox, int box_stride, int cs, int ns, int k) {
+  const size_t rp = (size_t)rp_rpad(rows);
+  size_t b = 4 * ((size_t)ns * nbox * box_stride + (size_t)ns * chunk + (size_t)ns * rp + (size_t)2 * ns * cs * rp +
+                  (size_t)RP_SWARPS * (rp + 16));
+  b += (((size_t)rows * (k > 0 ? k : 1)) + 15) & ~(size_t)15;
+  b += 8 * (size_t)(5 * ns) + 128;
+  return b;
+}
+
+__device__ inline PipeSmem rp_carve(unsigned char* raw, const PipeArgs& a, int cs) {
+  PipeSmem s;
+  const int rp = rp_rpad(a.rows), ns = a.nstages, k = a.shift_k;
+  s.stage_floats = (size_t)a.nbox * a.box_stride;               // box_stride*4 is a multiple of 128 bytes
+  s.tile = reinterpret_cast<float*>(raw);
+  s.tv = s.tile + (size_t)ns * s.stage_floats;
+  s.wts = s.tv + (size_t)ns * a.chunk;
+  s.zbuf = s.wts + (size_t)ns * rp;
+  s.pscr = s.zbuf + (size_t)2 * ns * cs * rp;
+  s.tab = reinterpret_cast<uint8_t*>(s.pscr + (size_t)RP_SWARPS * (rp + 16));
+  uintptr_t b = reinterpret_cast<uintptr_t>(s.tab + (size_t)a.rows * (k > 0 ? k : 1));
+  b = (b + 15) & ~uintptr_t(15);
+  s.full = reinterpret_cast<uint64_t*>(b);
+  s.empty = s.full + ns;
+  s.wready = s.empty + ns;
+  s.zfull = s.wready + ns;
+  return s;
+}
+
+__device__ __forceinline__ void tma_box_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// remote 4-byte store that also signals 4 transaction bytes on the receiver's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+template <int CS>
+__global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap, PipeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS;
+  const int rows = a.rows, chunk = a.chunk, NS = a.nstages, NZ = 2 * a.nstages, nbox = a.nbox, boxw = a.boxw;
+  const int k = a.shift_k, Hn = a.headings;
+  const int rp = rp_rpad(rows);
+  const PipeSmem s = rp_carve(smem_raw, a, CS);
+  const int c0 = rank * chunk;
+  const int cn = max(0, min(chunk, a.D - c0));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = (a.B - cid + a.nclusters - 1) / a.nclusters;          // samples of this cluster: cid, cid + nclusters, ...
+  const uint32_t z_tx = (uint32_t)CS * (uint32_t)rows * 4u;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], (uint32_t)nbox);
+      mbar_init(&s.wready[i], 1);
+    }
+    for (int i = 0; i < NZ; ++i) mbar_init(&s.zfull[i], 1);
+    mbar_fence_init();
+    for (int i = 0; i < NZ; ++i) mbar_expect_tx(&s.zfull[i], z_tx);
+  }
+  // target-slice tails past D stay zero for the whole kernel (the tile tail is zero-filled by TMA); weight padding too
+  for (int i = threadIdx.x; i < NS * chunk; i += RP_THREADS) s.tv[i] = 0.f;
+  for (int i = threadIdx.x; i < NS * rp; i += RP_THREADS) s.wts[i] = 0.f;
+  for (int i = threadIdx.x; i < rows * k; i += RP_THREADS) {          // circular shift along the heading axis (model.py:333-349)
+    const int r = i / k, jj = i % k;
+    const int e = r / Hn, l = r % Hn;
+    int src = (l + jj - k / 2) % Hn;
+    if (src < 0) src += Hn;
+    s.tab[i] = (uint8_t)(e * Hn + src);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  cluster.sync();                               // every peer's barriers are initialised before any st.async reaches them
+
+  if (wid < RP_DWARPS) {
+    // ---------------------------------------------------- dot warps: lane = (row rl of an 8-row group, box bl)
+    const int rl = lane & 7, bl = lane >> 3;
+    const int groups = (rows + 7) >> 3;
+    if (wid < groups) {
+      constexpr int PP = CS / 4;                 // peers served by one lane
+      uint32_t zb_remote[PP], zf_remote[PP];
+#pragma unroll
+      for (int pp = 0; pp < PP; ++pp) {
+        zb_remote[pp] = map_to_rank(smem_u32(s.zbuf), (uint32_t)(bl * PP + pp));
+        zf_remote[pp] = map_to_rank(smem_u32(s.zfull), (uint32_t)(bl * PP + pp));
+      }
+      const int b4w = boxw >> 2;
+      const bool box_ok = bl < nbox;
+      for (int i = 0; i < n; ++i) {
+        const int st = i % NS, zs = i % NZ;
+        mbar_wait(&s.full[st], (uint32_t)(i / NS) & 1u);
+        const float* tile = s.tile + (size_t)st * s.stage_floats + (box_ok ? bl * a.box_stride : 0);
+        const float4* tv4 = reinterpret_cast<const float4*>(s.tv + (size_t)st * chunk + (box_ok ? bl * boxw : 0));
+        for (int g = wid; g < groups; g += RP_DWARPS) {
+          const int r = g * 8 + rl;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (box_ok && r < rows) {
+            const float4* row4 = reinterpret_cast<const float4*>(tile + r * boxw);
+#pragma unroll 4
+            for (int j = 0; j < b4w; ++j) {
+              const float4 x = row4[j], y = tv4[j];
+              acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
+              acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+            }
+          }
+          float v = (acc.x + acc.y) + (acc.z + acc.w);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (r < rows) {
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp)    // peer bl*PP+pp: zbuf[zs][my rank][r]
+              st_async_f32(zb_remote[pp] + 4u * (uint32_t)((zs * CS + rank) * rp + r), v, zf_remote[pp] + 8u * (uint32_t)zs);
+          }
+        }
+      }
+    }
+  } else if (wid < RP_DWARPS + RP_MAX_BOX) {
+    // ------------------------------------------------- weighted-sum warps: warp = box, lane = float4 column(s) of the box
+    const int box = wid - RP_DWARPS;
+    if (box < nbox) {
+      const int b4w = boxw >> 2;
+      const int cA = lane, cB = lane + 32;       // boxw <= 256 floats: at most two float4 columns per lane
+      const bool actA = cA < b4w && box * boxw + 4 * cA < cn;
+      const bool actB = cB < b4w && box * boxw + 4 * cB < cn;
+      const int rows4 = rows >> 2;
+      for (int i = 0; i < n; ++i) {
+        const int st = i % NS;
+        const int b = cid + i * a.nclusters;
+        mbar_wait(&s.wready[st], (uint32_t)(i / NS) & 1u);
+        const float* tile = s.tile + (size_t)st * s.stage_floats + (size_t)box * a.box_stride;
+        const float4* w4 = reinterpret_cast<const float4*>(s.wts + (size_t)st * rp);
+        float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fma_row = [&](float wr, int r) {
+          if (actA) {
+            const float4 x = reinterpret_cast<const float4*>(tile + r * boxw)[cA];
+            accA.x = fmaf(wr, x.x, accA.x); accA.y = fmaf(wr, x.y, accA.y); accA.z = fmaf(wr, x.z, accA.z); accA.w = fmaf(wr, x.w, accA.w);
+          }
+          if (actB) {
+            const float4 x = reinterpret_cast<const float4*>(tile + r * boxw)[cB];
+            accB.x = fmaf(wr, x.x, accB.x); accB.y = fmaf(wr, x.y, accB.y); accB.z = fmaf(wr, x.z, accB.z); accB.w = fmaf(wr, x.w, accB.w);
+          }
+        };
+#pragma unroll 3
+        for (int g = 0; g < rows4; ++g) {
+          const float4 wv = w4[g];
+          fma_row(wv.x, 4 * g); fma_row(wv.y, 4 * g + 1); fma_row(wv.z, 4 * g + 2); fma_row(wv.w, 4 * g + 3);
+        }
+        for (int r = 4 * rows4; r < rows; ++r) fma_row(s.wts[(size_t)st * rp + r], r);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[st]);                   // this warp no longer needs the stage
+        float* dst = a.wc + (int64_t)b * a.ld_wc + c0 + box * boxw;
+        if (actA) stg_stream4(dst + 4 * cA, accA);
+        if (actB) stg_stream4(dst + 4 * cB, accB);
+      }
+    }
+  } else if (wid < RP_DWARPS + RP_MAX_BOX + RP_SWARPS) {
+    // --------- softmax warps (round-robin over samples): z_r = sum over ranks (fixed order), softmax, circular shift
+    const int sw = wid - RP_DWARPS - RP_MAX_BOX;
+    float* pw = s.pscr + (size_t)sw * (rp + 16);
+    float* kw = pw + rp;
+    const bool r0ok = lane < rows, r1ok = lane + 32 < rows;
+    for (int i = sw; i < n; i += RP_SWARPS) {
+      const int st = i % NS, zs = i % NZ;
+      const int b = cid + i * a.nclusters;
+      const bool writer = (i % CS) == rank;      // one CTA of the cluster stores the per-sample distributions
+      float kv = 0.f;
+      if (k > 0) {                               // independent of the exchange: done while the partial dots are in flight
+        const float kl = (lane < k) ? a.kappa_logits[(int64_t)b * a.ld_kappa + lane] : -INFINITY;
+        const float kmx = warp_max(kl);
+        const float ke = (lane < k) ? expf(kl - kmx) : 0.f;
+        kv = ke / warp_sum(ke);
+        if (lane < k) kw[lane] = kv;
+      }
+      mbar_wait_cluster(&s.zfull[zs], (uint32_t)(i / NZ) & 1u);
+      const float* zb = s.zbuf + (size_t)zs * CS * rp;
+      float z0 = -INFINITY, z1 = -INFINITY;
+      if (r0ok) {
+        z0 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) z0 += zb[c * rp + lane];
+      }
+      if (r1ok) {
+        z1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) z1 += zb[c * rp + lane + 32];
+      }
+      if (lane == 0) mbar_expect_tx(&s.zfull[zs], z_tx);            // re-arm the slot for sample i + 2*NS
+      const float mx = warp_max(fmaxf(z0, z1));
+      const float e0 = r0ok ? expf(z0 - mx) : 0.f;
+      const float e1 = r1ok ? expf(z1 - mx) : 0.f;
+      const float inv = 1.f / warp_sum(e0 + e1);
+      const float p0 = e0 * inv, p1 = e1 * inv;
+      float* w = s.wts + (size_t)st * rp;
+      if (k > 0) {
+        if (r0ok) pw[lane] = p0;
+        if (r1ok) pw[lane + 32] = p1;
+        __syncwarp();
+        float q0 = 0.f, q1 = 0.f;
+        if (r0ok) {
+          for (int jj = 0; jj < k; ++jj) q0 = fmaf(kw[jj], pw[s.tab[lane * k + jj]], q0);
+          w[lane] = q0;
+        }
+        if (r1ok) {
+          for (int jj = 0; jj < k; ++jj) q1 = fmaf(kw[jj], pw[s.tab[(lane + 32) * k + jj]], q1);
+          w[lane + 32] = q1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.wready[st]);                  // release: weights visible to the weighted-sum warps
+        if (writer) {
+          if (a.q_out) {
+            if (r0ok) a.q_out[(int64_t)b * rows + lane] = q0;
+            if (r1ok) a.q_out[(int64_t)b * rows + lane + 32] = q1;
+          }
+          if (a.kappa_out && lane < k) a.kappa_out[(int64_t)b * k + lane] = kv;
+        }
+      } else {
+        if (r0ok) w[lane] = p0;
+        if (r1ok) w[lane + 32] = p1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.wready[st]);
+        if (writer && a.q_out) {
+          if (r0ok) a.q_out[(int64_t)b * rows + lane] = p0;
+          if (r1ok) a.q_out[(int64_t)b * rows + lane + 32] = p1;
+        }
+      }
+      if (writer && a.attn_out) {
+        if (r0ok) a.attn_out[(int64_t)b * rows + lane] = p0;
+        if (r1ok) a.attn_out[(int64_t)b * rows + lane + 32] = p1;
+      }
+      __syncwarp();                              // pw / kw are rewritten by the next sample of this warp
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------------- producer: TMA loads into the stage ring
+    const uint32_t stage_tx = (uint32_t)nbox * (uint32_t)rows * (uint32_t)boxw * 4u + (uint32_t)cn * 4u;
+    for (int j = 0; j < n; ++j) {
+      const int st = j % NS;
+      const int b = cid + j * a.nclusters;
+      if (j >= NS) mbar_wait(&s.empty[st], (uint32_t)(j / NS - 1) & 1u);
+      mbar_expect_tx(&s.full[st], stage_tx);
+      float* dst = s.tile + (size_t)st * s.stage_floats;
+      for (int sb = 0; sb < nbox; ++sb) tma_box_3d(dst + (size_t)sb * a.box_stride, &tmap, c0 + sb * boxw, 0, b, &s.full[st]);
+      if (cn > 0) bulk_g2s(s.tv + (size_t)st * chunk, a.t + (int64_t)b * a.ld_t + c0, (uint32_t)cn * 4u, &s.full[st]);
+    }
+  }
+  __syncwarp();
+  cluster.sync();                                // nobody exits while a peer may still push into its shared memory
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int CS>
+int launch_pipe(const CUtensorMap& tmap, PipeArgs a, size_t smem, cudaStream_t st) {
+  auto kern = row_attention_fwd_pipe_kernel<CS>;
+  static int max_clusters = -1;                  // per (CS) instantiation; the smem request below is the worst case
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe attr", e); return DASA_ERR_CUDA; }
+  if (CS > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe cluster attr", e); return DASA_ERR_CUDA; }
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(RP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    cfg.gridDim = dim3(CS * DASA_NUM_SMS);
+    cudaLaunchConfig_t q = cfg;
+    q.dynamicSmemBytes = 200 * 1024;             // 1 CTA / SM by construction
+    int nc = 0;
+    e = cudaOccupancyMaxActiveClusters(&nc, kern, &q);
+    if (e != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = DASA_NUM_SMS / CS / 2; }
+    max_clusters = nc;
+  }
+  a.nclusters = a.B < max_clusters ? a.B : max_clusters;
+  cfg.gridDim = dim3((unsigned)(a.nclusters * CS));
+  e = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+  if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe", e); return DASA_ERR_CUDA; }
+  return DASA_OK;
+}
+
+}  // namespace
+
+// Returns DASA_ERR_UNSUPPORTED when the shape does not fit this kernel (the caller then uses the one-shot cluster kernel).
+int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D, const float* t,
+                                     int64_t ld_t, int shift_k, int headings, const float* kappa_logits, int64_t ld_kappa,
+                                     float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, cudaStream_t st) {
+  if (rows > RP_MAX_ROWS || shift_k > RP_MAX_K || D % 4 != 0) return DASA_ERR_UNSUPPORTED;
+  if (!dasa_aligned16(t) || ld_t % 4 != 0 || !dasa_aligned16(wc) || ld_wc % 4 != 0) return DASA_ERR_UNSUPPORTED;
+  // channel slice per CTA, split into <= 4 TMA boxes of equal width (<= 256 floats); prefer an odd number of float4 per box row
+  int best_cs = 0, best_ns = 0, best_nbox = 0, best_boxw = 0, best_stride = 0;
+  for (int cs = 8; cs <= 16 && best_cs == 0; cs *= 2) {
+    const int c4 = (int)dasa_cdiv(D / 4, cs);                        // float4 columns per CTA
+    if ((int64_t)(cs - 1) * c4 * 4 >= D) continue;                   // every rank owns >= 1 column
+    for (int pass = 0; pass < 2 && best_cs == 0; ++pass) {           // pass 0: odd box width only
+      for (int nbox = 1; nbox <= RP_MAX_BOX; ++nbox) {
+        const int b4 = (int)dasa_cdiv(c4, nbox);
+        if (b4 * 4 > 256 || (pass == 0 && (b4 & 1) == 0)) continue;
+        if ((int64_t)b4 * nbox != c4) continue;                      // equal boxes tile the slice exactly (no overlap with the peer)
+        const int boxw = b4 * 4;
+        const int stride = (int)(dasa_cdiv((int64_t)rows * boxw, 32) * 32);   // floats; 128-byte aligned box bases
+        int ns = 8;
+        while (ns >= 3 && rp_smem_bytes(rows, nbox * boxw, nbox, stride, cs, ns, shift_k) > 227 * 1024) --ns;
+        if (ns < 3) continue;
+        best_cs = cs; best_ns = ns; best_nbox = nbox; best_boxw = boxw; best_stride = stride;
+        break;
+      }
+    }
+  }
+  if (best_cs == 0) return DASA_ERR_UNSUPPORTED;
+  const int cs = best_cs, ns = best_ns, nbox = best_nbox, boxw = best_boxw, chunk = best_nbox * best_boxw;
+  EncodeFn enc = reinterpret_cast<EncodeFn>(dasa_tensormap_encoder());
+  if (enc == nullptr) return DASA_ERR_UNSUPPORTED;
+  CUtensorMap tmap;
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld_row * 4, (cuuint64_t)ld_sample * 4};
+  cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ctx), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return DASA_ERR_UNSUPPORTED;
+  PipeArgs a{t, ld_t, kappa_logits, ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out,
+             B, rows, D, chunk, nbox, boxw, best_stride, shift_k, headings, ns, 0};
+  const size_t smem = rp_smem_bytes(rows, chunk, nbox, best_stride, cs, ns, shift_k);
+  return cs == 8 ? launch_pipe<8>(tmap, a, smem, st) : launch_pipe<16>(tmap, a, smem, st);
+}

@@ -150,6 +150,46 @@ def test_shift_attention_fwd_bwd(cfg, B):
     assert_close(mod.linear_shift.bias.grad, st["feat_att_layer.linear_shift.bias"].grad, 2e-4, "db_shift")
 
 
+def _row_attention_f64(ctx, t, k, headings, kl):
+    """model.py:318-353 restated in float64: softmax over the rows, circular k-tap shift along the heading axis."""
+    ctx, t = ctx.double(), t.double()
+    p = torch.softmax(torch.einsum("brd,bd->br", ctx, t), 1)
+    w = p
+    if k > 0:
+        kap = torch.softmax(kl.double(), 1)
+        B, rows = p.shape
+        pe = p.view(B, rows // headings, headings)
+        w = torch.zeros_like(pe)
+        for j in range(k):
+            w = w + kap[:, j, None, None] * torch.roll(pe, -(j - k // 2), 2)
+        w = w.reshape(B, rows)
+    return torch.einsum("br,brd->bd", w, ctx), p, w
+
+
+@pytest.mark.parametrize("B,rows,D,k,headings", [(300, 36, 2176, 5, 12), (1000, 36, 2176, 5, 12), (150, 36, 4224, 5, 12),
+                                                 (200, 36, 520, 3, 12), (257, 50, 2048, 0, 1), (64, 36, 3200, 5, 12)])
+def test_row_attention_fwd_large_batch(B, rows, D, k, headings):
+    """Batches >= 64 without a mask take the persistent pipelined cluster kernel (row_attention_pipe.cu)."""
+    gen = g(B + D)
+    ctx = torch.relu(torch.randn(B, rows, D, generator=gen)) * 0.5
+    t = torch.randn(B, D, generator=gen) * 0.05
+    kl = torch.randn(B, max(k, 1), generator=gen)
+    wc, attn, q, kappa = ops.row_attention_fwd(ctx.to(DEV), t.to(DEV), None, k, headings, kl.to(DEV) if k else None, want_q=True)
+    wc_ref, p_ref, w_ref = _row_attention_f64(ctx, t, k, headings, kl)
+    assert_close(attn, p_ref, 1e-5, "softmax")
+    assert_close(q, w_ref, 1e-5, "shifted weights")
+    assert_close(wc, wc_ref, 1e-5, "weighted context")
+    if k:
+        assert_close(kappa, torch.softmax(kl.double(), 1), 1e-5, "kappa")
+    # strided context (the RGB slice of a wider feature row), output into a strided buffer
+    if D > 128:
+        wide = torch.zeros(B, rows, D + 128)
+        wide[..., :D] = ctx
+        wd = wide.to(DEV)
+        wc2, attn2, _, _ = ops.row_attention_fwd(wd[..., :D], t.to(DEV), None, k, headings, kl.to(DEV) if k else None)
+        assert torch.equal(wc2, wc) and torch.equal(attn2, attn)
+
+
 @pytest.mark.parametrize("cfg,B", [(SMALL, 5), (FULL, 3), (FULL, 24)])
 def test_soft_dot_attention_fwd_bwd(cfg, B):
     st = {k: v.clone().requires_grad_(True) for k, v in synth.decoder_state(cfg, 0).items()}
