@@ -99,26 +99,30 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
   asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+// Suspending wait: the warp sleeps in hardware until the phase completes (or the hint expires) instead of spinning in the
+// issue slots of the warps that have work (measured: the default try_wait returned ~400 times per wait).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 16); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
     if (done) return;
   }
   __trap();
 }
 
-template <int CS>
+// ROWS / B4W (float4 columns per box row) > 0: compile-time shape (fully unrolled inner loops); 0: taken from the arguments
+template <int CS, int ROWS, int B4W>
 __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap, PipeArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / CS;
-  const int rows = a.rows, chunk = a.chunk, NS = a.nstages, NZ = 2 * a.nstages, nbox = a.nbox, boxw = a.boxw;
+  const int rows = ROWS ? ROWS : a.rows, boxw = B4W ? 4 * B4W : a.boxw;
+  const int chunk = a.chunk, NS = a.nstages, NZ = 2 * a.nstages, nbox = a.nbox;
   const int k = a.shift_k, Hn = a.headings;
   const int rp = rp_rpad(rows);
   const PipeSmem s = rp_carve(smem_raw, a, CS);
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       const bool box_ok = bl < nbox;
       for (int i = 0; i < n; ++i) {
         const int st = i % NS, zs = i % NZ;
-        mbar_wait(&s.full[st], (uint32_t)(i / NS) & 1u);
+        mbar_wait_sleep(&s.full[st], (uint32_t)(i / NS) & 1u);
         const float* tile = s.tile + (size_t)st * s.stage_floats + (box_ok ? bl * a.box_stride : 0);
         const float4* tv4 = reinterpret_cast<const float4*>(s.tv + (size_t)st * chunk + (box_ok ? bl * boxw : 0));
         for (int g = wid; g < groups; g += RP_DWARPS) {
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           if (box_ok && r < rows) {
             const float4* row4 = reinterpret_cast<const float4*>(tile + r * boxw);
-#pragma unroll 4
+#pragma unroll(B4W ? B4W : 4)
             for (int j = 0; j < b4w; ++j) {
               const float4 x = row4[j], y = tv4[j];
               acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
@@ -201,13 +205,14 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
     if (box < nbox) {
       const int b4w = boxw >> 2;
       const int cA = lane, cB = lane + 32;       // boxw <= 256 floats: at most two float4 columns per lane
+      const bool twocol = B4W ? (B4W > 32) : (b4w > 32);           // uniform: no predicated-off second column in the common case
       const bool actA = cA < b4w && box * boxw + 4 * cA < cn;
-      const bool actB = cB < b4w && box * boxw + 4 * cB < cn;
+      const bool actB = twocol && cB < b4w && box * boxw + 4 * cB < cn;
       const int rows4 = rows >> 2;
       for (int i = 0; i < n; ++i) {
         const int st = i % NS;
         const int b = cid + i * a.nclusters;
-        mbar_wait(&s.wready[st], (uint32_t)(i / NS) & 1u);
+        mbar_wait_sleep(&s.wready[st], (uint32_t)(i / NS) & 1u);
         const float* tile = s.tile + (size_t)st * s.stage_floats + (size_t)box * a.box_stride;
         const float4* w4 = reinterpret_cast<const float4*>(s.wts + (size_t)st * rp);
         float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -216,12 +221,12 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
             const float4 x = reinterpret_cast<const float4*>(tile + r * boxw)[cA];
             accA.x = fmaf(wr, x.x, accA.x); accA.y = fmaf(wr, x.y, accA.y); accA.z = fmaf(wr, x.z, accA.z); accA.w = fmaf(wr, x.w, accA.w);
           }
-          if (actB) {
+          if (twocol && actB) {
             const float4 x = reinterpret_cast<const float4*>(tile + r * boxw)[cB];
             accB.x = fmaf(wr, x.x, accB.x); accB.y = fmaf(wr, x.y, accB.y); accB.z = fmaf(wr, x.z, accB.z); accB.w = fmaf(wr, x.w, accB.w);
           }
         };
-#pragma unroll 3
+#pragma unroll(ROWS ? ROWS / 4 : 2)
         for (int g = 0; g < rows4; ++g) {
           const float4 wv = w4[g];
           fma_row(wv.x, 4 * g); fma_row(wv.y, 4 * g + 1); fma_row(wv.z, 4 * g + 2); fma_row(wv.w, 4 * g + 3);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
         kv = ke / warp_sum(ke);
         if (lane < k) kw[lane] = kv;
       }
-      mbar_wait_cluster(&s.zfull[zs], (uint32_t)(i / NZ) & 1u);
+      mbar_wait_sleep(&s.zfull[zs], (uint32_t)(i / NZ) & 1u);
       const float* zb = s.zbuf + (size_t)zs * CS * rp;
       float z0 = -INFINITY, z1 = -INFINITY;
       if (r0ok) {
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
     for (int j = 0; j < n; ++j) {
       const int st = j % NS;
       const int b = cid + j * a.nclusters;
-      if (j >= NS) mbar_wait(&s.empty[st], (uint32_t)(j / NS - 1) & 1u);
+      if (j >= NS) mbar_wait_sleep(&s.empty[st], (uint32_t)(j / NS - 1) & 1u);
       mbar_expect_tx(&s.full[st], stage_tx);
       float* dst = s.tile + (size_t)st * s.stage_floats;
       for (int sb = 0; sb < nbox; ++sb) tma_box_3d(dst + (size_t)sb * a.box_stride, &tmap, c0 + sb * boxw, 0, b, &s.full[st]);
@@ -331,9 +336,9 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int CS>
+template <int CS, int ROWS, int B4W>
 int launch_pipe(const CUtensorMap& tmap, PipeArgs a, size_t smem, cudaStream_t st) {
-  auto kern = row_attention_fwd_pipe_kernel<CS>;
+  auto kern = row_attention_fwd_pipe_kernel<CS, ROWS, B4W>;
   static int max_clusters = -1;                  // per (CS) instantiation; the smem request below is the worst case
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe attr", e); return DASA_ERR_CUDA; }
@@ -411,5 +416,8 @@ int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t l
   PipeArgs a{t, ld_t, kappa_logits, ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out,
              B, rows, D, chunk, nbox, boxw, best_stride, shift_k, headings, ns, 0};
   const size_t smem = rp_smem_bytes(rows, chunk, nbox, best_stride, cs, ns, shift_k);
-  return cs == 8 ? launch_pipe<8>(tmap, a, smem, st) : launch_pipe<16>(tmap, a, smem, st);
+  const int b4 = boxw / 4;
+  if (cs == 8 && rows == 36 && b4 == 17) return launch_pipe<8, 36, 17>(tmap, a, smem, st);      // 36 views x (2048 + 128)
+  if (cs == 16 && rows == 36 && b4 == 33) return launch_pipe<16, 36, 33>(tmap, a, smem, st);    // 36 views x (4096 + 128)
+  return cs == 8 ? launch_pipe<8, 0, 0>(tmap, a, smem, st) : launch_pipe<16, 0, 0>(tmap, a, smem, st);
 }
