@@ -7,7 +7,7 @@
 //     nbox TMA boxes [rows x boxw] (boxw*4 bytes is an odd multiple of 16 when the shape allows it, so that 8 consecutive
 //     rows fall into 8 different 16-byte bank groups) + the target slice (bulk copy), completing on the stage's `full`.
 //   * producer warp : waits `empty[stage]`, issues the TMA loads of the next sample;
-//   * dot warps     : lane = (row of an 8-row group, box): one box-row dot product per lane, 2 shuffles to add the boxes,
+//   * dot warps     : lane = (row of an 8-row group, box), two groups per warp: box-row dot products, 2 shuffles to add the boxes,
 //                     partial sums PUSHED into every CTA of the cluster with st.async (data + complete_tx on the receiver's
 //                     `zfull` mbarrier - no cluster-wide barrier anywhere in the loop);
 //   * softmax warps : (4, round-robin over samples) wait `zfull`, add the CS partials in fixed rank order (all CTAs get
@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int RP_DWARPS = 8;          // dot-product warps (ceil(rows/8) of them are active)
+constexpr int RP_DWARPS = 4;          // dot-product warps, 16 rows each (ceil(rows/16) of them are active)
 constexpr int RP_MAX_BOX = 4;         // boxes per slice = weighted-sum warps
 constexpr int RP_SWARPS = 4;          // softmax warps
 constexpr int RP_WARPS = RP_DWARPS + RP_MAX_BOX + RP_SWARPS + 1;
@@ -36,6 +36,7 @@ struct PipeArgs {
   const float* kappa_logits; int64_t ld_kappa;
   float* wc; int64_t ld_wc; float* attn_out; float* q_out; float* kappa_out;
   int B, rows, D, chunk, nbox, boxw, box_stride, shift_k, headings, nstages, nclusters;   // box_stride in floats
+  long long* trace;      // debug: [CTA][sample][8] SM-clock stamps of the pipeline hand-offs (nullptr in production)
 };
 
 // Shared memory of one CTA. NS stages; the partial-dot exchange ring is 2*NS deep: a peer can push sample j only after this
@@ -99,23 +100,35 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
   asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
 }
-// Suspending wait: the warp sleeps in hardware until the phase completes (or the hint expires) instead of spinning in the
-// issue slots of the warps that have work (measured: the default try_wait returned ~400 times per wait).
+// Waiting warps back off with nanosleep: a bare try_wait loop retried ~35 times per wait (measured) and took a third of the
+// SM's issue slots away from the warps that had work.
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 16); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
-    if (done) return;
+  if (mbar_try(bar, parity)) return;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    __nanosleep(32);
+    if (mbar_try(bar, parity)) return;
   }
   __trap();
 }
+__device__ __forceinline__ float warp_max_f32(float v) {       // sm_100a: one REDUX instead of five shuffle steps
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
 
 // ROWS / B4W (float4 columns per box row) > 0: compile-time shape (fully unrolled inner loops); 0: taken from the arguments
-template <int CS, int ROWS, int B4W>
+// KT > 0: compile-time shift taps (source rows hoisted into registers, fully unrolled); 0: runtime k through the table
+template <int CS, int ROWS, int B4W, int KT>
 __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap, PipeArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
   const int cid = blockIdx.x / CS;
   const int rows = ROWS ? ROWS : a.rows, boxw = B4W ? 4 * B4W : a.boxw;
   const int chunk = a.chunk, NS = a.nstages, NZ = 2 * a.nstages, nbox = a.nbox;
-  const int k = a.shift_k, Hn = a.headings;
+  const int k = KT ? KT : a.shift_k, Hn = a.headings;
   const int rp = rp_rpad(rows);
   const PipeSmem s = rp_carve(smem_raw, a, CS);
   const int c0 = rank * chunk;
@@ -131,6 +144,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = (a.B - cid + a.nclusters - 1) / a.nclusters;          // samples of this cluster: cid, cid + nclusters, ...
   const uint32_t z_tx = (uint32_t)CS * (uint32_t)rows * 4u;
+  long long* trace = a.trace ? a.trace + (size_t)blockIdx.x * 8 * ((a.B + a.nclusters - 1) / a.nclusters) : nullptr;
+#define RP_STAMP(i_, slot_) do { if (trace && lane == 0) trace[(size_t)(i_) * 8 + (slot_)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -158,10 +173,11 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
   cluster.sync();                               // every peer's barriers are initialised before any st.async reaches them
 
   if (wid < RP_DWARPS) {
-    // ---------------------------------------------------- dot warps: lane = (row rl of an 8-row group, box bl)
+    // ------------------------- dot warps: lane = (row rl of an 8-row group, box bl), two 8-row groups per warp (one target
+    // load feeds two rows: the broadcast target loads cost as many shared-memory wavefronts as the tile loads)
     const int rl = lane & 7, bl = lane >> 3;
-    const int groups = (rows + 7) >> 3;
-    if (wid < groups) {
+    const int pairs = (rows + 15) >> 4;
+    if (wid < pairs) {
       constexpr int PP = CS / 4;                 // peers served by one lane
       uint32_t zb_remote[PP], zf_remote[PP];
 #pragma unroll
@@ -171,32 +187,50 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       }
       const int b4w = boxw >> 2;
       const bool box_ok = bl < nbox;
+      const int rA = wid * 16 + rl, rB = rA + 8;
+      const bool okA = box_ok && rA < rows, okB = box_ok && rB < rows;
+      // branch-free: lanes without a row / box re-read a valid address (broadcast, no extra wavefronts) and are masked below,
+      // so the unrolled loads are not fenced in by a divergent region and run ahead of the FMAs
+      const int offA = min(rA, rows - 1) * boxw, offB = min(rB, rows - 1) * boxw;
       for (int i = 0; i < n; ++i) {
         const int st = i % NS, zs = i % NZ;
         mbar_wait_sleep(&s.full[st], (uint32_t)(i / NS) & 1u);
+        if (wid == 0) RP_STAMP(i, 1);
         const float* tile = s.tile + (size_t)st * s.stage_floats + (box_ok ? bl * a.box_stride : 0);
         const float4* tv4 = reinterpret_cast<const float4*>(s.tv + (size_t)st * chunk + (box_ok ? bl * boxw : 0));
-        for (int g = wid; g < groups; g += RP_DWARPS) {
-          const int r = g * 8 + rl;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (box_ok && r < rows) {
-            const float4* row4 = reinterpret_cast<const float4*>(tile + r * boxw);
+        const float4* rowA = reinterpret_cast<const float4*>(tile + offA);
+        const float4* rowB = reinterpret_cast<const float4*>(tile + offB);
+        float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wid * 16 + 8 < rows) {               // uniform: the warp's second 8-row group exists
 #pragma unroll(B4W ? B4W : 4)
-            for (int j = 0; j < b4w; ++j) {
-              const float4 x = row4[j], y = tv4[j];
-              acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
-              acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
-            }
+          for (int j = 0; j < b4w; ++j) {
+            const float4 y = tv4[j], xa = rowA[j], xb = rowB[j];
+            accA.x = fmaf(xa.x, y.x, accA.x); accA.y = fmaf(xa.y, y.y, accA.y);
+            accA.z = fmaf(xa.z, y.z, accA.z); accA.w = fmaf(xa.w, y.w, accA.w);
+            accB.x = fmaf(xb.x, y.x, accB.x); accB.y = fmaf(xb.y, y.y, accB.y);
+            accB.z = fmaf(xb.z, y.z, accB.z); accB.w = fmaf(xb.w, y.w, accB.w);
           }
-          float v = (acc.x + acc.y) + (acc.z + acc.w);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (r < rows) {
-#pragma unroll
-            for (int pp = 0; pp < PP; ++pp)    // peer bl*PP+pp: zbuf[zs][my rank][r]
-              st_async_f32(zb_remote[pp] + 4u * (uint32_t)((zs * CS + rank) * rp + r), v, zf_remote[pp] + 8u * (uint32_t)zs);
+        } else {
+#pragma unroll(B4W ? B4W : 4)
+          for (int j = 0; j < b4w; ++j) {
+            const float4 y = tv4[j], xa = rowA[j];
+            accA.x = fmaf(xa.x, y.x, accA.x); accA.y = fmaf(xa.y, y.y, accA.y);
+            accA.z = fmaf(xa.z, y.z, accA.z); accA.w = fmaf(xa.w, y.w, accA.w);
           }
         }
+        float vA = okA ? (accA.x + accA.y) + (accA.z + accA.w) : 0.f;
+        float vB = okB ? (accB.x + accB.y) + (accB.z + accB.w) : 0.f;
+        vA += __shfl_xor_sync(0xffffffffu, vA, 8);
+        vB += __shfl_xor_sync(0xffffffffu, vB, 8);
+        vA += __shfl_xor_sync(0xffffffffu, vA, 16);
+        vB += __shfl_xor_sync(0xffffffffu, vB, 16);
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {        // peer bl*PP+pp: zbuf[zs][my rank][row]
+          const uint32_t dst = zb_remote[pp] + 4u * (uint32_t)((zs * CS + rank) * rp), bar = zf_remote[pp] + 8u * (uint32_t)zs;
+          if (rA < rows) st_async_f32(dst + 4u * (uint32_t)rA, vA, bar);
+          if (rB < rows) st_async_f32(dst + 4u * (uint32_t)rB, vB, bar);
+        }
+        if (wid == 0) RP_STAMP(i, 2);
       }
     }
   } else if (wid < RP_DWARPS + RP_MAX_BOX) {
@@ -204,24 +238,25 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
     const int box = wid - RP_DWARPS;
     if (box < nbox) {
       const int b4w = boxw >> 2;
-      const int cA = lane, cB = lane + 32;       // boxw <= 256 floats: at most two float4 columns per lane
+      const int cA = min(lane, b4w - 1), cB = min(lane + 32, b4w - 1);   // boxw <= 256 floats: at most two float4 columns per lane
       const bool twocol = B4W ? (B4W > 32) : (b4w > 32);           // uniform: no predicated-off second column in the common case
-      const bool actA = cA < b4w && box * boxw + 4 * cA < cn;
-      const bool actB = twocol && cB < b4w && box * boxw + 4 * cB < cn;
+      const bool actA = lane < b4w && box * boxw + 4 * cA < cn;          // inactive lanes re-read a valid column (broadcast) and do not store
+      const bool actB = twocol && lane + 32 < b4w && box * boxw + 4 * cB < cn;
       const int rows4 = rows >> 2;
       for (int i = 0; i < n; ++i) {
         const int st = i % NS;
         const int b = cid + i * a.nclusters;
         mbar_wait_sleep(&s.wready[st], (uint32_t)(i / NS) & 1u);
+        if (box == 0) RP_STAMP(i, 5);
         const float* tile = s.tile + (size_t)st * s.stage_floats + (size_t)box * a.box_stride;
         const float4* w4 = reinterpret_cast<const float4*>(s.wts + (size_t)st * rp);
         float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = make_float4(0.f, 0.f, 0.f, 0.f);
         auto fma_row = [&](float wr, int r) {
-          if (actA) {
+          {
             const float4 x = reinterpret_cast<const float4*>(tile + r * boxw)[cA];
             accA.x = fmaf(wr, x.x, accA.x); accA.y = fmaf(wr, x.y, accA.y); accA.z = fmaf(wr, x.z, accA.z); accA.w = fmaf(wr, x.w, accA.w);
           }
-          if (twocol && actB) {
+          if (twocol) {
             const float4 x = reinterpret_cast<const float4*>(tile + r * boxw)[cB];
             accB.x = fmaf(wr, x.x, accB.x); accB.y = fmaf(wr, x.y, accB.y); accB.z = fmaf(wr, x.z, accB.z); accB.w = fmaf(wr, x.w, accB.w);
           }
@@ -234,6 +269,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
         for (int r = 4 * rows4; r < rows; ++r) fma_row(s.wts[(size_t)st * rp + r], r);
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.empty[st]);                   // this warp no longer needs the stage
+        if (box == 0) RP_STAMP(i, 6);
         float* dst = a.wc + (int64_t)b * a.ld_wc + c0 + box * boxw;
         if (actA) stg_stream4(dst + 4 * cA, accA);
         if (actB) stg_stream4(dst + 4 * cB, accB);
@@ -245,6 +281,14 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
     float* pw = s.pscr + (size_t)sw * (rp + 16);
     float* kw = pw + rp;
     const bool r0ok = lane < rows, r1ok = lane + 32 < rows;
+    int src0[KT ? KT : 1], src1[KT ? KT : 1];
+    if (KT) {
+#pragma unroll
+      for (int jj = 0; jj < (KT ? KT : 1); ++jj) {
+        src0[jj] = r0ok ? s.tab[lane * k + jj] : 0;
+        src1[jj] = r1ok ? s.tab[(lane + 32) * k + jj] : 0;
+      }
+    }
     for (int i = sw; i < n; i += RP_SWARPS) {
       const int st = i % NS, zs = i % NZ;
       const int b = cid + i * a.nclusters;
@@ -252,12 +296,13 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       float kv = 0.f;
       if (k > 0) {                               // independent of the exchange: done while the partial dots are in flight
         const float kl = (lane < k) ? a.kappa_logits[(int64_t)b * a.ld_kappa + lane] : -INFINITY;
-        const float kmx = warp_max(kl);
+        const float kmx = warp_max_f32(kl);
         const float ke = (lane < k) ? expf(kl - kmx) : 0.f;
         kv = ke / warp_sum(ke);
         if (lane < k) kw[lane] = kv;
       }
       mbar_wait_sleep(&s.zfull[zs], (uint32_t)(i / NZ) & 1u);
+      RP_STAMP(i, 3);
       const float* zb = s.zbuf + (size_t)zs * CS * rp;
       float z0 = -INFINITY, z1 = -INFINITY;
       if (r0ok) {
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
         for (int c = 0; c < CS; ++c) z1 += zb[c * rp + lane + 32];
       }
       if (lane == 0) mbar_expect_tx(&s.zfull[zs], z_tx);            // re-arm the slot for sample i + 2*NS
-      const float mx = warp_max(fmaxf(z0, z1));
+      const float mx = warp_max_f32(fmaxf(z0, z1));
       const float e0 = r0ok ? expf(z0 - mx) : 0.f;
       const float e1 = r1ok ? expf(z1 - mx) : 0.f;
       const float inv = 1.f / warp_sum(e0 + e1);
@@ -282,16 +327,28 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
         if (r1ok) pw[lane + 32] = p1;
         __syncwarp();
         float q0 = 0.f, q1 = 0.f;
-        if (r0ok) {
-          for (int jj = 0; jj < k; ++jj) q0 = fmaf(kw[jj], pw[s.tab[lane * k + jj]], q0);
-          w[lane] = q0;
-        }
-        if (r1ok) {
-          for (int jj = 0; jj < k; ++jj) q1 = fmaf(kw[jj], pw[s.tab[(lane + 32) * k + jj]], q1);
-          w[lane + 32] = q1;
+        if (KT) {                                // independent loads, no table look-up on the critical path
+#pragma unroll
+          for (int jj = 0; jj < (KT ? KT : 1); ++jj) {
+            const float kj = kw[jj];
+            q0 = fmaf(kj, pw[src0[jj]], q0);
+            q1 = fmaf(kj, pw[src1[jj]], q1);
+          }
+          if (r0ok) w[lane] = q0;
+          if (r1ok) w[lane + 32] = q1;
+        } else {
+          if (r0ok) {
+            for (int jj = 0; jj < k; ++jj) q0 = fmaf(kw[jj], pw[s.tab[lane * k + jj]], q0);
+            w[lane] = q0;
+          }
+          if (r1ok) {
+            for (int jj = 0; jj < k; ++jj) q1 = fmaf(kw[jj], pw[s.tab[(lane + 32) * k + jj]], q1);
+            w[lane + 32] = q1;
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.wready[st]);                  // release: weights visible to the weighted-sum warps
+        RP_STAMP(i, 4);
         if (writer) {
           if (a.q_out) {
             if (r0ok) a.q_out[(int64_t)b * rows + lane] = q0;
@@ -322,23 +379,27 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       const int st = j % NS;
       const int b = cid + j * a.nclusters;
       if (j >= NS) mbar_wait_sleep(&s.empty[st], (uint32_t)(j / NS - 1) & 1u);
+      RP_STAMP(j, 0);
       mbar_expect_tx(&s.full[st], stage_tx);
       float* dst = s.tile + (size_t)st * s.stage_floats;
       for (int sb = 0; sb < nbox; ++sb) tma_box_3d(dst + (size_t)sb * a.box_stride, &tmap, c0 + sb * boxw, 0, b, &s.full[st]);
       if (cn > 0) bulk_g2s(s.tv + (size_t)st * chunk, a.t + (int64_t)b * a.ld_t + c0, (uint32_t)cn * 4u, &s.full[st]);
     }
   }
+#undef RP_STAMP
   __syncwarp();
   cluster.sync();                                // nobody exits while a peer may still push into its shared memory
 }
+
+long long* g_trace = nullptr;   // set by dasa_debug_row_attention_trace (profiling scripts only)
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int CS, int ROWS, int B4W>
+template <int CS, int ROWS, int B4W, int KT>
 int launch_pipe(const CUtensorMap& tmap, PipeArgs a, size_t smem, cudaStream_t st) {
-  auto kern = row_attention_fwd_pipe_kernel<CS, ROWS, B4W>;
+  auto kern = row_attention_fwd_pipe_kernel<CS, ROWS, B4W, KT>;
   static int max_clusters = -1;                  // per (CS) instantiation; the smem request below is the worst case
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe attr", e); return DASA_ERR_CUDA; }
@@ -414,10 +475,16 @@ int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t l
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DASA_ERR_UNSUPPORTED;
   PipeArgs a{t, ld_t, kappa_logits, ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out,
-             B, rows, D, chunk, nbox, boxw, best_stride, shift_k, headings, ns, 0};
+             B, rows, D, chunk, nbox, boxw, best_stride, shift_k, headings, ns, 0, g_trace};
   const size_t smem = rp_smem_bytes(rows, chunk, nbox, best_stride, cs, ns, shift_k);
   const int b4 = boxw / 4;
-  if (cs == 8 && rows == 36 && b4 == 17) return launch_pipe<8, 36, 17>(tmap, a, smem, st);      // 36 views x (2048 + 128)
-  if (cs == 16 && rows == 36 && b4 == 33) return launch_pipe<16, 36, 33>(tmap, a, smem, st);    // 36 views x (4096 + 128)
-  return cs == 8 ? launch_pipe<8, 0, 0>(tmap, a, smem, st) : launch_pipe<16, 0, 0>(tmap, a, smem, st);
+  if (cs == 8 && rows == 36 && b4 == 17 && shift_k == 5) return launch_pipe<8, 36, 17, 5>(tmap, a, smem, st);     // 36 x (2048+128), k=5
+  if (cs == 16 && rows == 36 && b4 == 33 && shift_k == 5) return launch_pipe<16, 36, 33, 5>(tmap, a, smem, st);   // 36 x (4096+128), k=5
+  return cs == 8 ? launch_pipe<8, 0, 0, 0>(tmap, a, smem, st) : launch_pipe<16, 0, 0, 0>(tmap, a, smem, st);
+}
+
+// Debug hook for scripts/: stamps of the pipeline hand-offs go to `buf` ([CTAs][ceil(B/clusters)][8] int64); nullptr = off.
+extern "C" int dasa_debug_row_attention_trace(void* buf) {
+  g_trace = static_cast<long long*>(buf);
+  return DASA_OK;
 }

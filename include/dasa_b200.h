@@ -111,6 +111,11 @@ int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t ld_sample, 
                            const float* t, int64_t ld_t, const uint8_t* mask, int64_t ld_mask,
                            int shift_k, int headings, const float* kappa_logits, int64_t ld_kappa,
                            float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, void* stream);
+/* Debug hook (scripts/ only): when buf != NULL the large-batch pipelined forward writes SM-clock stamps of its hand-offs
+ * (producer issue, dots start/end, softmax start/end, weighted-sum start/end) to buf[CTA][ceil(B/clusters)][8] (int64).
+ * Pass NULL to switch it off. Not used by the product path. */
+int dasa_debug_row_attention_trace(void* buf);
+
 /* backward (Appendix A, K3 / K4): given dwc -> dctx (may be NULL), dt, dkappa_logits (shift only).
  * dctx_accumulate != 0 adds into dctx instead of overwriting it.                                                  */
 int dasa_row_attention_bwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,

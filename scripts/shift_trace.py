@@ -1,0 +1,34 @@
+"""GPU helper: per-sample hand-off timeline of the pipelined view-attention kernel (SM clock cycles, CTA-local)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dasa_b200 import ops, lib
+B, V, F = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 36, 2176
+f = torch.rand(B, V, F, device="cuda"); t = torch.randn(B, F, device="cuda") * 0.05; kl = torch.randn(B, 5, device="cuda")
+for _ in range(3):
+    ops.row_attention_fwd(f, t, None, 5, 12, kl)
+torch.cuda.synchronize()
+NCL = 15                         # clusters resident on this part (cudaOccupancyMaxActiveClusters)
+nper = (B + NCL - 1) // NCL
+tr = torch.zeros(NCL * 8, nper, 8, dtype=torch.int64, device="cuda")
+lib.load().dasa_debug_row_attention_trace(tr.data_ptr())
+ops.row_attention_fwd(f, t, None, 5, 12, kl)
+torch.cuda.synchronize()
+lib.load().dasa_debug_row_attention_trace(None)
+tr = tr.cpu().double()
+names = ["P issue", "D full", "D pushed", "S zfull", "S publish", "W start", "W release"]
+for cta in (0, 3, 60):
+    x = tr[cta]
+    ok = (x[:, :7] > 0).all(1)
+    n = int(ok.sum())
+    x = x[:n]
+    mid = slice(20, n - 20)
+    print("CTA %d: %d samples; period per sample (cycles): %s" % (cta, n, ["%.0f" % float((x[mid, k][1:] - x[mid, k][:-1]).mean()) for k in range(7)]))
+    for k in range(6):
+        d = x[mid, k + 1] - x[mid, k]
+        print("   %-10s -> %-10s mean %7.0f  p10 %7.0f  p90 %7.0f" % (names[k], names[k + 1], float(d.mean()), float(d.quantile(0.1)), float(d.quantile(0.9))))
+    NS = 5
+    d = x[NS:, 0][20:-20] - x[:-NS, 6][20:-20]
+    print("   W release(i) -> P issue(i+%d) mean %7.0f" % (NS, float(d.mean())))
+    d = x[mid, 6] - x[mid, 0]
+    print("   stage residency (P issue -> W release) mean %7.0f" % float(d.mean()))
