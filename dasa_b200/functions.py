@@ -383,3 +383,40 @@ class MaskedCEFn(torch.autograd.Function):
     def backward(ctx, dloss, _da):
         (dlogit,) = ctx.saved_tensors
         return dlogit * dloss, None, None
+
+
+class PolicySampleFn(torch.autograd.Function):
+    """feedback='sample' action selection (agent_dg.py:876-882): returns (action[B], log_prob[B], entropy[B]).
+    `u` = one uniform per episode (device RNG) or None with `action_in` (injected actions, tests) / argmax."""
+
+    @staticmethod
+    def forward(ctx, logit, u, action_in):
+        action, lp, ent, probs = ops.policy_sample_fwd(logit.contiguous(), u, action_in)
+        ctx.save_for_backward(probs, action, ent)
+        ctx.mark_non_differentiable(action)
+        return action, lp, ent
+
+    @staticmethod
+    def backward(ctx, _da, dlp, dent):
+        probs, action, ent = ctx.saved_tensors
+        dlp = dlp.contiguous() if dlp is not None else None
+        dent = dent.contiguous() if dent is not None else None
+        return ops.policy_sample_bwd(probs, action, dlp, dent, ent), None, None
+
+
+class A2CLossFn(torch.autograd.Function):
+    """The A2C epilogue of vl_rollout (agent_dg.py:943-999) as one fused kernel over [T,B] stacks: returns (loss[1], total[1])."""
+
+    @staticmethod
+    def forward(ctx, logp, ent, value, last_value, reward, mask, ended, gamma, ent_coef, normalize):
+        loss, total, dlogp, dent, dvalue = ops.a2c_loss(logp.contiguous(), None if ent is None else ent.contiguous(),
+                                                        value.contiguous(), last_value.contiguous(), reward, mask, ended,
+                                                        gamma, ent_coef, normalize)
+        ctx.save_for_backward(dlogp, dent, dvalue)
+        ctx.mark_non_differentiable(total)
+        return loss, total
+
+    @staticmethod
+    def backward(ctx, dloss, _dt):
+        dlogp, dent, dvalue = ctx.saved_tensors
+        return dlogp * dloss, (None if dent is None else dent * dloss), dvalue * dloss, None, None, None, None, None, None, None

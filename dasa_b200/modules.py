@@ -286,6 +286,14 @@ class Critic(nn.Module):
         x = _drop(x, "critic", self.p, self.training)
         return Fn.linear(x, self.state2value[3].weight, self.state2value[3].bias).squeeze()
 
+    def forward_steps(self, states, steps):
+        """The critic over the hidden states of `steps` actions stacked along dim 0 ([steps*B, dim]) in one batched call
+        (the reference calls it once per action, agent_dg.py:977); dropout masks follow the per-step tags 't<i>.critic'."""
+        x = Fn.linear(states, self.state2value[0].weight, self.state2value[0].bias, "relu")
+        m, scale = _source.mask_steps("critic", (states.shape[0] // steps, self.dim), self.p, self.training, states.device, steps)
+        x = Fn.dropout(x, m, scale)
+        return Fn.linear(x, self.state2value[3].weight, self.state2value[3].bias).reshape(-1)
+
 
 # -------------------------------------------------------------------------------------------------------- encoder
 class _BertSelfAttention(nn.Module):

@@ -431,6 +431,47 @@ def masked_ce(logit, target, ignore_index, grad_scale, loss_acc, want_grad=True,
     return dlogit, action, lp, ent
 
 
+def policy_sample_fwd(logit, u=None, action_in=None, want_probs=True):
+    """Categorical(softmax(logit)): (action, log_prob(action), entropy, probs). action = action_in | sample(u) | argmax."""
+    B, Nc = logit.shape
+    assert logit.stride(1) == 1
+    dev = logit.device
+    action = torch.empty(B, device=dev, dtype=torch.int64)
+    lp = torch.empty(B, device=dev, dtype=torch.float32)
+    ent = torch.empty(B, device=dev, dtype=torch.float32)
+    probs = torch.empty(B, Nc, device=dev, dtype=torch.float32) if want_probs else None
+    call("dasa_policy_sample_fwd", _p(logit), logit.stride(0), B, Nc, _p(u), _p(action_in), _p(action), _p(lp), _p(ent),
+         _p(probs), _stream())
+    return action, lp, ent, probs
+
+
+def policy_sample_bwd(probs, action, dlogp, dent, entropy):
+    B, Nc = probs.shape
+    dlogit = torch.empty(B, Nc, device=probs.device, dtype=torch.float32)
+    call("dasa_policy_sample_bwd", _p(probs), _p(action), _p(dlogp), _p(dent), _p(entropy), B, Nc, _p(dlogit), Nc, _stream())
+    return dlogit
+
+
+def nav_reward(action, cand_leng, ignore_id, dist, last_dist, ended, reward, mask):
+    call("dasa_nav_reward", _p(action), _p(cand_leng), int(ignore_id), _p(dist), _p(last_dist), _p(ended), _p(reward), _p(mask),
+         action.numel(), _stream())
+
+
+def a2c_loss(logp, ent, value, last_value, reward, mask, ended, gamma, ent_coef, normalize):
+    """Returns (loss[1], total[1], dlogp, dent, dvalue) for [T,B] stacks (contiguous)."""
+    T, B = logp.shape
+    dev = logp.device
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    total = torch.empty(1, device=dev, dtype=torch.float32)
+    dlogp = torch.empty(T, B, device=dev, dtype=torch.float32)
+    dvalue = torch.empty(T, B, device=dev, dtype=torch.float32)
+    dent = torch.empty(T, B, device=dev, dtype=torch.float32) if ent is not None else None
+    call("dasa_a2c_loss", _p(logp), _p(ent), _p(value), _p(last_value), _p(reward), _p(mask), _p(ended), float(gamma),
+         float(ent_coef), {"none": 0, "total": 1, "batch": 2}[normalize], T, B, _p(loss), _p(total), _p(dlogp), _p(dent),
+         _p(dvalue), _stream())
+    return loss, total, dlogp, dent, dvalue
+
+
 def rmsprop_step(param, grad, square_avg, lr, alpha=0.99, eps=1e-8, weight_decay=0.0, clip_coef=None):
     call("dasa_rmsprop_step", _p(param), _p(grad), _p(square_avg), param.numel(), float(lr), float(alpha), float(eps),
          float(weight_decay), _p(clip_coef), _stream())

@@ -29,6 +29,7 @@ class DeviceEpisodes:
         self.seq = ep.seq.to(device)
         self.seq_mask = ep.seq_mask.to(device)
         self.seq_lengths = ep.seq_lengths.to(device).to(torch.int32)
+        self.dist = ep.dist.to(device) if hasattr(ep, "dist") else None      # [T+1, B] goal distances (sampled feedback)
         self.resident = resident
         if resident:
             for k in self.FIELDS:
@@ -86,7 +87,7 @@ class NavPolicy:
                     p.grad.zero_()
 
     # ------------------------------------------------------------------------------------------------ one nav step
-    def step(self, ep, t, carry, lang_out=None):
+    def step(self, ep, t, carry, lang_out=None, want_ctx=False):
         """Loop body of vl_rollout up to the masked logits (agent_dg.py:727-841). carry = None at t == 0."""
         cfg, tr = self.cfg, self.decoder.training
         a_t, f_t, d_t, cand, cand_d, leng, _ = ep.step(t)
@@ -101,6 +102,8 @@ class NavPolicy:
         prev_h1, c_0 = (en_h, en_c) if carry is None else carry
         h_t, c_t, logit, h1, _ = self.decoder(a_t, df_t, cand_g, prev_h1, prev_h1, c_0, ctx, ep.seq_mask,
                                               already_dropfeat=True, cand_leng=leng)
+        if want_ctx:
+            return logit, h_t, (h1, c_t), ctx
         return logit, h_t, (h1, c_t)
 
     # ------------------------------------------------------------------------------------------- teacher-forced rollout
@@ -162,6 +165,50 @@ class NavPolicy:
             actions.append(a_t)
         src.prefix = base_prefix
         return total * (ml_weight / ep.B), logits, actions
+
+    # ------------------------------------------------------------------------------- sampled feedback + A2C (a10, a11)
+    def sample_rollout(self, ep, T=None, actions_in=None, gamma=0.9, ent_coef=0.01, normalize="total", tag_steps=True):
+        """feedback='sample', train_rl=True, train_ml=None (agent_dg.py:725-999) over a pre-generated observation stream
+        holding T+1 observations and goal distances `ep.dist` [T+1,B] (there is no simulator offline). Per action:
+        AdaIN -> encoder -> decoder -> Categorical sample (device RNG, or `actions_in[t]` injected) with log-prob and entropy
+        -> reward / mask / ended kernel; then the extra decoder + critic call on the next observation, the critic over all T
+        hidden states as ONE batch, and the fused A2C epilogue. Nothing is read back to the host inside the rollout.
+        Returns (loss [1], dict)."""
+        T = (ep.T - 1) if T is None else T
+        assert ep.resident and ep.dist is not None and ep.T >= T + 1, "sample_rollout needs T+1 resident observations + dist"
+        cfg, B, dev = self.cfg, ep.B, ep.f_t.device
+        src = M.dropout_source()
+        base_prefix = src.prefix
+        ended = torch.zeros(B, dtype=torch.uint8, device=dev)
+        reward = torch.empty(T, B, device=dev)
+        mask = torch.empty(T, B, device=dev)
+        carry, ctx, hidden, logps, ents, actions, logits = None, None, [], [], [], [], []
+        lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T) if self.batch_language else None
+        for t in range(T):
+            if tag_steps:
+                src.prefix = base_prefix + "t%d." % t
+            logit, h_t, carry, ctx = self.step(ep, t, carry, None if lang_all is None else lang_all[t], want_ctx=True)
+            hidden.append(h_t)
+            logits.append(logit)
+            u = torch.rand(B, device=dev) if actions_in is None else None
+            a_t, lp, en = Fn.PolicySampleFn.apply(logit, u, None if actions_in is None else actions_in[t])
+            ops.nav_reward(a_t, ep.cand_leng[t], cfg.ignore_id, ep.dist[t + 1], ep.dist[t], ended, reward[t], mask[t])
+            logps.append(lp)
+            ents.append(en)
+            actions.append(a_t)
+        # last action in A2C (agent_dg.py:945-957): the decoder sees the RAW next observation and applies its own drop_env
+        a_n, f_n, _, cand_n, _, _, _ = ep.step(T)
+        src.prefix = base_prefix + "last."
+        h1, c_t = carry
+        last_h, _, _, _, _ = self.decoder(a_n, f_n.clone(), cand_n.clone(), hidden[-1], h1, c_t, ctx, ep.seq_mask,
+                                          already_dropfeat=False)
+        last_value = self.critic(last_h).detach().reshape(B)
+        src.prefix = base_prefix
+        values = self.critic.forward_steps(torch.cat(hidden, 0), T).view(T, B)       # a8: one batched call, per-step masks
+        loss, total = Fn.A2CLossFn.apply(torch.stack(logps), torch.stack(ents), values, last_value, reward, mask, ended,
+                                         gamma, ent_coef, normalize)
+        return loss, {"logits": logits, "actions": actions, "logps": logps, "ents": ents, "values": values,
+                      "last_value": last_value, "reward": reward, "mask": mask, "ended": ended, "total": total}
 
     def backward(self, loss):
         """loss.backward() + the deferred, batched weight-gradient GEMMs (functions.defer_weight_grads)."""

@@ -236,6 +236,10 @@ class Episodes:
                     self.target[t, b] = n                                       # STOP = END row
                 else:
                     self.target[t, b] = int(torch.randint(0, n, (1,), generator=g))
+        # distance to the goal before action t (dist[t]) and after it (dist[t+1]) for the sampled-feedback reward
+        # (agent_dg.py:906-925): a random walk that never stands still; drawn last so earlier fields keep their bits
+        steps = (torch.rand(T, B, generator=g) * 2.0 + 0.5) * torch.where(torch.rand(T, B, generator=g) < 0.6, -1.0, 1.0)
+        self.dist = torch.cat([torch.rand(1, B, generator=g) * 10.0 + 4.0, steps], 0).cumsum(0).abs().float()
         if pin and torch.cuda.is_available():
             for k in ("input_a_t", "f_t", "d_t", "cand_feat", "cand_dfeat", "cand_leng", "target"):
                 setattr(self, k, getattr(self, k).pin_memory())

@@ -240,6 +240,27 @@ int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* target, int ig
                    float grad_scale, float* loss_acc, float* dlogit, int64_t* action, float* logprob_action,
                    float* entropy, void* stream);
 
+/* ------------------------------------------------------------------------------- sampled feedback / A2C (a10, a11)
+ * feedback='sample' (agent_dg.py:876-882): probs = softmax(logit); entropy = Categorical(probs).entropy();
+ * action = injected (action_in != NULL) | inverse-CDF sample with the uniform u[b] (u != NULL) | argmax;
+ * logprob = log probs[action]. probs [B,Nc] is kept for the backward:
+ *   dlogit_j = dlogp (delta_aj - p_j) - dent p_j (log p_j + H).                                                      */
+int dasa_policy_sample_fwd(const float* logit, int64_t ld, int B, int Nc, const float* u, const int64_t* action_in,
+                           int64_t* action, float* logprob, float* entropy, float* probs, void* stream);
+int dasa_policy_sample_bwd(const float* probs, const int64_t* action, const float* dlogp, const float* dent,
+                           const float* entropy, int B, int Nc, float* dlogit, int64_t ld, void* stream);
+/* reward / mask / ended bookkeeping of one action (agent_dg.py:890-930): END = last candidate or ignore id; reward +-2 on
+ * END by dist < 3, else sign of the distance reduction; mask = 0 for episodes that had already ended; ended |= END.   */
+int dasa_nav_reward(const int64_t* action, const int32_t* cand_leng, int ignore_id, const float* dist,
+                    const float* last_dist, uint8_t* ended, float* reward, float* mask, int B, void* stream);
+/* A2C epilogue (agent_dg.py:943-999) over [T,B] stacks: R_b = ended_b ? 0 : last_value_b; for t = T-1..0:
+ *   R = R*gamma + reward_t; a = R - value_t; loss += sum_b (-logp_t a m_t + 0.5 a^2 m_t - ent_coef ent_t m_t); total += m_t;
+ * loss /= total (normalize 1) | B (2) | 1 (0). Also writes dloss/dlogp, dloss/dent, dloss/dvalue (the advantage in the
+ * policy term is detached, as in the reference). ent / dent may be NULL (feedback='argmax').                          */
+int dasa_a2c_loss(const float* logp, const float* ent, const float* value, const float* last_value, const float* reward,
+                  const float* mask, const uint8_t* ended, float gamma, float ent_coef, int normalize, int T, int B,
+                  float* loss, float* total, float* dlogp, float* dent, float* dvalue, void* stream);
+
 /* ----------------------------------------------------------------------------------------------- optimizer (a12)
  * torch.optim.RMSprop step (alpha=0.99, eps=1e-8, no momentum, not centered; agent_dg.py:214-241) fused over one
  * flat parameter group, with the clip coefficient of clip_grad_norm (agent_dg.py:1392-1393) folded in:

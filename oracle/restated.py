@@ -361,6 +361,7 @@ def policy_step(state, cfg, seq, mask, lengths, step_inputs, carry, drops=NoDrop
     prev_h1, c_0 = (en_h, en_c) if carry is None else carry
     h_t, c_t, logit, h1, aux = decoder_step(state["decoder"], cfg, input_a_t, df_t, cand, prev_h1, c_0, ctx, mask, drops)
     logit = logit.masked_fill(length2mask(cand_leng, logit.shape[1]), -float("inf"))
+    aux["ctx"] = ctx
     return logit, h_t, (h1, c_t), aux
 
 
@@ -382,3 +383,97 @@ def teacher_rollout(state, cfg, episodes, T=None, ml_weight=0.4, drops=NoDrop(),
         actions.append(logit.argmax(1))
     loss = total * ml_weight / episodes.B
     return loss, logits, actions
+
+
+# ------------------------------------------------------------------------------- sampled feedback + A2C (a10, a11)
+class _Tagged:
+    """Dropout source view that prefixes every tag (e.g. 'last.' for the extra decoder / critic call of the A2C epilogue)."""
+
+    def __init__(self, base, prefix):
+        self.base, self.prefix, self.training = base, prefix, base.training
+
+    def __call__(self, x, p, tag):
+        return self.base(x, p, self.prefix + tag)
+
+
+def nav_reward(a_t, cand_leng, ignore_id, dist, last_dist, ended):
+    """The reward / mask / ended bookkeeping after one action (agent_dg.py:890-930), loop for loop. `dist` is the distance
+    to the goal after the action. Returns (reward [B] f32, mask [B] f32, ended [B] bool). The reference raises when a
+    non-END action leaves the distance unchanged; here that case yields reward 0 (the synthetic walks never produce it)."""
+    B = a_t.shape[0]
+    cpu_a_t = a_t.clone()
+    for i in range(B):
+        if int(cpu_a_t[i]) == int(cand_leng[i]) - 1 or int(cpu_a_t[i]) == ignore_id:
+            cpu_a_t[i] = -1
+    reward, mask = torch.zeros(B), torch.ones(B)
+    for i in range(B):
+        if bool(ended[i]):
+            reward[i], mask[i] = 0.0, 0.0
+        elif int(cpu_a_t[i]) == -1:
+            reward[i] = 2.0 if float(dist[i]) < 3 else -2.0
+        else:
+            r = -(float(dist[i]) - float(last_dist[i]))
+            reward[i] = 1.0 if r > 0 else (-1.0 if r < 0 else 0.0)
+    return reward, mask, ended | (cpu_a_t == -1)
+
+
+def a2c_epilogue(policy_log_probs, entropys, values, last_value, rewards, masks, ended, gamma=0.9, ent_coef=0.01,
+                 normalize="total"):
+    """agent_dg.py:959-999 for lists of T per-step [B] tensors. values[t] = critic(hidden_states[t]); last_value is detached.
+    Returns (rl_loss, total)."""
+    B = last_value.shape[0]
+    discount_reward = torch.where(ended, torch.zeros(B), last_value.detach().float())
+    rl_loss, total = 0.0, 0.0
+    for t in range(len(rewards) - 1, -1, -1):
+        discount_reward = discount_reward * gamma + rewards[t]
+        mask_, r_, v_ = masks[t], discount_reward.clone(), values[t]
+        a_ = (r_ - v_).detach()
+        rl_loss = rl_loss + (-policy_log_probs[t] * a_ * mask_).sum()
+        rl_loss = rl_loss + (((r_ - v_) ** 2) * mask_).sum() * 0.5
+        if entropys is not None:
+            rl_loss = rl_loss + (-ent_coef * entropys[t] * mask_).sum()
+        total = total + float(masks[t].sum())
+    if normalize == "total":
+        rl_loss = rl_loss / total
+    elif normalize == "batch":
+        rl_loss = rl_loss / B
+    return rl_loss, total
+
+
+def sample_rollout(state, cfg, episodes, T, actions, drops=NoDrop(), gamma=0.9, ent_coef=0.01, normalize="total",
+                   adain="channel"):
+    """vl_rollout with feedback='sample', train_rl=True, train_ml=None (agent_dg.py:725-999) over a pre-generated observation
+    stream (episodes must hold T+1 observations and `dist` [T+1,B]); `actions[t]` are the sampled actions (injected, so that
+    the CUDA path and this oracle follow the same trajectory). Returns (loss, dict of intermediates)."""
+    seq, mask, lengths = episodes.seq, episodes.seq_mask, episodes.seq_lengths
+    B = episodes.B
+    ended = torch.zeros(B, dtype=torch.bool)
+    last_dist = episodes.dist[0]
+    carry, rewards, masks, hidden, logps, ents, logits = None, [], [], [], [], [], []
+    for t in range(T):
+        step = episodes.step(t)
+        sdrops = _Prefixed(drops, t) if drops.training else drops
+        logit, h_t, carry, aux = policy_step(state, cfg, seq, mask, lengths, step, carry, sdrops, adain)
+        hidden.append(h_t)
+        logits.append(logit)
+        c = torch.distributions.Categorical(F.softmax(logit, 1))            # agent_dg.py:877-883
+        ents.append(c.entropy())
+        a_t = actions[t]
+        logps.append(c.log_prob(a_t))
+        dist = episodes.dist[t + 1]
+        r, m, ended = nav_reward(a_t, step[5], cfg.ignore_id, dist, last_dist, ended)
+        rewards.append(r)
+        masks.append(m)
+        last_dist = dist
+    # last action in A2C (agent_dg.py:945-957): RAW features of the next observation, decoder applies its own drop_env
+    nxt = episodes.step(T)
+    ldrops = _Tagged(drops, "last.") if drops.training else drops
+    h1, c_t = carry
+    last_h, _, _, _, _ = decoder_step(state["decoder"], cfg, nxt[0], nxt[1], nxt[3], h1, c_t, aux["ctx"], mask, ldrops,
+                                      already_dropfeat=False)
+    last_value = critic(state["critic"], last_h, ldrops, cfg.dropout).detach()
+    values = [critic(state["critic"], hidden[t], _Prefixed(drops, t) if drops.training else drops, cfg.dropout)
+              for t in range(T)]
+    loss, total = a2c_epilogue(logps, ents, values, last_value, rewards, masks, ended, gamma, ent_coef, normalize)
+    return loss, {"logits": logits, "logps": logps, "ents": ents, "values": values, "last_value": last_value,
+                  "rewards": rewards, "masks": masks, "ended": ended, "total": total}

@@ -416,3 +416,85 @@ def test_mha_forward_both_precisions(prec, tol, B, Lq, Lk):
         ops.set_precision("fp32")
     assert_close(probs, p, tol, "probs")
     assert_close(out, want, tol, "attention output")
+
+
+# ------------------------------------------------------------------------------- sampled feedback + A2C kernels
+@pytest.mark.parametrize("B,Nc", [(20, 14), (513, 9), (3, 40)])
+def test_policy_sample_fwd_bwd(B, Nc):
+    gen = g(B * Nc)
+    logit = torch.randn(B, Nc, generator=gen) * 3
+    leng = torch.randint(2, Nc + 1, (B,), generator=gen)
+    logit = logit.masked_fill(R.length2mask(leng, Nc), -float("inf")).requires_grad_(True)
+    act = (torch.rand(B, generator=gen) * leng.float()).long().clamp(max=leng - 1)
+    c = torch.distributions.Categorical(torch.softmax(logit, 1))
+    lp, ent = c.log_prob(act), c.entropy()
+    wl, we = torch.randn(B, generator=gen), torch.randn(B, generator=gen)
+    (lp * wl + ent * we).sum().backward()
+    ld = logit.detach().to(DEV).requires_grad_(True)
+    a2, lp2, ent2 = Fn.PolicySampleFn.apply(ld, None, act.to(DEV))
+    assert torch.equal(a2.cpu(), act)
+    assert_close(lp2, lp, 1e-5, "log_prob")
+    assert_close(ent2, ent, 1e-5, "entropy")
+    (lp2 * wl.to(DEV) + ent2 * we.to(DEV)).sum().backward()
+    assert_close(ld.grad, logit.grad, 1e-5, "dlogit")
+    # argmax mode is torch.max; sampling mode is the inverse CDF of the supplied uniforms
+    a3, _, _, probs = ops.policy_sample_fwd(ld.detach())
+    assert torch.equal(a3.cpu(), logit.detach().argmax(1))
+    u = torch.rand(B, generator=gen)
+    a4, lp4, _, _ = ops.policy_sample_fwd(ld.detach(), u=u.to(DEV))
+    cdf = probs.double().cpu().cumsum(1)
+    want = (cdf <= u.double()[:, None]).sum(1).clamp(max=Nc - 1)
+    live = torch.isfinite(logit.detach())
+    assert bool(live.gather(1, a4.cpu()[:, None]).all())
+    near = ((cdf - u.double()[:, None]).abs() < 1e-5).any(1)          # fp32 vs fp64 prefix sums may flip exact ties
+    assert torch.equal(a4.cpu()[~near], want[~near])
+    assert_close(lp4, torch.log_softmax(logit.detach().double(), 1).gather(1, a4.cpu()[:, None]).squeeze(1), 1e-5, "lp(sample)")
+
+
+def test_policy_sample_distribution():
+    """Sampling frequencies follow softmax(logit) (chi-square-like bound on 200k draws)."""
+    logit = torch.tensor([[0.5, -1.0, 2.0, -float("inf"), 0.0]]).repeat(200000, 1).to(DEV)
+    torch.manual_seed(1)
+    a, _, _, p = ops.policy_sample_fwd(logit, u=torch.rand(200000, device=DEV))
+    freq = torch.bincount(a, minlength=5).double() / 200000
+    assert float(freq[3]) == 0.0
+    assert float((freq - p[0].double()).abs().max()) < 5e-3
+
+
+@pytest.mark.parametrize("T,B,norm", [(5, 20, "total"), (35, 512, "total"), (4, 7, "batch"), (3, 1500, "none")])
+def test_a2c_loss_matches_oracle(T, B, norm):
+    gen = g(T * B)
+    logp = (-torch.rand(T, B, generator=gen) * 3).requires_grad_(True)
+    ent = (torch.rand(T, B, generator=gen) * 2).requires_grad_(True)
+    val = torch.randn(T, B, generator=gen).requires_grad_(True)
+    last = torch.randn(B, generator=gen)
+    rew = torch.randint(-2, 3, (T, B), generator=gen).float()
+    ended_at = torch.randint(1, T + 2, (B,), generator=gen)
+    mask = (torch.arange(T)[:, None] < ended_at[None, :]).float()
+    ended = ended_at <= T
+    loss, total = R.a2c_epilogue(list(logp), list(ent), list(val), last, list(rew), list(mask), ended, 0.9, 0.01, norm)
+    loss.backward()
+    lp2, en2, v2 = (x.detach().to(DEV).requires_grad_(True) for x in (logp, ent, val))
+    loss2, total2 = Fn.A2CLossFn.apply(lp2, en2, v2, last.to(DEV), rew.to(DEV), mask.to(DEV), ended.to(torch.uint8).to(DEV),
+                                       0.9, 0.01, norm)
+    assert float(total2) == total
+    assert_close(loss2, loss, 1e-5, "a2c loss")
+    loss2.backward()
+    assert_close(lp2.grad, logp.grad, 1e-5, "dlogp")
+    assert_close(en2.grad, ent.grad, 1e-5, "dent")
+    assert_close(v2.grad, val.grad, 1e-5, "dvalue")
+
+
+def test_nav_reward_bit_exact():
+    gen = g(99)
+    B = 257
+    leng = torch.randint(2, 14, (B,), generator=gen).int()
+    a = (torch.rand(B, generator=gen) * leng.float()).long().clamp(max=leng.long() - 1)
+    a[::7] = -100
+    dist, last = torch.rand(B, generator=gen) * 6, torch.rand(B, generator=gen) * 6
+    ended = torch.rand(B, generator=gen) < 0.3
+    r, m, e2 = R.nav_reward(a, leng, -100, dist, last, ended)
+    ed = ended.to(torch.uint8).to(DEV)
+    rd, md = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
+    ops.nav_reward(a.to(DEV), leng.to(DEV), -100, dist.to(DEV), last.to(DEV), ed, rd, md)
+    assert torch.equal(rd.cpu(), r) and torch.equal(md.cpu(), m) and torch.equal(ed.cpu().bool(), e2)

@@ -269,3 +269,99 @@ def test_tf32_deferred_training_step_close_to_oracle():
             assert e2 <= 1e-2, "tf32 grad %s.%s L2 rel err %.3e" % (grp, k, e2)
             assert e <= 5e-2, "tf32 grad %s.%s max rel err %.3e" % (grp, k, e)
     print("worst tf32 gradient L2 rel err %.3e" % worst)
+
+
+# ------------------------------------------------------------------------------- sampled feedback + A2C (a10, a11)
+def _sample_masks(cfg, B, T, L, nc, seed):
+    keep = _train_masks(cfg, B, T, L, nc, seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+
+    def add(tag, shape, p):
+        keep[tag] = (torch.rand(*shape, generator=gen) >= p, p)
+    for t in range(T):
+        add("t%d.critic" % t, (B, cfg.hidden), cfg.dropout)
+    add("last.critic", (B, cfg.hidden), cfg.dropout)
+    add("last.dec.act", (B, cfg.action_emb), cfg.dropout)
+    add("last.dec.feat", (B, cfg.views, cfg.rgb_size), cfg.featdropout)
+    add("last.dec.h_prev", (B, cfg.hidden), cfg.dropout)
+    add("last.dec.h1", (B, cfg.hidden), cfg.dropout)
+    add("last.dec.htilde", (B, cfg.hidden), cfg.dropout)
+    add("last.dec.cand", (B, nc, cfg.rgb_size), cfg.featdropout)
+    return keep
+
+
+def _legal_actions(ep, T, seed):
+    """Sampled actions inside every episode's candidate set; some episodes stop early (END = last candidate)."""
+    gen = torch.Generator().manual_seed(seed)
+    acts = []
+    for t in range(T):
+        leng = ep.cand_leng[t].long()
+        a = (torch.rand(ep.B, generator=gen) * (leng - 1).float()).long().clamp(max=leng - 2).clamp(min=0)
+        stop = torch.rand(ep.B, generator=gen) < 0.25
+        stop[0] = False                                   # episode 0 never stops: the batch does not exit early
+        acts.append(torch.where(stop, leng - 1, a))
+    return acts
+
+
+@pytest.mark.parametrize("train", [False, True])
+@pytest.mark.parametrize("cfg,B,T", [(SMALL, 4, 3)])
+def test_sample_rollout_a2c_loss_and_gradients(cfg, B, T, train):
+    """feedback='sample' rollout + A2C epilogue (agent_dg.py:725-999) with injected actions (and dropout masks in train
+    mode): per-step log-probs / entropies / values / rewards / masks, the loss, and every parameter gradient incl. the
+    critic's, against the oracle's autograd."""
+    st = synth.policy_state(cfg, 2)
+    ep = synth.Episodes(B, T + 1, cfg, seed=41)
+    L, nc = ep.seq_mask.shape[1], ep.cand_feat.shape[2]
+    acts = _legal_actions(ep, T, 5)
+    ost = {grp: {k: v.clone().requires_grad_(True) for k, v in d.items()} for grp, d in st.items()}
+    keep = _sample_masks(cfg, B, T, L, nc, 78) if train else {}
+    drops = R.MaskDrops({k: m.float() / (1 - p) for k, (m, p) in keep.items()}) if train else R.NoDrop()
+    loss, ref = R.sample_rollout(ost, cfg, ep, T, acts, drops=drops)
+    loss.backward()
+
+    pol = NavPolicy(cfg, st)
+    pol = pol.train() if train else pol.eval()
+    dep = DeviceEpisodes(ep)
+    src = M.DropoutSource(injected={k: m for k, (m, p) in keep.items()})
+    with M.use_dropout_source(src):
+        loss2, out = pol.sample_rollout(dep, T, actions_in=[a.to(DEV) for a in acts])
+    assert torch.equal(out["reward"].cpu(), torch.stack(ref["rewards"]))
+    assert torch.equal(out["mask"].cpu(), torch.stack(ref["masks"]))
+    assert torch.equal(out["ended"].cpu().bool(), ref["ended"])
+    assert float(out["total"]) == ref["total"]
+    assert_close(torch.stack(out["logps"]), torch.stack(ref["logps"]), 1e-4, "log-probs")
+    assert_close(torch.stack(out["ents"]), torch.stack(ref["ents"]), 1e-4, "entropies")
+    assert_close(out["values"], torch.stack(ref["values"]), 1e-4, "values")
+    assert_close(out["last_value"], ref["last_value"], 1e-4, "last value")
+    assert_close(loss2, loss, 1e-4, "A2C loss")
+    loss2.backward()
+    checked = 0
+    for grp, mod in (("adaIn", pol.adaIn), ("decoder", pol.decoder), ("encoder", pol.encoder), ("critic", pol.critic)):
+        for k, prm in mod.named_parameters():
+            want = ost[grp][k].grad
+            if want is None or float(want.abs().max()) == 0.0:
+                assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, "unexpected grad for %s.%s" % (grp, k)
+                continue
+            assert prm.grad is not None, "missing grad for %s.%s" % (grp, k)
+            assert_close(prm.grad, want, 1e-3, "grad %s.%s" % (grp, k))
+            checked += 1
+    assert checked >= 24
+
+
+def test_sample_rollout_device_rng_is_a_valid_trajectory():
+    """With the device RNG every sampled action is a live candidate, log-probs are those of the sampled actions, and the
+    loss is finite and differentiable."""
+    cfg, B, T = SMALL, 6, 4
+    pol = NavPolicy(cfg, synth.policy_state(cfg, 3)).train()
+    dep = DeviceEpisodes(synth.Episodes(B, T + 1, cfg, seed=43))
+    torch.manual_seed(0)
+    with M.use_dropout_source(M.DropoutSource(seed=9)):
+        loss, out = pol.sample_rollout(dep, T)
+    loss.backward()
+    assert torch.isfinite(loss).all()
+    for t in range(T):
+        a, lg = out["actions"][t], out["logits"][t]
+        assert bool((a >= 0).all()) and bool((a < dep.cand_leng[t].long()).all())
+        want = torch.log_softmax(lg.detach().double(), 1).gather(1, a[:, None]).squeeze(1)
+        assert_close(out["logps"][t], want, 1e-4, "log-prob of the sampled action")
+    assert pol.critic.state2value[0].weight.grad is not None
