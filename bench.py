@@ -41,6 +41,11 @@ def parse():
     ap.add_argument("--schedule", default="batched", choices=["batched", "sequential"],
                     help="batched: AdaIN + encoder of all T teacher-forced actions as one batch; sequential: per action")
     ap.add_argument("--skip-sequential", action="store_true", help="do not also time the per-action schedule")
+    ap.add_argument("--feedback", default="teacher", choices=["teacher", "sample"],
+                    help="teacher: BASELINE configs[1] (default). sample: accumulate_gradient('sample') = teacher-forced rollout + "
+                         "sampled A2C rollout per optimizer step (configs[3] with --batch 512)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket exactly one eager step with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     return ap.parse_args()
 
 
@@ -124,7 +129,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t_sample = 1
+    t_sample = 8 if args.batch <= 20 else 1
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_rollout_sample(args.batch, t_sample)
     times, steps = [], 0
@@ -188,6 +193,14 @@ def micro_rooflines(peak_gbs):
     add("adain_view_stats", 4 * (B * V * C + 4 * B * C), t)
     t = timeit(lambda: ops.row_attention_fwd(f, h_t, None, 5, 12, kl))
     add("shift_attention_fwd", 4 * (B * V * F + 2 * B * F + B * V + B * 5), t)
+    del g, o, d
+    B4 = 4096                                               # the large-batch plateau of the persistent pipelined kernel
+    f4 = torch.rand(B4, V, F, device=dev)
+    h4 = torch.randn(B4, F, device=dev) * 0.05
+    kl4 = torch.randn(B4, 5, device=dev)
+    t = timeit(lambda: ops.row_attention_fwd(f4, h4, None, 5, 12, kl4))
+    add("shift_attention_fwd@4096", 4 * (B4 * V * F + 2 * B4 * F + B4 * V + B4 * 5), t)
+    out["shift_attention_fwd@4096"]["batch"] = B4
     return out
 
 
@@ -206,7 +219,7 @@ def run_ours(args):
     lib.load()
     ops.set_precision(args.precision)
     from dasa_b200 import functions as Fn
-    Fn.defer_weight_grads(True)      # one long-K weight-gradient GEMM per weight per rollout
+    Fn.defer_weight_grads(args.batch <= 64)      # one long-K weight-gradient GEMM per weight per rollout (holds dY, X until then)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -221,7 +234,11 @@ def run_ours(args):
     pol.flatten_parameters()
     from dasa_b200 import dist as ddist
     ddist.broadcast_(pol.param_buffers(), world)
-    host_ep = synth.Episodes(B, T, cfg, seed=100 + rank, pin=True)
+    sample = args.feedback == "sample"
+    if sample:
+        args.schedule = "sequential"                        # the next observation depends on the sampled action
+        pol.schedule = "sequential"
+    host_ep = synth.Episodes(B, T + (1 if sample else 0), cfg, seed=100 + rank, pin=True)
     ep_res = DeviceEpisodes(host_ep, dev, resident=True)
     src = M.DropoutSource(seed=1234 + rank, device_seed=True, device=dev)
     loss_host = torch.zeros(1).pin_memory()
@@ -233,6 +250,15 @@ def run_ours(args):
         with M.use_dropout_source(src):
             # per-rank factor ml_weight / (B_local * world): summed gradients == one process running the global batch
             loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT / world, tag_steps=False)
+            if sample:
+                # agent_dg.py:1352-1356: IL rollout, then the RL rollout, summed into one loss. Backpropagating each rollout as
+                # soon as it ends accumulates the same gradients and halves the activation footprint (512 episodes x 35
+                # actions x 2 rollouts of bi-LSTM gates do not fit 180 GB at once).
+                pol.backward(loss)
+                rl, _ = pol.sample_rollout(ep, T, tag_steps=False)
+                rl = rl / world
+                pol.backward(rl)
+                return (loss.detach() + rl.detach()).reshape(1)
         pol.backward(loss)
         return loss
 
@@ -240,10 +266,34 @@ def run_ours(args):
         ddist.allreduce_sum_(pol.grad_buffers(), world)     # NCCL over NVLink: 4 flat buffers, ~190 MB
         pol.optim_step(LR)
 
-    def one_step(ep, read_back, upload=False):
-        if upload:                                          # e2e: this rollout's inputs come from pinned host memory
+    # e2e: every rollout's inputs come from pinned host memory. The copy of rollout i+1 runs on a side stream into a staging
+    # set while rollout i computes (one device-to-device hand-over per step); the first upload of a timed region is exposed.
+    up = {"stream": None, "stage": None, "ready": None, "free": None, "pending": False}
+
+    def start_upload():
+        if up["stream"] is None:
+            up["stream"] = torch.cuda.Stream()
+            up["stage"] = {k: torch.empty_like(getattr(ep_res, k)) for k in DeviceEpisodes.FIELDS}
+            up["ready"], up["free"] = torch.cuda.Event(), torch.cuda.Event()
+            up["free"].record()
+        up["stream"].wait_event(up["free"])                 # the staging set has been handed over
+        with torch.cuda.stream(up["stream"]):
             for k in DeviceEpisodes.FIELDS:
-                getattr(ep_res, k).copy_(getattr(host_ep, k), non_blocking=True)
+                up["stage"][k].copy_(getattr(host_ep, k), non_blocking=True)
+            up["ready"].record()
+        up["pending"] = True
+
+    def one_step(ep, read_back, upload=False, prefetch_next=False):
+        if upload:
+            if not up["pending"]:
+                start_upload()
+            torch.cuda.current_stream().wait_event(up["ready"])
+            for k in DeviceEpisodes.FIELDS:
+                getattr(ep_res, k).copy_(up["stage"][k], non_blocking=True)
+            up["free"].record()
+            up["pending"] = False
+            if prefetch_next:
+                start_upload()
         if state["graph"] is not None:
             state["graph"].replay()
             loss = state["loss"]
@@ -277,8 +327,8 @@ def run_ours(args):
         l0 = lib.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            one_step(ep_res, read_back, upload)
+        for i in range(steps):
+            one_step(ep_res, read_back, upload, prefetch_next=upload and i + 1 < steps)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -292,7 +342,7 @@ def run_ours(args):
     for _ in range(2):                                      # eager warm-up (allocator, caches, autotuned smem attributes)
         one_step(ep_res, False)
     torch.cuda.synchronize()
-    if not args.no_graph:
+    if not args.no_graph and not args.profile_step:
         try:
             capture()
         except Exception as e:                              # stay on eager launches, say so in the JSON line
@@ -300,16 +350,27 @@ def run_ours(args):
             torch.cuda.synchronize()
             Fn.invalidate_weight_caches()
 
+    if args.profile_step:
+        state["graph"] = None
+        Fn.invalidate_weight_caches()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        one_step(ep_res, False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_step, launches = timed(False, False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(True, True, max(1, args.steps // 2), 1)
+    ms_e2e, _ = timed(True, True, args.steps, 1)
     Fn.invalidate_weight_caches()
     # the same workload on the per-action schedule (the order a sampled / greedy rollout is forced to use)
     ms_seq = None
-    if args.schedule == "batched" and not args.skip_sequential:
+    if args.schedule == "batched" and not args.skip_sequential and not sample:
         state["graph"], state["loss"] = None, None
         pol.schedule = "sequential"
         torch.cuda.synchronize()
@@ -327,7 +388,7 @@ def run_ours(args):
         pol.schedule = args.schedule
         Fn.invalidate_weight_caches()
 
-    nav = B * T * world
+    nav = B * T * world * (2 if sample else 1)            # sample feedback: a teacher-forced and a sampled rollout per step
     value = nav / (ms_step * 1e-3)
     e2e_value = nav / (ms_e2e * 1e-3)
     if rank != 0:
@@ -342,17 +403,22 @@ def run_ours(args):
     if not args.skip_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        dt, n = cpu_rollout_sample(B, 1)
+        t_cpu = min(T, 35 if B <= 20 else 2)
+        dt, n = cpu_rollout_sample(B, t_cpu)
         cpu = {"value": n / dt, "unit": "nav steps/s", "cores": cores, "kind": "port",
-               "sample": "oracle port on host CPU: B=%d rollout truncated to 1 of %d actions, fwd+bwd (%.1f s)" % (B, T, dt)}
+               "sample": "oracle port on host CPU (torch %d threads): one teacher-forced rollout, B=%d, %d of %d actions, fwd+bwd "
+                         "(%.1f s)" % (cores, B, t_cpu, T, dt)}
     line = {
         "metric": "nav_steps_per_sec", "value": value, "unit": "nav steps/s (episodes x actions)", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products in the dense projections)" if args.precision == "tf32" else "f32",
         "data": "synthetic",
-        "config": {"workload": "agent_dg teacher-forced vl_rollout fwd+bwd+RMSprop, B=%d/GPU, T=%d, 36x2176 views, 80-token "
-                               "instructions, 9 la + 3 vl layers evaluated for every action (the instruction-only la stack of the T actions batched "
-                               "into one pass, own dropout masks per action; nothing cached) (BASELINE.json configs[1])" % (B, T),
+        "config": {"workload": ("agent_dg teacher-forced vl_rollout fwd+bwd+RMSprop, B=%d/GPU, T=%d, 36x2176 views, 80-token "
+                                "instructions, 9 la + 3 vl layers evaluated for every action (the instruction-only la stack of the T actions batched "
+                                "into one pass, own dropout masks per action; nothing cached) (BASELINE.json configs[1])" % (B, T)) if not sample else
+                               ("agent_dg accumulate_gradient('sample'): teacher-forced vl_rollout + sampled-feedback A2C vl_rollout (Categorical "
+                                "sampling on the device, critic, A2C epilogue), fwd+bwd+RMSprop, B=%d episodes/GPU, T=%d, synthetic observation "
+                                "stream (BASELINE.json configs[3])" % (B, T)),
                    "precision": args.precision, "l2": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2",
                    "parallelism": "dp%d" % world,
                    "schedule": ("batched: the agent follows the teacher, so all T observations are known up front and AdaIN + "
