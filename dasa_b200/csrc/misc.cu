@@ -30,7 +30,19 @@ __global__ void __launch_bounds__(256) act_backward_kernel(int act, const float*
     float g = dy[(int64_t)r * lddy + c];
     if (mask != nullptr) g *= mask[i] ? scale : 0.f;
     const float yv = y[(int64_t)r * ldy + c];
-    dx[(int64_t)r * lddx + c] = (act == 0) ? g * (1.f - yv * yv) : (yv > 0.f ? g : 0.f);
+    float o;
+    if (act == 0) o = g * (1.f - yv * yv);
+    else if (act == 1) o = yv > 0.f ? g : 0.f;
+    else o = g * (0.5f * (1.f + erff(yv * 0.70710678118654752f)) + yv * 0.3989422804014327f * expf(-0.5f * yv * yv));   // gelu'(pre-activation)
+    dx[(int64_t)r * lddx + c] = o;
+  }
+}
+
+// y = x * 0.5 * (1 + erf(x / sqrt(2)))  (vilmodel.gelu, vilmodel.py:125-131)
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = v * 0.5f * (1.f + erff(v * 0.70710678118654752f));
   }
 }
 
@@ -190,9 +202,15 @@ extern "C" int dasa_dropout_apply(const float* x, int64_t ldx, const uint8_t* ma
 extern "C" int dasa_act_backward(int act, const float* dy, int64_t lddy, const float* y, int64_t ldy, const uint8_t* mask, float scale,
                                  float* dx, int64_t lddx, int R, int C, void* stream) {
   if (R <= 0 || C <= 0) return DASA_OK;
-  if (act != 0 && act != 1) return DASA_ERR_BAD_SHAPE;
+  if (act < 0 || act > 2) return DASA_ERR_BAD_SHAPE;
   act_backward_kernel<<<ew_grid((int64_t)R * C), 256, 0, (cudaStream_t)stream>>>(act, dy, lddy, y, ldy, mask, scale, dx, lddx, R, C);
   return dasa_check_launch("act_backward_kernel");
+}
+
+extern "C" int dasa_gelu_fwd(const float* x, float* y, int64_t n, void* stream) {
+  if (n <= 0) return DASA_OK;
+  gelu_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  return dasa_check_launch("gelu_fwd_kernel");
 }
 
 extern "C" int dasa_axpy2d(float a, const float* x, int64_t ldx, float* y, int64_t ldy, int accumulate, int R, int C, void* stream) {

@@ -56,17 +56,18 @@ def flush_weight_grads():
 
 
 class LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b) with act in {none, tanh, relu} fused in the GEMM epilogue."""
+    """y = act(x W^T + b) with act in {none, tanh, relu} fused in the GEMM epilogue; act = gelu (finetune config) keeps the
+    pre-activation for the backward and applies the erf-GELU in a second pass."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         epi = {None: EPI_BIAS if bias is not None else EPI_NONE,
                "tanh": EPI_BIAS_TANH if bias is not None else EPI_TANH,
-               "relu": EPI_BIAS_RELU}[act]
+               "relu": EPI_BIAS_RELU, "gelu": EPI_BIAS}[act]
         y = ops.linear_fwd(x, weight, bias, epi)
         ctx.act, ctx.has_bias = act, bias is not None
         ctx.save_for_backward(x, weight, bias if bias is not None else x.new_empty(0), y if act else x.new_empty(0))
-        return y
+        return ops.gelu_fwd(y) if act == "gelu" else y
 
     @staticmethod
     def backward(ctx, dy):
@@ -420,3 +421,55 @@ class A2CLossFn(torch.autograd.Function):
     def backward(ctx, dloss, _dt):
         dlogp, dent, dvalue = ctx.saved_tensors
         return dlogp * dloss, (None if dent is None else dent * dloss), dvalue * dloss, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------- finetune config (--d_update_add_layer)
+class MHAFn(torch.autograd.Function):
+    """BertSelfAttention / BertOutAttention core (vilmodel.py:203-236, 479-506): softmax(q k^T / sqrt(dh) + pad) (dropout) v."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, key_pad, drop_mask, drop_scale):
+        out, probs = ops.mha_fwd(q, k, v, heads, key_pad, drop_mask, drop_scale, save_probs=True)
+        ctx.heads, ctx.scale = heads, drop_scale
+        ctx.save_for_backward(q, k, v, probs, drop_mask if drop_mask is not None else q.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, probs, mask = ctx.saved_tensors
+        dq, dk, dv = ops.mha_bwd(q, k, v, probs, dout, ctx.heads, mask if mask.numel() else None, ctx.scale)
+        return dq, dk, dv, None, None, None, None
+
+
+class DropResLNFn(torch.autograd.Function):
+    """BertSelfOutput / BertOutput / VisionEncoder tail: LN(x*mask*scale + resid) * gamma + beta (* post_mask*post_scale)."""
+
+    @staticmethod
+    def forward(ctx, x, resid, gamma, beta, eps, mask, scale, post_mask, post_scale):
+        out, stats, z = ops.dropout_residual_layernorm(x, resid, gamma, beta, eps, mask, scale, post_mask, post_scale, save=True)
+        ctx.scale, ctx.post_scale, ctx.has_resid = scale, post_scale, resid is not None
+        e = x.new_empty(0)
+        ctx.save_for_backward(z, stats, gamma, beta, mask if mask is not None else e, post_mask if post_mask is not None else e)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, stats, gamma, beta, mask, post_mask = ctx.saved_tensors
+        dg, db = _zeros_like_grad(gamma), _zeros_like_grad(beta)
+        dx, dresid = ops.layernorm_bwd(dout.contiguous(), z, gamma, stats, dg, db, mask if mask.numel() else None, ctx.scale,
+                                       post_mask if post_mask.numel() else None, ctx.post_scale)
+        return dx, (dresid if ctx.has_resid else None), None, None, None, None, None, None, None
+
+
+class ReverseTokensFn(torch.autograd.Function):
+    """Per-sample token reversal (r2rmodel.py:2326-2330); self-inverse, so the backward is the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x, lengths_i32):
+        ctx.save_for_backward(lengths_i32)
+        return ops.reverse_tokens(x, lengths_i32)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (lengths,) = ctx.saved_tensors
+        return ops.reverse_tokens(dy.contiguous(), lengths), None

@@ -490,6 +490,57 @@ class DicModel(nn.Module):
         return lang, visn
 
 
+def _dicmodel_grad_methods():
+    """Differentiable twin of DicModel._cross_modal for the finetune config (--d_update_add_layer True, train.py:179-180):
+    same kernels in the forward, autograd Functions (functions.MHAFn / DropResLNFn / LinearFn) so that the three
+    cross-modal layers and the vision encoder receive gradients (vilmodel.py:1383-1410 without the detach at :1408-1410)."""
+
+    def _out_ln_g(self, out_mod, x, resid, tag, training):
+        y = Fn.linear(x, out_mod.dense.weight, out_mod.dense.bias)
+        m, s = self._mask(tag, (y.shape[0] // self._steps,) + tuple(y.shape[1:]), training, y.device)
+        return Fn.DropResLNFn.apply(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias, out_mod.LayerNorm.eps,
+                                    m, s, None, 1.0)
+
+    def _att_g(self, att, out_mod, x, ctx, key_pad, tag, training):
+        cfg = self.cfg
+        q = Fn.linear(x, att.query.weight, att.query.bias)
+        k = Fn.linear(ctx, att.key.weight, att.key.bias)
+        v = Fn.linear(ctx, att.value.weight, att.value.bias)
+        B, Lq, Lk = x.shape[0], x.shape[1], ctx.shape[1]
+        m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
+        o = Fn.MHAFn.apply(q, k, v, cfg.bert_heads, key_pad, m, s)
+        return self._out_ln_g(out_mod, o, x, tag + ".out", training)
+
+    def _ffn_g(self, inter_mod, out_mod, x, tag, training):
+        y = Fn.linear(x, inter_mod.dense.weight, inter_mod.dense.bias, "gelu")
+        return self._out_ln_g(out_mod, y, x, tag, training)
+
+    def cross_modal_grad(self, lang, pad_mask, img_feats, training, steps=1):
+        cfg, ve = self.cfg, self.vision_encoder
+        self._steps = steps
+        try:
+            v = Fn.linear(img_feats, ve.visn_fc.weight, ve.visn_fc.bias)
+            m, s = self._mask("enc.visn", (v.shape[0] // steps,) + tuple(v.shape[1:]), training, v.device)
+            visn = Fn.DropResLNFn.apply(v, None, ve.visn_layer_norm.weight, ve.visn_layer_norm.bias, 1e-12, None, 1.0, m, s)
+            for i, layer in enumerate(self.addlayer):
+                t = "enc.vl%d" % i
+                xa = layer.visual_attention
+                l1 = self._att_g(xa.att, xa.output, lang, visn, None, t + ".x_lv", training)
+                v1 = self._att_g(xa.att, xa.output, visn, lang, pad_mask, t + ".x_vl", training)
+                l2 = self._att_g(layer.lang_self_att.self, layer.lang_self_att.output, l1, l1, pad_mask, t + ".ls", training)
+                v2 = self._att_g(layer.visn_self_att.self, layer.visn_self_att.output, v1, v1, None, t + ".vs", training)
+                lang = self._ffn_g(layer.lang_inter, layer.lang_output, l2, t + ".lo", training)
+                visn = self._ffn_g(layer.visn_inter, layer.visn_output, v2, t + ".vo", training)
+            return lang, visn
+        finally:
+            self._steps = 1
+
+    DicModel._out_ln_g, DicModel._att_g, DicModel._ffn_g, DicModel.cross_modal_grad = _out_ln_g, _att_g, _ffn_g, cross_modal_grad
+
+
+_dicmodel_grad_methods()
+
+
 class DicEncoder(nn.Module):
     """r2rmodel.py:2199-2365. Constructor signature as the reference; `cfg` (optional) shrinks the transformer for tests."""
 
@@ -503,8 +554,6 @@ class DicEncoder(nn.Module):
         from dataclasses import replace
         cfg = replace(cfg or FULL, vl_layers=vl_layers, la_layers=la_layers, enc_hidden=hidden_size, hidden=dec_hidden_size,
                       enc_dropout=dropout_ratio, update_add_layer=bool(update_add_layer))
-        if cfg.update_add_layer:
-            raise NotImplementedError("finetune (--d_update_add_layer) backward through the VL layers lands in a later round")
         self.cfg = cfg
         self.hidden_size, self.dec_hidden_size, self.dropout_ratio = hidden_size, dec_hidden_size, dropout_ratio
         self.drop = nn.Dropout(p=dropout_ratio)
@@ -537,9 +586,13 @@ class DicEncoder(nn.Module):
             lang_all = self.bert.language_stack(inputs[:, :L].contiguous(), pad, tr, steps)
         lang_all = lang_all.reshape(steps * B, L, -1)
         pad_all = pad.repeat(steps, 1)
-        lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps)
-        len32 = torch.as_tensor(lengths, device=lang.device).to(torch.int32).repeat(steps)
-        rev = ops.reverse_tokens(lang, len32)
+        len32 = torch.as_tensor(lengths, device=lang_all.device).to(torch.int32).repeat(steps)
+        if self.cfg.update_add_layer:                    # finetune: gradients flow into the cross-modal layers
+            lang, visn = self.bert.cross_modal_grad(lang_all, pad_all, f_all, tr, steps)
+            rev = Fn.ReverseTokensFn.apply(lang, len32)
+        else:
+            lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps)
+            rev = ops.reverse_tokens(lang, len32)
         l = self.lstm
         ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0,
                                               l.weight_ih_l0_reverse, l.weight_hh_l0_reverse, l.bias_ih_l0_reverse,
@@ -569,9 +622,13 @@ class DicEncoder(nn.Module):
             lang0 = self.bert.language_stack(ids, pad, tr)
             if self.cache_language and not tr:
                 self._lang_cache = (key, lang0)
-        lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr)
-        len32 = torch.as_tensor(lengths, device=lang.device).to(torch.int32)
-        rev = ops.reverse_tokens(lang, len32)
+        len32 = torch.as_tensor(lengths, device=lang0.device).to(torch.int32)
+        if self.cfg.update_add_layer:                    # finetune: gradients flow into the cross-modal layers
+            lang, visn = self.bert.cross_modal_grad(lang0, pad, f_t_all, tr)
+            rev = Fn.ReverseTokensFn.apply(lang, len32)
+        else:
+            lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr)
+            rev = ops.reverse_tokens(lang, len32)
         l = self.lstm
         ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0,
                                               l.weight_ih_l0_reverse, l.weight_hh_l0_reverse, l.bias_ih_l0_reverse,

@@ -198,9 +198,16 @@ def act_backward(act, dy, y, mask=None, scale=1.0):
     y2, _, _, ldy = _rows(y)
     dx = torch.empty(dy.shape, device=dy.device, dtype=torch.float32)
     x2, _, _, ldx = _rows_out(dx)
-    call("dasa_act_backward", 0 if act == "tanh" else 1, _p(d2), ldd, _p(y2), ldy, _p(mask), float(scale), _p(x2), ldx, R, C,
+    call("dasa_act_backward", {"tanh": 0, "relu": 1, "gelu": 2}[act], _p(d2), ldd, _p(y2), ldy, _p(mask), float(scale), _p(x2), ldx, R, C,
          _stream())
     return dx
+
+
+def gelu_fwd(x):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    call("dasa_gelu_fwd", _p(x), _p(y), x.numel(), _stream())
+    return y
 
 
 def axpy2d(a, x, y, accumulate=True):

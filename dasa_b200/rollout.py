@@ -232,13 +232,15 @@ class NavPolicy:
         """Re-home the trainable parameters of each optimizer group (encoder / decoder / critic / adaIn, agent_dg.py:214-241)
         in one flat fp32 buffer, with a matching flat gradient buffer that every `p.grad` views: zero_grad is one memset per
         group, the data-parallel reduction one all-reduce per group, clip + RMSprop one launch per group. The frozen BERT stack
-        (detached in the train config, vilmodel.py:1377-1410) is excluded and marked requires_grad=False."""
+        (detached in the train config, vilmodel.py:1377-1410) is excluded and marked requires_grad=False; in the finetune
+        config (update_add_layer) the cross-modal layers and the vision encoder stay trainable."""
         groups = []
         for name, m, clip in (("encoder", self.encoder, 40.0), ("decoder", self.decoder, 40.0), ("critic", self.critic, None),
                               ("adaIn", self.adaIn, None)):
             ps = []
             for k, p in m.named_parameters():
-                if name == "encoder" and k.startswith("bert."):
+                finetuned = self.cfg.update_add_layer and (k.startswith("bert.addlayer.") or k.startswith("bert.vision_encoder."))
+                if name == "encoder" and k.startswith("bert.") and not finetuned:
                     p.requires_grad_(False)
                     continue
                 ps.append(p)

@@ -218,9 +218,12 @@ int dasa_reverse_tokens(const float* x, float* out, const int32_t* lengths, int 
 /* y = x * mask * scale (mask may be NULL -> copy); strided rows                                                     */
 int dasa_dropout_apply(const float* x, int64_t ldx, const uint8_t* mask, float scale, float* y, int64_t ldy,
                        int R, int C, void* stream);
-/* dx = dy * (1 - y*y) (tanh), dx = dy * (y > 0) (relu), optional keep mask folded in front (dy*mask*scale)        */
-int dasa_act_backward(int act /*0 tanh, 1 relu*/, const float* dy, int64_t lddy, const float* y, int64_t ldy,
+/* dx = dy * (1 - y*y) (tanh), dx = dy * (y > 0) (relu), dx = dy * gelu'(y) with y = the PRE-activation (gelu, finetune
+ * config), optional keep mask folded in front (dy*mask*scale)                                                       */
+int dasa_act_backward(int act /*0 tanh, 1 relu, 2 gelu*/, const float* dy, int64_t lddy, const float* y, int64_t ldy,
                       const uint8_t* mask, float scale, float* dx, int64_t lddx, int R, int C, void* stream);
+/* y = gelu_erf(x) over n contiguous elements (vilmodel.py:125-131); the forward-only path fuses it in the GEMM epilogue */
+int dasa_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
 /* y (+)= a*x   elementwise over [R,C] strided                                                                      */
 int dasa_axpy2d(float a, const float* x, int64_t ldx, float* y, int64_t ldy, int accumulate, int R, int C, void* stream);
 /* keep-mask generator (counter-based hash RNG): mask[i] = u(seed, offset+i) >= p                                   */

@@ -498,3 +498,81 @@ def test_nav_reward_bit_exact():
     rd, md = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
     ops.nav_reward(a.to(DEV), leng.to(DEV), -100, dist.to(DEV), last.to(DEV), ed, rd, md)
     assert torch.equal(rd.cpu(), r) and torch.equal(md.cpu(), m) and torch.equal(ed.cpu().bool(), e2)
+
+
+# ------------------------------------------------------------------- finetune config: attention / LN / GELU backward
+@pytest.mark.parametrize("B,Lq,Lk,heads,dh,pad,drop", [(3, 7, 7, 4, 16, True, True), (2, 45, 36, 12, 64, False, True),
+                                                        (4, 36, 80, 12, 64, True, False)])
+def test_mha_fwd_bwd_matches_torch(B, Lq, Lk, heads, dh, pad, drop):
+    gen = g(B * Lq + Lk)
+    Hd = heads * dh
+    q, k, v = (torch.randn(B, n, Hd, generator=gen, requires_grad=True) for n in (Lq, Lk, Lk))
+    key_pad = None
+    add = 0.0
+    if pad:
+        lens = torch.randint(1, Lk + 1, (B,), generator=gen)
+        key_pad = torch.arange(Lk)[None, :] >= lens[:, None]
+        add = (key_pad.float() * -10000.0)[:, None, None, :]
+    keep = (torch.rand(B, heads, Lq, Lk, generator=gen) >= 0.1) if drop else None
+    s = torch.matmul(q.view(B, Lq, heads, dh).permute(0, 2, 1, 3), k.view(B, Lk, heads, dh).permute(0, 2, 3, 1)) / math.sqrt(dh) + add
+    pr = torch.softmax(s, -1)
+    if drop:
+        pr = pr * keep.float() / 0.9
+    o = torch.matmul(pr, v.view(B, Lk, heads, dh).permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Lq, Hd)
+    do = torch.randn(B, Lq, Hd, generator=gen)
+    o.backward(do)
+    qd, kd, vd = (x.detach().to(DEV).requires_grad_(True) for x in (q, k, v))
+    o2 = Fn.MHAFn.apply(qd, kd, vd, heads, key_pad.to(DEV) if pad else None,
+                        ops.as_keep_mask(keep.to(DEV)) if drop else None, 1 / 0.9 if drop else 1.0)
+    assert_close(o2, o, 1e-4, "mha out")
+    o2.backward(do.to(DEV))
+    assert_close(qd.grad, q.grad, 2e-4, "dq")
+    assert_close(kd.grad, k.grad, 2e-4, "dk")
+    assert_close(vd.grad, v.grad, 2e-4, "dv")
+
+
+@pytest.mark.parametrize("R,Hd,resid,pre,post", [(37, 768, True, True, False), (20, 768, False, False, True), (5, 64, True, False, False)])
+def test_dropout_residual_layernorm_bwd(R, Hd, resid, pre, post):
+    gen = g(R + Hd)
+    x = torch.randn(R, Hd, generator=gen, requires_grad=True)
+    r = torch.randn(R, Hd, generator=gen, requires_grad=True) if resid else None
+    gamma = (1 + 0.1 * torch.randn(Hd, generator=gen)).requires_grad_(True)
+    beta = (0.1 * torch.randn(Hd, generator=gen)).requires_grad_(True)
+    km = (torch.rand(R, Hd, generator=gen) >= 0.1) if pre else None
+    pm = (torch.rand(R, Hd, generator=gen) >= 0.1) if post else None
+    z = x * (km.float() / 0.9) if pre else x
+    z = z + r if resid else z
+    y = torch.nn.functional.layer_norm(z, (Hd,), gamma, beta, 1e-12)
+    y = y * (pm.float() / 0.9) if post else y
+    dy = torch.randn(R, Hd, generator=gen)
+    y.backward(dy)
+    xd = x.detach().to(DEV).requires_grad_(True)
+    rd = r.detach().to(DEV).requires_grad_(True) if resid else None
+    gd, bd = gamma.detach().to(DEV).requires_grad_(True), beta.detach().to(DEV).requires_grad_(True)
+    y2 = Fn.DropResLNFn.apply(xd, rd, gd, bd, 1e-12, ops.as_keep_mask(km.to(DEV)) if pre else None, 1 / 0.9 if pre else 1.0,
+                              ops.as_keep_mask(pm.to(DEV)) if post else None, 1 / 0.9 if post else 1.0)
+    assert_close(y2, y, 1e-4, "LN out")
+    y2.backward(dy.to(DEV))
+    assert_close(xd.grad, x.grad, 2e-4, "dx")
+    if resid:
+        assert_close(rd.grad, r.grad, 2e-4, "dresid")
+    assert_close(gd.grad, gamma.grad, 2e-4, "dgamma")
+    assert_close(bd.grad, beta.grad, 2e-4, "dbeta")
+
+
+def test_linear_gelu_fwd_bwd():
+    gen = g(17)
+    x = torch.randn(6, 11, 48, generator=gen, requires_grad=True)
+    w = (torch.randn(96, 48, generator=gen) * 0.2).requires_grad_(True)
+    b = torch.randn(96, generator=gen).requires_grad_(True)
+    y = R.gelu_erf(torch.nn.functional.linear(x, w, b))
+    dy = torch.randn(y.shape, generator=gen)
+    y.backward(dy)
+    xd, wd, bd = (t.detach().to(DEV).requires_grad_(True) for t in (x, w, b))
+    y2 = Fn.linear(xd, wd, bd, "gelu")
+    assert_close(y2, y, 1e-4, "gelu(linear)")
+    y2.backward(dy.to(DEV))
+    Fn.flush_weight_grads()
+    assert_close(xd.grad, x.grad, 2e-4, "dx")
+    assert_close(wd.grad, w.grad, 2e-4, "dW")
+    assert_close(bd.grad, b.grad, 2e-4, "db")

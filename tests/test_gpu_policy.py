@@ -365,3 +365,45 @@ def test_sample_rollout_device_rng_is_a_valid_trajectory():
         want = torch.log_softmax(lg.detach().double(), 1).gather(1, a[:, None]).squeeze(1)
         assert_close(out["logps"][t], want, 1e-4, "log-prob of the sampled action")
     assert pol.critic.state2value[0].weight.grad is not None
+
+
+# --------------------------------------------------------------------- finetune config (--d_update_add_layer True)
+@pytest.mark.parametrize("schedule", ["batched", "sequential"])
+def test_finetune_rollout_gradients_reach_cross_modal_layers(schedule):
+    """configs[2]: update_add_layer=True (train.py:179-180) - the three LXRTXLayers and the vision encoder are trained.
+    Train-mode teacher-forced rollout with injected dropout masks: loss and every parameter gradient (adaIn, decoder,
+    bi-LSTM, init linears, bert.addlayer.*, bert.vision_encoder.*) against the oracle's autograd; the language layers stay
+    frozen (detach at vilmodel.py:1377-1378)."""
+    from dataclasses import replace
+    cfg = replace(SMALL, update_add_layer=True)
+    B, T = 2, 2
+    st = synth.policy_state(cfg, 4)
+    ep = synth.Episodes(B, T, cfg, seed=51)
+    L, nc = ep.seq_mask.shape[1], ep.cand_feat.shape[2]
+    keep = _train_masks(cfg, B, T, L, nc, 79)
+    ost = {grp: {k: v.clone().requires_grad_(True) for k, v in d.items()} for grp, d in st.items()}
+    drops = R.MaskDrops({k: m.float() / (1 - p) for k, (m, p) in keep.items()})
+    loss, logits, _ = R.teacher_rollout(ost, cfg, ep, T, drops=drops)
+    loss.backward()
+    pol = NavPolicy(cfg, st).train()
+    dep = DeviceEpisodes(ep)
+    with M.use_dropout_source(M.DropoutSource(injected={k: m for k, (m, p) in keep.items()})):
+        loss2, logits2, _ = pol.teacher_rollout(dep, T, schedule=schedule)
+    assert_close(loss2, loss, 1e-4, "finetune loss")
+    pol.backward(loss2)
+    checked, vl = 0, 0
+    for k, prm in pol.encoder.named_parameters():
+        want = ost["encoder"][k].grad
+        if want is None or float(want.abs().max()) == 0.0:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, "unexpected grad for encoder.%s" % k
+            continue
+        assert prm.grad is not None, "missing grad for encoder.%s" % k
+        if float(want.abs().max()) < 1e-7:        # attention key biases: softmax is shift-invariant, the gradient is round-off
+            assert float(prm.grad.abs().max()) < 1e-6, "grad encoder.%s should vanish" % k
+            continue
+        assert_close(prm.grad, want, 2e-3, "grad encoder.%s" % k)
+        checked += 1
+        vl += k.startswith("bert.addlayer.") or k.startswith("bert.vision_encoder.")
+    assert vl >= 60 and checked > vl
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for k, p in pol.encoder.named_parameters()
+               if k.startswith("bert.lalayer.") or k.startswith("bert.embeddings."))
