@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--feedback", default="teacher", choices=["teacher", "sample"],
                     help="teacher: BASELINE configs[1] (default). sample: accumulate_gradient('sample') = teacher-forced rollout + "
                          "sampled A2C rollout per optimizer step (configs[3] with --batch 512)")
+    ap.add_argument("--finetune", action="store_true",
+                    help="configs[2]: --d_update_add_layer True (gradients through the 3 cross-modal layers + vision encoder), "
+                         "batch 2, two accumulate_gradient('sample') passes (GT + augmented env, train.py:226-243) per optimizer "
+                         "step, lr 2e-6: the latency-bound small-batch path")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket exactly one eager step with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     return ap.parse_args()
@@ -228,7 +232,15 @@ def run_ours(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
 
-    cfg, B, T = FULL, args.batch, args.actions
+    if args.finetune:
+        from dataclasses import replace
+        args.feedback = "sample"
+        if args.batch == B_DEFAULT:
+            args.batch = 2
+    cfg, B, T = (replace(FULL, update_add_layer=True) if args.finetune else FULL), args.batch, args.actions
+    n_acc = 2 if args.finetune else 1                       # GT env + augmented env per optimizer step
+    ml_weights = [ML_WEIGHT, 0.6][:n_acc]                   # --mlWeight_org / --mlWeight_aug (param.py:58-59)
+    lr = 2e-6 if args.finetune else LR
     pol = NavPolicy(cfg, synth.policy_state(cfg, 0), dev).train()
     pol.schedule = args.schedule
     pol.flatten_parameters()
@@ -264,7 +276,7 @@ def run_ours(args):
 
     def finish():
         ddist.allreduce_sum_(pol.grad_buffers(), world)     # NCCL over NVLink: 4 flat buffers, ~190 MB
-        pol.optim_step(LR)
+        pol.optim_step(lr)
 
     # e2e: every rollout's inputs come from pinned host memory. The copy of rollout i+1 runs on a side stream into a staging
     # set while rollout i computes (one device-to-device hand-over per step); the first upload of a timed region is exposed.
@@ -388,7 +400,7 @@ def run_ours(args):
         pol.schedule = args.schedule
         Fn.invalidate_weight_caches()
 
-    nav = B * T * world * (2 if sample else 1)            # sample feedback: a teacher-forced and a sampled rollout per step
+    nav = B * T * world * (2 if sample else 1) * n_acc    # sample feedback: a teacher-forced and a sampled rollout per pass
     value = nav / (ms_step * 1e-3)
     e2e_value = nav / (ms_e2e * 1e-3)
     if rank != 0:
@@ -416,9 +428,11 @@ def run_ours(args):
         "config": {"workload": ("agent_dg teacher-forced vl_rollout fwd+bwd+RMSprop, B=%d/GPU, T=%d, 36x2176 views, 80-token "
                                 "instructions, 9 la + 3 vl layers evaluated for every action (the instruction-only la stack of the T actions batched "
                                 "into one pass, own dropout masks per action; nothing cached) (BASELINE.json configs[1])" % (B, T)) if not sample else
+                               ("FINETUNE (d_update_add_layer: cross-modal layers + vision encoder trained, lr 2e-6, 2 accumulate_gradient "
+                                "passes per optimizer step; BASELINE.json configs[2]) - " if args.finetune else "") +
                                ("agent_dg accumulate_gradient('sample'): teacher-forced vl_rollout + sampled-feedback A2C vl_rollout (Categorical "
                                 "sampling on the device, critic, A2C epilogue), fwd+bwd+RMSprop, B=%d episodes/GPU, T=%d, synthetic observation "
-                                "stream (BASELINE.json configs[3])" % (B, T)),
+                                "stream%s" % (B, T, "" if args.finetune else " (BASELINE.json configs[3])")),
                    "precision": args.precision, "l2": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2",
                    "parallelism": "dp%d" % world,
                    "schedule": ("batched: the agent follows the teacher, so all T observations are known up front and AdaIN + "
