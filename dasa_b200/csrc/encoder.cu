@@ -192,6 +192,9 @@ struct MhaArgs {
   const uint8_t* key_pad; int64_t ld_pad; const uint8_t* drop_mask; float drop_scale;
   float* out; int64_t ldo, so; float* probs_out;
   int B, heads, Lq, Lk, dh;
+  // packed (variable-length) operands: rows of sample b start at row q_off[b] / k_off[b] of the packed matrix and there are
+  // q_len[b] / k_len[b] of them; Lq / Lk are then the maxima (shared-memory carve-up, mask / probs indexing). NULL = dense.
+  const int32_t *q_off, *q_len, *k_off, *k_len;
 };
 
 // Register-tiled: a warp owns 4 query rows; lane l owns keys l, l+32, l+64 (scores) / head-dim columns l, l+32 (P.V).
@@ -199,15 +202,17 @@ struct MhaArgs {
 __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
-  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh, dhp = dh + 4;
+  const int Lq = a.q_len ? a.q_len[b] : a.Lq, Lk = a.k_len ? a.k_len[b] : a.Lk, dh = a.dh, dhp = dh + 4;
   const int LqP = (Lq + 3) & ~3, LkP = (Lk + 3) & ~3;
+  const int LqM = (a.Lq + 3) & ~3, LkM = (a.Lk + 3) & ~3;     // carve-up by the maxima
   float* Qs = smem;                      // [LqP][dhp]
-  float* Ks = Qs + LqP * dhp;            // [LkP][dhp]
-  float* Vs = Ks + LkP * dhp;            // [LkP][dh]
-  float* Ss = Vs + LkP * dh;             // [LqP][LkP]
-  const float* qb = a.q + (int64_t)b * a.sq + h * dh;
-  const float* kb = a.k + (int64_t)b * a.sk + h * dh;
-  const float* vb = a.v + (int64_t)b * a.sv + h * dh;
+  float* Ks = Qs + LqM * dhp;            // [LkP][dhp]
+  float* Vs = Ks + LkM * dhp;            // [LkP][dh]
+  float* Ss = Vs + LkM * dh;             // [LqP][LkP]
+  const float* qb = a.q + (a.q_off ? (int64_t)a.q_off[b] * a.ldq : (int64_t)b * a.sq) + h * dh;
+  const float* kb = a.k + (a.k_off ? (int64_t)a.k_off[b] * a.ldk : (int64_t)b * a.sk) + h * dh;
+  const float* vb = a.v + (a.k_off ? (int64_t)a.k_off[b] * a.ldv : (int64_t)b * a.sv) + h * dh;
+  if (Lq <= 0) return;
   const int d4n = dh >> 2;
   for (int i = threadIdx.x; i < LqP * d4n; i += blockDim.x) {
     const int r = i / d4n, c = i % d4n;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
             float p = 0.f;
             if (j < Lk) {
               p = v[t] * inv;
-              const int64_t gi = (((int64_t)b * a.heads + h) * Lq + i) * Lk + j;
+              const int64_t gi = (((int64_t)b * a.heads + h) * a.Lq + i) * a.Lk + j;     // padded-shape mask / probs
               if (a.probs_out != nullptr) a.probs_out[gi] = p;
               if (a.drop_mask != nullptr) p *= a.drop_mask[gi] ? a.drop_scale : 0.f;
             }
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
         }
       }
     }
-    float* ob = a.out + (int64_t)b * a.so + h * dh;
+    float* ob = a.out + (a.q_off ? (int64_t)a.q_off[b] * a.ldo : (int64_t)b * a.so) + h * dh;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       if (i0 + r < Lq) {
@@ -351,51 +356,59 @@ constexpr int MHA_TC_MAXNT = 12;     // key tiles of 8 -> Lk <= 96
 
 __host__ __device__ inline int mha_tc_pstride(int LkP) { return LkP + ((36 - (LkP & 31)) & 31); }   // stride % 32 == 4
 
-// one CTA per (sample, head); warp w owns query m-tiles w, w+4, ... (16 rows each)
+// one CTA per (sample, head); warp w owns query m-tiles w, w+nwarps, ... (16 rows each). NT = compile-time bound on the key
+// tiles (6 for Lk <= 48, else 12): the unrolled softmax over unused tiles would still issue (predicated off).
+template <int NT>
 __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
-  const int Lq = a.Lq, Lk = a.Lk, dh = a.dh;
+  const int Lq = a.q_len ? a.q_len[b] : a.Lq, Lk = a.k_len ? a.k_len[b] : a.Lk, dh = a.dh;
+  if (Lq <= 0) return;
   const int LqP = (Lq + 15) & ~15, LkP = (Lk + 7) & ~7;
-  const int QS = dh + 4, VS = dh + 8, PS = mha_tc_pstride(LkP);
+  const int LqM = (a.Lq + 15) & ~15, LkM = (a.Lk + 7) & ~7;  // carve-up by the maxima
+  const int QS = dh + 4, VS = dh + 8, PS = mha_tc_pstride(LkM);
   uint32_t* Qs = reinterpret_cast<uint32_t*>(smem);          // [LqP][QS]  tf32 bit patterns
-  uint32_t* Ks = Qs + LqP * QS;                              // [LkP][QS]
-  uint32_t* Vs = Ks + LkP * QS;                              // [LkP][VS]
-  uint32_t* Ps = Vs + LkP * VS;                              // [LqP][PS]
-  const float* qb = a.q + (int64_t)b * a.sq + h * dh;
-  const float* kb = a.k + (int64_t)b * a.sk + h * dh;
-  const float* vb = a.v + (int64_t)b * a.sv + h * dh;
+  uint32_t* Ks = Qs + LqM * QS;                              // [LkP][QS]
+  uint32_t* Vs = Ks + LkM * QS;                              // [LkP][VS]
+  uint32_t* Ps = Vs + LkM * VS;                              // [LqP][PS]
+  const float* qb = a.q + (a.q_off ? (int64_t)a.q_off[b] * a.ldq : (int64_t)b * a.sq) + h * dh;
+  const float* kb = a.k + (a.k_off ? (int64_t)a.k_off[b] * a.ldk : (int64_t)b * a.sk) + h * dh;
+  const float* vb = a.v + (a.k_off ? (int64_t)a.k_off[b] * a.ldv : (int64_t)b * a.sv) + h * dh;
   const int d4n = dh >> 2;
-  for (int i = threadIdx.x; i < LqP * d4n; i += MHA_TC_THREADS) {
+  // stage Q, K, V of this (sample, head): one fused loop, three independent streaming loads per iteration and the loop
+  // unrolled, so ~9 x 16 B per thread are in flight (the separate, rolled loops exposed the full DRAM latency per row)
+  const int nthr = blockDim.x;
+  const int nit = (max(LqP, LkP) * d4n + nthr - 1) / nthr;
+#pragma unroll 3
+  for (int it = 0; it < nit; ++it) {
+    const int i = threadIdx.x + it * nthr;
     const int r = i / d4n, c = i % d4n;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < Lq) v = *reinterpret_cast<const float4*>(qb + (int64_t)r * a.ldq + 4 * c);
-    *reinterpret_cast<uint4*>(Qs + r * QS + 4 * c) = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
-  }
-  for (int i = threadIdx.x; i < LkP * d4n; i += MHA_TC_THREADS) {
-    const int r = i / d4n, c = i % d4n;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv, vv = qv;
+    if (r < Lq) qv = ldg_stream4(qb + (int64_t)r * a.ldq + 4 * c);
     if (r < Lk) {
-      kv = *reinterpret_cast<const float4*>(kb + (int64_t)r * a.ldk + 4 * c);
-      vv = *reinterpret_cast<const float4*>(vb + (int64_t)r * a.ldv + 4 * c);
+      kv = ldg_stream4(kb + (int64_t)r * a.ldk + 4 * c);
+      vv = ldg_stream4(vb + (int64_t)r * a.ldv + 4 * c);
     }
-    *reinterpret_cast<uint4*>(Ks + r * QS + 4 * c) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
-    *reinterpret_cast<uint4*>(Vs + r * VS + 4 * c) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+    if (r < LqP) *reinterpret_cast<uint4*>(Qs + r * QS + 4 * c) = make_uint4(f2tf32(qv.x), f2tf32(qv.y), f2tf32(qv.z), f2tf32(qv.w));
+    if (r < LkP) {
+      *reinterpret_cast<uint4*>(Ks + r * QS + 4 * c) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
+      *reinterpret_cast<uint4*>(Vs + r * VS + 4 * c) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nkt = LkP >> 3;                                  // key tiles
   const float scale = rsqrtf((float)dh);
   const uint8_t* pad = a.key_pad ? a.key_pad + (int64_t)b * a.ld_pad : nullptr;
-  for (int mt = warp; mt * 16 < Lq; mt += MHA_TC_THREADS / 32) {
+  for (int mt = warp; mt * 16 < Lq; mt += (nthr >> 5)) {
     const int r0 = mt * 16 + g, r1 = r0 + 8;
-    float acc[MHA_TC_MAXNT][4];
+    float acc[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
     for (int k0 = 0; k0 < dh; k0 += 8) {
       const uint32_t a0 = Qs[r0 * QS + k0 + t], a1 = Qs[r1 * QS + k0 + t], a2 = Qs[r0 * QS + k0 + t + 4], a3 = Qs[r1 * QS + k0 + t + 4];
 #pragma unroll
-      for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         if (nt < nkt) {
           const uint32_t b0 = Ks[(nt * 8 + g) * QS + k0 + t], b1 = Ks[(nt * 8 + g) * QS + k0 + t + 4];
           mma_m16n8k8_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
@@ -405,7 +418,7 @@ __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
     // scores -> masked softmax per row; a row lives in the 4 lanes sharing g (cols 2t, 2t+1 of every key tile)
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       if (nt < nkt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -424,12 +437,12 @@ __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       if (nt < nkt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          acc[nt][e] = (acc[nt][e] == -INFINITY) ? 0.f : expf(acc[nt][e] - mx0);
-          acc[nt][2 + e] = (acc[nt][2 + e] == -INFINITY) ? 0.f : expf(acc[nt][2 + e] - mx1);
+          acc[nt][e] = (acc[nt][e] == -INFINITY) ? 0.f : __expf(acc[nt][e] - mx0);
+          acc[nt][2 + e] = (acc[nt][2 + e] == -INFINITY) ? 0.f : __expf(acc[nt][2 + e] - mx1);
           s0 += acc[nt][e];
           s1 += acc[nt][2 + e];
         }
@@ -438,9 +451,9 @@ __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
     const float inv0 = 1.f / s0, inv1 = 1.f / s1;
-    const int64_t pb0 = (((int64_t)b * a.heads + h) * Lq + r0) * Lk, pb1 = (((int64_t)b * a.heads + h) * Lq + r1) * Lk;
+    const int64_t pb0 = (((int64_t)b * a.heads + h) * a.Lq + r0) * a.Lk, pb1 = (((int64_t)b * a.heads + h) * a.Lq + r1) * a.Lk;
 #pragma unroll
-    for (int nt = 0; nt < MHA_TC_MAXNT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       if (nt < nkt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
         }
       }
     }
-    float* ob = a.out + (int64_t)b * a.so + h * dh;
+    float* ob = a.out + (a.q_off ? (int64_t)a.q_off[b] * a.ldo : (int64_t)b * a.so) + h * dh;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (nt * 8 < dh) {
@@ -587,6 +600,35 @@ __global__ void __launch_bounds__(256) reverse_tokens_kernel(const float* __rest
   }
 }
 
+// packed variant: x holds only the valid tokens, sample b's rows start at off[b]
+__global__ void __launch_bounds__(256) reverse_tokens_packed_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                    const int32_t* __restrict__ off, const int32_t* __restrict__ lengths,
+                                                                    int B, int L, int Hd) {
+  const int n4 = Hd >> 2;
+  const int64_t total = (int64_t)B * L * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % n4);
+    const int64_t bl = i / n4;
+    const int l = (int)(bl % L), b = (int)(bl / L);
+    const int src = lengths[b] - 1 - l;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src >= 0) v = reinterpret_cast<const float4*>(x + ((int64_t)off[b] + src) * Hd)[j];
+    reinterpret_cast<float4*>(out + ((int64_t)b * L + l) * Hd)[j] = v;
+  }
+}
+
+// dst[r, :] = src[idx[r], :]  (row gather: packs the valid tokens of a padded [B*L, C] matrix)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
+                                                          float* __restrict__ dst, int64_t ld_dst, int R, int C) {
+  const int n4 = C >> 2;
+  const int64_t total = (int64_t)R * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % n4);
+    const int r = (int)(i / n4);
+    reinterpret_cast<float4*>(dst + (int64_t)r * ld_dst)[j] = reinterpret_cast<const float4*>(src + (int64_t)idx[r] * ld_src)[j];
+  }
+}
+
 inline bool ln_shape_ok(int Hd) { return Hd % 4 == 0 && Hd >= 4 && Hd <= 32 * 4 * LN_MAXV; }
 
 }  // namespace
@@ -634,7 +676,8 @@ extern "C" int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* 
   return dasa_check_launch("layernorm_bwd_kernel");
 }
 
-extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
+static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_t* k_off, const int32_t* k_len,
+                        const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                             int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
                             float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out, int B, int heads, int Lq,
                             int Lk, int dh, int precision, void* stream) {
@@ -646,10 +689,13 @@ extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float
     const size_t smem_tc = sizeof(float) * ((size_t)LqP * (dh + 4) + (size_t)LkP * (dh + 4) + (size_t)LkP * (dh + 8) +
                                             (size_t)LqP * mha_tc_pstride(LkP));
     if (smem_tc <= 227 * 1024) {
-      cudaError_t e2 = cudaFuncSetAttribute(mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+      auto kern = (LkP <= 48) ? mha_fwd_tc_kernel<6> : mha_fwd_tc_kernel<MHA_TC_MAXNT>;
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
       if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc attr", e2); return DASA_ERR_CUDA; }
-      MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh};
-      mha_fwd_tc_kernel<<<(unsigned)(B * heads), MHA_TC_THREADS, smem_tc, (cudaStream_t)stream>>>(at);
+      MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
+                 q_off, q_len, k_off, k_len};
+      const int warps = (LqP / 16) < 4 ? (LqP / 16) : 4;       // one warp per 16-row query tile, no idle warps
+      kern<<<(unsigned)(B * heads), 32 * warps, smem_tc, (cudaStream_t)stream>>>(at);
       return dasa_check_launch("mha_fwd_tc_kernel");
     }
   }
@@ -662,9 +708,29 @@ extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float
   if (smem > 227 * 1024) return DASA_ERR_BAD_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { dasa_set_error("mha_fwd attr", e); return DASA_ERR_CUDA; }
-  MhaArgs a{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh};
+  MhaArgs a{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
+                 q_off, q_len, k_off, k_len};
   mha_fwd_kernel<<<(unsigned)(B * heads), 256, smem, (cudaStream_t)stream>>>(a);
   return dasa_check_launch("mha_fwd_kernel");
+}
+
+extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
+                            int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
+                            float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out, int B, int heads, int Lq,
+                            int Lk, int dh, int precision, void* stream) {
+  return mha_fwd_impl(nullptr, nullptr, nullptr, nullptr, q, ldq, sq, k, ldk, sk, v, ldv, sv, key_pad, ld_pad, drop_mask,
+                      drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh, precision, stream);
+}
+
+extern "C" int dasa_mha_fwd_varlen(const float* q, int64_t ldq, const int32_t* q_off, const int32_t* q_len, const float* k,
+                                   int64_t ldk, const float* v, int64_t ldv, const int32_t* k_off, const int32_t* k_len,
+                                   int64_t dense_q_stride, int64_t dense_kv_stride, const uint8_t* drop_mask, float drop_scale,
+                                   float* out, int64_t ldo, int B, int heads, int max_Lq, int max_Lk, int dh, int precision,
+                                   void* stream) {
+  if ((q_off == nullptr) != (q_len == nullptr) || (k_off == nullptr) != (k_len == nullptr)) return DASA_ERR_BAD_SHAPE;
+  return mha_fwd_impl(q_off, q_len, k_off, k_len, q, ldq, dense_q_stride, k, ldk, dense_kv_stride, v, ldv, dense_kv_stride,
+                      nullptr, 0, drop_mask, drop_scale, out, ldo, dense_q_stride / (ldq ? ldq : 1) * ldo, nullptr, B, heads,
+                      max_Lq, max_Lk, dh, precision, stream);
 }
 
 extern "C" int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
@@ -682,6 +748,28 @@ extern "C" int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float
                dq, dk, dv, lddq, sdq, lddk, sdk, lddv, sdv, B, heads, Lq, Lk, dh};
   mha_bwd_kernel<<<(unsigned)(B * heads), 256, smem, (cudaStream_t)stream>>>(a);
   return dasa_check_launch("mha_bwd_kernel");
+}
+
+extern "C" int dasa_reverse_tokens_packed(const float* x, const int32_t* offsets, const int32_t* lengths, float* out, int B, int L,
+                                          int Hd, void* stream) {
+  if (B <= 0 || L <= 0) return DASA_OK;
+  if (Hd % 4 != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(x) || !dasa_aligned16(out)) return DASA_ERR_BAD_ALIGN;
+  const int64_t total = (int64_t)B * L * (Hd / 4);
+  const unsigned grid = (unsigned)min((int64_t)DASA_NUM_SMS * 8, dasa_cdiv(total, 256));
+  reverse_tokens_packed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, offsets, lengths, B, L, Hd);
+  return dasa_check_launch("reverse_tokens_packed_kernel");
+}
+
+extern "C" int dasa_gather_rows(const float* src, int64_t ld_src, const int32_t* idx, float* dst, int64_t ld_dst, int R, int C,
+                                void* stream) {
+  if (R <= 0 || C <= 0) return DASA_OK;
+  if (C % 4 != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(src) || !dasa_aligned16(dst) || ld_src % 4 || ld_dst % 4) return DASA_ERR_BAD_ALIGN;
+  const int64_t total = (int64_t)R * (C / 4);
+  const unsigned grid = (unsigned)min((int64_t)DASA_NUM_SMS * 8, dasa_cdiv(total, 256));
+  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, ld_dst, R, C);
+  return dasa_check_launch("gather_rows_kernel");
 }
 
 extern "C" int dasa_reverse_tokens(const float* x, float* out, const int32_t* lengths, int B, int L, int Hd, void* stream) {

@@ -371,6 +371,34 @@ class _VisionEncoder(nn.Module):
         self.visn_layer_norm = nn.LayerNorm(hid, eps=1e-12)
 
 
+class PackInfo:
+    """Row bookkeeping for the packed (padding-free) evaluation of the frozen language / cross-modal stack: the valid tokens
+    of `steps` x B sequences stored back to back. Padded keys get an additive -10000 in the reference (vilmodel.py:1339-1347),
+    i.e. exactly 0 after the fp32 softmax, and padded query rows are never read downstream (r2rmodel.py:2326-2357), so
+    dropping them changes no output."""
+
+    def __init__(self, lengths_host, L, steps, device):
+        lens = [int(x) for x in lengths_host] * steps
+        self.L, self.steps, self.nseq = L, steps, len(lens)
+        off, rows, o = [], [], 0
+        for b, n in enumerate(lens):
+            off.append(o)
+            rows.extend(range(b * L, b * L + n))
+            o += n
+        self.ntok = o
+        self.max_len = max(lens)
+        self.off = torch.tensor(off, dtype=torch.int32, device=device)
+        self.len = torch.tensor(lens, dtype=torch.int32, device=device)
+        self.rows = torch.tensor(rows, dtype=torch.int32, device=device)      # packed row -> row of the padded [nseq*L, .] layout
+        self.rows64 = self.rows.to(torch.int64)
+        self.pair = (self.off, self.len)
+
+    def step_slice(self, t):
+        """Rows of rollout step t inside a packed tensor built with steps > 1."""
+        n1 = self.ntok // self.steps
+        return slice(t * n1, (t + 1) * n1)
+
+
 class DicModel(nn.Module):
     """vilmodel.py:1245-1423, forward-only kernels (train config: every output is detached, vilmodel.py:1377-1410)."""
 
@@ -401,40 +429,65 @@ class DicModel(nn.Module):
         self._qkv_cache[key] = (ver, w, b)
         return w, b
 
-    def _out_ln(self, out_mod, x, resid, tag, training):
+    def _row_mask(self, tag, y, pack, training):
+        """Dropout mask for a [.., hid] activation: padded per-step shape, or one row per packed token."""
+        if pack is None:
+            return self._mask(tag, (y.shape[0] // self._steps,) + tuple(y.shape[1:]), training, y.device)
         p = self.cfg.bert_dropout
+        if not training or p <= 0.0:
+            return None, 1.0
+        if _source.injected is None:
+            return _source.mask(tag, (pack.ntok, y.shape[-1]), p, training, y.device)
+        m, s = self._mask(tag, (pack.nseq // self._steps, pack.L, y.shape[-1]), training, y.device)   # tests: padded masks
+        return (None, 1.0) if m is None else (m.reshape(-1, y.shape[-1])[pack.rows64].contiguous(), s)
+
+    def _out_ln(self, out_mod, x, resid, tag, training, pack=None):
         y = ops.linear_fwd(x, out_mod.dense.weight, out_mod.dense.bias)
-        m, s = self._mask(tag, (y.shape[0] // self._steps,) + tuple(y.shape[1:]), training, y.device)
+        m, s = self._row_mask(tag, y, pack, training)
         return ops.dropout_residual_layernorm(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias,
                                               out_mod.LayerNorm.eps, m, s)
 
-    def _self_att(self, att_mod, x, key_pad, tag, training):
+    def _self_att(self, att_mod, x, key_pad, tag, training, pack=None):
         cfg = self.cfg
         hid = cfg.bert_hidden
         w, b = self._qkv(att_mod.self)
         qkv = ops.linear_fwd(x, w, b)
+        if pack is not None:                     # x [ntok, hid]: only valid tokens, no key padding left to mask
+            m, s = self._mask(tag + ".probs", (pack.nseq // self._steps, cfg.bert_heads, pack.L, pack.L), training, x.device)
+            o = ops.mha_fwd_varlen(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], cfg.bert_heads, pack.pair, pack.pair,
+                                   pack.L, pack.L, m, s)
+            return self._out_ln(att_mod.output, o, x, tag + ".out", training, pack)
         B, L = x.shape[0], x.shape[1]
         m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, L, L), training, x.device)
         o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s)
         return self._out_ln(att_mod.output, o, x, tag + ".out", training)
 
-    def _cross_att(self, xatt, x, ctx, key_pad, tag, training):
+    def _cross_att(self, xatt, x, ctx, key_pad, tag, training, q_pack=None, k_pack=None):
+        """q_pack: x is the packed language stream (ctx dense); k_pack: ctx is the packed language stream (x dense)."""
         cfg = self.cfg
         hid = cfg.bert_hidden
         q = ops.linear_fwd(x, xatt.att.query.weight, xatt.att.query.bias)
         w, b = self._qkv(xatt.att, "kv")
         kv = ops.linear_fwd(ctx, w, b)
+        if q_pack is not None or k_pack is not None:
+            pk = q_pack or k_pack
+            Lq = pk.L if q_pack is not None else x.shape[1]
+            Lk = pk.L if k_pack is not None else ctx.shape[1]
+            m, s = self._mask(tag + ".probs", (pk.nseq // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
+            o = ops.mha_fwd_varlen(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, q_pack.pair if q_pack else None,
+                                   k_pack.pair if k_pack else None, Lq, Lk, m, s)
+            return self._out_ln(xatt.output, o, x, tag + ".out", training, q_pack)
         B, Lq, Lk = x.shape[0], x.shape[1], ctx.shape[1]
         m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
         o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s)
         return self._out_ln(xatt.output, o, x, tag + ".out", training)
 
-    def _ffn(self, inter_mod, out_mod, x, tag, training):
+    def _ffn(self, inter_mod, out_mod, x, tag, training, pack=None):
         y = ops.linear_fwd(x, inter_mod.dense.weight, inter_mod.dense.bias, ops.EPI_BIAS_GELU)
-        return self._out_ln(out_mod, y, x, tag, training)
+        return self._out_ln(out_mod, y, x, tag, training, pack)
 
     @torch.no_grad()
-    def language_stack(self, input_ids, pad_mask, training, steps=1):
+    def language_stack(self, input_ids, pad_mask, training, steps=1, pack=None):
         """BertEmbeddings + la_layers x BertLayer (vilmodel.py:1366-1378). pad_mask: uint8 [B, L], 1 = padding.
         steps > 1 evaluates the stack for `steps` rollout actions at once: the instruction does not depend on the action
         taken, so the T per-action evaluations of the reference (agent_dg.py:789-797, each with its own dropout masks) are
@@ -448,9 +501,11 @@ class DicModel(nn.Module):
         m, s = self._mask("enc.emb", (B // steps, L, cfg.bert_hidden), training, input_ids.device)
         x = ops.embed_layernorm(input_ids, e.word_embeddings.weight, e.position_embeddings.weight,
                                 e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps, m, s)
+        if pack is not None:                     # drop the padding rows: everything below runs on valid tokens only
+            x = ops.gather_rows(x.view(B * L, -1), pack.rows)
         for i, layer in enumerate(self.lalayer):
-            a = self._self_att(layer.attention, x, pad_mask, "enc.la%d.att" % i, training)
-            x = self._ffn(layer.intermediate, layer.output, a, "enc.la%d.ffn" % i, training)
+            a = self._self_att(layer.attention, x, pad_mask, "enc.la%d.att" % i, training, pack)
+            x = self._ffn(layer.intermediate, layer.output, a, "enc.la%d.ffn" % i, training, pack)
         self._steps = 1
         return x
 
@@ -463,17 +518,17 @@ class DicModel(nn.Module):
         return _source.mask(tag, shape, self.cfg.bert_dropout, training, device)
 
     @torch.no_grad()
-    def cross_modal(self, lang, pad_mask, img_feats, training, steps=1):
+    def cross_modal(self, lang, pad_mask, img_feats, training, steps=1, pack=None):
         """VisionEncoder + vl_layers x LXRTXLayer (vilmodel.py:1383-1410). steps > 1: the inputs hold `steps` rollout actions
         stacked along dim 0 (teacher-forced rollouts know every observation up front); per-action dropout masks are kept."""
         cfg, ve = self.cfg, self.vision_encoder
         self._steps = steps
         try:
-            return self._cross_modal(lang, pad_mask, img_feats, training)
+            return self._cross_modal(lang, pad_mask, img_feats, training, pack)
         finally:
             self._steps = 1
 
-    def _cross_modal(self, lang, pad_mask, img_feats, training):
+    def _cross_modal(self, lang, pad_mask, img_feats, training, pack=None):
         cfg, ve = self.cfg, self.vision_encoder
         v = ops.linear_fwd(img_feats, ve.visn_fc.weight, ve.visn_fc.bias)
         m, s = self._mask("enc.visn", (v.shape[0] // self._steps,) + tuple(v.shape[1:]), training, v.device)
@@ -481,11 +536,11 @@ class DicModel(nn.Module):
                                               None, 1.0, m, s)
         for i, layer in enumerate(self.addlayer):
             t = "enc.vl%d" % i
-            l1 = self._cross_att(layer.visual_attention, lang, visn, None, t + ".x_lv", training)
-            v1 = self._cross_att(layer.visual_attention, visn, lang, pad_mask, t + ".x_vl", training)
-            l2 = self._self_att(layer.lang_self_att, l1, pad_mask, t + ".ls", training)
+            l1 = self._cross_att(layer.visual_attention, lang, visn, None, t + ".x_lv", training, q_pack=pack)
+            v1 = self._cross_att(layer.visual_attention, visn, lang, pad_mask, t + ".x_vl", training, k_pack=pack)
+            l2 = self._self_att(layer.lang_self_att, l1, pad_mask, t + ".ls", training, pack)
             v2 = self._self_att(layer.visn_self_att, v1, None, t + ".vs", training)
-            lang = self._ffn(layer.lang_inter, layer.lang_output, l2, t + ".lo", training)
+            lang = self._ffn(layer.lang_inter, layer.lang_output, l2, t + ".lo", training, pack)
             visn = self._ffn(layer.visn_inter, layer.visn_output, v2, t + ".vo", training)
         return lang, visn
 
@@ -567,29 +622,74 @@ class DicEncoder(nn.Module):
         self.encoder_lstm2decoder_ct = nn.Linear(n_in, dec_hidden_size)
         self.cache_language = False     # exact in eval mode; opt-in
         self._lang_cache = None
+        self.pack_tokens = True         # evaluate the frozen transformer stack on valid tokens only (see PackInfo)
+        self._packs = {}
 
-    def language_for_rollout(self, inputs, mask, steps):
-        """The language stack for `steps` actions in one batched pass -> [steps, B, L, hid] (see DicModel.language_stack)."""
+    def _pack(self, lengths, lengths_host, L, steps, device):
+        """PackInfo for this batch, or None (lengths only known on the device, finetune config, or packing switched off)."""
+        if not self.pack_tokens or self.cfg.update_add_layer:
+            return None
+        if lengths_host is None:
+            if isinstance(lengths, (list, tuple)):
+                lengths_host = lengths
+            elif torch.is_tensor(lengths) and not lengths.is_cuda:
+                lengths_host = lengths.tolist()
+            else:
+                return None
+        key = (tuple(int(x) for x in lengths_host), L, steps, str(device))
+        hit = self._packs.get(key)
+        if hit is None:
+            if len(self._packs) > 16:
+                self._packs.clear()
+            hit = self._packs[key] = PackInfo(key[0], L, steps, device)
+        return hit
+
+    class RolloutLanguage:
+        """Language-stack output of all `steps` actions of a rollout: padded [steps, B, L, hid] or packed rows."""
+
+        def __init__(self, x, pack, steps, B, L):
+            self.x, self.pack, self.steps, self.B, self.L = x, pack, steps, B, L
+
+        def __getitem__(self, t):
+            if self.pack is None:
+                return self.x.view(self.steps, self.B, self.L, -1)[t]
+            return self.x[self.pack.step_slice(t)]
+
+        def all(self):
+            return self.x if self.pack is not None else self.x.reshape(self.steps * self.B, self.L, -1)
+
+    def language_for_rollout(self, inputs, mask, steps, lengths_host=None):
+        """The language stack for `steps` actions in one batched pass (see DicModel.language_stack); index the result with the
+        action number to get that action's slice for forward(lang_out=...)."""
         L = mask.size(1)
         pad = mask.to(torch.uint8).contiguous()
-        out = self.bert.language_stack(inputs[:, :L].contiguous(), pad, self.training, steps)
-        return out.view(steps, inputs.shape[0], L, -1)
+        pack = self._pack(None, lengths_host, L, steps, inputs.device)
+        out = self.bert.language_stack(inputs[:, :L].contiguous(), pad, self.training, steps, pack)
+        return DicEncoder.RolloutLanguage(out, pack, steps, inputs.shape[0], L)
 
-    def encode_rollout(self, inputs, mask, lengths, f_all, steps, lang_all=None):
+    def encode_rollout(self, inputs, mask, lengths, f_all, steps, lang_all=None, lengths_host=None):
         """Encoder for `steps` actions of a TEACHER-FORCED rollout in one batch (the trajectory, hence every panorama, is
         independent of the policy's outputs): f_all [steps*B, 36, F] -> (ctx [steps*B, L, 2H], decoder_init [B, Hd], c_t [B, Hd])
         where the decoder initial state comes from action 0 (agent_dg.py:812-815). Per-action dropout masks are preserved."""
         tr = self.training
         B, L = inputs.shape[0], mask.size(1)
         pad = mask.to(torch.uint8).contiguous()
+        pack = self._pack(lengths, lengths_host, L, steps, f_all.device)
         if lang_all is None:
-            lang_all = self.bert.language_stack(inputs[:, :L].contiguous(), pad, tr, steps)
-        lang_all = lang_all.reshape(steps * B, L, -1)
+            lang_all = self.bert.language_stack(inputs[:, :L].contiguous(), pad, tr, steps, pack)
+        elif isinstance(lang_all, DicEncoder.RolloutLanguage):
+            assert (lang_all.pack is None) == (pack is None)
+            lang_all = lang_all.all()
+        if pack is None:
+            lang_all = lang_all.reshape(steps * B, L, -1)
         pad_all = pad.repeat(steps, 1)
         len32 = torch.as_tensor(lengths, device=lang_all.device).to(torch.int32).repeat(steps)
         if self.cfg.update_add_layer:                    # finetune: gradients flow into the cross-modal layers
             lang, visn = self.bert.cross_modal_grad(lang_all, pad_all, f_all, tr, steps)
             rev = Fn.ReverseTokensFn.apply(lang, len32)
+        elif pack is not None:
+            lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps, pack)
+            rev = ops.reverse_tokens_packed(lang, pack.off, pack.len, L)
         else:
             lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps)
             rev = ops.reverse_tokens(lang, len32)
@@ -605,7 +705,7 @@ class DicEncoder(nn.Module):
         ctx = Fn.dropout(ctx, m, sc)
         return ctx, decoder_init, c_t
 
-    def forward(self, inputs, mask, lengths, f_t_all=None, lang_out=None):
+    def forward(self, inputs, mask, lengths, f_t_all=None, lang_out=None, lengths_host=None):
         """inputs [B, maxInput] int64, mask [B, Lmax] bool (True = pad), lengths [B] (sorted desc), f_t_all [B, 36, F]
         -> (ctx [B, Lmax, 2H], decoder_init [B, Hd], c_t [B, Hd], mask, vision_outputs [B, 36, 768]).
         lang_out (optional extension): this action's language-stack output from language_for_rollout()."""
@@ -613,19 +713,24 @@ class DicEncoder(nn.Module):
         L = mask.size(1)
         pad = mask.to(torch.uint8).contiguous()
         ids = inputs[:, :L]
-        key = (inputs.data_ptr(), L, inputs._version)
+        pack = self._pack(lengths, lengths_host, L, 1, inputs.device)
+        key = (inputs.data_ptr(), L, inputs._version, pack is not None)
         if lang_out is not None:
-            lang0 = lang_out
+            lang0 = lang_out                             # this action's slice of language_for_rollout() (same packing)
+            assert (lang0.dim() == 2) == (pack is not None), "lang_out layout does not match this call's packing"
         elif self.cache_language and not tr and self._lang_cache is not None and self._lang_cache[0] == key:
             lang0 = self._lang_cache[1]
         else:
-            lang0 = self.bert.language_stack(ids, pad, tr)
+            lang0 = self.bert.language_stack(ids, pad, tr, 1, pack)
             if self.cache_language and not tr:
                 self._lang_cache = (key, lang0)
         len32 = torch.as_tensor(lengths, device=lang0.device).to(torch.int32)
         if self.cfg.update_add_layer:                    # finetune: gradients flow into the cross-modal layers
             lang, visn = self.bert.cross_modal_grad(lang0, pad, f_t_all, tr)
             rev = Fn.ReverseTokensFn.apply(lang, len32)
+        elif pack is not None:
+            lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr, 1, pack)
+            rev = ops.reverse_tokens_packed(lang, pack.off, pack.len, L)
         else:
             lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr)
             rev = ops.reverse_tokens(lang, len32)

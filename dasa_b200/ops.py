@@ -403,6 +403,46 @@ def mha_fwd(q, k, v, heads, key_pad=None, drop_mask=None, drop_scale=1.0, save_p
     return (out, probs) if save_probs else out
 
 
+def mha_fwd_varlen(q, k, v, heads, q_pack=None, k_pack=None, max_lq=None, max_lk=None, drop_mask=None, drop_scale=1.0):
+    """Attention over packed operands. q: [Nq, Hd] packed (q_pack = (off, len) int32 tensors) or dense [B, Lq, Hd] (q_pack None);
+    k, v likewise. Returns out laid out like q."""
+    Hd = q.shape[-1]
+    dh = Hd // heads
+    if q_pack is not None:
+        B = q_pack[0].numel()
+        out = torch.empty(q.shape[0], Hd, device=q.device, dtype=torch.float32)
+        ldq, ldo, sq = q.stride(0), Hd, 0
+    else:
+        B, max_lq = q.shape[0], q.shape[1]
+        out = torch.empty(B, max_lq, Hd, device=q.device, dtype=torch.float32)
+        ldq, ldo, sq = q.stride(1), Hd, q.stride(0)
+    if k_pack is not None:
+        ldk, ldv, skv = k.stride(0), v.stride(0), 0
+    else:
+        max_lk = k.shape[1]
+        ldk, ldv, skv = k.stride(1), v.stride(1), k.stride(0)
+        assert v.stride(0) == k.stride(0)
+    call("dasa_mha_fwd_varlen", _p(q), ldq, _p(q_pack[0]) if q_pack else None, _p(q_pack[1]) if q_pack else None, _p(k), ldk,
+         _p(v), ldv, _p(k_pack[0]) if k_pack else None, _p(k_pack[1]) if k_pack else None, sq, skv, _p(drop_mask),
+         float(drop_scale), _p(out), ldo, B, heads, int(max_lq), int(max_lk), dh, _precision, _stream())
+    return out
+
+
+def gather_rows(src2d, idx_i32, out=None):
+    R, C = idx_i32.numel(), src2d.shape[1]
+    if out is None:
+        out = torch.empty(R, C, device=src2d.device, dtype=torch.float32)
+    call("dasa_gather_rows", _p(src2d), src2d.stride(0), _p(idx_i32), _p(out), out.stride(0), R, C, _stream())
+    return out
+
+
+def reverse_tokens_packed(x_packed, offsets_i32, lengths_i32, L):
+    B, Hd = lengths_i32.numel(), x_packed.shape[1]
+    out = torch.empty(B, L, Hd, device=x_packed.device, dtype=torch.float32)
+    call("dasa_reverse_tokens_packed", _p(x_packed), _p(offsets_i32), _p(lengths_i32), _p(out), B, L, Hd, _stream())
+    return out
+
+
 def mha_bwd(q, k, v, probs, dout, heads, drop_mask=None, drop_scale=1.0):
     B, Lq, Hd = q.shape
     Lk = k.shape[1]

@@ -29,6 +29,7 @@ class DeviceEpisodes:
         self.seq = ep.seq.to(device)
         self.seq_mask = ep.seq_mask.to(device)
         self.seq_lengths = ep.seq_lengths.to(device).to(torch.int32)
+        self.seq_lengths_host = [int(x) for x in ep.seq_lengths.tolist()]   # lets the encoder drop padding rows without a sync
         self.dist = ep.dist.to(device) if hasattr(ep, "dist") else None      # [T+1, B] goal distances (sampled feedback)
         self.resident = resident
         if resident:
@@ -98,7 +99,8 @@ class NavPolicy:
         m_c, s_c = src.mask("dec.cand", (B, cand.shape[1], C), cfg.featdropout, tr, f_t.device)
         df_t = self.adaIn.gate_features(f_t, d_t, m_f, s_f)                 # K1 views
         cand_g = self.adaIn.gate_features(cand, cand_d, m_c, s_c)           # K1 candidates
-        ctx, en_h, en_c, _, _ = self.encoder(ep.seq, ep.seq_mask, ep.seq_lengths, f_t_all=f_t, lang_out=lang_out)   # RAW f_t
+        ctx, en_h, en_c, _, _ = self.encoder(ep.seq, ep.seq_mask, ep.seq_lengths, f_t_all=f_t, lang_out=lang_out,
+                                             lengths_host=ep.seq_lengths_host)                                  # RAW f_t
         prev_h1, c_0 = (en_h, en_c) if carry is None else carry
         h_t, c_t, logit, h1, _ = self.decoder(a_t, df_t, cand_g, prev_h1, prev_h1, c_0, ctx, ep.seq_mask,
                                               already_dropfeat=True, cand_leng=leng)
@@ -135,7 +137,8 @@ class NavPolicy:
             m_c, s_c = src.mask_steps("dec.cand", (B, nc, C), cfg.featdropout, tr, dev, T)
             df_all = self.adaIn.gate_features(f_all, d_all, m_f, s_f)                 # K1, all actions
             candg_all = self.adaIn.gate_features(cand_all, candd_all, m_c, s_c)
-            ctx_all, en_h, en_c = self.encoder.encode_rollout(ep.seq, ep.seq_mask, ep.seq_lengths, f_all, T)
+            ctx_all, en_h, en_c = self.encoder.encode_rollout(ep.seq, ep.seq_mask, ep.seq_lengths, f_all, T,
+                                                              lengths_host=ep.seq_lengths_host)
             L = ctx_all.shape[1]
             ctx_steps = ctx_all.view(T, B, L, -1).unbind(0)          # unbind: one stacked gradient instead of T zero-filled ones
             df_steps = df_all.view(T, B, cfg.views, cfg.feat).unbind(0)
@@ -154,7 +157,7 @@ class NavPolicy:
             src.prefix = base_prefix
             return total * (ml_weight / ep.B), logits, actions
         # the instruction-only language stack of all T actions in one batched pass (per-action dropout masks preserved)
-        lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T) if self.batch_language else None
+        lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T, ep.seq_lengths_host) if self.batch_language else None
         for t in range(T):
             if tag_steps:
                 src.prefix = base_prefix + "t%d." % t
@@ -183,7 +186,7 @@ class NavPolicy:
         reward = torch.empty(T, B, device=dev)
         mask = torch.empty(T, B, device=dev)
         carry, ctx, hidden, logps, ents, actions, logits = None, None, [], [], [], [], []
-        lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T) if self.batch_language else None
+        lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T, ep.seq_lengths_host) if self.batch_language else None
         for t in range(T):
             if tag_steps:
                 src.prefix = base_prefix + "t%d." % t

@@ -210,6 +210,22 @@ int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_
                  const float* dout, int64_t ldo, int64_t so, float* dq, int64_t lddq, int64_t sdq, float* dk,
                  int64_t lddk, int64_t sdk, float* dv, int64_t lddv, int64_t sdv,
                  int B, int heads, int Lq, int Lk, int dh, void* stream);
+/* Packed (variable-length) forward of the same attention for the frozen language / cross-modal stack: the valid tokens of
+ * all sequences are stored back to back (no padding rows are computed at all - padded keys carry an additive -10000 in the
+ * reference, i.e. an exact 0 after the fp32 softmax, so the valid outputs are unchanged). For a packed operand, sample b
+ * owns rows [off[b], off[b]+len[b]); pass NULL off/len for a dense operand ([B, max_L, *], sample stride dense_*_stride
+ * elements, e.g. the 36 panorama views). out is laid out like q. drop_mask keeps the padded shape [B,heads,max_Lq,max_Lk]. */
+int dasa_mha_fwd_varlen(const float* q, int64_t ldq, const int32_t* q_off, const int32_t* q_len, const float* k,
+                        int64_t ldk, const float* v, int64_t ldv, const int32_t* k_off, const int32_t* k_len,
+                        int64_t dense_q_stride, int64_t dense_kv_stride, const uint8_t* drop_mask, float drop_scale,
+                        float* out, int64_t ldo, int B, int heads, int max_Lq, int max_Lk, int dh, int precision,
+                        void* stream);
+/* dst[r,:] = src[idx[r],:] for r < R (C % 4 == 0): packs the valid tokens of a padded [B*L, C] activation             */
+int dasa_gather_rows(const float* src, int64_t ld_src, const int32_t* idx, float* dst, int64_t ld_dst, int R, int C,
+                     void* stream);
+/* token reversal straight from the packed layout into the padded [B, L, Hd] input of the bi-LSTM                        */
+int dasa_reverse_tokens_packed(const float* x, const int32_t* offsets, const int32_t* lengths, float* out, int B, int L,
+                               int Hd, void* stream);
 /* token reversal (r2rmodel.py:2326-2330): out[b,i,:] = x[b, len_b-1-i, :] for i < len_b else 0. Self-inverse, so
  * the same call maps gradients back.                                                                                */
 int dasa_reverse_tokens(const float* x, float* out, const int32_t* lengths, int B, int L, int Hd, void* stream);

@@ -1,0 +1,20 @@
+"""GPU helper: la-layer self-attention shape of the batched rollout (700 sequences x 12 heads x 45 tokens x 64)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dasa_b200 import ops
+ops.set_precision("tf32")
+B, L, H, hd = 700, 45, 12, 768
+qkv = torch.randn(B, L, 3 * hd, device="cuda")
+pad = (torch.arange(L, device="cuda")[None, :] >= torch.randint(8, L + 1, (B, 1), device="cuda")).to(torch.uint8)
+mask = (torch.rand(B, H, L, L, device="cuda") >= 0.1).to(torch.uint8)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+ts = []
+for i in range(8):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(); ops.mha_fwd(qkv[..., :hd], qkv[..., hd:2 * hd], qkv[..., 2 * hd:], H, pad, mask, 1 / 0.9); e1.record()
+    torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+ts.sort(); ms = ts[len(ts) // 2]
+byt = 4 * B * L * hd * 4 + B * H * L * L
+print("mha_fwd B=%d L=%d: %.1f us, %.0f GB/s" % (B, L, ms * 1e3, byt / ms / 1e6))

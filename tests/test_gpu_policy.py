@@ -407,3 +407,28 @@ def test_finetune_rollout_gradients_reach_cross_modal_layers(schedule):
     assert vl >= 60 and checked > vl
     assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for k, p in pol.encoder.named_parameters()
                if k.startswith("bert.lalayer.") or k.startswith("bert.embeddings."))
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_packed_encoder_equals_padded_encoder(train):
+    """The frozen transformer stack evaluated on valid tokens only (PackInfo, mha_fwd_varlen) returns the same ctx / decoder
+    init / vision stream as the padded evaluation, in eval mode and with injected dropout masks."""
+    cfg, B = SMALL, 5
+    st = synth.policy_state(cfg, 0)
+    ep = synth.Episodes(B, 1, cfg, seed=12)
+    dep = DeviceEpisodes(ep)
+    assert min(dep.seq_lengths_host) < dep.seq_mask.shape[1], "the batch must contain padding"
+    L, nc = ep.seq_mask.shape[1], ep.cand_feat.shape[2]
+    keep = _train_masks(cfg, B, 1, L, nc, 80) if train else {}
+    pol = NavPolicy(cfg, st)
+    pol = pol.train() if train else pol.eval()
+    outs = []
+    for packed in (False, True):
+        pol.encoder.pack_tokens = packed
+        src = M.DropoutSource(injected={k: m for k, (m, p) in keep.items()}, prefix="t0.")
+        with torch.no_grad(), M.use_dropout_source(src):
+            outs.append(pol.encoder(dep.seq, dep.seq_mask, dep.seq_lengths, f_t_all=dep.f_t[0], lengths_host=dep.seq_lengths_host))
+    for a, b, name in zip(outs[0], outs[1], ("ctx", "decoder_init", "c_t", "mask", "vision")):
+        if a.dtype == torch.bool:
+            continue
+        assert_close(b, a, 2e-6, "packed vs padded " + name)
