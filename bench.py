@@ -453,12 +453,13 @@ def run_ours(args):
 
 
 def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
-    """Event-time every dasa_gemm launch of one training rollout (the GEMM family is >80 %% of device time, see
-    profiles/), and report the tensor roofline of the aggregate: algorithmic FLOPs / summed duration."""
+    """Event-time every dasa_gemm launch of one training rollout. The dominant kernel of the step is the tcgen05 TF32 GEMM
+    (gemm_tf32_kernel<128,..>) on the token-major shapes of the transformer stack / bi-LSTM input projections (M >= 2048 rows;
+    ~45 % of the step in profiles/r01_ncu_launches_step_summary.txt): its tensor roofline = algorithmic FLOPs / summed duration.
+    The M = batch (20-row) decoder GEMMs stream their weights once per action and are reported against the HBM roofline."""
     from dasa_b200 import lib, modules as M
     events = []
     orig = lib.call
-    flops = [0.0]
 
     def hooked(name, *a):
         if name != "dasa_gemm":
@@ -467,26 +468,41 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
         e0.record()
         rc = orig(name, *a)
         e1.record()
-        events.append((e0, e1))
-        flops[0] += 2.0 * a[2] * a[3] * a[4]
+        events.append((e0, e1, int(a[2]), int(a[3]), int(a[4])))
         return rc
     import dasa_b200.ops as ops_mod
     ops_mod.call = hooked
+    T = ep.T if ep.dist is None else ep.T - 1
     try:
         pol.zero_grad()
         src.advance()
         with M.use_dropout_source(src):
-            loss, _, _ = pol.teacher_rollout(ep, min(ep.T, 4), ML_WEIGHT, tag_steps=False)
+            loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT, tag_steps=False)
         pol.backward(loss)
         torch.cuda.synchronize()
     finally:
         ops_mod.call = orig
-    secs = sum(a.elapsed_time(b) for a, b in events) * 1e-3
+    big = [(a.elapsed_time(b) * 1e-3, m, n, k) for a, b, m, n, k in events if m >= 2048]
+    small = [(a.elapsed_time(b) * 1e-3, m, n, k) for a, b, m, n, k in events if m < 2048]
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0       # TF32 dense peak = half the bf16 figure
-    ach = flops[0] / secs / 1e12
-    return {"bound": "tensor", "kernel": "dasa_gemm (tcgen05 tf32 / FFMA)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak, "traffic": None, "launches_timed": len(events),
-            "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src}
+    secs = sum(t for t, _, _, _ in big)
+    flops = sum(2.0 * m * n * k for _, m, n, k in big)
+    ach = flops / max(secs, 1e-12) / 1e12
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    s_secs = sum(t for t, _, _, _ in small)
+    s_bytes = sum(4.0 * (n * k + m * k + m * n) for _, m, n, k in small)
+    return {"bound": "tensor", "kernel": "gemm_tf32_kernel<128,3,*> (tcgen05.mma kind::tf32, TMA 128B-swizzle operands, TMEM accumulator), "
+                                         "token-major GEMMs with M >= 2048", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak,
+            # ncu --set full, one launch M=20300 N=3072 K=768 GELU epilogue (profiles/r01_gemm_tf32_big_ncu_full.txt):
+            # dram__bytes_read.sum + dram__bytes_write.sum; algorithmic bytes of that launch = 4*(M*K + N*K + M*N) = 321e6
+            "traffic": 267.7e6, "traffic_launch": "M=20300 N=3072 K=768 (algorithmic 321e6 B, 95.7 GFLOP)",
+            "launches_timed": len(big), "device_seconds": secs,
+            "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src,
+            "small_m_gemms": {"bound": "hbm", "what": "decoder / critic GEMMs with M = batch rows: weights streamed once per action",
+                              "achieved": s_bytes / max(s_secs, 1e-12) / 1e9, "peak": hbm, "unit": "GB/s",
+                              "frac": s_bytes / max(s_secs, 1e-12) / 1e9 / hbm, "launches_timed": len(small),
+                              "device_seconds": s_secs, "note": "eager launches, event-bracketed: includes launch gaps"}}
 
 
 if __name__ == "__main__":

@@ -23,6 +23,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in cta_mask and signals each one's barrier
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -79,7 +93,11 @@ struct TcParams {
   int debug;             // bit0: skip epilogue global stores (timing experiments only)
 };
 
-template <int BN, int STAGES, int EPI>
+// MC = 1: launched as clusters of two CTAs along N (same 128 rows of A, neighbouring column tiles). Each CTA loads HALF of the
+// A tile and multicasts it into both CTAs, so the L2 -> SM operand traffic per tile drops from (A + B) to (A/2 + B): the fp32
+// operand stream (32 FLOP/B at 128x128) is what bounds this kernel, not the tensor pipe. A stage is recycled only after BOTH
+// CTAs' MMAs have consumed it (tcgen05.commit multicast onto both `empty` barriers, which then count 2 arrivals).
+template <int BN, int STAGES, int EPI, int MC = 0>
 __global__ void __launch_bounds__(TC_THREADS, (STAGES <= 4 ? 2 : 1))
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -101,14 +119,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);       // BN fp32 accumulator columns x 128 lanes
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();           // the peer's barriers exist before any multicast load / commit reaches them
   tc_fence_after();
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TC_STAMP(1);
 
@@ -120,7 +140,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&empty_bar[s], ph ^ 1);
       mbar_expect_tx(&full_bar[s], STAGE_BYTES);
       unsigned char* a_dst = tiles + s * STAGE_BYTES;
-      tma_load_2d(a_dst, &tmA, kbeg + kb * TC_BK, m0, &full_bar[s]);
+      if constexpr (MC) {                       // my 64-row half of A goes to both CTAs; the peer supplies the other half
+        tma_load_2d_mc(a_dst + crank * (A_BYTES / 2), &tmA, kbeg + kb * TC_BK, m0 + (int)crank * (TC_BM / 2), &full_bar[s], (uint16_t)3);
+      } else {
+        tma_load_2d(a_dst, &tmA, kbeg + kb * TC_BK, m0, &full_bar[s]);
+      }
       tma_load_2d(a_dst + A_BYTES, &tmB, kbeg + kb * TC_BK, n0, &full_bar[s]);
       if (kb == 0) TC_STAMP(2);
     }
@@ -143,7 +167,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // advance the start address by k*32 bytes inside the 128-byte swizzled row (address field is in 16-byte units)
         umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
       }
-      umma_commit(&empty_bar[s]);      // smem stage free once these MMAs have consumed it
+      if constexpr (MC) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // frees the stage in BOTH CTAs' books
+      else umma_commit(&empty_bar[s]);  // smem stage free once these MMAs have consumed it
     }
     umma_commit(tmem_full);            // accumulator complete
     TC_STAMP(5);
@@ -222,6 +247,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
   if (threadIdx.x == 32) TC_STAMP(8);
+  if constexpr (MC) cluster_sync_all();           // the peer may still commit onto / multicast into this CTA's shared memory
 }
 
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N, float alpha, float beta,
@@ -296,6 +322,45 @@ int launch_tc_e(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
   return dasa_check_launch("gemm_tf32_kernel");
 }
 
+// cluster (2,1,1) launch of the A-multicast variant; ta must have been built with 64-row boxes
+template <int BN, int STAGES, int EPI>
+int launch_tc_mc_e(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+  auto kern = gemm_tf32_kernel<BN, STAGES, EPI, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { dasa_set_error("gemm_tf32<mc> attr", e); return DASA_ERR_CUDA; }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)dasa_cdiv(p.N, BN), (unsigned)dasa_cdiv(p.M, TC_BM), 1);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (e != cudaSuccess) { dasa_set_error("gemm_tf32_kernel<mc>", e); return DASA_ERR_CUDA; }
+  return DASA_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc_mc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+  switch (p.epilogue) {
+    case DASA_EPI_BIAS: return launch_tc_mc_e<BN, STAGES, DASA_EPI_BIAS>(ta, tb, p, st);
+    case DASA_EPI_BIAS_GELU: return launch_tc_mc_e<BN, STAGES, DASA_EPI_BIAS_GELU>(ta, tb, p, st);
+    case DASA_EPI_GATE: return launch_tc_mc_e<BN, STAGES, DASA_EPI_GATE>(ta, tb, p, st);
+    case DASA_EPI_NONE: return launch_tc_mc_e<BN, STAGES, DASA_EPI_NONE>(ta, tb, p, st);
+    default: return DASA_ERR_UNSUPPORTED;
+  }
+}
+
 template <int BN, int STAGES>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int splits, cudaStream_t st) {
   // split-K launches only store raw partial sums: one (NONE) instantiation serves them all
@@ -312,6 +377,15 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, i
 }
 
 }  // namespace
+
+// A-multicast variant: measured NO gain on B200 (M=20300 N=3072 K=768: 315 us vs 297 us; N=768 K=3072: 209 vs 205 us) - at 46-67 %
+// of the TF32 peak the kernel is bound by the per-tile prologue / epilogue, not by the L2 -> SM operand stream - so it is off
+// unless DASA_TC_MULTICAST=1 or dasa_debug_gemm_multicast(1); kept (and tested) as the base of a persistent multicast kernel.
+static int g_use_mc = -1;
+extern "C" int dasa_debug_gemm_multicast(int on) {
+  g_use_mc = on ? 1 : 0;
+  return DASA_OK;
+}
 
 extern "C" int dasa_debug_tc_timestamps(unsigned long long* host16) {
   return cudaMemcpyFromSymbol(host16, g_tc_ts, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : DASA_ERR_CUDA;
@@ -342,11 +416,20 @@ int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, c
     if (workspace == nullptr || workspace_bytes < need) { pl.splits = 1; pl.k_per_split = (int)dasa_cdiv(K, TC_BK) * TC_BK; }
     else partial = static_cast<float*>(workspace);
   }
-  CUtensorMap ta, tb;
-  if (!make_map(&ta, A, M, K, lda, TC_BM) || !make_map(&tb, B, N, K, ldb, pl.bn)) return DASA_ERR_UNSUPPORTED;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("DASA_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  if (g_use_mc < 0) { const char* e = getenv("DASA_TC_MULTICAST"); g_use_mc = e ? atoi(e) : 0; }
+  const int use_mc = g_use_mc;
   TcParams p{M, N, K, alpha, beta, C, ldc, epilogue, ep, partial, pl.k_per_split, dbg};
+  CUtensorMap ta, tb;
+  // many-wave 128x128 problems with an even number of column tiles: pairs of CTAs share their A rows through TMA multicast
+  const int64_t ntn = dasa_cdiv(N, 128);
+  if (use_mc && pl.bn == 128 && pl.splits == 1 && (ntn % 2) == 0 && dasa_cdiv(M, TC_BM) * ntn > 2 * DASA_NUM_SMS &&
+      (epilogue == DASA_EPI_BIAS || epilogue == DASA_EPI_BIAS_GELU || epilogue == DASA_EPI_GATE || epilogue == DASA_EPI_NONE)) {
+    if (!make_map(&ta, A, M, K, lda, TC_BM / 2) || !make_map(&tb, B, N, K, ldb, 128)) return DASA_ERR_UNSUPPORTED;
+    return launch_tc_mc<128, 3>(ta, tb, p, st);
+  }
+  if (!make_map(&ta, A, M, K, lda, TC_BM) || !make_map(&tb, B, N, K, ldb, pl.bn)) return DASA_ERR_UNSUPPORTED;
   // 3 x 32 KB / 4 x 24 KB stages = 96 KB of pipeline per CTA: two CTAs co-reside on an SM, so one CTA's epilogue and
   // prologue overlap the other's main loop and a 192-tile problem needs no second wave.
   // otherwise (one CTA per SM anyway) the deep 6/8-stage ring keeps 192 KB of loads in flight per SM.

@@ -62,7 +62,11 @@ typedef struct {
   int64_t ld_gate;
   float* gate_out;            /* EPI_GATE: sigmoid(acc+bias) saved here when non-NULL, [M, ld_gate_out] */
   int64_t ld_gate_out;
-  const uint8_t* drop_mask;   /* optional keep mask [M, N] contiguous, applied to the final value */
+  const uint8_t* drop_mask;   /* Debug / experiment switch: route many-wave 128x128 TF32 GEMMs through the cluster-of-2 TMA-multicast variant (each CTA
+ * loads half of the shared A tile and multicasts it). Off by default: measured no gain on B200 (see gemm_tc.cu). */
+int dasa_debug_gemm_multicast(int on);
+
+/* optional keep mask [M, N] contiguous, applied to the final value */
   float drop_scale;
 } dasa_epilogue_t;
 

@@ -576,3 +576,62 @@ def test_linear_gelu_fwd_bwd():
     assert_close(xd.grad, x.grad, 2e-4, "dx")
     assert_close(wd.grad, w.grad, 2e-4, "dW")
     assert_close(bd.grad, b.grad, 2e-4, "db")
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 3e-3)])
+def test_mha_varlen_packed_matches_padded(prec, tol):
+    """dasa_mha_fwd_varlen: packed queries and/or keys give the same rows as the padded call with a key padding mask."""
+    gen = g(77)
+    B, L, V, heads, dh = 6, 45, 36, 12, 64
+    Hd = heads * dh
+    lens = torch.randint(5, L + 1, (B,), generator=gen)
+    lens[0] = L
+    pad = torch.arange(L)[None, :] >= lens[:, None]
+    x = torch.randn(B, L, 3 * Hd, generator=gen)
+    vis = torch.randn(B, V, 3 * Hd, generator=gen)
+    keep = torch.rand(B, heads, L, L, generator=gen) >= 0.1
+    rows = torch.cat([torch.arange(n) + b * L for b, n in enumerate(lens.tolist())])
+    off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)[:-1]]).int().to(DEV)
+    len32 = lens.int().to(DEV)
+    xd, vd = x.to(DEV), vis.to(DEV)
+    xp = xd.view(B * L, -1)[rows.to(DEV)].contiguous()
+    km = keep.to(torch.uint8).to(DEV)
+    ops.set_precision(prec)
+    try:
+        ref = ops.mha_fwd(xd[..., :Hd], xd[..., Hd:2 * Hd], xd[..., 2 * Hd:], heads, pad.to(DEV), km, 1 / 0.9)
+        got = ops.mha_fwd_varlen(xp[:, :Hd], xp[:, Hd:2 * Hd], xp[:, 2 * Hd:], heads, (off, len32), (off, len32), L, L, km, 1 / 0.9)
+        assert_close(got, ref.view(B * L, Hd)[rows.to(DEV)], tol, "self-attention, packed q and k")
+        # language queries (packed) over the dense views; dense view queries over the packed language keys
+        ref = ops.mha_fwd(xd[..., :Hd], vd[..., Hd:2 * Hd], vd[..., 2 * Hd:], heads)
+        got = ops.mha_fwd_varlen(xp[:, :Hd], vd[..., Hd:2 * Hd], vd[..., 2 * Hd:], heads, (off, len32), None, L, V)
+        assert_close(got, ref.view(B * L, Hd)[rows.to(DEV)], tol, "packed q, dense k")
+        ref = ops.mha_fwd(vd[..., :Hd], xd[..., Hd:2 * Hd], xd[..., 2 * Hd:], heads, pad.to(DEV))
+        got = ops.mha_fwd_varlen(vd[..., :Hd], xp[:, Hd:2 * Hd], xp[:, 2 * Hd:], heads, None, (off, len32), V, L)
+        assert_close(got, ref, tol, "dense q, packed k")
+    finally:
+        ops.set_precision("fp32")
+    rev = ops.reverse_tokens_packed(xp[:, :Hd].contiguous(), off, len32, L)
+    assert torch.equal(rev, ops.reverse_tokens(xd[..., :Hd].contiguous(), len32))
+
+
+def test_gemm_tf32_multicast_variant():
+    """Cluster-of-2 TMA-multicast tcgen05 GEMM (experiment switch): same numbers as the default kernel, all its epilogues."""
+    from dasa_b200 import lib
+    gen = g(3)
+    M, N, K = 5000, 1024, 800                       # 40 x 8 tiles > 2 x 148: eligible
+    A, W, b = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen), torch.randn(N, generator=gen)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), b.to(DEV)
+    ref = A.double() @ W.double().t() + b.double()
+    outs = []
+    for on in (0, 1):
+        lib.load().dasa_debug_gemm_multicast(on)
+        try:
+            C = torch.empty(M, N, device=DEV)
+            ops.gemm(Ad, K, 1, Wd, K, 1, C, N, M, N, K, epilogue=ops.EPI_BIAS, bias=bd, precision=ops.PREC_TF32)
+            Cg = torch.empty(M, N, device=DEV)
+            ops.gemm(Ad, K, 1, Wd, K, 1, Cg, N, M, N, K, epilogue=ops.EPI_BIAS_GELU, bias=bd, precision=ops.PREC_TF32)
+        finally:
+            lib.load().dasa_debug_gemm_multicast(0)
+        outs.append((C, Cg))
+        assert_close(C, ref, 3e-3, "tf32 gemm (multicast=%d)" % on)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
