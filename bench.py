@@ -378,6 +378,8 @@ def run_ours(args):
         sampler.start()
     ms_step, launches = timed(False, False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    launch_mode = "cuda-graph replay of the whole rollout" if state["graph"] is not None else \
+        "eager launches (%s)" % (state["graph_error"] or "--no-graph")
     ms_e2e, _ = timed(True, True, args.steps, 1)
     Fn.invalidate_weight_caches()
     # the same workload on the per-action schedule (the order a sampled / greedy rollout is forced to use)
@@ -438,8 +440,7 @@ def run_ours(args):
                    "schedule": ("batched: the agent follows the teacher, so all T observations are known up front and AdaIN + "
                                 "cross-modal layers + bi-LSTM of the T actions run as one batch; decoder sequential"
                                 if args.schedule == "batched" else "sequential: AdaIN -> encoder -> decoder per action"),
-                   "launch": "cuda-graph replay of the whole rollout" if state["graph"] is not None else
-                             "eager launches (%s)" % (state["graph_error"] or "--no-graph")},
+                   "launch": launch_mode},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "nav steps/s", "h2d_bytes_per_step": host_ep.h2d_bytes_per_step() * T,
                 "d2h_bytes_per_step": 4},

@@ -84,3 +84,7 @@ size_t dasa_gemm_tc_workspace(int M, int N, int K);
 int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
                  const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue, const EpiParams& ep,
                  void* workspace, size_t workspace_bytes, cudaStream_t st);
+// persistent CTA-pair (cta_group::2) kernel, gemm_tc2.cu: tile width (256 / 128) or 0 = keep the single-CTA kernel
+int dasa_gemm_pair_plan(int M, int N, int K);
+int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                      float* C, int64_t ldc, int epilogue, const EpiParams& ep, cudaStream_t st);

@@ -401,6 +401,7 @@ bool dasa_gemm_tc_supported(int a_kmajor, int b_kmajor, int M, int N, int K, con
 }
 
 size_t dasa_gemm_tc_workspace(int M, int N, int K) {
+  if (dasa_gemm_pair_plan(M, N, K)) return 0;
   TcPlan pl = plan_tc(M, N, K);
   return pl.splits > 1 ? (size_t)pl.splits * M * N * sizeof(float) : 0;
 }
@@ -409,6 +410,9 @@ int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, c
                  int64_t ldb, float beta, float* C, int64_t ldc, int epilogue, const EpiParams& ep, void* workspace,
                  size_t workspace_bytes, cudaStream_t st) {
   (void)a_kmajor; (void)b_kmajor;
+  // many-tile problems: persistent CTA-pair kernel (gemm_tc2.cu), 256 x BN tiles, half the L2 -> SM operand bytes per FLOP
+  if (const int bn2 = dasa_gemm_pair_plan(M, N, K))
+    return dasa_gemm_tc_pair(bn2, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, st);
   TcPlan pl = plan_tc(M, N, K);
   float* partial = nullptr;
   if (pl.splits > 1) {

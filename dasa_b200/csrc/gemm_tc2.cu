@@ -1,0 +1,349 @@
+// Persistent CTA-pair (tcgen05 cta_group::2) TF32 GEMM for the many-tile token-major projections:
+//   C[M,N] = epi(alpha * A[M,K] * B[N,K]^T + beta*C),  A and B K-major fp32 in HBM.
+//
+// Why a second kernel: the 128x128 single-CTA kernel (gemm_tc.cu) pulls (128+128) x 32 fp32 per 1 MFLOP through L2 -> SM
+// (32 FLOP/B) and ncu shows it pinned at the L2 output cap (3.0 GB in 300 us for M=20300 N=3072 K=768), well below the tensor
+// pipe. Here two SMs of a TPC form one 256 x BN tile: each CTA stages ITS 128 rows of A and ITS BN/2 rows of B only, the
+// leader's single thread issues tcgen05.mma.cta_group::2 (UMMA 256 x BN x 8) which reads both halves of B from both SMs'
+// shared memory, and each CTA's TMEM receives its own 128 accumulator rows: 64 FLOP per L2 byte at BN = 256.
+// The kernel is persistent (one pair per TPC, static tile schedule) with a double-buffered TMEM accumulator, so the eight
+// epilogue warps drain tile i (tcgen05.ld -> smem transpose -> fused epilogue -> coalesced 128-bit stores) while the MMA
+// thread already accumulates tile i+1.
+//   warp 0 lane 0 : TMA producer (both CTAs; cp.async.bulk.tensor .cta_group::2 completing on the LEADER's mbarrier)
+//   warp 1 lane 0 : MMA issuer (leader CTA only); tcgen05.commit multicast frees the stage / publishes the accumulator in both CTAs
+//   warps 2..9    : epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4): two warps per SM sub-partition, so
+//                   one warp's tcgen05.ld / shared-memory round trip hides behind the other's activation math
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "gemm_common.cuh"
+
+namespace {
+
+constexpr int P_BM = 128;            // rows of A per CTA (256 per pair)
+constexpr int P_BK = 32;             // 32 fp32 = one 128-byte swizzle row
+constexpr int P_EPI_WARPS = 8;       // two warps per TMEM lane quarter, each draining half of the tile's columns
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_EPI_LD = 36;         // staging row stride (floats): conflict-free 128-bit rows
+
+struct PairParams {
+  int M, N, K;
+  float alpha, beta;
+  float* C; int64_t ldc;
+  EpiParams ep;
+  int tiles_n, tiles_total, num_pairs;
+};
+
+__device__ __forceinline__ void p_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void p_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t p_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void p_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t p_mapa(uint32_t local, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
+}
+__device__ __forceinline__ void p_remote_arrive(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pair-aware tile load: lands in the executing CTA's shared memory, completes its bytes on the mbarrier at `bar_cluster`
+__device__ __forceinline__ void p_tma_load_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void p_commit_pair(uint64_t* bar) {       // arrives on `bar` at the same offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void p_umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint64_t p_desc_sw128(const void* smem_ptr) {   // K-major, 128B swizzle, 8-row atoms 1024 B apart
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, PairParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int A_BYTES = P_BM * P_BK * 4, B_BYTES = (BN / 2) * P_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers of BN fp32 columns
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* stage_all = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_all + P_EPI_WARPS * 32 * P_EPI_LD);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;              // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                  // [2], the leader's copy is the one that counts
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = p_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int nkb = (p.K + P_BK - 1) / P_BK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * P_EPI_WARPS); }   // every epilogue warp of both CTAs
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  p_fence_before();
+  __syncthreads();
+  p_cluster_sync();                                       // the peer's barriers and TMEM exist before anything reaches them
+  p_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // -------------------------------------------------------------- TMA producer (both CTAs)
+      uint32_t it = 0;
+      for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs) {
+        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+        const int m0 = mt * (2 * P_BM) + (int)crank * P_BM;
+        const int nb0 = nt * BN + (int)crank * (BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // both CTAs' boxes complete on the leader's barrier
+          const uint32_t fb = p_mapa(smem_u32(&full_bar[s]), 0);
+          unsigned char* dst = tiles + s * STAGE_BYTES;
+          p_tma_load_2sm(dst, &tmA, kb * P_BK, m0, fb);
+          p_tma_load_2sm(dst + A_BYTES, &tmB, kb * P_BK, nb0, fb);
+        }
+      }
+      // drain: every multicast commit aimed at this CTA's `empty` barriers has landed before the CTA may exit
+      const uint32_t last = it;
+      for (uint32_t j = (last > (uint32_t)STAGES ? last - STAGES : 0u); j < last; ++j)
+        mbar_wait(&empty_bar[j % STAGES], (j / STAGES) & 1);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // -------------------------------------------------------------- MMA issuer (leader CTA, single thread)
+      // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 256 (128 rows in each CTA's TMEM)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs, ++tcount) {
+        const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty[a], aph ^ 1);               // both CTAs' epilogues have drained this accumulator buffer
+        p_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          p_fence_after();
+          unsigned char* src = tiles + s * STAGE_BYTES;
+          const uint64_t da = p_desc_sw128(src);
+          const uint64_t db = p_desc_sw128(src + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < P_BK / 8; ++k)
+            p_umma_tf32_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          p_commit_pair(&empty_bar[s]);                    // stage free in both CTAs once these MMAs retire
+        }
+        p_commit_pair(&tmem_full[a]);                      // accumulator complete: visible to both CTAs' epilogues
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps 2..9 (both CTAs)
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const int chalf = (warp - 2) >> 2;                     // which half of the tile's columns
+    constexpr int CW = BN / 2;                             // columns per epilogue warp
+    float* stg = stage_all + (warp - 2) * 32 * P_EPI_LD;
+    const int col4 = lane & 7, rsub = lane >> 3;           // read-back: 8 lanes x float4 per row, 4 rows per instruction
+    const float alpha = p.alpha, beta = p.beta;
+    const bool c_vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool plain = c_vec && beta == 0.f && alpha == 1.f;
+    const uint32_t empty_remote0 = p_mapa(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t empty_remote1 = p_mapa(smem_u32(&tmem_empty[1]), 0);
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs, ++tcount) {
+      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+      const int m_base = mt * (2 * P_BM) + (int)crank * P_BM + q * 32;
+      const int n_base = nt * BN + chalf * CW;
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&tmem_full[a], aph);
+      p_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + chalf * CW;
+      const bool interior = plain && (m_base + 32 <= p.M) && (n_base + CW <= p.N);   // warp-uniform: no edge checks at all
+#pragma unroll 1
+      for (int c0 = 0; c0 < CW; c0 += 32) {
+        uint32_t r[32];
+        p_tmem_ld32(t_addr + (uint32_t)c0, r);
+        if (c0 + 32 >= CW) {                               // last TMEM read of this buffer: hand it back to the MMA thread
+          p_fence_before();
+          __syncwarp();
+          if (lane == 0) p_remote_arrive(a ? empty_remote1 : empty_remote0);
+        }
+        float* srow = stg + lane * P_EPI_LD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(srow + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int n = n_base + c0 + 4 * col4;
+        if (interior) {
+          float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (epi_has_bias<EPI>()) {
+            if (p.ep.bias != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) bias4[e] = __ldg(p.ep.bias + n + e);
+            }
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int m = m_base + rr + rsub;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + (rr + rsub) * P_EPI_LD + 4 * col4);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = apply_activation_t<EPI>(v[e] + bias4[e], m, n + e, p.N, p.ep);
+            *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else if (n < p.N) {
+          const bool vec_ok = c_vec && (n + 3 < p.N);
+          float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (epi_has_bias<EPI>()) {
+            if (p.ep.bias != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) bias4[e] = __ldg(p.ep.bias + n + e);
+            }
+          }
+#pragma unroll 2
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int m = m_base + rr + rsub;
+            if (m >= p.M) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + (rr + rsub) * P_EPI_LD + 4 * col4);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            float* crow = p.C + (int64_t)m * p.ldc + n;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (n + e < p.N) {
+                float x = alpha * v[e];
+                if (beta != 0.f) x += beta * crow[e];
+                v[e] = apply_activation_t<EPI>(x + bias4[e], m, n + e, p.N, p.ep);
+              }
+            }
+            if (vec_ok) *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+            else
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) crow[e] = v[e];
+          }
+        }
+        __syncwarp();                                      // staging rows are rewritten by the next chunk
+      }
+    }
+  }
+
+  p_fence_before();
+  __syncthreads();
+  p_cluster_sync();                                        // neither CTA frees TMEM / exits while the other may still signal it
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool pair_make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(dasa_tensormap_encoder());
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES, int EPI>
+int launch_pair_e(const CUtensorMap& ta, const CUtensorMap& tb, const PairParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + P_EPI_WARPS * 32 * P_EPI_LD * 4 + 256 + 1024;
+  static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
+  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { dasa_set_error("gemm_tf32_pair attr", e); return DASA_ERR_CUDA; }
+    attr_set = true;
+  }
+  kern<<<dim3(2u * (unsigned)p.num_pairs), P_THREADS, smem, st>>>(ta, tb, p);     // __cluster_dims__(2,1,1): one pair per TPC
+  return dasa_check_launch("gemm_tf32_pair_kernel");
+}
+
+template <int BN, int STAGES>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const PairParams& p, int epilogue, cudaStream_t st) {
+  switch (epilogue) {
+    case DASA_EPI_BIAS: return launch_pair_e<BN, STAGES, DASA_EPI_BIAS>(ta, tb, p, st);
+    case DASA_EPI_BIAS_TANH: return launch_pair_e<BN, STAGES, DASA_EPI_BIAS_TANH>(ta, tb, p, st);
+    case DASA_EPI_BIAS_GELU: return launch_pair_e<BN, STAGES, DASA_EPI_BIAS_GELU>(ta, tb, p, st);
+    case DASA_EPI_BIAS_RELU: return launch_pair_e<BN, STAGES, DASA_EPI_BIAS_RELU>(ta, tb, p, st);
+    case DASA_EPI_GATE: return launch_pair_e<BN, STAGES, DASA_EPI_GATE>(ta, tb, p, st);
+    case DASA_EPI_TANH: return launch_pair_e<BN, STAGES, DASA_EPI_TANH>(ta, tb, p, st);
+    default: return launch_pair_e<BN, STAGES, DASA_EPI_NONE>(ta, tb, p, st);
+  }
+}
+
+}  // namespace
+
+static int g_pair_mode = -1;          // -1: read DASA_TC_PAIR (default 1), 0: never, 1: when eligible, 2: always (tests)
+extern "C" int dasa_debug_gemm_pair(int mode) {
+  g_pair_mode = mode;
+  return DASA_OK;
+}
+
+// Tile width for the pair kernel, or 0 when the single-CTA kernel should keep the problem. A pair processes 256 x BN tiles; the
+// static schedule wants at least one full wave over the 74 TPCs and little tail quantisation.
+int dasa_gemm_pair_plan(int M, int N, int K) {
+  if (g_pair_mode < 0) { const char* e = getenv("DASA_TC_PAIR"); g_pair_mode = e ? atoi(e) : 1; }
+  if (g_pair_mode == 0 || K < P_BK) return 0;
+  if (g_pair_mode == 2) return 256;
+  // measured on B200 (scripts/pair_gemm.py): 256-wide tiles beat both the 128-wide pair tiles and the single-CTA kernel on every
+  // many-tile shape of the rollout (540-770 vs 320-600 TFLOP/s); problems that do not fill one wave of the 74 TPCs, or that
+  // leave most of the last wave idle, stay on the single-CTA kernel (which can split K).
+  const int pairs = DASA_NUM_SMS / 2;
+  const int64_t t = dasa_cdiv(M, 2 * P_BM) * dasa_cdiv(N, 256);
+  if (t < pairs) return 0;
+  const double eff = (double)t / (double)(dasa_cdiv(t, pairs) * pairs);
+  return eff >= 0.6 ? 256 : 0;
+}
+
+int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                      float* C, int64_t ldc, int epilogue, const EpiParams& ep, cudaStream_t st) {
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ep = ep;
+  p.tiles_n = (int)dasa_cdiv(N, bn);
+  p.tiles_total = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta, tb;
+  if (!pair_make_map(&ta, A, M, K, lda, P_BM) || !pair_make_map(&tb, B, N, K, ldb, bn / 2)) return DASA_ERR_UNSUPPORTED;
+  if (bn != 256) return DASA_ERR_UNSUPPORTED;
+  return launch_pair<256, 5>(ta, tb, p, epilogue, st);
+}

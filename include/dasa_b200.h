@@ -62,13 +62,16 @@ typedef struct {
   int64_t ld_gate;
   float* gate_out;            /* EPI_GATE: sigmoid(acc+bias) saved here when non-NULL, [M, ld_gate_out] */
   int64_t ld_gate_out;
-  const uint8_t* drop_mask;   /* Debug / experiment switch: route many-wave 128x128 TF32 GEMMs through the cluster-of-2 TMA-multicast variant (each CTA
- * loads half of the shared A tile and multicasts it). Off by default: measured no gain on B200 (see gemm_tc.cu). */
-int dasa_debug_gemm_multicast(int on);
-
-/* optional keep mask [M, N] contiguous, applied to the final value */
+  const uint8_t* drop_mask;   /* optional keep mask [M, N] contiguous, applied to the final value */
   float drop_scale;
 } dasa_epilogue_t;
+
+/* Debug / experiment switch: route many-wave 128x128 TF32 GEMMs through the cluster-of-2 TMA-multicast variant (each CTA
+ * loads half of the shared A tile and multicasts it). Off by default: measured no gain on B200 (see gemm_tc.cu). */
+int dasa_debug_gemm_multicast(int on);
+/* Routing of K-major TF32 GEMMs to the persistent CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles, gemm_tc2.cu):
+ * 0 = never, 1 = when the tile count fills the 74 TPCs (default; also env DASA_TC_PAIR), 2 = always (tests). */
+int dasa_debug_gemm_pair(int mode);
 
 size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
 int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,

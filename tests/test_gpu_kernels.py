@@ -625,6 +625,7 @@ def test_gemm_tf32_multicast_variant():
     outs = []
     for on in (0, 1):
         lib.load().dasa_debug_gemm_multicast(on)
+        lib.load().dasa_debug_gemm_pair(0)
         try:
             C = torch.empty(M, N, device=DEV)
             ops.gemm(Ad, K, 1, Wd, K, 1, C, N, M, N, K, epilogue=ops.EPI_BIAS, bias=bd, precision=ops.PREC_TF32)
@@ -632,6 +633,81 @@ def test_gemm_tf32_multicast_variant():
             ops.gemm(Ad, K, 1, Wd, K, 1, Cg, N, M, N, K, epilogue=ops.EPI_BIAS_GELU, bias=bd, precision=ops.PREC_TF32)
         finally:
             lib.load().dasa_debug_gemm_multicast(0)
+            lib.load().dasa_debug_gemm_pair(1)
         outs.append((C, Cg))
         assert_close(C, ref, 3e-3, "tf32 gemm (multicast=%d)" % on)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 32), (777, 515, 96), (3000, 768, 768), (1000, 132, 40), (20300, 768, 160)])
+def test_gemm_tf32_pair_kernel(shape):
+    """Persistent CTA-pair tcgen05 GEMM (cta_group::2, 256x256 tiles, gemm_tc2.cu) forced on for every shape: all fused
+    epilogues, ragged M / N / K edges, beta accumulation, strided output rows, dropout keep mask; against an fp64 reference
+    (TF32 products: 3e-3 of the output scale) and against the single-CTA tcgen05 kernel."""
+    from dasa_b200 import lib
+    M, N, K = shape
+    gen = g(11)
+    A, W, b = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) * 0.1, torch.randn(N, generator=gen)
+    F = torch.rand(M, N + 8, generator=gen)
+    keep = (torch.rand(M, N, generator=gen) > 0.3).to(torch.uint8)
+    C0 = torch.randn(M, N + 4, generator=gen)
+    Ad, Wd, bd, Fd, kd = A.to(DEV), W.to(DEV), b.to(DEV), F.to(DEV), keep.to(DEV)
+    acc = A.double() @ W.double().t()
+    sig = torch.sigmoid(acc + b.double())
+    cases = [
+        ("none", dict(epilogue=ops.EPI_NONE), acc),
+        ("bias", dict(epilogue=ops.EPI_BIAS, bias=bd), acc + b.double()),
+        ("bias+tanh", dict(epilogue=ops.EPI_BIAS_TANH, bias=bd), torch.tanh(acc + b.double())),
+        ("bias+gelu", dict(epilogue=ops.EPI_BIAS_GELU, bias=bd), torch.nn.functional.gelu(acc + b.double())),
+        ("bias+relu", dict(epilogue=ops.EPI_BIAS_RELU, bias=bd), torch.relu(acc + b.double())),
+        ("tanh", dict(epilogue=ops.EPI_TANH), torch.tanh(acc)),
+        ("bias+drop", dict(epilogue=ops.EPI_BIAS, bias=bd, drop_mask=kd, drop_scale=1 / 0.7), (acc + b.double()) * keep.double() / 0.7),
+    ]
+    L = lib.load()
+    try:
+        for name, kw, ref in cases:
+            outs = []
+            for mode in (0, 2):
+                L.dasa_debug_gemm_pair(mode)
+                C = torch.full((M, N + 4), 7.0, device=DEV)                      # strided rows; the pad columns must stay untouched
+                ops.gemm(Ad, K, 1, Wd, K, 1, C, N + 4, M, N, K, precision=ops.PREC_TF32, **kw)
+                assert float((C[:, N:] - 7.0).abs().max()) == 0.0, name
+                outs.append(C[:, :N])
+            # tanh has slope 1 where TF32 rounding of |acc| ~ 10 lands: the absolute product error passes straight through
+            assert_close(outs[1], ref, 1e-2 if "tanh" in name else 3e-3, "pair kernel, %s" % name)
+            assert_close(outs[1], outs[0], 1e-5, "pair vs single-CTA kernel, %s" % name)
+        # sigmoid gate: out = sigmoid(acc + b) * f (f strided), the gate itself saved on the side
+        L.dasa_debug_gemm_pair(2)
+        C, G = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+        ops.gemm(Ad, K, 1, Wd, K, 1, C, N, M, N, K, precision=ops.PREC_TF32, epilogue=ops.EPI_GATE, bias=bd, gate_src=Fd, ld_gate=N + 8,
+                 gate_out=G, ld_gate_out=N)
+        assert_close(G, sig, 3e-3, "pair kernel, gate")
+        assert_close(C, sig * F[:, :N].double(), 3e-3, "pair kernel, gated output")
+        # alpha / beta accumulation into an existing strided C
+        C = C0.to(DEV).clone()
+        ops.gemm(Ad, K, 1, Wd, K, 1, C, N + 4, M, N, K, alpha=0.5, beta=1.0, precision=ops.PREC_TF32)
+        assert_close(C[:, :N], 0.5 * acc + C0[:, :N].double(), 3e-3, "pair kernel, alpha/beta")
+        assert torch.equal(C[:, N:].cpu(), C0[:, N:])
+    finally:
+        L.dasa_debug_gemm_pair(1)
+
+
+def test_gemm_pair_plan_routes_big_token_major_shapes():
+    """The rollout's many-tile GEMMs run on the pair kernel by default and agree with the single-CTA kernel's TF32 result."""
+    from dasa_b200 import lib
+    L = lib.load()
+    gen = g(12)
+    M, N, K = 9472, 2304, 768                       # 37 x 9 = 333 pair tiles: 4.5 waves of the 74 TPCs
+    A, W, b = torch.randn(M, K, generator=gen).to(DEV), torch.randn(N, K, generator=gen).to(DEV), torch.randn(N, generator=gen).to(DEV)
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.dasa_debug_gemm_pair(mode)
+            n0 = lib.launches
+            C = torch.empty(M, N, device=DEV)
+            ops.gemm(A, K, 1, W, K, 1, C, N, M, N, K, epilogue=ops.EPI_BIAS, bias=b, precision=ops.PREC_TF32)
+            outs.append(C)
+    finally:
+        L.dasa_debug_gemm_pair(1)
+    assert_close(outs[1], outs[0], 1e-5, "default routing vs single-CTA kernel")
+    assert_close(outs[1], A.double().cpu() @ W.double().cpu().t() + b.double().cpu(), 3e-3, "default routing vs fp64")
