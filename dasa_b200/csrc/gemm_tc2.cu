@@ -29,10 +29,26 @@ constexpr int P_EPI_LD = 36;         // staging row stride (floats): conflict-fr
 struct PairParams {
   int M, N, K;
   float alpha, beta;
-  float* C; int64_t ldc;
+  float* C[2]; int64_t ldc;      // one output per group (grouped launches: the two directions of the bi-LSTM recurrence)
   EpiParams ep;
-  int tiles_n, tiles_total, num_pairs;
+  int tiles_n, tiles_mn;         // column tiles / tiles of one (group, K split)
+  int splits, kb_per_split;      // split-K: partial sums go to C[g] + split * split_stride, epilogue NONE
+  int64_t split_stride;
+  int tiles_total, num_pairs;
 };
+
+struct PairTile { int g, ks, mt, nt; };
+__device__ __forceinline__ PairTile pair_decode(const PairParams& p, int w) {
+  PairTile t;
+  const int per_group = p.tiles_mn * p.splits;
+  t.g = w / per_group;
+  int r = w - t.g * per_group;
+  t.ks = r / p.tiles_mn;
+  r -= t.ks * p.tiles_mn;
+  t.mt = r / p.tiles_n;
+  t.nt = r - t.mt * p.tiles_n;
+  return t;
+}
 
 __device__ __forceinline__ void p_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void p_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -86,7 +102,8 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 template <int BN, int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
-gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, PairParams p) {
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, PairParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int A_BYTES = P_BM * P_BK * 4, B_BYTES = (BN / 2) * P_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers of BN fp32 columns
@@ -106,6 +123,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * P_EPI_WARPS); }   // every epilogue warp of both CTAs
     mbar_fence_init();
@@ -125,18 +144,21 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       // -------------------------------------------------------------- TMA producer (both CTAs)
       uint32_t it = 0;
       for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs) {
-        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-        const int m0 = mt * (2 * P_BM) + (int)crank * P_BM;
-        const int nb0 = nt * BN + (int)crank * (BN / 2);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const PairTile t = pair_decode(p, tile);
+        const int m0 = t.mt * (2 * P_BM) + (int)crank * P_BM;
+        const int nb0 = t.nt * BN + (int)crank * (BN / 2);
+        const CUtensorMap* ma = t.g ? &tmA1 : &tmA;
+        const CUtensorMap* mb = t.g ? &tmB1 : &tmB;
+        const int kb0 = t.ks * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // both CTAs' boxes complete on the leader's barrier
           const uint32_t fb = p_mapa(smem_u32(&full_bar[s]), 0);
           unsigned char* dst = tiles + s * STAGE_BYTES;
-          p_tma_load_2sm(dst, &tmA, kb * P_BK, m0, fb);
-          p_tma_load_2sm(dst + A_BYTES, &tmB, kb * P_BK, nb0, fb);
+          p_tma_load_2sm(dst, ma, kb * P_BK, m0, fb);
+          p_tma_load_2sm(dst + A_BYTES, mb, kb * P_BK, nb0, fb);
         }
       }
       // drain: every multicast commit aimed at this CTA's `empty` barriers has landed before the CTA may exit
@@ -155,7 +177,9 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(&tmem_empty[a], aph ^ 1);               // both CTAs' epilogues have drained this accumulator buffer
         p_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const PairTile t = pair_decode(p, tile);
+        const int kb0 = t.ks * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -165,7 +189,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint64_t db = p_desc_sw128(src + A_BYTES);
 #pragma unroll
           for (int k = 0; k < P_BK / 8; ++k)
-            p_umma_tf32_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            p_umma_tf32_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           p_commit_pair(&empty_bar[s]);                    // stage free in both CTAs once these MMAs retire
         }
         p_commit_pair(&tmem_full[a]);                      // accumulator complete: visible to both CTAs' epilogues
@@ -179,15 +203,17 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     float* stg = stage_all + (warp - 2) * 32 * P_EPI_LD;
     const int col4 = lane & 7, rsub = lane >> 3;           // read-back: 8 lanes x float4 per row, 4 rows per instruction
     const float alpha = p.alpha, beta = p.beta;
-    const bool c_vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool c_vec = ((p.ldc & 3) == 0) && (((reinterpret_cast<uintptr_t>(p.C[0]) | reinterpret_cast<uintptr_t>(p.C[1])) & 15) == 0) &&
+                       ((p.split_stride & 3) == 0);
     const bool plain = c_vec && beta == 0.f && alpha == 1.f;
     const uint32_t empty_remote0 = p_mapa(smem_u32(&tmem_empty[0]), 0);
     const uint32_t empty_remote1 = p_mapa(smem_u32(&tmem_empty[1]), 0);
     uint32_t tcount = 0;
     for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs, ++tcount) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-      const int m_base = mt * (2 * P_BM) + (int)crank * P_BM + q * 32;
-      const int n_base = nt * BN + chalf * CW;
+      const PairTile t = pair_decode(p, tile);
+      const int m_base = t.mt * (2 * P_BM) + (int)crank * P_BM + q * 32;
+      const int n_base = t.nt * BN + chalf * CW;
+      float* const Cg = p.C[t.g] + (int64_t)t.ks * p.split_stride;
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&tmem_full[a], aph);
       p_fence_after();
@@ -224,7 +250,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = apply_activation_t<EPI>(v[e] + bias4[e], m, n + e, p.N, p.ep);
-            *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(Cg + (int64_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
           }
         } else if (n < p.N) {
           const bool vec_ok = c_vec && (n + 3 < p.N);
@@ -241,7 +267,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (m >= p.M) continue;
             const float4 a4 = *reinterpret_cast<const float4*>(stg + (rr + rsub) * P_EPI_LD + 4 * col4);
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
-            float* crow = p.C + (int64_t)m * p.ldc + n;
+            float* crow = Cg + (int64_t)m * p.ldc + n;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               if (n + e < p.N) {
@@ -284,7 +310,7 @@ bool pair_make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K,
 }
 
 template <int BN, int STAGES, int EPI>
-int launch_pair_e(const CUtensorMap& ta, const CUtensorMap& tb, const PairParams& p, cudaStream_t st) {
+int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + P_EPI_WARPS * 32 * P_EPI_LD * 4 + 256 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
   auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI>;
@@ -294,12 +320,12 @@ int launch_pair_e(const CUtensorMap& ta, const CUtensorMap& tb, const PairParams
     if (e != cudaSuccess) { dasa_set_error("gemm_tf32_pair attr", e); return DASA_ERR_CUDA; }
     attr_set = true;
   }
-  kern<<<dim3(2u * (unsigned)p.num_pairs), P_THREADS, smem, st>>>(ta, tb, p);     // __cluster_dims__(2,1,1): one pair per TPC
+  kern<<<dim3(2u * (unsigned)p.num_pairs), P_THREADS, smem, st>>>(ta[0], tb[0], ta[1], tb[1], p);     // __cluster_dims__(2,1,1): one pair per TPC
   return dasa_check_launch("gemm_tf32_pair_kernel");
 }
 
 template <int BN, int STAGES>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const PairParams& p, int epilogue, cudaStream_t st) {
+int launch_pair(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, int epilogue, cudaStream_t st) {
   switch (epilogue) {
     case DASA_EPI_BIAS: return launch_pair_e<BN, STAGES, DASA_EPI_BIAS>(ta, tb, p, st);
     case DASA_EPI_BIAS_TANH: return launch_pair_e<BN, STAGES, DASA_EPI_BIAS_TANH>(ta, tb, p, st);
@@ -330,20 +356,48 @@ int dasa_gemm_pair_plan(int M, int N, int K) {
   // leave most of the last wave idle, stay on the single-CTA kernel (which can split K).
   const int pairs = DASA_NUM_SMS / 2;
   const int64_t t = dasa_cdiv(M, 2 * P_BM) * dasa_cdiv(N, 256);
-  if (t < pairs) return 0;
+  if (t < pairs) return (2 * t >= pairs && K >= 2048) ? 256 : 0;     // long-K weight-gradient shapes: one partial wave still wins
   const double eff = (double)t / (double)(dasa_cdiv(t, pairs) * pairs);
   return eff >= 0.6 ? 256 : 0;
 }
 
 int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                       float* C, int64_t ldc, int epilogue, const EpiParams& ep, cudaStream_t st) {
-  PairParams p{};
-  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.ep = ep;
-  p.tiles_n = (int)dasa_cdiv(N, bn);
-  p.tiles_total = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
-  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
-  CUtensorMap ta, tb;
-  if (!pair_make_map(&ta, A, M, K, lda, P_BM) || !pair_make_map(&tb, B, N, K, ldb, bn / 2)) return DASA_ERR_UNSUPPORTED;
   if (bn != 256) return DASA_ERR_UNSUPPORTED;
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C[0] = C; p.C[1] = C; p.ldc = ldc; p.ep = ep;
+  p.tiles_n = (int)dasa_cdiv(N, bn);
+  p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  p.splits = 1; p.kb_per_split = (int)dasa_cdiv(K, P_BK); p.split_stride = 0;
+  p.tiles_total = p.tiles_mn;
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta[2], tb[2];
+  if (!pair_make_map(&ta[0], A, M, K, lda, P_BM) || !pair_make_map(&tb[0], B, N, K, ldb, bn / 2)) return DASA_ERR_UNSUPPORTED;
+  ta[1] = ta[0]; tb[1] = tb[0];
   return launch_pair<256, 5>(ta, tb, p, epilogue, st);
+}
+
+// Two independent problems of the same shape in ONE launch, optionally split along K (raw partial sums, no epilogue):
+//   P[g][s] (M x N, row stride ldc, at C[g] + s * split_stride) = A[g][:, Ks] * B[g][:, Ks]^T.
+// The recurrent GEMMs of the two bi-LSTM directions are issued this way, so one time step is one launch that fills the TPCs.
+int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
+                              float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K < P_BK || splits < 1) return DASA_ERR_BAD_SHAPE;
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.C[0] = C[0]; p.C[1] = C[1]; p.ldc = ldc;
+  p.tiles_n = (int)dasa_cdiv(N, 256);
+  p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  const int nkb = (int)dasa_cdiv(K, P_BK);
+  if (splits > nkb) splits = nkb;
+  p.kb_per_split = (int)dasa_cdiv(nkb, splits);
+  p.splits = (int)dasa_cdiv(nkb, p.kb_per_split);          // every split owns at least one k-block
+  p.split_stride = split_stride;
+  p.tiles_total = 2 * p.tiles_mn * p.splits;
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta[2], tb[2];
+  for (int g = 0; g < 2; ++g) {
+    if (!dasa_aligned16(A[g]) || !dasa_aligned16(B[g]) || (lda & 3) || (ldb & 3)) return DASA_ERR_BAD_ALIGN;
+    if (!pair_make_map(&ta[g], A[g], M, K, lda, P_BM) || !pair_make_map(&tb[g], B[g], N, K, ldb, 128)) return DASA_ERR_UNSUPPORTED;
+  }
+  return launch_pair_e<256, 5, DASA_EPI_NONE>(ta, tb, p, st) == DASA_OK ? p.splits : DASA_ERR_CUDA;
 }

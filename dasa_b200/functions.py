@@ -290,14 +290,21 @@ class BiLSTMFn(torch.autograd.Function):
         acts = torch.empty(2, L, B, 4 * H, device=dev, dtype=torch.float32)
         params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
         fused = B <= ops.lib.load().dasa_bilstm_max_batch() and H % 64 == 0
-        if fused:
+        # large batches on the tensor-core precision: grouped CTA-pair GEMM of both directions + one pointwise launch per step
+        paired = (not fused) and ops._precision == ops.PREC_TF32 and H % 32 == 0
+        if fused or paired:
             xp = [ops.linear_fwd(x, w_ih) for (w_ih, _, _, _) in params]       # [B, L, 4H] all time steps at once
             P2 = ops.lib.P * 2
             a = ops.lib.BiLstmFwd(P2(xp[0].data_ptr(), xp[1].data_ptr()), P2(w_hh_f.data_ptr(), w_hh_r.data_ptr()),
                                   P2(b_ih_f.data_ptr(), b_ih_r.data_ptr()), P2(b_hh_f.data_ptr(), b_hh_r.data_ptr()),
                                   P2(hs[0].data_ptr(), hs[1].data_ptr()), P2(cs[0].data_ptr(), cs[1].data_ptr()),
                                   P2(acts[0].data_ptr(), acts[1].data_ptr()), out.data_ptr(), lengths.data_ptr(), B, L, H)
-            ops.call("dasa_bilstm_seq_fwd", ops.ctypes.byref(a), ops._precision, ops._stream())
+            if fused:
+                ops.call("dasa_bilstm_seq_fwd", ops.ctypes.byref(a), ops._precision, ops._stream())
+            else:
+                nb = ops.lib.load().dasa_bilstm_seq_gemm_workspace(B, H, 0)
+                ws = ops.workspace(nb)
+                ops.call("dasa_bilstm_seq_gemm_fwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         else:
             gh = torch.empty(B, 4 * H, device=dev, dtype=torch.float32)
             for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
@@ -310,6 +317,7 @@ class BiLSTMFn(torch.autograd.Function):
         h_fin = torch.stack((hs[0, L], hs[1, L]))
         c_fin = torch.stack((cs[0, L], cs[1, L]))
         ctx.fused = fused
+        ctx.paired = paired
         ctx.save_for_backward(x, lengths, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hs, cs, acts)
         return out, h_fin, c_fin
 
@@ -324,7 +332,7 @@ class BiLSTMFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dx = torch.zeros(B, L, In, device=dev, dtype=torch.float32) if need_dx else None
         dgates_all = torch.empty(2, L, B, 4 * H, device=dev, dtype=torch.float32)     # indexed by step s
-        if ctx.fused:
+        if ctx.fused or ctx.paired:
             dhf = dh_fin.contiguous() if dh_fin is not None else None
             dcf = dc_fin.contiguous() if dc_fin is not None else None
             wt = (_transposed(w_hh_f), _transposed(w_hh_r))
@@ -338,11 +346,16 @@ class BiLSTMFn(torch.autograd.Function):
                                   P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates_all[0].data_ptr(), dgates_all[1].data_ptr()),
                                   P2(work[0, 0].data_ptr(), work[0, 1].data_ptr()),
                                   P2(work[1, 0].data_ptr(), work[1, 1].data_ptr()), lengths.data_ptr(), B, L, H)
-            ops.call("dasa_bilstm_seq_bwd", ops.ctypes.byref(a), ops._precision, ops._stream())
+            if ctx.fused:
+                ops.call("dasa_bilstm_seq_bwd", ops.ctypes.byref(a), ops._precision, ops._stream())
+            else:
+                nb = ops.lib.load().dasa_bilstm_seq_gemm_workspace(B, H, 1)
+                ws = ops.workspace(nb)
+                ops.call("dasa_bilstm_seq_gemm_bwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
             dgates = dgates_all[d]
             order = list(range(L)) if d == 0 else list(range(L - 1, -1, -1))
-            if not ctx.fused:
+            if not (ctx.fused or ctx.paired):
                 dh = dh_fin[d].contiguous() if dh_fin is not None else torch.zeros(B, H, device=dev)
                 dc = dc_fin[d].contiguous() if dc_fin is not None else torch.zeros(B, H, device=dev)
                 dh_rec = torch.empty(B, H, device=dev, dtype=torch.float32)

@@ -183,6 +183,13 @@ int dasa_bilstm_max_batch(void);
 /* precision: DASA_PREC_FP32 = FFMA kernels (exact fp32); DASA_PREC_TF32 = mma.sync TF32 tensor-core kernels (H % 128 == 0) */
 int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* args, int precision, void* stream);
 int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, int precision, void* stream);
+/* Large-batch form of the same recurrence (the batched teacher-forced schedule runs all T x B instruction copies at once):
+ * per time step ONE grouped launch of the persistent CTA-pair tcgen05 GEMM for both directions (TF32 products) + ONE pointwise
+ * launch; backward splits K three ways and the next step's pointwise kernel sums the partials (deterministic order).
+ * Same argument structs; w_hh_t[d] = W_hh[d]^T as [H, 4H] rows. workspace: dasa_bilstm_seq_gemm_workspace(B, H, backward) bytes. */
+size_t dasa_bilstm_seq_gemm_workspace(int B, int H, int backward);
+int dasa_bilstm_seq_gemm_fwd(const dasa_bilstm_fwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
+int dasa_bilstm_seq_gemm_bwd(const dasa_bilstm_bwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------- encoder pieces (a9)
  * BertEmbeddings (vilmodel.py:161-176): out[b,l,:] = LN(word[ids[b,l]] + pos[l] + type[0]) (* mask*scale).          */
