@@ -454,10 +454,11 @@ def run_ours(args):
 
 
 def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
-    """Event-time every dasa_gemm launch of one training rollout. The dominant kernel of the step is the tcgen05 TF32 GEMM
-    (gemm_tf32_kernel<128,..>) on the token-major shapes of the transformer stack / bi-LSTM input projections (M >= 2048 rows;
-    ~45 % of the step in profiles/r01_ncu_launches_step_summary.txt): its tensor roofline = algorithmic FLOPs / summed duration.
-    The M = batch (20-row) decoder GEMMs stream their weights once per action and are reported against the HBM roofline."""
+    """Event-time every dasa_gemm launch of one training rollout. The dominant kernel of the step is the persistent CTA-pair
+    tcgen05 TF32 GEMM (gemm_tf32_pair_kernel<256,5,*>, gemm_tc2.cu) on the token-major shapes of the transformer stack, the AdaIN
+    gate and the bi-LSTM input projections (M >= 2048 rows; ~40 % of the step in profiles/r01_ncu_launches_step3_summary.txt):
+    its tensor roofline = algorithmic FLOPs (2*M*N*K per launch) / summed duration. The M = batch (20-row) decoder GEMMs stream
+    their weights once per action and are reported against the HBM roofline."""
     from dasa_b200 import lib, modules as M
     events = []
     orig = lib.call
@@ -492,12 +493,12 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     s_secs = sum(t for t, _, _, _ in small)
     s_bytes = sum(4.0 * (n * k + m * k + m * n) for _, m, n, k in small)
-    return {"bound": "tensor", "kernel": "gemm_tf32_kernel<128,3,*> (tcgen05.mma kind::tf32, TMA 128B-swizzle operands, TMEM accumulator), "
-                                         "token-major GEMMs with M >= 2048", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak,
-            # ncu --set full, one launch M=20300 N=3072 K=768 GELU epilogue (profiles/r01_gemm_tf32_big_ncu_full.txt):
+    return {"bound": "tensor", "kernel": "gemm_tf32_pair_kernel<256,5,*> (persistent CTA pair, tcgen05.mma cta_group::2 kind::tf32 256x256x8, "
+                                         "TMA 128B-swizzle operands, double-buffered TMEM accumulator), token-major GEMMs with M >= 2048",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            # ncu --set full, one launch M=20300 N=3072 K=768 GELU epilogue (profiles/r01_gemm_tf32_pair_ncu_full.txt):
             # dram__bytes_read.sum + dram__bytes_write.sum; algorithmic bytes of that launch = 4*(M*K + N*K + M*N) = 321e6
-            "traffic": 267.7e6, "traffic_launch": "M=20300 N=3072 K=768 (algorithmic 321e6 B, 95.7 GFLOP)",
+            "traffic": 267.2e6, "traffic_launch": "M=20300 N=3072 K=768 (algorithmic 321e6 B, 95.8 GFLOP)",
             "launches_timed": len(big), "device_seconds": secs,
             "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src,
             "small_m_gemms": {"bound": "hbm", "what": "decoder / critic GEMMs with M = batch rows: weights streamed once per action",
