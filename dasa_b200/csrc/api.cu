@@ -42,6 +42,8 @@ extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float 
   if (epilogue == DASA_EPI_GATE && (epi == nullptr || epi->gate_src == nullptr)) return DASA_ERR_BAD_SHAPE;
   const EpiParams ep = make_epi(epi);
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DASA_PREC_TF32 && dasa_gemm_skinny_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb))
+    return dasa_gemm_skinny(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, st);
   if (precision == DASA_PREC_TF32 && dasa_gemm_tc_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc))
     return dasa_gemm_tc(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
                         workspace_bytes, st);

@@ -72,6 +72,10 @@ int dasa_debug_gemm_multicast(int on);
 /* Routing of K-major TF32 GEMMs to the persistent CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles, gemm_tc2.cu):
  * 0 = never, 1 = when the tile count fills the 74 TPCs (default; also env DASA_TC_PAIR), 2 = always (tests). */
 int dasa_debug_gemm_pair(int mode);
+/* Routing of K-major TF32 GEMMs with M <= 32 rows (the decoder's per-action projections) to the weight-streaming mma.sync kernel
+ * (gemm_skinny.cu: K slices reduced through shared memory and a thread-block cluster's DSMEM): 0 = off, 1 = on for the shapes where it wins (default; env
+ * DASA_SKINNY), 2 = every eligible shape (tests). */
+int dasa_debug_gemm_skinny(int on);
 
 size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
 int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,

@@ -713,3 +713,44 @@ def test_gemm_pair_plan_routes_big_token_major_shapes():
         L.dasa_debug_gemm_pair(1)
     assert_close(outs[1], outs[0], 1e-5, "default routing vs single-CTA kernel")
     assert_close(outs[1], A.double().cpu() @ W.double().cpu().t() + b.double().cpu(), 3e-3, "default routing vs fp64")
+
+
+@pytest.mark.parametrize("shape", [(20, 4096, 2240), (20, 1024, 4096), (20, 2176, 1024), (1, 64, 128), (32, 48, 64), (7, 2240, 4096),
+                                   (20, 1000, 96), (13, 16, 32)])
+def test_gemm_skinny_kernel(shape):
+    """Weight-streaming mma.sync TF32 kernel for M <= 32 rows (the decoder's per-action projections): K slices reduced through
+    shared memory and the cluster's DSMEM. Against fp64 (TF32 products: 3e-3 of the output scale) for every epilogue it serves,
+    beta accumulation and strided rows, forced on for every shape; bit-reproducible."""
+    from dasa_b200 import lib
+    M, N, K = shape
+    gen = g(21)
+    A, W, b = torch.randn(M, K + 4, generator=gen), torch.randn(N, K, generator=gen) * 0.1, torch.randn(N, generator=gen)
+    C0 = torch.randn(M, N + 4, generator=gen)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), b.to(DEV)
+    acc = A[:, :K].double() @ W.double().t()
+    L = lib.load()
+    cases = [("none", dict(epilogue=ops.EPI_NONE), acc), ("bias", dict(epilogue=ops.EPI_BIAS, bias=bd), acc + b.double()),
+             ("bias+tanh", dict(epilogue=ops.EPI_BIAS_TANH, bias=bd), torch.tanh(acc + b.double())),
+             ("tanh", dict(epilogue=ops.EPI_TANH), torch.tanh(acc)),
+             ("bias+relu", dict(epilogue=ops.EPI_BIAS_RELU, bias=bd), torch.relu(acc + b.double()))]
+    try:
+        for name, kw, ref in cases:
+            outs = []
+            for mode in (2, 0):
+                L.dasa_debug_gemm_skinny(mode)
+                C = torch.full((M, N + 4), 7.0, device=DEV)
+                ops.gemm(Ad, K + 4, 1, Wd, K, 1, C, N + 4, M, N, K, precision=ops.PREC_TF32, **kw)
+                assert float((C[:, N:] - 7.0).abs().max()) == 0.0, name
+                outs.append(C[:, :N])
+            assert_close(outs[0], ref, 1e-2 if "tanh" in name else 3e-3, "skinny kernel, %s" % name)
+            assert_close(outs[0], outs[1], 3e-3, "skinny vs tile kernel, %s" % name)
+        L.dasa_debug_gemm_skinny(2)
+        C = C0.to(DEV).clone()
+        ops.gemm(Ad, K + 4, 1, Wd, K, 1, C, N + 4, M, N, K, alpha=0.5, beta=1.0, precision=ops.PREC_TF32)
+        assert_close(C[:, :N], 0.5 * acc + C0[:, :N].double(), 3e-3, "skinny kernel, alpha/beta")
+        assert torch.equal(C[:, N:].cpu(), C0[:, N:])
+        C2 = C0.to(DEV).clone()
+        ops.gemm(Ad, K + 4, 1, Wd, K, 1, C2, N + 4, M, N, K, alpha=0.5, beta=1.0, precision=ops.PREC_TF32)
+        assert torch.equal(C, C2), "skinny kernel must be deterministic"
+    finally:
+        L.dasa_debug_gemm_skinny(1)
