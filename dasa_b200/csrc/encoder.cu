@@ -501,6 +501,194 @@ __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
   }
 }
 
+// dh == 64 variant with only K and V in shared memory. Q never touches shared memory: a lane loads the float4s of its two
+// query rows straight from global memory and uses component j in MMA step j (any bijection of the reduction index is a valid
+// dot product as long as both operands use it: "MMA k index t / t+4 of step j" = head-dim 32c + 4t + j / 32c + 16 + 4t + j).
+// The softmax probabilities never touch shared memory either: the score accumulator fragment (row g, keys 2t, 2t+1) is reused
+// directly as the A fragment of P.V by reading V rows 2t / 2t+1 for MMA k indices t / t+4. Shared memory per CTA drops from
+// 93 KB to 47 KB at 80 keys (23 KB at 36 views): 4-9 CTAs per SM instead of 2, which is what this latency-bound kernel needs.
+constexpr int MHA2_KS = 80;          // K row stride (floats): == 16 mod 32 -> conflict-free 128-bit fragment loads
+constexpr int MHA2_VS = 68;          // V row stride: 2*VS == 8 mod 32 -> rows 2t (t = 0..3) land in distinct bank groups
+
+template <int NT>
+__global__ void __launch_bounds__(MHA_TC_THREADS, 4) mha_fwd_tc64_kernel(MhaArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int dh = 64;
+  const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
+  const int Lq = a.q_len ? a.q_len[b] : a.Lq, Lk = a.k_len ? a.k_len[b] : a.Lk;
+  if (Lq <= 0) return;
+  const int LkP = (Lk + 7) & ~7, LkM = (a.Lk + 7) & ~7;
+  uint32_t* Ks = reinterpret_cast<uint32_t*>(smem);          // [LkP][KS] tf32 bit patterns
+  uint32_t* Vs = Ks + LkM * MHA2_KS;                         // [LkP][VS]
+  const float* qb = a.q + (a.q_off ? (int64_t)a.q_off[b] * a.ldq : (int64_t)b * a.sq) + h * dh;
+  const float* kb = a.k + (a.k_off ? (int64_t)a.k_off[b] * a.ldk : (int64_t)b * a.sk) + h * dh;
+  const float* vb = a.v + (a.k_off ? (int64_t)a.k_off[b] * a.ldv : (int64_t)b * a.sv) + h * dh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nwarps = blockDim.x >> 5;
+  // the first query tile of this warp is requested BEFORE the K / V staging so that all three streams are in flight together
+  float4 qf[2][2][2];                                        // [row r0 / r1][32-wide chunk][k half]
+  auto load_q = [&](int mt) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int col = 32 * c + 16 * hf + 4 * t;
+        qf[0][c][hf] = (r0 < Lq) ? ldg_stream4(qb + (int64_t)r0 * a.ldq + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qf[1][c][hf] = (r1 < Lq) ? ldg_stream4(qb + (int64_t)r1 * a.ldq + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+  // keep bits of the probability dropout mask for this lane's (row, key) pairs: bit 4*nt + 2*e + row. Requested together with Q,
+  // i.e. before the K / V staging barrier, so their latency is off the softmax -> P.V critical path.
+  const int nkt_early = LkP >> 3;
+  uint64_t keep = ~0ull;
+  auto load_mask = [&](int mt) {
+    keep = ~0ull;
+    if (a.drop_mask == nullptr) return;
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const uint8_t* m0 = a.drop_mask + (((int64_t)b * a.heads + h) * a.Lq + r0) * a.Lk;
+    const uint8_t* m1 = m0 + (int64_t)8 * a.Lk;
+    uint64_t bits = 0;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < nkt_early) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          const bool in = j < Lk;
+          const uint64_t k0 = (in && r0 < Lq) ? (m0[j] != 0) : 1;
+          const uint64_t k1 = (in && r1 < Lq) ? (m1[j] != 0) : 1;
+          bits |= (k0 << (4 * nt + 2 * e)) | (k1 << (4 * nt + 2 * e + 1));
+        }
+      }
+    }
+    keep = bits;
+  };
+  if (warp * 16 < Lq) { load_q(warp); load_mask(warp); }
+  const int nit = (LkP * 16 + blockDim.x - 1) / blockDim.x;
+#pragma unroll 4
+  for (int it = 0; it < nit; ++it) {
+    const int i = threadIdx.x + it * blockDim.x;
+    const int r = i >> 4, c = i & 15;
+    if (r < LkP) {
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (r < Lk) {
+        kv = ldg_stream4(kb + (int64_t)r * a.ldk + 4 * c);
+        vv = ldg_stream4(vb + (int64_t)r * a.ldv + 4 * c);
+      }
+      *reinterpret_cast<uint4*>(Ks + r * MHA2_KS + 4 * c) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
+      *reinterpret_cast<uint4*>(Vs + r * MHA2_VS + 4 * c) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+    }
+  }
+  __syncthreads();
+  const int nkt = LkP >> 3;
+  const float scale = 0.125f;                                // 1 / sqrt(64)
+  const uint8_t* pad = a.key_pad ? a.key_pad + (int64_t)b * a.ld_pad : nullptr;
+  for (int mt = warp; mt * 16 < Lq; mt += nwarps) {
+    if (mt != warp) { load_q(mt); load_mask(mt); }
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t qa[4][4];                                     // [step j][a0..a3]
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        qa[j][0] = f2tf32(reinterpret_cast<const float*>(&qf[0][c][0])[j]);
+        qa[j][1] = f2tf32(reinterpret_cast<const float*>(&qf[1][c][0])[j]);
+        qa[j][2] = f2tf32(reinterpret_cast<const float*>(&qf[0][c][1])[j]);
+        qa[j][3] = f2tf32(reinterpret_cast<const float*>(&qf[1][c][1])[j]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt < nkt) {
+          const uint32_t* krow = Ks + (nt * 8 + g) * MHA2_KS + 32 * c + 4 * t;
+          const uint4 k0 = *reinterpret_cast<const uint4*>(krow);
+          const uint4 k1 = *reinterpret_cast<const uint4*>(krow + 16);
+          mma_m16n8k8_tf32(acc[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], k0.x, k1.x);
+          mma_m16n8k8_tf32(acc[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], k0.y, k1.y);
+          mma_m16n8k8_tf32(acc[nt], qa[2][0], qa[2][1], qa[2][2], qa[2][3], k0.z, k1.z);
+          mma_m16n8k8_tf32(acc[nt], qa[3][0], qa[3][1], qa[3][2], qa[3][3], k0.w, k1.w);
+        }
+      }
+    }
+    // scores -> masked softmax per row; a row lives in the 4 lanes sharing g (cols 2t, 2t+1 of every key tile)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < nkt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          float add = 0.f;
+          const bool ok = j < Lk;
+          if (ok && pad != nullptr && pad[j]) add = -10000.0f;
+          acc[nt][e] = ok ? acc[nt][e] * scale + add : -INFINITY;
+          acc[nt][2 + e] = ok ? acc[nt][2 + e] * scale + add : -INFINITY;
+          mx0 = fmaxf(mx0, acc[nt][e]);
+          mx1 = fmaxf(mx1, acc[nt][2 + e]);
+        }
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < nkt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          acc[nt][e] = (acc[nt][e] == -INFINITY) ? 0.f : __expf(acc[nt][e] - mx0);
+          acc[nt][2 + e] = (acc[nt][2 + e] == -INFINITY) ? 0.f : __expf(acc[nt][2 + e] - mx1);
+          s0 += acc[nt][e];
+          s1 += acc[nt][2 + e];
+        }
+      }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float inv0 = 1.f / s0, inv1 = 1.f / s1;
+    const int64_t pb0 = (((int64_t)b * a.heads + h) * a.Lq + r0) * a.Lk, pb1 = (((int64_t)b * a.heads + h) * a.Lq + r1) * a.Lk;
+    float o[8][4];
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) { o[n8][0] = o[n8][1] = o[n8][2] = o[n8][3] = 0.f; }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < nkt) {
+        uint32_t pa[4];                                      // A fragment of P.V: k index t <-> key 2t, k index t+4 <-> key 2t+1
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          float p0 = acc[nt][e] * inv0, p1 = acc[nt][2 + e] * inv1;
+          if (j < Lk) {
+            if (r0 < Lq) {
+              if (a.probs_out != nullptr) a.probs_out[pb0 + j] = p0;
+              if (a.drop_mask != nullptr) p0 *= ((keep >> (4 * nt + 2 * e)) & 1) ? a.drop_scale : 0.f;
+            }
+            if (r1 < Lq) {
+              if (a.probs_out != nullptr) a.probs_out[pb1 + j] = p1;
+              if (a.drop_mask != nullptr) p1 *= ((keep >> (4 * nt + 2 * e + 1)) & 1) ? a.drop_scale : 0.f;
+            }
+          } else { p0 = 0.f; p1 = 0.f; }
+          pa[2 * e] = f2tf32(p0);                            // e = 0 -> a0 (row g, k t);   e = 1 -> a2 (row g, k t+4)
+          pa[2 * e + 1] = f2tf32(p1);                        // e = 0 -> a1 (row g+8, k t); e = 1 -> a3 (row g+8, k t+4)
+        }
+        const uint32_t* v0 = Vs + (nt * 8 + 2 * t) * MHA2_VS + g;
+#pragma unroll
+        for (int n8 = 0; n8 < 8; ++n8) mma_m16n8k8_tf32(o[n8], pa[0], pa[1], pa[2], pa[3], v0[n8 * 8], v0[MHA2_VS + n8 * 8]);
+      }
+    }
+    float* ob = a.out + (a.q_off ? (int64_t)a.q_off[b] * a.ldo : (int64_t)b * a.so) + h * dh;
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      const int d = n8 * 8 + 2 * t;
+      if (r0 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r0 * a.ldo + d) = make_float2(o[n8][0], o[n8][1]);
+      if (r1 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r1 * a.ldo + d) = make_float2(o[n8][2], o[n8][3]);
+    }
+  }
+}
+
 struct MhaBwdArgs {
   const float *q, *k, *v; int64_t ldq, sq, ldk, sk, ldv, sv;
   const float* probs; const uint8_t* drop_mask; float drop_scale;
@@ -686,6 +874,17 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
       dasa_aligned16(k) && dasa_aligned16(v) && !(ldq % 4 || ldk % 4 || ldv % 4 || sq % 4 || sk % 4 || sv % 4) &&
       dasa_aligned16(out) && !(ldo % 2 || so % 2)) {
     const int LqP = (Lq + 15) & ~15, LkP = (Lk + 7) & ~7;
+    if (dh == 64) {                                            // K / V only in shared memory, Q and P in registers
+      const size_t smem64 = sizeof(float) * (size_t)LkP * (MHA2_KS + MHA2_VS);
+      auto kern = (LkP <= 48) ? mha_fwd_tc64_kernel<6> : mha_fwd_tc64_kernel<MHA_TC_MAXNT>;
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
+      if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc64 attr", e2); return DASA_ERR_CUDA; }
+      MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
+                 q_off, q_len, k_off, k_len};
+      const int warps = (LqP / 16) < 4 ? (LqP / 16) : 4;
+      kern<<<(unsigned)(B * heads), 32 * warps, smem64, (cudaStream_t)stream>>>(at);
+      return dasa_check_launch("mha_fwd_tc64_kernel");
+    }
     const size_t smem_tc = sizeof(float) * ((size_t)LqP * (dh + 4) + (size_t)LkP * (dh + 4) + (size_t)LkP * (dh + 8) +
                                             (size_t)LqP * mha_tc_pstride(LkP));
     if (smem_tc <= 227 * 1024) {
