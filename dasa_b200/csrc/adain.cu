@@ -130,6 +130,38 @@ __global__ void __launch_bounds__(256) channel_modulate_kernel(const float* __re
   }
 }
 
+// backward of out = a[n,c] * f[n,v,c] + b[n,c]: da = sum_v dout*f, db = sum_v dout, df = a*dout (optional). One pass over
+// dout and f: a thread owns 4 channels of one sample and walks the V view rows (coalesced 128-bit rows across the warp).
+__global__ void __launch_bounds__(128) channel_modulate_bwd_kernel(const float* __restrict__ dout, int64_t ldo_row,
+                                                                   int64_t ldo_sample, const float* __restrict__ f,
+                                                                   int64_t ldf_row, int64_t ldf_sample,
+                                                                   const float* __restrict__ a, float* __restrict__ da,
+                                                                   float* __restrict__ db, float* __restrict__ df,
+                                                                   int64_t lddf_row, int64_t lddf_sample, int N, int V, int C) {
+  const int c4 = C >> 2;
+  const int64_t total = (int64_t)N * c4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / c4), c = (int)(i % c4) << 2;
+    const float* po = dout + (int64_t)n * ldo_sample + c;
+    const float* pf = f + (int64_t)n * ldf_sample + c;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (df != nullptr) av = __ldg(reinterpret_cast<const float4*>(a + (int64_t)n * C + c));
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+#pragma unroll 6
+    for (int v = 0; v < V; ++v) {
+      const float4 g = ldg_stream4(po + (int64_t)v * ldo_row);
+      const float4 x = ldg_stream4(pf + (int64_t)v * ldf_row);
+      sa.x = fmaf(g.x, x.x, sa.x); sa.y = fmaf(g.y, x.y, sa.y); sa.z = fmaf(g.z, x.z, sa.z); sa.w = fmaf(g.w, x.w, sa.w);
+      sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+      if (df != nullptr)
+        stg_stream4(df + (int64_t)n * lddf_sample + (int64_t)v * lddf_row + c,
+                    make_float4(av.x * g.x, av.y * g.y, av.z * g.z, av.w * g.w));
+    }
+    *reinterpret_cast<float4*>(da + (int64_t)n * C + c) = sa;
+    if (db != nullptr) *reinterpret_cast<float4*>(db + (int64_t)n * C + c) = sb;
+  }
+}
+
 // adaptive_instance_normalization: one CTA (128 threads) per (sample, view) row; the content row lives in registers,
 // the style row only feeds the two reductions. Two-pass variance (mean first) like torch.var.
 template <int VPT>
@@ -242,6 +274,20 @@ extern "C" int dasa_channel_modulate(const float* f, int64_t ldf_row, int64_t ld
   channel_modulate_kernel<<<stream_grid((int64_t)N * V * C / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       f, ldf_row, ldf_sample, a, b, out, ldo_row, ldo_sample, N, V, C);
   return dasa_check_launch("channel_modulate_kernel");
+}
+
+extern "C" int dasa_channel_modulate_bwd(const float* dout, int64_t ldo_row, int64_t ldo_sample, const float* f, int64_t ldf_row,
+                                         int64_t ldf_sample, const float* a, float* da, float* db, float* df, int64_t lddf_row,
+                                         int64_t lddf_sample, int N, int V, int C, void* stream) {
+  if (N <= 0) return DASA_OK;
+  if (C % 4 != 0 || V <= 0) return DASA_ERR_BAD_SHAPE;
+  if (!vec_ok(dout, ldo_row) || ldo_sample % 4 != 0 || !vec_ok(f, ldf_row) || ldf_sample % 4 != 0 || !dasa_aligned16(da) ||
+      (db != nullptr && !dasa_aligned16(db)) ||
+      (df != nullptr && (!vec_ok(df, lddf_row) || lddf_sample % 4 != 0 || a == nullptr || !dasa_aligned16(a))))
+    return DASA_ERR_BAD_ALIGN;
+  channel_modulate_bwd_kernel<<<stream_grid((int64_t)N * C / 4, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+      dout, ldo_row, ldo_sample, f, ldf_row, ldf_sample, a, da, db, df, lddf_row, lddf_sample, N, V, C);
+  return dasa_check_launch("channel_modulate_bwd_kernel");
 }
 
 extern "C" int dasa_adain_rows(const float* f, int64_t ldf, const float* d, int64_t ldd, float* out, int64_t ldo, int R,

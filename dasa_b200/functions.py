@@ -138,6 +138,24 @@ class AdaINGateFn(torch.autograd.Function):
         return None, None, None, None, None, None, None
 
 
+class ChannelModulateFn(torch.autograd.Function):
+    """DGAdaStatChannel / DGAdaMeanChannel modulation out = a[:, None, :] * f + b[:, None, :] (agent_dg.py:1636, 1661);
+    backward = one pass over (dout, f): da, db per (sample, channel), df only when f requires grad (env data does not)."""
+
+    @staticmethod
+    def forward(ctx, f, a, b):
+        ctx.save_for_backward(f, a)
+        return ops.channel_modulate(f, a, b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        f, a = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        df, da, db = ops.channel_modulate_bwd(dout, f, a, want_df=ctx.needs_input_grad[0], want_db=ctx.needs_input_grad[2])
+        return df, (da if ctx.needs_input_grad[1] else None), db
+
+
 class ShiftAttnFn(torch.autograd.Function):
     """ShiftSoftDotAttention, output_tilde=False (model.py:318-353): returns (weighted_context, pre-shift softmax)."""
 

@@ -135,8 +135,16 @@ class DGAdaChannel(nn.Module):
         return Fn.AdaINGateFn.apply(feat, dfeat, self.a_fc.weight, self.a_fc.bias, drop_mask, drop_scale, self.channel)
 
 
+def _view_stats_nograd(d_t):
+    """The depth features are environment data in the agent (agent_dg.py:742-777: built from obs, never a graph output), so
+    the statistics carry no gradient; asking for one is outside the path and fails loudly."""
+    if d_t.requires_grad:
+        raise NotImplementedError("gradients w.r.t. the depth features d_t are not on the agent_dg path (d_t is env data)")
+    return ops.view_stats(d_t)
+
+
 class DGAdaStatChannel(nn.Module):
-    """agent_dg.py:1639-1661 (forward; these variants are not in the named training configuration)."""
+    """agent_dg.py:1639-1661, forward + backward (a_fc / b_fc gradients through ChannelModulateFn)."""
 
     def __init__(self, channel, eps=1e-6):
         super().__init__()
@@ -145,14 +153,14 @@ class DGAdaStatChannel(nn.Module):
         self.eps = eps
 
     def forward(self, f_t, d_t):
-        stats = ops.view_stats(d_t)
-        a = ops.linear_fwd(stats, self.a_fc.weight, self.a_fc.bias)
-        b = ops.linear_fwd(stats, self.b_fc.weight, self.b_fc.bias)
-        return ops.channel_modulate(f_t, a, b)
+        stats = _view_stats_nograd(d_t)
+        a = Fn.linear(stats, self.a_fc.weight, self.a_fc.bias)
+        b = Fn.linear(stats, self.b_fc.weight, self.b_fc.bias)
+        return Fn.ChannelModulateFn.apply(f_t, a, b)
 
 
 class DGAdaMeanChannel(nn.Module):
-    """agent_dg.py:1620-1636 (forward)."""
+    """agent_dg.py:1620-1636, forward + backward."""
 
     def __init__(self, channel, eps=1e-6):
         super().__init__()
@@ -161,10 +169,10 @@ class DGAdaMeanChannel(nn.Module):
         self.eps, self.channel = eps, channel
 
     def forward(self, f_t, d_t):
-        mean = ops.view_stats(d_t)[:, :self.channel]
-        a = ops.linear_fwd(mean, self.a_fc.weight, self.a_fc.bias)
-        b = ops.linear_fwd(mean, self.b_fc.weight, self.b_fc.bias)
-        return ops.channel_modulate(f_t, a, b)
+        mean = _view_stats_nograd(d_t)[:, :self.channel].contiguous()
+        a = Fn.linear(mean, self.a_fc.weight, self.a_fc.bias)
+        b = Fn.linear(mean, self.b_fc.weight, self.b_fc.bias)
+        return Fn.ChannelModulateFn.apply(f_t, a, b)
 
 
 def adaptive_instance_normalization(content_feat, style_feat):

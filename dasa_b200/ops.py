@@ -271,6 +271,19 @@ def channel_modulate(f, a, b, out=None):
     return out
 
 
+def channel_modulate_bwd(dout, f, a, want_df=False, want_db=True):
+    """Backward of channel_modulate in one pass over dout and f: returns (df | None, da [N, C], db [N, C] | None)."""
+    N, V, C = f.shape
+    assert f.stride(2) == 1 and dout.stride(2) == 1 and dout.shape == f.shape
+    da = torch.empty(N, C, device=f.device, dtype=torch.float32)
+    db = torch.empty(N, C, device=f.device, dtype=torch.float32) if want_db else None
+    df = torch.empty(N, V, C, device=f.device, dtype=torch.float32) if want_df else None
+    call("dasa_channel_modulate_bwd", _p(dout), dout.stride(1), dout.stride(0), _p(f), f.stride(1), f.stride(0),
+         _p(a.contiguous()), _p(da), _p(db), _p(df), 0 if df is None else df.stride(1), 0 if df is None else df.stride(0),
+         N, V, C, _stream())
+    return df, da, db
+
+
 def adain_rows(f, d, eps=1e-5, out=None):
     f2, R, C, ldf = _rows(f)
     d2, _, _, ldd = _rows(d)

@@ -101,6 +101,11 @@ int dasa_view_stats(const float* d, int64_t ld_row, int64_t ld_sample, int N, in
 /* a2: out[n,v,c] = a[n,c] * f[n,v,c] + b[n,c]  (agent_dg.py:1636, 1661); b may be NULL                          */
 int dasa_channel_modulate(const float* f, int64_t ldf_row, int64_t ldf_sample, const float* a, const float* b,
                           float* out, int64_t ldo_row, int64_t ldo_sample, int N, int V, int C, void* stream);
+/* a2 backward of channel_modulate (autograd of agent_dg.py:1636, 1661): da[n,c] = sum_v dout*f, db[n,c] = sum_v dout
+ *     (db may be NULL), df[n,v,c] = a[n,c]*dout (df may be NULL: f is environment data in the agent). One pass.    */
+int dasa_channel_modulate_bwd(const float* dout, int64_t ldo_row, int64_t ldo_sample, const float* f, int64_t ldf_row,
+                              int64_t ldf_sample, const float* a, float* da, float* db, float* df, int64_t lddf_row,
+                              int64_t lddf_sample, int N, int V, int C, void* stream);
 /* a2: model.adaptive_instance_normalization (model.py:1822-1840): per (n, view) row statistics over the C channels,
  *     unbiased variance + eps; out = (f - mu_f) / sd_f * sd_d + mu_d. One pass: read f, read d, write out.      */
 int dasa_adain_rows(const float* f, int64_t ldf, const float* d, int64_t ldd, float* out, int64_t ldo,

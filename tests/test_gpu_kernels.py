@@ -124,6 +124,36 @@ def test_adain_stat_mean_default(cfg, B):
     assert_close(M.adaptive_instance_normalization(fd, dd), R.adain_default(f, d), 1e-4, "adain default")
 
 
+@pytest.mark.parametrize("cfg,B", [(SMALL, 4), (FULL, 3)])
+@pytest.mark.parametrize("kind", ["stat", "mean"])
+def test_adain_stat_mean_backward(cfg, B, kind):
+    """a2 backward: gradients of a_fc / b_fc (and of f when it requires grad) against autograd through the oracle."""
+    cls, fn = {"stat": (M.DGAdaStatChannel, R.adain_stat_channel), "mean": (M.DGAdaMeanChannel, R.adain_mean_channel)}[kind]
+    ep = synth.Episodes(B, 1, cfg, seed=6)
+    C = cfg.rgb_size
+    f, d = ep.f_t[0][..., :C].clone().requires_grad_(True), ep.d_t[0][..., :C]
+    st = {k: v.clone().requires_grad_(True) for k, v in synth.adain_state(cfg, 0, kind).items()}
+    w = torch.randn(B, cfg.views, C, generator=g(9))
+    (fn(st, f, d) * w).sum().backward()
+    mod = cls(C).to(DEV)
+    mod.load_state_dict({k: v.detach() for k, v in st.items()})
+    f_all = ep.f_t[0].to(DEV)                                   # strided RGB slice of the [B, V, C+A] buffer, read in place
+    fd = f_all[..., :C].detach().requires_grad_(True)
+    dd = ep.d_t[0].to(DEV)[..., :C]
+    out = mod(fd, dd)
+    (out * w.to(DEV)).sum().backward()
+    for k, p in mod.state_dict(keep_vars=True).items():
+        assert_close(p.grad, st[k].grad, 2e-4, "%s d%s" % (kind, k))
+    assert_close(fd.grad, f.grad, 1e-4, kind + " df")
+    # env-data form: f carries no gradient -> df is not produced
+    mod.zero_grad()
+    out = mod(f_all[..., :C], dd)
+    (out * w.to(DEV)).sum().backward()
+    assert_close(mod.a_fc.weight.grad, st["a_fc.weight"].grad, 2e-4, kind + " da_fc (no df)")
+    with pytest.raises(NotImplementedError):
+        mod(f_all[..., :C], dd.clone().requires_grad_(True))
+
+
 # ------------------------------------------------------------------------------------------- decoder attention
 @pytest.mark.parametrize("cfg,B", [(SMALL, 5), (FULL, 3), (FULL, 40)])
 def test_shift_attention_fwd_bwd(cfg, B):
