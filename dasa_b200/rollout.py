@@ -178,11 +178,13 @@ class NavPolicy:
         hidden states as ONE batch, and the fused A2C epilogue. Nothing is read back to the host inside the rollout.
         Returns (loss [1], dict)."""
         T = (ep.T - 1) if T is None else T
-        assert ep.resident and ep.dist is not None and ep.T >= T + 1, "sample_rollout needs T+1 resident observations + dist"
+        live = getattr(ep, "live", False)       # env.EnvEpisodes: the sampled action drives a device-resident environment
+        assert ep.resident and (live or ep.dist is not None) and ep.T >= T + 1, \
+            "sample_rollout needs T+1 resident observations + dist (or live environment episodes)"
         cfg, B, dev = self.cfg, ep.B, ep.f_t.device
         src = M.dropout_source()
         base_prefix = src.prefix
-        ended = torch.zeros(B, dtype=torch.uint8, device=dev)
+        ended = ep.ended if live else torch.zeros(B, dtype=torch.uint8, device=dev)
         reward = torch.empty(T, B, device=dev)
         mask = torch.empty(T, B, device=dev)
         carry, ctx, hidden, logps, ents, actions, logits = None, None, [], [], [], [], []
@@ -195,7 +197,10 @@ class NavPolicy:
             logits.append(logit)
             u = torch.rand(B, device=dev) if actions_in is None else None
             a_t, lp, en = Fn.PolicySampleFn.apply(logit, u, None if actions_in is None else actions_in[t])
-            ops.nav_reward(a_t, ep.cand_leng[t], cfg.ignore_id, ep.dist[t + 1], ep.dist[t], ended, reward[t], mask[t])
+            if live:    # make_equiv_action + next state + reward / mask / ended on the device (agent_dg.py:890-935)
+                ep.advance(t, a_t, reward[t], mask[t])
+            else:
+                ops.nav_reward(a_t, ep.cand_leng[t], cfg.ignore_id, ep.dist[t + 1], ep.dist[t], ended, reward[t], mask[t])
             logps.append(lp)
             ents.append(en)
             actions.append(a_t)
@@ -226,6 +231,8 @@ class NavPolicy:
         for t in range(T):
             logit, h_t, carry = self.step(ep, t, carry)
             _, a_t, _, _ = ops.masked_ce(logit, None, self.cfg.ignore_id, 0.0, None, want_grad=False)
+            if getattr(ep, "live", False):
+                ep.advance(t, a_t)
             actions.append(a_t)
             logits.append(logit)
         return actions, logits

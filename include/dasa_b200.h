@@ -314,6 +314,34 @@ int dasa_sumsq(const float* x, int64_t n, float* out, void* stream);
 /* clip_coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))                                                         */
 int dasa_clip_coef(const float* sumsq, float max_norm, float* clip_coef, void* stream);
 
+/* --------------------------------------------------------------------- device-resident environment
+ * Tables (dasa_b200/navgraph.py; replace R2RBatch.paths / .distances / buffered_state_dict, env.py:182-198, 291-298):
+ *   rgb_bank, dep_bank [n_vp, V, C]; nbr, nbr_point [n_vp, dmax]; deg [n_vp]; cand_angle [n_vp, dmax, 12, 4];
+ *   view_angle [12, V, 4]; agent_angle [V, 4]; dist_tab [n_vp, n_vp]; next_hop [n_vp, n_vp] (candidate slot, -1 at goal).
+ * Episode state [B]: vp (viewpoint), view (viewIndex 0..35), goal, ended.
+ * dasa_env_observe = env.py:_get_obs + make_candidate (buffered branch, :299-311) + agent_dg.py get_input_feat (:313-323),
+ *   _candidate_variable (:300-311), _teacher_action (:325-344): writes f_t/d_t [B, V, C+A] (sample stride ld_f_sample),
+ *   cand/cand_d [B, nc, C+A] (sample stride ld_c_sample; slot deg = END row = zeros, later slots zero), input_a_t [B, A],
+ *   cand_leng [B] (= deg + 1), target [B] (teacher candidate index, deg = STOP at the goal, ignore_id once ended; may be
+ *   NULL), dist [B] (distance to the goal; may be NULL). ended may be NULL.                                           */
+int dasa_env_observe(const float* rgb_bank, const float* dep_bank, const int32_t* nbr, const int32_t* nbr_point,
+                     const int32_t* deg, const float* cand_angle, const float* view_angle, const float* agent_angle,
+                     const float* dist_tab, const int32_t* next_hop, int n_vp, int dmax, const int32_t* vp,
+                     const int32_t* view, const int32_t* goal, const uint8_t* ended, int B, int V, int C, int A, int nc,
+                     int headings, int ignore_id, float* f_t, float* d_t, int64_t ld_f_sample, float* cand,
+                     float* cand_d, int64_t ld_c_sample, float* input_a_t, int32_t* cand_leng, int64_t* target,
+                     float* dist, void* stream);
+/* dasa_env_step = agent_dg.py:890-935: END = (action == deg) or ignore_id; otherwise make_equiv_action (:358-391): view =
+ *   the candidate's pointId, vp = the candidate's viewpoint (ended episodes keep moving under sampled feedback, as in the
+ *   reference); d = dist_tab[vp, goal]; reward = +-2 on END by d < 3, else sign(last_dist - d), 0 and mask 0 if already
+ *   ended; ended |= END; last_dist = d. traj_vp / traj_view [B] (may be NULL) record the state after the action.
+ *   err[0] |= 1 for an action outside the candidate list, |= 2 where the reference raises "The action doesn't change
+ *   the move" (agent_dg.py:925).                                                                                       */
+int dasa_env_step(const int64_t* action, int ignore_id, const int32_t* nbr, const int32_t* nbr_point, const int32_t* deg,
+                  int dmax, const float* dist_tab, int n_vp, int32_t* vp, int32_t* view, const int32_t* goal,
+                  uint8_t* ended, float* last_dist, float* reward, float* mask, int32_t* traj_vp, int32_t* traj_view,
+                  int32_t* err, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ class _Location:
 class SimState:
     def __init__(self, ix):
         self.viewIndex = ix
-        self.heading = (ix % 12) * math.pi / 6.0
+        self.heading = (ix % 12) * (math.pi * 2.0 / 12)      # heading_step * headingIncrement (MatterSim.cpp:347-350)
         self.elevation = (ix // 12 - 1) * math.pi / 6.0
         self.location = _Location()
         self.navigableLocations = []

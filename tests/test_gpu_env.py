@@ -1,0 +1,209 @@
+"""GPU tier: the device-resident environment (dasa_b200/env.py, csrc/env.cu) against the CPU oracle (oracle/env_restated.py,
+pinned against the reference's env.py / agent_dg.py) and against the reference-generated fixture tests/golden/env_rollout.pt.
+Everything here is integer / table-lookup / copy work, so the bar is BIT-EXACT."""
+import os
+from dataclasses import replace
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from dasa_b200 import synth
+from dasa_b200.config import FULL, SMALL
+from dasa_b200.navgraph import NavGraph
+from oracle import env_restated as E
+from oracle import restated as R
+from tests.envcase import lists, random_actions, scenario
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "env_rollout.pt")
+BUF_KEYS = ("input_a_t", "f_t", "d_t", "cand_feat", "cand_dfeat", "cand_leng", "target", "dist")
+
+
+def _cfg(C):
+    return replace(SMALL, rgb_size=C)
+
+
+def _device_rollout(g, rgb, dep, start, view, goal, T, actions, cfg):
+    from dasa_b200.env import DeviceEnv
+    env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+    buf = env.alloc(T)
+    reward = torch.empty(T, env.B, device=DEV)
+    mask = torch.empty(T, env.B, device=DEV)
+    ended, vps, views = [], [], []
+    for t in range(T):
+        env.observe(buf, t)
+        a = buf["target"][t] if actions is None else torch.as_tensor(actions[t]).to(DEV)
+        env.step(a, reward[t], mask[t])
+        ended.append(env.ended.clone())
+        vps.append(env.vp.clone())
+        views.append(env.view.clone())
+    torch.cuda.synchronize()
+    return env, buf, reward, mask, ended, vps, views
+
+
+def _compare(steps, g, buf, reward, mask, ended, vps, views, T, name_index=None):
+    for t in range(T):
+        s = steps[t]
+        nc_ref = np.asarray(s["cand_feat"]).shape[1]
+        for k in BUF_KEYS:
+            if k not in s:
+                continue
+            got = buf[k][t].cpu().numpy()
+            want = np.asarray(s[k])
+            if k in ("cand_feat", "cand_dfeat"):
+                assert not got[:, nc_ref:].any(), "step %d %s: padding slots must be zero" % (t, k)
+                got = got[:, :nc_ref]
+            assert np.array_equal(got, want), "step %d %s" % (t, k)
+        assert np.array_equal(reward[t].cpu().numpy(), np.asarray(s["reward"])), "step %d reward" % t
+        assert np.array_equal(mask[t].cpu().numpy(), np.asarray(s["mask"])), "step %d mask" % t
+        assert np.array_equal(ended[t].cpu().numpy().astype(bool), np.asarray(s["ended"]).astype(bool)), "step %d ended" % t
+        assert np.array_equal(views[t].cpu().numpy(), np.asarray(s["viewIndex"])), "step %d viewIndex" % t
+        if "vp" in s:
+            assert np.array_equal(vps[t].cpu().numpy(), np.asarray(s["vp"]))
+        else:
+            assert [g.names[i] for i in vps[t].cpu().tolist()] == s["viewpoint"]
+
+
+@pytest.mark.parametrize("seed,n,B,C", [(0, 24, 5, 32), (1, 40, 9, 64), (2, 30, 3, 2048)])
+@pytest.mark.parametrize("closed_loop", [False, True])
+def test_env_matches_oracle(seed, n, B, C, closed_loop):
+    T = 8
+    g, rgb, dep, start, view, goal = scenario(n=n, B=B, T=T, C=C, seed=seed)
+    cfg = _cfg(C)
+    actions = None
+    if closed_loop:
+        for s2 in range(seed, seed + 50):                      # a random walk without a zero-progress move (reference raises)
+            actions = random_actions(g, start, T, s2)
+            ora = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+            ora.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+            try:
+                steps = E.rollout(ora, T, C, cfg.angle_size, actions)
+                break
+            except NameError:
+                continue
+    else:
+        ora = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+        ora.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+        steps = E.rollout(ora, T, C, cfg.angle_size, None)
+    env, buf, reward, mask, ended, vps, views = _device_rollout(g, rgb, dep, start, view, goal, T, actions, cfg)
+    _compare(steps, g, buf, reward, mask, ended, vps, views, T)
+    env.check()
+
+
+def test_env_matches_reference_golden():
+    """Vectors produced by the reference's own env.py / agent_dg.py helpers (oracle/make_golden_env.py)."""
+    gold = torch.load(GOLD, weights_only=False)
+    G = gold["graph"]
+    g = NavGraph(G["nbrs"], G["weights"], G["headings"], G["elevations"], G["points"], G["names"])
+    cfg = _cfg(gold["C"])
+    T = gold["T"]
+    for key, actions in (("teacher", None), ("closed", [a.numpy() for a in gold["actions"]])):
+        steps = [{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in s.items()} for s in gold[key]]
+        env, buf, reward, mask, ended, vps, views = _device_rollout(g, gold["rgb"].numpy(), gold["dep"].numpy(), gold["start"].numpy(),
+                                                                    gold["view"].numpy(), gold["goal"].numpy(), T, actions, cfg)
+        _compare(steps, g, buf, reward, mask, ended, vps, views, T)
+
+
+def test_env_error_flags():
+    from dasa_b200.env import DeviceEnv
+    g, rgb, dep, start, view, goal = scenario(seed=4)
+    env = DeviceEnv(g, rgb, dep, _cfg(32), DEV).reset(start, view, goal)
+    bad = torch.full((env.B,), 99, dtype=torch.int64, device=DEV)
+    env.step(bad)
+    with pytest.raises(RuntimeError):
+        env.check()
+    with pytest.raises(RuntimeError):
+        DeviceEnv(g, rgb, dep, _cfg(32), "cpu")
+
+
+class _OracleEpisodes:
+    """Oracle-side episodes assembled from oracle/env_restated.rollout steps (what R.teacher_rollout / R.sample_rollout read)."""
+
+    def __init__(self, steps, instr, cfg):
+        self.seq, self.seq_mask, self.seq_lengths = instr
+        self.B, self.T, self.cfg = len(steps[0]["target"]), len(steps), cfg
+        self.steps = steps
+        self.dist = torch.stack([torch.from_numpy(s["dist"]) for s in steps])
+
+    def step(self, t):
+        s = self.steps[t]
+        return (torch.from_numpy(s["input_a_t"]), torch.from_numpy(s["f_t"]), torch.from_numpy(s["d_t"]),
+                torch.from_numpy(s["cand_feat"]), torch.from_numpy(s["cand_dfeat"]), torch.from_numpy(s["cand_leng"]),
+                torch.from_numpy(s["target"]))
+
+
+@pytest.mark.parametrize("schedule", ["batched", "sequential"])
+def test_teacher_rollout_on_device_env(schedule):
+    """agent_dg teacher-forced rollout with the observations produced on the device == the oracle policy over the oracle
+    environment (loss, logits, greedy actions, a weight gradient)."""
+    from dasa_b200.env import DeviceEnv
+    from dasa_b200.rollout import NavPolicy
+    cfg, B, T = SMALL, 4, 5
+    g, rgb, dep, start, view, goal = scenario(n=20, B=B, T=T, C=cfg.rgb_size, seed=6)
+    instr = synth.instructions(B, cfg, 6)
+    ora = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+    ora.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+    oep = _OracleEpisodes(E.rollout(ora, T, cfg.rgb_size, cfg.angle_size, None), instr, cfg)
+    st = synth.policy_state(cfg, 0)
+    ost = {grp: {k: v.clone().requires_grad_(True) for k, v in d.items()} for grp, d in st.items()}
+    loss_ref, logits_ref, act_ref = R.teacher_rollout(ost, cfg, oep, T)
+    loss_ref.backward()
+    pol = NavPolicy(cfg, st, DEV).eval()
+    env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+    ep = env.teacher_episodes(T, instr)
+    loss, logits, act = pol.teacher_rollout(ep, T, schedule=schedule)
+    pol.backward(loss)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * max(1e-6, abs(float(loss_ref)))
+    for t in range(T):
+        nc = logits_ref[t].shape[1]
+        a, b = logits[t].cpu()[:, :nc], logits_ref[t]
+        fin = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), fin)
+        assert float((a[fin] - b[fin]).abs().max()) <= 1e-4 * float(b[fin].abs().max())
+        assert torch.equal(act[t].cpu(), act_ref[t])
+    gw, gr = pol.decoder.lstm.weight_hh.grad.cpu(), ost["decoder"]["lstm.weight_hh"].grad
+    assert float((gw - gr).abs().max()) <= 1e-3 * float(gr.abs().max())
+    env.check()
+
+
+def test_sample_rollout_on_live_env():
+    """Sampled-feedback A2C rollout in closed loop with the device environment (injected actions) == oracle policy + oracle env."""
+    from dasa_b200.env import DeviceEnv
+    from dasa_b200.rollout import NavPolicy
+    cfg, B, T = SMALL, 4, 5
+    g, rgb, dep, start, view, goal = scenario(n=20, B=B, T=T, C=cfg.rgb_size, seed=8)
+    instr = synth.instructions(B, cfg, 8)
+    for s2 in range(50):
+        actions = random_actions(g, start, T, s2) + [np.array([int(cfg.ignore_id)] * B, np.int64)]
+        ora = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+        ora.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+        try:
+            steps = E.rollout(ora, T + 1, cfg.rgb_size, cfg.angle_size, actions)
+            break
+        except NameError:
+            continue
+    oep = _OracleEpisodes(steps, instr, cfg)
+    st = synth.policy_state(cfg, 1)
+    ost = {grp: {k: v.clone().requires_grad_(True) for k, v in d.items()} for grp, d in st.items()}
+    acts_t = [torch.from_numpy(a) for a in actions[:T]]
+    loss_ref, info_ref = R.sample_rollout(ost, cfg, oep, T, acts_t)
+    loss_ref.backward()
+    pol = NavPolicy(cfg, st, DEV).eval()
+    env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+    ep = env.live_episodes(T, instr)
+    loss, info = pol.sample_rollout(ep, T, actions_in=[a.to(DEV) for a in acts_t])
+    pol.backward(loss)
+    torch.cuda.synchronize()
+    assert torch.equal(info["reward"].cpu(), torch.stack(info_ref["rewards"]))
+    assert torch.equal(info["mask"].cpu(), torch.stack(info_ref["masks"]))
+    assert torch.equal(info["ended"].cpu().bool(), info_ref["ended"].bool())
+    assert abs(float(loss) - float(loss_ref)) <= 2e-4 * max(1e-6, abs(float(loss_ref)))
+    gw, gr = pol.decoder.lstm.weight_hh.grad.cpu(), ost["decoder"]["lstm.weight_hh"].grad
+    assert float((gw - gr).abs().max()) <= 1e-3 * float(gr.abs().max())
+    assert torch.equal(ep.traj[1:T + 1].cpu(), torch.tensor([[g.names.index(v) for v in s["viewpoint"]] for s in steps[:T]],
+                                                              dtype=torch.int32))
+    env.check()
