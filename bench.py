@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-micro", action="store_true")
+    ap.add_argument("--skip-env", action="store_true", help="do not time the device-resident-environment end-to-end arm")
+    ap.add_argument("--env-viewpoints", type=int, default=512, help="viewpoints of the synthetic navigation graph (e2e_env arm)")
     ap.add_argument("--schedule", default="batched", choices=["batched", "sequential"],
                     help="batched: AdaIN + encoder of all T teacher-forced actions as one batch; sequential: per action")
     ap.add_argument("--skip-sequential", action="store_true", help="do not also time the per-action schedule")
@@ -318,16 +320,17 @@ def run_ours(args):
             loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
 
-    def capture():
-        """Whole rollout (forward, backward, deferred weight grads, and for N=1 clip + RMSprop) as ONE CUDA graph."""
+    def capture(make_ep=None, key=""):
+        """Whole rollout (forward, backward, deferred weight grads, and for N=1 clip + RMSprop) as ONE CUDA graph. With
+        make_ep the episodes themselves (device environment: T x observe + step kernels) are built inside the graph."""
         Fn.invalidate_weight_caches()                       # cached transposes must be rebuilt INSIDE the graph every replay
         g = torch.cuda.CUDAGraph()
         l0 = lib.launches
         with torch.cuda.graph(g):
-            loss = fwd_bwd(ep_res)
+            loss = fwd_bwd(ep_res if make_ep is None else make_ep())
             if world == 1:
                 finish()
-        state["graph"], state["loss"], state["launches"] = g, loss, lib.launches - l0
+        state["graph" + key], state["loss" + key], state["launches" + key] = g, loss, lib.launches - l0
 
     def timed(read_back, upload, steps, warmup):
         for _ in range(warmup):
@@ -382,6 +385,13 @@ def run_ours(args):
         "eager launches (%s)" % (state["graph_error"] or "--no-graph")
     ms_e2e, _ = timed(True, True, args.steps, 1)
     Fn.invalidate_weight_caches()
+    env_arm = None
+    if not sample and not args.skip_env:
+        try:
+            env_arm = env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, loss_host, host_ep)
+        except Exception as e:                              # reported, never fatal for the headline line
+            env_arm = {"error": repr(e)[:300]}
+        Fn.invalidate_weight_caches()
     # the same workload on the per-action schedule (the order a sampled / greedy rollout is forced to use)
     ms_seq = None
     if args.schedule == "batched" and not args.skip_sequential and not sample:
@@ -444,6 +454,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "nav steps/s", "h2d_bytes_per_step": host_ep.h2d_bytes_per_step() * T,
                 "d2h_bytes_per_step": 4},
+        "e2e_env": env_arm,
         "roofline": roof, "kernels": extra, "cpu_baseline": cpu,
         "sequential_schedule": None if ms_seq is None else {"value": nav / (ms_seq * 1e-3), "unit": "nav steps/s",
                                                              "ms_per_step": ms_seq},
@@ -451,6 +462,132 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, loss_host, host_ep):
+    """End-to-end arm over the device-resident environment (dasa_b200/env.py): the RGB / depth feature
+    banks and the navigation-graph tables live in HBM (the reference keeps them in host RAM and re-uploads every observation),
+    so a rollout's host inputs are the episode descriptors (start viewpoint, heading, goal: 12 B per episode) and the tokenised
+    instructions. Per step, inside the timed region: H2D of those from pinned memory, T x (observe, step) kernels that unroll the
+    teacher-forced trajectories and assemble every observation, the same forward + backward + optimizer work as `value`, and
+    the loss read back. New start / goal pairs every step (the trajectories differ; shapes do not, so one CUDA graph replays)."""
+    import torch.distributed as dist
+    from dasa_b200 import lib, synth
+    from dasa_b200.env import DeviceEnv
+    from dasa_b200.navgraph import NavGraph
+    n = args.env_viewpoints
+    g = NavGraph.synthetic(n, seed=0)
+    gen = torch.Generator().manual_seed(4242)
+    rgb = synth.resnet_like((n, cfg.views, cfg.rgb_size), gen)
+    dep = synth.resnet_like((n, cfg.views, cfg.rgb_size), gen)
+    env = DeviceEnv(g, rgb, dep, cfg, dev)
+    del rgb, dep
+    K = 8
+    import numpy as np
+    sets = [g.sample_episodes(B, seed=1000 * rank + k) for k in range(K)]
+    h_start = torch.from_numpy(np.stack([s[0] for s in sets])).pin_memory()
+    h_view = torch.from_numpy(np.stack([s[1] for s in sets])).pin_memory()
+    h_goal = torch.from_numpy(np.stack([s[2] for s in sets])).pin_memory()
+    h_seq, h_mask, h_len = host_ep.seq.pin_memory(), host_ep.seq_mask.pin_memory(), host_ep.seq_lengths.to(torch.int32).pin_memory()
+    d_seq, d_mask, d_len = h_seq.to(dev), h_mask.to(dev), h_len.to(dev)
+    lengths_host = [int(x) for x in host_ep.seq_lengths.tolist()]
+    h2d = 3 * B * 4 + h_seq.numel() * 8 + h_mask.numel() + h_len.numel() * 4
+
+    def make_ep():
+        return env.teacher_episodes(T, (d_seq, d_mask, d_len, lengths_host))
+
+    def upload(i):
+        d_seq.copy_(h_seq, non_blocking=True)
+        d_mask.copy_(h_mask, non_blocking=True)
+        d_len.copy_(h_len, non_blocking=True)
+        env.reset(h_start[i % K], h_view[i % K], h_goal[i % K])
+
+    def step(i):
+        upload(i)
+        if state.get("graph_env") is not None:
+            state["graph_env"].replay()
+            loss = state["loss_env"]
+            if world > 1:
+                finish()
+        else:
+            loss = fwd_bwd(make_ep())
+            finish()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    env.reset(h_start[0], h_view[0], h_goal[0])
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    env.check()
+    mode = "eager launches"
+    if not args.no_graph:
+        try:
+            capture(make_ep, "_env")
+            mode = "cuda-graph replay (environment unroll + rollout + optimizer)"
+        except Exception as e:
+            state["graph_env"] = None
+            mode = "eager launches (%s)" % repr(e)[:120]
+            torch.cuda.synchronize()
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = lib.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(2 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    env.check()
+    ms = float(ms) / args.steps
+    n_launch = (lib.launches - l0) // args.steps + (state.get("launches_env", 0) if state.get("graph_env") is not None else 0)
+    state["graph_env"] = None
+    # HBM roofline of the observation gather at a large batch (L2 flushed between launches)
+    obs_roof = None
+    if rank == 0 and not args.skip_micro:
+        Bm = 1024
+        sb = g.sample_episodes(Bm, seed=77)
+        env_m = DeviceEnv.__new__(DeviceEnv)
+        env_m.__dict__.update(env.__dict__)                 # same resident tables / banks, own episode state
+        env_m.B = 0
+        env_m.reset(*sb)
+        bufm = env_m.alloc(1)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            env_m.observe(bufm, 0)
+            a1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a0.elapsed_time(a1) * 1e-3)
+        ts.sort()
+        # algorithmic bytes: per view / live candidate row read 2 x C floats (RGB + depth bank rows) and write 2 x (C + A);
+        # END / padding rows are written only
+        live_rows = Bm * cfg.views + int(g.deg[sb[0]].sum())
+        all_rows = Bm * (cfg.views + env.nc)
+        bytes_ = 4.0 * (live_rows * 2 * cfg.rgb_size + all_rows * 2 * cfg.feat)
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        t_med = ts[len(ts) // 2]
+        obs_roof = {"bound": "hbm", "achieved": bytes_ / t_med / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": bytes_ / t_med / 1e9 / peak, "batch": Bm, "us": t_med * 1e6}
+        del bufm, flush
+    return {"value": B * T * world / (ms * 1e-3), "unit": "nav steps/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 4, "gpu_launches": n_launch, "launch": mode, "env_observe_roofline": obs_roof,
+            "what": "feature banks (%d viewpoints x 36 views x 2048 x {RGB, depth} = %.0f MB) + graph tables resident in HBM; per step the "
+                    "episode descriptors and tokenised instructions are uploaded, the teacher-forced trajectories are unrolled and "
+                    "every observation is assembled on the device (env_observe / env_step kernels), then the same fwd+bwd+RMSprop "
+                    "as `value`" % (n, 2 * n * cfg.views * cfg.rgb_size * 4 / 1e6)}
 
 
 def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):

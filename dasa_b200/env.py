@@ -116,8 +116,8 @@ class DeviceEnv:
 
 
 class EnvEpisodes:
-    """Duck-types rollout.DeviceEpisodes on top of a DeviceEnv. instr = (seq [B,80] int64, mask [B,Lmax] bool, lengths [B])
-    as produced by the tokenizer side (host tensors; uploaded once per rollout)."""
+    """Duck-types rollout.DeviceEpisodes on top of a DeviceEnv. instr = (seq [B,80] int64, mask [B,Lmax] bool, lengths [B]
+    [, lengths as a host list]) as produced by the tokenizer side (host tensors are uploaded once per rollout)."""
 
     FIELDS = FIELDS
     resident = True
@@ -125,10 +125,12 @@ class EnvEpisodes:
     def __init__(self, env, buf, T, instr, live=False, traj=None):
         self.env, self.buf, self.T, self.B, self.cfg, self.live = env, buf, T, env.B, env.cfg, live
         dev = env.device
-        seq, mask, lengths = instr
+        seq, mask, lengths = instr[:3]
         self.seq, self.seq_mask = seq.to(dev, non_blocking=True), mask.to(dev, non_blocking=True)
         self.seq_lengths = lengths.to(dev, non_blocking=True).to(torch.int32)
-        self.seq_lengths_host = [int(x) for x in lengths.tolist()]
+        # host copy of the lengths (lets the encoder drop padding rows without a sync); pass it as instr[3] when `lengths`
+        # already lives on the device (e.g. inside a CUDA-graph capture, where .tolist() would be an illegal sync)
+        self.seq_lengths_host = list(instr[3]) if len(instr) > 3 else [int(x) for x in lengths.tolist()]
         for k in FIELDS:
             setattr(self, k, buf[k])
         self.dist = buf["dist"] if not live else None
