@@ -27,6 +27,13 @@ extern "C" int dasa_version(void) { return 101; }
 extern "C" const char* dasa_build_arch(void) { return "sm_100a"; }
 extern "C" const char* dasa_last_error(void) { return g_last_error; }
 
+/* 1 when dasa_gemm(precision = TF32) runs this operand-layout combination on the tensor cores without transposed copies */
+extern "C" int dasa_gemm_layout_on_tensor_cores(int a_kmajor, int b_kmajor, int M, int N, int K) {
+  if (a_kmajor && b_kmajor) return 1;
+  if (M <= 0 || N <= 0 || K < 32 || dasa_tensormap_encoder() == nullptr) return 0;
+  return dasa_gemm_pair_plan(M, N, K) == 256 ? 1 : 0;
+}
+
 extern "C" size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision) {
   size_t a = dasa_gemm_simt_workspace(M, N, K);
   size_t b = (precision == DASA_PREC_TF32) ? dasa_gemm_tc_workspace(M, N, K) : 0;
@@ -44,6 +51,8 @@ extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float 
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == DASA_PREC_TF32 && dasa_gemm_skinny_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb))
     return dasa_gemm_skinny(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, st);
+  if (precision == DASA_PREC_TF32 && dasa_gemm_pair_mn_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, epilogue))
+    return dasa_gemm_tc_pair_mn(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
   if (precision == DASA_PREC_TF32 && dasa_gemm_tc_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc))
     return dasa_gemm_tc(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
                         workspace_bytes, st);

@@ -88,6 +88,11 @@ int dasa_gemm_tc(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, c
 int dasa_gemm_pair_plan(int M, int N, int K);
 int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                       float* C, int64_t ldc, int epilogue, const EpiParams& ep, cudaStream_t st);
+// MN-major operand layouts on the pair kernel (no transposed copies for dX = dY.W and dW = dY^T.X), gemm_tc2.cu
+bool dasa_gemm_pair_mn_supported(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                                 int64_t ldb, int epilogue);
+int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
+                         int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st);
 // grouped (2 problems) / split-K launch of the pair kernel; returns the number of K splits actually used (>= 1) or a negative error
 int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st);

@@ -88,6 +88,22 @@ __device__ __forceinline__ uint64_t p_desc_sw128(const void* smem_ptr) {   // K-
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand (tcgen05 accepts MN-major TF32 operands, unlike wgmma). For 32-bit elements the only MN-major shared-memory
+// layout the tensor core reads is the 128-byte swizzle with 32-byte atomicity (descriptor layout type 1; byte-address swizzle
+// <2,5,2>: the 32 B chunk index is XORed with the row index mod 4) = what a TMA box {32 mn, P_BK k} written with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces: per 32-wide chunk of the M/N extent, P_BK rows (one per k) of 128 bytes.
+// Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = distance between 32-wide M/N chunks (P_BK * 128 B),
+// SBO = distance between groups of 4 k rows (512 B). One UMMA (K = 8) consumes two 4-row groups of every chunk.
+__device__ __forceinline__ uint64_t p_desc_sw128_mn(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((P_BK * 128) >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -100,7 +116,9 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES, int EPI>
+// AMN / BMN: the operand is MN-major in HBM (A stored [K][M], B stored [K][N]): dX = dY.W and dW = dY^T.X run without any
+// transposed copy of the activations / weights.
+template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, PairParams p) {
@@ -157,8 +175,18 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // both CTAs' boxes complete on the leader's barrier
           const uint32_t fb = p_mapa(smem_u32(&full_bar[s]), 0);
           unsigned char* dst = tiles + s * STAGE_BYTES;
-          p_tma_load_2sm(dst, ma, kb * P_BK, m0, fb);
-          p_tma_load_2sm(dst + A_BYTES, mb, kb * P_BK, nb0, fb);
+          if constexpr (AMN) {
+#pragma unroll
+            for (int c = 0; c < P_BM / 32; ++c) p_tma_load_2sm(dst + c * (P_BK * 128), ma, m0 + 32 * c, kb * P_BK, fb);
+          } else {
+            p_tma_load_2sm(dst, ma, kb * P_BK, m0, fb);
+          }
+          if constexpr (BMN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) p_tma_load_2sm(dst + A_BYTES + c * (P_BK * 128), mb, nb0 + 32 * c, kb * P_BK, fb);
+          } else {
+            p_tma_load_2sm(dst + A_BYTES, mb, kb * P_BK, nb0, fb);
+          }
         }
       }
       // drain: every multicast commit aimed at this CTA's `empty` barriers has landed before the CTA may exit
@@ -170,7 +198,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0 && crank == 0) {
       // -------------------------------------------------------------- MMA issuer (leader CTA, single thread)
       // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 256 (128 rows in each CTA's TMEM)
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs, ++tcount) {
         const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -185,11 +214,13 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&full_bar[s], ph);
           p_fence_after();
           unsigned char* src = tiles + s * STAGE_BYTES;
-          const uint64_t da = p_desc_sw128(src);
-          const uint64_t db = p_desc_sw128(src + A_BYTES);
+          const uint64_t da = AMN ? p_desc_sw128_mn(src) : p_desc_sw128(src);
+          const uint64_t db = BMN ? p_desc_sw128_mn(src + A_BYTES) : p_desc_sw128(src + A_BYTES);
+          // K-major: 8 tf32 = 32 B further along the swizzled row; MN-major: the next group of 8 k rows (1024 B)
+          constexpr uint64_t ka = AMN ? 64 : 2, kbs = BMN ? 64 : 2;
 #pragma unroll
           for (int k = 0; k < P_BK / 8; ++k)
-            p_umma_tf32_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+            p_umma_tf32_pair(d_tmem, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           p_commit_pair(&empty_bar[s]);                    // stage free in both CTAs once these MMAs retire
         }
         p_commit_pair(&tmem_full[a]);                      // accumulator complete: visible to both CTAs' epilogues
@@ -309,11 +340,24 @@ bool pair_make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES, int EPI>
+// MN-major operand stored [K rows][cols] (row stride ld): box = 32 columns (one 128-byte swizzle row) x P_BK k rows
+bool pair_make_map_mn(CUtensorMap* map, const float* base, int64_t cols, int64_t K, int64_t ld) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(dasa_tensormap_encoder());
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)P_BK};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false>
 int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + P_EPI_WARPS * 32 * P_EPI_LD * 4 + 256 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
-  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI>;
+  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI, AMN, BMN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -375,6 +419,36 @@ int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, 
   if (!pair_make_map(&ta[0], A, M, K, lda, P_BM) || !pair_make_map(&tb[0], B, N, K, ldb, bn / 2)) return DASA_ERR_UNSUPPORTED;
   ta[1] = ta[0]; tb[1] = tb[0];
   return launch_pair<256, 5>(ta, tb, p, epilogue, st);
+}
+
+// Operand layouts other than (K-major, K-major): C = alpha * op(A) * op(B) + beta * C with an MN-major A ([K][M] in memory)
+// and / or B ([K][N]); no fused epilogue (the backward GEMMs dX = dY.W and dW += dY^T.X are the users).
+bool dasa_gemm_pair_mn_supported(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                                 int64_t ldb, int epilogue) {
+  if (a_kmajor && b_kmajor) return false;
+  if (epilogue != DASA_EPI_NONE || M <= 0 || N <= 0 || K < P_BK) return false;
+  if (!dasa_aligned16(A) || !dasa_aligned16(B) || (lda & 3) || (ldb & 3)) return false;
+  if (dasa_tensormap_encoder() == nullptr) return false;
+  return dasa_gemm_pair_plan(M, N, K) == 256;
+}
+
+int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
+                         int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st) {
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C[0] = C; p.C[1] = C; p.ldc = ldc;
+  p.tiles_n = (int)dasa_cdiv(N, 256);
+  p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  p.splits = 1; p.kb_per_split = (int)dasa_cdiv(K, P_BK); p.split_stride = 0;
+  p.tiles_total = p.tiles_mn;
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta[2], tb[2];
+  const bool oka = a_kmajor ? pair_make_map(&ta[0], A, M, K, lda, P_BM) : pair_make_map_mn(&ta[0], A, M, K, lda);
+  const bool okb = b_kmajor ? pair_make_map(&tb[0], B, N, K, ldb, 128) : pair_make_map_mn(&tb[0], B, N, K, ldb);
+  if (!oka || !okb) return DASA_ERR_UNSUPPORTED;
+  ta[1] = ta[0]; tb[1] = tb[0];
+  if (a_kmajor) return launch_pair_e<256, 5, DASA_EPI_NONE, false, true>(ta, tb, p, st);
+  if (b_kmajor) return launch_pair_e<256, 5, DASA_EPI_NONE, true, false>(ta, tb, p, st);
+  return launch_pair_e<256, 5, DASA_EPI_NONE, true, true>(ta, tb, p, st);
 }
 
 // Two independent problems of the same shape in ONE launch, optionally split along K (raw partial sums, no epilogue):

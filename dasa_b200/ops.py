@@ -117,6 +117,7 @@ def transpose(x, out=None):
     return out[:, :R]
 
 
+use_mn_major = True    # feed tcgen05 MN-major operands where the pair kernel takes the problem (else transposed copies)
 _wt_cache = {}
 weights_epoch = 0      # bumped by the optimizer step (raw-pointer updates do not bump tensor versions)
 
@@ -149,6 +150,9 @@ def linear_bwd_input(dy, w, out=None, beta=0.0, precision=None):
         out = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=torch.float32)
     o2, _, _, ldc = _rows_out(out)
     if precision is None and _tc_ok(N) and lda % 4 == 0 and d2.data_ptr() % 16 == 0:
+        if use_mn_major and K % 4 == 0 and lib.load().dasa_gemm_layout_on_tensor_cores(1, 0, M, K, N):
+            gemm(d2, lda, 1, w, K, 0, o2, ldc, M, K, N, beta=beta)  # W read in place as an MN-major B operand
+            return out
         wt = transposed_weight(w)                                  # [K, N] rows of stride Np
         gemm(d2, lda, 1, wt, wt.stride(0), 1, o2, ldc, M, K, N, beta=beta)
         return out
@@ -163,6 +167,11 @@ def linear_bwd_weight(dy, x, dw, accumulate=True, precision=None):
     x2, Mx, K, ldx = _rows(x)
     assert M == Mx and dw.shape == (N, K) and dw.is_contiguous()
     if precision is None and _tc_ok(M) and M >= 64:
+        if (use_mn_major and ldd % 4 == 0 and ldx % 4 == 0 and d2.data_ptr() % 16 == 0 and x2.data_ptr() % 16 == 0 and
+                lib.load().dasa_gemm_layout_on_tensor_cores(0, 0, N, K, M)):
+            # dY [M, N] and X [M, K] are MN-major operands of dW = dY^T X as they stand: no transposed copies
+            gemm(d2, ldd, 0, x2, ldx, 0, dw, K, N, K, M, beta=1.0 if accumulate else 0.0)
+            return dw
         dyt, xt = transpose(d2), transpose(x2)                    # [N, Mp], [K, Mp]: both K-major over the row index
         gemm(dyt, dyt.stride(0), 1, xt, xt.stride(0), 1, dw, K, N, K, M, beta=1.0 if accumulate else 0.0)
         return dw

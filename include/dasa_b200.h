@@ -78,6 +78,11 @@ int dasa_debug_gemm_pair(int mode);
 int dasa_debug_gemm_skinny(int on);
 
 size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
+/* 1 when dasa_gemm(DASA_PREC_TF32) runs this operand-layout combination on the tensor cores directly: always for two K-major
+ * operands; for an MN-major A ([K][M] in memory) and / or B ([K][N]) when the problem is large enough for the persistent CTA-pair
+ * kernel, which feeds tcgen05 MN-major TF32 operands (TMA boxes of 32 columns x 32 k rows, 128B swizzle) — the backward GEMMs
+ * dX = dY.W and dW += dY^T.X then need no transposed copy. Otherwise such layouts run on the FFMA kernel.                */
+int dasa_gemm_layout_on_tensor_cores(int a_kmajor, int b_kmajor, int M, int N, int K);
 int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
               const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue,
               const dasa_epilogue_t* epi, int precision, void* workspace, size_t workspace_bytes, void* stream);

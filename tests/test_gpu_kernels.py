@@ -784,3 +784,68 @@ def test_gemm_skinny_kernel(shape):
         assert torch.equal(C, C2), "skinny kernel must be deterministic"
     finally:
         L.dasa_debug_gemm_skinny(1)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 32), (512, 260, 96), (777, 516, 1000), (4096, 768, 3000), (2048, 2240, 700)])
+@pytest.mark.parametrize("layout", [(1, 0), (0, 0), (0, 1)])
+def test_gemm_tf32_pair_kernel_mn_major(shape, layout):
+    """MN-major operands on the CTA-pair tcgen05 kernel (A stored [K][M] and / or B stored [K][N]; TMA boxes of 32 columns x 32
+    k rows, MN-major shared-memory descriptors): the backward GEMMs dX = dY.W (1,0) and dW += dY^T.X (0,0) without transposed
+    copies. Against an fp64 reference (TF32 products) and against the K-major pair kernel fed explicit transposes."""
+    from dasa_b200 import lib
+    M, N, K = shape
+    ak, bk = layout
+    gen = g(13 + M + ak)
+    pad4 = lambda n: (n + 3) // 4 * 4
+    A = torch.randn((M, K) if ak else (K, pad4(M) + 4), generator=gen)   # padded rows: strided operands (TMA: stride % 16 B == 0)
+    Bm = torch.randn((N, K) if bk else (K, pad4(N) + 8), generator=gen) * 0.1
+    C0 = torch.randn(M, N + 4, generator=gen)
+    A_log = A if ak else A[:, :M].t()
+    B_log = Bm if bk else Bm[:, :N].t()
+    acc = A_log.double() @ B_log.double().t()
+    Ad, Bd = A.to(DEV), Bm.to(DEV)
+    L = lib.load()
+    try:
+        L.dasa_debug_gemm_pair(2)
+        assert L.dasa_gemm_layout_on_tensor_cores(ak, bk, M, N, K) == 1
+        C = torch.full((M, N + 4), 7.0, device=DEV)
+        ops.gemm(Ad, Ad.stride(0), ak, Bd, Bd.stride(0), bk, C, N + 4, M, N, K, precision=ops.PREC_TF32)
+        assert float((C[:, N:] - 7.0).abs().max()) == 0.0
+        assert_close(C[:, :N], acc, 3e-3, "MN-major pair kernel")
+        # the same products through the K-major path (explicit transposes): identical tensor-core arithmetic
+        At = A_log.contiguous().to(DEV)
+        Bt = B_log.contiguous().to(DEV)
+        Ck = torch.empty(M, N, device=DEV)
+        ops.gemm(At, K, 1, Bt, K, 1, Ck, N, M, N, K, precision=ops.PREC_TF32)
+        assert_close(C[:, :N], Ck, 1e-5, "MN-major vs K-major pair kernel")
+        # accumulate into an existing gradient (beta = 1), as linear_bwd_weight does
+        C2 = C0.to(DEV).clone()
+        ops.gemm(Ad, Ad.stride(0), ak, Bd, Bd.stride(0), bk, C2, N + 4, M, N, K, beta=1.0, precision=ops.PREC_TF32)
+        assert_close(C2[:, :N], acc + C0[:, :N].double(), 3e-3, "MN-major pair kernel, beta")
+        assert torch.equal(C2[:, N:].cpu(), C0[:, N:])
+    finally:
+        L.dasa_debug_gemm_pair(1)
+
+
+def test_linear_backward_helpers_tf32_mn_major():
+    """ops.linear_bwd_input / linear_bwd_weight at rollout-sized shapes: the MN-major route equals the transposed-copy route."""
+    gen = g(21)
+    M, N, K = 6000, 4096, 768
+    x, w, dy = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) * 0.05, torch.randn(M, N, generator=gen)
+    xd, wd, dyd = x.to(DEV), w.to(DEV), dy.to(DEV)
+    ops.set_precision("tf32")
+    try:
+        outs = []
+        for flag in (True, False):
+            ops.use_mn_major = flag
+            dx = ops.linear_bwd_input(dyd, wd)
+            dw = torch.zeros(N, K, device=DEV)
+            ops.linear_bwd_weight(dyd, xd, dw, True)
+            outs.append((dx, dw))
+        assert_close(outs[0][0], dy.double() @ w.double(), 3e-3, "dx (MN-major B)")
+        assert_close(outs[0][1], dy.double().t() @ x.double(), 3e-3, "dw (MN-major A, B)")
+        assert_close(outs[0][0], outs[1][0], 1e-5, "dx: MN-major vs transposed copy")
+        assert_close(outs[0][1], outs[1][1], 1e-5, "dw: MN-major vs transposed copy")
+    finally:
+        ops.use_mn_major = True
+        ops.set_precision("fp32")
