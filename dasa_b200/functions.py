@@ -27,18 +27,33 @@ def defer_weight_grads(flag=True):
     _defer = bool(flag)
 
 
-def _wgrad(weight, dy, x, bias=None):
+def _bias_grads(dY, bias, bias2):
+    """db += colsum(dY); a second bias fed by the same dY (nn.LSTM's b_ih / b_hh) reuses the column sums instead of a second
+    pass over dY."""
+    if bias is None or not bias.requires_grad:
+        bias, bias2 = bias2, None
+    if bias is None or not bias.requires_grad:
+        return
+    if bias2 is None or not bias2.requires_grad:
+        ops.colsum(dY, _zeros_like_grad(bias), True)
+        return
+    s = torch.empty_like(bias)
+    ops.colsum(dY, s, False)
+    ops.axpy2d(1.0, s, _zeros_like_grad(bias), accumulate=True)
+    ops.axpy2d(1.0, s, _zeros_like_grad(bias2), accumulate=True)
+
+
+def _wgrad(weight, dy, x, bias=None, bias2=None):
     """dW += dy^T x ; db += colsum(dy) — immediately, or queued until flush_weight_grads()."""
     if not weight.requires_grad:
         return
     if not _defer:
         ops.linear_bwd_weight(dy, x, _zeros_like_grad(weight), True)
-        if bias is not None and bias.requires_grad:
-            ops.colsum(dy, _zeros_like_grad(bias), True)
+        _bias_grads(dy, bias, bias2)
         return
     ent = _queue.get(id(weight))
     if ent is None:
-        ent = _queue[id(weight)] = [weight, bias, [], []]
+        ent = _queue[id(weight)] = [weight, bias, [], [], bias2]
     d2, x2 = ops._rows(dy)[0], ops._rows(x)[0]
     ent[2].append(d2)
     ent[3].append(x2)
@@ -46,12 +61,11 @@ def _wgrad(weight, dy, x, bias=None):
 
 def flush_weight_grads():
     """Run the queued weight-gradient reductions (call once after loss.backward())."""
-    for weight, bias, dys, xs in _queue.values():
+    for weight, bias, dys, xs, bias2 in _queue.values():
         dY = dys[0] if len(dys) == 1 else torch.cat(dys, 0)
         X = xs[0] if len(xs) == 1 else torch.cat(xs, 0)
         ops.linear_bwd_weight(dY, X, _zeros_like_grad(weight), True)
-        if bias is not None and bias.requires_grad:
-            ops.colsum(dY, _zeros_like_grad(bias), True)
+        _bias_grads(dY, bias, bias2)
     _queue.clear()
 
 
@@ -268,8 +282,8 @@ class LSTMCellFn(torch.autograd.Function):
         dc0 = torch.empty(B, H, device=h.device, dtype=torch.float32)
         ops.lstm_pointwise_bwd(None if dh1 is None else dh1.contiguous(), None, None if dc1 is None else dc1.contiguous(),
                                acts, c.contiguous(), c1, dgates, dc0)
-        _wgrad(w_ih, dgates, x, b_ih)
-        _wgrad(w_hh, dgates, h, b_hh)
+        _wgrad(w_ih, dgates, x, b_ih, b_hh)         # db_ih == db_hh: one column sum
+        _wgrad(w_hh, dgates, h)
         dx = ops.linear_bwd_input(dgates, w_ih) if ctx.needs_input_grad[0] else None
         dh = ops.linear_bwd_input(dgates, w_hh) if ctx.needs_input_grad[1] else None
         return dx, dh, (dc0 if ctx.needs_input_grad[2] else None), None, None, None, None
@@ -391,8 +405,8 @@ class BiLSTMFn(torch.autograd.Function):
             # weight gradients: one GEMM each over all L*B rows; x rows for step s are x[:, order[s]]
             xs = x if d == 0 else x.flip(1)
             xs = xs.transpose(0, 1).contiguous()                       # [L, B, In] in step order
-            _wgrad(w_ih, dgates.view(L * B, 4 * H), xs.view(L * B, In), b_ih)
-            _wgrad(w_hh, dgates.view(L * B, 4 * H), hs[d, :L].reshape(L * B, H), b_hh)
+            _wgrad(w_ih, dgates.view(L * B, 4 * H), xs.view(L * B, In), b_ih, b_hh)    # db_ih == db_hh: one column sum
+            _wgrad(w_hh, dgates.view(L * B, 4 * H), hs[d, :L].reshape(L * B, H))
             if need_dx:
                 dxs = ops.linear_bwd_input(dgates.view(L * B, 4 * H), w_ih).view(L, B, In).transpose(0, 1)
                 dx += dxs if d == 0 else dxs.flip(1)

@@ -285,10 +285,31 @@ class NavPolicy:
         self._opt = {"groups": groups, "lr": lr, "sumsq": torch.zeros(1, device=self.device),
                      "coef": torch.ones(1, device=self.device)}
 
-    def optim_step(self, lr=1e-4):
-        """clip_grad_norm_(encoder, 40), clip_grad_norm_(decoder, 40), RMSprop on all four groups (agent_dg.py:1389-1405).
-        Parameters that never received a gradient are skipped, like torch.optim does for grad=None (in the flat layout they
-        carry an all-zero gradient, for which the RMSprop update is exactly zero)."""
+    @staticmethod
+    def lr_lambda(iter_count, warm_steps=1000, decay_start=4000, decay_intervals=2000, lr_decay=0.2):
+        """The multiplier of agent_dg.py:219-227 (README flags --warm_steps 1000 --decay_start 4000 --decay_intervals 2000
+        --lr_decay 0.2): linear warm-up, flat, then a 0.2x step every 2000 iterations."""
+        if warm_steps > 0 and iter_count < warm_steps:
+            return (1.0 + iter_count) / warm_steps
+        if iter_count < decay_start:
+            return 1.0
+        return lr_decay ** ((iter_count - decay_start) // decay_intervals)
+
+    def group_lr(self, name, lr, use_lr_scheduler):
+        """LambdaLR on the decoder, critic and adaIn optimizers; the encoder optimizer has no scheduler (agent_dg.py:230-241).
+        Optimizer step number i (0-based) runs with lr * lr_lambda(i), as torch's LambdaLR does."""
+        if not use_lr_scheduler or name == "encoder":
+            return lr
+        return lr * self.lr_lambda(self.iteration, **self.lr_schedule)
+
+    iteration = 0
+    lr_schedule = {}
+
+    def optim_step(self, lr=1e-4, use_lr_scheduler=False):
+        """clip_grad_norm_(encoder, 40), clip_grad_norm_(decoder, 40), RMSprop on all four groups, then the three LambdaLR
+        schedulers (agent_dg.py:1389-1405). Parameters that never received a gradient are skipped, like torch.optim does for
+        grad=None (in the flat layout they carry an all-zero gradient, for which the RMSprop update is exactly zero).
+        The learning rate is a host scalar: a CUDA graph that contains this call replays with the rate it was captured with."""
         if getattr(self, "_flat", None) is not None:
             o = self._opt
             for g in self._flat:
@@ -298,7 +319,9 @@ class NavPolicy:
                     ops.sumsq(g["flat_g"], o["sumsq"])
                     ops.clip_coef(o["sumsq"], g["clip"], o["coef"])
                     coef = o["coef"]
-                ops.rmsprop_step(g["flat_p"], g["flat_g"], g["flat_sq"], lr, 0.99, 1e-8, 0.0, coef)
+                ops.rmsprop_step(g["flat_p"], g["flat_g"], g["flat_sq"], self.group_lr(g["name"], lr, use_lr_scheduler), 0.99,
+                                 1e-8, 0.0, coef)
+            self.iteration += 1
             Fn.invalidate_weight_caches()       # parameters changed behind autograd's back (raw-pointer update)
             return
         if self._opt is None:
@@ -313,6 +336,8 @@ class NavPolicy:
                     ops.sumsq(p.grad, o["sumsq"])
                 ops.clip_coef(o["sumsq"], g["clip"], o["coef"])
                 coef = o["coef"]
+            glr = self.group_lr(g["name"], lr, use_lr_scheduler)
             for p, sq in live:
-                ops.rmsprop_step(p.data, p.grad, sq, lr, 0.99, 1e-8, 0.0, coef)
+                ops.rmsprop_step(p.data, p.grad, sq, glr, 0.99, 1e-8, 0.0, coef)
+        self.iteration += 1
         Fn.invalidate_weight_caches()

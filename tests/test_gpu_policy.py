@@ -228,6 +228,40 @@ def test_optimizer_step_matches_torch_rmsprop():
         assert_close(q, p, 1e-5, "param %s after step" % k)
 
 
+def test_lr_scheduler_matches_torch_lambdalr():
+    """optim_step(use_lr_scheduler=True): decoder / critic / adaIn follow torch's LambdaLR with the reference's lr_lambda
+    (agent_dg.py:219-241), the encoder keeps the base rate; three consecutive steps against torch.optim on copies."""
+    import copy
+    cfg = SMALL
+    pol = NavPolicy(cfg, synth.policy_state(cfg, 3)).eval()
+    pol.lr_schedule = dict(warm_steps=2, decay_start=2, decay_intervals=1, lr_decay=0.2)     # exercises all three branches
+    dep = DeviceEpisodes(synth.Episodes(3, 2, cfg, seed=9))
+    refs, opts, scheds = {}, {}, {}
+    for name, mod in (("encoder", pol.encoder), ("decoder", pol.decoder), ("adaIn", pol.adaIn)):
+        refs[name] = copy.deepcopy(mod)
+        opts[name] = torch.optim.RMSprop([p for p in refs[name].parameters()], lr=1e-3)
+        if name != "encoder":
+            scheds[name] = torch.optim.lr_scheduler.LambdaLR(opts[name], lambda it: NavPolicy.lr_lambda(it, **pol.lr_schedule))
+    assert [round(NavPolicy.lr_lambda(i), 6) for i in (0, 999, 1000, 3999, 4000, 5999, 6000)] == [0.001, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2]
+    for it in range(4):
+        pol.zero_grad()
+        loss, _, _ = pol.teacher_rollout(dep, 2)
+        loss.backward()
+        for name, mod in (("encoder", pol.encoder), ("decoder", pol.decoder), ("adaIn", pol.adaIn)):
+            for p, q in zip(refs[name].parameters(), mod.parameters()):
+                p.grad = None if (q.grad is None or not q.requires_grad) else q.grad.clone()
+            if name != "adaIn":
+                torch.nn.utils.clip_grad_norm_(refs[name].parameters(), 40.0)
+            opts[name].step()
+            if name in scheds:
+                scheds[name].step()
+        pol.optim_step(1e-3, use_lr_scheduler=True)
+        for name, mod in (("encoder", pol.encoder), ("decoder", pol.decoder), ("adaIn", pol.adaIn)):
+            for (k, p), q in zip(refs[name].named_parameters(), mod.parameters()):
+                if q.grad is not None:
+                    assert_close(q, p, 2e-5, "iteration %d %s.%s" % (it, name, k))
+
+
 def test_tf32_deferred_training_step_close_to_oracle():
     """The benchmarked configuration: tcgen05 TF32 projections (forward AND transposed backward GEMMs) + deferred, batched
     weight-gradient GEMMs. Stated bound for the tensor-core path: 1e-2 relative (north_star); fp32 path stays at 1e-4."""
