@@ -254,16 +254,21 @@ class NavPolicy:
                     p.requires_grad_(False)
                     continue
                 ps.append(p)
-            n = sum(p.numel() for p in ps)
-            flat_p = torch.empty(n, device=self.device, dtype=torch.float32)
-            flat_g = torch.zeros(n, device=self.device, dtype=torch.float32)
-            off = 0
+            # every parameter starts on a 256-byte boundary (a 5-element bias must not knock the weights behind it off the
+            # 16-byte alignment TMA needs: misaligned weights silently fall back to the FFMA GEMM). The padding stays zero in
+            # the parameter, gradient and RMSprop buffers, for which the update is exactly zero.
+            ALIGN = 64
+            offs, n = [], 0
             for p in ps:
+                offs.append(n)
+                n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            flat_p = torch.zeros(n, device=self.device, dtype=torch.float32)
+            flat_g = torch.zeros(n, device=self.device, dtype=torch.float32)
+            for p, off in zip(ps, offs):
                 k = p.numel()
                 flat_p[off:off + k].copy_(p.data.reshape(-1))
                 p.data = flat_p[off:off + k].view_as(p)
                 p.grad = flat_g[off:off + k].view_as(p)
-                off += k
             groups.append({"name": name, "params": ps, "clip": clip, "flat_p": flat_p, "flat_g": flat_g,
                            "flat_sq": torch.zeros_like(flat_p)})
         self._flat = groups
