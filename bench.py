@@ -644,9 +644,36 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
                               "device_seconds": s_secs, "note": "eager launches, event-bracketed: includes launch gaps"}}
 
 
-if __name__ == "__main__":
+def main():
+    """Everything that libraries write to stdout while the benchmark runs (e.g. NCCL's version banner) goes to stderr: stdout
+    carries exactly ONE line, the JSON record."""
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    import builtins
+    orig_print = builtins.print
+
+    def capture_print(*args, **kw):
+        if kw.get("file") in (None, sys.stdout) and len(args) == 1 and isinstance(args[0], str) and args[0].startswith("{"):
+            lines.append(args[0])
+        else:
+            orig_print(*args, **kw)
+    builtins.print = capture_print
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines[-1:]:
+        print(ln, flush=True)
+
+
+if __name__ == "__main__":
+    main()
