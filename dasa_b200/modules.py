@@ -245,14 +245,37 @@ class BAttnDecoderLSTM(nn.Module):
         self.candidate_att_layer = SoftDotAttention(hidden_size, feature_size)
         self.pred_back = pred_back
 
+    def embed_actions(self, actions_all, steps):
+        """The action embeddings of `steps` actions stacked along dim 0 ([steps*B, A] -> [steps*B, E]) in one call: they do
+        not depend on the recurrent state (model.py:504-505), so a teacher-forced rollout hoists them out of its loop.
+        Dropout masks follow the per-step tags 't<i>.dec.act'."""
+        p, tr = self.dropout_ratio, self.training
+        emb = Fn.linear(actions_all, self.embedding[0].weight, self.embedding[0].bias, "tanh")
+        m, s = _source.mask_steps("dec.act", (actions_all.shape[0] // steps, emb.shape[1]), p, tr, emb.device, steps)
+        return Fn.dropout(emb, m, s)
+
+    def candidate_logits_steps(self, h_tilde_all, cand_all, cand_leng_all, steps):
+        """drop(h_tilde) -> candidate_att_layer for `steps` actions at once (model.py:555-559): the logits feed the loss only,
+        never the recurrence, so a teacher-forced rollout evaluates them after its loop as ONE projection over steps*B rows
+        instead of `steps` weight-streaming ones. Dropout masks follow the per-step tags 't<i>.dec.htilde'."""
+        p, tr = self.dropout_ratio, self.training
+        m, s = _source.mask_steps("dec.htilde", (h_tilde_all.shape[0] // steps, h_tilde_all.shape[1]), p, tr,
+                                  h_tilde_all.device, steps)
+        _, logit = self.candidate_att_layer(Fn.dropout(h_tilde_all, m, s), cand_all, output_prob=False,
+                                            cand_leng=cand_leng_all, rgb_channels=self.feature_size - self.angle_feat_size)
+        return logit
+
     def forward(self, action, feature, cand_feat, h_0, prev_h1, c_0, ctx, ctx_mask=None, already_dropfeat=False,
-                cand_leng=None):
+                cand_leng=None, emb=None, want_logit=True):
         """Same contract as the reference; h_0 is ignored there too (model.py:472-474, 514). When not already_dropfeat
         and in training mode the dropped features are written back into the caller's tensors like the reference does
-        (model.py:508, 557). `cand_leng` (int32 [B], optional extension) lets the logits come out already -inf-masked."""
+        (model.py:508, 557). Optional extensions: `cand_leng` (int32 [B]) lets the logits come out already -inf-masked;
+        `emb` = this action's slice of embed_actions(); want_logit=False skips the candidate branch (the caller batches it
+        with candidate_logits_steps) and returns logit = None."""
         A, p, tr = self.angle_feat_size, self.dropout_ratio, self.training
-        emb = Fn.linear(action, self.embedding[0].weight, self.embedding[0].bias, "tanh")
-        emb = _drop(emb, "dec.act", p, tr)
+        if emb is None:
+            emb = Fn.linear(action, self.embedding[0].weight, self.embedding[0].bias, "tanh")
+            emb = _drop(emb, "dec.act", p, tr)
         if not already_dropfeat and tr:
             m, s = _source.mask("dec.feat", feature[..., :-A].shape, self.featdropout, tr, feature.device)
             if m is not None:
@@ -267,6 +290,8 @@ class BAttnDecoderLSTM(nn.Module):
                                        self.lstm.bias_hh)
         h_1_drop = _drop(h_1, "dec.h1", p, tr)
         h_tilde, alpha = self.attention_layer(h_1_drop, ctx, ctx_mask)
+        if not want_logit:
+            return h_1, c_1, None, h_tilde, {}
         h_tilde_drop = _drop(h_tilde, "dec.htilde", p, tr)
         if not already_dropfeat and tr:
             m, s = _source.mask("dec.cand", cand_feat[..., :-A].shape, self.featdropout, tr, cand_feat.device)

@@ -143,18 +143,23 @@ class NavPolicy:
             ctx_steps = ctx_all.view(T, B, L, -1).unbind(0)          # unbind: one stacked gradient instead of T zero-filled ones
             df_steps = df_all.view(T, B, cfg.views, cfg.feat).unbind(0)
             cand_steps = candg_all.view(T, B, nc, cfg.feat).unbind(0)
+            # Off the recurrent path, hence batched over the T actions: the action embeddings (before the loop) and the
+            # candidate logits + cross entropy (after it). The loop keeps only what h_tilde_t -> h_tilde_{t+1} needs.
+            emb_steps = self.decoder.embed_actions(ep.input_a_t[:T].reshape(T * B, -1), T).view(T, B, -1).unbind(0)
+            h_tildes = []
             for t in range(T):
                 if tag_steps:
                     src.prefix = base_prefix + "t%d." % t
                 prev_h1, c_0 = (en_h, en_c) if carry is None else carry
-                h_t, c_t, logit, h1, _ = self.decoder(ep.input_a_t[t], df_steps[t], cand_steps[t], prev_h1, prev_h1, c_0,
-                                                      ctx_steps[t], ep.seq_mask, already_dropfeat=True, cand_leng=ep.cand_leng[t])
+                h_t, c_t, _, h1, _ = self.decoder(None, df_steps[t], None, prev_h1, prev_h1, c_0, ctx_steps[t], ep.seq_mask,
+                                                  already_dropfeat=True, emb=emb_steps[t], want_logit=False)
                 carry = (h1, c_t)
-                loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.target_at(t), cfg.ignore_id)
-                total = loss_t if total is None else total + loss_t
-                logits.append(logit)
-                actions.append(a_t)
+                h_tildes.append(h1)
             src.prefix = base_prefix
+            logit_all = self.decoder.candidate_logits_steps(torch.cat(h_tildes, 0), candg_all, ep.cand_leng[:T].reshape(T * B), T)
+            total, a_all = Fn.MaskedCEFn.apply(logit_all, ep.target[:T].reshape(T * B), cfg.ignore_id)
+            logits = list(logit_all.view(T, B, nc).unbind(0))
+            actions = list(a_all.view(T, B).unbind(0))
             return total * (ml_weight / ep.B), logits, actions
         # the instruction-only language stack of all T actions in one batched pass (per-action dropout masks preserved)
         lang_all = self.encoder.language_for_rollout(ep.seq, ep.seq_mask, T, ep.seq_lengths_host) if self.batch_language else None
