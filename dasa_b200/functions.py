@@ -171,30 +171,38 @@ class ChannelModulateFn(torch.autograd.Function):
 
 
 class ShiftAttnFn(torch.autograd.Function):
-    """ShiftSoftDotAttention, output_tilde=False (model.py:318-353): returns (weighted_context, pre-shift softmax)."""
+    """ShiftSoftDotAttention with output_tilde=False (model.py:318-353): returns (weighted_context, pre-shift softmax).
+    linear_in and linear_shift read the same h, so their weights are stacked ([F + k (padded to 32), H], cached until the
+    parameters change) and ONE projection produces the attention target and the shift-kernel logits; the backward writes dt
+    and dkappa into one buffer and one GEMM returns dh."""
 
     @staticmethod
     def forward(ctx, h, context, w_in, w_shift, b_shift, headings):
-        t = ops.linear_fwd(h, w_in)
-        kl = ops.linear_fwd(h, w_shift, b_shift)
-        k = w_shift.shape[0]
+        F_all, k = w_in.shape[0], w_shift.shape[0]
+        Wc, bc = ops.stacked_weights((w_in, w_shift), 0, 32, (None, b_shift))
+        tk = ops.linear_fwd(h, Wc, bc)                                    # [B, F + k + pad]
+        t, kl = tk[:, :F_all], tk[:, F_all:F_all + k]
         wc, p, q, kappa = ops.row_attention_fwd(context, t, None, k, headings, kl)
         ctx.k, ctx.headings = k, headings
-        ctx.save_for_backward(h, context, w_in, w_shift, b_shift, t, p, q, kappa)
+        ctx.save_for_backward(h, context, w_in, w_shift, b_shift, tk, p, q, kappa)
         ctx.mark_non_differentiable(p)
         return wc, p
 
     @staticmethod
     def backward(ctx, dwc, _dp):
-        h, context, w_in, w_shift, b_shift, t, p, q, kappa = ctx.saved_tensors
+        h, context, w_in, w_shift, b_shift, tk, p, q, kappa = ctx.saved_tensors
+        F_all, k = w_in.shape[0], ctx.k
         need_dctx = ctx.needs_input_grad[1]
-        dctx, dt, dkl = ops.row_attention_bwd(context, t, p, q, kappa, dwc.contiguous(), ctx.k, ctx.headings, need_dctx)
+        dtk = torch.zeros(tk.shape, device=tk.device, dtype=torch.float32)       # padding columns must be exact zeros
+        dt, dkl = dtk[:, :F_all], dtk[:, F_all:F_all + k]
+        dctx, _, _ = ops.row_attention_bwd(context, tk[:, :F_all], p, q, kappa, dwc.contiguous(), k, ctx.headings, need_dctx,
+                                           dt=dt, dkl=dkl)
         _wgrad(w_in, dt, h)
         _wgrad(w_shift, dkl, h, b_shift)
         dh = None
         if ctx.needs_input_grad[0]:
-            dh = ops.linear_bwd_input(dt, w_in)
-            ops.linear_bwd_input(dkl, w_shift, out=dh, beta=1.0)
+            Wc, _ = ops.stacked_weights((w_in, w_shift), 0, 32, (None, b_shift))
+            dh = ops.linear_bwd_input(dtk, Wc)
         return dh, dctx, None, None, None, None
 
 
@@ -260,33 +268,38 @@ class CandLogitsFn(torch.autograd.Function):
 
 
 class LSTMCellFn(torch.autograd.Function):
-    """nn.LSTMCell (model.py:437,514): two gate GEMMs (x W_ih^T, h W_hh^T accumulated) + fused pointwise."""
+    """nn.LSTMCell (model.py:437,514) on the concatenated input xh = [x ; h] (the caller builds it with the one torch.cat it
+    needs anyway) against the column-stacked weight [W_ih | W_hh] (cached until the parameters change): ONE gate GEMM forward
+    and ONE for d[x ; h] backward instead of two each, + the fused pointwise kernels."""
 
     @staticmethod
-    def forward(ctx, x, h, c, w_ih, w_hh, b_ih, b_hh):
-        B, H = h.shape
-        gates = ops.linear_fwd(x, w_ih)
-        ops.linear_fwd(h, w_hh, out=gates, beta=1.0)
-        h1 = torch.empty(B, H, device=h.device, dtype=torch.float32)
-        c1 = torch.empty(B, H, device=h.device, dtype=torch.float32)
-        acts = torch.empty(B, 4 * H, device=h.device, dtype=torch.float32)
+    def forward(ctx, xh, c, w_ih, w_hh, b_ih, b_hh):
+        B, H = c.shape
+        Wc, _ = ops.stacked_weights((w_ih, w_hh), 1)
+        gates = ops.linear_fwd(xh, Wc)
+        h1 = torch.empty(B, H, device=c.device, dtype=torch.float32)
+        c1 = torch.empty(B, H, device=c.device, dtype=torch.float32)
+        acts = torch.empty(B, 4 * H, device=c.device, dtype=torch.float32)
         ops.lstm_pointwise_fwd(gates, None, b_ih, b_hh, c.contiguous(), None, h1, c1, None, acts)
-        ctx.save_for_backward(x, h, c, w_ih, w_hh, b_ih, b_hh, acts, c1)
+        ctx.save_for_backward(xh, c, w_ih, w_hh, b_ih, b_hh, acts, c1)
         return h1, c1
 
     @staticmethod
     def backward(ctx, dh1, dc1):
-        x, h, c, w_ih, w_hh, b_ih, b_hh, acts, c1 = ctx.saved_tensors
-        B, H = h.shape
-        dgates = torch.empty(B, 4 * H, device=h.device, dtype=torch.float32)
-        dc0 = torch.empty(B, H, device=h.device, dtype=torch.float32)
+        xh, c, w_ih, w_hh, b_ih, b_hh, acts, c1 = ctx.saved_tensors
+        B, H = c.shape
+        n_x = w_ih.shape[1]
+        dgates = torch.empty(B, 4 * H, device=c.device, dtype=torch.float32)
+        dc0 = torch.empty(B, H, device=c.device, dtype=torch.float32)
         ops.lstm_pointwise_bwd(None if dh1 is None else dh1.contiguous(), None, None if dc1 is None else dc1.contiguous(),
                                acts, c.contiguous(), c1, dgates, dc0)
-        _wgrad(w_ih, dgates, x, b_ih, b_hh)         # db_ih == db_hh: one column sum
-        _wgrad(w_hh, dgates, h)
-        dx = ops.linear_bwd_input(dgates, w_ih) if ctx.needs_input_grad[0] else None
-        dh = ops.linear_bwd_input(dgates, w_hh) if ctx.needs_input_grad[1] else None
-        return dx, dh, (dc0 if ctx.needs_input_grad[2] else None), None, None, None, None
+        _wgrad(w_ih, dgates, xh[:, :n_x], b_ih, b_hh)         # db_ih == db_hh: one column sum
+        _wgrad(w_hh, dgates, xh[:, n_x:])
+        dxh = None
+        if ctx.needs_input_grad[0]:
+            Wc, _ = ops.stacked_weights((w_ih, w_hh), 1)
+            dxh = ops.linear_bwd_input(dgates, Wc)
+        return dxh, (dc0 if ctx.needs_input_grad[1] else None), None, None, None, None
 
 
 def invalidate_weight_caches():

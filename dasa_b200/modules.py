@@ -285,9 +285,8 @@ class BAttnDecoderLSTM(nn.Module):
                 feature = dropped
         h_prev_drop = _drop(prev_h1, "dec.h_prev", p, tr)
         attn_feat, _ = self.feat_att_layer(h_prev_drop, feature, output_tilde=False)
-        x = torch.cat((emb, attn_feat), 1)
-        h_1, c_1 = Fn.LSTMCellFn.apply(x, prev_h1, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih,
-                                       self.lstm.bias_hh)
+        xh = torch.cat((emb, attn_feat, prev_h1), 1)        # [x ; h]: one gate GEMM against [W_ih | W_hh]
+        h_1, c_1 = Fn.LSTMCellFn.apply(xh, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih, self.lstm.bias_hh)
         h_1_drop = _drop(h_1, "dec.h1", p, tr)
         h_tilde, alpha = self.attention_layer(h_1_drop, ctx, ctx_mask)
         if not want_logit:

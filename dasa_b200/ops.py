@@ -137,6 +137,43 @@ def transposed_weight(w):
     return wt
 
 
+_stack_cache = {}
+
+
+def stacked_weights(ws, dim, pad_to=1, biases=None):
+    """Several weights concatenated into one GEMM operand, cached until any of them changes (like transposed_weight):
+      dim = 0: rows stacked ([N1+N2(+pad), K]: one projection producing several outputs), zero rows up to a multiple of pad_to;
+      dim = 1: columns stacked ([N, K1+K2]: one projection over concatenated inputs).
+    `biases` (dim = 0 only): per-weight bias or None -> the matching stacked bias vector (zeros where None / padding).
+    Returns (W, bias | None). Gradients are NOT routed through the stack: callers accumulate into the original parameters."""
+    key = tuple(id(w) for w in ws) + (dim,)
+    tag = tuple((w._version, w.data_ptr()) for w in ws) + (weights_epoch,) + \
+        (tuple((b._version, b.data_ptr()) if b is not None else None for b in biases) if biases else ())
+    hit = _stack_cache.get(key)
+    if hit is not None and hit[0] == tag and all(r() is w for r, w in zip(hit[3], ws)):
+        return hit[1], hit[2]
+    if len(_stack_cache) > 64:
+        for k in [k for k, v in _stack_cache.items() if any(r() is None for r in v[3])]:
+            del _stack_cache[k]
+    with torch.no_grad():
+        if dim == 1:
+            W = torch.cat([w.detach() for w in ws], 1).contiguous()
+            bias = None
+        else:
+            n = sum(w.shape[0] for w in ws)
+            npad = (n + pad_to - 1) // pad_to * pad_to
+            W = torch.zeros(npad, ws[0].shape[1], device=ws[0].device, dtype=torch.float32)
+            bias = torch.zeros(npad, device=ws[0].device, dtype=torch.float32) if biases else None
+            off = 0
+            for i, w in enumerate(ws):
+                W[off:off + w.shape[0]].copy_(w.detach())
+                if biases and biases[i] is not None:
+                    bias[off:off + w.shape[0]].copy_(biases[i].detach())
+                off += w.shape[0]
+    _stack_cache[key] = (tag, W, bias, [weakref.ref(w) for w in ws])
+    return W, bias
+
+
 def _tc_ok(*dims):
     return _precision == PREC_TF32 and all(d >= 32 and d % 4 == 0 for d in dims)
 
@@ -321,12 +358,17 @@ def row_attention_fwd(ctx, t, mask=None, shift_k=0, headings=12, kappa_logits=No
     return wc, attn, q, kappa
 
 
-def row_attention_bwd(ctx, t, attn, q, kappa, dwc, shift_k=0, headings=12, need_dctx=True, dctx=None, accumulate=False):
+def row_attention_bwd(ctx, t, attn, q, kappa, dwc, shift_k=0, headings=12, need_dctx=True, dctx=None, accumulate=False,
+                      dt=None, dkl=None):
+    """dt / dkl (optional): caller-owned output views (e.g. column ranges of one buffer that feeds a single stacked GEMM)."""
     B, rows, D = ctx.shape
     if need_dctx and dctx is None:
         dctx = torch.empty(B, rows, D, device=ctx.device, dtype=torch.float32)
-    dt = torch.empty(B, D, device=ctx.device, dtype=torch.float32)
-    dkl = torch.empty(B, shift_k, device=ctx.device, dtype=torch.float32) if shift_k > 0 else None
+    if dt is None:
+        dt = torch.empty(B, D, device=ctx.device, dtype=torch.float32)
+    if dkl is None:
+        dkl = torch.empty(B, shift_k, device=ctx.device, dtype=torch.float32) if shift_k > 0 else None
+    assert dt.stride(1) == 1 and (dkl is None or dkl.stride(1) == 1)
     assert dwc.stride(1) == 1
     call("dasa_row_attention_bwd", _p(ctx), ctx.stride(1), ctx.stride(0), B, rows, D, _p(t), t.stride(0), _p(attn), _p(q),
          _p(kappa), shift_k, headings, _p(dwc), dwc.stride(0), _p(dctx), dctx.stride(1) if dctx is not None else 0,

@@ -147,11 +147,12 @@ class NavPolicy:
             # candidate logits + cross entropy (after it). The loop keeps only what h_tilde_t -> h_tilde_{t+1} needs.
             emb_steps = self.decoder.embed_actions(ep.input_a_t[:T].reshape(T * B, -1), T).view(T, B, -1).unbind(0)
             h_tildes = []
+            mask_u8 = ep.seq_mask.to(torch.uint8)            # converted once (the attention kernel reads uint8 pad flags)
             for t in range(T):
                 if tag_steps:
                     src.prefix = base_prefix + "t%d." % t
                 prev_h1, c_0 = (en_h, en_c) if carry is None else carry
-                h_t, c_t, _, h1, _ = self.decoder(None, df_steps[t], None, prev_h1, prev_h1, c_0, ctx_steps[t], ep.seq_mask,
+                h_t, c_t, _, h1, _ = self.decoder(None, df_steps[t], None, prev_h1, prev_h1, c_0, ctx_steps[t], mask_u8,
                                                   already_dropfeat=True, emb=emb_steps[t], want_logit=False)
                 carry = (h1, c_t)
                 h_tildes.append(h1)

@@ -285,7 +285,8 @@ def test_lstm_cell_fwd_bwd(cfg, B):
     (h1 * dh1).sum().add((c1 * dc1).sum()).backward()
     P = {k: v.detach().to(DEV).requires_grad_(True) for k, v in st.items()}
     xd, hd, cd = (t.detach().to(DEV).requires_grad_(True) for t in (x, h, c))
-    h2, c2 = Fn.LSTMCellFn.apply(xd, hd, cd, P["lstm.weight_ih"], P["lstm.weight_hh"], P["lstm.bias_ih"], P["lstm.bias_hh"])
+    xh = torch.cat((xd, hd), 1)                                   # the decoder's one concatenation [emb ; attn_feat ; prev_h1]
+    h2, c2 = Fn.LSTMCellFn.apply(xh, cd, P["lstm.weight_ih"], P["lstm.weight_hh"], P["lstm.bias_ih"], P["lstm.bias_hh"])
     assert_close(h2, h1, 1e-4, "h1")
     assert_close(c2, c1, 1e-4, "c1")
     torch.autograd.backward([h2, c2], [dh1.to(DEV), dc1.to(DEV)])
