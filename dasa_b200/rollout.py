@@ -281,6 +281,82 @@ class NavPolicy:
         self._opt = {"sumsq": torch.zeros(1, device=self.device), "coef": torch.ones(1, device=self.device)}
         return groups
 
+    # ------------------------------------------------------------------------------------- checkpoints (agent_dg.py:1466-1510)
+    def _named_groups(self):
+        names = ("encoder", "decoder", "critic", "adaIn")
+        return [(n, m) for n, m in zip(names, self.models) if m is not None]
+
+    def _square_avg(self, name, p, index):
+        """RMSprop second-moment tensor of parameter `p` (flat layout: a view of the group's flat buffer; else the list)."""
+        if getattr(self, "_flat", None) is not None:
+            for g in self._flat:
+                if g["name"] == name:
+                    for q in g["params"]:
+                        if q is p:
+                            off = (p.data_ptr() - g["flat_p"].data_ptr()) // 4
+                            return g["flat_sq"][off:off + p.numel()].view_as(p)
+            return None
+        if self._opt is not None and "groups" in self._opt:
+            for g in self._opt["groups"]:
+                if g["name"] == name:
+                    for q, sq in zip(g["params"], g["sq"]):
+                        if q is p:
+                            return sq
+        return None
+
+    def save(self, epoch, path, lr=1e-4):
+        """Seq2SeqAgent.save (agent_dg.py:1466-1487): {name: {'epoch', 'state_dict', 'optimizer'}} for encoder / decoder /
+        critic / adaIn, with the optimizer entry in torch.optim.RMSprop's state_dict layout (param index = position in
+        module.parameters(), 'square_avg' + 'step' per parameter that has been updated), so the reference's load() with
+        --loadOptim accepts it."""
+        import os
+        the_dir, _ = os.path.split(path)
+        if the_dir:
+            os.makedirs(the_dir, exist_ok=True)
+        states = {}
+        for name, model in self._named_groups():
+            params = list(model.parameters())
+            state = {}
+            for i, p in enumerate(params):
+                sq = self._square_avg(name, p, i) if self.iteration > 0 else None
+                if sq is not None and p.requires_grad:
+                    state[i] = {"step": torch.tensor(float(self.iteration)), "square_avg": sq.detach().clone()}
+            group = {"lr": self.group_lr(name, lr, bool(self.lr_schedule)), "momentum": 0, "alpha": 0.99, "eps": 1e-08,
+                     "centered": False, "weight_decay": 0, "capturable": False, "foreach": None, "maximize": False,
+                     "differentiable": False, "params": list(range(len(params)))}
+            states[name] = {"epoch": epoch + 1,
+                            "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+                            "optimizer": {"state": state, "param_groups": [group]}}
+        torch.save(states, path)
+
+    def load(self, path, load_optim=False):
+        """Seq2SeqAgent.load (agent_dg.py:1489-1510): parameters (and, with load_optim = --loadOptim, the RMSprop second
+        moments and the step count) from a checkpoint written by the reference or by save(). Returns the epoch."""
+        states = torch.load(path, map_location="cpu", weights_only=False)
+        for name, model in self._named_groups():
+            if name not in states:
+                continue
+            state = model.state_dict()
+            if set(state.keys()) != set(states[name]["state_dict"].keys()):
+                print("NOTICE: DIFFERENT KEYS IN THE LISTEREN")
+            with torch.no_grad():       # copy in place: parameters may be views of the flat buffers
+                for k, v in states[name]["state_dict"].items():
+                    if k in state:
+                        state[k].copy_(v)
+            if load_optim:
+                opt = states[name]["optimizer"]
+                if getattr(self, "_flat", None) is None and (self._opt is None or "groups" not in self._opt):
+                    self._build_optimizer(1e-4)
+                for i, p in enumerate(model.parameters()):
+                    ent = opt["state"].get(i)
+                    sq = self._square_avg(name, p, i)
+                    if ent is not None and sq is not None:
+                        with torch.no_grad():
+                            sq.copy_(ent["square_avg"])
+                        self.iteration = max(self.iteration, int(float(ent["step"])))
+        Fn.invalidate_weight_caches()
+        return states["encoder"]["epoch"] - 1
+
     def grad_buffers(self):
         return [g["flat_g"] for g in self._flat]
 

@@ -66,3 +66,62 @@ def test_decoder_eval_does_not_mutate_inputs(ref_mods):
     with torch.no_grad():
         dec(a_t, f_t, cand, h, h, h, ctx, ep.seq_mask)
     assert torch.equal(f_t, f0) and torch.equal(cand, c0)
+
+
+def test_checkpoint_roundtrip_with_reference_agent(tmp_path):
+    """Seq2SeqAgent.save / load (agent_dg.py:1466-1510), run UNMODIFIED on the reference modules, against NavPolicy.save / load:
+    a reference-written snapshot loads into the drop-in modules (parameters and RMSprop state) and a snapshot written here
+    loads through the reference's own load() with --loadOptim."""
+    from dasa_b200.rollout import NavPolicy
+    from oracle.make_golden import build_reference_modules
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = load_reference.load()
+    st = synth.policy_state(SMALL, 4)
+    enc, dec, cri, ada = build_reference_modules(ref, SMALL, st)
+    agent = object.__new__(ref.agent_dg.Seq2SeqAgent)
+    agent.encoder, agent.decoder, agent.critic, agent.adaIn = enc, dec, cri, ada
+    mk = lambda m: torch.optim.RMSprop(m.parameters(), lr=1e-4)
+    agent.encoder_optimizer, agent.decoder_optimizer, agent.critic_optimizer, agent.adaIn_optimizer = mk(enc), mk(dec), mk(cri), mk(ada)
+    # give the optimizers some state: one step on synthetic gradients of the trainable tensors
+    gen = torch.Generator().manual_seed(0)
+    for m in (dec, cri, ada):
+        for p in m.parameters():
+            p.grad = torch.randn(p.shape, generator=gen) * 0.01
+    for k, p in enc.named_parameters():
+        if not k.startswith("bert."):
+            p.grad = torch.randn(p.shape, generator=gen) * 0.01
+    for o in (agent.encoder_optimizer, agent.decoder_optimizer, agent.critic_optimizer, agent.adaIn_optimizer):
+        o.step()
+    ref.args.adaIn_type, ref.args.loadOptim = "channel", True
+    path = str(tmp_path / "snap" / "ref_agent")
+    agent.save(7, path)                                                        # the reference's own save()
+
+    pol = NavPolicy(SMALL, synth.policy_state(SMALL, 9), "cpu")                # different weights, CPU-resident modules
+    pol.flatten_parameters()
+    assert pol.load(path, load_optim=True) == 7
+    for name, m_ref, m_new in (("encoder", enc, pol.encoder), ("decoder", dec, pol.decoder), ("critic", cri, pol.critic),
+                               ("adaIn", ada, pol.adaIn)):
+        a, b = m_ref.state_dict(), m_new.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (name, k)
+    sq_ref = agent.decoder_optimizer.state_dict()["state"]
+    for i, p in enumerate(pol.decoder.parameters()):
+        if i in sq_ref:
+            assert torch.equal(pol._square_avg("decoder", p, i), sq_ref[i]["square_avg"])
+    assert pol.iteration == 1
+
+    # and back: a snapshot written here through the reference's load()
+    with torch.no_grad():
+        for p in pol.decoder.parameters():
+            p.add_(0.5)
+    path2 = str(tmp_path / "snap" / "new_agent")
+    pol.save(11, path2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        assert agent.load(path2) == 11                                         # the reference's own load(), --loadOptim
+    for (k, a), b in zip(dec.state_dict().items(), pol.decoder.state_dict().values()):
+        assert torch.equal(a, b), k
+    sq_new = agent.decoder_optimizer.state_dict()["state"]
+    for i, p in enumerate(pol.decoder.parameters()):
+        if i in sq_new and pol._square_avg("decoder", p, i) is not None and p.requires_grad and i in sq_ref:
+            assert torch.equal(sq_new[i]["square_avg"], pol._square_avg("decoder", p, i))
