@@ -324,6 +324,8 @@ def run_ours(args):
         """Whole rollout (forward, backward, deferred weight grads, and for N=1 clip + RMSprop) as ONE CUDA graph. With
         make_ep the episodes themselves (device environment: T x observe + step kernels) are built inside the graph."""
         Fn.invalidate_weight_caches()                       # cached transposes must be rebuilt INSIDE the graph every replay
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()                            # the eager warm-up's cached blocks cannot serve the graph's private pool
         g = torch.cuda.CUDAGraph()
         l0 = lib.launches
         with torch.cuda.graph(g):
@@ -420,7 +422,15 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # dominant kernel of the step: the tcgen05/FFMA GEMM family streams the policy's weights; timed live with CUDA events
+    # dominant kernel of the step: the tcgen05/FFMA GEMM family streams the policy's weights; timed live with CUDA events.
+    # The captured graphs (and their private memory pools) are released first: at 512 episodes/GPU a graph pool and an eager
+    # rollout do not fit the 180 GB together.
+    import gc
+    for k in [k for k in state if k.startswith("graph") or k.startswith("loss")]:
+        state[k] = None
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     roof = dominant_kernel_roofline(pol, ep_res, src, peaks, peak_src)
     extra = {} if args.skip_micro else micro_rooflines(peak_gbs)
     cpu = None
