@@ -178,6 +178,47 @@ extern "C" int dasa_policy_sample_bwd(const float* probs, const int64_t* action,
   return dasa_check_launch("policy_sample_bwd_kernel");
 }
 
+// Speaker greedy decode, word selection of one step (speaker.py:318-343): logits[:, unk] = -inf; word = argmax (first index
+// on ties, like torch.max); the emitted word is <PAD> for sequences that had already ended; ended |= (emitted == <EOS>).
+// One warp per sequence. next_word feeds the next decoder step (the raw argmax, as the reference feeds `word`).
+__global__ void __launch_bounds__(128) speaker_select_kernel(const float* __restrict__ logit, int64_t ld, int B, int V, int unk,
+                                                             int pad, int eos, uint8_t* __restrict__ ended,
+                                                             int64_t* __restrict__ next_word, int64_t* __restrict__ emitted,
+                                                             int64_t ld_emitted) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* z = logit + (int64_t)b * ld;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int j = lane; j < V; j += 32) {
+    const float v = (j == unk) ? -INFINITY : z[j];
+    if (v > mx || (v == mx && j < arg)) { mx = v; arg = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  if (lane == 0) {
+    const bool was_ended = ended[b] != 0;
+    const int w = was_ended ? pad : arg;
+    next_word[b] = arg;
+    emitted[(int64_t)b * ld_emitted] = w;
+    ended[b] = (uint8_t)(was_ended || w == eos);
+  }
+}
+
+extern "C" int dasa_speaker_select(const float* logit, int64_t ld, int B, int V, int unk, int pad, int eos, uint8_t* ended,
+                                   int64_t* next_word, int64_t* emitted, int64_t ld_emitted, void* stream) {
+  if (B <= 0) return DASA_OK;
+  if (V <= 0) return DASA_ERR_BAD_SHAPE;
+  speaker_select_kernel<<<(unsigned)dasa_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(logit, ld, B, V, unk, pad, eos, ended, next_word,
+                                                                                    emitted, ld_emitted);
+  return dasa_check_launch("speaker_select_kernel");
+}
+
 extern "C" int dasa_nav_reward(const int64_t* action, const int32_t* cand_leng, int ignore_id, const float* dist,
                                const float* last_dist, uint8_t* ended, float* reward, float* mask, int B, void* stream) {
   if (B <= 0) return DASA_OK;

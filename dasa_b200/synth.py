@@ -132,6 +132,51 @@ def encoder_state(cfg: PolicyConfig = FULL, seed=0):
     return sd
 
 
+def speaker_state(feat, rnn_dim=512, wemb=256, vocab=992, seed=0):
+    """SpeakerEncoder / SpeakerDecoder parameters (model.py:984-1052) -> (encoder state_dict, decoder state_dict)."""
+    g, enc, dec = _gen(7000 + seed), OrderedDict(), OrderedDict()
+    Hh = rnn_dim // 2
+
+    def lstm(sd, pre, n_in, H, sfxs):
+        for sfx in sfxs:
+            sd[pre + "weight_ih_l0" + sfx] = torch.randn(4 * H, n_in, generator=g) / math.sqrt(n_in)
+            sd[pre + "weight_hh_l0" + sfx] = torch.randn(4 * H, H, generator=g) / math.sqrt(H)
+            sd[pre + "bias_ih_l0" + sfx] = torch.randn(4 * H, generator=g) * 0.02
+            sd[pre + "bias_hh_l0" + sfx] = torch.randn(4 * H, generator=g) * 0.02
+    lstm(enc, "lstm.", feat, Hh, ("", "_reverse"))
+    _lin(enc, g, "attention_layer.linear_in", feat, rnn_dim, bias=False, gain=0.5)
+    _lin(enc, g, "attention_layer.linear_out", rnn_dim, rnn_dim + feat, bias=False)
+    lstm(enc, "post_lstm.", rnn_dim, Hh, ("", "_reverse"))
+    dec["embedding.weight"] = torch.randn(vocab, wemb, generator=g) * 0.3
+    dec["embedding.weight"][0].zero_()                      # padding_idx = <PAD> = 0
+    lstm(dec, "lstm.", wemb, rnn_dim, ("",))
+    _lin(dec, g, "attention_layer.linear_in", rnn_dim, rnn_dim, bias=False, gain=1.0)
+    _lin(dec, g, "attention_layer.linear_out", rnn_dim, 2 * rnn_dim, bias=False)
+    _lin(dec, g, "projection", vocab, rnn_dim, gain=3.0)
+    _lin(dec, g, "baseline_projection.0", 128, rnn_dim)
+    _lin(dec, g, "baseline_projection.3", 1, 128)
+    return enc, dec
+
+
+def speaker_inputs(B, L, cfg: PolicyConfig = FULL, seed=0):
+    """Shortest-path features as Speaker.from_shortest_path returns them (speaker.py:150-190): can_feats [B, L, F] (the view
+    row of the taken candidate), img_feats [B, L, 36, F], path lengths [B] (sorted like the instruction batch is not required)."""
+    g = _gen(8000 + seed)
+    C, A, V, F = cfg.rgb_size, cfg.angle_size, cfg.views, cfg.feat
+    img = torch.empty(B, L, V, F)
+    img[..., :C] = resnet_like((B, L, V, C), g)
+    base = torch.randint(0, V, (B * L,), generator=g)
+    img[..., C:] = view_angle_features(base, cfg).view(B, L, V, A)
+    pick = torch.randint(0, V, (B, L), generator=g)
+    can = torch.gather(img, 2, pick[:, :, None, None].expand(B, L, 1, F)).squeeze(2).clone()
+    lengths = torch.randint(max(2, L // 2), L + 1, (B,), generator=g)
+    lengths[0] = L
+    for b in range(B):                                       # padded steps are zeros (speaker.py:181-186)
+        can[b, int(lengths[b]):] = 0
+        img[b, int(lengths[b]):] = 0
+    return can, img, lengths
+
+
 def policy_state(cfg: PolicyConfig = FULL, seed=0, adain_kind="channel"):
     return {"adaIn": adain_state(cfg, seed, adain_kind), "decoder": decoder_state(cfg, seed),
             "critic": critic_state(cfg, seed), "encoder": encoder_state(cfg, seed)}

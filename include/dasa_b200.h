@@ -300,6 +300,10 @@ int dasa_policy_sample_bwd(const float* probs, const int64_t* action, const floa
  * END by dist < 3, else sign of the distance reduction; mask = 0 for episodes that had already ended; ended |= END.   */
 int dasa_nav_reward(const int64_t* action, const int32_t* cand_leng, int ignore_id, const float* dist,
                     const float* last_dist, uint8_t* ended, float* reward, float* mask, int B, void* stream);
+/* Speaker greedy decode (speaker.py:318-343), word selection of one step: logits[:, unk] = -inf; word = argmax (first index on
+ * ties); emitted[b * ld_emitted] = ended[b] ? pad : word; next_word[b] = word (fed to the next step); ended |= emitted == eos. */
+int dasa_speaker_select(const float* logit, int64_t ld, int B, int V, int unk, int pad, int eos, uint8_t* ended,
+                        int64_t* next_word, int64_t* emitted, int64_t ld_emitted, void* stream);
 /* A2C epilogue (agent_dg.py:943-999) over [T,B] stacks: R_b = ended_b ? 0 : last_value_b; for t = T-1..0:
  *   R = R*gamma + reward_t; a = R - value_t; loss += sum_b (-logp_t a m_t + 0.5 a^2 m_t - ent_coef ent_t m_t); total += m_t;
  * loss /= total (normalize 1) | B (2) | 1 (0). Also writes dloss/dlogp, dloss/dent, dloss/dvalue (the advantage in the

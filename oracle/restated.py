@@ -477,3 +477,64 @@ def sample_rollout(state, cfg, episodes, T, actions, drops=NoDrop(), gamma=0.9, 
     loss, total = a2c_epilogue(logps, ents, values, last_value, rewards, masks, ended, gamma, ent_coef, normalize)
     return loss, {"logits": logits, "logps": logps, "ents": ents, "values": values, "last_value": last_value,
                   "rewards": rewards, "masks": masks, "ended": ended, "total": total}
+
+
+# ------------------------------------------------------------------------------------ speaker inference
+def _lstm_dir(sd, pre, sfx, x, h0=None, c0=None, reverse=False):
+    """One direction of a one-layer batch_first nn.LSTM over full-length sequences, step by step with lstm_cell."""
+    B, L, _ = x.shape
+    H = sd[pre + "weight_hh_l0" + sfx].shape[1]
+    h = torch.zeros(B, H) if h0 is None else h0
+    c = torch.zeros(B, H) if c0 is None else c0
+    out = [None] * L
+    for l in (range(L - 1, -1, -1) if reverse else range(L)):
+        h, c = lstm_cell(sd[pre + "weight_ih_l0" + sfx], sd[pre + "weight_hh_l0" + sfx], sd[pre + "bias_ih_l0" + sfx],
+                         sd[pre + "bias_hh_l0" + sfx], x[:, l], h, c)
+        out[l] = h
+    return torch.stack(out, 1), h, c
+
+
+def speaker_encoder(sd, action_embeds, feature):
+    """model.SpeakerEncoder.forward in eval mode (model.py:1005-1036): bi-LSTM over the taken-candidate features, soft-dot
+    attention of every step's state over that step's 36 views, post bi-LSTM. action_embeds [B, L, F], feature [B, L, 36, F]."""
+    B, L, Fd = action_embeds.shape
+    ctx = torch.cat((_lstm_dir(sd, "lstm.", "", action_embeds)[0], _lstm_dir(sd, "lstm.", "_reverse", action_embeds, reverse=True)[0]), 2)
+    hidden = ctx.shape[2]
+    x, _ = soft_dot_attention(sd, "attention_layer.", ctx.reshape(B * L, hidden), feature.reshape(B * L, -1, Fd))
+    x = x.view(B, L, hidden)
+    return torch.cat((_lstm_dir(sd, "post_lstm.", "", x)[0], _lstm_dir(sd, "post_lstm.", "_reverse", x, reverse=True)[0]), 2)
+
+
+def speaker_decoder_step(sd, word, ctx, ctx_mask, h0, c0):
+    """model.SpeakerDecoder.forward for one word per sequence in eval mode (model.py:1054-1078): word [B] int64,
+    h0 / c0 [B, H] -> (logit [B, V], h1, c1)."""
+    embeds = sd["embedding.weight"][word]
+    h1, c1 = lstm_cell(sd["lstm.weight_ih_l0"], sd["lstm.weight_hh_l0"], sd["lstm.bias_ih_l0"], sd["lstm.bias_hh_l0"], embeds, h0, c0)
+    x, _ = soft_dot_attention(sd, "attention_layer.", h1, ctx, ctx_mask)
+    return F.linear(x, sd["projection.weight"], sd["projection.bias"]), h1, c1
+
+
+def speaker_infer_greedy(enc_sd, dec_sd, can_feats, img_feats, lengths, bos, eos, pad, unk, max_decode=120):
+    """Speaker.infer_batch with sampling=False (speaker.py:265-350) after from_shortest_path(): returns (words [B, n] int64,
+    ctx, list of per-step logits)."""
+    ctx = speaker_encoder(enc_sd, can_feats, img_feats)
+    B = ctx.shape[0]
+    ctx_mask = length2mask(torch.as_tensor(lengths), ctx.shape[1])
+    H = dec_sd["lstm.weight_hh_l0"].shape[1]
+    h_t, c_t = torch.zeros(B, H), torch.zeros(B, H)
+    ended = torch.zeros(B, dtype=torch.bool)
+    word = torch.full((B,), bos, dtype=torch.int64)
+    words, all_logits = [], []
+    for i in range(max_decode):
+        logits, h_t, c_t = speaker_decoder_step(dec_sd, word, ctx, ctx_mask, h_t, c_t)
+        logits = logits.clone()
+        logits[:, unk] = -float("inf")
+        all_logits.append(logits)
+        _, word = logits.max(1)
+        cpu_word = word.clone()
+        cpu_word[ended] = pad
+        words.append(cpu_word)
+        ended = ended | (cpu_word == eos)
+        if bool(ended.all()):
+            break
+    return torch.stack(words, 1), ctx, all_logits
