@@ -108,6 +108,26 @@ class DeviceEnv:
             self.step(buf["target"][t], traj_vp=traj[t + 1])
         return EnvEpisodes(self, buf, T, instr, traj=traj)
 
+    def shortest_path_features(self, max_steps=None):
+        """Speaker.from_shortest_path (speaker.py:163-198) on the device: follow the teacher from the current state until every
+        episode has stopped. Returns ((img_feats [B, L, 36, F], can_feats [B, L, F]), length [B]) — the inputs of the speaker's
+        encoder: the panorama of every visited viewpoint and the feature row of the candidate taken there (zeros for STOP).
+        One host sync at the end (the padded length L = longest path)."""
+        T = int(max_steps or self.cfg.max_action)
+        buf = self.alloc(T)
+        for t in range(T):
+            self.observe(buf, t)
+            self.step(buf["target"][t])
+        tgt, leng = buf["target"], buf["cand_leng"].long()                       # [T, B]
+        stop = (tgt == leng - 1) | (tgt == self.cfg.ignore_id)                     # speaker.py:184-186
+        idx = tgt.clamp(min=0)[:, :, None, None].expand(T, self.B, 1, self.cfg.feat)
+        can = torch.gather(buf["cand_feat"], 2, idx).squeeze(2)
+        can = torch.where(stop[:, :, None], torch.zeros_like(can), can)
+        ended_before = (stop.long().cumsum(0) - stop.long()) > 0                    # ended BEFORE step t
+        length = (~ended_before).long().sum(0)                                      # length += (1 - ended), speaker.py:189
+        L = int(length.max())
+        return (buf["f_t"][:L].transpose(0, 1).contiguous(), can[:L].transpose(0, 1).contiguous()), length
+
     def live_episodes(self, T, instr):
         """Closed-loop episodes for sampled / greedy feedback: observation t is produced when the policy asks for it and
         the policy's own action drives the transition (EnvEpisodes.advance)."""

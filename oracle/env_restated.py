@@ -238,3 +238,32 @@ def rollout(env, T, rgb_size, angle_size, actions=None, ignoreid=-100):
                       "dist": dist_before, "reward": reward, "mask": mask, "ended": ended.copy(),
                       "viewpoint": [ob["viewpoint"] for ob in obs], "viewIndex": np.array([ob["viewIndex"] for ob in obs])})
     return steps
+
+
+def from_shortest_path(env, rgb_size, angle_size, ignoreid=-100):
+    """Speaker.from_shortest_path (speaker.py:163-198) + Speaker._teacher_action / _candidate_variable (:137-161): follow the
+    teacher until every episode stopped. Returns (img_feats [B, L, 36, F], can_feats [B, L, F], length [B])."""
+    obs = env.get_obs()
+    B, F = len(obs), rgb_size + angle_size
+    ended = np.array([False] * B)
+    length = np.zeros(B, np.int64)
+    img_feats, can_feats = [], []
+    while not ended.all():
+        f_t = np.empty((B, 36, F), np.float32)
+        for i, ob in enumerate(obs):
+            f_t[i] = ob["feature"]
+        img_feats.append(f_t)
+        ta = teacher_action(obs, ended, ignoreid)
+        for i, act in enumerate(ta):
+            if act < 0 or act == len(obs[i]["candidate"]):
+                ta[i] = -1
+        cf = np.zeros((B, F), np.float32)
+        for i, (ob, act) in enumerate(zip(obs, ta)):
+            if act != -1:
+                cf[i, :] = ob["candidate"][act]["feature"]
+        can_feats.append(cf)
+        env.make_equiv_action(ta, obs)
+        length += (1 - ended)
+        ended[:] = np.logical_or(ended, (ta == -1))
+        obs = env.get_obs()
+    return np.stack(img_feats, 1), np.stack(can_feats, 1), length

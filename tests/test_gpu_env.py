@@ -207,3 +207,20 @@ def test_sample_rollout_on_live_env():
     assert torch.equal(ep.traj[1:T + 1].cpu(), torch.tensor([[g.names.index(v) for v in s["viewpoint"]] for s in steps[:T]],
                                                               dtype=torch.int32))
     env.check()
+
+
+def test_shortest_path_features_for_the_speaker():
+    """DeviceEnv.shortest_path_features == Speaker.from_shortest_path restated over the oracle environment (bit-exact)."""
+    from dasa_b200.env import DeviceEnv
+    C = 32
+    g, rgb, dep, start, view, goal = scenario(n=30, B=6, C=C, seed=11)
+    cfg = _cfg(C)
+    ora = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+    ora.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+    img, can, length = E.from_shortest_path(ora, C, cfg.angle_size)
+    env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+    (img_d, can_d), length_d = env.shortest_path_features(12)
+    assert np.array_equal(length_d.cpu().numpy(), length)
+    assert np.array_equal(can_d.cpu().numpy(), can)
+    # panoramas: the reference keeps observing after an episode stopped (same viewpoint); compare all L steps
+    assert np.array_equal(img_d.cpu().numpy(), img)
