@@ -876,7 +876,9 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
     const int LqP = (Lq + 15) & ~15, LkP = (Lk + 7) & ~7;
     if (dh == 64) {                                            // K / V only in shared memory, Q and P in registers
       const size_t smem64 = sizeof(float) * (size_t)LkP * (MHA2_KS + MHA2_VS);
-      auto kern = (LkP <= 48) ? mha_fwd_tc64_kernel<6> : mha_fwd_tc64_kernel<MHA_TC_MAXNT>;
+      // key-tile count as a template parameter: 6 (<= 48 keys: the 36 views), 8 (<= 64 keys: R2R instructions, no register
+      // spills), 12 (<= 96 keys)
+      auto kern = (LkP <= 48) ? mha_fwd_tc64_kernel<6> : ((LkP <= 64) ? mha_fwd_tc64_kernel<8> : mha_fwd_tc64_kernel<MHA_TC_MAXNT>);
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
       if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc64 attr", e2); return DASA_ERR_CUDA; }
       MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
