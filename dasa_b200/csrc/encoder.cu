@@ -511,7 +511,7 @@ constexpr int MHA2_KS = 80;          // K row stride (floats): == 16 mod 32 -> c
 constexpr int MHA2_VS = 68;          // V row stride: 2*VS == 8 mod 32 -> rows 2t (t = 0..3) land in distinct bank groups
 
 template <int NT>
-__global__ void __launch_bounds__(MHA_TC_THREADS, 4) mha_fwd_tc64_kernel(MhaArgs a) {
+__global__ void __launch_bounds__(MHA_TC_THREADS, (NT >= 10 ? 3 : 4)) mha_fwd_tc64_kernel(MhaArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int dh = 64;
   const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
@@ -878,7 +878,16 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
       const size_t smem64 = sizeof(float) * (size_t)LkP * (MHA2_KS + MHA2_VS);
       // key-tile count as a template parameter: 6 (<= 48 keys: the 36 views), 8 (<= 64 keys: R2R instructions, no register
       // spills), 12 (<= 96 keys)
-      auto kern = (LkP <= 48) ? mha_fwd_tc64_kernel<6> : ((LkP <= 64) ? mha_fwd_tc64_kernel<8> : mha_fwd_tc64_kernel<MHA_TC_MAXNT>);
+      void (*kern)(MhaArgs) = mha_fwd_tc64_kernel<MHA_TC_MAXNT>;
+      switch (LkP >> 3) {                                      // exact tile counts for the lengths the rollout produces
+        case 1: case 2: case 3: case 4: kern = mha_fwd_tc64_kernel<4>; break;
+        case 5: kern = mha_fwd_tc64_kernel<5>; break;          // the 36 views
+        case 6: kern = mha_fwd_tc64_kernel<6>; break;
+        case 7: kern = mha_fwd_tc64_kernel<7>; break;
+        case 8: kern = mha_fwd_tc64_kernel<8>; break;
+        case 9: case 10: kern = mha_fwd_tc64_kernel<10>; break;
+        default: break;
+      }
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
       if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc64 attr", e2); return DASA_ERR_CUDA; }
       MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
