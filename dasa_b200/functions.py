@@ -69,6 +69,12 @@ def flush_weight_grads():
     _queue.clear()
 
 
+def _rowmajor(t):
+    """Row-strided 2-D gradients (column slices of a wider buffer) are passed to the kernels in place: every kernel takes a
+    leading dimension. Only tensors without a unit inner stride are copied."""
+    return t if (t.dim() == 2 and t.stride(1) == 1) else t.contiguous()
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) with act in {none, tanh, relu} fused in the GEMM epilogue; act = gelu (finetune config) keeps the
     pre-activation for the backward and applies the erf-GELU in a second pass."""
@@ -108,7 +114,7 @@ class DropoutFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (mask,) = ctx.saved_tensors
-        return ops.dropout_apply(dy.contiguous(), mask, ctx.scale), None, None
+        return ops.dropout_apply(_rowmajor(dy), mask, ctx.scale), None, None
 
 
 def dropout(x, mask, scale):
@@ -195,7 +201,7 @@ class ShiftAttnFn(torch.autograd.Function):
         need_dctx = ctx.needs_input_grad[1]
         dtk = torch.zeros(tk.shape, device=tk.device, dtype=torch.float32)       # padding columns must be exact zeros
         dt, dkl = dtk[:, :F_all], dtk[:, F_all:F_all + k]
-        dctx, _, _ = ops.row_attention_bwd(context, tk[:, :F_all], p, q, kappa, dwc.contiguous(), k, ctx.headings, need_dctx,
+        dctx, _, _ = ops.row_attention_bwd(context, tk[:, :F_all], p, q, kappa, _rowmajor(dwc), k, ctx.headings, need_dctx,
                                            dt=dt, dkl=dkl)
         _wgrad(w_in, dt, h)
         _wgrad(w_shift, dkl, h, b_shift)
@@ -227,7 +233,7 @@ class SoftDotAttnFn(torch.autograd.Function):
     def backward(ctx, dht, _da):
         h, context, w_in, w_out, t, alpha, cat, h_tilde = ctx.saved_tensors
         D = ctx.D
-        du = ops.act_backward("tanh", dht.contiguous(), h_tilde)
+        du = ops.act_backward("tanh", _rowmajor(dht), h_tilde)
         _wgrad(w_out, du, cat)
         dcat = ops.linear_bwd_input(du, w_out)
         need_dctx = ctx.needs_input_grad[1]
@@ -235,7 +241,7 @@ class SoftDotAttnFn(torch.autograd.Function):
         _wgrad(w_in, dt, h)
         dh = None
         if ctx.needs_input_grad[0]:
-            dh = dcat[:, D:].contiguous()
+            dh = dcat[:, D:]                                   # accumulate in place in the [dwc ; dh] buffer (row stride D + H)
             ops.linear_bwd_input(dt, w_in, out=dh, beta=1.0)
         return dh, dctx, None, None, None
 
@@ -291,7 +297,7 @@ class LSTMCellFn(torch.autograd.Function):
         n_x = w_ih.shape[1]
         dgates = torch.empty(B, 4 * H, device=c.device, dtype=torch.float32)
         dc0 = torch.empty(B, H, device=c.device, dtype=torch.float32)
-        ops.lstm_pointwise_bwd(None if dh1 is None else dh1.contiguous(), None, None if dc1 is None else dc1.contiguous(),
+        ops.lstm_pointwise_bwd(None if dh1 is None else _rowmajor(dh1), None, None if dc1 is None else _rowmajor(dc1),
                                acts, c.contiguous(), c1, dgates, dc0)
         _wgrad(w_ih, dgates, xh[:, :n_x], b_ih, b_hh)         # db_ih == db_hh: one column sum
         _wgrad(w_hh, dgates, xh[:, n_x:])
