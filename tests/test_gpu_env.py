@@ -224,3 +224,66 @@ def test_shortest_path_features_for_the_speaker():
     assert np.array_equal(can_d.cpu().numpy(), can)
     # panoramas: the reference keeps observing after an episode stopped (same viewpoint); compare all L steps
     assert np.array_equal(img_d.cpu().numpy(), img)
+
+
+def test_env_properties_at_full_size():
+    """Size-independent properties at BASELINE geometry (36 x 2176 views, 512 episodes, a 512-viewpoint graph), where the Python
+    oracle would take minutes: the teacher reaches every goal in exactly hops(start, goal) moves, rewards are +1 per move and +2
+    for the stop, masks switch off after the stop, trajectories follow graph edges, and the assembled panoramas / candidates
+    equal a torch gather from the feature banks."""
+    from dasa_b200.env import DeviceEnv
+    cfg = FULL
+    g = NavGraph.synthetic(512, seed=3)
+    gen = torch.Generator().manual_seed(5)
+    rgb = synth.resnet_like((g.n, cfg.views, cfg.rgb_size), gen)
+    dep = synth.resnet_like((g.n, cfg.views, cfg.rgb_size), gen)
+    B, T = 512, 10
+    start, view, goal = g.sample_episodes(B, seed=1, min_hops=3, max_hops=7)
+    hops = torch.from_numpy(g.hops()[start, goal])
+    env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+    buf = env.alloc(T)
+    reward = torch.empty(T, B, device=DEV)
+    mask = torch.empty(T, B, device=DEV)
+    traj = torch.empty(T + 1, B, dtype=torch.int32, device=DEV)
+    traj[0].copy_(env.vp)
+    views_before = []
+    for t in range(T):
+        views_before.append(env.view.clone())
+        env.observe(buf, t)
+        env.step(buf["target"][t], reward[t], mask[t], traj_vp=traj[t + 1])
+    env.check()
+    traj_c, reward_c, mask_c = traj.cpu().long(), reward.cpu(), mask.cpu()
+    tgt, leng = buf["target"].cpu(), buf["cand_leng"].cpu().long()
+    assert torch.equal(traj_c[-1], torch.from_numpy(goal).long())                      # every goal reached
+    for t in range(T):
+        moving = t < hops
+        stopping = t == hops
+        after = t > hops
+        assert torch.equal(reward_c[t][moving], torch.ones(int(moving.sum())))         # each teacher move shortens the path
+        assert torch.equal(reward_c[t][stopping], torch.full((int(stopping.sum()),), 2.0))   # stop within 3 m of the goal
+        assert float(reward_c[t][after].abs().max() if after.any() else 0.0) == 0.0
+        assert torch.equal(mask_c[t], (~after).float())
+        assert torch.equal(tgt[t][stopping], leng[t][stopping] - 1)                     # STOP = the END row
+        assert bool((tgt[t][after] == cfg.ignore_id).all())
+        # moves follow graph edges
+        nbr = torch.from_numpy(g.nbr).long()
+        ok = (nbr[traj_c[t]] == traj_c[t + 1][:, None]).any(1) | (traj_c[t] == traj_c[t + 1])
+        assert bool(ok.all())
+    assert torch.equal(buf["dist"][0].cpu(), torch.from_numpy(g.dist[start, goal]))
+    # panoramas and candidates of step 2 against a torch gather from the banks
+    t = 2
+    vp = traj[t].long()
+    C = cfg.rgb_size
+    assert torch.equal(buf["f_t"][t][..., :C], env.rgb_bank[vp])
+    assert torch.equal(buf["d_t"][t][..., :C], env.dep_bank[vp])
+    assert torch.equal(buf["f_t"][t][..., C:], buf["d_t"][t][..., C:])
+    va = torch.from_numpy(g.view_angle).to(DEV)[(views_before[t] % 12).long()]           # [B, 36, 4]
+    assert torch.equal(buf["f_t"][t][..., C:], va.repeat(1, 1, cfg.angle_size // 4))
+    deg = torch.from_numpy(g.deg).to(DEV)[vp].long()
+    k = torch.arange(env.nc, device=DEV)[None, :]
+    live = k < deg[:, None]
+    pt = torch.from_numpy(g.nbr_point).to(DEV).long()[vp]                               # [B, dmax]
+    want = env.rgb_bank[vp[:, None].expand(-1, env.dmax), pt]                            # [B, dmax, C]
+    got = buf["cand_feat"][t][:, :env.dmax, :C]
+    assert torch.equal(got[live[:, :env.dmax]], want[live[:, :env.dmax]])
+    assert float(buf["cand_feat"][t][~live].abs().max()) == 0.0                         # END row and padding are zeros

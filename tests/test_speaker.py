@@ -73,3 +73,38 @@ def test_speaker_infer_matches_oracle(seed, bias):
     safe = (margins > 1e-4).cumprod(1).bool()             # once a near-tie flips a word the continuation may differ
     assert torch.equal(words.cpu()[safe], want_words[safe])
     assert safe.float().mean() > 0.9
+
+
+@pytest.mark.gpu
+def test_speaker_full_geometry():
+    """README geometry (features 2176, rnn_dim 512, wemb 256, 992-word vocabulary, 20 paths of up to 8 viewpoints): encoder ctx
+    and the first decode steps against the oracle; the decoded array obeys the protocol invariants (nothing but <PAD> after
+    <EOS>, no <UNK>, no <PAD> before <EOS>)."""
+    from dasa_b200 import speaker as S
+    from dasa_b200.config import FULL
+    tok = dict(pad=0, unk=1, eos=2, bos=991)
+    enc_sd, dec_sd = synth.speaker_state(FULL.feat, rnn_dim=512, wemb=256, vocab=992, seed=3)
+    dec_sd["projection.bias"][tok["eos"]] += 0.6
+    can, img, lengths = synth.speaker_inputs(20, 8, FULL, 3)
+    want_words, want_ctx, want_logits = R.speaker_infer_greedy(enc_sd, dec_sd, can, img, lengths, tok["bos"], tok["eos"], tok["pad"],
+                                                               tok["unk"], 6)
+    enc = S.SpeakerEncoder(FULL.feat, 512, 0.5, True).cuda().eval()
+    dec = S.SpeakerDecoder(992, 256, tok["pad"], 512, 0.5).cuda().eval()
+    enc.load_state_dict(enc_sd, strict=True)
+    dec.load_state_dict(dec_sd, strict=True)
+    with torch.no_grad():
+        ctx = enc(can.cuda(), img.cuda(), lengths)
+    err = float((ctx.cpu() - want_ctx).abs().max() / want_ctx.abs().max())
+    assert err <= 1e-4, "speaker encoder ctx rel err %.2e" % err
+    words = S.infer_batch(enc, dec, can.cuda(), img.cuda(), lengths, tok["bos"], tok["eos"], tok["pad"], tok["unk"], 40).cpu()
+    n = min(words.shape[1], want_words.shape[1])
+    margins = torch.stack([lg.topk(2, 1).values[:, 0] - lg.topk(2, 1).values[:, 1] for lg in want_logits], 1)[:, :n]
+    safe = (margins > 1e-4).cumprod(1).bool()
+    assert torch.equal(words[:, :n][safe], want_words[:, :n][safe])
+    assert not bool((words == tok["unk"]).any())
+    for row in words.tolist():
+        if tok["eos"] in row:
+            i = row.index(tok["eos"])
+            assert all(w == tok["pad"] for w in row[i + 1:]) and tok["pad"] not in row[:i]
+        else:
+            assert tok["pad"] not in row
