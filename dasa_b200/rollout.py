@@ -88,17 +88,48 @@ class NavPolicy:
                     p.grad.zero_()
 
     # ------------------------------------------------------------------------------------------------ one nav step
-    def step(self, ep, t, carry, lang_out=None, want_ctx=False):
-        """Loop body of vl_rollout up to the masked logits (agent_dg.py:727-841). carry = None at t == 0."""
+    def make_noise(self):
+        """noise = decoder.drop_env(ones(feature_size)) of the augmented (speaker) rollouts (agent_dg.py:656, 677): a uint8
+        keep vector [C]; its scale is 1 / (1 - featdropout). None in eval mode (drop_env is the identity there)."""
+        if not self.decoder.training:
+            return None
+        m, _ = M.dropout_source().mask("env.noise", (self.cfg.rgb_size,), self.cfg.featdropout, True, self.device)
+        return m
+
+    def _consistent(self, noise, f_t, n_cand_rows):
+        """consistent_drop with --env_drop_stage after_adain --depth_drop (agent_dg.py:780-785): the [C] mask, shared by the
+        batch, the views and all steps, replaces the decoder's per-element drop_env masks on the AdaIN'd views / candidates
+        (folded into the gate GEMM's epilogue as row-broadcast masks) and also multiplies the RAW views the encoder reads."""
+        cfg = self.cfg
+        C, A = cfg.rgb_size, cfg.angle_size
+        scale = 1.0 / (1.0 - cfg.featdropout)
+        noise = ops.as_keep_mask(noise)
+        rows_f = f_t.shape[0] * f_t.shape[1]
+        m_f = noise.view(1, C).expand(rows_f, C).contiguous()
+        m_c = noise.view(1, C).expand(n_cand_rows, C).contiguous()
+        f_enc = torch.empty(f_t.shape, device=f_t.device, dtype=torch.float32)
+        ops.dropout_apply(f_t[..., :C], m_f, scale, out=f_enc[..., :C])
+        ops.axpy2d(1.0, f_t[..., C:], f_enc[..., C:], accumulate=False)
+        return m_f, m_c, scale, f_enc
+
+    def step(self, ep, t, carry, lang_out=None, want_ctx=False, noise=None):
+        """Loop body of vl_rollout up to the masked logits (agent_dg.py:727-841). carry = None at t == 0. `noise`: the [C]
+        keep vector of an augmented rollout (see make_noise / _consistent)."""
         cfg, tr = self.cfg, self.decoder.training
         a_t, f_t, d_t, cand, cand_d, leng, _ = ep.step(t)
         src = M.dropout_source()
         B, V, _ = f_t.shape
         C = cfg.rgb_size
-        m_f, s_f = src.mask("dec.feat", (B, V, C), cfg.featdropout, tr, f_t.device)
-        m_c, s_c = src.mask("dec.cand", (B, cand.shape[1], C), cfg.featdropout, tr, f_t.device)
+        if noise is not None:
+            m_f, m_c, s_f, f_t_enc = self._consistent(noise, f_t, B * cand.shape[1])
+            s_c = s_f
+        else:
+            m_f, s_f = src.mask("dec.feat", (B, V, C), cfg.featdropout, tr, f_t.device)
+            m_c, s_c = src.mask("dec.cand", (B, cand.shape[1], C), cfg.featdropout, tr, f_t.device)
+            f_t_enc = f_t
         df_t = self.adaIn.gate_features(f_t, d_t, m_f, s_f)                 # K1 views
         cand_g = self.adaIn.gate_features(cand, cand_d, m_c, s_c)           # K1 candidates
+        f_t = f_t_enc                                                       # what the encoder sees
         ctx, en_h, en_c, _, _ = self.encoder(ep.seq, ep.seq_mask, ep.seq_lengths, f_t_all=f_t, lang_out=lang_out,
                                              lengths_host=ep.seq_lengths_host)                                  # RAW f_t
         prev_h1, c_0 = (en_h, en_c) if carry is None else carry
@@ -109,7 +140,7 @@ class NavPolicy:
         return logit, h_t, (h1, c_t)
 
     # ------------------------------------------------------------------------------------------- teacher-forced rollout
-    def teacher_rollout(self, ep, T=None, ml_weight=0.4, tag_steps=True, schedule=None):
+    def teacher_rollout(self, ep, T=None, ml_weight=0.4, tag_steps=True, schedule=None, noise=None):
         """feedback='teacher', train_rl=False (agent_dg.py:1368-1370): returns (loss tensor [1], logits list, actions list).
         loss = sum_t CE_sum(logit_t, target_t) * ml_weight / B  (agent_dg.py:850, 1024).
 
@@ -133,11 +164,16 @@ class NavPolicy:
             cand_all = ep.cand_feat[:T].reshape(T * B, nc, cfg.feat)
             candd_all = ep.cand_dfeat[:T].reshape(T * B, nc, cfg.feat)
             dev = f_all.device
-            m_f, s_f = src.mask_steps("dec.feat", (B, cfg.views, C), cfg.featdropout, tr, dev, T)
-            m_c, s_c = src.mask_steps("dec.cand", (B, nc, C), cfg.featdropout, tr, dev, T)
+            f_enc = f_all
+            if noise is not None:                   # augmented rollout: one [C] mask for every view / candidate row and step
+                m_f, m_c, s_f, f_enc = self._consistent(noise, f_all, T * B * nc)
+                s_c = s_f
+            else:
+                m_f, s_f = src.mask_steps("dec.feat", (B, cfg.views, C), cfg.featdropout, tr, dev, T)
+                m_c, s_c = src.mask_steps("dec.cand", (B, nc, C), cfg.featdropout, tr, dev, T)
             df_all = self.adaIn.gate_features(f_all, d_all, m_f, s_f)                 # K1, all actions
             candg_all = self.adaIn.gate_features(cand_all, candd_all, m_c, s_c)
-            ctx_all, en_h, en_c = self.encoder.encode_rollout(ep.seq, ep.seq_mask, ep.seq_lengths, f_all, T,
+            ctx_all, en_h, en_c = self.encoder.encode_rollout(ep.seq, ep.seq_mask, ep.seq_lengths, f_enc, T,
                                                               lengths_host=ep.seq_lengths_host)
             L = ctx_all.shape[1]
             ctx_steps = ctx_all.view(T, B, L, -1).unbind(0)          # unbind: one stacked gradient instead of T zero-filled ones
@@ -167,7 +203,7 @@ class NavPolicy:
         for t in range(T):
             if tag_steps:
                 src.prefix = base_prefix + "t%d." % t
-            logit, h_t, carry = self.step(ep, t, carry, None if lang_all is None else lang_all[t])
+            logit, h_t, carry = self.step(ep, t, carry, None if lang_all is None else lang_all[t], noise=noise)
             loss_t, a_t = Fn.MaskedCEFn.apply(logit, ep.target_at(t), self.cfg.ignore_id)
             total = loss_t if total is None else total + loss_t
             logits.append(logit)

@@ -66,8 +66,9 @@ def recorded_dropout(seed, record):
         F.dropout = orig
 
 
-def reference_rollout(ref, mods, cfg, ep, T, ml_weight=0.4):
-    """Loop body of vl_rollout (agent_dg.py:727-851), feedback='teacher', around the reference modules."""
+def reference_rollout(ref, mods, cfg, ep, T, ml_weight=0.4, noise=None):
+    """Loop body of vl_rollout (agent_dg.py:727-851), feedback='teacher', around the reference modules. noise (a [C] tensor)
+    switches on consistent_drop with --env_drop_stage after_adain --depth_drop (agent_dg.py:780-785, 812-820)."""
     enc, dec, cri, ada = mods
     C = cfg.rgb_size
     crit = torch.nn.CrossEntropyLoss(ignore_index=cfg.ignore_id, reduction="sum")   # agent_dg.py:250
@@ -77,11 +78,17 @@ def reference_rollout(ref, mods, cfg, ep, T, ml_weight=0.4):
         df_t = f_t.clone()
         df_t[:, :, :C] = ada(f_t[:, :, :C].clone(), d_t[:, :, :C].clone())
         cand[:, :, :C] = ada(cand[:, :, :C].clone(), cand_d[:, :, :C].clone())
+        consistent_drop = noise is not None
+        if consistent_drop:
+            cand[..., :C] *= noise
+            f_t[..., :C] *= noise
+            cand_d[..., :C] *= noise
+            df_t[..., :C] *= noise
         ctx, en_h, en_c, _, _ = enc(ep.seq, mask=ep.seq_mask, lengths=ep.seq_lengths, f_t_all=f_t.clone())
         if t == 0:
-            h_t, c_t, logit, h1, _ = dec(a_t, df_t, cand, en_h, en_h, en_c, ctx, ep.seq_mask, already_dropfeat=False)
+            h_t, c_t, logit, h1, _ = dec(a_t, df_t, cand, en_h, en_h, en_c, ctx, ep.seq_mask, already_dropfeat=consistent_drop)
         else:
-            h_t, c_t, logit, h1, _ = dec(a_t, df_t, cand, h_t, h1, c_t, ctx, ep.seq_mask, already_dropfeat=False)
+            h_t, c_t, logit, h1, _ = dec(a_t, df_t, cand, h_t, h1, c_t, ctx, ep.seq_mask, already_dropfeat=consistent_drop)
         cmask = torch.arange(logit.shape[1]).unsqueeze(0) >= leng.view(-1, 1).long()   # utils.length2mask
         logit.masked_fill_(cmask, -float("inf"))
         total = total + crit(logit, target)

@@ -337,7 +337,7 @@ class _Prefixed:
 
 
 def policy_step(state, cfg, seq, mask, lengths, step_inputs, carry, drops=NoDrop(), adain="channel",
-                lang_cache=None):
+                lang_cache=None, noise=None):
     """One iteration of the vl_rollout loop body up to the masked logits (agent_dg.py:727-841).
     carry = None at t==0 (decoder starts from the encoder state, :812-815) else (h1, c_t).
     Note: the encoder sees the RAW f_t while the decoder sees the AdaIN'd copy (agent_dg.py:728,764-768,793)."""
@@ -357,16 +357,24 @@ def policy_step(state, cfg, seq, mask, lengths, step_inputs, carry, drops=NoDrop
         raise ValueError(adain)
     df_t = torch.cat([df_rgb, f_t[..., C:]], -1)
     cand = torch.cat([cand_rgb, cand_feat[..., C:]], -1)
+    if noise is not None:
+        # consistent_drop with --env_drop_stage after_adain --depth_drop (agent_dg.py:780-785): one [C] mask, shared by the
+        # batch, the views and all steps, multiplies the AdaIN'd candidates, the RAW f_t (the encoder's input) and the
+        # AdaIN'd views; the decoder is then called with already_dropfeat=True (agent_dg.py:812-820)
+        cand = torch.cat([cand[..., :C] * noise, cand[..., C:]], -1)
+        f_t = torch.cat([f_t[..., :C] * noise, f_t[..., C:]], -1)
+        df_t = torch.cat([df_t[..., :C] * noise, df_t[..., C:]], -1)
     ctx, en_h, en_c, _ = encoder_forward(state["encoder"], cfg, seq, mask, lengths, f_t, drops, lang_cache)
     prev_h1, c_0 = (en_h, en_c) if carry is None else carry
-    h_t, c_t, logit, h1, aux = decoder_step(state["decoder"], cfg, input_a_t, df_t, cand, prev_h1, c_0, ctx, mask, drops)
+    h_t, c_t, logit, h1, aux = decoder_step(state["decoder"], cfg, input_a_t, df_t, cand, prev_h1, c_0, ctx, mask, drops,
+                                            already_dropfeat=noise is not None)
     logit = logit.masked_fill(length2mask(cand_leng, logit.shape[1]), -float("inf"))
     aux["ctx"] = ctx
     return logit, h_t, (h1, c_t), aux
 
 
 def teacher_rollout(state, cfg, episodes, T=None, ml_weight=0.4, drops=NoDrop(), adain="channel",
-                    cache_language=False):
+                    cache_language=False, noise=None):
     """Teacher-forced vl_rollout (agent_dg.py:725-936, feedback='teacher', train_rl=False) followed by the loss
     assembly (agent_dg.py:1006-1024): loss = sum_t CE_sum(logit_t, target_t, ignore -100) * ml_weight / B.
     Returns (loss, list of masked logits, list of argmax actions)."""
@@ -377,7 +385,7 @@ def teacher_rollout(state, cfg, episodes, T=None, ml_weight=0.4, drops=NoDrop(),
     for t in range(T):
         step = episodes.step(t)
         sdrops = _Prefixed(drops, t) if drops.training else drops
-        logit, h_t, carry, _ = policy_step(state, cfg, seq, mask, lengths, step, carry, sdrops, adain, lang_cache)
+        logit, h_t, carry, _ = policy_step(state, cfg, seq, mask, lengths, step, carry, sdrops, adain, lang_cache, noise)
         total = total + F.cross_entropy(logit, step[6], ignore_index=cfg.ignore_id, reduction="sum")
         logits.append(logit)
         actions.append(logit.argmax(1))

@@ -466,3 +466,30 @@ def test_packed_encoder_equals_padded_encoder(train):
         if a.dtype == torch.bool:
             continue
         assert_close(b, a, 2e-6, "packed vs padded " + name)
+
+
+@pytest.mark.parametrize("schedule", ["batched", "sequential"])
+def test_consistent_drop_rollout(schedule):
+    """Augmented-rollout feature dropout (agent_dg.py:656, 780-785, 812-820): one [C] mask shared by batch, views and steps,
+    against the oracle (itself pinned against the reference modules): loss, logits, AdaIN / decoder / bi-LSTM gradients."""
+    cfg, B, T = SMALL, 4, 3
+    st = synth.policy_state(cfg, 6)
+    ep = synth.Episodes(B, T, cfg, seed=33)
+    gen = torch.Generator().manual_seed(2)
+    keep = torch.rand(cfg.rgb_size, generator=gen) >= cfg.featdropout
+    noise = keep.float() / (1 - cfg.featdropout)
+    ost = {grp: {k: v.clone().requires_grad_(True) for k, v in d.items()} for grp, d in st.items()}
+    loss_ref, logits_ref, _ = R.teacher_rollout(ost, cfg, ep, T, noise=noise)
+    loss_ref.backward()
+    pol = NavPolicy(cfg, st).eval()
+    dep = DeviceEpisodes(ep)
+    loss, logits, _ = pol.teacher_rollout(dep, T, schedule=schedule, noise=keep.to(torch.uint8).cuda())
+    pol.backward(loss)
+    assert_close(loss, loss_ref, 1e-4, "loss")
+    lg, lg2 = torch.stack(logits_ref).detach(), torch.stack(logits).detach().cpu()
+    fin = torch.isfinite(lg)
+    assert torch.equal(fin, torch.isfinite(lg2))
+    assert_close(lg2[fin], lg[fin], 1e-4, "logits")
+    for grp, mod, key in (("adaIn", pol.adaIn, "a_fc.weight"), ("decoder", pol.decoder, "lstm.weight_ih"),
+                          ("encoder", pol.encoder, "lstm.weight_ih_l0")):
+        assert_close(dict(mod.named_parameters())[key].grad, ost[grp][key].grad, 1e-3, "%s.%s grad" % (grp, key))

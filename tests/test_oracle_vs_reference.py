@@ -125,3 +125,23 @@ def test_checkpoint_roundtrip_with_reference_agent(tmp_path):
     for i, p in enumerate(pol.decoder.parameters()):
         if i in sq_new and pol._square_avg("decoder", p, i) is not None and p.requires_grad and i in sq_ref:
             assert torch.equal(sq_new[i]["square_avg"], pol._square_avg("decoder", p, i))
+
+
+def test_consistent_drop_rollout_matches_reference(ref_mods):
+    """Aug-rollout feature dropout (consistent_drop, after_adain, depth_drop): one [C] mask shared by batch, views and steps on
+    the AdaIN'd candidates, the raw and the AdaIN'd views; decoder called with already_dropfeat=True (agent_dg.py:780-785)."""
+    from oracle.make_golden import reference_rollout
+    ref, st, mods = ref_mods
+    ep = synth.Episodes(4, 3, SMALL, seed=33)
+    gen = torch.Generator().manual_seed(2)
+    noise = (torch.rand(SMALL.rgb_size, generator=gen) >= SMALL.featdropout).float() / (1 - SMALL.featdropout)
+    with torch.no_grad():
+        loss_ref, logits_ref, _ = reference_rollout(ref, mods, SMALL, ep, 3, noise=noise)
+        loss, logits, _ = R.teacher_rollout(st, SMALL, ep, 3, noise=noise)
+        loss_plain, _, _ = R.teacher_rollout(st, SMALL, ep, 3)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    assert abs(float(loss) - float(loss_plain)) > 1e-4 * abs(float(loss_ref))           # the mask does change the rollout
+    for a, b in zip(logits, logits_ref):
+        fin = torch.isfinite(b)
+        assert torch.equal(fin, torch.isfinite(a))
+        torch.testing.assert_close(a[fin], b[fin], rtol=1e-4, atol=1e-5)
