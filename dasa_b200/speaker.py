@@ -77,7 +77,8 @@ class SpeakerDecoder(nn.Module):
 
 
 @torch.no_grad()
-def infer_batch(encoder, decoder, can_feats, img_feats, lengths, bos, eos, pad, unk, max_decode=120, check_every=8):
+def infer_batch(encoder, decoder, can_feats, img_feats, lengths, bos, eos, pad, unk, max_decode=120, check_every=8,
+                featdropmask=None, featdrop_scale=1.0):
     """Greedy branch of Speaker.infer_batch (speaker.py:265-350) given the shortest-path features from_shortest_path()
     produces: can_feats [B, L, F] (the taken candidates), img_feats [B, L, 36, F], lengths (list / tensor of path lengths).
     Returns the instructions as an int64 tensor [B, n] on the device, n = the step at which every sequence had emitted <EOS>
@@ -87,7 +88,20 @@ def infer_batch(encoder, decoder, can_feats, img_feats, lengths, bos, eos, pad, 
     decoder.eval()
     dev = can_feats.device
     B = can_feats.shape[0]
-    ctx = encoder(can_feats, img_feats, lengths)
+    if featdropmask is not None:
+        # the agent's env-drop noise shared with the speaker (speaker.py:291-293; agent_dg.py:656-659): a uint8 keep vector [C]
+        # with its scale; the RGB part of both feature tensors is multiplied, the angle part is left alone
+        C = featdropmask.numel()
+        keep = ops.as_keep_mask(featdropmask)
+
+        def masked(x):
+            rows = x.numel() // x.shape[-1]
+            out = torch.empty_like(x)
+            ops.dropout_apply(x[..., :C], keep.view(1, C).expand(rows, C).contiguous(), featdrop_scale, out=out[..., :C])
+            ops.axpy2d(1.0, x[..., C:], out[..., C:], accumulate=False)
+            return out
+        can_feats, img_feats = masked(can_feats), masked(img_feats)
+    ctx = encoder(can_feats, img_feats, lengths, already_dropfeat=featdropmask is not None)
     lengths = torch.as_tensor(lengths, device=dev)
     ctx_mask = (torch.arange(ctx.shape[1], device=dev)[None, :] >= lengths[:, None]).to(torch.uint8)     # utils.length2mask
     h_t = torch.zeros(1, B, decoder.hidden_size, device=dev)

@@ -108,3 +108,30 @@ def test_speaker_full_geometry():
             assert all(w == tok["pad"] for w in row[i + 1:]) and tok["pad"] not in row[:i]
         else:
             assert tok["pad"] not in row
+
+
+@pytest.mark.gpu
+def test_speaker_featdropmask():
+    """infer_batch(featdropmask=noise) (speaker.py:291-296): the agent's env-drop mask multiplies the RGB part of both feature
+    tensors before the encoder."""
+    from dasa_b200 import speaker as S
+    enc_sd, dec_sd, can, img, lengths = speaker_case(1, 0.65)
+    C = SMALL.rgb_size
+    gen = torch.Generator().manual_seed(4)
+    keep = torch.rand(C, generator=gen) >= 0.4
+    noise = keep.float() / 0.6
+    can2, img2 = can.clone(), img.clone()
+    can2[..., :C] *= noise
+    img2[..., :C] *= noise
+    want_words, want_ctx, want_logits = R.speaker_infer_greedy(enc_sd, dec_sd, can2, img2, lengths, TOK["bos"], TOK["eos"], TOK["pad"],
+                                                               TOK["unk"], 16)
+    enc = S.SpeakerEncoder(SMALL.feat, DIMS["rnn_dim"], 0.5, True).cuda().eval()
+    dec = S.SpeakerDecoder(DIMS["vocab"], DIMS["wemb"], TOK["pad"], DIMS["rnn_dim"], 0.5).cuda().eval()
+    enc.load_state_dict(enc_sd, strict=True)
+    dec.load_state_dict(dec_sd, strict=True)
+    words = S.infer_batch(enc, dec, can.cuda(), img.cuda(), lengths, TOK["bos"], TOK["eos"], TOK["pad"], TOK["unk"], 16,
+                          featdropmask=keep.to(torch.uint8).cuda(), featdrop_scale=1 / 0.6).cpu()
+    assert tuple(words.shape) == tuple(want_words.shape)
+    margins = torch.stack([lg.topk(2, 1).values[:, 0] - lg.topk(2, 1).values[:, 1] for lg in want_logits], 1)
+    safe = (margins > 1e-4).cumprod(1).bool()
+    assert torch.equal(words[safe], want_words[safe]) and safe.float().mean() > 0.9
