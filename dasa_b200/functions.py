@@ -276,36 +276,43 @@ class CandLogitsFn(torch.autograd.Function):
 class LSTMCellFn(torch.autograd.Function):
     """nn.LSTMCell (model.py:437,514) on the concatenated input xh = [x ; h] (the caller builds it with the one torch.cat it
     needs anyway) against the column-stacked weight [W_ih | W_hh] (cached until the parameters change): ONE gate GEMM forward
-    and ONE for d[x ; h] backward instead of two each, + the fused pointwise kernels."""
+    and ONE for d[x ; h] backward instead of two each, + the fused pointwise kernels. With a keep mask the decoder's
+    drop(h_1) (model.py:515-516) is produced by the same pointwise kernel: returns (h1, c1, h1_dropped)."""
 
     @staticmethod
-    def forward(ctx, xh, c, w_ih, w_hh, b_ih, b_hh):
+    def forward(ctx, xh, c, w_ih, w_hh, b_ih, b_hh, drop_mask=None, drop_scale=1.0):
         B, H = c.shape
         Wc, _ = ops.stacked_weights((w_ih, w_hh), 1)
         gates = ops.linear_fwd(xh, Wc)
         h1 = torch.empty(B, H, device=c.device, dtype=torch.float32)
         c1 = torch.empty(B, H, device=c.device, dtype=torch.float32)
         acts = torch.empty(B, 4 * H, device=c.device, dtype=torch.float32)
-        ops.lstm_pointwise_fwd(gates, None, b_ih, b_hh, c.contiguous(), None, h1, c1, None, acts)
-        ctx.save_for_backward(xh, c, w_ih, w_hh, b_ih, b_hh, acts, c1)
-        return h1, c1
+        h1d = torch.empty(B, H, device=c.device, dtype=torch.float32) if drop_mask is not None else None
+        ops.lstm_pointwise_fwd(gates, None, b_ih, b_hh, c.contiguous(), None, h1, c1, h1d, acts, seq_mask=drop_mask,
+                               seq_scale=drop_scale)
+        ctx.scale = drop_scale
+        ctx.save_for_backward(xh, c, w_ih, w_hh, b_ih, b_hh, acts, c1, drop_mask if drop_mask is not None else c.new_empty(0))
+        if drop_mask is None:
+            return h1, c1
+        return h1, c1, h1d
 
     @staticmethod
-    def backward(ctx, dh1, dc1):
-        xh, c, w_ih, w_hh, b_ih, b_hh, acts, c1 = ctx.saved_tensors
+    def backward(ctx, dh1, dc1, dh1d=None):
+        xh, c, w_ih, w_hh, b_ih, b_hh, acts, c1, mask = ctx.saved_tensors
         B, H = c.shape
         n_x = w_ih.shape[1]
         dgates = torch.empty(B, 4 * H, device=c.device, dtype=torch.float32)
         dc0 = torch.empty(B, H, device=c.device, dtype=torch.float32)
-        ops.lstm_pointwise_bwd(None if dh1 is None else _rowmajor(dh1), None, None if dc1 is None else _rowmajor(dc1),
-                               acts, c.contiguous(), c1, dgates, dc0)
+        ops.lstm_pointwise_bwd(None if dh1 is None else _rowmajor(dh1), None if dh1d is None else _rowmajor(dh1d),
+                               None if dc1 is None else _rowmajor(dc1), acts, c.contiguous(), c1, dgates, dc0,
+                               dh2_mask=mask if (mask.numel() and dh1d is not None) else None, dh2_scale=ctx.scale)
         _wgrad(w_ih, dgates, xh[:, :n_x], b_ih, b_hh)         # db_ih == db_hh: one column sum
         _wgrad(w_hh, dgates, xh[:, n_x:])
         dxh = None
         if ctx.needs_input_grad[0]:
             Wc, _ = ops.stacked_weights((w_ih, w_hh), 1)
             dxh = ops.linear_bwd_input(dgates, Wc)
-        return dxh, (dc0 if ctx.needs_input_grad[1] else None), None, None, None, None
+        return dxh, (dc0 if ctx.needs_input_grad[1] else None), None, None, None, None, None, None
 
 
 def invalidate_weight_caches():

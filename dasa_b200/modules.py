@@ -286,8 +286,13 @@ class BAttnDecoderLSTM(nn.Module):
         h_prev_drop = _drop(prev_h1, "dec.h_prev", p, tr)
         attn_feat, _ = self.feat_att_layer(h_prev_drop, feature, output_tilde=False)
         xh = torch.cat((emb, attn_feat, prev_h1), 1)        # [x ; h]: one gate GEMM against [W_ih | W_hh]
-        h_1, c_1 = Fn.LSTMCellFn.apply(xh, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih, self.lstm.bias_hh)
-        h_1_drop = _drop(h_1, "dec.h1", p, tr)
+        m_h1, s_h1 = _source.mask("dec.h1", (xh.shape[0], self.hidden_size), p, tr, xh.device)
+        if m_h1 is not None:       # drop(h_1) comes out of the cell's pointwise kernel
+            h_1, c_1, h_1_drop = Fn.LSTMCellFn.apply(xh, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih,
+                                                     self.lstm.bias_hh, m_h1, s_h1)
+        else:
+            h_1, c_1 = Fn.LSTMCellFn.apply(xh, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih, self.lstm.bias_hh)
+            h_1_drop = h_1
         h_tilde, alpha = self.attention_layer(h_1_drop, ctx, ctx_mask)
         if not want_logit:
             return h_1, c_1, None, h_tilde, {}

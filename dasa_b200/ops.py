@@ -397,24 +397,26 @@ def cand_logits_bwd(cand, t, leng, dlogit, Dc, need_dcand=True):
 
 
 # -------------------------------------------------------------------------------------------------------- LSTM
-def lstm_pointwise_fwd(ga, gb, bias_a, bias_b, c_prev, h_prev, h_out, c_out, seq_out=None, acts_out=None, active=None, pos=0):
+def lstm_pointwise_fwd(ga, gb, bias_a, bias_b, c_prev, h_prev, h_out, c_out, seq_out=None, acts_out=None, active=None, pos=0,
+                       seq_mask=None, seq_scale=1.0):
     B, H = h_out.shape
 
     def ld(t):
         return 0 if t is None else t.stride(0)
     call("dasa_lstm_pointwise_fwd", _p(ga), ld(ga), _p(gb), ld(gb), _p(bias_a), _p(bias_b), _p(c_prev), ld(c_prev), _p(h_prev),
          ld(h_prev), _p(h_out), ld(h_out), _p(c_out), ld(c_out), _p(seq_out), ld(seq_out), _p(acts_out), ld(acts_out),
-         _p(active), int(pos), B, H, _stream())
+         _p(active), int(pos), B, H, _p(seq_mask), float(seq_scale), _stream())
 
 
-def lstm_pointwise_bwd(dh, dh2, dc, acts, c_prev, c_new, dgates, dc_prev, dh_pass=None, active=None, pos=0):
+def lstm_pointwise_bwd(dh, dh2, dc, acts, c_prev, c_new, dgates, dc_prev, dh_pass=None, active=None, pos=0, dh2_mask=None,
+                       dh2_scale=1.0):
     B, H = c_new.shape
 
     def ld(t):
         return 0 if t is None else t.stride(0)
     call("dasa_lstm_pointwise_bwd", _p(dh), ld(dh), _p(dh2), ld(dh2), _p(dc), ld(dc), _p(acts), ld(acts), _p(c_prev), ld(c_prev),
          _p(c_new), ld(c_new), _p(dgates), ld(dgates), _p(dc_prev), ld(dc_prev), _p(dh_pass), ld(dh_pass), _p(active), int(pos),
-         B, H, _stream())
+         B, H, _p(dh2_mask), float(dh2_scale), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ encoder pieces

@@ -164,14 +164,18 @@ int dasa_cand_logits_bwd(const float* cand, int64_t ld_row, int64_t ld_sample, i
 int dasa_lstm_pointwise_fwd(const float* ga, int64_t ld_ga, const float* gb, int64_t ld_gb, const float* bias_a,
                             const float* bias_b, const float* c_prev, int64_t ld_cp, const float* h_prev, int64_t ld_hp,
                             float* h_out, int64_t ld_h, float* c_out, int64_t ld_c, float* seq_out, int64_t ld_seq,
-                            float* acts_out, int64_t ld_acts, const int32_t* active, int pos, int B, int H, void* stream);
-/* backward: (dh, dc_in, saved acts, c_prev, c_new) -> dgates [B,4H], dc_prev. dh2 (optional) is added to dh.
+                            float* acts_out, int64_t ld_acts, const int32_t* active, int pos, int B, int H,
+                            const uint8_t* seq_mask, float seq_scale, void* stream);
+/* seq_mask (optional, contiguous [B,H] keep flags) with seq_scale: seq_out = dropout(h') — the decoder's drop(h_1) fused
+ * into the cell (model.py:515-516).
+ * backward: (dh, dc_in, saved acts, c_prev, c_new) -> dgates [B,4H], dc_prev. dh2 (optional) is added to dh, through
+ * dh2_mask * dh2_scale when given (the gradient of the dropped copy).
  * Inactive rows (pos >= active[b]) pass dh/dc straight through into dh_pass/dc_prev and produce zero dgates.       */
 int dasa_lstm_pointwise_bwd(const float* dh, int64_t ld_dh, const float* dh2, int64_t ld_dh2, const float* dc,
                             int64_t ld_dc, const float* acts, int64_t ld_acts, const float* c_prev, int64_t ld_cp,
                             const float* c_new, int64_t ld_cn, float* dgates, int64_t ld_dg, float* dc_prev,
                             int64_t ld_dcp, float* dh_pass, int64_t ld_dhp, const int32_t* active, int pos,
-                            int B, int H, void* stream);
+                            int B, int H, const uint8_t* dh2_mask, float dh2_scale, void* stream);
 
 /* Fused recurrence of the packed bidirectional encoder LSTM (r2rmodel.py:2339-2357) for small batches (B <= 20,
  * H % 64 == 0): ONE call issues the whole time loop (one launch per step covering both directions; each CTA owns 16
