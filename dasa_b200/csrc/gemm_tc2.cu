@@ -237,6 +237,15 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const bool c_vec = ((p.ldc & 3) == 0) && (((reinterpret_cast<uintptr_t>(p.C[0]) | reinterpret_cast<uintptr_t>(p.C[1])) & 15) == 0) &&
                        ((p.split_stride & 3) == 0);
     const bool plain = c_vec && beta == 0.f && alpha == 1.f;
+    // sigmoid-gate epilogue (DGAdaChannel): the gate operand f, the keep mask and the saved gate are moved as 128-bit / 32-bit
+    // vectors, and f + mask of a whole 32 x 32 chunk are requested BEFORE the accumulator chunk is read from TMEM, so their DRAM
+    // latency hides behind the TMEM read and the shared-memory transpose instead of stalling every row of the chunk
+    bool gate_vec = false;
+    if constexpr (EPI == DASA_EPI_GATE) {
+      gate_vec = (p.ep.gate_src != nullptr) && ((reinterpret_cast<uintptr_t>(p.ep.gate_src) & 15) == 0) && ((p.ep.ld_gate & 3) == 0) &&
+                 (p.ep.gate_out == nullptr || (((reinterpret_cast<uintptr_t>(p.ep.gate_out) & 15) == 0) && ((p.ep.ld_gate_out & 3) == 0))) &&
+                 (p.ep.drop_mask == nullptr || (((reinterpret_cast<uintptr_t>(p.ep.drop_mask) & 3) == 0) && ((p.N & 3) == 0)));
+    }
     const uint32_t empty_remote0 = p_mapa(smem_u32(&tmem_empty[0]), 0);
     const uint32_t empty_remote1 = p_mapa(smem_u32(&tmem_empty[1]), 0);
     uint32_t tcount = 0;
@@ -252,6 +261,21 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool interior = plain && (m_base + 32 <= p.M) && (n_base + CW <= p.N);   // warp-uniform: no edge checks at all
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
+        float4 gsrc[8];
+        uint32_t gmask[8];
+        const bool gate_fast = (EPI == DASA_EPI_GATE) && gate_vec && interior;
+        if constexpr (EPI == DASA_EPI_GATE) {
+          if (gate_fast) {
+            const int ng = n_base + c0 + 4 * col4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int mg = m_base + 4 * i + rsub;
+              gsrc[i] = __ldg(reinterpret_cast<const float4*>(p.ep.gate_src + (int64_t)mg * p.ep.ld_gate + ng));
+              gmask[i] = (p.ep.drop_mask != nullptr) ? __ldg(reinterpret_cast<const uint32_t*>(p.ep.drop_mask + (int64_t)mg * p.N + ng))
+                                                     : 0x01010101u;
+            }
+          }
+        }
         uint32_t r[32];
         p_tmem_ld32(t_addr + (uint32_t)c0, r);
         if (c0 + 32 >= CW) {                               // last TMEM read of this buffer: hand it back to the MMA thread
@@ -274,6 +298,24 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               for (int e = 0; e < 4; ++e) bias4[e] = __ldg(p.ep.bias + n + e);
             }
           }
+          if (gate_fast) {
+            if constexpr (EPI == DASA_EPI_GATE) {
+              const float ds = (p.ep.drop_mask != nullptr) ? p.ep.drop_scale : 1.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = m_base + 4 * i + rsub;
+                const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * P_EPI_LD + 4 * col4);
+                const float4 sg = make_float4(sigmoidf_(a4.x + bias4[0]), sigmoidf_(a4.y + bias4[1]), sigmoidf_(a4.z + bias4[2]),
+                                              sigmoidf_(a4.w + bias4[3]));
+                if (p.ep.gate_out != nullptr) *reinterpret_cast<float4*>(p.ep.gate_out + (int64_t)m * p.ep.ld_gate_out + n) = sg;
+                const uint32_t mk = gmask[i];
+                const float4 f4 = gsrc[i];
+                *reinterpret_cast<float4*>(Cg + (int64_t)m * p.ldc + n) =
+                    make_float4(sg.x * f4.x * ((mk & 0xFFu) ? ds : 0.f), sg.y * f4.y * ((mk & 0xFF00u) ? ds : 0.f),
+                                sg.z * f4.z * ((mk & 0xFF0000u) ? ds : 0.f), sg.w * f4.w * ((mk & 0xFF000000u) ? ds : 0.f));
+              }
+            }
+          } else {
 #pragma unroll
           for (int rr = 0; rr < 32; rr += 4) {
             const int m = m_base + rr + rsub;
@@ -282,6 +324,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = apply_activation_t<EPI>(v[e] + bias4[e], m, n + e, p.N, p.ep);
             *reinterpret_cast<float4*>(Cg + (int64_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+          }
           }
         } else if (n < p.N) {
           const bool vec_ok = c_vec && (n + 3 < p.N);
