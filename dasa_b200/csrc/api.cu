@@ -37,6 +37,11 @@ extern "C" int dasa_gemm_layout_on_tensor_cores(int a_kmajor, int b_kmajor, int 
 extern "C" size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision) {
   size_t a = dasa_gemm_simt_workspace(M, N, K);
   size_t b = (precision == DASA_PREC_TF32) ? dasa_gemm_tc_workspace(M, N, K) : 0;
+  if (precision == DASA_PREC_TF32) {                   // MN-major operand layouts: split-K partials of few-tile long-K problems
+    const int s = dasa_gemm_pair_mn_splits(M, N, K);
+    const size_t c = s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+    if (c > b) b = c;
+  }
   return a > b ? a : b;
 }
 
@@ -52,7 +57,7 @@ extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float 
   if (precision == DASA_PREC_TF32 && dasa_gemm_skinny_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb))
     return dasa_gemm_skinny(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, st);
   if (precision == DASA_PREC_TF32 && dasa_gemm_pair_mn_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, epilogue))
-    return dasa_gemm_tc_pair_mn(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st);
+    return dasa_gemm_tc_pair_mn(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
   if (precision == DASA_PREC_TF32 && dasa_gemm_tc_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc))
     return dasa_gemm_tc(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
                         workspace_bytes, st);

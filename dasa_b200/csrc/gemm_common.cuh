@@ -91,8 +91,9 @@ int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, 
 // MN-major operand layouts on the pair kernel (no transposed copies for dX = dY.W and dW = dY^T.X), gemm_tc2.cu
 bool dasa_gemm_pair_mn_supported(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int64_t lda, const float* B,
                                  int64_t ldb, int epilogue);
+int dasa_gemm_pair_mn_splits(int M, int N, int K);     // K splits (1 = none) the MN-major path uses for this shape
 int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
-                         int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st);
+                         int64_t ldb, float beta, float* C, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st);
 // grouped (2 problems) / split-K launch of the pair kernel; returns the number of K splits actually used (>= 1) or a negative error
 int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st);

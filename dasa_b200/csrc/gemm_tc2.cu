@@ -475,23 +475,82 @@ bool dasa_gemm_pair_mn_supported(int a_kmajor, int b_kmajor, int M, int N, int K
   return dasa_gemm_pair_plan(M, N, K) == 256;
 }
 
+// Few-tile, long-K problems (the weight gradients: 4096 x 768 outputs reduced over 35 700 rows = 48 tiles for 74 CTA pairs): K is
+// split so that the tiles fill whole waves; partial sums go to the workspace and one pass folds them into C.
+int dasa_gemm_pair_mn_splits(int M, int N, int K) {
+  const int pairs = DASA_NUM_SMS / 2;
+  const int64_t tiles = dasa_cdiv(M, 2 * P_BM) * dasa_cdiv(N, 256);
+  const int64_t nkb = dasa_cdiv(K, P_BK);
+  if (tiles >= pairs || nkb < 64) return 1;
+  int best = 1;
+  double best_t = (double)dasa_cdiv(tiles, pairs);
+  for (int s = 2; s <= 4; ++s) {
+    const double t = (double)dasa_cdiv(tiles * s, pairs) / s;
+    if (t < best_t - 0.15) { best_t = t; best = s; }
+  }
+  return best;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) pair_split_reduce_kernel(const float* __restrict__ part, int splits, int64_t stride, float alpha,
+                                                                float beta, float* __restrict__ C, int64_t ldc, int M, int N) {
+  const int n4 = N >> 2;
+  const int64_t total = (int64_t)M * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / n4), n = (int)(i % n4) << 2;
+    float4 acc = *reinterpret_cast<const float4*>(part + (int64_t)m * N + n);
+    for (int sidx = 1; sidx < splits; ++sidx) {                 // fixed order: deterministic
+      const float4 v = *reinterpret_cast<const float4*>(part + sidx * stride + (int64_t)m * N + n);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* c = C + (int64_t)m * ldc + n;
+    if (beta != 0.f) {
+      acc.x = alpha * acc.x + beta * c[0]; acc.y = alpha * acc.y + beta * c[1];
+      acc.z = alpha * acc.z + beta * c[2]; acc.w = alpha * acc.w + beta * c[3];
+    } else {
+      acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+    }
+    c[0] = acc.x; c[1] = acc.y; c[2] = acc.z; c[3] = acc.w;
+  }
+}
+}  // namespace
+
 int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
-                         int64_t ldb, float beta, float* C, int64_t ldc, cudaStream_t st) {
+                         int64_t ldb, float beta, float* C, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   PairParams p{};
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C[0] = C; p.C[1] = C; p.ldc = ldc;
   p.tiles_n = (int)dasa_cdiv(N, 256);
   p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
   p.splits = 1; p.kb_per_split = (int)dasa_cdiv(K, P_BK); p.split_stride = 0;
   p.tiles_total = p.tiles_mn;
+  int splits = dasa_gemm_pair_mn_splits(M, N, K);
+  if ((N & 3) != 0 || workspace == nullptr || workspace_bytes < (size_t)splits * M * N * sizeof(float) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+    splits = 1;
+  if (splits > 1) {
+    const int nkb = (int)dasa_cdiv(K, P_BK);
+    p.kb_per_split = (int)dasa_cdiv(nkb, splits);
+    p.splits = (int)dasa_cdiv(nkb, p.kb_per_split);
+    p.split_stride = (int64_t)M * N;
+    p.C[0] = p.C[1] = static_cast<float*>(workspace);
+    p.ldc = N; p.alpha = 1.f; p.beta = 0.f;
+    p.tiles_total = p.tiles_mn * p.splits;
+  }
   p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
   CUtensorMap ta[2], tb[2];
   const bool oka = a_kmajor ? pair_make_map(&ta[0], A, M, K, lda, P_BM) : pair_make_map_mn(&ta[0], A, M, K, lda);
   const bool okb = b_kmajor ? pair_make_map(&tb[0], B, N, K, ldb, 128) : pair_make_map_mn(&tb[0], B, N, K, ldb);
   if (!oka || !okb) return DASA_ERR_UNSUPPORTED;
   ta[1] = ta[0]; tb[1] = tb[0];
-  if (a_kmajor) return launch_pair_e<256, 5, DASA_EPI_NONE, false, true>(ta, tb, p, st);
-  if (b_kmajor) return launch_pair_e<256, 5, DASA_EPI_NONE, true, false>(ta, tb, p, st);
-  return launch_pair_e<256, 5, DASA_EPI_NONE, true, true>(ta, tb, p, st);
+  int rc;
+  if (a_kmajor) rc = launch_pair_e<256, 5, DASA_EPI_NONE, false, true>(ta, tb, p, st);
+  else if (b_kmajor) rc = launch_pair_e<256, 5, DASA_EPI_NONE, true, false>(ta, tb, p, st);
+  else rc = launch_pair_e<256, 5, DASA_EPI_NONE, true, true>(ta, tb, p, st);
+  if (rc != DASA_OK || p.splits <= 1) return rc;
+  const int64_t work = (int64_t)M * (N >> 2);
+  const unsigned grid = (unsigned)(dasa_cdiv(work, 256) < (int64_t)DASA_NUM_SMS * 8 ? dasa_cdiv(work, 256) : (int64_t)DASA_NUM_SMS * 8);
+  pair_split_reduce_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(workspace), p.splits, p.split_stride, alpha, beta, C, ldc, M, N);
+  return dasa_check_launch("pair_split_reduce_kernel");
 }
 
 // Two independent problems of the same shape in ONE launch, optionally split along K (raw partial sums, no epilogue):

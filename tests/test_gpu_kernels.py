@@ -846,7 +846,8 @@ def test_linear_backward_helpers_tf32_mn_major():
         assert_close(outs[0][0], dy.double() @ w.double(), 3e-3, "dx (MN-major B)")
         assert_close(outs[0][1], dy.double().t() @ x.double(), 3e-3, "dw (MN-major A, B)")
         assert_close(outs[0][0], outs[1][0], 1e-5, "dx: MN-major vs transposed copy")
-        assert_close(outs[0][1], outs[1][1], 1e-5, "dw: MN-major vs transposed copy")
+        # the MN-major route splits this few-tile reduction over K (fp32 partial sums folded in a fixed order)
+        assert_close(outs[0][1], outs[1][1], 1e-4, "dw: MN-major vs transposed copy")
     finally:
         ops.use_mn_major = True
         ops.set_precision("fp32")
