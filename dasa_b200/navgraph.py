@@ -188,16 +188,32 @@ class NavGraph:
         return start, view, goal
 
     def hops(self):
-        """Number of moves the teacher needs from every start to every goal (follows next_hop)."""
+        """Number of moves the teacher needs from every start to every goal (follows next_hop); -1 across components."""
         if getattr(self, "_hops", None) is None:
             n = self.n
             h = np.full((n, n), -1, np.int64)
             for g in range(n):
+                col = self.dist64[:, g]
+                reach = np.nonzero(np.isfinite(col))[0]              # only g's own component (one scan of a multi-scan union)
                 # process sources in order of increasing distance to g so the successor is already known
-                for s in np.argsort(self.dist64[:, g]):
-                    if not np.isfinite(self.dist64[s, g]):
-                        continue
+                for s in reach[np.argsort(col[reach], kind="stable")]:
                     k = self.next_hop[s, g]
                     h[s, g] = 0 if k < 0 else h[self.nbr[s, k], g] + 1
             self._hops = h
         return self._hops
+
+    @staticmethod
+    def union(graphs, prefixes=None):
+        """Disjoint union of several graphs (one per scan, as R2RBatch keeps them: env.py:182-198) in ONE table set, so that a
+        batch may mix episodes from different scans: viewpoint ids are offset per graph, distances across graphs are inf and
+        next_hop is -1 there. names become '<prefix>_<name>' (the reference's long ids '<scan>_<viewpoint>')."""
+        nbrs, w, hd, el, pt, names = [], [], [], [], [], []
+        off = 0
+        for gi, g in enumerate(graphs):
+            pre = (prefixes[gi] if prefixes else "g%d" % gi) + "_"
+            for i in range(g.n):
+                nbrs.append([j + off for j in g.nbrs[i]])
+                w.append(list(g.weights[i])); hd.append(list(g.headings[i])); el.append(list(g.elevations[i]))
+                pt.append(list(g.points[i])); names.append(pre + g.names[i])
+            off += g.n
+        return NavGraph(nbrs, w, hd, el, pt, names)

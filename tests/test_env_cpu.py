@@ -66,3 +66,21 @@ def test_angle_tables_bitexact():
         for hb in (0, 7):
             want = E.angle_feature(g.headings[i][k] - hb * R30, g.elevations[i][k], 128)
             assert np.array_equal(np.tile(g.cand_angle[i, k, hb], 32), want)
+
+
+def test_union_of_scans():
+    """Several scans in one table set (a batch mixes scans, env.py:182-198 keeps one graph per scan): per-component tables equal
+    the single-graph ones, cross-scan distances are inf, the teacher never leaves its scan."""
+    g1, *_ = scenario(n=14, seed=1)
+    g2, *_ = scenario(n=20, seed=2)
+    u = NavGraph.union([g1, g2], ["scanA", "scanB"])
+    assert u.n == 34 and u.names[0].startswith("scanA_") and u.names[14].startswith("scanB_")
+    assert np.array_equal(u.dist64[:14, :14], g1.dist64) and np.array_equal(u.dist64[14:, 14:], g2.dist64)
+    assert np.isinf(u.dist64[:14, 14:]).all() and np.isinf(u.dist64[14:, :14]).all()
+    assert np.array_equal(u.next_hop[:14, :14], g1.next_hop) and np.array_equal(u.next_hop[14:, 14:], g2.next_hop)
+    assert (u.next_hop[:14, 14:] == -1).all()
+    assert np.array_equal(u.nbr[14:][u.nbr[14:] >= 0], g2.nbr[g2.nbr >= 0] + 14)
+    h = u.hops()
+    assert (h[:14, 14:] == -1).all() and np.array_equal(h[14:, 14:], g2.hops())
+    s, v, goal = u.sample_episodes(12, 0, min_hops=2, max_hops=5)
+    assert ((s < 14) == (goal < 14)).all()                      # start and goal always in the same scan

@@ -287,3 +287,20 @@ def test_env_properties_at_full_size():
     got = buf["cand_feat"][t][:, :env.dmax, :C]
     assert torch.equal(got[live[:, :env.dmax]], want[live[:, :env.dmax]])
     assert float(buf["cand_feat"][t][~live].abs().max()) == 0.0                         # END row and padding are zeros
+
+
+def test_env_on_a_union_of_scans():
+    """A batch that mixes episodes from two scans (disjoint union of two graphs in one table set): bit-exact vs the oracle."""
+    g1, *_ = scenario(n=14, seed=1)
+    g2, *_ = scenario(n=20, seed=2)
+    u = NavGraph.union([g1, g2], ["scanA", "scanB"])
+    T, C = 7, 32
+    g, rgb, dep, start, view, goal = scenario(B=8, T=T, C=C, seed=3, graph=u)
+    assert (start < 14).any() and (start >= 14).any()
+    cfg = _cfg(C)
+    ora = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+    ora.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+    steps = E.rollout(ora, T, C, cfg.angle_size, None)
+    env, buf, reward, mask, ended, vps, views = _device_rollout(g, rgb, dep, start, view, goal, T, None, cfg)
+    _compare(steps, g, buf, reward, mask, ended, vps, views, T)
+    env.check()
