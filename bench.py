@@ -199,7 +199,28 @@ def micro_rooflines(peak_gbs):
     add("adain_view_stats", 4 * (B * V * C + 4 * B * C), t)
     t = timeit(lambda: ops.row_attention_fwd(f, h_t, None, 5, 12, kl))
     add("shift_attention_fwd", 4 * (B * V * F + 2 * B * F + B * V + B * 5), t)
-    del g, o, d
+    # K1 in its GEMM-fused form (what the rollout runs): sigmoid(d W^T + b) * f * keep-mask, gate saved on the side — tensor-bound
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    prec = ops.get_precision()
+    ops.set_precision("tf32")
+    W = torch.randn(C, C, device=dev) / C ** 0.5
+    bias = torch.randn(C, device=dev) * 0.02
+    R = B * V
+    sgate = torch.empty(R, C, device=dev)
+    keep = (torch.rand(R, C, device=dev) >= 0.4).to(torch.uint8)
+    f2, d2, o2 = f.view(R, F), d.view(R, F), o.view(R, F)
+    t = timeit(lambda: ops.gemm(d2, F, 1, W, C, 1, o2, F, R, C, C, epilogue=ops.EPI_GATE, bias=bias, gate_src=f2, ld_gate=F,
+                                gate_out=sgate, ld_gate_out=C, drop_mask=keep, drop_scale=1 / 0.6))
+    ops.set_precision(prec)
+    out["adain_gate_gemm_fused"] = {"bound": "tensor", "achieved": 2.0 * R * C * C / t / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                    "frac": 2.0 * R * C * C / t / 1e12 / peak_tf, "batch": B,
+                                    "what": "tcgen05 TF32 GEMM %d x %d x %d with the sigmoid-gate epilogue (f strided in place, keep mask, gate "
+                                            "saved)" % (R, C, C)}
+    del g, o, d, sgate, keep, W
     B4 = 4096                                               # the large-batch plateau of the persistent pipelined kernel
     f4 = torch.rand(B4, V, F, device=dev)
     h4 = torch.randn(B4, F, device=dev) * 0.05
