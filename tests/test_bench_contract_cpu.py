@@ -1,0 +1,45 @@
+"""CPU tier: the committed bench lines (profiles/r01_bench_*.json, produced by bench.py on B200) carry every key of the driver's
+contract, and bench.py's argument surface matches it."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config", "clocks", "e2e", "gpu_launches", "roofline")
+
+
+def _load(name):
+    line = open(os.path.join(ROOT, "profiles", name)).read().strip()
+    assert line.count("\n") == 0, "one JSON line"
+    return json.loads(line)
+
+
+def test_bench_lines_follow_the_contract():
+    for name, n in (("r01_bench_n1.json", 1), ("r01_bench_n2.json", 2), ("r01_bench_n4.json", 4), ("r01_bench_n8.json", 8)):
+        d = _load(name)
+        for k in REQUIRED:
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+        r = d["roofline"]
+        assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r) and r["bound"] in ("hbm", "tensor")
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+        assert abs(d["value"] - 20 * 35 * n / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    d = _load("r01_bench_n1.json")
+    c = d["cpu_baseline"]
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("port", "reference")
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # weak scaling: the per-rank step at 8 GPUs stays within 15 % of the 1-GPU step of the same build (the n = 8 line was
+    # measured at the 32.4 ms build: 34.6 ms per step, 7.48x)
+    assert _load("r01_bench_n8.json")["ms_per_step"] <= 1.15 * 32.4
+
+
+def test_bench_cli_surface():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in out.stdout
