@@ -45,6 +45,16 @@ extern "C" size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision) 
   return a > b ? a : b;
 }
 
+// ---- which kernel family took each dasa_gemm call (host-side counters; tests assert the benchmarked configuration really runs
+// on the tensor-core kernels and that NO TF32-mode GEMM silently fell back to the FFMA kernel)
+int64_t g_gemm_routes[DASA_ROUTE_COUNT] = {0};
+
+extern "C" int dasa_debug_gemm_route_counts(int64_t* out, int n, int reset) {
+  for (int i = 0; i < n && i < DASA_ROUTE_COUNT; ++i) out[i] = g_gemm_routes[i];
+  if (reset) memset(g_gemm_routes, 0, sizeof(g_gemm_routes));
+  return DASA_OK;
+}
+
 extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
                          const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue,
                          const dasa_epilogue_t* epi, int precision, void* workspace, size_t workspace_bytes,
@@ -54,13 +64,34 @@ extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float 
   if (epilogue == DASA_EPI_GATE && (epi == nullptr || epi->gate_src == nullptr)) return DASA_ERR_BAD_SHAPE;
   const EpiParams ep = make_epi(epi);
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == DASA_PREC_TF32 && dasa_gemm_skinny_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb))
+  if (precision == DASA_PREC_TF32 && dasa_gemm_skinny_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb)) {
+    ++g_gemm_routes[DASA_ROUTE_SKINNY];
     return dasa_gemm_skinny(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, st);
-  if (precision == DASA_PREC_TF32 && dasa_gemm_pair_mn_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, epilogue))
+  }
+  if (precision == DASA_PREC_TF32 && dasa_gemm_pair_mn_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, epilogue)) {
+    ++g_gemm_routes[dasa_gemm_pair_mn_splits(M, N, K) > 1 ? DASA_ROUTE_PAIR_MN_SPLITK : DASA_ROUTE_PAIR_MN];
     return dasa_gemm_tc_pair_mn(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
-  if (precision == DASA_PREC_TF32 && dasa_gemm_tc_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc))
+  }
+  if (precision == DASA_PREC_TF32 && dasa_gemm_tc_supported(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc)) {
+    ++g_gemm_routes[dasa_gemm_pair_plan(M, N, K) ? DASA_ROUTE_PAIR : DASA_ROUTE_TC_SINGLE];
     return dasa_gemm_tc(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
                         workspace_bytes, st);
+  }
+  if (precision == DASA_PREC_TF32) {
+    // A K-major x K-major problem with K >= 32 lands here only through a misaligned base / leading dimension (TMA needs 16 B):
+    // counted separately and reported once, because it silently costs a tensor-core GEMM its ~10x.
+    const bool eligible = a_kmajor && b_kmajor && K >= 32 && M > 0 && N > 0;
+    ++g_gemm_routes[eligible ? DASA_ROUTE_SIMT_MISALIGNED : DASA_ROUTE_SIMT_TF32_MODE];
+    static bool warned = false;
+    if (eligible && !warned) {
+      warned = true;
+      fprintf(stderr, "dasa_b200: warning: TF32 GEMM M=%d N=%d K=%d fell back to the FFMA kernel (operand base / leading dimension "
+                      "not 16-byte aligned: A=%p lda=%lld B=%p ldb=%lld); see dasa_debug_gemm_route_counts\n",
+              M, N, K, (const void*)A, (long long)lda, (const void*)B, (long long)ldb);
+    }
+  } else {
+    ++g_gemm_routes[DASA_ROUTE_SIMT_FP32];
+  }
   return dasa_gemm_simt(a_kmajor, b_kmajor, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, epilogue, ep, workspace,
                         workspace_bytes, st);
 }

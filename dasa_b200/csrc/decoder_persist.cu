@@ -1,0 +1,1042 @@
+// Persistent decoder rollout (include/dasa_b200.h: dasa_decoder_rollout_fwd / _bwd): BAttnDecoderLSTM.forward
+// (model.py:472-574) and its backward for T consecutive actions in ONE cooperative launch.
+//
+// Why: at B = 20 episodes every projection of the decoder is a weight-streaming problem (84 MB of fp32 weights per action
+// for 0.8 GFLOP) and the per-op path spends ~250 us per action in ~28 dependent launches against a ~20 us streaming floor.
+// Here one CTA per SM stays resident for the whole rollout; the phases of an action are separated by a device-wide barrier
+// (one release-add + acquire-poll on an L2 word, ~1 us) instead of kernel boundaries.
+//
+//   GEMM phases   Y[b, n] = sum_k X[b, k] W[n, k]: a CTA owns 16 (or 32) rows of W and ALL of K; its 8 warps split K in
+//                 32-wide chunks, each lane streams its W rows straight from HBM with 128-bit no-allocate loads into
+//                 mma.sync.m16n8k8 TF32 A fragments (W rows = MMA M, the <= 32 episodes = MMA N), two chunks in flight per
+//                 warp; X (<= 32 x K, produced by the previous phase on other SMs) is read through L2 (ld.global.cg). The
+//                 K slices are folded across the warps in shared memory in a fixed order (deterministic), the epilogue
+//                 (bias / tanh / the whole LSTM cell / dropout of the next operand) runs on the folded tile.
+//   attention     a CTA owns (episode, channel slice): the [rows x slice] tile of the panorama / instruction context is
+//                 bulk-async copied (TMA engine, mbarrier completion) into shared memory ONE ACTION AHEAD, so the 19 MB of
+//                 per-action context stream under the GEMM phases; partial row dots go through an L2 scratch, the softmax
+//                 (+ circular heading shift) is recomputed by every slice owner, the weighted sum comes from the resident tile.
+//
+// The k-index trick of gemm_skinny.cu is used throughout: a lane loads 4 consecutive k of its rows and uses component j in
+// MMA step j for BOTH operands, so every global access is 128-bit and any bijection of the reduction index is a valid GEMM.
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int DP_THREADS = 256;
+constexpr int DP_WARPS = 8;
+constexpr int DP_CHUNK = 32;         // k per chunk
+constexpr int DP_MAXROWS = 128;      // attention rows (views / tokens)
+constexpr int DP_MAXK = 15;          // shift kernel taps
+
+// ------------------------------------------------------------------------------------------------ device-wide barrier
+struct GridBar {
+  unsigned int* ctr;
+  unsigned int target;
+  unsigned int nblk;
+};
+
+// All CTAs are co-resident (cooperative launch). Thread 0 publishes the CTA's writes (bar.sync orders the other threads'
+// writes before its gpu-scope release) and polls with acquire loads. Bounded: a protocol bug traps instead of hanging the box.
+__device__ __forceinline__ void grid_sync(GridBar& gb) {
+  gb.target += gb.nblk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+    unsigned int v, it = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      if (++it > (1u << 22)) __trap();
+    } while ((int)(v - gb.target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t dp_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void dp_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// data produced by OTHER SMs earlier in this launch: L2 is the point of coherence, never the (non-coherent) L1 / texture path
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+// Launders a pointer through an empty volatile asm: everything derived from it is computed AFTER this point. Without it the
+// compiler hoists the per-lane row addresses of all eight GEMM phases out of the rollout loop and keeps them live across every
+// phase (~100 registers): the K loops then spill.
+template <typename T>
+__device__ __forceinline__ T* dp_opaque(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+// component j of a float4 with j a compile-time constant after unrolling (no address-of: the fragments must stay in registers)
+__device__ __forceinline__ float f4_get(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+
+struct Slice { int c0, cn; };
+// channel slice s of S over D channels, float4-granular
+__device__ __host__ __forceinline__ Slice dp_slice(int D, int S, int s) {
+  const int n4 = D >> 2;
+  const int a = (int)(((int64_t)n4 * s) / S), b = (int)(((int64_t)n4 * (s + 1)) / S);
+  Slice r; r.c0 = 4 * a; r.cn = 4 * (b - a);
+  return r;
+}
+__host__ __device__ __forceinline__ int dp_chunk_pitch(int D, int S) { return (int)(((D >> 2) + S - 1) / S) * 4; }
+
+// ---------------------------------------------------------------------------------------------------- GEMM building block
+// One CTA-wide product: res[m][nl] = sum_k X[m, k] * W_row(nl)[k] for m < 8*MT (rows >= M read as zero), nl < 16*RT.
+// wrow[i] (i < 2*RT) = this lane's W row for local row g + 8*i, already offset by 4*t. K % 32 == 0.
+// red: DP_WARPS*RT*MT*128 floats, res: 16*RT*8*MT floats (shared memory). Ends with a __syncthreads: res is complete.
+template <int MT, int RT>
+struct GemmFrag {
+  float4 w[2 * RT][2];
+  float4 x[MT][2];
+};
+
+template <int MT, int RT>
+__device__ __forceinline__ void dp_load(GemmFrag<MT, RT>& f, const float* (&wrow)[2 * RT], const float* (&xrow)[MT],
+                                        const bool (&xok)[MT], int kc) {
+#pragma unroll
+  for (int i = 0; i < 2 * RT; ++i) {
+    f.w[i][0] = ldg_stream4(wrow[i] + kc);
+    f.w[i][1] = ldg_stream4(wrow[i] + kc + 16);
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    if (xok[i]) {
+      f.x[i][0] = ld_cg4(xrow[i] + kc);
+      f.x[i][1] = ld_cg4(xrow[i] + kc + 16);
+    } else {
+      f.x[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      f.x[i][1] = f.x[i][0];
+    }
+  }
+}
+
+template <int MT, int RT>
+__device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFrag<MT, RT>& f) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t bf[MT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      bf[i][0] = dp_tf32(f4_get(f.x[i][0], j));
+      bf[i][1] = dp_tf32(f4_get(f.x[i][1], j));
+    }
+#pragma unroll
+    for (int h = 0; h < RT; ++h) {
+      uint32_t af[4];
+      af[0] = dp_tf32(f4_get(f.w[2 * h][0], j));       // (row g,     k = t)
+      af[1] = dp_tf32(f4_get(f.w[2 * h + 1][0], j));   // (row g + 8, k = t)
+      af[2] = dp_tf32(f4_get(f.w[2 * h][1], j));       // (row g,     k = t + 4)
+      af[3] = dp_tf32(f4_get(f.w[2 * h + 1][1], j));   // (row g + 8, k = t + 4)
+#pragma unroll
+      for (int i = 0; i < MT; ++i) dp_mma(acc[h][i], af, bf[i][0], bf[i][1]);
+    }
+  }
+}
+
+template <int MT, int RT>
+__device__ __forceinline__ void dp_gemm_block(const float* (&wrow)[2 * RT], const float* X, int64_t ldx, int M, int K,
+                                              float* red, float* res) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float* xrow[MT];
+  bool xok[MT];
+  X = dp_opaque(X);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int m = 8 * i + g;
+    xok[i] = m < M;
+    xrow[i] = X + (int64_t)(xok[i] ? m : 0) * ldx + 4 * t;
+  }
+  float acc[RT][MT][4];
+#pragma unroll
+  for (int h = 0; h < RT; ++h)
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[h][i][e] = 0.f;
+
+  const int nchunks = K / DP_CHUNK;
+  GemmFrag<MT, RT> f0, f1;
+  int c = warp;
+  if (c < nchunks) dp_load<MT, RT>(f0, wrow, xrow, xok, c * DP_CHUNK);
+#pragma unroll 1
+  for (; c < nchunks; c += 2 * DP_WARPS) {
+    const bool has1 = c + DP_WARPS < nchunks;
+    if (has1) dp_load<MT, RT>(f1, wrow, xrow, xok, (c + DP_WARPS) * DP_CHUNK);
+    dp_compute<MT, RT>(acc, f0);
+    if (c + 2 * DP_WARPS < nchunks) dp_load<MT, RT>(f0, wrow, xrow, xok, (c + 2 * DP_WARPS) * DP_CHUNK);
+    if (has1) dp_compute<MT, RT>(acc, f1);
+  }
+
+  // fold the K slices of the 8 warps in warp order (deterministic)
+#pragma unroll
+  for (int h = 0; h < RT; ++h)
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[(((warp * RT + h) * MT + i) * 4 + e) * 32 + lane] = acc[h][i][e];
+  __syncthreads();
+  constexpr int NL = 16 * RT, OUTS = NL * 8 * MT;
+  for (int o = threadIdx.x; o < OUTS; o += DP_THREADS) {
+    const int nl = o % NL, m = o / NL;
+    const int h = nl >> 4, r16 = nl & 15, i = m >> 3, mm = m & 7;
+    const int e = (mm & 1) + (r16 >= 8 ? 2 : 0), ln = (r16 & 7) * 4 + (mm >> 1);
+    float s = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < DP_WARPS; ++w2) s += red[(((w2 * RT + h) * MT + i) * 4 + e) * 32 + ln];
+    res[o] = s;                      // res[m * NL + nl]
+  }
+  __syncthreads();
+}
+
+// plain row block: rows n0 .. n0+15 of W (clamped to N-1; the caller never stores rows >= N)
+__device__ __forceinline__ void dp_rows16(const float* (&wrow)[2], const float* W, int64_t ldw, int n0, int N) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int n = n0 + g + 8 * i;
+    n = n < N ? n : N - 1;
+    wrow[i] = W + (int64_t)n * ldw + 4 * t;
+  }
+}
+
+// --------------------------------------------------------------------------------------------- attention building blocks
+struct AttnSmem {
+  float* tile;       // [rows][pitch]
+  float* tv;         // [pitch] target slice
+  float* dv;         // [pitch] (bwd) upstream gradient slice
+  float* zrow;       // [DP_MAXROWS] logits / dq
+  float* prow;       // [DP_MAXROWS] softmax
+  float* wrow;       // [DP_MAXROWS] final weights (shifted q or alpha)
+  float* aux;        // [DP_MAXROWS] dz (bwd)
+  float* aux2;       // [DP_MAXROWS] dp (bwd)
+  float* kap;        // [16]
+  float* colred;     // [8 * 128 * 4] column partial sums of the weighted sum
+  uint64_t* bar;
+};
+
+// stage the unmasked rows of this CTA's channel slice with bulk-async copies (warp 0), completion on s.bar
+__device__ __forceinline__ void dp_issue_tile(float* tile, int pitch, uint64_t* bar, const float* src_b, int64_t ld_row, int rows,
+                                              int c0, int cn, const uint8_t* mask_b) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int mine = 0;
+    for (int r = lane; r < rows; r += 32) mine += (mask_b == nullptr || mask_b[r] == 0) ? 1 : 0;
+    const int nvalid = (int)__reduce_add_sync(0xffffffffu, (unsigned)mine);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)nvalid * (uint32_t)cn * 4u);
+    __syncwarp();
+    if (cn > 0)
+      for (int r = lane; r < rows; r += 32)
+        if (mask_b == nullptr || mask_b[r] == 0)
+          bulk_g2s(tile + (size_t)r * pitch, src_b + (int64_t)r * ld_row + c0, (uint32_t)cn * 4u, bar);
+  }
+}
+
+// partial row dots of the resident slice against vec (shared memory): zp[r] = tile[r, :cn] . vec ; masked rows -> 0
+__device__ __forceinline__ void dp_partial_dots(const float* tile, int pitch, const float* vec, int rows, int cn,
+                                                const uint8_t* mask_b, float* zp) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n4 = cn >> 2;
+  for (int r = wid; r < rows; r += DP_WARPS) {
+    float acc = 0.f;
+    if (mask_b == nullptr || mask_b[r] == 0) {
+      const float4* row = reinterpret_cast<const float4*>(tile + (size_t)r * pitch);
+      const float4* v4 = reinterpret_cast<const float4*>(vec);
+      for (int j = lane; j < n4; j += 32) {
+        const float4 a = row[j], b = v4[j];
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) zp[r] = acc;
+  }
+}
+
+// out[c0 + 4*col ..] = sum_r w[r] * tile[r, col]  over unmasked rows (w in shared memory); out may be any global row
+__device__ __forceinline__ void dp_weighted_sum(const AttnSmem& s, int pitch, int rows, int cn, const uint8_t* mask_b, const float* w,
+                                                float* out) {
+  const int n4 = cn >> 2;
+  if (n4 <= 0) return;
+  const int G = n4 >= DP_THREADS ? 1 : min(DP_THREADS / n4, 8);
+  const int passes = (n4 + DP_THREADS - 1) / DP_THREADS;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int col = (G > 1) ? (int)(threadIdx.x % n4) : (int)threadIdx.x + pass * DP_THREADS;
+    const int grp = (G > 1) ? (int)(threadIdx.x / n4) : 0;
+    const bool act = (col < n4) && (grp < G);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+      const float4* tp = reinterpret_cast<const float4*>(s.tile) + col;
+      const int p4 = pitch >> 2;
+      for (int r = grp; r < rows; r += G) {
+        if (mask_b != nullptr && mask_b[r] != 0) continue;
+        const float wr = w[r];
+        const float4 v = tp[(size_t)r * p4];
+        acc.x = fmaf(wr, v.x, acc.x); acc.y = fmaf(wr, v.y, acc.y); acc.z = fmaf(wr, v.z, acc.z); acc.w = fmaf(wr, v.w, acc.w);
+      }
+    }
+    if (G > 1) {
+      __syncthreads();
+      if (act) reinterpret_cast<float4*>(s.colred)[grp * n4 + col] = acc;
+      __syncthreads();
+      if (act && grp == 0)
+        for (int g2 = 1; g2 < G; ++g2) {
+          const float4 o = reinterpret_cast<const float4*>(s.colred)[g2 * n4 + col];
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+    }
+    if (act && grp == 0) *reinterpret_cast<float4*>(out + 4 * col) = acc;
+  }
+}
+
+// warp 0: z[r] = sum over the S slice partials (fixed order), masked softmax -> s.prow (0 for masked rows)
+__device__ __forceinline__ void dp_softmax_rows(const AttnSmem& s, const float* zpart_b, int S, int rows, const uint8_t* mask_b) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float z[DP_MAXROWS / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < DP_MAXROWS / 32; ++i) {
+      const int r = lane + 32 * i;
+      float v = -INFINITY;
+      if (r < rows && (mask_b == nullptr || mask_b[r] == 0)) {
+        v = 0.f;
+        for (int k = 0; k < S; ++k) v += ld_cg(zpart_b + (size_t)k * DP_MAXROWS + r);
+      }
+      z[i] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < DP_MAXROWS / 32; ++i) {
+      z[i] = (z[i] == -INFINITY) ? 0.f : expf(z[i] - mx);
+      sum += z[i];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < DP_MAXROWS / 32; ++i) {
+      const int r = lane + 32 * i;
+      if (r < rows) s.prow[r] = z[i] * inv;
+    }
+  }
+}
+
+struct SmemPlan {
+  int pitchF, pitchC;          // floats per tile row
+  size_t off_red, off_res, off_tileF, off_tileC, off_tv, off_dv, off_small, total;
+};
+
+__host__ __device__ inline SmemPlan dp_plan(int MT, int V, int L, int F, int D, int S) {
+  SmemPlan p;
+  p.pitchF = dp_chunk_pitch(F, S);
+  p.pitchC = dp_chunk_pitch(D, S);
+  size_t o = 0;
+  p.off_red = o; o += sizeof(float) * (size_t)DP_WARPS * 2 * MT * 128;
+  p.off_res = o; o += sizeof(float) * (size_t)32 * 8 * MT;
+  p.off_tileF = o; o += sizeof(float) * (size_t)V * p.pitchF;
+  p.off_tileC = o; o += sizeof(float) * (size_t)L * p.pitchC;
+  const int pm = p.pitchF > p.pitchC ? p.pitchF : p.pitchC;
+  p.off_tv = o; o += sizeof(float) * (size_t)pm;
+  p.off_dv = o; o += sizeof(float) * (size_t)pm;
+  p.off_small = o; o += sizeof(float) * (5 * DP_MAXROWS + 16 + 8 * 128 * 4) + 32;
+  p.total = (o + 127) & ~(size_t)127;
+  return p;
+}
+
+__device__ __forceinline__ AttnSmem dp_attn_smem(unsigned char* raw, const SmemPlan& pl, bool feat) {
+  float* small = reinterpret_cast<float*>(raw + pl.off_small);
+  AttnSmem s;
+  s.tv = reinterpret_cast<float*>(raw + pl.off_tv);
+  s.dv = reinterpret_cast<float*>(raw + pl.off_dv);
+  s.zrow = small; s.prow = small + DP_MAXROWS; s.wrow = small + 2 * DP_MAXROWS; s.aux = small + 3 * DP_MAXROWS;
+  s.aux2 = small + 4 * DP_MAXROWS;
+  s.kap = small + 5 * DP_MAXROWS;
+  s.colred = s.kap + 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.colred + 8 * 128 * 4);
+  s.tile = reinterpret_cast<float*>(raw + (feat ? pl.off_tileF : pl.off_tileC));
+  s.bar = bars + (feat ? 0 : 1);
+  return s;
+}
+
+// which (episode, channel slice) this CTA owns in the attention phases
+struct AttnOwner {
+  bool on;
+  int b, s;
+  Slice sl;
+  const uint8_t* mask_b;
+};
+__device__ __forceinline__ AttnOwner dp_owner(int B, int S, int width, const uint8_t* mask, int64_t mask_ld) {
+  AttnOwner o;
+  o.on = (int)blockIdx.x < B * S;
+  o.b = o.on ? (int)blockIdx.x / S : 0;
+  o.s = o.on ? (int)blockIdx.x % S : 0;
+  o.sl = dp_slice(width, S, o.s);
+  o.mask_b = (o.on && mask) ? mask + (int64_t)o.b * mask_ld : nullptr;
+  return o;
+}
+
+// ---- the GEMM phases (one function each)
+
+// The three 16-row GEMM phases of an action share ONE instance of the K loop (the phase picks operands and epilogue at run
+// time): with one inlined copy per phase the kernel grew to ~90k instructions and the compiler stopped keeping the operand
+// fragments in registers.
+template <int MT>
+__device__ __forceinline__ void fwd_gemm16(const dasa_decoder_fwd_t& a, const int t, const int ph, float* red, float* res) {
+  const int T = a.T, B = a.B, H = a.H, E = a.E, F = a.F, D = a.D, NK = a.NK;
+  const int KX = E + F + H, DC = D + H;
+  const int tid = threadIdx.x;
+  const int64_t tb = (int64_t)t * B;
+  const float scale = a.drop_scale;
+  const float* W; const float* X;
+  int64_t ldw, ldx;
+  int N, K;
+  if (ph == 0)      { W = a.w_feat;    ldw = H;  N = NK; K = H;  X = a.hprev_drop + tb * H; ldx = H; }    // P1: tk = W_feat drop(h~) + b
+  else if (ph == 4) { W = a.w_att_in;  ldw = H;  N = D;  K = H;  X = a.cat + tb * DC + D;   ldx = DC; }   // P4: t2 = W_att_in drop(h_1)
+  else              { W = a.w_att_out; ldw = DC; N = H;  K = DC; X = a.cat + tb * DC;       ldx = DC; }   // P6: h~ = tanh(W_att_out [wc ; drop(h_1)])
+  W = dp_opaque(W);
+  const int nitems = (N + 15) / 16;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const float* wrow[2];
+    dp_rows16(wrow, W, ldw, item * 16, N);
+    dp_gemm_block<MT, 1>(wrow, X, ldx, B, K, red, res);
+    for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
+      const int m = o >> 4, n = item * 16 + (o & 15);
+      if (m >= B || n >= N) continue;
+      if (ph == 0) {
+        a.tk[(tb + m) * NK + n] = res[o] + __ldg(a.b_feat + n);
+      } else if (ph == 4) {
+        a.t2[(tb + m) * D + n] = res[o];
+      } else {
+        const float v = tanhf(res[o]);
+        a.htilde[(tb + m) * H + n] = v;
+        if (t + 1 < T) {
+          a.xh[(tb + B + m) * KX + E + F + n] = v;
+          const int64_t mi = (tb + B + m) * H + n;
+          a.hprev_drop[mi] = a.m_hprev ? (a.m_hprev[mi] ? v * scale : 0.f) : v;
+        }
+      }
+    }
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void fwd_p3(const dasa_decoder_fwd_t& a, const int t, float* red, float* res) {
+  const int T = a.T, B = a.B, H = a.H, E = a.E, F = a.F, D = a.D, NK = a.NK;
+  const int KX = E + F + H, DC = D + H;
+  const int tid = threadIdx.x;
+  const int64_t tb = (int64_t)t * B;
+  const float scale = a.drop_scale;
+  (void)T; (void)NK; (void)KX; (void)DC; (void)scale; (void)tb; (void)tid;
+    {
+      const float* X = a.xh + tb * KX;
+      const int nitems = H / 8;
+      const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const float* wrow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wrow[i] = dp_opaque(a.w_lstm) + (int64_t)(i * H + item * 8 + g) * KX + 4 * tq;
+        dp_gemm_block<MT, 2>(wrow, X, KX, B, KX, red, res);
+        for (int o = tid; o < 8 * MT * 8; o += DP_THREADS) {
+          const int m = o >> 3, j = o & 7, u = item * 8 + j;
+          if (m >= B) continue;
+          float gt[4];
+#pragma unroll
+          for (int qg = 0; qg < 4; ++qg) gt[qg] = res[m * 32 + qg * 8 + j] + __ldg(a.b_ih + qg * H + u) + __ldg(a.b_hh + qg * H + u);
+          const float ig = sigmoidf_(gt[0]), fg = sigmoidf_(gt[1]), gg = tanhf(gt[2]), og = sigmoidf_(gt[3]);
+          const float cp = ld_cg(a.c + (tb + m) * H + u);
+          const float c1 = fg * cp + ig * gg;
+          const float h1 = og * tanhf(c1);
+          float* ac = a.acts + (tb + m) * 4 * H;
+          ac[u] = ig; ac[H + u] = fg; ac[2 * H + u] = gg; ac[3 * H + u] = og;
+          a.c[(tb + B + m) * H + u] = c1;
+          a.h1[(tb + m) * H + u] = h1;
+          const int64_t mi = (tb + m) * H + u;
+          a.cat[(tb + m) * DC + D + u] = a.m_h1 ? (a.m_h1[mi] ? h1 * scale : 0.f) : h1;
+        }
+      }
+    }
+}
+
+// ---- attention phases: NOT inlined, so that none of their state is live across the register-hungry GEMM phases
+__device__ __noinline__ void fwd_issue_feat(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)t * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row, a.V,
+                o.sl.c0, o.sl.cn, nullptr);
+}
+__device__ __noinline__ void fwd_issue_ctx(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)t * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, a.L,
+                o.sl.c0, o.sl.cn, o.mask_b);
+}
+
+// P2a: partial view logits of this CTA's channel slice
+__device__ __noinline__ void fwd_p2a(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  const int tid = threadIdx.x;
+  const int64_t tb = (int64_t)t * a.B;
+  const float* tk_b = a.tk + (tb + o.b) * a.NK;
+  for (int c = tid; c < o.sl.cn; c += DP_THREADS) sf.tv[c] = ld_cg(tk_b + o.sl.c0 + c);
+  __syncthreads();
+  mbar_wait(sf.bar, (uint32_t)(t & 1));
+  dp_partial_dots(sf.tile, pl.pitchF, sf.tv, a.V, o.sl.cn, nullptr, a.zpart + ((size_t)o.b * S + o.s) * DP_MAXROWS);
+}
+
+// P2b: softmax over the views, circular heading shift, weighted sum -> xh[:, E + slice]; then prefetch the next action's tile
+__device__ __noinline__ void fwd_p2b(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  const int tid = threadIdx.x, V = a.V, F = a.F, E = a.E, NK = a.NK, KX = a.E + a.F + a.H;
+  const int64_t tb = (int64_t)t * a.B;
+  dp_softmax_rows(sf, a.zpart + (size_t)o.b * S * DP_MAXROWS, S, V, nullptr);
+  if (tid < 32) {
+    const int k = a.shift_k, lane = tid;
+    const float kl = (lane < k) ? ld_cg(a.tk + (tb + o.b) * NK + F + lane) : -INFINITY;
+    const float kmx = warp_max(kl);
+    const float e = (lane < k) ? expf(kl - kmx) : 0.f;
+    const float ksum = warp_sum(e);
+    if (lane < k) {
+      sf.kap[lane] = e / ksum;
+      if (o.s == 0) a.kappa[(tb + o.b) * k + lane] = e / ksum;
+    }
+  }
+  __syncthreads();
+  {
+    const int k = a.shift_k, half = k / 2, Hn = a.headings;
+    for (int r = tid; r < V; r += DP_THREADS) {
+      const int e = r / Hn, l = r % Hn;
+      float qv = 0.f;
+      for (int j = 0; j < k; ++j) {
+        int src = (l + j - half) % Hn;
+        if (src < 0) src += Hn;
+        qv = fmaf(sf.kap[j], sf.prow[e * Hn + src], qv);
+      }
+      sf.wrow[r] = qv;
+      if (o.s == 0) {
+        a.p[(tb + o.b) * V + r] = sf.prow[r];
+        a.q[(tb + o.b) * V + r] = qv;
+      }
+    }
+  }
+  __syncthreads();
+  dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.wrow, a.xh + (tb + o.b) * KX + E + o.sl.c0);
+  __syncthreads();                                     // every thread is done with the tile: prefetch the next action's
+  if (t + 1 < a.T)
+    dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)(t + 1) * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row,
+                  V, o.sl.c0, o.sl.cn, nullptr);
+}
+
+// P5a: partial token logits
+__device__ __noinline__ void fwd_p5a(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  const int tid = threadIdx.x;
+  const int64_t tb = (int64_t)t * a.B;
+  const float* t2_b = a.t2 + (tb + o.b) * a.D;
+  for (int c = tid; c < o.sl.cn; c += DP_THREADS) sc.tv[c] = ld_cg(t2_b + o.sl.c0 + c);
+  __syncthreads();
+  mbar_wait(sc.bar, (uint32_t)(t & 1));
+  dp_partial_dots(sc.tile, pl.pitchC, sc.tv, a.L, o.sl.cn, o.mask_b, a.zpart + ((size_t)o.b * S + o.s) * DP_MAXROWS);
+}
+
+// P5b: masked softmax over the tokens, weighted context -> cat[:, slice]; then prefetch the next action's tile
+__device__ __noinline__ void fwd_p5b(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  const int tid = threadIdx.x, L = a.L, DC = a.D + a.H;
+  const int64_t tb = (int64_t)t * a.B;
+  dp_softmax_rows(sc, a.zpart + (size_t)o.b * S * DP_MAXROWS, S, L, o.mask_b);
+  __syncthreads();
+  if (o.s == 0)
+    for (int r = tid; r < L; r += DP_THREADS) a.alpha[(tb + o.b) * L + r] = sc.prow[r];
+  dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.prow, a.cat + (tb + o.b) * DC + o.sl.c0);
+  __syncthreads();
+  if (t + 1 < a.T)
+    dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)(t + 1) * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, L,
+                  o.sl.c0, o.sl.cn, o.mask_b);
+}
+
+__device__ __noinline__ void fwd_prologue(const dasa_decoder_fwd_t& a) {
+  const int B = a.B, H = a.H, E = a.E, KX = a.E + a.F + a.H;
+  const int gtid = blockIdx.x * DP_THREADS + threadIdx.x, gthreads = gridDim.x * DP_THREADS;
+  const float scale = a.drop_scale;
+  // recurrent state of action 0, action embeddings of every action into the [x ; h] rows
+  for (int i = gtid; i < B * H; i += gthreads) {
+    const int b = i / H, n = i % H;
+    const float h = __ldg(a.h0 + i);
+    a.xh[(int64_t)b * KX + E + a.F + n] = h;
+    a.hprev_drop[i] = a.m_hprev ? (a.m_hprev[i] ? h * scale : 0.f) : h;
+    a.c[i] = __ldg(a.c0 + i);
+  }
+  for (int i = gtid; i < a.T * B * E; i += gthreads) {
+    const int r = i / E, e = i % E;
+    a.xh[(int64_t)r * KX + e] = __ldg(a.emb + i);
+  }
+}
+
+// ============================================================================================================== FORWARD
+template <int MT>
+__global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_fwd_kernel(const __grid_constant__ dasa_decoder_fwd_t a, const int S,
+                                                                            const __grid_constant__ SmemPlan pl) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* red = reinterpret_cast<float*>(smem_raw + pl.off_red);
+  float* res = reinterpret_cast<float*>(smem_raw + pl.off_res);
+  GridBar gb{a.barrier, 0u, gridDim.x};
+  if (threadIdx.x == 0) {
+    const AttnSmem sf = dp_attn_smem(smem_raw, pl, true), sc = dp_attn_smem(smem_raw, pl, false);
+    mbar_init(sf.bar, 1); mbar_init(sc.bar, 1); mbar_fence_init();
+  }
+  __syncthreads();
+  fwd_issue_feat(a, pl, smem_raw, S, 0);          // the tiles of action 0 stream in under the prologue and P1
+  fwd_issue_ctx(a, pl, smem_raw, S, 0);
+  fwd_prologue(a);
+  grid_sync(gb);
+  for (int t = 0; t < a.T; ++t) {
+#pragma unroll 1
+    for (int ph = 0; ph < 8; ++ph) {
+      switch (ph) {
+        case 1: fwd_p2a(a, pl, smem_raw, S, t); break;
+        case 2: fwd_p2b(a, pl, smem_raw, S, t); break;
+        case 3: fwd_p3<MT>(a, t, red, res); break;          // gates + LSTM cell (CTA = 8 units x 4 gates)
+        case 5: fwd_p5a(a, pl, smem_raw, S, t); break;
+        case 6: fwd_p5b(a, pl, smem_raw, S, t); break;
+        default: fwd_gemm16<MT>(a, t, ph, red, res); break;   // P1 (ph 0), P4 (ph 4), P6 (ph 7)
+      }
+      grid_sync(gb);
+    }
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const int t, const int ph, float* red, float* res) {
+  const int B = a.B, H = a.H, D = a.D, NK = a.NK;
+  const int DC = D + H;
+  const int tid = threadIdx.x;
+  const int64_t tb = (int64_t)t * B;
+  const float scale = a.drop_scale;
+  const float* W; const float* X;
+  int64_t ldw, ldx;
+  int N, K;
+  if (ph == 0)      { W = a.w_att_out_t; ldw = a.ld_w_att_out_t; N = DC; K = H;  X = a.du + tb * H;   ldx = H; }    // B6: dcat = du W_att_out
+  else if (ph == 3) { W = a.w_att_in_t;  ldw = a.ld_w_att_in_t;  N = H;  K = D;  X = a.dt2 + tb * D;  ldx = D; }    // B4: dh1d, LSTM cell backward
+  else              { W = a.w_feat_t;    ldw = a.ld_w_feat_t;    N = H;  K = NK; X = a.dtk + tb * NK; ldx = NK; }   // B1: dh~_{t-1}, du_{t-1}
+  W = dp_opaque(W);
+  const int nitems = (N + 15) / 16;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const float* wrow[2];
+    dp_rows16(wrow, W, ldw, item * 16, N);
+    dp_gemm_block<MT, 1>(wrow, X, ldx, B, K, red, res);
+    for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
+      const int m = o >> 4, n = item * 16 + (o & 15);
+      if (m >= B || n >= N) continue;
+      if (ph == 0) {
+        a.dcat[(int64_t)m * DC + n] = res[o];
+      } else if (ph == 3) {
+        const int u = n;
+        const int64_t mi = (tb + m) * H + u;
+        const float dh1d = res[o] + ld_cg(a.dcat + (int64_t)m * DC + D + u);
+        float dhv = a.m_h1 ? (a.m_h1[mi] ? dh1d * scale : 0.f) : dh1d;
+        if (a.d_h1) dhv += __ldg(a.d_h1 + mi);
+        const float* ac = a.acts + (tb + m) * 4 * H;
+        const float ig = __ldg(ac + u), fg = __ldg(ac + H + u), gg = __ldg(ac + 2 * H + u), og = __ldg(ac + 3 * H + u);
+        const float cp = __ldg(a.c + mi);
+        const float tc = tanhf(__ldg(a.c + (tb + B + m) * H + u));
+        const float dcv = ld_cg(a.dc_carry + (int64_t)m * H + u);
+        const float dct = dcv + dhv * og * (1.f - tc * tc);
+        float* dg = a.dgates + (tb + m) * 4 * H;
+        dg[u] = dct * gg * ig * (1.f - ig);
+        dg[H + u] = dct * cp * fg * (1.f - fg);
+        dg[2 * H + u] = dct * ig * (1.f - gg * gg);
+        dg[3 * H + u] = dhv * tc * og * (1.f - og);
+        a.dc_carry[(int64_t)m * H + u] = dct * fg;
+      } else {
+        const int64_t mi = (tb + m) * H + n;
+        float v = res[o];
+        v = a.m_hprev ? (a.m_hprev[mi] ? v * scale : 0.f) : v;
+        v += ld_cg(a.dhdir + (int64_t)m * H + n);
+        if (t > 0) {
+          const int64_t pj = mi - (int64_t)B * H;
+          const float ht = __ldg(a.htilde + pj);
+          a.du[pj] = (__ldg(a.d_htilde + pj) + v) * (1.f - ht * ht);
+        } else {
+          a.dh0[(int64_t)m * H + n] = v;
+        }
+      }
+    }
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void bwd_b3(const dasa_decoder_bwd_t& a, const int t, float* red, float* res) {
+  const int T = a.T, B = a.B, H = a.H, E = a.E, F = a.F, D = a.D, NK = a.NK;
+  const int KX = E + F + H, DC = D + H;
+  const int tid = threadIdx.x;
+  const int64_t tb = (int64_t)t * B;
+  const float scale = a.drop_scale;
+  (void)T; (void)NK; (void)KX; (void)DC; (void)scale; (void)tb; (void)tid;
+    {
+      const float* X = a.dgates + tb * 4 * H;
+      const int nitems = (KX + 31) / 32;
+      const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const float* wrow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int n = item * 32 + g + 8 * i;
+          n = n < KX ? n : KX - 1;
+          wrow[i] = dp_opaque(a.w_lstm_t) + (int64_t)n * a.ld_w_lstm_t + 4 * tq;
+        }
+        dp_gemm_block<MT, 2>(wrow, X, 4 * H, B, 4 * H, red, res);
+        for (int o = tid; o < 32 * 8 * MT; o += DP_THREADS) {
+          const int m = o >> 5, n = item * 32 + (o & 31);
+          if (m >= B || n >= KX) continue;
+          const float v = res[o];
+          if (n < E) a.demb[(tb + m) * E + n] = v;
+          else if (n < E + F) a.dattn[(int64_t)m * F + (n - E)] = v;
+          else a.dhdir[(int64_t)m * H + (n - E - F)] = v;
+        }
+      }
+    }
+}
+
+__device__ __noinline__ void bwd_issue_feat(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)t * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row, a.V,
+                o.sl.c0, o.sl.cn, nullptr);
+}
+__device__ __noinline__ void bwd_issue_ctx(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)t * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, a.L,
+                o.sl.c0, o.sl.cn, o.mask_b);
+}
+
+// B5a: partial dalpha_l = ctx_l . dwc   (par = parity of the tile's mbarrier phase)
+__device__ __noinline__ void bwd_b5a(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t, uint32_t par) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  const int tid = threadIdx.x, D = a.D, DC = a.D + a.H;
+  const int64_t tb = (int64_t)t * a.B;
+  for (int c = tid; c < o.sl.cn; c += DP_THREADS) {
+    sc.dv[c] = ld_cg(a.dcat + (int64_t)o.b * DC + o.sl.c0 + c);
+    sc.tv[c] = __ldg(a.t2 + (tb + o.b) * D + o.sl.c0 + c);
+  }
+  __syncthreads();
+  mbar_wait(sc.bar, par);
+  dp_partial_dots(sc.tile, pl.pitchC, sc.dv, a.L, o.sl.cn, o.mask_b, a.zpart + ((size_t)o.b * S + o.s) * DP_MAXROWS);
+}
+
+// B5b: dz = alpha (dalpha - sum alpha dalpha); dt2 slice; dctx slice; then prefetch the previous action's tile
+__device__ __noinline__ void bwd_b5b(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  const int tid = threadIdx.x, L = a.L, D = a.D;
+  const int64_t tb = (int64_t)t * a.B;
+  const float* zp = a.zpart + (size_t)o.b * S * DP_MAXROWS;
+  if (tid < 32) {
+    const int lane = tid;
+    float pd = 0.f;
+    for (int r = lane; r < L; r += 32) {
+      const bool ok = o.mask_b == nullptr || o.mask_b[r] == 0;
+      float v = 0.f;
+      if (ok) for (int k = 0; k < S; ++k) v += ld_cg(zp + (size_t)k * DP_MAXROWS + r);
+      const float al = ok ? __ldg(a.alpha + (tb + o.b) * L + r) : 0.f;
+      sc.zrow[r] = v;
+      sc.prow[r] = al;
+      pd = fmaf(al, v, pd);
+    }
+    pd = warp_sum(pd);
+    __syncwarp();
+    for (int r = lane; r < L; r += 32) sc.aux[r] = sc.prow[r] * (sc.zrow[r] - pd);
+  }
+  __syncthreads();
+  dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.aux, a.dt2 + (tb + o.b) * D + o.sl.c0);      // dt2[c] = sum_l dz_l ctx[l, c]
+  {                                                     // dctx[l, c] = alpha_l dwc[c] + dz_l t2[c]   (zero rows where masked)
+    const int n4 = o.sl.cn >> 2;
+    float* dst_b = a.dctx + ((tb + o.b) * L) * (int64_t)D + o.sl.c0;
+    for (int i = tid; i < L * n4; i += DP_THREADS) {
+      const int r = i / n4, col = i % n4;
+      const float wr = sc.prow[r], dz = sc.aux[r];
+      const float4 dw = reinterpret_cast<const float4*>(sc.dv)[col];
+      const float4 tv = reinterpret_cast<const float4*>(sc.tv)[col];
+      const float4 ov = make_float4(fmaf(wr, dw.x, dz * tv.x), fmaf(wr, dw.y, dz * tv.y), fmaf(wr, dw.z, dz * tv.z),
+                                    fmaf(wr, dw.w, dz * tv.w));
+      stg_stream4(dst_b + (int64_t)r * D + 4 * col, ov);
+    }
+  }
+  __syncthreads();
+  if (t > 0)
+    dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)(t - 1) * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, L,
+                  o.sl.c0, o.sl.cn, o.mask_b);
+}
+
+// B2a: partial dq_v = feat_v . dattn
+__device__ __noinline__ void bwd_b2a(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t, uint32_t par) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  const int tid = threadIdx.x, F = a.F;
+  const int64_t tb = (int64_t)t * a.B;
+  for (int c = tid; c < o.sl.cn; c += DP_THREADS) {
+    sf.dv[c] = ld_cg(a.dattn + (int64_t)o.b * F + o.sl.c0 + c);
+    sf.tv[c] = __ldg(a.tk + (tb + o.b) * a.NK + o.sl.c0 + c);
+  }
+  __syncthreads();
+  mbar_wait(sf.bar, par);
+  dp_partial_dots(sf.tile, pl.pitchF, sf.dv, a.V, o.sl.cn, nullptr, a.zpart + ((size_t)o.b * S + o.s) * DP_MAXROWS);
+}
+
+// B2b: undo the shift, dz, dt slice, dfeat slice, dkappa logits; then prefetch the previous action's tile
+__device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  const int tid = threadIdx.x, V = a.V, F = a.F, NK = a.NK;
+  const int64_t tb = (int64_t)t * a.B;
+  const float* zp = a.zpart + (size_t)o.b * S * DP_MAXROWS;
+  float* dtk_b = a.dtk + (tb + o.b) * NK;
+  if (tid < 32) {
+    const int lane = tid, k = a.shift_k, half = k / 2, Hn = a.headings;
+    float* dq = sf.zrow;
+    float* dp = sf.aux2;
+    for (int r = lane; r < V; r += 32) {
+      float v = 0.f;
+      for (int kk = 0; kk < S; ++kk) v += ld_cg(zp + (size_t)kk * DP_MAXROWS + r);
+      dq[r] = v;
+      sf.prow[r] = __ldg(a.p + (tb + o.b) * V + r);
+      sf.wrow[r] = __ldg(a.q + (tb + o.b) * V + r);
+    }
+    if (lane < k) sf.kap[lane] = __ldg(a.kappa + (tb + o.b) * k + lane);
+    __syncwarp();
+    for (int r = lane; r < V; r += 32) {
+      const int e = r / Hn, m = r % Hn;
+      float v = 0.f;
+      for (int j = 0; j < k; ++j) {
+        int src = (m - j + half) % Hn;
+        if (src < 0) src += Hn;
+        v = fmaf(sf.kap[j], dq[e * Hn + src], v);
+      }
+      dp[r] = v;
+    }
+    // dkappa_j = sum_{e,l} dq[e,l] p[e,(l+j-half) mod Hn];  dkappa_logit = kappa (dkappa - sum kappa dkappa)
+    float dk_mine = 0.f, dot = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float part = 0.f;
+      for (int r = lane; r < V; r += 32) {
+        const int e = r / Hn, l = r % Hn;
+        int src = (l + j - half) % Hn;
+        if (src < 0) src += Hn;
+        part = fmaf(dq[r], sf.prow[e * Hn + src], part);
+      }
+      part = warp_sum(part);
+      dot = fmaf(sf.kap[j], part, dot);
+      if (lane == j) dk_mine = part;
+    }
+    if (o.s == 0) {
+      if (lane < k) dtk_b[F + lane] = sf.kap[lane] * (dk_mine - dot);
+      for (int c = F + k + lane; c < NK; c += 32) dtk_b[c] = 0.f;       // padding columns of the stacked projection
+    }
+    __syncwarp();
+    float pd = 0.f;
+    for (int r = lane; r < V; r += 32) pd = fmaf(sf.prow[r], dp[r], pd);
+    pd = warp_sum(pd);
+    for (int r = lane; r < V; r += 32) sf.aux[r] = sf.prow[r] * (dp[r] - pd);
+  }
+  __syncthreads();
+  dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.aux, dtk_b + o.sl.c0);     // dt[c] = sum_v dz_v feat[v, c]
+  {                                                     // dfeat[v, c] = q_v dattn[c] + dz_v t[c]
+    const int n4 = o.sl.cn >> 2;
+    float* dst_b = a.dfeat + (int64_t)t * a.dfeat_ld_t + (int64_t)o.b * a.dfeat_ld_b + o.sl.c0;
+    for (int i = tid; i < V * n4; i += DP_THREADS) {
+      const int r = i / n4, col = i % n4;
+      const float wr = sf.wrow[r], dz = sf.aux[r];
+      const float4 dw = reinterpret_cast<const float4*>(sf.dv)[col];
+      const float4 tv = reinterpret_cast<const float4*>(sf.tv)[col];
+      const float4 ov = make_float4(fmaf(wr, dw.x, dz * tv.x), fmaf(wr, dw.y, dz * tv.y), fmaf(wr, dw.z, dz * tv.z),
+                                    fmaf(wr, dw.w, dz * tv.w));
+      stg_stream4(dst_b + (int64_t)r * a.dfeat_ld_row + 4 * col, ov);
+    }
+  }
+  __syncthreads();
+  if (t > 0)
+    dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)(t - 1) * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row, V,
+                  o.sl.c0, o.sl.cn, nullptr);
+}
+
+__device__ __noinline__ void bwd_prologue(const dasa_decoder_bwd_t& a) {
+  const int B = a.B, H = a.H;
+  const int gtid = blockIdx.x * DP_THREADS + threadIdx.x, gthreads = gridDim.x * DP_THREADS;
+  for (int i = gtid; i < B * H; i += gthreads) {      // du of the last action, zero cell-state gradient
+    const int64_t j = (int64_t)(a.T - 1) * B * H + i;
+    const float ht = __ldg(a.htilde + j);
+    a.du[j] = __ldg(a.d_htilde + j) * (1.f - ht * ht);
+    a.dc_carry[i] = a.d_c_last ? __ldg(a.d_c_last + i) : 0.f;
+  }
+}
+
+// ============================================================================================================= BACKWARD
+template <int MT>
+__global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(const __grid_constant__ dasa_decoder_bwd_t a, const int S,
+                                                                            const __grid_constant__ SmemPlan pl) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* red = reinterpret_cast<float*>(smem_raw + pl.off_red);
+  float* res = reinterpret_cast<float*>(smem_raw + pl.off_res);
+  GridBar gb{a.barrier, 0u, gridDim.x};
+  if (threadIdx.x == 0) {
+    const AttnSmem sf = dp_attn_smem(smem_raw, pl, true), sc = dp_attn_smem(smem_raw, pl, false);
+    mbar_init(sf.bar, 1); mbar_init(sc.bar, 1); mbar_fence_init();
+  }
+  __syncthreads();
+  bwd_issue_feat(a, pl, smem_raw, S, a.T - 1);    // the tiles of the LAST action stream in under the prologue and B6
+  bwd_issue_ctx(a, pl, smem_raw, S, a.T - 1);
+  bwd_prologue(a);
+  grid_sync(gb);
+  for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
+    const uint32_t par = (uint32_t)(it & 1);
+#pragma unroll 1
+    for (int ph = 0; ph < 8; ++ph) {
+      switch (ph) {
+        case 1: bwd_b5a(a, pl, smem_raw, S, t, par); break;
+        case 2: bwd_b5b(a, pl, smem_raw, S, t); break;
+        case 4: bwd_b3<MT>(a, t, red, res); break;          // d[x ; h] = dgates [W_ih | W_hh]
+        case 5: bwd_b2a(a, pl, smem_raw, S, t, par); break;
+        case 6: bwd_b2b(a, pl, smem_raw, S, t); break;
+        default: bwd_gemm16<MT>(a, t, ph, red, res); break;   // B6 (ph 0), B4 (ph 3), B1 (ph 7)
+      }
+      grid_sync(gb);
+    }
+  }
+  const int gtid = blockIdx.x * DP_THREADS + threadIdx.x, gthreads = gridDim.x * DP_THREADS;
+  for (int i = gtid; i < a.B * a.H; i += gthreads) a.dc0[i] = ld_cg(a.dc_carry + i);
+}
+
+// ------------------------------------------------------------------------------------------------------------- host side
+struct LaunchPlan {
+  int grid, S, MT;
+  SmemPlan pl;
+  bool ok;
+};
+
+int dp_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = DASA_NUM_SMS;
+  }
+  return n;
+}
+
+LaunchPlan dp_launch_plan(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k) {
+  LaunchPlan lp{};
+  lp.ok = false;
+  if (B < 1 || B > 32 || H < 16 || (H % 16) != 0 || ((E + F + H) % 32) != 0 || (NK % 32) != 0 || (D % 32) != 0 || (F % 4) != 0 ||
+      (E % 4) != 0 || (H % 32) != 0 || V < 1 || V > DP_MAXROWS || L < 1 || L > DP_MAXROWS || shift_k < 1 || shift_k > DP_MAXK ||
+      NK < F + shift_k)
+    return lp;
+  lp.grid = dp_sm_count();
+  lp.MT = (B + 7) / 8;
+  int S = lp.grid / B;
+  if (S > 8) S = 8;
+  if (S < 1) return lp;
+  while (S > 1 && ((F >> 2) < S || (D >> 2) < S)) --S;
+  lp.S = S;
+  lp.pl = dp_plan(lp.MT, V, L, F, D, S);
+  lp.ok = lp.pl.total <= 225 * 1024;
+  return lp;
+}
+
+template <typename Kern, typename Args>
+int dp_launch(Kern kern, const Args& a, const LaunchPlan& lp, unsigned int* barrier, cudaStream_t st, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.pl.total);
+  if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
+  e = cudaMemsetAsync(barrier, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)lp.grid);
+  cfg.blockDim = dim3(DP_THREADS);
+  cfg.dynamicSmemBytes = lp.pl.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident, or the launch fails (never a partial grid that deadlocks)
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, a, lp.S, lp.pl);
+  if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
+  return DASA_OK;
+}
+
+}  // namespace
+
+extern "C" int dasa_decoder_rollout_supported(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k) {
+  return dp_launch_plan(B, H, E, F, V, L, D, NK, shift_k).ok ? 1 : 0;
+}
+
+extern "C" size_t dasa_decoder_rollout_scratch_floats(int B) { return (size_t)(B < 1 ? 1 : B) * 8 * DP_MAXROWS; }
+
+extern "C" int dasa_decoder_rollout_fwd(const dasa_decoder_fwd_t* a, void* stream) {
+  if (a == nullptr || a->T <= 0) return a == nullptr ? DASA_ERR_BAD_SHAPE : DASA_OK;
+  const LaunchPlan lp = dp_launch_plan(a->B, a->H, a->E, a->F, a->V, a->L, a->D, a->NK, a->shift_k);
+  if (!lp.ok) return DASA_ERR_UNSUPPORTED;
+  if (a->headings <= 0 || (a->V % a->headings) != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(a->feat) || !dasa_aligned16(a->ctx) || (a->feat_ld_row & 3) || (a->feat_ld_b & 3) || (a->feat_ld_t & 3) ||
+      (a->ctx_ld_row & 3) || (a->ctx_ld_b & 3) || (a->ctx_ld_t & 3))
+    return DASA_ERR_BAD_ALIGN;
+  const void* w[] = {a->w_feat, a->w_lstm, a->w_att_in, a->w_att_out, a->hprev_drop, a->xh, a->cat, a->tk, a->t2};
+  for (const void* p : w)
+    if (p == nullptr || !dasa_aligned16(p)) return DASA_ERR_BAD_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (lp.MT) {
+    case 1: return dp_launch(decoder_rollout_fwd_kernel<1>, *a, lp, a->barrier, st, "decoder_rollout_fwd_kernel<1>");
+    case 2: return dp_launch(decoder_rollout_fwd_kernel<2>, *a, lp, a->barrier, st, "decoder_rollout_fwd_kernel<2>");
+    case 3: return dp_launch(decoder_rollout_fwd_kernel<3>, *a, lp, a->barrier, st, "decoder_rollout_fwd_kernel<3>");
+    default: return dp_launch(decoder_rollout_fwd_kernel<4>, *a, lp, a->barrier, st, "decoder_rollout_fwd_kernel<4>");
+  }
+}
+
+extern "C" int dasa_decoder_rollout_bwd(const dasa_decoder_bwd_t* a, void* stream) {
+  if (a == nullptr || a->T <= 0) return a == nullptr ? DASA_ERR_BAD_SHAPE : DASA_OK;
+  const LaunchPlan lp = dp_launch_plan(a->B, a->H, a->E, a->F, a->V, a->L, a->D, a->NK, a->shift_k);
+  if (!lp.ok) return DASA_ERR_UNSUPPORTED;
+  if (a->headings <= 0 || (a->V % a->headings) != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(a->feat) || !dasa_aligned16(a->ctx) || (a->feat_ld_row & 3) || (a->feat_ld_b & 3) || (a->feat_ld_t & 3) ||
+      (a->ctx_ld_row & 3) || (a->ctx_ld_b & 3) || (a->ctx_ld_t & 3) || (a->dfeat_ld_row & 3) || (a->dfeat_ld_b & 3) ||
+      (a->dfeat_ld_t & 3) || (a->ld_w_feat_t & 3) || (a->ld_w_lstm_t & 3) || (a->ld_w_att_in_t & 3) || (a->ld_w_att_out_t & 3))
+    return DASA_ERR_BAD_ALIGN;
+  const void* w[] = {a->w_feat_t, a->w_lstm_t, a->w_att_in_t, a->w_att_out_t, a->du, a->dt2, a->dgates, a->dtk, a->dfeat, a->dctx,
+                     a->dcat, a->dattn};
+  for (const void* p : w)
+    if (p == nullptr || !dasa_aligned16(p)) return DASA_ERR_BAD_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (lp.MT) {
+    case 1: return dp_launch(decoder_rollout_bwd_kernel<1>, *a, lp, a->barrier, st, "decoder_rollout_bwd_kernel<1>");
+    case 2: return dp_launch(decoder_rollout_bwd_kernel<2>, *a, lp, a->barrier, st, "decoder_rollout_bwd_kernel<2>");
+    case 3: return dp_launch(decoder_rollout_bwd_kernel<3>, *a, lp, a->barrier, st, "decoder_rollout_bwd_kernel<3>");
+    default: return dp_launch(decoder_rollout_bwd_kernel<4>, *a, lp, a->barrier, st, "decoder_rollout_bwd_kernel<4>");
+  }
+}

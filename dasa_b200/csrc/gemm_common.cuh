@@ -73,6 +73,8 @@ static __device__ __noinline__ float apply_epilogue(float v, int m, int n, int N
   }
 }
 
+extern int64_t g_gemm_routes[DASA_ROUTE_COUNT];     // api.cu: per-route call counters (dasa_debug_gemm_route_counts)
+
 // implemented in gemm_simt.cu / gemm_tc.cu
 size_t dasa_gemm_simt_workspace(int M, int N, int K);
 int dasa_gemm_simt(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,

@@ -559,6 +559,7 @@ int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float 
 int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K < P_BK || splits < 1) return DASA_ERR_BAD_SHAPE;
+  ++g_gemm_routes[DASA_ROUTE_PAIR_GROUPED];
   PairParams p{};
   p.M = M; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.C[0] = C[0]; p.C[1] = C[1]; p.ldc = ldc;
   p.tiles_n = (int)dasa_cdiv(N, 256);

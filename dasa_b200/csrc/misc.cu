@@ -57,24 +57,26 @@ __global__ void __launch_bounds__(256) axpy2d_kernel(float a, const float* __res
   }
 }
 
-// splitmix64-style counter hash -> uniform in [0,1)
-__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+// The seed goes through its own avalanche round before the element index is folded in. (Adding the raw seed to
+// (idx + 1) * G made "seed + G" the same stream shifted by one element: the per-replay seed bump of a captured graph produced
+// masks correlated with the previous iteration's.)
+__device__ __forceinline__ uint64_t mix_seed(uint64_t seed) {
+  uint64_t s = (seed ^ 0x2545F4914F6CDD1Dull) * 0xD6E8FEB86659FD93ull;
+  s = (s ^ (s >> 32)) * 0xD6E8FEB86659FD93ull;
+  return s ^ (s >> 32);
 }
 
 // 16 keep flags per thread: four 64-bit hashes, one byte lane each 16 bits -> one 128-bit store
-__device__ __forceinline__ uint64_t hash64(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+// (splitmix64-style finaliser over mixed_seed ^ counter)
+__device__ __forceinline__ uint64_t hash64(uint64_t mixed_seed, uint64_t idx) {
+  uint64_t z = mixed_seed ^ ((idx + 1) * 0x9E3779B97F4A7C15ull);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
 
-__device__ __forceinline__ void mask_fill(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+__device__ __forceinline__ void mask_fill(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t raw_seed, uint64_t offset) {
+  const uint64_t seed = mix_seed(raw_seed);
   const uint32_t thr = (uint32_t)(p * 65536.0f);                       // keep iff 16-bit uniform >= p
   const int64_t n16 = n >> 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
@@ -89,7 +91,7 @@ __device__ __forceinline__ void mask_fill(uint8_t* __restrict__ mask, int64_t n,
   }
   // tail (n not a multiple of 16)
   for (int64_t i = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    mask[i] = (uint32_t)(hash64(seed ^ 0x5bd1e995u, offset + (uint64_t)i) & 0xFFFF) >= thr ? 1 : 0;
+    mask[i] = (uint32_t)(hash64(seed ^ 0x5bd1e9955bd1e995ull, offset + (uint64_t)i) & 0xFFFF) >= thr ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
@@ -124,16 +126,20 @@ __global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict_
   const float lse = mx + logf(sum);
   const int64_t t = target ? target[b] : (int64_t)ignore_index;
   const bool valid = target && (t != (int64_t)ignore_index);
+  // torch's CrossEntropyLoss raises on a target outside [0, Nc); a kernel inside a captured graph cannot, so the loss is
+  // poisoned with NaN instead of silently reading past the row (e.g. a candidate buffer narrower than cand_leng)
+  const bool in_range = !valid || (t >= 0 && t < (int64_t)Nc);
   float ent = 0.f;
   for (int j = lane; j < Nc; j += 32) {
     const float lp = z[j] - lse;          // -inf for masked candidates
     const float p = expf(lp);
     if (p > 0.f) ent -= p * lp;
-    if (dlogit != nullptr) dlogit[(int64_t)b * Nc + j] = valid ? (p - (j == (int)t ? 1.f : 0.f)) * grad_scale : 0.f;
+    if (dlogit != nullptr)
+      dlogit[(int64_t)b * Nc + j] = !in_range ? NAN : (valid ? (p - (j == (int)t ? 1.f : 0.f)) * grad_scale : 0.f);
   }
   ent = warp_sum(ent);
   if (lane == 0) {
-    if (valid && loss_acc != nullptr) atomicAdd(loss_acc, lse - z[t]);
+    if (valid && loss_acc != nullptr) atomicAdd(loss_acc, in_range ? lse - z[t] : NAN);
     if (action != nullptr) action[b] = arg;
     if (logprob_action != nullptr) logprob_action[b] = z[arg] - lse;
     if (entropy != nullptr) entropy[b] = ent;
@@ -177,12 +183,30 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
   }
 }
 
+// Two-stage, fixed-order sum of squares (bit-reproducible clip coefficient): every block folds its grid-stride slice, the
+// LAST block to finish (ticket counter) adds the block partials in index order and accumulates into out[0].
+constexpr int SUMSQ_BLOCKS = DASA_NUM_SMS * 4;
+__device__ float g_sumsq_part[SUMSQ_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ bool last;
   float s = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fmaf(x[i], x[i], s);
   s = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) {
+    g_sumsq_part[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float v = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(g_sumsq_part + i);   // fixed slice per thread
+  v = block_sum(v, red);
+  if (threadIdx.x == 0) { out[0] += v; g_sumsq_ticket = 0; }
 }
 
 __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef) {
@@ -263,7 +287,10 @@ extern "C" int dasa_rmsprop_step(float* param, const float* grad, float* square_
 
 extern "C" int dasa_sumsq(const float* x, int64_t n, float* out, void* stream) {
   if (n <= 0) return DASA_OK;
-  sumsq_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  // launches on one stream are ordered, which is what the shared partial buffer / ticket rely on (one optimizer per process)
+  int64_t g = dasa_cdiv(n, 256 * 8);
+  g = g < 1 ? 1 : (g > SUMSQ_BLOCKS ? SUMSQ_BLOCKS : g);
+  sumsq_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, n, out);
   return dasa_check_launch("sumsq_kernel");
 }
 

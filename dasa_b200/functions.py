@@ -315,6 +315,64 @@ class LSTMCellFn(torch.autograd.Function):
         return dxh, (dc0 if ctx.needs_input_grad[1] else None), None, None, None, None, None, None
 
 
+class DecoderRolloutFn(torch.autograd.Function):
+    """BAttnDecoderLSTM.forward up to h_tilde (model.py:504-554) for T consecutive actions in ONE cooperative launch each way
+    (csrc/decoder_persist.cu). emb [T,B,E] (embedded, dropped actions), feat [T,B,V,F] (AdaIN'd, dropped views), ctx [T,B,L,D],
+    (h0, c0) = (h_tilde, c) before action 0. Returns (h_tilde [T,B,H], h_1 [T,B,H], c [T,B,H]); T = 1 is the per-action form.
+    Weight gradients: the kernel leaves the dY of every projection in [T*B, .] buffers and one long-K GEMM per weight follows
+    (immediately, or at flush_weight_grads() when deferred)."""
+
+    @staticmethod
+    def forward(ctx_, emb, feat, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale, w_in, w_shift, b_shift, w_ih, w_hh, b_ih, b_hh,
+                w_att_in, w_att_out, headings):
+        k = w_shift.shape[0]
+        Wf, bf = ops.stacked_weights((w_in, w_shift), 0, 32, (None, b_shift))
+        Wl, _ = ops.stacked_weights((w_ih, w_hh), 1)
+        o = ops.decoder_rollout_fwd(emb, feat, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale, Wf, bf, Wl, b_ih, b_hh, w_att_in,
+                                    w_att_out, headings, k)
+        ctx_.headings, ctx_.k, ctx_.scale = headings, k, scale
+        ctx_.saved = o
+        e = emb.new_empty(0)
+        ctx_.save_for_backward(feat, ctx, ctx_mask if ctx_mask is not None else e, m_hprev if m_hprev is not None else e,
+                               m_h1 if m_h1 is not None else e, w_in, w_shift, b_shift, w_ih, w_hh, b_ih, b_hh, w_att_in, w_att_out)
+        return o["htilde"], o["h1"], o["c"][1:]
+
+    @staticmethod
+    def backward(ctx_, d_htilde, d_h1, d_c):
+        (feat, ctx, ctx_mask, m_hprev, m_h1, w_in, w_shift, b_shift, w_ih, w_hh, b_ih, b_hh, w_att_in,
+         w_att_out) = ctx_.saved_tensors
+        o = ctx_.saved
+        T, B, H = o["htilde"].shape
+        F_all, k = w_in.shape[0], ctx_.k
+        n_x = w_ih.shape[1]
+        D = ctx.shape[3]
+        if d_htilde is None:
+            d_htilde = torch.zeros_like(o["htilde"])
+        Wf, _ = ops.stacked_weights((w_in, w_shift), 0, 32, (None, b_shift))
+        Wl, _ = ops.stacked_weights((w_ih, w_hh), 1)
+        d_c_last = None
+        if d_c is not None:
+            # only the last cell state leaves the kernel as a recurrent carry (per-action use); earlier slots are internal
+            d_c_last = d_c[T - 1]
+        g = ops.decoder_rollout_bwd(o, feat, ctx, ctx_mask if ctx_mask.numel() else None, m_hprev if m_hprev.numel() else None,
+                                    m_h1 if m_h1.numel() else None, ctx_.scale, ops.transposed_weight(Wf), ops.transposed_weight(Wl),
+                                    ops.transposed_weight(w_att_in), ops.transposed_weight(w_att_out), ctx_.headings, k, d_htilde,
+                                    d_h1, d_c_last)
+        R = T * B
+        du, dt2, dg, dtk = g["du"].view(R, H), g["dt2"].view(R, D), g["dgates"].view(R, 4 * H), g["dtk"].view(R, -1)
+        cat, xh, hpd = o["cat"].view(R, -1), o["xh"].view(R, -1), o["hprev_drop"].view(R, H)
+        _wgrad(w_att_out, du, cat)
+        _wgrad(w_att_in, dt2, cat[:, D:])
+        _wgrad(w_ih, dg, xh[:, :n_x], b_ih, b_hh)            # db_ih == db_hh: one column sum
+        _wgrad(w_hh, dg, xh[:, n_x:])
+        _wgrad(w_in, dtk[:, :F_all], hpd)
+        _wgrad(w_shift, dtk[:, F_all:F_all + k], hpd, b_shift)
+        ctx_.saved = None
+        need = ctx_.needs_input_grad
+        return (g["demb"] if need[0] else None, g["dfeat"] if need[1] else None, g["dctx"] if need[2] else None, None,
+                g["dh0"] if need[4] else None, g["dc0"] if need[5] else None) + (None,) * 13
+
+
 def invalidate_weight_caches():
     """Call after parameters were updated through raw pointers (the fused RMSprop kernel does not bump tensor versions)."""
     ops.weights_epoch += 1

@@ -33,6 +33,31 @@ class BiLstmBwd(ctypes.Structure):
                 ("dgates", P * 2), ("dh_pass", P * 2), ("dc_work", P * 2), ("lengths", P), ("B", I), ("L", I), ("H", I)]
 
 
+class DecoderFwd(ctypes.Structure):
+    """dasa_decoder_fwd_t (field order and types exactly as in include/dasa_b200.h)"""
+    _fields_ = ([(k, I) for k in ("T", "B", "H", "E", "F", "V", "L", "D", "headings", "shift_k", "NK")] +
+                [("emb", P), ("feat", P), ("feat_ld_row", L), ("feat_ld_b", L), ("feat_ld_t", L),
+                 ("ctx", P), ("ctx_ld_row", L), ("ctx_ld_b", L), ("ctx_ld_t", L), ("ctx_mask", P), ("ctx_mask_ld", L),
+                 ("h0", P), ("c0", P), ("m_hprev", P), ("m_h1", P), ("drop_scale", F),
+                 ("w_feat", P), ("b_feat", P), ("w_lstm", P), ("b_ih", P), ("b_hh", P), ("w_att_in", P), ("w_att_out", P)] +
+                [(k, P) for k in ("hprev_drop", "tk", "p", "q", "kappa", "xh", "acts", "c", "h1", "cat", "t2", "alpha", "htilde",
+                                  "zpart", "barrier")])
+
+
+class DecoderBwd(ctypes.Structure):
+    """dasa_decoder_bwd_t"""
+    _fields_ = ([(k, I) for k in ("T", "B", "H", "E", "F", "V", "L", "D", "headings", "shift_k", "NK")] +
+                [("feat", P), ("feat_ld_row", L), ("feat_ld_b", L), ("feat_ld_t", L),
+                 ("ctx", P), ("ctx_ld_row", L), ("ctx_ld_b", L), ("ctx_ld_t", L), ("ctx_mask", P), ("ctx_mask_ld", L),
+                 ("m_hprev", P), ("m_h1", P), ("drop_scale", F),
+                 ("w_feat_t", P), ("ld_w_feat_t", L), ("w_lstm_t", P), ("ld_w_lstm_t", L), ("w_att_in_t", P), ("ld_w_att_in_t", L),
+                 ("w_att_out_t", P), ("ld_w_att_out_t", L)] +
+                [(k, P) for k in ("tk", "p", "q", "kappa", "acts", "c", "cat", "t2", "alpha", "htilde", "d_htilde", "d_h1",
+                                  "d_c_last", "du", "dt2", "dgates", "dtk", "demb")] +
+                [("dfeat", P), ("dfeat_ld_row", L), ("dfeat_ld_b", L), ("dfeat_ld_t", L)] +
+                [(k, P) for k in ("dctx", "dh0", "dc0", "dcat", "dattn", "dhdir", "dc_carry", "zpart", "barrier")])
+
+
 class Epilogue(ctypes.Structure):
     """dasa_epilogue_t"""
     _fields_ = [("bias", P), ("gate_src", P), ("ld_gate", L), ("gate_out", P), ("ld_gate_out", L),
@@ -115,3 +140,14 @@ def call(name, *args):
     if rc != 0:
         raise DasaError("%s failed: %s (%s)" % (name, ERRORS.get(rc, rc), load().dasa_last_error().decode()))
     return rc
+
+
+ROUTES = ("skinny", "pair", "pair_mn", "pair_mn_splitk", "pair_grouped", "tc_single", "simt_tf32_mode", "simt_misaligned",
+          "simt_fp32")
+
+
+def gemm_route_counts(reset=False):
+    """{route name: number of dasa_gemm calls it took} since the last reset (include/dasa_b200.h DASA_ROUTE_*)."""
+    buf = (ctypes.c_int64 * len(ROUTES))()
+    load().dasa_debug_gemm_route_counts(buf, len(ROUTES), int(bool(reset)))
+    return dict(zip(ROUTES, [int(x) for x in buf]))

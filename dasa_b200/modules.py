@@ -265,6 +265,39 @@ class BAttnDecoderLSTM(nn.Module):
                                             cand_leng=cand_leng_all, rgb_channels=self.feature_size - self.angle_feat_size)
         return logit
 
+    # ------------------------------------------------------------------ persistent whole-rollout kernel (decoder_persist.cu)
+    def _persistent_geometry(self, B, V, L, D):
+        H, E, F = self.hidden_size, self.embedding_size, self.feature_size
+        k = self.feat_att_layer.kernel_size
+        NK = (F + k + 31) // 32 * 32
+        return (B, H, E, F, V, L, D, NK, k)
+
+    def _rollout_fn(self, emb, feature, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale):
+        fa, al, l = self.feat_att_layer, self.attention_layer, self.lstm
+        if ctx_mask is not None and ctx_mask.dtype != torch.uint8:
+            ctx_mask = ctx_mask.to(torch.uint8)
+        return Fn.DecoderRolloutFn.apply(emb, feature, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale, fa.linear_in.weight,
+                                         fa.linear_shift.weight, fa.linear_shift.bias, l.weight_ih, l.weight_hh, l.bias_ih,
+                                         l.bias_hh, al.linear_in.weight, al.linear_out.weight, fa.headings)
+
+    def rollout_steps(self, emb_all, feat_all, ctx_all, ctx_mask, h0, c0, steps):
+        """model.py:504-554 for `steps` consecutive teacher-forced actions in one cooperative launch (forward; one more for the
+        backward): emb_all [steps*B, E] (from embed_actions), feat_all [steps*B, V, F], ctx_all [steps*B, L, D] -> h_tilde of
+        every action [steps*B, H], or None when the kernel does not take this geometry / precision (the caller then loops over
+        forward()). Dropout masks follow the per-step tags 't<i>.dec.h_prev' / 't<i>.dec.h1'."""
+        TB, V, _ = feat_all.shape
+        B = TB // steps
+        L, D = ctx_all.shape[1], ctx_all.shape[2]
+        if not (feat_all.is_contiguous() and ctx_all.is_contiguous() and
+                ops.decoder_rollout_supported(*self._persistent_geometry(B, V, L, D))):
+            return None
+        p, tr, H = self.dropout_ratio, self.training, self.hidden_size
+        m_hp, s = _source.mask_steps("dec.h_prev", (B, H), p, tr, feat_all.device, steps)
+        m_h1, _ = _source.mask_steps("dec.h1", (B, H), p, tr, feat_all.device, steps)
+        ht, _, _ = self._rollout_fn(emb_all.view(steps, B, -1), feat_all.view(steps, B, V, -1), ctx_all.view(steps, B, L, D),
+                                    ctx_mask, h0, c0, m_hp, m_h1, s)
+        return ht.view(steps * B, H)
+
     def forward(self, action, feature, cand_feat, h_0, prev_h1, c_0, ctx, ctx_mask=None, already_dropfeat=False,
                 cand_leng=None, emb=None, want_logit=True):
         """Same contract as the reference; h_0 is ignored there too (model.py:472-474, 514). When not already_dropfeat
@@ -283,6 +316,16 @@ class BAttnDecoderLSTM(nn.Module):
                 with torch.no_grad():
                     feature.copy_(dropped)
                 feature = dropped
+        if (feature.dim() == 3 and feature.is_contiguous() and ctx.is_contiguous() and ops.decoder_rollout_supported(
+                *self._persistent_geometry(feature.shape[0], feature.shape[1], ctx.shape[1], ctx.shape[2]))):
+            # one cooperative launch for the whole step up to h_tilde (8 device-wide barriers instead of ~28 dependent launches)
+            B, H = feature.shape[0], self.hidden_size
+            m_hp, s = _source.mask("dec.h_prev", (B, H), p, tr, feature.device)
+            m_h1, _ = _source.mask("dec.h1", (B, H), p, tr, feature.device)
+            ht, h1s, cs = self._rollout_fn(emb.unsqueeze(0), feature.unsqueeze(0), ctx.unsqueeze(0), ctx_mask, prev_h1, c_0,
+                                           m_hp, m_h1, s)
+            h_1, c_1, h_tilde = h1s[0], cs[0], ht[0]
+            return self._logit_tail(h_1, c_1, h_tilde, cand_feat, already_dropfeat, cand_leng, want_logit)
         h_prev_drop = _drop(prev_h1, "dec.h_prev", p, tr)
         attn_feat, _ = self.feat_att_layer(h_prev_drop, feature, output_tilde=False)
         xh = torch.cat((emb, attn_feat, prev_h1), 1)        # [x ; h]: one gate GEMM against [W_ih | W_hh]
@@ -294,6 +337,11 @@ class BAttnDecoderLSTM(nn.Module):
             h_1, c_1 = Fn.LSTMCellFn.apply(xh, c_0, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih, self.lstm.bias_hh)
             h_1_drop = h_1
         h_tilde, alpha = self.attention_layer(h_1_drop, ctx, ctx_mask)
+        return self._logit_tail(h_1, c_1, h_tilde, cand_feat, already_dropfeat, cand_leng, want_logit)
+
+    def _logit_tail(self, h_1, c_1, h_tilde, cand_feat, already_dropfeat, cand_leng, want_logit):
+        """drop(h_tilde) -> candidate logits (model.py:555-559)."""
+        A, p, tr = self.angle_feat_size, self.dropout_ratio, self.training
         if not want_logit:
             return h_1, c_1, None, h_tilde, {}
         h_tilde_drop = _drop(h_tilde, "dec.htilde", p, tr)

@@ -596,3 +596,116 @@ def sumsq(x, out):
 
 def clip_coef(sumsq_t, max_norm, coef):
     call("dasa_clip_coef", _p(sumsq_t), float(max_norm), _p(coef), _stream())
+
+
+# ---------------------------------------------------------------------- persistent decoder rollout (csrc/decoder_persist.cu)
+persistent_decoder = True      # route the decoder through the cooperative whole-rollout kernel when it applies (TF32 precision)
+
+
+def decoder_rollout_supported(B, H, E, F, V, L, D, NK, shift_k):
+    """True when dasa_decoder_rollout_fwd/_bwd take this geometry (B <= 32, shared-memory plan fits) AND the tensor-core precision
+    is selected: the kernel multiplies in TF32, so the exact-fp32 mode keeps the per-op FFMA path."""
+    if not persistent_decoder or _precision != PREC_TF32:
+        return False
+    return bool(lib.load().dasa_decoder_rollout_supported(B, H, E, F, V, L, D, NK, shift_k))
+
+
+def _ld3(t):
+    """(row, sample, action) strides of a [T, B, R, C] tensor with unit inner stride."""
+    assert t.dim() == 4 and t.stride(3) == 1, (t.shape, t.stride())
+    return t.stride(2), t.stride(1), t.stride(0)
+
+
+def decoder_rollout_fwd(emb, feat, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale, w_feat, b_feat, w_lstm, b_ih, b_hh, w_att_in,
+                        w_att_out, headings, shift_k):
+    """emb [T,B,E], feat [T,B,V,F], ctx [T,B,L,D] -> dict of every [T, B, .] buffer dasa_decoder_fwd_t writes."""
+    _chk(emb, feat, ctx, h0, c0, w_feat, b_feat, w_lstm, b_ih, b_hh, w_att_in, w_att_out)
+    T, B, E = emb.shape
+    V, F = feat.shape[2], feat.shape[3]
+    L, D = ctx.shape[2], ctx.shape[3]
+    H = h0.shape[1]
+    NK = w_feat.shape[0]
+    dev = emb.device
+    KX, DC = E + F + H, D + H
+    assert w_lstm.shape == (4 * H, KX) and w_att_in.shape == (D, H) and w_att_out.shape == (H, DC) and w_feat.shape[1] == H
+
+    def new(*shape):
+        return torch.empty(*shape, device=dev, dtype=torch.float32)
+    o = {"hprev_drop": new(T, B, H), "tk": new(T, B, NK), "p": new(T, B, V), "q": new(T, B, V), "kappa": new(T, B, shift_k),
+         "xh": new(T, B, KX), "acts": new(T, B, 4 * H), "c": new(T + 1, B, H), "h1": new(T, B, H), "cat": new(T, B, DC),
+         "t2": new(T, B, D), "alpha": new(T, B, L), "htilde": new(T, B, H)}
+    zpart = new(lib.load().dasa_decoder_rollout_scratch_floats(B))
+    barrier = torch.empty(32, device=dev, dtype=torch.int32)
+    emb, h0, c0 = emb.contiguous(), h0.contiguous(), c0.contiguous()
+    if ctx_mask is not None:
+        ctx_mask = ctx_mask if ctx_mask.dtype == torch.uint8 else ctx_mask.to(torch.uint8)
+        assert ctx_mask.stride(1) == 1
+    a = lib.DecoderFwd()
+    a.T, a.B, a.H, a.E, a.F, a.V, a.L, a.D, a.headings, a.shift_k, a.NK = T, B, H, E, F, V, L, D, headings, shift_k, NK
+    a.emb = _p(emb)
+    a.feat = _p(feat)
+    a.feat_ld_row, a.feat_ld_b, a.feat_ld_t = _ld3(feat)
+    a.ctx = _p(ctx)
+    a.ctx_ld_row, a.ctx_ld_b, a.ctx_ld_t = _ld3(ctx)
+    a.ctx_mask, a.ctx_mask_ld = _p(ctx_mask), (ctx_mask.stride(0) if ctx_mask is not None else 0)
+    a.h0, a.c0 = _p(h0), _p(c0)
+    a.m_hprev, a.m_h1, a.drop_scale = _p(m_hprev), _p(m_h1), float(scale)
+    a.w_feat, a.b_feat, a.w_lstm, a.b_ih, a.b_hh = _p(w_feat), _p(b_feat), _p(w_lstm), _p(b_ih), _p(b_hh)
+    a.w_att_in, a.w_att_out = _p(w_att_in), _p(w_att_out)
+    for k, v in o.items():
+        setattr(a, k, _p(v))
+    a.zpart, a.barrier = _p(zpart), _p(barrier)
+    keep = (emb, feat, ctx, ctx_mask, h0, c0, zpart, barrier)      # referenced until the launch is enqueued
+    call("dasa_decoder_rollout_fwd", ctypes.byref(a), _stream())
+    del keep
+    return o
+
+
+def decoder_rollout_bwd(saved, feat, ctx, ctx_mask, m_hprev, m_h1, scale, w_feat_t, w_lstm_t, w_att_in_t, w_att_out_t, headings,
+                        shift_k, d_htilde, d_h1, d_c_last):
+    """Backward of decoder_rollout_fwd. `saved` = its output dict; the *_t weights are [in, out] rows (ops.transposed_weight)."""
+    T, B, H = saved["htilde"].shape
+    E = saved["xh"].shape[2] - feat.shape[3] - H
+    V, F = feat.shape[2], feat.shape[3]
+    L, D = ctx.shape[2], ctx.shape[3]
+    NK = saved["tk"].shape[2]
+    dev = feat.device
+
+    def new(*shape):
+        return torch.empty(*shape, device=dev, dtype=torch.float32)
+    g = {"du": new(T, B, H), "dt2": new(T, B, D), "dgates": new(T, B, 4 * H), "dtk": new(T, B, NK), "demb": new(T, B, E),
+         "dfeat": new(T, B, V, F), "dctx": new(T, B, L, D), "dh0": new(B, H), "dc0": new(B, H)}
+    scratch = {"dcat": new(B, D + H), "dattn": new(B, F), "dhdir": new(B, H), "dc_carry": new(B, H)}
+    zpart = new(lib.load().dasa_decoder_rollout_scratch_floats(B))
+    barrier = torch.empty(32, device=dev, dtype=torch.int32)
+    d_htilde = d_htilde.contiguous()
+    d_h1 = None if d_h1 is None else d_h1.contiguous()
+    d_c_last = None if d_c_last is None else d_c_last.contiguous()
+    if ctx_mask is not None:
+        ctx_mask = ctx_mask if ctx_mask.dtype == torch.uint8 else ctx_mask.to(torch.uint8)
+    a = lib.DecoderBwd()
+    a.T, a.B, a.H, a.E, a.F, a.V, a.L, a.D, a.headings, a.shift_k, a.NK = T, B, H, E, F, V, L, D, headings, shift_k, NK
+    a.feat = _p(feat)
+    a.feat_ld_row, a.feat_ld_b, a.feat_ld_t = _ld3(feat)
+    a.ctx = _p(ctx)
+    a.ctx_ld_row, a.ctx_ld_b, a.ctx_ld_t = _ld3(ctx)
+    a.ctx_mask, a.ctx_mask_ld = _p(ctx_mask), (ctx_mask.stride(0) if ctx_mask is not None else 0)
+    a.m_hprev, a.m_h1, a.drop_scale = _p(m_hprev), _p(m_h1), float(scale)
+    a.w_feat_t, a.ld_w_feat_t = _p(w_feat_t), w_feat_t.stride(0)
+    a.w_lstm_t, a.ld_w_lstm_t = _p(w_lstm_t), w_lstm_t.stride(0)
+    a.w_att_in_t, a.ld_w_att_in_t = _p(w_att_in_t), w_att_in_t.stride(0)
+    a.w_att_out_t, a.ld_w_att_out_t = _p(w_att_out_t), w_att_out_t.stride(0)
+    for k in ("tk", "p", "q", "kappa", "acts", "c", "cat", "t2", "alpha", "htilde"):
+        setattr(a, k, _p(saved[k]))
+    a.d_htilde, a.d_h1, a.d_c_last = _p(d_htilde), _p(d_h1), _p(d_c_last)
+    for k in ("du", "dt2", "dgates", "dtk", "demb", "dctx", "dh0", "dc0"):
+        setattr(a, k, _p(g[k]))
+    a.dfeat = _p(g["dfeat"])
+    a.dfeat_ld_row, a.dfeat_ld_b, a.dfeat_ld_t = _ld3(g["dfeat"])
+    for k, v in scratch.items():
+        setattr(a, k, _p(v))
+    a.zpart, a.barrier = _p(zpart), _p(barrier)
+    keep = (d_htilde, d_h1, d_c_last, ctx_mask, scratch, zpart, barrier)
+    call("dasa_decoder_rollout_bwd", ctypes.byref(a), _stream())
+    del keep
+    return g

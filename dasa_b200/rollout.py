@@ -181,19 +181,24 @@ class NavPolicy:
             cand_steps = candg_all.view(T, B, nc, cfg.feat).unbind(0)
             # Off the recurrent path, hence batched over the T actions: the action embeddings (before the loop) and the
             # candidate logits + cross entropy (after it). The loop keeps only what h_tilde_t -> h_tilde_{t+1} needs.
-            emb_steps = self.decoder.embed_actions(ep.input_a_t[:T].reshape(T * B, -1), T).view(T, B, -1).unbind(0)
-            h_tildes = []
             mask_u8 = ep.seq_mask.to(torch.uint8)            # converted once (the attention kernel reads uint8 pad flags)
-            for t in range(T):
-                if tag_steps:
-                    src.prefix = base_prefix + "t%d." % t
-                prev_h1, c_0 = (en_h, en_c) if carry is None else carry
-                h_t, c_t, _, h1, _ = self.decoder(None, df_steps[t], None, prev_h1, prev_h1, c_0, ctx_steps[t], mask_u8,
-                                                  already_dropfeat=True, emb=emb_steps[t], want_logit=False)
-                carry = (h1, c_t)
-                h_tildes.append(h1)
-            src.prefix = base_prefix
-            logit_all = self.decoder.candidate_logits_steps(torch.cat(h_tildes, 0), candg_all, ep.cand_leng[:T].reshape(T * B), T)
+            emb_all = self.decoder.embed_actions(ep.input_a_t[:T].reshape(T * B, -1), T)
+            # the recurrent part of all T actions: ONE cooperative launch (csrc/decoder_persist.cu) where the kernel applies ...
+            h_tilde_all = self.decoder.rollout_steps(emb_all, df_all, ctx_all, mask_u8, en_h, en_c, T)
+            if h_tilde_all is None:                          # ... else one decoder call per action (exact-fp32 mode, B > 32)
+                emb_steps = emb_all.view(T, B, -1).unbind(0)
+                h_tildes = []
+                for t in range(T):
+                    if tag_steps:
+                        src.prefix = base_prefix + "t%d." % t
+                    prev_h1, c_0 = (en_h, en_c) if carry is None else carry
+                    h_t, c_t, _, h1, _ = self.decoder(None, df_steps[t], None, prev_h1, prev_h1, c_0, ctx_steps[t], mask_u8,
+                                                      already_dropfeat=True, emb=emb_steps[t], want_logit=False)
+                    carry = (h1, c_t)
+                    h_tildes.append(h1)
+                src.prefix = base_prefix
+                h_tilde_all = torch.cat(h_tildes, 0)
+            logit_all = self.decoder.candidate_logits_steps(h_tilde_all, candg_all, ep.cand_leng[:T].reshape(T * B), T)
             total, a_all = Fn.MaskedCEFn.apply(logit_all, ep.target[:T].reshape(T * B), cfg.ignore_id)
             logits = list(logit_all.view(T, B, nc).unbind(0))
             actions = list(a_all.view(T, B).unbind(0))

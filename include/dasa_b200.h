@@ -77,6 +77,22 @@ int dasa_debug_gemm_pair(int mode);
  * DASA_SKINNY), 2 = every eligible shape (tests). */
 int dasa_debug_gemm_skinny(int on);
 
+/* Which kernel family took each dasa_gemm call since the last reset (host-side counters, one slot per DASA_ROUTE_*):
+ * tests assert with them that the benchmarked configuration really runs on the tcgen05 kernels and that no TF32-mode GEMM
+ * silently fell back to the FFMA kernel because of a misaligned operand (that case also prints one warning to stderr).
+ * out[i] = count of route i for i < min(n, DASA_ROUTE_COUNT); reset != 0 zeroes the counters afterwards.               */
+enum { DASA_ROUTE_SKINNY = 0,          /* gemm_skinny.cu: M <= 32 weight-streaming mma.sync TF32                        */
+       DASA_ROUTE_PAIR = 1,            /* gemm_tc2.cu: persistent CTA-pair tcgen05 kernel, K-major operands             */
+       DASA_ROUTE_PAIR_MN = 2,         /* gemm_tc2.cu: MN-major operand(s) (dX = dY.W, dW = dY^T.X)                     */
+       DASA_ROUTE_PAIR_MN_SPLITK = 3,  /* the same, K split + deterministic fold                                        */
+       DASA_ROUTE_PAIR_GROUPED = 4,    /* two problems per launch (bi-LSTM recurrence, both directions)                 */
+       DASA_ROUTE_TC_SINGLE = 5,       /* gemm_tc.cu: single-CTA tcgen05 kernel (few-tile problems, split-K)            */
+       DASA_ROUTE_SIMT_TF32_MODE = 6,  /* FFMA kernel under DASA_PREC_TF32 for a layout / size the tensor kernels do not take (e.g. K < 32) */
+       DASA_ROUTE_SIMT_MISALIGNED = 7, /* FFMA kernel under DASA_PREC_TF32 ONLY because of operand alignment: a performance bug */
+       DASA_ROUTE_SIMT_FP32 = 8,       /* FFMA kernel, DASA_PREC_FP32 requested                                          */
+       DASA_ROUTE_COUNT = 9 };
+int dasa_debug_gemm_route_counts(int64_t* out, int n, int reset);
+
 size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
 /* 1 when dasa_gemm(DASA_PREC_TF32) runs this operand-layout combination on the tensor cores directly: always for two K-major
  * operands; for an MN-major A ([K][M] in memory) and / or B ([K][N]) when the problem is large enough for the persistent CTA-pair
@@ -208,6 +224,80 @@ int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, int precision, void* stre
 size_t dasa_bilstm_seq_gemm_workspace(int B, int H, int backward);
 int dasa_bilstm_seq_gemm_fwd(const dasa_bilstm_fwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
 int dasa_bilstm_seq_gemm_bwd(const dasa_bilstm_bwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------- persistent decoder rollout
+ * BAttnDecoderLSTM.forward (model.py:472-574) for T consecutive actions of B <= 32 episodes in ONE cooperative launch: one CTA
+ * per SM stays resident for the whole rollout, the phases of an action are separated by a device-wide barrier instead of
+ * kernel boundaries (8 barriers instead of ~28 dependent launches per action). Per action t:
+ *   P1  tk = [linear_in ; linear_shift] drop(h~_{t-1}) + b           weight-streaming mma.sync TF32, 16 W rows per CTA
+ *   P2  ShiftSoftDotAttention over feat[t] (model.py:327-345)        channel slices resident in shared memory (bulk-async
+ *                                                                     prefetched one action ahead), partial dots through L2
+ *   P3  gates = [W_ih | W_hh] [emb ; attn_feat ; h~_{t-1}] + b, LSTM cell fused in the epilogue (CTA = 8 units x 4 gates)
+ *   P4  t2 = attention_layer.linear_in drop(h_1)
+ *   P5  SoftDotAttention over ctx[t] with the padding mask (model.py:276-288)
+ *   P6  h~_t = tanh(linear_out [wc ; drop(h_1)])  (+ drop(h~_t) for the next action)
+ * T = 1 is the per-action form the sampled / greedy rollouts use. All [T, B, .] buffers are contiguous unless a stride is
+ * given. Everything the backward pass re-reads is written to caller-owned buffers (no recomputation).
+ * Dropout: m_hprev / m_h1 are [T, B, H] keep masks (NULL = eval), scale = 1/(1-p); emb and feat arrive already dropped.
+ * Requirements: H % 16 == 0, (E+F+H) % 32 == 0, NK % 32 == 0, D % 4 == 0, F % 4 == 0, V, L <= 128, B <= 32, shift_k <= 15;
+ * dasa_decoder_rollout_supported() says whether the shared-memory plan fits (else use the per-op entry points).      */
+typedef struct {
+  int T, B, H, E, F, V, L, D, headings, shift_k, NK;
+  const float* emb;                                   /* [T, B, E] drop(tanh(embedding(action)))  (model.py:504-505)        */
+  const float* feat; int64_t feat_ld_row, feat_ld_b, feat_ld_t;   /* [T, B, V, F] AdaIN'd (and dropped) views            */
+  const float* ctx; int64_t ctx_ld_row, ctx_ld_b, ctx_ld_t;       /* [T, B, L, D] encoder context per action              */
+  const uint8_t* ctx_mask; int64_t ctx_mask_ld;       /* [B, L] 1 = padding (NULL = none)                                  */
+  const float* h0; const float* c0;                   /* [B, H] recurrent state before action 0 (h~_{-1}, c_{-1})          */
+  const uint8_t* m_hprev; const uint8_t* m_h1; float drop_scale;
+  const float* w_feat; const float* b_feat;           /* [NK, H] = [feat_att.linear_in ; linear_shift ; 0], bias [NK]      */
+  const float* w_lstm; const float* b_ih; const float* b_hh;      /* [4H, E+F+H] = [W_ih | W_hh]                          */
+  const float* w_att_in;                              /* [D, H]   attention_layer.linear_in                                */
+  const float* w_att_out;                             /* [H, D+H] attention_layer.linear_out                               */
+  float* hprev_drop;                                  /* [T, B, H]   drop(h~_{t-1})                                        */
+  float* tk;                                          /* [T, B, NK]  attention target | shift logits                      */
+  float* p; float* q; float* kappa;                   /* [T, B, V] pre-shift softmax, [T, B, V] shifted, [T, B, shift_k]   */
+  float* xh;                                          /* [T, B, E+F+H] = [emb ; attn_feat ; h~_{t-1}]                      */
+  float* acts;                                        /* [T, B, 4H]  post-nonlinearity gates i,f,g,o                       */
+  float* c;                                           /* [T+1, B, H] cell state, slot 0 = c0                               */
+  float* h1;                                          /* [T, B, H]                                                         */
+  float* cat;                                         /* [T, B, D+H] = [wc ; drop(h_1)]                                    */
+  float* t2;                                          /* [T, B, D]                                                         */
+  float* alpha;                                       /* [T, B, L]                                                         */
+  float* htilde;                                      /* [T, B, H]                                                         */
+  float* zpart;                                       /* scratch, dasa_decoder_rollout_scratch_floats(B) floats            */
+  unsigned int* barrier;                              /* scratch, 4 bytes, zeroed by the call                              */
+} dasa_decoder_fwd_t;
+/* Backward of the same T actions (reverse order) in one cooperative launch. Weight operands are the TRANSPOSED weights
+ * ([in, out] rows with leading dimension ld_*): dX = dY.W then streams K-major rows like the forward. Weight gradients are NOT
+ * formed here: du, dt2, dgates, dtk (the dY of the four projections) are left in [T, B, .] buffers for one long-K GEMM each.
+ *   d_htilde [T, B, H]: gradient arriving at every h~_t from outside the recurrence (candidate logits); d_h1 (optional): at h_1
+ *   (the critic reads it in the sampled rollout); d_c_last (optional): at the last cell state (per-action use, T = 1). Outputs: demb [T, B, E], dfeat [T, B, V, F] (strides given), dctx [T, B, L, D]
+ *   contiguous (zero rows where masked), dh0, dc0 [B, H].                                                                    */
+typedef struct {
+  int T, B, H, E, F, V, L, D, headings, shift_k, NK;
+  const float* feat; int64_t feat_ld_row, feat_ld_b, feat_ld_t;
+  const float* ctx; int64_t ctx_ld_row, ctx_ld_b, ctx_ld_t;
+  const uint8_t* ctx_mask; int64_t ctx_mask_ld;
+  const uint8_t* m_hprev; const uint8_t* m_h1; float drop_scale;
+  const float* w_feat_t; int64_t ld_w_feat_t;         /* [H, NK]                                                           */
+  const float* w_lstm_t; int64_t ld_w_lstm_t;         /* [E+F+H, 4H]                                                       */
+  const float* w_att_in_t; int64_t ld_w_att_in_t;     /* [H, D]                                                            */
+  const float* w_att_out_t; int64_t ld_w_att_out_t;   /* [D+H, H]                                                          */
+  const float* tk; const float* p; const float* q; const float* kappa; const float* acts; const float* c;
+  const float* cat; const float* t2; const float* alpha; const float* htilde;
+  const float* d_htilde; const float* d_h1; const float* d_c_last;   /* d_c_last (optional) [B, H]: gradient at c_{T-1}      */
+  float* du; float* dt2; float* dgates; float* dtk;   /* [T, B, H], [T, B, D], [T, B, 4H], [T, B, NK]                      */
+  float* demb;                                        /* [T, B, E]                                                         */
+  float* dfeat; int64_t dfeat_ld_row, dfeat_ld_b, dfeat_ld_t;
+  float* dctx;                                        /* [T, B, L, D] contiguous                                           */
+  float* dh0; float* dc0;                             /* [B, H]                                                            */
+  float* dcat; float* dattn; float* dhdir; float* dc_carry;   /* scratch [B, D+H], [B, F], [B, H], [B, H]                  */
+  float* zpart; unsigned int* barrier;
+} dasa_decoder_bwd_t;
+int dasa_decoder_rollout_supported(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k);
+size_t dasa_decoder_rollout_scratch_floats(int B);
+int dasa_decoder_rollout_fwd(const dasa_decoder_fwd_t* args, void* stream);
+int dasa_decoder_rollout_bwd(const dasa_decoder_bwd_t* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------- encoder pieces (a9)
  * BertEmbeddings (vilmodel.py:161-176): out[b,l,:] = LN(word[ids[b,l]] + pos[l] + type[0]) (* mask*scale).          */
