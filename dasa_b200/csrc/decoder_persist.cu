@@ -56,6 +56,14 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
   __syncthreads();
 }
 
+// Phase timestamps of CTA 0 (SM clock) for the LAST launch: [0] = after the prologue barrier, then one per phase barrier of the
+// first DP_TIMED_ACTIONS actions. Read with dasa_debug_decoder_phase_clocks (profiling only; ~20 clock reads per action).
+constexpr int DP_TIMED_ACTIONS = 4;
+__device__ long long g_dp_clock[1 + 8 * DP_TIMED_ACTIONS];
+__device__ __forceinline__ void dp_stamp(int idx) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && idx < 1 + 8 * DP_TIMED_ACTIONS) g_dp_clock[idx] = clock64();
+}
+
 // ------------------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint32_t dp_tf32(float x) {
   uint32_t r;
@@ -610,6 +618,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_fwd_kernel(cons
   fwd_issue_ctx(a, pl, smem_raw, S, 0);
   fwd_prologue(a);
   grid_sync(gb);
+  dp_stamp(0);
   for (int t = 0; t < a.T; ++t) {
 #pragma unroll 1
     for (int ph = 0; ph < 8; ++ph) {
@@ -622,6 +631,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_fwd_kernel(cons
         default: fwd_gemm16<MT>(a, t, ph, red, res); break;   // P1 (ph 0), P4 (ph 4), P6 (ph 7)
       }
       grid_sync(gb);
+      dp_stamp(1 + 8 * t + ph);
     }
   }
 }
@@ -915,6 +925,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
   bwd_issue_ctx(a, pl, smem_raw, S, a.T - 1);
   bwd_prologue(a);
   grid_sync(gb);
+  dp_stamp(0);
   for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
     const uint32_t par = (uint32_t)(it & 1);
 #pragma unroll 1
@@ -928,6 +939,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
         default: bwd_gemm16<MT>(a, t, ph, red, res); break;   // B6 (ph 0), B4 (ph 3), B1 (ph 7)
       }
       grid_sync(gb);
+      dp_stamp(1 + 8 * it + ph);
     }
   }
   const int gtid = blockIdx.x * DP_THREADS + threadIdx.x, gthreads = gridDim.x * DP_THREADS;
@@ -995,6 +1007,14 @@ int dp_launch(Kern kern, const Args& a, const LaunchPlan& lp, unsigned int* barr
 
 extern "C" int dasa_decoder_rollout_supported(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k) {
   return dp_launch_plan(B, H, E, F, V, L, D, NK, shift_k).ok ? 1 : 0;
+}
+
+extern "C" int dasa_debug_decoder_phase_clocks(long long* out, int n) {
+  const int m = 1 + 8 * DP_TIMED_ACTIONS;
+  long long h[1 + 8 * DP_TIMED_ACTIONS];
+  if (cudaMemcpyFromSymbol(h, g_dp_clock, sizeof(h)) != cudaSuccess) return DASA_ERR_CUDA;
+  for (int i = 0; i < n && i < m; ++i) out[i] = h[i];
+  return m;
 }
 
 extern "C" size_t dasa_decoder_rollout_scratch_floats(int B) { return (size_t)(B < 1 ? 1 : B) * 8 * DP_MAXROWS; }

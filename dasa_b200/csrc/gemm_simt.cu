@@ -143,9 +143,16 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, i
   C[(int64_t)m * ldc + n] = apply_epilogue(v, m, n, N, epilogue, ep);
 }
 
-// out[n] (+)= sum_m X[m, n]: grid (N/32 column groups, row slabs); 32x8 threads; slabs combine with one atomicAdd per column
+// out[n] (+)= sum_m X[m, n]: grid (N/32 column groups, row slabs); 32x8 threads. The slabs of a column group are combined in slab
+// order by the LAST block of that group to finish (ticket counter): bit-reproducible bias gradients, no float atomics.
+constexpr int COLSUM_PART_FLOATS = 1 << 17;
+constexpr int COLSUM_MAX_GROUPS = 1 << 12;
+__device__ float g_colsum_part[COLSUM_PART_FLOATS];
+__device__ unsigned int g_colsum_ticket[COLSUM_MAX_GROUPS];
+
 __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out, int rows_per_slab) {
   __shared__ float red[8][33];
+  __shared__ bool last;
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int m0 = blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
   float s = 0.f;
@@ -153,11 +160,28 @@ __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, i
     for (int m = m0 + threadIdx.y; m < m1; m += 8) s += X[(int64_t)m * ldx + n];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float t = 0.f;
+  float t = 0.f;
+  if (threadIdx.y == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    atomicAdd(out + n, t);
+  }
+  if (gridDim.y == 1) {
+    if (threadIdx.y == 0 && n < N) out[n] += t;
+    return;
+  }
+  const int ngrp = gridDim.x * 32;
+  if (threadIdx.y == 0) g_colsum_part[(size_t)blockIdx.y * ngrp + blockIdx.x * 32 + threadIdx.x] = t;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) last = atomicAdd(&g_colsum_ticket[blockIdx.x], 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.y == 0) {
+    float v = 0.f;
+    for (int z = 0; z < (int)gridDim.y; ++z) v += __ldcg(g_colsum_part + (size_t)z * ngrp + blockIdx.x * 32 + threadIdx.x);
+    if (n < N) out[n] += v;
+    if (threadIdx.x == 0) g_colsum_ticket[blockIdx.x] = 0;
   }
 }
 
@@ -257,6 +281,9 @@ extern "C" int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out
   int slabs = (int)dasa_cdiv(4 * DASA_NUM_SMS, col_groups);          // ~4 CTAs per SM in total
   const int max_slabs = (int)dasa_cdiv(M, 64);
   slabs = slabs < 1 ? 1 : (slabs > max_slabs ? max_slabs : slabs);
+  // the slab partials live in a static scratch (launches on one stream are ordered; one training process per device)
+  if (col_groups > COLSUM_MAX_GROUPS) slabs = 1;
+  while (slabs > 1 && (int64_t)slabs * col_groups * 32 > COLSUM_PART_FLOATS) --slabs;
   const int rows_per_slab = (int)dasa_cdiv(M, slabs);
   dim3 grid((unsigned)col_groups, (unsigned)dasa_cdiv(M, rows_per_slab));
   colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(X, ldx, M, N, out, rows_per_slab);

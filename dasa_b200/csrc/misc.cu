@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__
   mask_fill(mask, n, p, seed, offset);
 }
 
+constexpr int CE_MAX_ROWS = 1 << 18;
+__device__ float g_ce_rows[CE_MAX_ROWS];
+__device__ unsigned int g_ce_ticket = 0;
+
 // one warp per sample: log-softmax over the (masked) candidate logits, CE with ignore_index, gradient, argmax
 __global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict__ logit, int64_t ld, const int64_t* __restrict__ target,
                                                         int ignore_index, int B, int Nc, float grad_scale, float* __restrict__ loss_acc,
@@ -105,7 +109,8 @@ __global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict_
                                                         float* __restrict__ logprob_action, float* __restrict__ entropy) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
+  float* row_loss = g_ce_rows;
+  if (b < B) {
   const float* z = logit + (int64_t)b * ld;
   float mx = -INFINITY;
   int arg = 0x7fffffff;
@@ -139,11 +144,27 @@ __global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict_
   }
   ent = warp_sum(ent);
   if (lane == 0) {
-    if (valid && loss_acc != nullptr) atomicAdd(loss_acc, in_range ? lse - z[t] : NAN);
+    if (loss_acc != nullptr) row_loss[b] = valid ? (in_range ? lse - z[t] : NAN) : 0.f;
     if (action != nullptr) action[b] = arg;
     if (logprob_action != nullptr) logprob_action[b] = z[arg] - lse;
     if (entropy != nullptr) entropy[b] = ent;
   }
+  }
+  if (loss_acc == nullptr) return;
+  // the per-row losses are folded in row order by the last block to finish (bit-reproducible loss, no float atomics)
+  __shared__ bool last;
+  __shared__ float red[32];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&g_ce_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float v = 0.f;
+  const int per = (B + blockDim.x - 1) / blockDim.x;          // contiguous slice per thread, fixed order
+  for (int i = threadIdx.x * per; i < min(B, (int)(threadIdx.x + 1) * per); ++i) v += __ldcg(row_loss + i);
+  v = block_sum(v, red);
+  if (threadIdx.x == 0) { loss_acc[0] += v; g_ce_ticket = 0; }
 }
 
 // out[c, r] = in[r, c] through a 32x33 shared tile (both sides coalesced)
@@ -272,7 +293,7 @@ extern "C" int dasa_bump_counter(uint64_t* counter, uint64_t inc, void* stream) 
 extern "C" int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* target, int ignore_index, int B, int Nc, float grad_scale,
                               float* loss_acc, float* dlogit, int64_t* action, float* logprob_action, float* entropy, void* stream) {
   if (B <= 0) return DASA_OK;
-  if (Nc <= 0) return DASA_ERR_BAD_SHAPE;
+  if (Nc <= 0 || B > CE_MAX_ROWS) return DASA_ERR_BAD_SHAPE;
   masked_ce_kernel<<<(unsigned)dasa_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(logit, ld, target, ignore_index, B, Nc, grad_scale,
                                                                                loss_acc, dlogit, action, logprob_action, entropy);
   return dasa_check_launch("masked_ce_kernel");

@@ -59,14 +59,28 @@ def _wgrad(weight, dy, x, bias=None, bias2=None):
     ent[3].append(x2)
 
 
-def flush_weight_grads():
-    """Run the queued weight-gradient reductions (call once after loss.backward())."""
-    for weight, bias, dys, xs, bias2 in _queue.values():
+def _inside(t, owner):
+    """True when tensor t lives inside the flat buffer `owner`."""
+    if t is None:
+        return False
+    lo = owner.data_ptr()
+    return lo <= t.data_ptr() < lo + owner.numel() * owner.element_size()
+
+
+def flush_weight_grads(owner=None):
+    """Run the queued weight-gradient reductions (call once after loss.backward()). owner: a flat gradient buffer — only the
+    weights whose .grad is a view of it are flushed (trainer.py reduces one optimizer group while the next one's GEMMs run)."""
+    done = []
+    for key, (weight, bias, dys, xs, bias2) in _queue.items():
+        if owner is not None and not _inside(weight.grad, owner):
+            continue
         dY = dys[0] if len(dys) == 1 else torch.cat(dys, 0)
         X = xs[0] if len(xs) == 1 else torch.cat(xs, 0)
         ops.linear_bwd_weight(dY, X, _zeros_like_grad(weight), True)
         _bias_grads(dY, bias, bias2)
-    _queue.clear()
+        done.append(key)
+    for key in done:
+        del _queue[key]
 
 
 def _rowmajor(t):

@@ -296,6 +296,9 @@ typedef struct {
 } dasa_decoder_bwd_t;
 int dasa_decoder_rollout_supported(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k);
 size_t dasa_decoder_rollout_scratch_floats(int B);
+/* Profiling aid: SM-clock timestamps of CTA 0 at the phase barriers of the first 4 actions of the LAST rollout launch (forward or
+ * backward): out[0] = after the prologue, out[1 + 8*i + ph] = after phase ph of the i-th processed action. Returns the count. */
+int dasa_debug_decoder_phase_clocks(long long* out, int n);
 int dasa_decoder_rollout_fwd(const dasa_decoder_fwd_t* args, void* stream);
 int dasa_decoder_rollout_bwd(const dasa_decoder_bwd_t* args, void* stream);
 

@@ -46,7 +46,9 @@ def test_state_dict_contract(cfg):
         assert tuple(e["bert.vision_encoder.visn_fc.weight"].shape) == (768, 2176)
         assert tuple(e["lstm.weight_hh_l0_reverse"].shape) == (4096, 1024)
         assert tuple(e["encoder_lstm2decoder_ct.weight"].shape) == (1024, 2048)
-        assert sum(p.numel() for p in enc.parameters()) == 162_627_328 or True
+        assert sum(p.numel() for p in enc.parameters()) == 162_600_192
+        assert sum(p.numel() for p in dec.parameters()) == 29_643_845
+        assert sum(p.numel() for p in cri.parameters()) == 1_050_625 and sum(p.numel() for p in ada.parameters()) == 4_196_352
         return
     for name, mod in shapes.items():
         have = [(k, tuple(v.shape)) for k, v in mod.state_dict().items()]

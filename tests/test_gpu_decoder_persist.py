@@ -81,9 +81,13 @@ def _problem(cfg, B, T, L, seed, train):
 
     def rn(*s, scale=1.0):
         return (torch.randn(*s, generator=g) * scale).to(DEV)
-    w = {"w_in": rn(F, H, scale=H ** -0.5), "w_shift": rn(k, H, scale=H ** -0.5), "b_shift": rn(k, scale=0.1),
+    # attention projections scaled so that the view / token logits are O(1..5) like the policy's own (synth.policy_state): with
+    # unit-variance logits of 2176 terms the softmax is a near one-hot whose gradient amplifies the TF32 rounding of the logits
+    # ~20x, which measures the conditioning of the synthetic problem rather than the kernel
+    att = 0.15 if F >= 1024 else 1.0
+    w = {"w_in": rn(F, H, scale=att * H ** -0.5), "w_shift": rn(k, H, scale=H ** -0.5), "b_shift": rn(k, scale=0.1),
          "w_ih": rn(4 * H, E + F, scale=(E + F) ** -0.5), "w_hh": rn(4 * H, H, scale=H ** -0.5), "b_ih": rn(4 * H, scale=0.1),
-         "b_hh": rn(4 * H, scale=0.1), "w_att_in": rn(D, H, scale=H ** -0.5), "w_att_out": rn(H, D + H, scale=(D + H) ** -0.5)}
+         "b_hh": rn(4 * H, scale=0.1), "w_att_in": rn(D, H, scale=att * H ** -0.5), "w_att_out": rn(H, D + H, scale=(D + H) ** -0.5)}
     emb = torch.tanh(rn(T, B, E))
     feat = rn(T, B, V, F, scale=0.5).abs()
     ctx = rn(T, B, L, D, scale=0.5)
@@ -216,7 +220,8 @@ def test_module_step_and_rollout_use_the_persistent_kernel(train):
         l2 = torch.stack(l2).detach().cpu()
         assert torch.equal(torch.isfinite(l2), fin)
         assert rel(l2[fin], lg[fin]) <= 1e-2, name
-    assert rel(torch.stack(logits_s), torch.stack(logits_b)) <= 2e-3
+    ls_, lb_ = torch.stack(logits_s).detach().cpu(), torch.stack(logits_b).detach().cpu()
+    assert rel(ls_[fin], lb_[fin]) <= 2e-3
     for grp, mod in (("adaIn", pol.adaIn), ("decoder", pol.decoder), ("encoder", pol.encoder)):
         for k, prm in mod.named_parameters():
             want = ost[grp][k].grad
