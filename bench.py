@@ -50,6 +50,9 @@ def parse():
                     help="configs[2]: --d_update_add_layer True (gradients through the 3 cross-modal layers + vision encoder), "
                          "batch 2, two accumulate_gradient('sample') passes (GT + augmented env, train.py:226-243) per optimizer "
                          "step, lr 2e-6: the latency-bound small-batch path")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: blocking all-reduces after the last weight-gradient GEMM")
+    ap.add_argument("--skip-config3", action="store_true", help="N > 1: do not also time BASELINE configs[3] (512 episodes/GPU, sampled feedback)")
+    ap.add_argument("--skip-config0", action="store_true", help="do not time BASELINE configs[0] (single eval decode step, GPU vs CPU eager)")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket exactly one eager step with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     return ap.parse_args()
@@ -236,13 +239,15 @@ def run_ours(args):
     from dasa_b200 import lib, modules as M, ops, synth
     from dasa_b200.config import FULL
     from dasa_b200.rollout import DeviceEpisodes, NavPolicy
+    from dasa_b200.trainer import RolloutTrainer
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.timedelta(seconds=600))
     lib.load()
     ops.set_precision(args.precision)
     from dasa_b200 import functions as Fn
@@ -266,9 +271,6 @@ def run_ours(args):
     lr = 2e-6 if args.finetune else LR
     pol = NavPolicy(cfg, synth.policy_state(cfg, 0), dev).train()
     pol.schedule = args.schedule
-    pol.flatten_parameters()
-    from dasa_b200 import dist as ddist
-    ddist.broadcast_(pol.param_buffers(), world)
     sample = args.feedback == "sample"
     if sample:
         args.schedule = "sequential"                        # the next observation depends on the sampled action
@@ -277,29 +279,13 @@ def run_ours(args):
     ep_res = DeviceEpisodes(host_ep, dev, resident=True)
     src = M.DropoutSource(seed=1234 + rank, device_seed=True, device=dev)
     loss_host = torch.zeros(1).pin_memory()
-    state = {"graph": None, "loss": None, "launches": 0, "graph_error": None}
-
-    def fwd_bwd(ep):
-        pol.zero_grad()
-        src.advance()
-        with M.use_dropout_source(src):
-            # per-rank factor ml_weight / (B_local * world): summed gradients == one process running the global batch
-            loss, _, _ = pol.teacher_rollout(ep, T, ML_WEIGHT / world, tag_steps=False)
-            if sample:
-                # agent_dg.py:1352-1356: IL rollout, then the RL rollout, summed into one loss. Backpropagating each rollout as
-                # soon as it ends accumulates the same gradients and halves the activation footprint (512 episodes x 35
-                # actions x 2 rollouts of bi-LSTM gates do not fit 180 GB at once).
-                pol.backward(loss)
-                rl, _ = pol.sample_rollout(ep, T, tag_steps=False)
-                rl = rl / world
-                pol.backward(rl)
-                return (loss.detach() + rl.detach()).reshape(1)
-        pol.backward(loss)
-        return loss
-
-    def finish():
-        ddist.allreduce_sum_(pol.grad_buffers(), world)     # NCCL over NVLink: 4 flat buffers, ~190 MB
-        pol.optim_step(lr)
+    # the product API for one optimizer step (dasa_b200/trainer.py): per-rank loss scaling / global A2C normaliser, deferred
+    # weight-gradient GEMMs flushed group by group with each group's NCCL all-reduce overlapped, clip + RMSprop, and the whole
+    # thing captured as ONE CUDA graph at any world size
+    tr = RolloutTrainer(pol, T, feedback=args.feedback, lr=lr, world=world, dropout_source=src, passes=ml_weights,
+                        overlap=not args.no_overlap)
+    tr.broadcast_parameters()
+    state = {"graph_error": None}
 
     # e2e: every rollout's inputs come from pinned host memory. The copy of rollout i+1 runs on a side stream into a staging
     # set while rollout i computes (one device-to-device hand-over per step); the first upload of a timed region is exposed.
@@ -329,31 +315,10 @@ def run_ours(args):
             up["pending"] = False
             if prefetch_next:
                 start_upload()
-        if state["graph"] is not None:
-            state["graph"].replay()
-            loss = state["loss"]
-            if world > 1:
-                finish()
-        else:
-            loss = fwd_bwd(ep_res)
-            finish()
+        loss = tr.step(ep_res)
         if read_back:
             loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
-
-    def capture(make_ep=None, key=""):
-        """Whole rollout (forward, backward, deferred weight grads, and for N=1 clip + RMSprop) as ONE CUDA graph. With
-        make_ep the episodes themselves (device environment: T x observe + step kernels) are built inside the graph."""
-        Fn.invalidate_weight_caches()                       # cached transposes must be rebuilt INSIDE the graph every replay
-        torch.cuda.synchronize()
-        torch.cuda.empty_cache()                            # the eager warm-up's cached blocks cannot serve the graph's private pool
-        g = torch.cuda.CUDAGraph()
-        l0 = lib.launches
-        with torch.cuda.graph(g):
-            loss = fwd_bwd(ep_res if make_ep is None else make_ep())
-            if world == 1:
-                finish()
-        state["graph" + key], state["loss" + key], state["launches" + key] = g, loss, lib.launches - l0
 
     def timed(read_back, upload, steps, warmup):
         for _ in range(warmup):
@@ -375,21 +340,24 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         n = (lib.launches - l0) // steps
-        return float(ms) / steps, (n + state["launches"] if state["graph"] is not None else n)
+        return float(ms) / steps, (n + tr.graph_launches if tr.graph is not None else n)
 
-    for _ in range(2):                                      # eager warm-up (allocator, caches, autotuned smem attributes)
+    for _ in range(2):                                      # eager warm-up (allocator, caches, smem attributes, NCCL communicator)
         one_step(ep_res, False)
     torch.cuda.synchronize()
-    if not args.no_graph and not args.profile_step:
+
+    def try_capture(trainer, ep):
+        if args.no_graph or args.profile_step:
+            return
         try:
-            capture()
+            trainer.capture(ep)
         except Exception as e:                              # stay on eager launches, say so in the JSON line
-            state["graph"], state["graph_error"] = None, repr(e)[:200]
+            trainer.release_graph()
+            state["graph_error"] = repr(e)[:200]
             torch.cuda.synchronize()
-            Fn.invalidate_weight_caches()
+    try_capture(tr, ep_res)
 
     if args.profile_step:
-        state["graph"] = None
         Fn.invalidate_weight_caches()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -404,38 +372,58 @@ def run_ours(args):
         sampler.start()
     ms_step, launches = timed(False, False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    launch_mode = "cuda-graph replay of the whole rollout" if state["graph"] is not None else \
+    launch_mode = ("cuda-graph replay of the whole optimizer step (rollout fwd+bwd, %sclip + RMSprop)" % (
+        "NCCL gradient all-reduces, " if world > 1 else "")) if tr.graph is not None else \
         "eager launches (%s)" % (state["graph_error"] or "--no-graph")
     ms_e2e, _ = timed(True, True, args.steps, 1)
     Fn.invalidate_weight_caches()
     env_arm = None
     if not sample and not args.skip_env:
         try:
-            env_arm = env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, loss_host, host_ep)
+            env_arm = env_e2e(args, cfg, B, T, dev, world, rank, tr, try_capture, loss_host, host_ep)
         except Exception as e:                              # reported, never fatal for the headline line
             env_arm = {"error": repr(e)[:300]}
         Fn.invalidate_weight_caches()
     # the same workload on the per-action schedule (the order a sampled / greedy rollout is forced to use)
     ms_seq = None
     if args.schedule == "batched" and not args.skip_sequential and not sample:
-        state["graph"], state["loss"] = None, None
+        tr.release_graph()
         pol.schedule = "sequential"
         torch.cuda.synchronize()
         try:
             for _ in range(2):
                 one_step(ep_res, False)
             torch.cuda.synchronize()
-            if not args.no_graph:
-                capture()
+            try_capture(tr, ep_res)
             ms_seq, _ = timed(False, False, max(1, args.steps // 2), 1)
         except Exception as e:
             ms_seq = None
             state["graph_error"] = repr(e)[:200]
-        state["graph"] = None
+        tr.release_graph()
         pol.schedule = args.schedule
-        Fn.invalidate_weight_caches()
 
-    nav = B * T * world * (2 if sample else 1) * n_acc    # sample feedback: a teacher-forced and a sampled rollout per pass
+    # standalone cost of the gradient all-reduce (the four flat buffers, back to back, nothing to overlap with): what the
+    # overlapped, captured reduction has to hide
+    allreduce_ms = None
+    if world > 1:
+        tr.release_graph()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            if i == 1:
+                a0.record()
+            for buf in pol.grad_buffers():
+                dist.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        ar = torch.tensor([a0.elapsed_time(a1) / 2.0], device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(ar)
+    config3 = None
+    if world > 1 and not sample and not args.finetune and not args.skip_config3:
+        config3 = config3_arm(args, cfg, T, dev, world, rank, pol, tr, peaks)
+    nav = B * T * world * (2 if sample else 1) * n_acc    # sample feedback: a teacher-forced and a sampled rollout per pass; n_acc passes
     value = nav / (ms_step * 1e-3)
     e2e_value = nav / (ms_e2e * 1e-3)
     if rank != 0:
@@ -447,12 +435,17 @@ def run_ours(args):
     # The captured graphs (and their private memory pools) are released first: at 512 episodes/GPU a graph pool and an eager
     # rollout do not fit the 180 GB together.
     import gc
-    for k in [k for k in state if k.startswith("graph") or k.startswith("loss")]:
-        state[k] = None
+    tr.release_graph()
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     roof = dominant_kernel_roofline(pol, ep_res, src, peaks, peak_src)
+    config0 = None
+    if not args.skip_config0 and not sample:
+        try:
+            config0 = config0_arm(args, cfg, dev, pol, ep_res, host_ep, not args.skip_cpu_baseline and world == 1)
+        except Exception as e:
+            config0 = {"error": repr(e)[:300]}
     extra = {} if args.skip_micro else micro_rooflines(peak_gbs)
     cpu = None
     if not args.skip_cpu_baseline and world == 1:
@@ -489,13 +482,18 @@ def run_ours(args):
         "roofline": roof, "kernels": extra, "cpu_baseline": cpu,
         "sequential_schedule": None if ms_seq is None else {"value": nav / (ms_seq * 1e-3), "unit": "nav steps/s",
                                                              "ms_per_step": ms_seq},
+        "graph_ms": ms_step if launch_mode.startswith("cuda-graph") else None, "allreduce_ms": allreduce_ms,
+        "allreduce": None if world == 1 else ("4 flat gradient buffers (%.0f MB fp32), each all-reduced asynchronously as soon as its "
+                                              "weight-gradient GEMMs are enqueued, largest first; standalone cost allreduce_ms" % (
+                                                  sum(b.numel() for b in pol.grad_buffers()) * 4 / 1e6)),
+        "config0_single_step": config0, "config3": config3,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, loss_host, host_ep):
+def env_e2e(args, cfg, B, T, dev, world, rank, tr_main, try_capture, loss_host, host_ep):
     """End-to-end arm over the device-resident environment (dasa_b200/env.py): the RGB / depth feature
     banks and the navigation-graph tables live in HBM (the reference keeps them in host RAM and re-uploads every observation),
     so a rollout's host inputs are the episode descriptors (start viewpoint, heading, goal: 12 B per episode) and the tokenised
@@ -533,16 +531,13 @@ def env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, 
         d_len.copy_(h_len, non_blocking=True)
         env.reset(h_start[i % K], h_view[i % K], h_goal[i % K])
 
+    from dasa_b200.trainer import RolloutTrainer
+    tr = RolloutTrainer(tr_main.pol, T, feedback="teacher", lr=tr_main.lr, world=world, dropout_source=tr_main.src,
+                        passes=tr_main.ml_weights, overlap=tr_main.overlap)
+
     def step(i):
         upload(i)
-        if state.get("graph_env") is not None:
-            state["graph_env"].replay()
-            loss = state["loss_env"]
-            if world > 1:
-                finish()
-        else:
-            loss = fwd_bwd(make_ep())
-            finish()
+        loss = tr.step(make_ep) if tr.graph is not None else tr.step_eager(make_ep())
         loss_host.copy_(loss.detach(), non_blocking=True)
 
     env.reset(h_start[0], h_view[0], h_goal[0])
@@ -550,15 +545,8 @@ def env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, 
         step(i)
     torch.cuda.synchronize()
     env.check()
-    mode = "eager launches"
-    if not args.no_graph:
-        try:
-            capture(make_ep, "_env")
-            mode = "cuda-graph replay (environment unroll + rollout + optimizer)"
-        except Exception as e:
-            state["graph_env"] = None
-            mode = "eager launches (%s)" % repr(e)[:120]
-            torch.cuda.synchronize()
+    try_capture(tr, make_ep)
+    mode = "cuda-graph replay (environment unroll + rollout + optimizer)" if tr.graph is not None else "eager launches"
     for i in range(2):
         step(i)
     torch.cuda.synchronize()
@@ -578,8 +566,8 @@ def env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, 
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     env.check()
     ms = float(ms) / args.steps
-    n_launch = (lib.launches - l0) // args.steps + (state.get("launches_env", 0) if state.get("graph_env") is not None else 0)
-    state["graph_env"] = None
+    n_launch = (lib.launches - l0) // args.steps + (tr.graph_launches if tr.graph is not None else 0)
+    tr.release_graph()
     # HBM roofline of the observation gather at a large batch (L2 flushed between launches)
     obs_roof = None
     if rank == 0 and not args.skip_micro:
@@ -619,6 +607,155 @@ def env_e2e(args, cfg, B, T, dev, world, rank, fwd_bwd, finish, capture, state, 
                     "episode descriptors and tokenised instructions are uploaded, the teacher-forced trajectories are unrolled and "
                     "every observation is assembled on the device (env_observe / env_step kernels), then the same fwd+bwd+RMSprop "
                     "as `value`" % (n, 2 * n * cfg.views * cfg.rgb_size * 4 / 1e6)}
+
+
+def config0_arm(args, cfg, dev, pol, ep, host_ep, with_cpu):
+    """BASELINE.json configs[0]: ONE agent_dg decode step (the loop body of vl_rollout up to the masked logits, agent_dg.py:727-841:
+    AdaIN gate on views + candidates, the 9 + 3 layer encoder, bi-LSTM, decoder), eval mode, forward only, batch 20, on the GPU
+    (CUDA-graph replay of the step, L2 flushed between replays) next to the reference algorithm on the host CPU (oracle port,
+    CPU eager, all cores)."""
+    from dasa_b200 import lib
+    was_training = pol.decoder.training
+    pol.eval()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    try:
+        with torch.no_grad():
+            for _ in range(2):
+                pol.step(ep, 0, None)
+            torch.cuda.synchronize()
+            l0 = lib.launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                logit, h_t, carry = pol.step(ep, 0, None)
+            n_launch = lib.launches - l0
+            ts = []
+            for i in range(7):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            ms_graph = ts[len(ts) // 2]
+            te = []
+            for i in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pol.step(ep, 0, None)
+                e1.record()
+                torch.cuda.synchronize()
+                te.append(e0.elapsed_time(e1))
+            te.sort()
+            del g
+        out = {"what": "one decode step (AdaIN gates, 9 la + 3 vl layers, bi-LSTM, decoder, masked candidate logits), eval forward, "
+                       "B=%d, 36 views x 2176, hidden 1024 (BASELINE.json configs[0])" % ep.B,
+               "gpu_ms": ms_graph, "gpu_ms_eager_launches": te[len(te) // 2], "gpu_launches": n_launch,
+               "gpu_steps_per_sec": ep.B / (ms_graph * 1e-3), "unit": "nav steps/s", "l2": "flushed between replays"}
+    finally:
+        if was_training:
+            pol.train()
+    if with_cpu:
+        from dasa_b200 import synth
+        from oracle import restated as R
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        st = synth.policy_state(cfg, 0)
+        tc = []
+        with torch.no_grad():
+            for i in range(4):
+                t0 = time.perf_counter()
+                R.teacher_rollout(st, cfg, host_ep, 1, ML_WEIGHT, R.NoDrop())
+                tc.append(time.perf_counter() - t0)
+        cpu_ms = 1e3 * sorted(tc[1:])[len(tc[1:]) // 2]
+        out.update({"cpu_ms": cpu_ms, "cpu_cores": cores, "cpu_kind": "port (oracle on CPU torch, eager)",
+                    "cpu_steps_per_sec": host_ep.B / (cpu_ms * 1e-3), "speedup": cpu_ms / out["gpu_ms"]})
+    return out
+
+
+def config3_arm(args, cfg, T, dev, world, rank, pol, tr_main, peaks):
+    """BASELINE.json configs[3] inside the N > 1 run: 512 episodes per GPU, accumulate_gradient('sample') (teacher-forced + sampled
+    A2C rollout per optimizer step, A2C loss normalised by the batch-GLOBAL live-action count), NCCL gradient all-reduce, one
+    warm-up + two timed optimizer steps, device time, max over ranks. Also the shift-attention / AdaIN-gate HBM rooflines at
+    B = 512 (rank 0). Errors are reported, never fatal for the headline line."""
+    import gc
+    import torch.distributed as dist
+    from dasa_b200 import functions as Fn, modules as M, ops, synth
+    from dasa_b200.rollout import DeviceEpisodes
+    from dasa_b200.trainer import RolloutTrainer
+    B3 = 512
+    out = {"batch_per_gpu": B3, "feedback": "sample"}
+    tr = None
+    try:
+        gc.collect()
+        torch.cuda.empty_cache()
+        Fn.defer_weight_grads(False)                        # 512 x 35 rows of dY / X per weight do not need (or fit) deferral
+        pol.schedule = "sequential"
+        ep = DeviceEpisodes(synth.Episodes(B3, T + 1, cfg, seed=300 + rank), dev, resident=True)
+        tr = RolloutTrainer(pol, T, feedback="sample", lr=tr_main.lr, world=world, dropout_source=tr_main.src,
+                            overlap=tr_main.overlap)
+        tr.step_eager(ep)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            tr.step_eager(ep)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / 2.0], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        nav = B3 * T * 2 * world
+        out.update({"value": nav / (float(ms) * 1e-3), "unit": "nav steps/s", "ms_per_step": float(ms), "n_gpus": world,
+                    "steps": 2, "warmup": 1, "launch": "eager launches",
+                    "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9})
+        del ep
+        if rank == 0:
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            V, C, A = cfg.views, cfg.rgb_size, cfg.angle_size
+            F = C + A
+            f = torch.rand(B3, V, F, device=dev)
+            gsrc = torch.randn(B3 * V, C, device=dev)
+            o = torch.empty(B3, V, F, device=dev)
+            h_t = torch.randn(B3, F, device=dev) * 0.05
+            kl = torch.randn(B3, 5, device=dev)
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+            def timeit(fn):
+                ts = []
+                for i in range(8):
+                    flush.zero_()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    fn()
+                    a1.record()
+                    torch.cuda.synchronize()
+                    if i >= 2:
+                        ts.append(a0.elapsed_time(a1) * 1e-3)
+                ts.sort()
+                return ts[len(ts) // 2]
+            roofs = {}
+            for name, bytes_, fn in (
+                    ("shift_attention_fwd", 4 * (B3 * V * F + 2 * B3 * F + B3 * V + B3 * 5),
+                     lambda: ops.row_attention_fwd(f, h_t, None, 5, 12, kl)),
+                    ("adain_gate_modulate", 4 * 3 * B3 * V * C, lambda: ops.gate_modulate(gsrc, f[..., :C], o[..., :C]))):
+                t = timeit(fn)
+                roofs[name] = {"bound": "hbm", "achieved": bytes_ / t / 1e9, "peak": peak, "frac": bytes_ / t / 1e9 / peak,
+                               "frac_of_8TBs": bytes_ / t / 1e9 / 8000.0, "unit": "GB/s", "batch": B3}
+            out["kernels_at_b512"] = roofs
+    except Exception as e:
+        out["error"] = repr(e)[:300]
+    finally:
+        Fn.defer_weight_grads(args.batch <= 64)
+        pol.schedule = args.schedule
+        Fn._queue.clear()
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
 
 
 def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
