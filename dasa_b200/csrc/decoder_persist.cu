@@ -20,6 +20,7 @@
 // The k-index trick of gemm_skinny.cu is used throughout: a lane loads 4 consecutive k of its rows and uses component j in
 // MMA step j for BOTH operands, so every global access is 128-bit and any bijection of the reduction index is a valid GEMM.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -30,6 +31,7 @@ constexpr int DP_WARPS = 8;
 constexpr int DP_CHUNK = 32;         // k per chunk
 constexpr int DP_MAXROWS = 128;      // attention rows (views / tokens)
 constexpr int DP_MAXK = 15;          // shift kernel taps
+constexpr int DP_NST2 = 2;           // chunks in flight per warp in the 32-row GEMM phases (register budget: 3 spill at 24 episodes); 3 in the 16-row ones
 
 // ------------------------------------------------------------------------------------------------ device-wide barrier
 struct GridBar {
@@ -44,14 +46,15 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
   gb.target += gb.nblk;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    // bar.sync orders every thread's writes before thread 0's gpu-scope release (cumulativity); the acquire poll + the closing
+    // bar.sync order them before every thread's later reads on the other SMs. Measured 1.26 us per barrier over 148 CTAs
+    // against 1.68 us with __threadfence() on both sides (scripts/barrier_bench.py).
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
     unsigned int v, it = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
       if (++it > (1u << 22)) __trap();
     } while ((int)(v - gb.target) < 0);
-    __threadfence();
   }
   __syncthreads();
 }
@@ -100,21 +103,37 @@ __host__ __device__ __forceinline__ int dp_chunk_pitch(int D, int S) { return (i
 
 // ---------------------------------------------------------------------------------------------------- GEMM building block
 // One CTA-wide product: res[m][nl] = sum_k X[m, k] * W_row(nl)[k] for m < 8*MT (rows >= M read as zero), nl < 16*RT.
-// wrow[i] (i < 2*RT) = this lane's W row for local row g + 8*i, already offset by 4*t. K % 32 == 0.
+// W is stored as fp16: its 10-bit mantissa is exactly TF32's, so for |w| in [2^-14, 65504] the value the tensor core multiplies is
+// bit-identical to cvt.rna.tf32(w) of the fp32 master weight (smaller |w| carry an absolute error <= 3e-8) while the weight
+// stream per action halves to 42 MB, which stays resident in the 126 MB L2 from one action to the next.
+// wrow[i] (i < 2*RT) = this lane's W row for local row g + 8*i, already offset by 4*t halves. K % 32 == 0.
 // red: DP_WARPS*RT*MT*128 floats, res: 16*RT*8*MT floats (shared memory). Ends with a __syncthreads: res is complete.
+typedef __half wt_t;
+__device__ __forceinline__ uint2 ldg_w4(const wt_t* p) {          // 4 consecutive fp16 weights, read-only path, no L1 allocation
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+// component j of 4 packed halves as a TF32 operand (the fp16 -> fp32 conversion is exact and already TF32-representable)
+__device__ __forceinline__ uint32_t h4_tf32(const uint2& v, int j) {
+  const uint32_t w = (j < 2) ? v.x : v.y;
+  const unsigned short h = (j & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
+  return __float_as_uint(__half2float(__ushort_as_half(h)));
+}
+
 template <int MT, int RT>
 struct GemmFrag {
-  float4 w[2 * RT][2];
+  uint2 w[2 * RT][2];
   float4 x[MT][2];
 };
 
 template <int MT, int RT>
-__device__ __forceinline__ void dp_load(GemmFrag<MT, RT>& f, const float* (&wrow)[2 * RT], const float* (&xrow)[MT],
+__device__ __forceinline__ void dp_load(GemmFrag<MT, RT>& f, const wt_t* (&wrow)[2 * RT], const float* (&xrow)[MT],
                                         const bool (&xok)[MT], int kc) {
 #pragma unroll
   for (int i = 0; i < 2 * RT; ++i) {
-    f.w[i][0] = ldg_stream4(wrow[i] + kc);
-    f.w[i][1] = ldg_stream4(wrow[i] + kc + 16);
+    f.w[i][0] = ldg_w4(wrow[i] + kc);
+    f.w[i][1] = ldg_w4(wrow[i] + kc + 16);
   }
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
@@ -141,18 +160,19 @@ __device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFr
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       uint32_t af[4];
-      af[0] = dp_tf32(f4_get(f.w[2 * h][0], j));       // (row g,     k = t)
-      af[1] = dp_tf32(f4_get(f.w[2 * h + 1][0], j));   // (row g + 8, k = t)
-      af[2] = dp_tf32(f4_get(f.w[2 * h][1], j));       // (row g,     k = t + 4)
-      af[3] = dp_tf32(f4_get(f.w[2 * h + 1][1], j));   // (row g + 8, k = t + 4)
+      af[0] = h4_tf32(f.w[2 * h][0], j);       // (row g,     k = t)
+      af[1] = h4_tf32(f.w[2 * h + 1][0], j);   // (row g + 8, k = t)
+      af[2] = h4_tf32(f.w[2 * h][1], j);       // (row g,     k = t + 4)
+      af[3] = h4_tf32(f.w[2 * h + 1][1], j);   // (row g + 8, k = t + 4)
 #pragma unroll
       for (int i = 0; i < MT; ++i) dp_mma(acc[h][i], af, bf[i][0], bf[i][1]);
     }
   }
 }
 
-template <int MT, int RT>
-__device__ __forceinline__ void dp_gemm_block(const float* (&wrow)[2 * RT], const float* X, int64_t ldx, int M, int K,
+// NST chunks of W / X in flight per warp (registers; the ring is fully unrolled so every fragment index is a constant)
+template <int MT, int RT, int NST>
+__device__ __forceinline__ void dp_gemm_block(const wt_t* (&wrow)[2 * RT], const float* X, int64_t ldx, int M, int K,
                                               float* red, float* res) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -174,16 +194,19 @@ __device__ __forceinline__ void dp_gemm_block(const float* (&wrow)[2 * RT], cons
       for (int e = 0; e < 4; ++e) acc[h][i][e] = 0.f;
 
   const int nchunks = K / DP_CHUNK;
-  GemmFrag<MT, RT> f0, f1;
+  GemmFrag<MT, RT> f[NST];
   int c = warp;
-  if (c < nchunks) dp_load<MT, RT>(f0, wrow, xrow, xok, c * DP_CHUNK);
+#pragma unroll
+  for (int s = 0; s < NST - 1; ++s)
+    if (c + s * DP_WARPS < nchunks) dp_load<MT, RT>(f[s], wrow, xrow, xok, (c + s * DP_WARPS) * DP_CHUNK);
 #pragma unroll 1
-  for (; c < nchunks; c += 2 * DP_WARPS) {
-    const bool has1 = c + DP_WARPS < nchunks;
-    if (has1) dp_load<MT, RT>(f1, wrow, xrow, xok, (c + DP_WARPS) * DP_CHUNK);
-    dp_compute<MT, RT>(acc, f0);
-    if (c + 2 * DP_WARPS < nchunks) dp_load<MT, RT>(f0, wrow, xrow, xok, (c + 2 * DP_WARPS) * DP_CHUNK);
-    if (has1) dp_compute<MT, RT>(acc, f1);
+  for (; c < nchunks; c += NST * DP_WARPS) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      const int cl = c + (s + NST - 1) * DP_WARPS;
+      if (cl < nchunks) dp_load<MT, RT>(f[(s + NST - 1) % NST], wrow, xrow, xok, cl * DP_CHUNK);
+      if (c + s * DP_WARPS < nchunks) dp_compute<MT, RT>(acc, f[s]);
+    }
   }
 
   // fold the K slices of the 8 warps in warp order (deterministic)
@@ -208,7 +231,7 @@ __device__ __forceinline__ void dp_gemm_block(const float* (&wrow)[2 * RT], cons
 }
 
 // plain row block: rows n0 .. n0+15 of W (clamped to N-1; the caller never stores rows >= N)
-__device__ __forceinline__ void dp_rows16(const float* (&wrow)[2], const float* W, int64_t ldw, int n0, int N) {
+__device__ __forceinline__ void dp_rows16(const wt_t* (&wrow)[2], const wt_t* W, int64_t ldw, int n0, int N) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -230,6 +253,7 @@ struct AttnSmem {
   float* aux2;       // [DP_MAXROWS] dp (bwd)
   float* kap;        // [16]
   float* colred;     // [8 * 128 * 4] column partial sums of the weighted sum
+  uint8_t* mk;       // [DP_MAXROWS] context padding flags of this CTA's episode
   uint64_t* bar;
 };
 
@@ -306,22 +330,26 @@ __device__ __forceinline__ void dp_weighted_sum(const AttnSmem& s, int pitch, in
   }
 }
 
-// warp 0: z[r] = sum over the S slice partials (fixed order), masked softmax -> s.prow (0 for masked rows)
+// z[r] = sum over the S slice partials (fixed order; one row per thread), then warp 0: masked softmax -> s.prow (0 for masked
+// rows). Ends with the softmax visible to warp 0 only: callers __syncthreads() before other warps read s.prow.
 __device__ __forceinline__ void dp_softmax_rows(const AttnSmem& s, const float* zpart_b, int S, int rows, const uint8_t* mask_b) {
+  for (int r = threadIdx.x; r < DP_MAXROWS; r += DP_THREADS) {
+    float v = -INFINITY;
+    if (r < rows && (mask_b == nullptr || mask_b[r] == 0)) {
+      v = 0.f;
+      for (int k = 0; k < S; ++k) v += ld_cg(zpart_b + (size_t)k * DP_MAXROWS + r);
+    }
+    s.zrow[r] = v;
+  }
+  __syncthreads();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     float z[DP_MAXROWS / 32];
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < DP_MAXROWS / 32; ++i) {
-      const int r = lane + 32 * i;
-      float v = -INFINITY;
-      if (r < rows && (mask_b == nullptr || mask_b[r] == 0)) {
-        v = 0.f;
-        for (int k = 0; k < S; ++k) v += ld_cg(zpart_b + (size_t)k * DP_MAXROWS + r);
-      }
-      z[i] = v;
-      mx = fmaxf(mx, v);
+      z[i] = s.zrow[lane + 32 * i];
+      mx = fmaxf(mx, z[i]);
     }
     mx = warp_max(mx);
     float sum = 0.f;
@@ -357,7 +385,7 @@ __host__ __device__ inline SmemPlan dp_plan(int MT, int V, int L, int F, int D, 
   const int pm = p.pitchF > p.pitchC ? p.pitchF : p.pitchC;
   p.off_tv = o; o += sizeof(float) * (size_t)pm;
   p.off_dv = o; o += sizeof(float) * (size_t)pm;
-  p.off_small = o; o += sizeof(float) * (5 * DP_MAXROWS + 16 + 8 * 128 * 4) + 32;
+  p.off_small = o; o += sizeof(float) * (5 * DP_MAXROWS + 16 + 8 * 128 * 4) + 32 + DP_MAXROWS;
   p.total = (o + 127) & ~(size_t)127;
   return p;
 }
@@ -372,6 +400,7 @@ __device__ __forceinline__ AttnSmem dp_attn_smem(unsigned char* raw, const SmemP
   s.kap = small + 5 * DP_MAXROWS;
   s.colred = s.kap + 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s.colred + 8 * 128 * 4);
+  s.mk = reinterpret_cast<uint8_t*>(bars + 4);          // padding flags of this CTA's episode (constant over the rollout)
   s.tile = reinterpret_cast<float*>(raw + (feat ? pl.off_tileF : pl.off_tileC));
   s.bar = bars + (feat ? 0 : 1);
   return s;
@@ -384,14 +413,27 @@ struct AttnOwner {
   Slice sl;
   const uint8_t* mask_b;
 };
-__device__ __forceinline__ AttnOwner dp_owner(int B, int S, int width, const uint8_t* mask, int64_t mask_ld) {
+// mask_s: the shared-memory copy of this CTA's episode padding flags (dp_stage_mask), or nullptr for "no mask"
+__device__ __forceinline__ AttnOwner dp_owner(int B, int S, int width, const uint8_t* mask_s) {
   AttnOwner o;
   o.on = (int)blockIdx.x < B * S;
   o.b = o.on ? (int)blockIdx.x / S : 0;
   o.s = o.on ? (int)blockIdx.x % S : 0;
   o.sl = dp_slice(width, S, o.s);
-  o.mask_b = (o.on && mask) ? mask + (int64_t)o.b * mask_ld : nullptr;
+  o.mask_b = o.on ? mask_s : nullptr;
   return o;
+}
+// once per launch: the padding flags of this CTA's episode into shared memory (they were re-read from global memory, one
+// dependent L2 round trip per row, in every attention phase of every action)
+__device__ __forceinline__ void dp_stage_mask(unsigned char* raw, const SmemPlan& pl, int B, int S, int L, const uint8_t* mask,
+                                              int64_t mask_ld) {
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  const bool on = (int)blockIdx.x < B * S;
+  const int b = on ? (int)blockIdx.x / S : 0;
+  for (int r = threadIdx.x; r < DP_MAXROWS; r += DP_THREADS) sc.mk[r] = (on && mask != nullptr && r < L) ? mask[(int64_t)b * mask_ld + r] : 0;
+}
+__device__ __forceinline__ const uint8_t* dp_mask_smem(unsigned char* raw, const SmemPlan& pl, const uint8_t* mask) {
+  return mask != nullptr ? dp_attn_smem(raw, pl, false).mk : nullptr;
 }
 
 // ---- the GEMM phases (one function each)
@@ -406,18 +448,18 @@ __device__ __forceinline__ void fwd_gemm16(const dasa_decoder_fwd_t& a, const in
   const int tid = threadIdx.x;
   const int64_t tb = (int64_t)t * B;
   const float scale = a.drop_scale;
-  const float* W; const float* X;
+  const wt_t* W; const float* X;
   int64_t ldw, ldx;
   int N, K;
-  if (ph == 0)      { W = a.w_feat;    ldw = H;  N = NK; K = H;  X = a.hprev_drop + tb * H; ldx = H; }    // P1: tk = W_feat drop(h~) + b
-  else if (ph == 4) { W = a.w_att_in;  ldw = H;  N = D;  K = H;  X = a.cat + tb * DC + D;   ldx = DC; }   // P4: t2 = W_att_in drop(h_1)
-  else              { W = a.w_att_out; ldw = DC; N = H;  K = DC; X = a.cat + tb * DC;       ldx = DC; }   // P6: h~ = tanh(W_att_out [wc ; drop(h_1)])
+  if (ph == 0)      { W = reinterpret_cast<const wt_t*>(a.w_feat);    ldw = H;  N = NK; K = H;  X = a.hprev_drop + tb * H; ldx = H; }    // P1: tk = W_feat drop(h~) + b
+  else if (ph == 4) { W = reinterpret_cast<const wt_t*>(a.w_att_in);  ldw = H;  N = D;  K = H;  X = a.cat + tb * DC + D;   ldx = DC; }   // P4: t2 = W_att_in drop(h_1)
+  else              { W = reinterpret_cast<const wt_t*>(a.w_att_out); ldw = DC; N = H;  K = DC; X = a.cat + tb * DC;       ldx = DC; }   // P6: h~ = tanh(W_att_out [wc ; drop(h_1)])
   W = dp_opaque(W);
   const int nitems = (N + 15) / 16;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const float* wrow[2];
+    const wt_t* wrow[2];
     dp_rows16(wrow, W, ldw, item * 16, N);
-    dp_gemm_block<MT, 1>(wrow, X, ldx, B, K, red, res);
+    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res);
     for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
       const int m = o >> 4, n = item * 16 + (o & 15);
       if (m >= B || n >= N) continue;
@@ -451,10 +493,10 @@ __device__ __forceinline__ void fwd_p3(const dasa_decoder_fwd_t& a, const int t,
       const int nitems = H / 8;
       const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const float* wrow[4];
+        const wt_t* wrow[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wrow[i] = dp_opaque(a.w_lstm) + (int64_t)(i * H + item * 8 + g) * KX + 4 * tq;
-        dp_gemm_block<MT, 2>(wrow, X, KX, B, KX, red, res);
+        for (int i = 0; i < 4; ++i) wrow[i] = dp_opaque(reinterpret_cast<const wt_t*>(a.w_lstm)) + (int64_t)(i * H + item * 8 + g) * KX + 4 * tq;
+        dp_gemm_block<MT, 2, DP_NST2>(wrow, X, KX, B, KX, red, res);
         for (int o = tid; o < 8 * MT * 8; o += DP_THREADS) {
           const int m = o >> 3, j = o & 7, u = item * 8 + j;
           if (m >= B) continue;
@@ -478,14 +520,14 @@ __device__ __forceinline__ void fwd_p3(const dasa_decoder_fwd_t& a, const int t,
 
 // ---- attention phases: NOT inlined, so that none of their state is live across the register-hungry GEMM phases
 __device__ __noinline__ void fwd_issue_feat(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
   if (!o.on) return;
   const AttnSmem sf = dp_attn_smem(raw, pl, true);
   dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)t * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row, a.V,
                 o.sl.c0, o.sl.cn, nullptr);
 }
 __device__ __noinline__ void fwd_issue_ctx(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
   if (!o.on) return;
   const AttnSmem sc = dp_attn_smem(raw, pl, false);
   dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)t * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, a.L,
@@ -494,7 +536,7 @@ __device__ __noinline__ void fwd_issue_ctx(const dasa_decoder_fwd_t& a, const Sm
 
 // P2a: partial view logits of this CTA's channel slice
 __device__ __noinline__ void fwd_p2a(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
   if (!o.on) return;
   const AttnSmem sf = dp_attn_smem(raw, pl, true);
   const int tid = threadIdx.x;
@@ -508,7 +550,7 @@ __device__ __noinline__ void fwd_p2a(const dasa_decoder_fwd_t& a, const SmemPlan
 
 // P2b: softmax over the views, circular heading shift, weighted sum -> xh[:, E + slice]; then prefetch the next action's tile
 __device__ __noinline__ void fwd_p2b(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
   if (!o.on) return;
   const AttnSmem sf = dp_attn_smem(raw, pl, true);
   const int tid = threadIdx.x, V = a.V, F = a.F, E = a.E, NK = a.NK, KX = a.E + a.F + a.H;
@@ -545,15 +587,12 @@ __device__ __noinline__ void fwd_p2b(const dasa_decoder_fwd_t& a, const SmemPlan
   }
   __syncthreads();
   dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.wrow, a.xh + (tb + o.b) * KX + E + o.sl.c0);
-  __syncthreads();                                     // every thread is done with the tile: prefetch the next action's
-  if (t + 1 < a.T)
-    dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)(t + 1) * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row,
-                  V, o.sl.c0, o.sl.cn, nullptr);
+  // the next action's tile is prefetched at the top of the NEXT phase (after the barrier): every thread is done with this one
 }
 
 // P5a: partial token logits
 __device__ __noinline__ void fwd_p5a(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
   if (!o.on) return;
   const AttnSmem sc = dp_attn_smem(raw, pl, false);
   const int tid = threadIdx.x;
@@ -567,7 +606,7 @@ __device__ __noinline__ void fwd_p5a(const dasa_decoder_fwd_t& a, const SmemPlan
 
 // P5b: masked softmax over the tokens, weighted context -> cat[:, slice]; then prefetch the next action's tile
 __device__ __noinline__ void fwd_p5b(const dasa_decoder_fwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
   if (!o.on) return;
   const AttnSmem sc = dp_attn_smem(raw, pl, false);
   const int tid = threadIdx.x, L = a.L, DC = a.D + a.H;
@@ -577,10 +616,6 @@ __device__ __noinline__ void fwd_p5b(const dasa_decoder_fwd_t& a, const SmemPlan
   if (o.s == 0)
     for (int r = tid; r < L; r += DP_THREADS) a.alpha[(tb + o.b) * L + r] = sc.prow[r];
   dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.prow, a.cat + (tb + o.b) * DC + o.sl.c0);
-  __syncthreads();
-  if (t + 1 < a.T)
-    dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)(t + 1) * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, L,
-                  o.sl.c0, o.sl.cn, o.mask_b);
 }
 
 __device__ __noinline__ void fwd_prologue(const dasa_decoder_fwd_t& a) {
@@ -613,6 +648,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_fwd_kernel(cons
     const AttnSmem sf = dp_attn_smem(smem_raw, pl, true), sc = dp_attn_smem(smem_raw, pl, false);
     mbar_init(sf.bar, 1); mbar_init(sc.bar, 1); mbar_fence_init();
   }
+  dp_stage_mask(smem_raw, pl, a.B, S, a.L, a.ctx_mask, a.ctx_mask_ld);
   __syncthreads();
   fwd_issue_feat(a, pl, smem_raw, S, 0);          // the tiles of action 0 stream in under the prologue and P1
   fwd_issue_ctx(a, pl, smem_raw, S, 0);
@@ -622,13 +658,19 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_fwd_kernel(cons
   for (int t = 0; t < a.T; ++t) {
 #pragma unroll 1
     for (int ph = 0; ph < 8; ++ph) {
+      // prefetch the next action's tiles at the top of the phase AFTER their last reader (a bulk copy in flight at a barrier
+      // delayed it): the view tile is free since the barrier that closed P2b, the context tile since the one that closed P5b
+      if (t + 1 < a.T) {
+        if (ph == 3) fwd_issue_feat(a, pl, smem_raw, S, t + 1);
+        if (ph == 7) fwd_issue_ctx(a, pl, smem_raw, S, t + 1);
+      }
       switch (ph) {
         case 1: fwd_p2a(a, pl, smem_raw, S, t); break;
         case 2: fwd_p2b(a, pl, smem_raw, S, t); break;
         case 3: fwd_p3<MT>(a, t, red, res); break;          // gates + LSTM cell (CTA = 8 units x 4 gates)
         case 5: fwd_p5a(a, pl, smem_raw, S, t); break;
         case 6: fwd_p5b(a, pl, smem_raw, S, t); break;
-        default: fwd_gemm16<MT>(a, t, ph, red, res); break;   // P1 (ph 0), P4 (ph 4), P6 (ph 7)
+        default: fwd_gemm16<MT>(a, t, ph, red, res); break;   // P1 (ph 0), P4 (ph 4), P6 (ph 7): ONE inlined copy
       }
       grid_sync(gb);
       dp_stamp(1 + 8 * t + ph);
@@ -643,18 +685,18 @@ __device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const in
   const int tid = threadIdx.x;
   const int64_t tb = (int64_t)t * B;
   const float scale = a.drop_scale;
-  const float* W; const float* X;
+  const wt_t* W; const float* X;
   int64_t ldw, ldx;
   int N, K;
-  if (ph == 0)      { W = a.w_att_out_t; ldw = a.ld_w_att_out_t; N = DC; K = H;  X = a.du + tb * H;   ldx = H; }    // B6: dcat = du W_att_out
-  else if (ph == 3) { W = a.w_att_in_t;  ldw = a.ld_w_att_in_t;  N = H;  K = D;  X = a.dt2 + tb * D;  ldx = D; }    // B4: dh1d, LSTM cell backward
-  else              { W = a.w_feat_t;    ldw = a.ld_w_feat_t;    N = H;  K = NK; X = a.dtk + tb * NK; ldx = NK; }   // B1: dh~_{t-1}, du_{t-1}
+  if (ph == 0)      { W = reinterpret_cast<const wt_t*>(a.w_att_out_t); ldw = a.ld_w_att_out_t; N = DC; K = H;  X = a.du + tb * H;   ldx = H; }    // B6: dcat = du W_att_out
+  else if (ph == 3) { W = reinterpret_cast<const wt_t*>(a.w_att_in_t);  ldw = a.ld_w_att_in_t;  N = H;  K = D;  X = a.dt2 + tb * D;  ldx = D; }    // B4: dh1d, LSTM cell backward
+  else              { W = reinterpret_cast<const wt_t*>(a.w_feat_t);    ldw = a.ld_w_feat_t;    N = H;  K = NK; X = a.dtk + tb * NK; ldx = NK; }   // B1: dh~_{t-1}, du_{t-1}
   W = dp_opaque(W);
   const int nitems = (N + 15) / 16;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const float* wrow[2];
+    const wt_t* wrow[2];
     dp_rows16(wrow, W, ldw, item * 16, N);
-    dp_gemm_block<MT, 1>(wrow, X, ldx, B, K, red, res);
+    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res);
     for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
       const int m = o >> 4, n = item * 16 + (o & 15);
       if (m >= B || n >= N) continue;
@@ -708,14 +750,14 @@ __device__ __forceinline__ void bwd_b3(const dasa_decoder_bwd_t& a, const int t,
       const int nitems = (KX + 31) / 32;
       const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const float* wrow[4];
+        const wt_t* wrow[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int n = item * 32 + g + 8 * i;
           n = n < KX ? n : KX - 1;
-          wrow[i] = dp_opaque(a.w_lstm_t) + (int64_t)n * a.ld_w_lstm_t + 4 * tq;
+          wrow[i] = dp_opaque(reinterpret_cast<const wt_t*>(a.w_lstm_t)) + (int64_t)n * a.ld_w_lstm_t + 4 * tq;
         }
-        dp_gemm_block<MT, 2>(wrow, X, 4 * H, B, 4 * H, red, res);
+        dp_gemm_block<MT, 2, DP_NST2>(wrow, X, 4 * H, B, 4 * H, red, res);
         for (int o = tid; o < 32 * 8 * MT; o += DP_THREADS) {
           const int m = o >> 5, n = item * 32 + (o & 31);
           if (m >= B || n >= KX) continue;
@@ -729,14 +771,14 @@ __device__ __forceinline__ void bwd_b3(const dasa_decoder_bwd_t& a, const int t,
 }
 
 __device__ __noinline__ void bwd_issue_feat(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
   if (!o.on) return;
   const AttnSmem sf = dp_attn_smem(raw, pl, true);
   dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)t * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row, a.V,
                 o.sl.c0, o.sl.cn, nullptr);
 }
 __device__ __noinline__ void bwd_issue_ctx(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
   if (!o.on) return;
   const AttnSmem sc = dp_attn_smem(raw, pl, false);
   dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)t * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, a.L,
@@ -745,7 +787,7 @@ __device__ __noinline__ void bwd_issue_ctx(const dasa_decoder_bwd_t& a, const Sm
 
 // B5a: partial dalpha_l = ctx_l . dwc   (par = parity of the tile's mbarrier phase)
 __device__ __noinline__ void bwd_b5a(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t, uint32_t par) {
-  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
   if (!o.on) return;
   const AttnSmem sc = dp_attn_smem(raw, pl, false);
   const int tid = threadIdx.x, D = a.D, DC = a.D + a.H;
@@ -761,7 +803,7 @@ __device__ __noinline__ void bwd_b5a(const dasa_decoder_bwd_t& a, const SmemPlan
 
 // B5b: dz = alpha (dalpha - sum alpha dalpha); dt2 slice; dctx slice; then prefetch the previous action's tile
 __device__ __noinline__ void bwd_b5b(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.D, a.ctx_mask, a.ctx_mask_ld);
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
   if (!o.on) return;
   const AttnSmem sc = dp_attn_smem(raw, pl, false);
   const int tid = threadIdx.x, L = a.L, D = a.D;
@@ -798,15 +840,11 @@ __device__ __noinline__ void bwd_b5b(const dasa_decoder_bwd_t& a, const SmemPlan
       stg_stream4(dst_b + (int64_t)r * D + 4 * col, ov);
     }
   }
-  __syncthreads();
-  if (t > 0)
-    dp_issue_tile(sc.tile, pl.pitchC, sc.bar, a.ctx + (int64_t)(t - 1) * a.ctx_ld_t + (int64_t)o.b * a.ctx_ld_b, a.ctx_ld_row, L,
-                  o.sl.c0, o.sl.cn, o.mask_b);
 }
 
 // B2a: partial dq_v = feat_v . dattn
 __device__ __noinline__ void bwd_b2a(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t, uint32_t par) {
-  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
   if (!o.on) return;
   const AttnSmem sf = dp_attn_smem(raw, pl, true);
   const int tid = threadIdx.x, F = a.F;
@@ -822,7 +860,7 @@ __device__ __noinline__ void bwd_b2a(const dasa_decoder_bwd_t& a, const SmemPlan
 
 // B2b: undo the shift, dz, dt slice, dfeat slice, dkappa logits; then prefetch the previous action's tile
 __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
-  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr, 0);
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
   if (!o.on) return;
   const AttnSmem sf = dp_attn_smem(raw, pl, true);
   const int tid = threadIdx.x, V = a.V, F = a.F, NK = a.NK;
@@ -891,10 +929,6 @@ __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan
       stg_stream4(dst_b + (int64_t)r * a.dfeat_ld_row + 4 * col, ov);
     }
   }
-  __syncthreads();
-  if (t > 0)
-    dp_issue_tile(sf.tile, pl.pitchF, sf.bar, a.feat + (int64_t)(t - 1) * a.feat_ld_t + (int64_t)o.b * a.feat_ld_b, a.feat_ld_row, V,
-                  o.sl.c0, o.sl.cn, nullptr);
 }
 
 __device__ __noinline__ void bwd_prologue(const dasa_decoder_bwd_t& a) {
@@ -920,6 +954,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
     const AttnSmem sf = dp_attn_smem(smem_raw, pl, true), sc = dp_attn_smem(smem_raw, pl, false);
     mbar_init(sf.bar, 1); mbar_init(sc.bar, 1); mbar_fence_init();
   }
+  dp_stage_mask(smem_raw, pl, a.B, S, a.L, a.ctx_mask, a.ctx_mask_ld);
   __syncthreads();
   bwd_issue_feat(a, pl, smem_raw, S, a.T - 1);    // the tiles of the LAST action stream in under the prologue and B6
   bwd_issue_ctx(a, pl, smem_raw, S, a.T - 1);
@@ -930,13 +965,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
     const uint32_t par = (uint32_t)(it & 1);
 #pragma unroll 1
     for (int ph = 0; ph < 8; ++ph) {
+      if (t > 0) {                                          // previous action's tiles, after their last reader's barrier
+        if (ph == 3) bwd_issue_ctx(a, pl, smem_raw, S, t - 1);
+        if (ph == 7) bwd_issue_feat(a, pl, smem_raw, S, t - 1);
+      }
       switch (ph) {
         case 1: bwd_b5a(a, pl, smem_raw, S, t, par); break;
         case 2: bwd_b5b(a, pl, smem_raw, S, t); break;
         case 4: bwd_b3<MT>(a, t, red, res); break;          // d[x ; h] = dgates [W_ih | W_hh]
         case 5: bwd_b2a(a, pl, smem_raw, S, t, par); break;
         case 6: bwd_b2b(a, pl, smem_raw, S, t); break;
-        default: bwd_gemm16<MT>(a, t, ph, red, res); break;   // B6 (ph 0), B4 (ph 3), B1 (ph 7)
+        default: bwd_gemm16<MT>(a, t, ph, red, res); break;   // B6 (ph 0), B4 (ph 3), B1 (ph 7): ONE inlined copy
       }
       grid_sync(gb);
       dp_stamp(1 + 8 * it + ph);
@@ -944,6 +983,51 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
   }
   const int gtid = blockIdx.x * DP_THREADS + threadIdx.x, gthreads = gridDim.x * DP_THREADS;
   for (int i = gtid; i < a.B * a.H; i += gthreads) a.dc0[i] = ld_cg(a.dc_carry + i);
+}
+
+// ---- barrier micro-benchmark (profiling aid): `iters` device-wide barriers with no work in between; out[0] = SM clocks of CTA 0
+template <int VARIANT>
+__device__ __forceinline__ void grid_sync_variant(GridBar& gb) {
+  gb.target += gb.nblk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (VARIANT == 0) {                     // fences on both sides of a release-add / acquire-poll
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+      unsigned int v, it = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+        if (++it > (1u << 22)) __trap();
+      } while ((int)(v - gb.target) < 0);
+      __threadfence();
+    } else if (VARIANT == 1) {                     // release-add / acquire-poll only (no extra fences)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+      unsigned int v, it = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+        if (++it > (1u << 22)) __trap();
+      } while ((int)(v - gb.target) < 0);
+    } else {                                // VARIANT 2: fence + relaxed atomic + volatile poll + fence (cooperative-groups style)
+      __threadfence();
+      atomicAdd(gb.ctr, 1u);
+      unsigned int it = 0;
+      while ((int)(*((volatile unsigned int*)gb.ctr) - gb.target) < 0) { if (++it > (1u << 22)) __trap(); }
+      __threadfence();
+    }
+  }
+  __syncthreads();
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(DP_THREADS, 1) barrier_bench_kernel(unsigned int* ctr, int iters, long long* out, float* junk) {
+  GridBar gb{ctr, 0u, gridDim.x};
+  grid_sync_variant<VARIANT>(gb);
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    junk[blockIdx.x * DP_THREADS + threadIdx.x] = (float)i;          // one global write per thread per interval, like a phase
+    grid_sync_variant<VARIANT>(gb);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = clock64() - t0;
 }
 
 // ------------------------------------------------------------------------------------------------------------- host side
@@ -1007,6 +1091,26 @@ int dp_launch(Kern kern, const Args& a, const LaunchPlan& lp, unsigned int* barr
 
 extern "C" int dasa_decoder_rollout_supported(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k) {
   return dp_launch_plan(B, H, E, F, V, L, D, NK, shift_k).ok ? 1 : 0;
+}
+
+extern "C" int dasa_debug_barrier_bench(int variant, int iters, unsigned int* ctr, long long* out, float* junk, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return DASA_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)dp_sm_count());
+  cfg.blockDim = dim3(DP_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (variant == 0) e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<0>, ctr, iters, out, junk);
+  else if (variant == 1) e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<1>, ctr, iters, out, junk);
+  else e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<2>, ctr, iters, out, junk);
+  if (e != cudaSuccess) { dasa_set_error("barrier_bench_kernel", e); return DASA_ERR_CUDA; }
+  return DASA_OK;
 }
 
 extern "C" int dasa_debug_decoder_phase_clocks(long long* out, int n) {

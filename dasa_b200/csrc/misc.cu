@@ -1,5 +1,6 @@
 // Small elementwise / per-row kernels: dropout plumbing, activation backward, masked cross-entropy + action selection
 // (agent_dg.py:832-886), fused RMSprop + gradient clipping (agent_dg.py:1389-1405).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -288,6 +289,25 @@ extern "C" int dasa_dropout_mask_dev(uint8_t* mask, int64_t n, float p, const ui
 extern "C" int dasa_bump_counter(uint64_t* counter, uint64_t inc, void* stream) {
   bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter), inc);
   return dasa_check_launch("bump_counter_kernel");
+}
+
+// fp32 -> fp16 (round to nearest even), 8 elements per thread
+__global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+    reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<uint4*>(h);
+  }
+  for (int64_t i = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
+}
+
+extern "C" int dasa_f32_to_f16(const float* in, dasa_half_t* out, int64_t n, void* stream) {
+  if (n <= 0) return DASA_OK;
+  if (n >= 8 && (!dasa_aligned16(in) || !dasa_aligned16(out))) return DASA_ERR_BAD_ALIGN;
+  f32_to_f16_kernel<<<ew_grid(n / 8 + 1), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__half*>(out), n);
+  return dasa_check_launch("f32_to_f16_kernel");
 }
 
 extern "C" int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* target, int ignore_index, int B, int Nc, float grad_scale,

@@ -137,6 +137,28 @@ def transposed_weight(w):
     return wt
 
 
+_half_cache = {}
+
+
+def half_weight(w):
+    """fp16 copy of a (derived) weight tensor, cached while `w` itself is alive and unchanged. `w` is normally the output of
+    stacked_weights / transposed_weight, which are rebuilt when a parameter changes, so the identity of `w` is the cache tag."""
+    key = id(w)
+    tag = (w._version, weights_epoch, w.data_ptr())
+    hit = _half_cache.get(key)
+    if hit is not None and hit[0] == tag and hit[2]() is w:
+        return hit[1]
+    if len(_half_cache) > 64:
+        for k in [k for k, v in _half_cache.items() if v[2]() is None]:
+            del _half_cache[k]
+    src = w.detach()
+    src = src if src.is_contiguous() else src.contiguous()
+    out = torch.empty(src.shape, device=src.device, dtype=torch.float16)
+    call("dasa_f32_to_f16", _p(src), _p(out), src.numel(), _stream())
+    _half_cache[key] = (tag, out, weakref.ref(w))
+    return out
+
+
 _stack_cache = {}
 
 
@@ -650,12 +672,13 @@ def decoder_rollout_fwd(emb, feat, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale, 
     a.ctx_mask, a.ctx_mask_ld = _p(ctx_mask), (ctx_mask.stride(0) if ctx_mask is not None else 0)
     a.h0, a.c0 = _p(h0), _p(c0)
     a.m_hprev, a.m_h1, a.drop_scale = _p(m_hprev), _p(m_h1), float(scale)
-    a.w_feat, a.b_feat, a.w_lstm, a.b_ih, a.b_hh = _p(w_feat), _p(b_feat), _p(w_lstm), _p(b_ih), _p(b_hh)
-    a.w_att_in, a.w_att_out = _p(w_att_in), _p(w_att_out)
+    hw = [half_weight(w) for w in (w_feat, w_lstm, w_att_in, w_att_out)]      # fp16 weight stream (cached per parameter epoch)
+    a.w_feat, a.b_feat, a.w_lstm, a.b_ih, a.b_hh = _p(hw[0]), _p(b_feat), _p(hw[1]), _p(b_ih), _p(b_hh)
+    a.w_att_in, a.w_att_out = _p(hw[2]), _p(hw[3])
     for k, v in o.items():
         setattr(a, k, _p(v))
     a.zpart, a.barrier = _p(zpart), _p(barrier)
-    keep = (emb, feat, ctx, ctx_mask, h0, c0, zpart, barrier)      # referenced until the launch is enqueued
+    keep = (emb, feat, ctx, ctx_mask, h0, c0, zpart, barrier, hw)      # referenced until the launch is enqueued
     call("dasa_decoder_rollout_fwd", ctypes.byref(a), _stream())
     del keep
     return o
@@ -691,10 +714,11 @@ def decoder_rollout_bwd(saved, feat, ctx, ctx_mask, m_hprev, m_h1, scale, w_feat
     a.ctx_ld_row, a.ctx_ld_b, a.ctx_ld_t = _ld3(ctx)
     a.ctx_mask, a.ctx_mask_ld = _p(ctx_mask), (ctx_mask.stride(0) if ctx_mask is not None else 0)
     a.m_hprev, a.m_h1, a.drop_scale = _p(m_hprev), _p(m_h1), float(scale)
-    a.w_feat_t, a.ld_w_feat_t = _p(w_feat_t), w_feat_t.stride(0)
-    a.w_lstm_t, a.ld_w_lstm_t = _p(w_lstm_t), w_lstm_t.stride(0)
-    a.w_att_in_t, a.ld_w_att_in_t = _p(w_att_in_t), w_att_in_t.stride(0)
-    a.w_att_out_t, a.ld_w_att_out_t = _p(w_att_out_t), w_att_out_t.stride(0)
+    hw = [half_weight(w) for w in (w_feat_t, w_lstm_t, w_att_in_t, w_att_out_t)]
+    a.w_feat_t, a.ld_w_feat_t = _p(hw[0]), hw[0].stride(0)
+    a.w_lstm_t, a.ld_w_lstm_t = _p(hw[1]), hw[1].stride(0)
+    a.w_att_in_t, a.ld_w_att_in_t = _p(hw[2]), hw[2].stride(0)
+    a.w_att_out_t, a.ld_w_att_out_t = _p(hw[3]), hw[3].stride(0)
     for k in ("tk", "p", "q", "kappa", "acts", "c", "cat", "t2", "alpha", "htilde"):
         setattr(a, k, _p(saved[k]))
     a.d_htilde, a.d_h1, a.d_c_last = _p(d_htilde), _p(d_h1), _p(d_c_last)
@@ -705,7 +729,7 @@ def decoder_rollout_bwd(saved, feat, ctx, ctx_mask, m_hprev, m_h1, scale, w_feat
     for k, v in scratch.items():
         setattr(a, k, _p(v))
     a.zpart, a.barrier = _p(zpart), _p(barrier)
-    keep = (d_htilde, d_h1, d_c_last, ctx_mask, scratch, zpart, barrier)
+    keep = (d_htilde, d_h1, d_c_last, ctx_mask, scratch, zpart, barrier, hw)
     call("dasa_decoder_rollout_bwd", ctypes.byref(a), _stream())
     del keep
     return g

@@ -85,9 +85,10 @@ class RolloutTrainer:
         self._works = []
 
     # ---------------------------------------------------------------------------------------------------- one iteration
-    def accumulate(self, ep):
+    def accumulate(self, ep, actions_in=None):
         """zero_grad + every accumulate_gradient pass, backward included (weight-gradient GEMMs still queued when deferred).
-        Returns the summed loss (device tensor [1], this rank's share)."""
+        Returns the summed loss (device tensor [1], this rank's share). actions_in: injected actions of the sampled rollout
+        ([T] list of [B] tensors; tests) instead of the device RNG's."""
         pol, T, world = self.pol, self.T, self.world
         pol.zero_grad()
         self.src.advance()
@@ -102,11 +103,11 @@ class RolloutTrainer:
                     losses.append(loss.detach())
                     if world > 1 and self.normalize == "total":
                         rl, out = pol.sample_rollout(ep, T, tag_steps=False, gamma=self.gamma, ent_coef=self.ent_coef,
-                                                     normalize="none")
+                                                     normalize="none", actions_in=actions_in)
                         rl = rl / self._global_total(out["total"]).clamp_(min=1.0)
                     else:
                         rl, out = pol.sample_rollout(ep, T, tag_steps=False, gamma=self.gamma, ent_coef=self.ent_coef,
-                                                     normalize=self.normalize)
+                                                     normalize=self.normalize, actions_in=actions_in)
                         if world > 1:
                             rl = rl / world if self.normalize == "batch" else rl
                     rl.backward()
@@ -124,6 +125,11 @@ class RolloutTrainer:
         self._flush_and_reduce()
         self._wait_reductions()
         self.pol.optim_step(self.lr, use_lr_scheduler=self.use_lr_scheduler)
+
+    def reduce_gradients(self):
+        """Deferred weight-gradient GEMMs + the all-reduces, completed (what finish() does before the optimizer)."""
+        self._flush_and_reduce()
+        self._wait_reductions()
 
     def step_eager(self, ep):
         loss = self.accumulate(ep)

@@ -241,6 +241,9 @@ int dasa_bilstm_seq_gemm_bwd(const dasa_bilstm_bwd_t* args, void* workspace, siz
  * Dropout: m_hprev / m_h1 are [T, B, H] keep masks (NULL = eval), scale = 1/(1-p); emb and feat arrive already dropped.
  * Requirements: H % 16 == 0, (E+F+H) % 32 == 0, NK % 32 == 0, D % 4 == 0, F % 4 == 0, V, L <= 128, B <= 32, shift_k <= 15;
  * dasa_decoder_rollout_supported() says whether the shared-memory plan fits (else use the per-op entry points).      */
+typedef unsigned short dasa_half_t;                   /* IEEE binary16 bits                                                */
+/* out[i] = fp16(in[i]) (round to nearest even), n elements; in 16-byte aligned when n >= 8. Used for the decoder kernel's weights. */
+int dasa_f32_to_f16(const float* in, dasa_half_t* out, int64_t n, void* stream);
 typedef struct {
   int T, B, H, E, F, V, L, D, headings, shift_k, NK;
   const float* emb;                                   /* [T, B, E] drop(tanh(embedding(action)))  (model.py:504-505)        */
@@ -249,10 +252,12 @@ typedef struct {
   const uint8_t* ctx_mask; int64_t ctx_mask_ld;       /* [B, L] 1 = padding (NULL = none)                                  */
   const float* h0; const float* c0;                   /* [B, H] recurrent state before action 0 (h~_{-1}, c_{-1})          */
   const uint8_t* m_hprev; const uint8_t* m_h1; float drop_scale;
-  const float* w_feat; const float* b_feat;           /* [NK, H] = [feat_att.linear_in ; linear_shift ; 0], bias [NK]      */
-  const float* w_lstm; const float* b_ih; const float* b_hh;      /* [4H, E+F+H] = [W_ih | W_hh]                          */
-  const float* w_att_in;                              /* [D, H]   attention_layer.linear_in                                */
-  const float* w_att_out;                             /* [H, D+H] attention_layer.linear_out                               */
+  /* Weights are FP16 copies of the fp32 parameters (dasa_f32_to_f16, refreshed after every optimizer step): fp16's 10-bit mantissa
+   * is TF32's, so the products equal the TF32 tensor-core products of the fp32 weights, at half the bytes per action.         */
+  const dasa_half_t* w_feat; const float* b_feat;     /* [NK, H] = [feat_att.linear_in ; linear_shift ; 0], bias [NK] fp32 */
+  const dasa_half_t* w_lstm; const float* b_ih; const float* b_hh;   /* [4H, E+F+H] = [W_ih | W_hh]                       */
+  const dasa_half_t* w_att_in;                        /* [D, H]   attention_layer.linear_in                                */
+  const dasa_half_t* w_att_out;                       /* [H, D+H] attention_layer.linear_out                               */
   float* hprev_drop;                                  /* [T, B, H]   drop(h~_{t-1})                                        */
   float* tk;                                          /* [T, B, NK]  attention target | shift logits                      */
   float* p; float* q; float* kappa;                   /* [T, B, V] pre-shift softmax, [T, B, V] shifted, [T, B, shift_k]   */
@@ -279,10 +284,10 @@ typedef struct {
   const float* ctx; int64_t ctx_ld_row, ctx_ld_b, ctx_ld_t;
   const uint8_t* ctx_mask; int64_t ctx_mask_ld;
   const uint8_t* m_hprev; const uint8_t* m_h1; float drop_scale;
-  const float* w_feat_t; int64_t ld_w_feat_t;         /* [H, NK]                                                           */
-  const float* w_lstm_t; int64_t ld_w_lstm_t;         /* [E+F+H, 4H]                                                       */
-  const float* w_att_in_t; int64_t ld_w_att_in_t;     /* [H, D]                                                            */
-  const float* w_att_out_t; int64_t ld_w_att_out_t;   /* [D+H, H]                                                          */
+  const dasa_half_t* w_feat_t; int64_t ld_w_feat_t;         /* [H, NK]     fp16, leading dimensions in elements                  */
+  const dasa_half_t* w_lstm_t; int64_t ld_w_lstm_t;         /* [E+F+H, 4H]                                                       */
+  const dasa_half_t* w_att_in_t; int64_t ld_w_att_in_t;     /* [H, D]                                                            */
+  const dasa_half_t* w_att_out_t; int64_t ld_w_att_out_t;   /* [D+H, H]                                                          */
   const float* tk; const float* p; const float* q; const float* kappa; const float* acts; const float* c;
   const float* cat; const float* t2; const float* alpha; const float* htilde;
   const float* d_htilde; const float* d_h1; const float* d_c_last;   /* d_c_last (optional) [B, H]: gradient at c_{T-1}      */
@@ -299,6 +304,10 @@ size_t dasa_decoder_rollout_scratch_floats(int B);
 /* Profiling aid: SM-clock timestamps of CTA 0 at the phase barriers of the first 4 actions of the LAST rollout launch (forward or
  * backward): out[0] = after the prologue, out[1 + 8*i + ph] = after phase ph of the i-th processed action. Returns the count. */
 int dasa_debug_decoder_phase_clocks(long long* out, int n);
+/* Profiling aid: `iters` device-wide barriers of the persistent kernels (one CTA per SM, cooperative launch) with one global write
+ * per thread in between; out[0] (device) = SM clocks CTA 0 spent. variant 0 = the barrier the rollout kernels use, 1 = release /
+ * acquire only, 2 = fence + relaxed atomic + volatile poll. junk: >= 256 * SMs floats, ctr: 4 bytes.                          */
+int dasa_debug_barrier_bench(int variant, int iters, unsigned int* ctr, long long* out, float* junk, void* stream);
 int dasa_decoder_rollout_fwd(const dasa_decoder_fwd_t* args, void* stream);
 int dasa_decoder_rollout_bwd(const dasa_decoder_bwd_t* args, void* stream);
 
