@@ -57,5 +57,22 @@ class PolicyConfig:
                        la_layers=2, vl_layers=2, critic_dim=128, max_input=24)
 
 
+def reference_args():
+    """The reference's global flag object (`from param import args`, param.py:18-215) when the host program has ALREADY imported
+    `param` (i.e. we are running inside r2r_src), else None. Never imported from here: param.py parses sys.argv at import."""
+    import sys
+    mod = sys.modules.get("param")
+    return getattr(mod, "args", None) if mod is not None else None
+
+
+def flag(name, explicit, default):
+    """Value of a flag the reference's modules read from the global `args` at construction time: the explicit
+    constructor kwarg when given, else param.args.<name> when the reference's param module is loaded, else the README default."""
+    if explicit is not None:
+        return explicit
+    a = reference_args()
+    return getattr(a, name, default) if a is not None else default
+
+
 FULL = PolicyConfig()
 SMALL = FULL.small()

@@ -192,9 +192,10 @@ __global__ void __launch_bounds__(256) dropout_mask_dev_kernel(uint8_t* __restri
 }
 
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
-                                                      int64_t n, float lr, float alpha, float eps, float wd,
-                                                      const float* __restrict__ clip) {
+                                                      int64_t n, float lr_host, float alpha, float eps, float wd,
+                                                      const float* __restrict__ clip, const float* __restrict__ lr_scale) {
   const float c = clip ? clip[0] : 1.f;
+  const float lr = lr_scale ? lr_host * lr_scale[0] : lr_host;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * c;
     const float pi = p[i];
@@ -320,10 +321,31 @@ extern "C" int dasa_masked_ce(const float* logit, int64_t ld, const int64_t* tar
 }
 
 extern "C" int dasa_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha, float eps,
-                                 float weight_decay, const float* clip_coef, void* stream) {
+                                 float weight_decay, const float* clip_coef, const float* lr_scale, void* stream) {
   if (n <= 0) return DASA_OK;
-  rmsprop_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, square_avg, n, lr, alpha, eps, weight_decay, clip_coef);
+  rmsprop_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, square_avg, n, lr, alpha, eps, weight_decay, clip_coef,
+                                                               lr_scale);
   return dasa_check_launch("rmsprop_kernel");
+}
+
+// LambdaLR multiplier of agent_dg.py:219-227 from a DEVICE iteration counter (a captured CUDA graph replays the schedule):
+// mult[0] = lr_lambda(*iter); then *iter += advance
+__global__ void lr_lambda_kernel(int* iter, int warm, int decay_start, int decay_intervals, float lr_decay, float* mult, int advance) {
+  const int it = *iter;
+  double a = 1.0;
+  if (warm > 0 && it < warm) a = (1.0 + (double)it) / (double)warm;
+  else if (it >= decay_start) {
+    const int n = (it - decay_start) / (decay_intervals > 0 ? decay_intervals : 1);
+    for (int i = 0; i < n && a > 1e-30; ++i) a *= (double)lr_decay;
+  }
+  mult[0] = (float)a;
+  *iter = it + advance;
+}
+
+extern "C" int dasa_lr_lambda(int* iter, int warm_steps, int decay_start, int decay_intervals, float lr_decay, float* mult, int advance,
+                              void* stream) {
+  lr_lambda_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(iter, warm_steps, decay_start, decay_intervals, lr_decay, mult, advance);
+  return dasa_check_launch("lr_lambda_kernel");
 }
 
 extern "C" int dasa_sumsq(const float* x, int64_t n, float* out, void* stream) {

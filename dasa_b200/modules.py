@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import functions as Fn
 from . import ops
-from .config import FULL, PolicyConfig
+from .config import FULL, PolicyConfig, flag
 
 
 # ------------------------------------------------------------------------------------------------- dropout source
@@ -118,8 +118,10 @@ def _drop(x, tag, p, training):
 class DGAdaChannel(nn.Module):
     """agent_dg.py:1513-1547 with ab_type in {a}, a_type='sigmoid' (the README configuration)."""
 
-    def __init__(self, channel, eps=1e-6, ab_type="a", a_type="sigmoid"):
+    def __init__(self, channel, eps=1e-6, ab_type=None, a_type=None):
+        """DGAdaChannel(channel) reads args.ab_type / args.a_type (agent_dg.py:1518-1546)."""
         super().__init__()
+        ab_type, a_type = flag("ab_type", ab_type, "a"), flag("a_type", a_type, "sigmoid")
         if ab_type != "a" or a_type != "sigmoid":
             raise NotImplementedError("only --ab_type a --a_type sigmoid is on the hot path (README.md:86)")
         self.a_fc = nn.Linear(channel, channel)
@@ -227,8 +229,15 @@ class BAttnDecoderLSTM(nn.Module):
     """model.py:422-574."""
 
     def __init__(self, embedding_size, hidden_size, dropout_ratio, feature_size=2048 + 4, pred_back=False,
-                 angle_feat_size=128, featdropout=0.4, use_shift=True, shift_kernel_size=5):
+                 angle_feat_size=None, featdropout=None, use_shift=None, shift_kernel_size=None):
+        """The first five arguments are the reference's (model.py:425). The rest are the flags it reads from the global `args`
+        (model.py:432-439): given explicitly, or taken from param.args when r2r_src's param module is loaded, or the README
+        values (--angle_feat_size 128 --featdropout 0.4 --use_shift --shift_kernel_size 5)."""
         super().__init__()
+        angle_feat_size = flag("angle_feat_size", angle_feat_size, 128)
+        featdropout = flag("featdropout", featdropout, 0.4)
+        use_shift = flag("use_shift", use_shift, True)
+        shift_kernel_size = flag("shift_kernel_size", shift_kernel_size, 5)
         if pred_back:
             raise NotImplementedError("--pred_back is not part of the agent_dg README configuration")
         self.embedding_size, self.feature_size, self.hidden_size = embedding_size, feature_size, hidden_size
@@ -360,8 +369,10 @@ class BAttnDecoderLSTM(nn.Module):
 class Critic(nn.Module):
     """model.py:970-982."""
 
-    def __init__(self, critic_dim=1024, dropout=0.5):
+    def __init__(self, critic_dim=None, dropout=None):
+        """model.Critic() takes no arguments and reads args.critic_dim / args.dropout (model.py:973-977)."""
         super().__init__()
+        critic_dim, dropout = flag("critic_dim", critic_dim, 1024), flag("dropout", dropout, 0.5)
         self.dim, self.p = critic_dim, dropout
         self.state2value = nn.Sequential(nn.Linear(critic_dim, critic_dim), nn.ReLU(), nn.Dropout(dropout),
                                          nn.Linear(critic_dim, 1))

@@ -607,9 +607,16 @@ def a2c_loss(logp, ent, value, last_value, reward, mask, ended, gamma, ent_coef,
     return loss, total, dlogp, dent, dvalue
 
 
-def rmsprop_step(param, grad, square_avg, lr, alpha=0.99, eps=1e-8, weight_decay=0.0, clip_coef=None):
+def rmsprop_step(param, grad, square_avg, lr, alpha=0.99, eps=1e-8, weight_decay=0.0, clip_coef=None, lr_scale=None):
     call("dasa_rmsprop_step", _p(param), _p(grad), _p(square_avg), param.numel(), float(lr), float(alpha), float(eps),
-         float(weight_decay), _p(clip_coef), _stream())
+         float(weight_decay), _p(clip_coef), _p(lr_scale), _stream())
+
+
+def lr_lambda(iter_dev, mult_dev, warm_steps, decay_start, decay_intervals, lr_decay, advance=1):
+    """mult_dev[0] = lr_lambda(iter_dev[0]); iter_dev[0] += advance (agent_dg.py:219-227, on the device)."""
+    assert iter_dev.dtype == torch.int32 and mult_dev.dtype == torch.float32
+    call("dasa_lr_lambda", _p(iter_dev), int(warm_steps), int(decay_start), int(decay_intervals), float(lr_decay), _p(mult_dev),
+         int(advance), _stream())
 
 
 def sumsq(x, out):

@@ -362,7 +362,7 @@ class NavPolicy:
                 sq = self._square_avg(name, p, i) if self.iteration > 0 else None
                 if sq is not None and p.requires_grad:
                     state[i] = {"step": torch.tensor(float(self.iteration)), "square_avg": sq.detach().clone()}
-            group = {"lr": self.group_lr(name, lr, bool(self.lr_schedule)), "momentum": 0, "alpha": 0.99, "eps": 1e-08,
+            group = {"lr": self.group_lr(name, lr), "momentum": 0, "alpha": 0.99, "eps": 1e-08,
                      "centered": False, "weight_decay": 0, "capturable": False, "foreach": None, "maximize": False,
                      "differentiable": False, "params": list(range(len(params)))}
             states[name] = {"epoch": epoch + 1,
@@ -395,6 +395,8 @@ class NavPolicy:
                         with torch.no_grad():
                             sq.copy_(ent["square_avg"])
                         self.iteration = max(self.iteration, int(float(ent["step"])))
+                        if self._opt is not None:
+                            self._opt.pop("iter_dev", None)       # the device-side schedule counter restarts from self.iteration
         Fn.invalidate_weight_caches()
         return states["encoder"]["epoch"] - 1
 
@@ -423,23 +425,42 @@ class NavPolicy:
             return 1.0
         return lr_decay ** ((iter_count - decay_start) // decay_intervals)
 
-    def group_lr(self, name, lr, use_lr_scheduler):
+    def group_lr(self, name, lr, use_lr_scheduler=None):
         """LambdaLR on the decoder, critic and adaIn optimizers; the encoder optimizer has no scheduler (agent_dg.py:230-241).
-        Optimizer step number i (0-based) runs with lr * lr_lambda(i), as torch's LambdaLR does."""
-        if not use_lr_scheduler or name == "encoder":
+        Optimizer step number i (0-based) runs with lr * lr_lambda(i), as torch's LambdaLR does. Without --use_lr_scheduler the
+        reference STILL constructs the adaIn LambdaLR (agent_dg.py:238) and never steps it, which pins the adaIn rate at
+        lr * lr_lambda(0) = lr / warm_steps: mirrored here."""
+        use = self.use_lr_scheduler if use_lr_scheduler is None else use_lr_scheduler
+        if name == "encoder":
             return lr
+        if not use:
+            return lr * self.lr_lambda(0, **self.lr_schedule) if name == "adaIn" else lr
         return lr * self.lr_lambda(self.iteration, **self.lr_schedule)
 
     iteration = 0
-    lr_schedule = {}
+    lr_schedule = {}            # overrides of lr_lambda's README defaults (--warm_steps 1000 --decay_start 4000 ...)
+    use_lr_scheduler = True     # README.md:82-96 trains with --use_lr_scheduler
 
-    def optim_step(self, lr=1e-4, use_lr_scheduler=False):
+    def _schedule_args(self):
+        d = dict(warm_steps=1000, decay_start=4000, decay_intervals=2000, lr_decay=0.2)
+        d.update(self.lr_schedule)
+        return d
+
+    def optim_step(self, lr=1e-4, use_lr_scheduler=None):
         """clip_grad_norm_(encoder, 40), clip_grad_norm_(decoder, 40), RMSprop on all four groups, then the three LambdaLR
         schedulers (agent_dg.py:1389-1405). Parameters that never received a gradient are skipped, like torch.optim does for
         grad=None (in the flat layout they carry an all-zero gradient, for which the RMSprop update is exactly zero).
-        The learning rate is a host scalar: a CUDA graph that contains this call replays with the rate it was captured with."""
+        Flat layout: the base rate is a host scalar, the LambdaLR multiplier is computed ON THE DEVICE from a device-resident
+        iteration counter (dasa_lr_lambda), so a CUDA graph that contains this call keeps following the schedule when replayed."""
+        use = self.use_lr_scheduler if use_lr_scheduler is None else use_lr_scheduler
         if getattr(self, "_flat", None) is not None:
             o = self._opt
+            if use:
+                if "iter_dev" not in o:
+                    o["iter_dev"] = torch.tensor([self.iteration], dtype=torch.int32, device=self.device)
+                    o["mult_dev"] = torch.ones(1, dtype=torch.float32, device=self.device)
+                sa = self._schedule_args()
+                ops.lr_lambda(o["iter_dev"], o["mult_dev"], sa["warm_steps"], sa["decay_start"], sa["decay_intervals"], sa["lr_decay"])
             for g in self._flat:
                 coef = None
                 if g["clip"] is not None:
@@ -447,8 +468,9 @@ class NavPolicy:
                     ops.sumsq(g["flat_g"], o["sumsq"])
                     ops.clip_coef(o["sumsq"], g["clip"], o["coef"])
                     coef = o["coef"]
-                ops.rmsprop_step(g["flat_p"], g["flat_g"], g["flat_sq"], self.group_lr(g["name"], lr, use_lr_scheduler), 0.99,
-                                 1e-8, 0.0, coef)
+                scheduled = use and g["name"] != "encoder"
+                ops.rmsprop_step(g["flat_p"], g["flat_g"], g["flat_sq"], lr if scheduled else self.group_lr(g["name"], lr, use), 0.99,
+                                 1e-8, 0.0, coef, o["mult_dev"] if scheduled else None)
             self.iteration += 1
             Fn.invalidate_weight_caches()       # parameters changed behind autograd's back (raw-pointer update)
             return
@@ -464,7 +486,7 @@ class NavPolicy:
                     ops.sumsq(p.grad, o["sumsq"])
                 ops.clip_coef(o["sumsq"], g["clip"], o["coef"])
                 coef = o["coef"]
-            glr = self.group_lr(g["name"], lr, use_lr_scheduler)
+            glr = self.group_lr(g["name"], lr, use)
             for p, sq in live:
                 ops.rmsprop_step(p.data, p.grad, sq, glr, 0.99, 1e-8, 0.0, coef)
         self.iteration += 1

@@ -25,10 +25,12 @@ from . import modules as M
 
 class RolloutTrainer:
     def __init__(self, policy, T, feedback="teacher", lr=1e-4, ml_weight=0.4, world=None, dropout_source=None,
-                 use_lr_scheduler=False, overlap=True, gamma=0.9, ent_coef=0.01, normalize="total", passes=None):
+                 use_lr_scheduler=None, overlap=True, gamma=0.9, ent_coef=0.01, normalize="total", passes=None):
         """feedback 'teacher': one teacher-forced rollout per step (BASELINE configs[1]); 'sample': accumulate_gradient('sample')
         = teacher-forced rollout + sampled A2C rollout (agent_dg.py:1352-1356). passes: ml_weight of every accumulate_gradient
-        pass of one optimizer step (finetune: GT env + augmented env, train.py:226-243); default one pass with `ml_weight`."""
+        pass of one optimizer step (finetune: GT env + augmented env, train.py:226-243); default one pass with `ml_weight`.
+        use_lr_scheduler None = the policy's setting (README: on). The LambdaLR multiplier lives on the device, so a captured
+        graph follows the schedule."""
         import torch.distributed as dist
         self.pol, self.T, self.feedback, self.lr = policy, T, feedback, lr
         self.ml_weights = list(passes) if passes is not None else [ml_weight]

@@ -423,7 +423,13 @@ int dasa_a2c_loss(const float* logp, const float* ent, const float* value, const
  * flat parameter group, with the clip coefficient of clip_grad_norm (agent_dg.py:1392-1393) folded in:
  *   g = grad * clip_coef[0] (clip_coef on device, may be NULL); sq = alpha*sq + (1-alpha) g^2; p -= lr * g/(sqrt(sq)+eps) */
 int dasa_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha, float eps,
-                      float weight_decay, const float* clip_coef, void* stream);
+                      float weight_decay, const float* clip_coef, const float* lr_scale, void* stream);
+/* lr_scale (device, may be NULL): the step runs with lr * lr_scale[0] - the LambdaLR multiplier of the decoder / critic / adaIn
+ * optimizers (agent_dg.py:219-241) kept on the device so that a captured CUDA graph follows the schedule.
+ * dasa_lr_lambda: mult[0] = lr_lambda(*iter) (linear warm-up over warm_steps, 1 until decay_start, then lr_decay ^
+ * ((iter - decay_start) / decay_intervals)), then *iter += advance.                                                            */
+int dasa_lr_lambda(int* iter, int warm_steps, int decay_start, int decay_intervals, float lr_decay, float* mult, int advance,
+                   void* stream);
 /* sum of squares of a flat buffer, accumulated into out[0] (for the global grad norm)                              */
 int dasa_sumsq(const float* x, int64_t n, float* out, void* stream);
 /* clip_coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))                                                         */

@@ -191,6 +191,9 @@ def test_graph_replay_reproduces_the_eager_step_bit_for_bit():
                 g["flat_p"].copy_(p)
                 g["flat_sq"].copy_(sq)
             src.seed_dev.copy_(seed0)
+            pol.iteration = 0                                # the LambdaLR multiplier comes from a device-side iteration counter
+            if "iter_dev" in pol._opt:
+                pol._opt["iter_dev"].zero_()
             Fn.invalidate_weight_caches()
 
         tr.step_eager(dep)                                   # warm-up (allocator, kernel attributes)

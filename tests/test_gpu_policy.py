@@ -223,7 +223,7 @@ def test_optimizer_step_matches_torch_rmsprop():
     opt = torch.optim.RMSprop(dec_ref.parameters(), lr=1e-4)
     torch.nn.utils.clip_grad_norm_(dec_ref.parameters(), 40.0)
     opt.step()
-    pol.optim_step(1e-4)
+    pol.optim_step(1e-4, use_lr_scheduler=False)
     for (k, p), q in zip(dec_ref.named_parameters(), pol.decoder.parameters()):
         assert_close(q, p, 1e-5, "param %s after step" % k)
 
@@ -493,3 +493,92 @@ def test_consistent_drop_rollout(schedule):
     for grp, mod, key in (("adaIn", pol.adaIn, "a_fc.weight"), ("decoder", pol.decoder, "lstm.weight_ih"),
                           ("encoder", pol.encoder, "lstm.weight_ih_l0")):
         assert_close(dict(mod.named_parameters())[key].grad, ost[grp][key].grad, 1e-3, "%s.%s grad" % (grp, key))
+
+
+# ------------------------------------------------------------------------ eval path: greedy decode + language cache (f2)
+def test_greedy_rollout_and_language_cache_full_geometry():
+    """The validation path (train.py:396-421 -> agent_dg.py:1327-1338, feedback='argmax'): greedy_rollout against the
+    reference-generated FULL-geometry fixture, and DicEncoder.cache_language (the instruction-only language stack evaluated
+    once per batch instead of once per action; exact in eval mode because the 9 la layers see neither the views nor any
+    dropout): cached logits must equal the uncached ones BIT FOR BIT, with one language-stack evaluation instead of T."""
+    g = torch.load(os.path.join(GOLDEN, "full_eval.pt"))
+    cfg, T = FULL, 2
+    st = synth.policy_state(cfg, g["meta"]["seed"])
+    ep = synth.Episodes(cfg=cfg, **g["meta"]["episodes"])
+    dep = DeviceEpisodes(ep)
+    pol = NavPolicy(cfg, st).eval()
+    calls = {"n": 0}
+    orig = pol.encoder.bert.language_stack
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    pol.encoder.bert.language_stack = counted
+    actions, logits = pol.greedy_rollout(dep, T)
+    assert calls["n"] == T
+    lg = torch.stack(logits).cpu()
+    ref = g["logits"]
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(lg), fin)
+    assert_close(lg[fin], ref[fin], 2e-4, "greedy logits vs reference")
+    top2 = ref.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 1e-3
+    assert torch.equal(torch.stack(actions).cpu()[safe], ref.argmax(-1)[safe])
+    assert torch.equal(torch.stack(actions).cpu(), lg.argmax(-1))          # the kernel's argmax is torch's (first index on ties)
+    # cached language stack
+    pol.encoder.cache_language = True
+    calls["n"] = 0
+    actions_c, logits_c = pol.greedy_rollout(dep, T)
+    assert calls["n"] == 1, "the language stack must be evaluated once per batch with cache_language"
+    assert torch.equal(torch.stack(logits_c), torch.stack(logits)), "cached vs uncached logits differ"
+    assert torch.equal(torch.stack(actions_c), torch.stack(actions))
+    # a different instruction batch must not hit the cache
+    dep2 = DeviceEpisodes(synth.Episodes(cfg=cfg, **dict(g["meta"]["episodes"], seed=g["meta"]["episodes"]["seed"] + 1)))
+    calls["n"] = 0
+    pol.greedy_rollout(dep2, 1)
+    assert calls["n"] == 1
+    # train mode never uses the cache (dropout inside the language layers)
+    pol.train()
+    calls["n"] = 0
+    with torch.no_grad(), M.use_dropout_source(M.DropoutSource(seed=3)):
+        pol.step(dep, 0, None)
+        pol.step(dep, 0, None)
+    assert calls["n"] == 2
+
+
+def test_flat_optimizer_follows_the_schedule_from_a_device_counter():
+    """The flat-buffer optimizer (what RolloutTrainer captures in a CUDA graph) takes the LambdaLR multiplier from a device
+    iteration counter: five steps with warm-up 2 / decay from 3 must equal torch RMSprop + LambdaLR on copies, the encoder at
+    the unscheduled rate; with the scheduler OFF the adaIn group is pinned at lr * lr_lambda(0) like the reference
+    (agent_dg.py:238: its LambdaLR is constructed but never stepped)."""
+    import copy
+    cfg = SMALL
+    for use in (True, False):
+        pol = NavPolicy(cfg, synth.policy_state(cfg, 3)).eval()
+        pol.lr_schedule = dict(warm_steps=2, decay_start=3, decay_intervals=1, lr_decay=0.5)
+        pol.use_lr_scheduler = use
+        dep = DeviceEpisodes(synth.Episodes(3, 2, cfg, seed=9))
+        refs, opts, scheds = {}, {}, {}
+        for name, mod in (("encoder", pol.encoder), ("decoder", pol.decoder), ("adaIn", pol.adaIn)):
+            refs[name] = copy.deepcopy(mod)
+            opts[name] = torch.optim.RMSprop([p for p in refs[name].parameters()], lr=1e-3)
+            if name == "adaIn" or (use and name != "encoder"):
+                scheds[name] = torch.optim.lr_scheduler.LambdaLR(opts[name], lambda it: NavPolicy.lr_lambda(it, **pol.lr_schedule))
+        pol.flatten_parameters()
+        for it in range(5):
+            pol.zero_grad()
+            loss, _, _ = pol.teacher_rollout(dep, 2)
+            loss.backward()
+            for name, mod in (("encoder", pol.encoder), ("decoder", pol.decoder), ("adaIn", pol.adaIn)):
+                for p, q in zip(refs[name].parameters(), mod.parameters()):
+                    p.grad = None if not q.requires_grad else q.grad.clone()
+                if name != "adaIn":
+                    torch.nn.utils.clip_grad_norm_([p for p in refs[name].parameters() if p.grad is not None], 40.0)
+                opts[name].step()
+                if use and name in scheds:
+                    scheds[name].step()
+            pol.optim_step(1e-3)
+            for name, mod in (("encoder", pol.encoder), ("decoder", pol.decoder), ("adaIn", pol.adaIn)):
+                for (k, p), q in zip(refs[name].named_parameters(), mod.parameters()):
+                    if q.requires_grad and float(q.grad.abs().max()) > 0:
+                        assert_close(q, p, 2e-5, "scheduler %s, iteration %d, %s.%s" % (use, it, name, k))

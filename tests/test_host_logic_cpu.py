@@ -55,3 +55,34 @@ def test_flat_parameter_layout_is_aligned_and_aliasing():
         assert all(float(p.abs().max()) == 0.0 for p in g["params"])
     enc_trainable = {k for k, p in pol.encoder.named_parameters() if p.requires_grad}
     assert enc_trainable and not any(k.startswith("bert.") for k in enc_trainable)   # frozen BERT stack in the train config
+
+
+def test_module_flags_default_from_param_args_when_loaded():
+    """the reference's modules read flags from the global `param.args`; ours take them as kwargs that default to
+    param.args.<flag> when r2r_src's `param` module is loaded (and to the README values otherwise)."""
+    import sys
+    import types
+    from dasa_b200 import config, modules as M
+    assert config.reference_args() is None or "param" in sys.modules
+    saved = sys.modules.get("param")
+    fake = types.ModuleType("param")
+    fake.args = types.SimpleNamespace(angle_feat_size=128, featdropout=0.25, use_shift=True, shift_kernel_size=3, critic_dim=64,
+                                      dropout=0.3, ab_type="a", a_type="sigmoid")
+    sys.modules["param"] = fake
+    try:
+        dec = M.BAttnDecoderLSTM(64, 32, 0.3, feature_size=64 + 128)
+        assert dec.featdropout == 0.25 and dec.feat_att_layer.kernel_size == 3 and dec.drop_env.p == 0.25
+        cri = M.Critic()
+        assert cri.dim == 64 and cri.p == 0.3
+        assert M.BAttnDecoderLSTM(64, 32, 0.3, feature_size=64 + 128, shift_kernel_size=5).feat_att_layer.kernel_size == 5   # explicit wins
+        fake.args.a_type = "gumbel_sigmoid"
+        import pytest
+        with pytest.raises(NotImplementedError):
+            M.DGAdaChannel(64)
+    finally:
+        if saved is None:
+            del sys.modules["param"]
+        else:
+            sys.modules["param"] = saved
+    dec = M.BAttnDecoderLSTM(64, 32, 0.3, feature_size=64 + 128)
+    assert dec.featdropout == 0.4 and dec.feat_att_layer.kernel_size == 5
