@@ -32,6 +32,7 @@ struct PairParams {
   float* C[2]; int64_t ldc;      // one output per group (grouped launches: the two directions of the bi-LSTM recurrence)
   EpiParams ep;
   int tiles_n, tiles_mn;         // column tiles / tiles of one (group, K split)
+  int M2, tiles_mn2;             // grouped launches: rows / tiles per K split of group 1 (its own row count; 0 rows = group absent)
   int splits, kb_per_split;      // split-K: partial sums go to C[g] + split * split_stride, epilogue NONE
   int64_t split_stride;
   int tiles_total, num_pairs;
@@ -40,11 +41,12 @@ struct PairParams {
 struct PairTile { int g, ks, mt, nt; };
 __device__ __forceinline__ PairTile pair_decode(const PairParams& p, int w) {
   PairTile t;
-  const int per_group = p.tiles_mn * p.splits;
-  t.g = w / per_group;
-  int r = w - t.g * per_group;
-  t.ks = r / p.tiles_mn;
-  r -= t.ks * p.tiles_mn;
+  const int per_group0 = p.tiles_mn * p.splits;
+  t.g = w >= per_group0 ? 1 : 0;
+  int r = w - t.g * per_group0;
+  const int tmn = t.g ? p.tiles_mn2 : p.tiles_mn;
+  t.ks = r / tmn;
+  r -= t.ks * tmn;
   t.mt = r / p.tiles_n;
   t.nt = r - t.mt * p.tiles_n;
   return t;
@@ -258,7 +260,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(&tmem_full[a], aph);
       p_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + chalf * CW;
-      const bool interior = plain && (m_base + 32 <= p.M) && (n_base + CW <= p.N);   // warp-uniform: no edge checks at all
+      const int Mg = t.g ? p.M2 : p.M;
+      const bool interior = plain && (m_base + 32 <= Mg) && (n_base + CW <= p.N);   // warp-uniform: no edge checks at all
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
         float4 gsrc[8];
@@ -338,7 +341,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 2
           for (int rr = 0; rr < 32; rr += 4) {
             const int m = m_base + rr + rsub;
-            if (m >= p.M) continue;
+            if (m >= Mg) continue;
             const float4 a4 = *reinterpret_cast<const float4*>(stg + (rr + rsub) * P_EPI_LD + 4 * col4);
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
             float* crow = Cg + (int64_t)m * p.ldc + n;
@@ -558,23 +561,35 @@ int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float 
 // The recurrent GEMMs of the two bi-LSTM directions are issued this way, so one time step is one launch that fills the TPCs.
 int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st) {
-  if (M <= 0 || N <= 0 || K < P_BK || splits < 1) return DASA_ERR_BAD_SHAPE;
+  return dasa_gemm_tc_pair_grouped2(M, M, N, K, A, lda, B, ldb, C, ldc, splits, split_stride, st);
+}
+
+// The same with a row count per group (M0 rows of A[0] / C[0], M1 rows of A[1] / C[1]; either may be 0): the padding-free
+// bi-LSTM recurrence, where the forward direction's live sequences shrink while the reverse direction's grow.
+int dasa_gemm_tc_pair_grouped2(int M0, int M1, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
+                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st) {
+  if (M0 < 0 || M1 < 0 || M0 + M1 <= 0 || N <= 0 || K < P_BK || splits < 1) return DASA_ERR_BAD_SHAPE;
   ++g_gemm_routes[DASA_ROUTE_PAIR_GROUPED];
   PairParams p{};
-  p.M = M; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.C[0] = C[0]; p.C[1] = C[1]; p.ldc = ldc;
+  p.M = M0; p.M2 = M1; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.C[0] = C[0]; p.C[1] = C[1]; p.ldc = ldc;
   p.tiles_n = (int)dasa_cdiv(N, 256);
-  p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  p.tiles_mn = (int)(dasa_cdiv(M0, 2 * P_BM) * p.tiles_n);
+  p.tiles_mn2 = (int)(dasa_cdiv(M1, 2 * P_BM) * p.tiles_n);
   const int nkb = (int)dasa_cdiv(K, P_BK);
   if (splits > nkb) splits = nkb;
   p.kb_per_split = (int)dasa_cdiv(nkb, splits);
   p.splits = (int)dasa_cdiv(nkb, p.kb_per_split);          // every split owns at least one k-block
   p.split_stride = split_stride;
-  p.tiles_total = 2 * p.tiles_mn * p.splits;
+  p.tiles_total = (p.tiles_mn + p.tiles_mn2) * p.splits;
   p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
   CUtensorMap ta[2], tb[2];
   for (int g = 0; g < 2; ++g) {
+    const int Mg = g ? M1 : M0;
+    if (Mg == 0) continue;
     if (!dasa_aligned16(A[g]) || !dasa_aligned16(B[g]) || (lda & 3) || (ldb & 3)) return DASA_ERR_BAD_ALIGN;
-    if (!pair_make_map(&ta[g], A[g], M, K, lda, P_BM) || !pair_make_map(&tb[g], B[g], N, K, ldb, 128)) return DASA_ERR_UNSUPPORTED;
+    if (!pair_make_map(&ta[g], A[g], Mg, K, lda, P_BM) || !pair_make_map(&tb[g], B[g], N, K, ldb, 128)) return DASA_ERR_UNSUPPORTED;
   }
+  if (M0 == 0) { ta[0] = ta[1]; tb[0] = tb[1]; }            // an absent group has no tiles: its maps are never fetched
+  if (M1 == 0) { ta[1] = ta[0]; tb[1] = tb[0]; }
   return launch_pair_e<256, 5, DASA_EPI_NONE>(ta, tb, p, st) == DASA_OK ? p.splits : DASA_ERR_CUDA;
 }

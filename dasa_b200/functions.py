@@ -511,6 +511,81 @@ class BiLSTMFn(torch.autograd.Function):
         return (dx, None) + (None,) * 8
 
 
+class PackedBiLSTMFn(torch.autograd.Function):
+    """The same bidirectional LSTM, padding-free (csrc/bilstm_packed.cu): x_packed [N_tokens, In] = the valid tokens of R
+    sequences back to back in ORIGINAL token order (PackInfo layout); plan = PackInfo.bilstm_plan() (length ranking, position
+    blocks, the gather index that also performs the token reversal of r2rmodel.py:2326-2330). Returns ctx [R, L, 2H] (zero rows
+    past each length), h_fin [2, R, H], c_fin [2, R, H] in original sequence order, like BiLSTMFn."""
+
+    @staticmethod
+    def forward(ctx, x_packed, plan, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        R, L, N = plan.R, plan.L, plan.N
+        H = w_hh_f.shape[1]
+        dev = x_packed.device
+        xc = x_packed.detach().index_select(0, plan.src)                       # [N, In] position-block order
+        params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
+        xp = [ops.linear_fwd(xc, w_ih) for (w_ih, _, _, _) in params]          # [N, 4H]: valid tokens only
+        hprev = torch.empty(2, N, H, device=dev, dtype=torch.float32)
+        cs = torch.empty(2, L + 1, R, H, device=dev, dtype=torch.float32)
+        acts = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float32)
+        out = torch.zeros(R, L, 2 * H, device=dev, dtype=torch.float32)
+        fin = torch.empty(2, 2, R, H, device=dev, dtype=torch.float32)         # [h | c][direction] in rank order
+        P2 = ops.lib.P * 2
+        cast = ops.ctypes.cast
+        a = ops.lib.BiLstmPackedFwd(R, L, H, cast(plan.n_rows, ops.lib.P), cast(plan.off, ops.lib.P), plan.perm.data_ptr(),
+                                    P2(xp[0].data_ptr(), xp[1].data_ptr()), P2(w_hh_f.data_ptr(), w_hh_r.data_ptr()),
+                                    P2(b_ih_f.data_ptr(), b_ih_r.data_ptr()), P2(b_hh_f.data_ptr(), b_hh_r.data_ptr()),
+                                    P2(hprev[0].data_ptr(), hprev[1].data_ptr()), P2(cs[0].data_ptr(), cs[1].data_ptr()),
+                                    P2(acts[0].data_ptr(), acts[1].data_ptr()), out.data_ptr(),
+                                    P2(fin[0, 0].data_ptr(), fin[0, 1].data_ptr()), P2(fin[1, 0].data_ptr(), fin[1, 1].data_ptr()))
+        ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 0))
+        ops.call("dasa_bilstm_packed_fwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
+        h_fin = fin[0].index_select(1, plan.rank_of)
+        c_fin = fin[1].index_select(1, plan.rank_of)
+        ctx.plan = plan
+        ctx.save_for_backward(xc, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hprev, cs, acts)
+        return out, h_fin, c_fin
+
+    @staticmethod
+    def backward(ctx, dout, dh_fin, dc_fin):
+        (xc, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hprev, cs, acts) = ctx.saved_tensors
+        plan = ctx.plan
+        R, L, N = plan.R, plan.L, plan.N
+        H = w_hh_f.shape[1]
+        dev = xc.device
+        dout = dout.contiguous() if dout is not None else torch.zeros(R, L, 2 * H, device=dev)
+        params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
+        dhf = dh_fin.index_select(1, plan.perm64).contiguous() if dh_fin is not None else None      # rank order
+        dcf = dc_fin.index_select(1, plan.perm64).contiguous() if dc_fin is not None else None
+        wt = (_transposed(w_hh_f), _transposed(w_hh_r))
+        dgates = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float32)
+        work = torch.empty(2, 2, R, H, device=dev, dtype=torch.float32)
+        P2 = ops.lib.P * 2
+        cast = ops.ctypes.cast
+
+        def pp(t, d):
+            return None if t is None else t[d].data_ptr()
+        a = ops.lib.BiLstmPackedBwd(R, L, H, cast(plan.n_rows, ops.lib.P), cast(plan.off, ops.lib.P), plan.perm.data_ptr(),
+                                    P2(wt[0].data_ptr(), wt[1].data_ptr()), P2(acts[0].data_ptr(), acts[1].data_ptr()),
+                                    P2(cs[0].data_ptr(), cs[1].data_ptr()), dout.data_ptr(), P2(pp(dhf, 0), pp(dhf, 1)),
+                                    P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates[0].data_ptr(), dgates[1].data_ptr()),
+                                    P2(work[0].data_ptr(), work[1].data_ptr()))
+        ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 1))
+        ops.call("dasa_bilstm_packed_bwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
+        dxc = None
+        for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
+            _wgrad(w_ih, dgates[d], xc, b_ih, b_hh)                            # db_ih == db_hh: one column sum
+            _wgrad(w_hh, dgates[d], hprev[d])
+            if ctx.needs_input_grad[0]:
+                g = ops.linear_bwd_input(dgates[d], w_ih)
+                dxc = g if dxc is None else dxc + g
+        dx = None
+        if dxc is not None:
+            dx = torch.empty_like(dxc)
+            dx[plan.src] = dxc                                                 # the gather index is a bijection of the N tokens
+        return (dx, None) + (None,) * 8
+
+
 class MaskedCEFn(torch.autograd.Function):
     """sum-reduced cross entropy with ignore_index over candidate logits that already carry -inf (agent_dg.py:850).
     Returns (loss[1], greedy action[B])."""

@@ -33,6 +33,18 @@ class BiLstmBwd(ctypes.Structure):
                 ("dgates", P * 2), ("dh_pass", P * 2), ("dc_work", P * 2), ("lengths", P), ("B", I), ("L", I), ("H", I)]
 
 
+class BiLstmPackedFwd(ctypes.Structure):
+    """dasa_bilstm_packed_fwd_t"""
+    _fields_ = [("R", I), ("L", I), ("H", I), ("n_rows", P), ("off", P), ("perm", P), ("xp", P * 2), ("w_hh", P * 2), ("b_ih", P * 2),
+                ("b_hh", P * 2), ("hprev", P * 2), ("cs", P * 2), ("acts", P * 2), ("out", P), ("h_fin", P * 2), ("c_fin", P * 2)]
+
+
+class BiLstmPackedBwd(ctypes.Structure):
+    """dasa_bilstm_packed_bwd_t"""
+    _fields_ = [("R", I), ("L", I), ("H", I), ("n_rows", P), ("off", P), ("perm", P), ("w_hh_t", P * 2), ("acts", P * 2), ("cs", P * 2),
+                ("dout", P), ("dh_fin", P * 2), ("dc_fin", P * 2), ("dgates", P * 2), ("dc_work", P * 2)]
+
+
 class DecoderFwd(ctypes.Structure):
     """dasa_decoder_fwd_t (field order and types exactly as in include/dasa_b200.h)"""
     _fields_ = ([(k, I) for k in ("T", "B", "H", "E", "F", "V", "L", "D", "headings", "shift_k", "NK")] +

@@ -488,6 +488,47 @@ class PackInfo:
         self.rows = torch.tensor(rows, dtype=torch.int32, device=device)      # packed row -> row of the padded [nseq*L, .] layout
         self.rows64 = self.rows.to(torch.int64)
         self.pair = (self.off, self.len)
+        self._lens_host, self._off_host, self._bl, self._device = lens, off, None, device
+
+    def bilstm_plan(self):
+        """Bookkeeping of the padding-free bi-LSTM (csrc/bilstm_packed.cu): sequences ranked by length (descending, stable), tokens
+        of the REVERSED sequences (r2rmodel.py:2326-2330) in position-block order. Built once per length pattern."""
+        if self._bl is None:
+            import ctypes
+            lens, offs, L = self._lens_host, self._off_host, self.L
+            R = len(lens)
+            order = sorted(range(R), key=lambda i: -lens[i])
+            n_rows = [0] * L
+            for n in lens:
+                for p in range(min(n, L)):
+                    n_rows[p] += 1
+            off = [0]
+            for p in range(L):
+                off.append(off[-1] + n_rows[p])
+            src = []
+            for p in range(L):
+                for r in range(n_rows[p]):
+                    i = order[r]
+                    src.append(offs[i] + lens[i] - 1 - p)       # position p of the reversed sequence = original token len-1-p
+            rank_of = [0] * R
+            for r, i in enumerate(order):
+                rank_of[i] = r
+            dev = self._device
+
+            class Plan:
+                pass
+            pl = Plan()
+            pl.R, pl.L, pl.N = R, L, off[-1]
+            pl.n_rows = (ctypes.c_int32 * L)(*n_rows)
+            pl.off = (ctypes.c_int64 * (L + 1))(*off)
+            pl.n_rows_list, pl.off_list = n_rows, off
+            pl.perm = torch.tensor(order, dtype=torch.int32, device=dev)
+            pl.perm64 = pl.perm.to(torch.int64)
+            pl.rank_of = torch.tensor(rank_of, dtype=torch.int64, device=dev)
+            pl.src = torch.tensor(src, dtype=torch.int64, device=dev)
+            pl.steps_used = max(lens)
+            self._bl = pl
+        return self._bl
 
     def step_slice(self, t):
         """Rows of rollout step t inside a packed tensor built with steps > 1."""
@@ -721,6 +762,12 @@ class DicEncoder(nn.Module):
         self.pack_tokens = True         # evaluate the frozen transformer stack on valid tokens only (see PackInfo)
         self._packs = {}
 
+    packed_lstm = True              # large batches on the tensor-core precision: padding-free recurrence (csrc/bilstm_packed.cu)
+
+    def _packed_lstm(self, pack):
+        return (self.packed_lstm and pack is not None and ops._precision == ops.PREC_TF32 and self.hidden_size % 32 == 0 and
+                pack.nseq > ops.lib.load().dasa_bilstm_max_batch())
+
     def _pack(self, lengths, lengths_host, L, steps, device):
         """PackInfo for this batch, or None (lengths only known on the device, finetune config, or packing switched off)."""
         if not self.pack_tokens or self.cfg.update_add_layer:
@@ -785,14 +832,17 @@ class DicEncoder(nn.Module):
             rev = Fn.ReverseTokensFn.apply(lang, len32)
         elif pack is not None:
             lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps, pack)
-            rev = ops.reverse_tokens_packed(lang, pack.off, pack.len, L)
+            rev = None if self._packed_lstm(pack) else ops.reverse_tokens_packed(lang, pack.off, pack.len, L)
         else:
             lang, visn = self.bert.cross_modal(lang_all, pad_all, f_all, tr, steps)
             rev = ops.reverse_tokens(lang, len32)
         l = self.lstm
-        ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0,
-                                              l.weight_ih_l0_reverse, l.weight_hh_l0_reverse, l.bias_ih_l0_reverse,
-                                              l.bias_hh_l0_reverse)
+        lstm_args = (l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0, l.weight_ih_l0_reverse, l.weight_hh_l0_reverse,
+                     l.bias_ih_l0_reverse, l.bias_hh_l0_reverse)
+        if rev is None:      # padding-free recurrence straight from the packed tokens (reversal folded into its gather index)
+            ctx, h_fin, c_fin = Fn.PackedBiLSTMFn.apply(lang, pack.bilstm_plan(), *lstm_args)
+        else:
+            ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, *lstm_args)
         h_cat = torch.cat((h_fin[1, :B], h_fin[0, :B]), 1)
         c_cat = torch.cat((c_fin[1, :B], c_fin[0, :B]), 1)
         decoder_init = Fn.linear(h_cat, self.encoder_lstm2decoder_ht.weight, self.encoder_lstm2decoder_ht.bias, "tanh")
@@ -826,14 +876,17 @@ class DicEncoder(nn.Module):
             rev = Fn.ReverseTokensFn.apply(lang, len32)
         elif pack is not None:
             lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr, 1, pack)
-            rev = ops.reverse_tokens_packed(lang, pack.off, pack.len, L)
+            rev = None if self._packed_lstm(pack) else ops.reverse_tokens_packed(lang, pack.off, pack.len, L)
         else:
             lang, visn = self.bert.cross_modal(lang0, pad, f_t_all, tr)
             rev = ops.reverse_tokens(lang, len32)
         l = self.lstm
-        ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0,
-                                              l.weight_ih_l0_reverse, l.weight_hh_l0_reverse, l.bias_ih_l0_reverse,
-                                              l.bias_hh_l0_reverse)
+        lstm_args = (l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0, l.weight_ih_l0_reverse, l.weight_hh_l0_reverse,
+                     l.bias_ih_l0_reverse, l.bias_hh_l0_reverse)
+        if rev is None:
+            ctx, h_fin, c_fin = Fn.PackedBiLSTMFn.apply(lang, pack.bilstm_plan(), *lstm_args)
+        else:
+            ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, *lstm_args)
         # h_t = cat(enc_h_t[-1], enc_h_t[-2]): reverse-direction final state first (r2rmodel.py:2345-2346)
         h_cat = torch.cat((h_fin[1], h_fin[0]), 1)
         c_cat = torch.cat((c_fin[1], c_fin[0]), 1)

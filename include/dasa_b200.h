@@ -225,6 +225,39 @@ size_t dasa_bilstm_seq_gemm_workspace(int B, int H, int backward);
 int dasa_bilstm_seq_gemm_fwd(const dasa_bilstm_fwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
 int dasa_bilstm_seq_gemm_bwd(const dasa_bilstm_bwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Padding-free form of the large-batch recurrence (nn.LSTM over a PackedSequence touches only valid tokens, r2rmodel.py:2339-2357).
+ * The R sequences are RANKED by length (descending; perm[rank] = original sequence index) and every per-token array is stored in
+ * position-block order: block p = the tokens at (reversed-sequence) position p of the n_rows[p] sequences longer than p, rank-major,
+ * at rows off[p] .. off[p] + n_rows[p] of a compact [N = off[L], .] array. The forward direction's step s works on block s, the
+ * reverse direction's on block L-1-s: live rows are a prefix of the ranks, so a step is one grouped tcgen05 GEMM with its own row
+ * count per direction on contiguous operand blocks, and x W_ih^T / the weight gradients run over N rows instead of R x L.
+ *   n_rows, off: HOST arrays ([L] non-increasing with n_rows[0] == R; [L+1] running sum). perm: DEVICE int32 [R].
+ *   xp[d] [N, 4H] = x W_ih[d]^T without bias; hprev[d] [N, H] receives the state BEFORE every token (the K-major operand of the
+ *   recurrent GEMM and of dW_hh); cs[d] [L+1, R, H] cell state before step s at index s, rank-major (live rows only);
+ *   acts[d] [N, 4H]; out [R, L, 2H] in ORIGINAL sequence order, zero-initialised by the caller (only valid tokens are written);
+ *   h_fin / c_fin [R, H] per direction in RANK order. workspace: dasa_bilstm_packed_workspace(R, H, backward) bytes.            */
+typedef struct {
+  int R, L, H;
+  const int32_t* n_rows; const int64_t* off; const int32_t* perm;
+  const float* xp[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];
+  float* hprev[2]; float* cs[2]; float* acts[2];
+  float* out;
+  float* h_fin[2]; float* c_fin[2];
+} dasa_bilstm_packed_fwd_t;
+/* Backward: dout [R, L, 2H] (original order), dh_fin / dc_fin [R, H] rank order (may be NULL), w_hh_t[d] = W_hh[d]^T [H, 4H].
+ * Writes dgates[d] [N, 4H] (compact token order: the dY of dW_ih = dgates^T x, dW_hh = dgates^T hprev, dX = dgates W_ih).
+ * dc_work[d]: scratch [2, R, H].                                                                                               */
+typedef struct {
+  int R, L, H;
+  const int32_t* n_rows; const int64_t* off; const int32_t* perm;
+  const float* w_hh_t[2]; const float* acts[2]; const float* cs[2];
+  const float* dout; const float* dh_fin[2]; const float* dc_fin[2];
+  float* dgates[2]; float* dc_work[2];
+} dasa_bilstm_packed_bwd_t;
+size_t dasa_bilstm_packed_workspace(int R, int H, int backward);
+int dasa_bilstm_packed_fwd(const dasa_bilstm_packed_fwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
+int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------- persistent decoder rollout
  * BAttnDecoderLSTM.forward (model.py:472-574) for T consecutive actions of B <= 32 episodes in ONE cooperative launch: one CTA
  * per SM stays resident for the whole rollout, the phases of an action are separated by a device-wide barrier instead of

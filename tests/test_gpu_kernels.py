@@ -851,3 +851,75 @@ def test_linear_backward_helpers_tf32_mn_major():
     finally:
         ops.use_mn_major = True
         ops.set_precision("fp32")
+
+
+# ------------------------------------------------------------------------------ padding-free bi-LSTM (bilstm_packed.cu)
+@pytest.mark.parametrize("R,L,In,H,seed", [(70, 12, 64, 64, 0), (300, 21, 96, 128, 1), (45, 9, 64, 32, 2)])
+def test_packed_bilstm_matches_padded_path(R, L, In, H, seed):
+    """PackedBiLSTMFn (length-ranked, position-block token order, per-direction row counts in the grouped tcgen05 GEMM) against
+    BiLSTMFn on the padded reversed input in exact fp32: sequence outputs (zero rows past each length), final states in original
+    order, and every gradient incl. the packed input's. TF32 recurrence over up to 21 steps: 5e-3 normwise."""
+    from dasa_b200 import functions as Fn
+    from dasa_b200 import modules as M
+    from dasa_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, L + 1, (R,), generator=g).tolist()
+    lens[3] = L
+    lens[5] = 1
+    pack = M.PackInfo(lens, L, 1, DEV)
+    plan = pack.bilstm_plan()
+    assert plan.N == sum(lens) and list(plan.n_rows_list)[0] == R
+    x = (torch.randn(pack.ntok, In, generator=g) * 0.5).to(DEV)
+
+    def weights():
+        gg = torch.Generator().manual_seed(seed + 100)
+        return [(torch.randn(*s, generator=gg) * sc).to(DEV).requires_grad_(True)
+                for s, sc in (((4 * H, In), In ** -0.5), ((4 * H, H), H ** -0.5), ((4 * H,), 0.1), ((4 * H,), 0.1)) * 2]
+    gout = torch.randn(R, L, 2 * H, generator=g).to(DEV)
+    ghf = torch.randn(2, R, H, generator=g).to(DEV)
+    gcf = torch.randn(2, R, H, generator=g).to(DEV)
+    # reference: padded path, exact fp32
+    w_ref = weights()
+    x_ref = x.clone().requires_grad_(True)
+    rev = ReversePackedFn.apply(x_ref, pack, L)
+    out_r, h_r, c_r = Fn.BiLSTMFn.apply(rev, pack.len, *w_ref)
+    ((out_r * gout).sum() + (h_r * ghf).sum() + (c_r * gcf).sum()).backward()
+    # packed path, TF32
+    w_pk = weights()
+    x_pk = x.clone().requires_grad_(True)
+    ops.set_precision("tf32")
+    try:
+        out_p, h_p, c_p = Fn.PackedBiLSTMFn.apply(x_pk, plan, *w_pk)
+        ((out_p * gout).sum() + (h_p * ghf).sum() + (c_p * gcf).sum()).backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision("fp32")
+    valid = torch.arange(L, device=DEV).view(1, L) < pack.len.view(R, 1)
+    assert float(out_p[~valid].abs().max()) == 0.0, "rows past a sequence's length must be exactly zero"
+    for name, a, b in (("out", out_p, out_r), ("h_fin", h_p, h_r), ("c_fin", c_p, c_r), ("dx", x_pk.grad, x_ref.grad)):
+        assert rel_err(a, b) <= 5e-3, "%s: %.3e" % (name, rel_err(a, b))
+    for i, nm in enumerate(("w_ih_f", "w_hh_f", "b_ih_f", "b_hh_f", "w_ih_r", "w_hh_r", "b_ih_r", "b_hh_r")):
+        assert rel_err(w_pk[i].grad, w_ref[i].grad) <= 5e-3, "grad %s: %.3e" % (nm, rel_err(w_pk[i].grad, w_ref[i].grad))
+
+
+class ReversePackedFn(torch.autograd.Function):
+    """test helper: packed tokens -> padded reversed [R, L, In] with a gradient back to the packed rows"""
+
+    @staticmethod
+    def forward(ctx, x, pack, L):
+        from dasa_b200 import ops
+        ctx.pack, ctx.L = pack, L
+        return ops.reverse_tokens_packed(x, pack.off, pack.len, L)
+
+    @staticmethod
+    def backward(ctx, g):
+        pack, L = ctx.pack, ctx.L
+        R = pack.nseq
+        lens = pack.len.to(torch.int64)
+        pos = torch.arange(L, device=g.device).view(1, L)
+        src_pos = lens.view(R, 1) - 1 - pos                                      # original token index at reversed position
+        ok = src_pos >= 0
+        rows = (pack.off.to(torch.int64).view(R, 1) + src_pos.clamp(min=0))[ok]
+        dx = torch.zeros(pack.ntok, g.shape[2], device=g.device)
+        dx[rows] = g[ok]
+        return dx, None, None
