@@ -55,6 +55,16 @@ extern "C" int dasa_debug_gemm_route_counts(int64_t* out, int n, int reset) {
   return DASA_OK;
 }
 
+extern "C" int dasa_gemm_f16_supported(int M, int N, int K) { return dasa_gemm_f16_pair_supported(M, N, K) ? 1 : 0; }
+
+extern "C" int dasa_gemm_f16(int M, int N, int K, const dasa_half_t* A, int64_t lda, const dasa_half_t* B, int64_t ldb, void* C,
+                             int64_t ldc, int c_half, int epilogue, const dasa_epilogue_t* epi, void* stream) {
+  if (A == nullptr || B == nullptr || C == nullptr) return DASA_ERR_BAD_SHAPE;
+  if (epi != nullptr && (epi->drop_mask != nullptr || epi->gate_src != nullptr)) return DASA_ERR_UNSUPPORTED;
+  const EpiParams ep = make_epi(epi);
+  return dasa_gemm_tc_pair_f16(M, N, K, A, lda, B, ldb, C, ldc, c_half, epilogue, ep, (cudaStream_t)stream);
+}
+
 extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
                          const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue,
                          const dasa_epilogue_t* epi, int precision, void* workspace, size_t workspace_bytes,

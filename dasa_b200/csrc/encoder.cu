@@ -1,6 +1,7 @@
 // Encoder-side kernels for DicEncoder / DicModel (r2rmodel.py:2272-2365, vilmodel.py:161-236, 479-506, 1083-1095):
 // embedding + LayerNorm, fused dropout/residual/LayerNorm, short-sequence multi-head attention (one CTA per
 // (sample, head), everything resident in shared memory), token reversal. The dense projections go through dasa_gemm.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(const int64_t* __r
 __global__ void __launch_bounds__(128) dropout_residual_layernorm_kernel(
     const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ mask, float scale, const float* __restrict__ resid,
     int64_t ldr, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, const uint8_t* __restrict__ post_mask,
-    float post_scale, float* __restrict__ out, int64_t ldo, float* __restrict__ stats_out, float* __restrict__ z_out, int R, int Hd) {
+    float post_scale, float* __restrict__ out, int64_t ldo, float* __restrict__ stats_out, float* __restrict__ z_out,
+    __half* __restrict__ out_half, int R, int Hd) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -117,6 +119,10 @@ __global__ void __launch_bounds__(128) dropout_residual_layernorm_kernel(
         o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
       }
       reinterpret_cast<float4*>(out + (int64_t)row * ldo)[j] = o;
+      if (out_half != nullptr) {         // fp16 copy [R, Hd] contiguous: the A operand of the next fp16 GEMM
+        __half2 h[2] = {__floats2half2_rn(o.x, o.y), __floats2half2_rn(o.z, o.w)};
+        reinterpret_cast<uint2*>(out_half + (int64_t)row * Hd)[j] = *reinterpret_cast<uint2*>(h);
+      }
     }
   }
 }
@@ -192,6 +198,7 @@ struct MhaArgs {
   const uint8_t* key_pad; int64_t ld_pad; const uint8_t* drop_mask; float drop_scale;
   float* out; int64_t ldo, so; float* probs_out;
   int B, heads, Lq, Lk, dh;
+  int out_half;      // `out` holds IEEE halves (ldo / so in halves): the A operand of the fp16 output projection
   // packed (variable-length) operands: rows of sample b start at row q_off[b] / k_off[b] of the packed matrix and there are
   // q_len[b] / k_len[b] of them; Lq / Lk are then the maxima (shared-memory carve-up, mask / probs indexing). NULL = dense.
   const int32_t *q_off, *q_len, *k_off, *k_len;
@@ -334,7 +341,11 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs a) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int d = lane + 32 * c;
-          if (d < dh) ob[(int64_t)(i0 + r) * a.ldo + d] = o[r][c];
+          if (d < dh) {
+            if (a.out_half) reinterpret_cast<__half*>(a.out)[(a.q_off ? (int64_t)a.q_off[b] * a.ldo : (int64_t)b * a.so) + h * dh +
+                                                             (int64_t)(i0 + r) * a.ldo + d] = __float2half_rn(o[r][c]);
+            else ob[(int64_t)(i0 + r) * a.ldo + d] = o[r][c];
+          }
         }
       }
   }
@@ -494,8 +505,14 @@ __global__ void __launch_bounds__(MHA_TC_THREADS) mha_fwd_tc_kernel(MhaArgs a) {
     for (int nt = 0; nt < 8; ++nt) {
       if (nt * 8 < dh) {
         const int d = nt * 8 + 2 * t;
-        if (r0 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r0 * a.ldo + d) = make_float2(o[nt][0], o[nt][1]);
-        if (r1 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r1 * a.ldo + d) = make_float2(o[nt][2], o[nt][3]);
+        if (a.out_half) {
+          __half* oh = reinterpret_cast<__half*>(a.out) + (a.q_off ? (int64_t)a.q_off[b] * a.ldo : (int64_t)b * a.so) + h * dh;
+          if (r0 < Lq) *reinterpret_cast<__half2*>(oh + (int64_t)r0 * a.ldo + d) = __floats2half2_rn(o[nt][0], o[nt][1]);
+          if (r1 < Lq) *reinterpret_cast<__half2*>(oh + (int64_t)r1 * a.ldo + d) = __floats2half2_rn(o[nt][2], o[nt][3]);
+        } else {
+          if (r0 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r0 * a.ldo + d) = make_float2(o[nt][0], o[nt][1]);
+          if (r1 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r1 * a.ldo + d) = make_float2(o[nt][2], o[nt][3]);
+        }
       }
     }
   }
@@ -683,8 +700,14 @@ __global__ void __launch_bounds__(MHA_TC_THREADS, (NT >= 10 ? 3 : 4)) mha_fwd_tc
 #pragma unroll
     for (int n8 = 0; n8 < 8; ++n8) {
       const int d = n8 * 8 + 2 * t;
-      if (r0 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r0 * a.ldo + d) = make_float2(o[n8][0], o[n8][1]);
-      if (r1 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r1 * a.ldo + d) = make_float2(o[n8][2], o[n8][3]);
+      if (a.out_half) {
+        __half* oh = reinterpret_cast<__half*>(a.out) + (a.q_off ? (int64_t)a.q_off[b] * a.ldo : (int64_t)b * a.so) + h * dh;
+        if (r0 < Lq) *reinterpret_cast<__half2*>(oh + (int64_t)r0 * a.ldo + d) = __floats2half2_rn(o[n8][0], o[n8][1]);
+        if (r1 < Lq) *reinterpret_cast<__half2*>(oh + (int64_t)r1 * a.ldo + d) = __floats2half2_rn(o[n8][2], o[n8][3]);
+      } else {
+        if (r0 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r0 * a.ldo + d) = make_float2(o[n8][0], o[n8][1]);
+        if (r1 < Lq) *reinterpret_cast<float2*>(ob + (int64_t)r1 * a.ldo + d) = make_float2(o[n8][2], o[n8][3]);
+      }
     }
   }
 }
@@ -837,7 +860,7 @@ extern "C" int dasa_embed_layernorm(const int64_t* ids, int64_t ld_ids, int B, i
 extern "C" int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, const uint8_t* drop_mask, float drop_scale,
                                                const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps,
                                                const uint8_t* post_mask, float post_scale, float* out, int64_t ldo,
-                                               float* stats_out, float* z_out, int R, int Hd, void* stream) {
+                                               float* stats_out, float* z_out, dasa_half_t* out_half, int R, int Hd, void* stream) {
   if (R <= 0) return DASA_OK;
   if (!ln_shape_ok(Hd)) return DASA_ERR_BAD_SHAPE;
   if (!dasa_aligned16(x) || ldx % 4 || (resid && (!dasa_aligned16(resid) || ldr % 4)) || !dasa_aligned16(out) || ldo % 4 ||
@@ -845,7 +868,8 @@ extern "C" int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, cons
       (post_mask && reinterpret_cast<uintptr_t>(post_mask) % 4) || (z_out && !dasa_aligned16(z_out)))
     return DASA_ERR_BAD_ALIGN;
   dropout_residual_layernorm_kernel<<<(unsigned)dasa_cdiv(R, 4), 128, 0, (cudaStream_t)stream>>>(
-      x, ldx, drop_mask, drop_scale, resid, ldr, gamma, beta, eps, post_mask, post_scale, out, ldo, stats_out, z_out, R, Hd);
+      x, ldx, drop_mask, drop_scale, resid, ldr, gamma, beta, eps, post_mask, post_scale, out, ldo, stats_out, z_out,
+      reinterpret_cast<__half*>(out_half), R, Hd);
   return dasa_check_launch("dropout_residual_layernorm_kernel");
 }
 
@@ -868,8 +892,9 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
                         const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                             int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
                             float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out, int B, int heads, int Lq,
-                            int Lk, int dh, int precision, void* stream) {
+                            int Lk, int dh, int precision, int out_half, void* stream) {
   if (B <= 0 || heads <= 0) return DASA_OK;
+  if (out_half && probs_out != nullptr) return DASA_ERR_UNSUPPORTED;      // the probability-saving path re-reads `out` as floats
   if (precision == DASA_PREC_TF32 && Lq > 0 && Lk > 0 && Lk <= 8 * MHA_TC_MAXNT && dh % 8 == 0 && dh <= 64 && dasa_aligned16(q) &&
       dasa_aligned16(k) && dasa_aligned16(v) && !(ldq % 4 || ldk % 4 || ldv % 4 || sq % 4 || sk % 4 || sv % 4) &&
       dasa_aligned16(out) && !(ldo % 2 || so % 2)) {
@@ -891,7 +916,7 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
       if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc64 attr", e2); return DASA_ERR_CUDA; }
       MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
-                 q_off, q_len, k_off, k_len};
+                 out_half, q_off, q_len, k_off, k_len};
       const int warps = (LqP / 16) < 4 ? (LqP / 16) : 4;
       kern<<<(unsigned)(B * heads), 32 * warps, smem64, (cudaStream_t)stream>>>(at);
       return dasa_check_launch("mha_fwd_tc64_kernel");
@@ -903,7 +928,7 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
       if (e2 != cudaSuccess) { dasa_set_error("mha_fwd_tc attr", e2); return DASA_ERR_CUDA; }
       MhaArgs at{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
-                 q_off, q_len, k_off, k_len};
+                 out_half, q_off, q_len, k_off, k_len};
       const int warps = (LqP / 16) < 4 ? (LqP / 16) : 4;       // one warp per 16-row query tile, no idle warps
       kern<<<(unsigned)(B * heads), 32 * warps, smem_tc, (cudaStream_t)stream>>>(at);
       return dasa_check_launch("mha_fwd_tc_kernel");
@@ -919,7 +944,7 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
   cudaError_t e = cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { dasa_set_error("mha_fwd attr", e); return DASA_ERR_CUDA; }
   MhaArgs a{q, k, v, ldq, sq, ldk, sk, ldv, sv, key_pad, ld_pad, drop_mask, drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh,
-                 q_off, q_len, k_off, k_len};
+                 out_half, q_off, q_len, k_off, k_len};
   mha_fwd_kernel<<<(unsigned)(B * heads), 256, smem, (cudaStream_t)stream>>>(a);
   return dasa_check_launch("mha_fwd_kernel");
 }
@@ -927,20 +952,20 @@ static int mha_fwd_impl(const int32_t* q_off, const int32_t* q_len, const int32_
 extern "C" int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                             int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
                             float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out, int B, int heads, int Lq,
-                            int Lk, int dh, int precision, void* stream) {
+                            int Lk, int dh, int precision, int out_half, void* stream) {
   return mha_fwd_impl(nullptr, nullptr, nullptr, nullptr, q, ldq, sq, k, ldk, sk, v, ldv, sv, key_pad, ld_pad, drop_mask,
-                      drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh, precision, stream);
+                      drop_scale, out, ldo, so, probs_out, B, heads, Lq, Lk, dh, precision, out_half, stream);
 }
 
 extern "C" int dasa_mha_fwd_varlen(const float* q, int64_t ldq, const int32_t* q_off, const int32_t* q_len, const float* k,
                                    int64_t ldk, const float* v, int64_t ldv, const int32_t* k_off, const int32_t* k_len,
                                    int64_t dense_q_stride, int64_t dense_kv_stride, const uint8_t* drop_mask, float drop_scale,
                                    float* out, int64_t ldo, int B, int heads, int max_Lq, int max_Lk, int dh, int precision,
-                                   void* stream) {
+                                   int out_half, void* stream) {
   if ((q_off == nullptr) != (q_len == nullptr) || (k_off == nullptr) != (k_len == nullptr)) return DASA_ERR_BAD_SHAPE;
   return mha_fwd_impl(q_off, q_len, k_off, k_len, q, ldq, dense_q_stride, k, ldk, dense_kv_stride, v, ldv, dense_kv_stride,
                       nullptr, 0, drop_mask, drop_scale, out, ldo, dense_q_stride / (ldq ? ldq : 1) * ldo, nullptr, B, heads,
-                      max_Lq, max_Lk, dh, precision, stream);
+                      max_Lq, max_Lk, dh, precision, out_half, stream);
 }
 
 extern "C" int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,

@@ -99,6 +99,9 @@ int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float 
 // grouped (2 problems) / split-K launch of the pair kernel; returns the number of K splits actually used (>= 1) or a negative error
 int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st);
+bool dasa_gemm_f16_pair_supported(int M, int N, int K);
+int dasa_gemm_tc_pair_f16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_half,
+                          int epilogue, const EpiParams& ep, cudaStream_t st);
 int dasa_gemm_tc_pair_grouped2(int M0, int M1, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                                float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st);
 // skinny (M <= 32) weight-streaming mma.sync TF32 kernel, gemm_skinny.cu

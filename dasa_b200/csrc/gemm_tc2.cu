@@ -15,6 +15,7 @@
 //                   one warp's tcgen05.ld / shared-memory round trip hides behind the other's activation math
 #include <cuda.h>
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "gemm_common.cuh"
 
@@ -33,6 +34,7 @@ struct PairParams {
   EpiParams ep;
   int tiles_n, tiles_mn;         // column tiles / tiles of one (group, K split)
   int M2, tiles_mn2;             // grouped launches: rows / tiles per K split of group 1 (its own row count; 0 rows = group absent)
+  int c_half;                    // fp16 operand kernels: C holds IEEE halves (ldc in halves) instead of floats
   int splits, kb_per_split;      // split-K: partial sums go to C[g] + split * split_stride, epilogue NONE
   int64_t split_stride;
   int tiles_total, num_pairs;
@@ -81,6 +83,21 @@ __device__ __forceinline__ void p_umma_tf32_pair(uint32_t tmem_d, uint64_t da, u
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void p_umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// 4 consecutive outputs of one row: floats, or halves when the kernel writes an fp16 activation for the next fp16 GEMM
+__device__ __forceinline__ void p_store4(float* C, int64_t row_off, int n, const float (&v)[4], bool c_half) {
+  if (c_half) {
+    __half2 h[2] = {__floats2half2_rn(v[0], v[1]), __floats2half2_rn(v[2], v[3])};
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(C) + row_off + n) = *reinterpret_cast<uint2*>(h);
+  } else {
+    *reinterpret_cast<float4*>(C + row_off + n) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
 __device__ __forceinline__ uint64_t p_desc_sw128(const void* smem_ptr) {   // K-major, 128B swizzle, 8-row atoms 1024 B apart
   const uint32_t addr = smem_u32(smem_ptr);
   uint64_t d = 0;
@@ -120,7 +137,10 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // AMN / BMN: the operand is MN-major in HBM (A stored [K][M], B stored [K][N]): dX = dY.W and dW = dY^T.X run without any
 // transposed copy of the activations / weights.
-template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false>
+// F16: both operands are IEEE fp16 in HBM (K-major, 64 elements = one 128-byte swizzle row per stage row), tcgen05 kind::f16 at
+// twice the TF32 rate, fp32 accumulate. fp16 carries TF32's 10 mantissa bits, so for operands inside fp16's normal range the
+// products equal the TF32 kernel's: used for the frozen, forward-only transformer stack, whose activations are O(1..100).
+template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, PairParams p) {
@@ -138,7 +158,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = p_ctarank();
   const int pair = blockIdx.x >> 1;
-  const int nkb = (p.K + P_BK - 1) / P_BK;
+  constexpr int BKE = F16 ? 2 * P_BK : P_BK;             // K elements per pipeline stage (128 bytes per operand row either way)
+  const int nkb = (p.K + BKE - 1) / BKE;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -181,13 +202,13 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int c = 0; c < P_BM / 32; ++c) p_tma_load_2sm(dst + c * (P_BK * 128), ma, m0 + 32 * c, kb * P_BK, fb);
           } else {
-            p_tma_load_2sm(dst, ma, kb * P_BK, m0, fb);
+            p_tma_load_2sm(dst, ma, kb * BKE, m0, fb);
           }
           if constexpr (BMN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c) p_tma_load_2sm(dst + A_BYTES + c * (P_BK * 128), mb, nb0 + 32 * c, kb * P_BK, fb);
           } else {
-            p_tma_load_2sm(dst + A_BYTES, mb, kb * P_BK, nb0, fb);
+            p_tma_load_2sm(dst + A_BYTES, mb, kb * BKE, nb0, fb);
           }
         }
       }
@@ -200,7 +221,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0 && crank == 0) {
       // -------------------------------------------------------------- MMA issuer (leader CTA, single thread)
       // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 256 (128 rows in each CTA's TMEM)
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+      constexpr uint32_t fmt = F16 ? 0u : 2u;            // kind::f16: 0 = F16 ; kind::tf32: 2 = TF32
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int tile = pair; tile < p.tiles_total; tile += p.num_pairs, ++tcount) {
@@ -221,8 +243,10 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           // K-major: 8 tf32 = 32 B further along the swizzled row; MN-major: the next group of 8 k rows (1024 B)
           constexpr uint64_t ka = AMN ? 64 : 2, kbs = BMN ? 64 : 2;
 #pragma unroll
-          for (int k = 0; k < P_BK / 8; ++k)
-            p_umma_tf32_pair(d_tmem, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          for (int k = 0; k < P_BK / 8; ++k) {             // 4 UMMAs of 32 bytes of K each (8 tf32 / 16 fp16)
+            if constexpr (F16) p_umma_f16_pair(d_tmem, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+            else p_umma_tf32_pair(d_tmem, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          }
           p_commit_pair(&empty_bar[s]);                    // stage free in both CTAs once these MMAs retire
         }
         p_commit_pair(&tmem_full[a]);                      // accumulator complete: visible to both CTAs' epilogues
@@ -326,7 +350,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = apply_activation_t<EPI>(v[e] + bias4[e], m, n + e, p.N, p.ep);
-            *reinterpret_cast<float4*>(Cg + (int64_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+            p_store4(Cg, (int64_t)m * p.ldc, n, v, F16 && p.c_half);
           }
           }
         } else if (n < p.N) {
@@ -353,7 +377,9 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 v[e] = apply_activation_t<EPI>(x + bias4[e], m, n + e, p.N, p.ep);
               }
             }
-            if (vec_ok) *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+            if (F16 && p.c_half) {                        // fp16 output: N % 4 == 0 and aligned rows are launch requirements
+              if (vec_ok) p_store4(Cg, (int64_t)m * p.ldc, n, v, true);
+            } else if (vec_ok) *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
             else
 #pragma unroll
               for (int e = 0; e < 4; ++e) if (n + e < p.N) crow[e] = v[e];
@@ -399,11 +425,11 @@ bool pair_make_map_mn(CUtensorMap* map, const float* base, int64_t cols, int64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false>
+template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false>
 int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + P_EPI_WARPS * 32 * P_EPI_LD * 4 + 256 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
-  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI, AMN, BMN>;
+  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI, AMN, BMN, F16>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -465,6 +491,50 @@ int dasa_gemm_tc_pair(int bn, int M, int N, int K, float alpha, const float* A, 
   if (!pair_make_map(&ta[0], A, M, K, lda, P_BM) || !pair_make_map(&tb[0], B, N, K, ldb, bn / 2)) return DASA_ERR_UNSUPPORTED;
   ta[1] = ta[0]; tb[1] = tb[0];
   return launch_pair<256, 5>(ta, tb, p, epilogue, st);
+}
+
+// fp16 operands (both K-major): C = epilogue(A B^T + bias), C fp32 or fp16. Forward-only GEMMs of the frozen transformer stack.
+namespace {
+bool pair_make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(dasa_tensormap_encoder());
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * P_BK), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+bool dasa_gemm_f16_pair_supported(int M, int N, int K) {
+  return M > 0 && N > 0 && K >= 2 * P_BK && (K % 8) == 0 && dasa_tensormap_encoder() != nullptr && dasa_gemm_pair_plan(M, N, K) == 256;
+}
+
+int dasa_gemm_tc_pair_f16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                          int c_half, int epilogue, const EpiParams& ep, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K < 2 * P_BK) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(A) || !dasa_aligned16(B) || !dasa_aligned16(C) || (lda & 7) || (ldb & 7) || (ldc & 3) || (c_half && (N & 3)))
+    return DASA_ERR_BAD_ALIGN;
+  ++g_gemm_routes[DASA_ROUTE_PAIR_F16];
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.C[0] = p.C[1] = static_cast<float*>(C); p.ldc = ldc; p.ep = ep;
+  p.c_half = c_half ? 1 : 0;
+  p.tiles_n = (int)dasa_cdiv(N, 256);
+  p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  p.splits = 1; p.kb_per_split = (int)dasa_cdiv(K, 2 * P_BK); p.split_stride = 0;
+  p.tiles_total = p.tiles_mn;
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta[2], tb[2];
+  if (!pair_make_map_f16(&ta[0], A, M, K, lda, P_BM) || !pair_make_map_f16(&tb[0], B, N, K, ldb, 128)) return DASA_ERR_UNSUPPORTED;
+  ta[1] = ta[0]; tb[1] = tb[0];
+  switch (epilogue) {
+    case DASA_EPI_NONE: return launch_pair_e<256, 5, DASA_EPI_NONE, false, false, true>(ta, tb, p, st);
+    case DASA_EPI_BIAS: return launch_pair_e<256, 5, DASA_EPI_BIAS, false, false, true>(ta, tb, p, st);
+    case DASA_EPI_BIAS_GELU: return launch_pair_e<256, 5, DASA_EPI_BIAS_GELU, false, false, true>(ta, tb, p, st);
+    default: return DASA_ERR_UNSUPPORTED;
+  }
 }
 
 // Operand layouts other than (K-major, K-major): C = alpha * op(A) * op(B) + beta * C with an MN-major A ([K][M] in memory)

@@ -155,7 +155,7 @@ def call(name, *args):
 
 
 ROUTES = ("skinny", "pair", "pair_mn", "pair_mn_splitk", "pair_grouped", "tc_single", "simt_tf32_mode", "simt_misaligned",
-          "simt_fp32")
+          "simt_fp32", "pair_f16")
 
 
 def gemm_route_counts(reset=False):

@@ -554,8 +554,11 @@ class DicModel(nn.Module):
     # fused [3*hid, hid] QKV weights (one GEMM instead of three); rebuilt when the parameters change version
     def _qkv(self, att, which="qkv"):
         key = (id(att), which)
+        # the raw-pointer optimizer (which does not bump tensor versions) only ever touches these weights in the finetune
+        # configuration; in the train configuration the stack is frozen and the fused copies (and their fp16 twins) live on
+        epoch = Fn.weights_epoch() if (self.update_add_layer and att.query.weight.requires_grad) else -1
         ver = (att.query.weight._version, att.key.weight._version, att.value.weight._version,
-               att.query.weight.data_ptr(), Fn.weights_epoch())
+               att.query.weight.data_ptr(), epoch)
         hit = self._qkv_cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]
@@ -578,50 +581,91 @@ class DicModel(nn.Module):
         m, s = self._mask(tag, (pack.nseq // self._steps, pack.L, y.shape[-1]), training, y.device)   # tests: padded masks
         return (None, 1.0) if m is None else (m.reshape(-1, y.shape[-1])[pack.rows64].contiguous(), s)
 
-    def _out_ln(self, out_mod, x, resid, tag, training, pack=None):
-        y = ops.linear_fwd(x, out_mod.dense.weight, out_mod.dense.bias)
-        m, s = self._row_mask(tag, y, pack, training)
-        return ops.dropout_residual_layernorm(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias,
-                                              out_mod.LayerNorm.eps, m, s)
+    # ---- forward-only stack (train configuration: every output is detached, vilmodel.py:1377-1410). An activation travels as
+    # (fp32 tensor, fp16 copy or None): where the token count gives the CTA-pair kernel enough tiles, the GEMMs take the fp16 copy
+    # and fp16 weights (ops.linear_f16: tcgen05 kind::f16, twice the TF32 rate, the same 10-bit mantissa); the residual stream,
+    # LayerNorm, softmax and every accumulation stay fp32.
+    @staticmethod
+    def _rows_of(t):
+        return t.numel() // t.shape[-1]
 
-    def _self_att(self, att_mod, x, key_pad, tag, training, pack=None):
+    def _lin(self, act, w, b, epi=None, out_half=False):
+        x, x16 = act
+        src = x16 if x16 is not None else x
+        M = self._rows_of(src)
+        if x16 is not None and (x is None or ops.gemm_f16_supported(M, w.shape[0], w.shape[1])):
+            y = ops.linear_f16(x16.reshape(M, x16.shape[-1]), ops.half_weight(w), b, epi, out_half)
+            return y.view(tuple(x16.shape[:-1]) + (w.shape[0],))
+        assert not out_half
+        return ops.linear_fwd(x, w, b) if epi is None else ops.linear_fwd(x, w, b, epi)
+
+    def _half_ok(self, M, n_out, n_in):
+        return ops.gemm_f16_supported(M, n_out, n_in)
+
+    def _out_ln(self, out_mod, act, resid, tag, training, pack=None):
+        """dense -> dropout -> + resid -> LayerNorm (BertSelfOutput / BertOutput). Returns (out fp32, fp16 copy or None)."""
+        y = self._lin(act, out_mod.dense.weight, out_mod.dense.bias)
+        m, s = self._row_mask(tag, y, pack, training)
+        hid = y.shape[-1]
+        want16 = self._half_ok(self._rows_of(y), hid, hid)
+        r = ops.dropout_residual_layernorm(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias, out_mod.LayerNorm.eps, m, s,
+                                           half_copy=want16)
+        return r if want16 else (r, None)
+
+    def _self_att(self, att_mod, act, key_pad, tag, training, pack=None):
         cfg = self.cfg
         hid = cfg.bert_hidden
+        x = act[0]
         w, b = self._qkv(att_mod.self)
-        qkv = ops.linear_fwd(x, w, b)
+        qkv = self._lin(act, w, b)
+        f16 = act[1] is not None and self._half_ok(self._rows_of(x), hid, hid)      # context in fp16 for the output projection
         if pack is not None:                     # x [ntok, hid]: only valid tokens, no key padding left to mask
             m, s = self._mask(tag + ".probs", (pack.nseq // self._steps, cfg.bert_heads, pack.L, pack.L), training, x.device)
             o = ops.mha_fwd_varlen(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], cfg.bert_heads, pack.pair, pack.pair,
-                                   pack.L, pack.L, m, s)
-            return self._out_ln(att_mod.output, o, x, tag + ".out", training, pack)
+                                   pack.L, pack.L, m, s, out_half=f16)
+            return self._out_ln(att_mod.output, (None, o) if f16 else (o, None), x, tag + ".out", training, pack)
         B, L = x.shape[0], x.shape[1]
         m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, L, L), training, x.device)
-        o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s)
-        return self._out_ln(att_mod.output, o, x, tag + ".out", training)
+        o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s, out_half=f16)
+        return self._out_ln(att_mod.output, (None, o) if f16 else (o, None), x, tag + ".out", training)
 
-    def _cross_att(self, xatt, x, ctx, key_pad, tag, training, q_pack=None, k_pack=None):
+    def _cross_att(self, xatt, act, act_ctx, key_pad, tag, training, q_pack=None, k_pack=None):
         """q_pack: x is the packed language stream (ctx dense); k_pack: ctx is the packed language stream (x dense)."""
         cfg = self.cfg
         hid = cfg.bert_hidden
-        q = ops.linear_fwd(x, xatt.att.query.weight, xatt.att.query.bias)
+        x, ctx = act[0], act_ctx[0]
+        q = self._lin(act, xatt.att.query.weight, xatt.att.query.bias)
         w, b = self._qkv(xatt.att, "kv")
-        kv = ops.linear_fwd(ctx, w, b)
+        kv = self._lin(act_ctx, w, b)
+        f16 = act[1] is not None and self._half_ok(self._rows_of(x), hid, hid)
         if q_pack is not None or k_pack is not None:
             pk = q_pack or k_pack
             Lq = pk.L if q_pack is not None else x.shape[1]
             Lk = pk.L if k_pack is not None else ctx.shape[1]
             m, s = self._mask(tag + ".probs", (pk.nseq // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
             o = ops.mha_fwd_varlen(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, q_pack.pair if q_pack else None,
-                                   k_pack.pair if k_pack else None, Lq, Lk, m, s)
-            return self._out_ln(xatt.output, o, x, tag + ".out", training, q_pack)
+                                   k_pack.pair if k_pack else None, Lq, Lk, m, s, out_half=f16)
+            return self._out_ln(xatt.output, (None, o) if f16 else (o, None), x, tag + ".out", training, q_pack)
         B, Lq, Lk = x.shape[0], x.shape[1], ctx.shape[1]
         m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
-        o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s)
-        return self._out_ln(xatt.output, o, x, tag + ".out", training)
+        o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s, out_half=f16)
+        return self._out_ln(xatt.output, (None, o) if f16 else (o, None), x, tag + ".out", training)
 
-    def _ffn(self, inter_mod, out_mod, x, tag, training, pack=None):
-        y = ops.linear_fwd(x, inter_mod.dense.weight, inter_mod.dense.bias, ops.EPI_BIAS_GELU)
-        return self._out_ln(out_mod, y, x, tag, training, pack)
+    def _ffn(self, inter_mod, out_mod, act, tag, training, pack=None):
+        x = act[0]
+        w1 = inter_mod.dense.weight
+        M = self._rows_of(x)
+        f16 = act[1] is not None and self._half_ok(M, w1.shape[0], w1.shape[1]) and self._half_ok(M, w1.shape[1], w1.shape[0])
+        if f16:     # the [M, 3072] GELU intermediate only ever exists as fp16 (half the bytes written and re-read)
+            y16 = self._lin((None, act[1]), w1, inter_mod.dense.bias, ops.EPI_BIAS_GELU, out_half=True)
+            return self._out_ln(out_mod, (None, y16), x, tag, training, pack)
+        y = ops.linear_fwd(x, w1, inter_mod.dense.bias, ops.EPI_BIAS_GELU)
+        return self._out_ln(out_mod, (y, None), x, tag, training, pack)
+
+    def _act(self, x):
+        """(fp32, fp16 copy) of a stream entering the stack."""
+        hid = x.shape[-1]
+        return (x, ops.to_half(x)) if self._half_ok(self._rows_of(x), hid, hid) else (x, None)
 
     @torch.no_grad()
     def language_stack(self, input_ids, pad_mask, training, steps=1, pack=None):
@@ -640,11 +684,12 @@ class DicModel(nn.Module):
                                 e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps, m, s)
         if pack is not None:                     # drop the padding rows: everything below runs on valid tokens only
             x = ops.gather_rows(x.view(B * L, -1), pack.rows)
+        act = self._act(x)
         for i, layer in enumerate(self.lalayer):
-            a = self._self_att(layer.attention, x, pad_mask, "enc.la%d.att" % i, training, pack)
-            x = self._ffn(layer.intermediate, layer.output, a, "enc.la%d.ffn" % i, training, pack)
+            a = self._self_att(layer.attention, act, pad_mask, "enc.la%d.att" % i, training, pack)
+            act = self._ffn(layer.intermediate, layer.output, a, "enc.la%d.ffn" % i, training, pack)
         self._steps = 1
-        return x
+        return act[0]
 
     _steps = 1
 
@@ -671,6 +716,7 @@ class DicModel(nn.Module):
         m, s = self._mask("enc.visn", (v.shape[0] // self._steps,) + tuple(v.shape[1:]), training, v.device)
         visn = ops.dropout_residual_layernorm(v, None, ve.visn_layer_norm.weight, ve.visn_layer_norm.bias, 1e-12,
                                               None, 1.0, m, s)
+        lang, visn = self._act(lang), self._act(visn)
         for i, layer in enumerate(self.addlayer):
             t = "enc.vl%d" % i
             l1 = self._cross_att(layer.visual_attention, lang, visn, None, t + ".x_lv", training, q_pack=pack)
@@ -679,7 +725,7 @@ class DicModel(nn.Module):
             v2 = self._self_att(layer.visn_self_att, v1, None, t + ".vs", training)
             lang = self._ffn(layer.lang_inter, layer.lang_output, l2, t + ".lo", training, pack)
             visn = self._ffn(layer.visn_inter, layer.visn_output, v2, t + ".vo", training)
-        return lang, visn
+        return lang[0], visn[0]
 
 
 def _dicmodel_grad_methods():

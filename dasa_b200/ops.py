@@ -137,6 +137,37 @@ def transposed_weight(w):
     return wt
 
 
+half_stack = True      # frozen transformer stack (forward-only): fp16 operands on the kind::f16 tensor-core path where the shapes allow
+
+
+def gemm_f16_supported(M, N, K):
+    """True when dasa_gemm_f16 takes the shape (enough 256 x 256 tiles for the CTA-pair kernel) under the tensor-core precision."""
+    return half_stack and _precision == PREC_TF32 and bool(lib.load().dasa_gemm_f16_supported(int(M), int(N), int(K)))
+
+
+def linear_f16(x16, w16, bias=None, epilogue=None, out_half=False):
+    """y[M, N] = epilogue(x16[M, K] w16[N, K]^T + bias) on the fp16-operand tcgen05 kernel; y fp32, or fp16 with out_half."""
+    assert x16.dtype == torch.float16 and w16.dtype == torch.float16 and x16.dim() == 2 and w16.dim() == 2
+    assert x16.stride(1) == 1 and w16.stride(1) == 1
+    M, K = x16.shape
+    N = w16.shape[0]
+    epi = epilogue if epilogue is not None else (EPI_BIAS if bias is not None else EPI_NONE)
+    y = torch.empty(M, N, device=x16.device, dtype=torch.float16 if out_half else torch.float32)
+    e = lib.Epilogue()
+    e.bias = _p(bias)
+    call("dasa_gemm_f16", M, N, K, _p(x16), x16.stride(0), _p(w16), w16.stride(0), _p(y), y.stride(0), int(out_half), int(epi),
+         ctypes.byref(e), _stream())
+    return y
+
+
+def to_half(x):
+    """fp16 copy of a contiguous fp32 tensor (dasa_f32_to_f16)."""
+    x = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    call("dasa_f32_to_f16", _p(x), _p(out), x.numel(), _stream())
+    return out
+
+
 _half_cache = {}
 
 
@@ -144,7 +175,9 @@ def half_weight(w):
     """fp16 copy of a (derived) weight tensor, cached while `w` itself is alive and unchanged. `w` is normally the output of
     stacked_weights / transposed_weight, which are rebuilt when a parameter changes, so the identity of `w` is the cache tag."""
     key = id(w)
-    tag = (w._version, weights_epoch, w.data_ptr())
+    # frozen tensors (requires_grad False: the detached transformer stack and weights derived from it) are not touched by the
+    # raw-pointer optimizer, so the per-step epoch does not invalidate their copies; an in-place load bumps _version
+    tag = (w._version, weights_epoch if w.requires_grad else -1, w.data_ptr())
     hit = _half_cache.get(key)
     if hit is not None and hit[0] == tag and hit[2]() is w:
         return hit[1]
@@ -453,9 +486,11 @@ def embed_layernorm(ids, word, pos, type0, gamma, beta, eps, mask=None, scale=1.
 
 
 def dropout_residual_layernorm(x, resid, gamma, beta, eps, mask=None, scale=1.0, post_mask=None, post_scale=1.0,
-                               save=False):
+                               save=False, half_copy=False):
+    """half_copy: also return an fp16 copy of the output ([R, Hd] contiguous, the A operand of the next fp16 GEMM)."""
     x2, R, Hd, ldx = _rows(x)
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    out16 = torch.empty(x.shape, device=x.device, dtype=torch.float16) if half_copy else None
     o2, _, _, ldo = _rows_out(out)
     r2, ldr = None, 0
     if resid is not None:
@@ -463,7 +498,9 @@ def dropout_residual_layernorm(x, resid, gamma, beta, eps, mask=None, scale=1.0,
     stats = torch.empty(R, 2, device=x.device, dtype=torch.float32) if save else None
     z = torch.empty(R, Hd, device=x.device, dtype=torch.float32) if save else None
     call("dasa_dropout_residual_layernorm", _p(x2), ldx, _p(mask), float(scale), _p(r2), ldr, _p(gamma), _p(beta), float(eps),
-         _p(post_mask), float(post_scale), _p(o2), ldo, _p(stats), _p(z), R, Hd, _stream())
+         _p(post_mask), float(post_scale), _p(o2), ldo, _p(stats), _p(z), _p(out16), R, Hd, _stream())
+    if half_copy:
+        return out, out16
     return (out, stats, z) if save else out
 
 
@@ -476,33 +513,35 @@ def layernorm_bwd(dout, z, gamma, stats, dgamma, dbeta, mask=None, scale=1.0, po
     return (dx if dx is not None else dresid), dresid
 
 
-def mha_fwd(q, k, v, heads, key_pad=None, drop_mask=None, drop_scale=1.0, save_probs=False):
-    """q [B,Lq,Hd] / k,v [B,Lk,Hd] views with unit inner stride (slices of a fused QKV buffer are fine)."""
+def mha_fwd(q, k, v, heads, key_pad=None, drop_mask=None, drop_scale=1.0, save_probs=False, out_half=False):
+    """q [B,Lq,Hd] / k,v [B,Lk,Hd] views with unit inner stride (slices of a fused QKV buffer are fine). out_half: the context
+    is written as fp16 (forward-only; the A operand of the fp16 output projection)."""
     B, Lq, Hd = q.shape
     Lk = k.shape[1]
     dh = Hd // heads
-    out = torch.empty(B, Lq, Hd, device=q.device, dtype=torch.float32)
+    out = torch.empty(B, Lq, Hd, device=q.device, dtype=torch.float16 if out_half else torch.float32)
     probs = torch.empty(B, heads, Lq, Lk, device=q.device, dtype=torch.float32) if save_probs else None
     if key_pad is not None and key_pad.dtype != torch.uint8:
         key_pad = key_pad.to(torch.uint8)
     call("dasa_mha_fwd", _p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1), v.stride(0),
          _p(key_pad), key_pad.stride(0) if key_pad is not None else 0, _p(drop_mask), float(drop_scale), _p(out), out.stride(1),
-         out.stride(0), _p(probs), B, heads, Lq, Lk, dh, _precision, _stream())
+         out.stride(0), _p(probs), B, heads, Lq, Lk, dh, _precision, int(out_half), _stream())
     return (out, probs) if save_probs else out
 
 
-def mha_fwd_varlen(q, k, v, heads, q_pack=None, k_pack=None, max_lq=None, max_lk=None, drop_mask=None, drop_scale=1.0):
+def mha_fwd_varlen(q, k, v, heads, q_pack=None, k_pack=None, max_lq=None, max_lk=None, drop_mask=None, drop_scale=1.0,
+                   out_half=False):
     """Attention over packed operands. q: [Nq, Hd] packed (q_pack = (off, len) int32 tensors) or dense [B, Lq, Hd] (q_pack None);
     k, v likewise. Returns out laid out like q."""
     Hd = q.shape[-1]
     dh = Hd // heads
     if q_pack is not None:
         B = q_pack[0].numel()
-        out = torch.empty(q.shape[0], Hd, device=q.device, dtype=torch.float32)
+        out = torch.empty(q.shape[0], Hd, device=q.device, dtype=torch.float16 if out_half else torch.float32)
         ldq, ldo, sq = q.stride(0), Hd, 0
     else:
         B, max_lq = q.shape[0], q.shape[1]
-        out = torch.empty(B, max_lq, Hd, device=q.device, dtype=torch.float32)
+        out = torch.empty(B, max_lq, Hd, device=q.device, dtype=torch.float16 if out_half else torch.float32)
         ldq, ldo, sq = q.stride(1), Hd, q.stride(0)
     if k_pack is not None:
         ldk, ldv, skv = k.stride(0), v.stride(0), 0
@@ -512,7 +551,7 @@ def mha_fwd_varlen(q, k, v, heads, q_pack=None, k_pack=None, max_lq=None, max_lk
         assert v.stride(0) == k.stride(0)
     call("dasa_mha_fwd_varlen", _p(q), ldq, _p(q_pack[0]) if q_pack else None, _p(q_pack[1]) if q_pack else None, _p(k), ldk,
          _p(v), ldv, _p(k_pack[0]) if k_pack else None, _p(k_pack[1]) if k_pack else None, sq, skv, _p(drop_mask),
-         float(drop_scale), _p(out), ldo, B, heads, int(max_lq), int(max_lk), dh, _precision, _stream())
+         float(drop_scale), _p(out), ldo, B, heads, int(max_lq), int(max_lk), dh, _precision, int(out_half), _stream())
     return out
 
 

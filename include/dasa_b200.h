@@ -22,6 +22,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+typedef unsigned short dasa_half_t;                   /* IEEE binary16 bits */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -90,9 +92,19 @@ enum { DASA_ROUTE_SKINNY = 0,          /* gemm_skinny.cu: M <= 32 weight-streami
        DASA_ROUTE_SIMT_TF32_MODE = 6,  /* FFMA kernel under DASA_PREC_TF32 for a layout / size the tensor kernels do not take (e.g. K < 32) */
        DASA_ROUTE_SIMT_MISALIGNED = 7, /* FFMA kernel under DASA_PREC_TF32 ONLY because of operand alignment: a performance bug */
        DASA_ROUTE_SIMT_FP32 = 8,       /* FFMA kernel, DASA_PREC_FP32 requested                                          */
-       DASA_ROUTE_COUNT = 9 };
+       DASA_ROUTE_PAIR_F16 = 9,        /* gemm_tc2.cu: fp16 operands, tcgen05 kind::f16 (dasa_gemm_f16)                 */
+       DASA_ROUTE_COUNT = 10 };
 int dasa_debug_gemm_route_counts(int64_t* out, int n, int reset);
 
+/* C[M, N] = epilogue(A[M, K] B[N, K]^T (+ bias)) with IEEE fp16 operands (both K-major, leading dimensions in elements, multiples of
+ * 8) on the persistent CTA-pair tcgen05 kernel with kind::f16 (twice the TF32 rate), fp32 accumulation. c_half = 0: C is float
+ * [M, ldc]; 1: C is fp16 [M, ldc] (N % 4 == 0) - the activation of the next fp16 GEMM. epilogue: DASA_EPI_NONE / _BIAS / _BIAS_GELU.
+ * Used for the forward-only GEMMs of the frozen transformer stack (vilmodel.py:1370-1410: 9 language + 3 cross-modal layers,
+ * detached in the train configuration): fp16 keeps TF32's 10 mantissa bits, so inside fp16's normal range the products are the
+ * TF32 kernel's. dasa_gemm_f16_supported: 1 when the shape has enough 256 x 256 tiles for this kernel (else use dasa_gemm).     */
+int dasa_gemm_f16_supported(int M, int N, int K);
+int dasa_gemm_f16(int M, int N, int K, const dasa_half_t* A, int64_t lda, const dasa_half_t* B, int64_t ldb, void* C, int64_t ldc,
+                  int c_half, int epilogue, const dasa_epilogue_t* epi, void* stream);
 size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
 /* 1 when dasa_gemm(DASA_PREC_TF32) runs this operand-layout combination on the tensor cores directly: always for two K-major
  * operands; for an MN-major A ([K][M] in memory) and / or B ([K][N]) when the problem is large enough for the persistent CTA-pair
@@ -274,7 +286,6 @@ int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* args, void* workspace
  * Dropout: m_hprev / m_h1 are [T, B, H] keep masks (NULL = eval), scale = 1/(1-p); emb and feat arrive already dropped.
  * Requirements: H % 16 == 0, (E+F+H) % 32 == 0, NK % 32 == 0, D % 4 == 0, F % 4 == 0, V, L <= 128, B <= 32, shift_k <= 15;
  * dasa_decoder_rollout_supported() says whether the shared-memory plan fits (else use the per-op entry points).      */
-typedef unsigned short dasa_half_t;                   /* IEEE binary16 bits                                                */
 /* out[i] = fp16(in[i]) (round to nearest even), n elements; in 16-byte aligned when n >= 8. Used for the decoder kernel's weights. */
 int dasa_f32_to_f16(const float* in, dasa_half_t* out, int64_t n, void* stream);
 typedef struct {
@@ -356,7 +367,8 @@ int dasa_embed_layernorm(const int64_t* ids, int64_t ld_ids, int B, int L, int H
 int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, const uint8_t* drop_mask, float drop_scale,
                                     const float* resid, int64_t ldr, const float* gamma, const float* beta, float eps,
                                     const uint8_t* post_mask, float post_scale, float* out, int64_t ldo,
-                                    float* stats_out, float* z_out, int R, int Hd, void* stream);
+                                    float* stats_out, float* z_out, dasa_half_t* out_half, int R, int Hd, void* stream);
+/* out_half (optional): an fp16 copy of `out`, [R, Hd] contiguous - the A operand of the next dasa_gemm_f16.            */
 /* backward of the above (finetune config): given dout -> dresid (gradient w.r.t. z, i.e. w.r.t. the residual input) and
  * dx (gradient w.r.t. x, = dresid * mask*scale); ACCUMULATES dgamma/dbeta (atomics).                                */
 int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* z, const float* gamma, const float* stats,
@@ -371,7 +383,8 @@ int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* z, const fl
 int dasa_mha_fwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                  int64_t ldv, int64_t sv, const uint8_t* key_pad, int64_t ld_pad, const uint8_t* drop_mask,
                  float drop_scale, float* out, int64_t ldo, int64_t so, float* probs_out,
-                 int B, int heads, int Lq, int Lk, int dh, int precision, void* stream);
+                 int B, int heads, int Lq, int Lk, int dh, int precision, int out_half, void* stream);
+/* out_half != 0 (forward-only, probs_out NULL): `out` receives IEEE halves (ldo / so in halves) for dasa_gemm_f16.      */
 int dasa_mha_bwd(const float* q, int64_t ldq, int64_t sq, const float* k, int64_t ldk, int64_t sk, const float* v,
                  int64_t ldv, int64_t sv, const float* probs, const uint8_t* drop_mask, float drop_scale,
                  const float* dout, int64_t ldo, int64_t so, float* dq, int64_t lddq, int64_t sdq, float* dk,
@@ -386,7 +399,7 @@ int dasa_mha_fwd_varlen(const float* q, int64_t ldq, const int32_t* q_off, const
                         int64_t ldk, const float* v, int64_t ldv, const int32_t* k_off, const int32_t* k_len,
                         int64_t dense_q_stride, int64_t dense_kv_stride, const uint8_t* drop_mask, float drop_scale,
                         float* out, int64_t ldo, int B, int heads, int max_Lq, int max_Lk, int dh, int precision,
-                        void* stream);
+                        int out_half, void* stream);
 /* dst[r,:] = src[idx[r],:] for r < R (C % 4 == 0): packs the valid tokens of a padded [B*L, C] activation             */
 int dasa_gather_rows(const float* src, int64_t ld_src, const int32_t* idx, float* dst, int64_t ld_dst, int R, int C,
                      void* stream);

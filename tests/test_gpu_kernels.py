@@ -923,3 +923,37 @@ class ReversePackedFn(torch.autograd.Function):
         dx = torch.zeros(pack.ntok, g.shape[2], device=g.device)
         dx[rows] = g[ok]
         return dx, None, None
+
+
+# ------------------------------------------------------------------------------------- fp16-operand tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,epi,half_out", [(19810, 3072, 768, "gelu", True), (5003, 768, 3072, "bias", False),
+                                                (7000, 2304, 768, "bias", False), (3000, 1536, 768, "none", False)])
+def test_gemm_f16_pair(M, N, K, epi, half_out):
+    """dasa_gemm_f16 (tcgen05 kind::f16, CTA-pair kernel) against fp64 on the SAME fp16-rounded operands: products of fp16 values
+    are exact in the fp32 accumulator, so only the accumulation order separates the two (1e-5); the fp16 output adds its own
+    2^-11 rounding."""
+    import math
+    from dasa_b200 import lib, ops
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g)).to(DEV)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV) if epi != "none" else None
+    a16, w16 = ops.to_half(a), ops.to_half(w)
+    assert torch.equal(a16, a.half()) and torch.equal(w16, w.half())
+    ops.set_precision("tf32")
+    lib.load().dasa_debug_gemm_pair(2)
+    lib.gemm_route_counts(reset=True)
+    try:
+        y = ops.linear_f16(a16, w16, b, ops.EPI_BIAS_GELU if epi == "gelu" else None, out_half=half_out)
+        torch.cuda.synchronize()
+    finally:
+        lib.load().dasa_debug_gemm_pair(1)
+        ops.set_precision("fp32")
+    assert lib.gemm_route_counts(reset=True)["pair_f16"] == 1
+    ref = a16.double() @ w16.double().t()
+    if b is not None:
+        ref = ref + b.double()
+    if epi == "gelu":
+        ref = 0.5 * ref * (1.0 + torch.erf(ref / math.sqrt(2.0)))
+    e = rel_err(y, ref)
+    assert e <= (1e-3 if half_out else 1e-5), e
