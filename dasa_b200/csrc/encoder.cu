@@ -3,6 +3,7 @@
 // (sample, head), everything resident in shared memory), token reversal. The dense projections go through dasa_gemm.
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace {
 
@@ -78,8 +79,14 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(const int64_t* __r
   }
 }
 
+// In-place dropout draws (rng.cuh) instead of a materialised mask: keep flag of element [row, c] = stream byte row * Hd + c.
+struct LnStream { const unsigned long long* seed_dev; unsigned long long seed, base; uint32_t thr; int on; };
+
+// XH: x holds IEEE halves (ldx in halves) - the fp16 output of the preceding dasa_gemm_f16
+template <bool XH>
 __global__ void __launch_bounds__(128) dropout_residual_layernorm_kernel(
-    const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ mask, float scale, const float* __restrict__ resid,
+    const void* __restrict__ x_, int64_t ldx, const uint8_t* __restrict__ mask, LnStream st, float scale,
+    const float* __restrict__ resid,
     int64_t ldr, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, const uint8_t* __restrict__ post_mask,
     float post_scale, float* __restrict__ out, int64_t ldo, float* __restrict__ stats_out, float* __restrict__ z_out,
     __half* __restrict__ out_half, int R, int Hd) {
@@ -87,15 +94,30 @@ __global__ void __launch_bounds__(128) dropout_residual_layernorm_kernel(
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   const int n4 = Hd >> 2;
+  DropStream ds;
+  ds.thr = st.thr; ds.base = st.base;
+  ds.mixed = st.on ? mix_seed(st.seed_dev ? st.seed_dev[0] : st.seed) : 0ull;
   RowVec z;
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
     const int j = lane + 32 * i;
     if (j < n4) {
-      float4 v = reinterpret_cast<const float4*>(x + (int64_t)row * ldx)[j];
+      float4 v;
+      if (XH) {
+        const uint2 raw = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x_) + (int64_t)row * ldx)[j];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        v = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + (int64_t)row * ldx)[j];
+      }
       if (mask != nullptr) {
         const float4 m = mask_f4(mask + (int64_t)row * Hd + 4 * j, scale);
         v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      } else if (st.on) {
+        const uint32_t k4 = stream_keep4(ds, (uint64_t)row * n4 + j);
+        v.x *= (k4 & 1u) ? scale : 0.f; v.y *= (k4 & 2u) ? scale : 0.f;
+        v.z *= (k4 & 4u) ? scale : 0.f; v.w *= (k4 & 8u) ? scale : 0.f;
       }
       if (resid != nullptr) {
         const float4 r = reinterpret_cast<const float4*>(resid + (int64_t)row * ldr)[j];
@@ -123,6 +145,90 @@ __global__ void __launch_bounds__(128) dropout_residual_layernorm_kernel(
         __half2 h[2] = {__floats2half2_rn(o.x, o.y), __floats2half2_rn(o.z, o.w)};
         reinterpret_cast<uint2*>(out_half + (int64_t)row * Hd)[j] = *reinterpret_cast<uint2*>(h);
       }
+    }
+  }
+}
+
+// Forward-only fast path of the frozen stack for Hd = 128 * NV (768 -> NV = 6): exact vector count (no per-vector guards),
+// every load of the row requested before the first use, dropout + residual as one FMA per element, the normalisation as
+// two FMAs per element ((x * rstd - mean * rstd) * gamma + beta), hash words advanced by addition (rng.cuh: (w + 1) * G).
+template <bool XH, int NV>
+__global__ void __launch_bounds__(128) ln_fwd_fast_kernel(
+    const void* __restrict__ x_, int64_t ldx, const uint8_t* __restrict__ mask, LnStream st, float scale,
+    const float* __restrict__ resid, int64_t ldr, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    float* __restrict__ out, int64_t ldo, __half* __restrict__ out_half, int R) {
+  constexpr int Hd = 128 * NV, n4 = 32 * NV;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  float4 v[NV], r[NV];
+  uint32_t mk[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    if (XH) {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x_) + (int64_t)row * ldx) + j);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+      v[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      v[i] = ldg_stream4(reinterpret_cast<const float*>(x_) + (int64_t)row * ldx + 4 * j);
+    }
+    r[i] = resid != nullptr ? ldg_stream4(resid + (int64_t)row * ldr + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mask != nullptr) mk[i] = *reinterpret_cast<const uint32_t*>(mask + (int64_t)row * Hd + 4 * j);
+  }
+  if (mask != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x = fmaf(v[i].x, (mk[i] & 0xFFu) ? scale : 0.f, r[i].x);
+      v[i].y = fmaf(v[i].y, (mk[i] & 0xFF00u) ? scale : 0.f, r[i].y);
+      v[i].z = fmaf(v[i].z, (mk[i] & 0xFF0000u) ? scale : 0.f, r[i].z);
+      v[i].w = fmaf(v[i].w, (mk[i] & 0xFF000000u) ? scale : 0.f, r[i].w);
+    }
+  } else if (st.on) {
+    const uint64_t mixed = mix_seed(st.seed_dev ? st.seed_dev[0] : st.seed);
+    uint64_t zg = (st.base + (uint64_t)row * n4 + lane + 1) * 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      uint64_t z = mixed ^ zg;
+      zg += 32ull * 0x9E3779B97F4A7C15ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      const uint32_t lo = (uint32_t)z, hi = (uint32_t)(z >> 32);
+      v[i].x = fmaf(v[i].x, ((lo & 0xFFFFu) >= st.thr) ? scale : 0.f, r[i].x);
+      v[i].y = fmaf(v[i].y, ((lo >> 16) >= st.thr) ? scale : 0.f, r[i].y);
+      v[i].z = fmaf(v[i].z, ((hi & 0xFFFFu) >= st.thr) ? scale : 0.f, r[i].z);
+      v[i].w = fmaf(v[i].w, ((hi >> 16) >= st.thr) ? scale : 0.f, r[i].w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i].x += r[i].x; v[i].y += r[i].y; v[i].z += r[i].z; v[i].w += r[i].w; }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.f / Hd);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a;
+    a = v[i].x - mean; q = fmaf(a, a, q); a = v[i].y - mean; q = fmaf(a, a, q);
+    a = v[i].z - mean; q = fmaf(a, a, q); a = v[i].w - mean; q = fmaf(a, a, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / Hd) + eps);
+  const float nm = -mean * rstd;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j), b = __ldg(reinterpret_cast<const float4*>(beta) + j);
+    float4 o;
+    o.x = fmaf(fmaf(v[i].x, rstd, nm), g.x, b.x); o.y = fmaf(fmaf(v[i].y, rstd, nm), g.y, b.y);
+    o.z = fmaf(fmaf(v[i].z, rstd, nm), g.z, b.z); o.w = fmaf(fmaf(v[i].w, rstd, nm), g.w, b.w);
+    stg_stream4(out + (int64_t)row * ldo + 4 * j, o);
+    if (out_half != nullptr) {
+      __half2 h[2] = {__floats2half2_rn(o.x, o.y), __floats2half2_rn(o.z, o.w)};
+      reinterpret_cast<uint2*>(out_half + (int64_t)row * Hd)[j] = *reinterpret_cast<uint2*>(h);
     }
   }
 }
@@ -867,10 +973,44 @@ extern "C" int dasa_dropout_residual_layernorm(const float* x, int64_t ldx, cons
       !dasa_aligned16(gamma) || !dasa_aligned16(beta) || (drop_mask && reinterpret_cast<uintptr_t>(drop_mask) % 4) ||
       (post_mask && reinterpret_cast<uintptr_t>(post_mask) % 4) || (z_out && !dasa_aligned16(z_out)))
     return DASA_ERR_BAD_ALIGN;
-  dropout_residual_layernorm_kernel<<<(unsigned)dasa_cdiv(R, 4), 128, 0, (cudaStream_t)stream>>>(
-      x, ldx, drop_mask, drop_scale, resid, ldr, gamma, beta, eps, post_mask, post_scale, out, ldo, stats_out, z_out,
-      reinterpret_cast<__half*>(out_half), R, Hd);
+  dropout_residual_layernorm_kernel<false><<<(unsigned)dasa_cdiv(R, 4), 128, 0, (cudaStream_t)stream>>>(
+      x, ldx, drop_mask, LnStream{nullptr, 0ull, 0ull, 0u, 0}, drop_scale, resid, ldr, gamma, beta, eps, post_mask, post_scale, out,
+      ldo, stats_out, z_out, reinterpret_cast<__half*>(out_half), R, Hd);
   return dasa_check_launch("dropout_residual_layernorm_kernel");
+}
+
+extern "C" int dasa_dropout_residual_layernorm_fwd(const void* x, int x_half, int64_t ldx, const uint8_t* drop_mask,
+                                                   const uint64_t* drop_seed_dev, uint64_t drop_seed, uint64_t drop_base,
+                                                   float drop_p, float drop_scale, const float* resid, int64_t ldr,
+                                                   const float* gamma, const float* beta, float eps, float* out, int64_t ldo,
+                                                   dasa_half_t* out_half, int R, int Hd, void* stream) {
+  if (R <= 0) return DASA_OK;
+  if (!ln_shape_ok(Hd)) return DASA_ERR_BAD_SHAPE;
+  if (!(x_half ? (reinterpret_cast<uintptr_t>(x) % 8 == 0 && ldx % 4 == 0) : (dasa_aligned16(x) && ldx % 4 == 0)) ||
+      (resid && (!dasa_aligned16(resid) || ldr % 4)) || !dasa_aligned16(out) || ldo % 4 || !dasa_aligned16(gamma) ||
+      !dasa_aligned16(beta) || (drop_mask && reinterpret_cast<uintptr_t>(drop_mask) % 4) ||
+      (out_half && reinterpret_cast<uintptr_t>(out_half) % 8))
+    return DASA_ERR_BAD_ALIGN;
+  const bool on = drop_mask == nullptr && drop_p > 0.f;
+  const LnStream st{reinterpret_cast<const unsigned long long*>(drop_seed_dev), (unsigned long long)drop_seed,
+                    (unsigned long long)drop_base, (uint32_t)(drop_p * 65536.0f), on ? 1 : 0};
+  const float scale = (drop_mask != nullptr || on) ? drop_scale : 1.f;
+  const unsigned grid = (unsigned)dasa_cdiv(R, 4);
+  if (Hd == 768) {
+    auto kern = x_half ? ln_fwd_fast_kernel<true, 6> : ln_fwd_fast_kernel<false, 6>;
+    kern<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ldx, drop_mask, st, scale, resid, ldr, gamma, beta, eps, out, ldo,
+                                                 reinterpret_cast<__half*>(out_half), R);
+    return dasa_check_launch("ln_fwd_fast_kernel");
+  }
+  if (x_half)
+    dropout_residual_layernorm_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        x, ldx, drop_mask, st, scale, resid, ldr, gamma, beta, eps, nullptr, 1.f, out, ldo, nullptr, nullptr,
+        reinterpret_cast<__half*>(out_half), R, Hd);
+  else
+    dropout_residual_layernorm_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        x, ldx, drop_mask, st, scale, resid, ldr, gamma, beta, eps, nullptr, 1.f, out, ldo, nullptr, nullptr,
+        reinterpret_cast<__half*>(out_half), R, Hd);
+  return dasa_check_launch("dropout_residual_layernorm_kernel(fwd)");
 }
 
 extern "C" int dasa_layernorm_bwd(const float* dout, int64_t lddo, const float* z, const float* gamma, const float* stats,

@@ -2,6 +2,7 @@
 // (agent_dg.py:832-886), fused RMSprop + gradient clipping (agent_dg.py:1389-1405).
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace {
 
@@ -56,24 +57,6 @@ __global__ void __launch_bounds__(256) axpy2d_kernel(float a, const float* __res
     float* dst = y + (int64_t)r * ldy + c;
     *dst = accumulate ? *dst + v : v;
   }
-}
-
-// The seed goes through its own avalanche round before the element index is folded in. (Adding the raw seed to
-// (idx + 1) * G made "seed + G" the same stream shifted by one element: the per-replay seed bump of a captured graph produced
-// masks correlated with the previous iteration's.)
-__device__ __forceinline__ uint64_t mix_seed(uint64_t seed) {
-  uint64_t s = (seed ^ 0x2545F4914F6CDD1Dull) * 0xD6E8FEB86659FD93ull;
-  s = (s ^ (s >> 32)) * 0xD6E8FEB86659FD93ull;
-  return s ^ (s >> 32);
-}
-
-// 16 keep flags per thread: four 64-bit hashes, one byte lane each 16 bits -> one 128-bit store
-// (splitmix64-style finaliser over mixed_seed ^ counter)
-__device__ __forceinline__ uint64_t hash64(uint64_t mixed_seed, uint64_t idx) {
-  uint64_t z = mixed_seed ^ ((idx + 1) * 0x9E3779B97F4A7C15ull);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
 }
 
 __device__ __forceinline__ void mask_fill(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t raw_seed, uint64_t offset) {

@@ -91,6 +91,17 @@ class DropoutSource:
 
     POOL_BYTES = 16 << 20
 
+    def stream(self, nbytes, p, training):
+        """In-place draws for a forward-only dropout site (nothing re-reads the mask): reserves `nbytes` stream bytes and returns
+        (ops.DropStream, scale); (None, 1.0) in eval mode. Only without injected masks - tests that inject masks get tensors
+        from mask() / mask_steps()."""
+        assert self.injected is None
+        if not training or p <= 0.0:
+            return None, 1.0
+        base = self.counter
+        self.counter += (int(nbytes) + 3) // 4
+        return ops.DropStream(self.seed_dev, self.seed, base, p), 1.0 / (1.0 - p)
+
 
 _source = DropoutSource()
 
@@ -569,8 +580,11 @@ class DicModel(nn.Module):
         self._qkv_cache[key] = (ver, w, b)
         return w, b
 
-    def _row_mask(self, tag, y, pack, training):
-        """Dropout mask for a [.., hid] activation: padded per-step shape, or one row per packed token."""
+    def _row_mask(self, tag, y, pack, training, stream_ok=False):
+        """Dropout mask for a [.., hid] activation: padded per-step shape, or one row per packed token. stream_ok: the consumer
+        can draw the flags itself (ops.DropStream) - used unless a test injects masks."""
+        if stream_ok and _source.injected is None and ops.stream_dropout:
+            return _source.stream(y.numel(), self.cfg.bert_dropout, training)
         if pack is None:
             return self._mask(tag, (y.shape[0] // self._steps,) + tuple(y.shape[1:]), training, y.device)
         p = self.cfg.bert_dropout
@@ -604,29 +618,50 @@ class DicModel(nn.Module):
 
     def _out_ln(self, out_mod, act, resid, tag, training, pack=None):
         """dense -> dropout -> + resid -> LayerNorm (BertSelfOutput / BertOutput). Returns (out fp32, fp16 copy or None)."""
-        y = self._lin(act, out_mod.dense.weight, out_mod.dense.bias)
-        m, s = self._row_mask(tag, y, pack, training)
+        w = out_mod.dense.weight
+        src = act[1] if act[1] is not None else act[0]
+        y16 = ops.half_ln_input and act[1] is not None and (act[0] is None or self._half_ok(self._rows_of(src), w.shape[0], w.shape[1]))
+        y = self._lin(act, w, out_mod.dense.bias, out_half=bool(y16))      # fp16 branch output: read once by the LayerNorm below
+        m, s = self._row_mask(tag, y, pack, training, stream_ok=True)
         hid = y.shape[-1]
         want16 = self._half_ok(self._rows_of(y), hid, hid)
-        r = ops.dropout_residual_layernorm(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias, out_mod.LayerNorm.eps, m, s,
-                                           half_copy=want16)
+        r = ops.dropout_residual_layernorm_fwd(y, resid, out_mod.LayerNorm.weight, out_mod.LayerNorm.bias, out_mod.LayerNorm.eps,
+                                               m, s, half_copy=want16)
         return r if want16 else (r, None)
+
+    def _probs_drop(self, tag, B, Lq, Lk, training, device, h16):
+        """Keep flags of the attention-probability dropout: drawn inside the fp16 attention kernel (ops.DropStream) unless a
+        test injects masks; a [B, heads, Lq, Lk] uint8 mask otherwise."""
+        heads = self.cfg.bert_heads
+        if h16 and _source.injected is None and ops.stream_dropout:
+            return _source.stream(ops.mha_h16_stream_bytes(B, heads, Lq, Lk), self.cfg.bert_dropout, training)
+        return self._mask(tag, (B // self._steps, heads, Lq, Lk), training, device)
 
     def _self_att(self, att_mod, act, key_pad, tag, training, pack=None):
         cfg = self.cfg
         hid = cfg.bert_hidden
         x = act[0]
         w, b = self._qkv(att_mod.self)
-        qkv = self._lin(act, w, b)
         f16 = act[1] is not None and self._half_ok(self._rows_of(x), hid, hid)      # context in fp16 for the output projection
+        # fp16 Q / K / V straight from the projection's epilogue -> the fp16 attention kernel (dh = 64)
+        h16 = f16 and ops.half_attention and self._half_ok(self._rows_of(x), 3 * hid, hid) and hid // cfg.bert_heads == 64
+        qkv = self._lin(act, w, b, out_half=h16)
         if pack is not None:                     # x [ntok, hid]: only valid tokens, no key padding left to mask
-            m, s = self._mask(tag + ".probs", (pack.nseq // self._steps, cfg.bert_heads, pack.L, pack.L), training, x.device)
-            o = ops.mha_fwd_varlen(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], cfg.bert_heads, pack.pair, pack.pair,
-                                   pack.L, pack.L, m, s, out_half=f16)
+            m, s = self._probs_drop(tag + ".probs", pack.nseq, pack.L, pack.L, training, x.device, h16)
+            if h16:
+                o = ops.mha_fwd_h16(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], cfg.bert_heads, pack.pair, pack.pair,
+                                    pack.L, pack.L, None, m, s)
+            else:
+                o = ops.mha_fwd_varlen(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], cfg.bert_heads, pack.pair, pack.pair,
+                                       pack.L, pack.L, m, s, out_half=f16)
             return self._out_ln(att_mod.output, (None, o) if f16 else (o, None), x, tag + ".out", training, pack)
         B, L = x.shape[0], x.shape[1]
-        m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, L, L), training, x.device)
-        o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s, out_half=f16)
+        m, s = self._probs_drop(tag + ".probs", B, L, L, training, x.device, h16)
+        if h16:
+            o = ops.mha_fwd_h16(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad=key_pad,
+                                drop=m, drop_scale=s)
+        else:
+            o = ops.mha_fwd(qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:], cfg.bert_heads, key_pad, m, s, out_half=f16)
         return self._out_ln(att_mod.output, (None, o) if f16 else (o, None), x, tag + ".out", training)
 
     def _cross_att(self, xatt, act, act_ctx, key_pad, tag, training, q_pack=None, k_pack=None):
@@ -634,21 +669,30 @@ class DicModel(nn.Module):
         cfg = self.cfg
         hid = cfg.bert_hidden
         x, ctx = act[0], act_ctx[0]
-        q = self._lin(act, xatt.att.query.weight, xatt.att.query.bias)
         w, b = self._qkv(xatt.att, "kv")
-        kv = self._lin(act_ctx, w, b)
         f16 = act[1] is not None and self._half_ok(self._rows_of(x), hid, hid)
+        h16 = (f16 and ops.half_attention and act_ctx[1] is not None and self._half_ok(self._rows_of(ctx), 2 * hid, hid)
+               and hid // cfg.bert_heads == 64)
+        q = self._lin(act, xatt.att.query.weight, xatt.att.query.bias, out_half=h16)
+        kv = self._lin(act_ctx, w, b, out_half=h16)
         if q_pack is not None or k_pack is not None:
             pk = q_pack or k_pack
             Lq = pk.L if q_pack is not None else x.shape[1]
             Lk = pk.L if k_pack is not None else ctx.shape[1]
-            m, s = self._mask(tag + ".probs", (pk.nseq // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
-            o = ops.mha_fwd_varlen(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, q_pack.pair if q_pack else None,
-                                   k_pack.pair if k_pack else None, Lq, Lk, m, s, out_half=f16)
+            m, s = self._probs_drop(tag + ".probs", pk.nseq, Lq, Lk, training, x.device, h16)
+            if h16:
+                o = ops.mha_fwd_h16(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, q_pack.pair if q_pack else None,
+                                    k_pack.pair if k_pack else None, Lq, Lk, None, m, s)
+            else:
+                o = ops.mha_fwd_varlen(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, q_pack.pair if q_pack else None,
+                                       k_pack.pair if k_pack else None, Lq, Lk, m, s, out_half=f16)
             return self._out_ln(xatt.output, (None, o) if f16 else (o, None), x, tag + ".out", training, q_pack)
         B, Lq, Lk = x.shape[0], x.shape[1], ctx.shape[1]
-        m, s = self._mask(tag + ".probs", (B // self._steps, cfg.bert_heads, Lq, Lk), training, x.device)
-        o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s, out_half=f16)
+        m, s = self._probs_drop(tag + ".probs", B, Lq, Lk, training, x.device, h16)
+        if h16:
+            o = ops.mha_fwd_h16(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad=key_pad, drop=m, drop_scale=s)
+        else:
+            o = ops.mha_fwd(q, kv[..., :hid], kv[..., hid:], cfg.bert_heads, key_pad, m, s, out_half=f16)
         return self._out_ln(xatt.output, (None, o) if f16 else (o, None), x, tag + ".out", training)
 
     def _ffn(self, inter_mod, out_mod, act, tag, training, pack=None):

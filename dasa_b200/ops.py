@@ -138,6 +138,9 @@ def transposed_weight(w):
 
 
 half_stack = True      # frozen transformer stack (forward-only): fp16 operands on the kind::f16 tensor-core path where the shapes allow
+half_attention = True  # ... and fp16 Q / K / V into the fp16 attention kernel (dasa_mha_fwd_h16)
+half_ln_input = True   # ... and the fp16 output of the dense projections into the residual LayerNorm
+stream_dropout = True  # forward-only dropout sites of that stack draw their keep flags in the consuming kernel (DropStream)
 
 
 def gemm_f16_supported(M, N, K):
@@ -553,6 +556,93 @@ def mha_fwd_varlen(q, k, v, heads, q_pack=None, k_pack=None, max_lq=None, max_lk
          _p(v), ldv, _p(k_pack[0]) if k_pack else None, _p(k_pack[1]) if k_pack else None, sq, skv, _p(drop_mask),
          float(drop_scale), _p(out), ldo, B, heads, int(max_lq), int(max_lk), dh, _precision, int(out_half), _stream())
     return out
+
+
+class DropStream:
+    """Dropout keep flags drawn in place by the consuming kernel (csrc/rng.cuh) instead of read from a mask tensor: stream
+    byte e = 16-bit lane e & 3 of hash(seed, base + e // 4) >= p * 65536. `dropout_mask((n,), p, seed, base)` (n % 16 == 0)
+    materialises the same bytes."""
+    __slots__ = ("seed_dev", "seed", "base", "p")
+
+    def __init__(self, seed_dev, seed, base, p):
+        self.seed_dev, self.seed, self.base, self.p = seed_dev, int(seed), int(base), float(p)
+
+
+def _drop_args(drop):
+    """(mask ptr, seed_dev ptr, seed, base, p) of a keep-mask tensor, a DropStream or None."""
+    if drop is None:
+        return None, None, 0, 0, 0.0
+    if isinstance(drop, DropStream):
+        return None, _p(drop.seed_dev), drop.seed & 0xFFFFFFFFFFFFFFFF, drop.base, drop.p
+    assert drop.dtype == torch.uint8 and drop.is_contiguous()
+    return _p(drop), None, 0, 0, 0.0
+
+
+def mha_h16_stream_bytes(B, heads, max_lq, max_lk):
+    """Stream bytes dasa_mha_fwd_h16 consumes for its in-place probability dropout."""
+    return B * heads * ((max_lq + 15) // 16) * (2 * ((max_lk + 15) // 16)) * 128
+
+
+def mha_h16_stream_index(B, heads, max_lq, max_lk, device="cpu"):
+    """int64 [B, heads, max_lq, max_lk]: the stream byte holding the keep flag of probability [b, h, r, j] (include/dasa_b200.h:
+    dasa_mha_fwd_h16). Tests use it to materialise the mask the kernel draws."""
+    nMT, nNT = (max_lq + 15) // 16, 2 * ((max_lk + 15) // 16)
+    b = torch.arange(B, device=device).view(B, 1, 1, 1)
+    h = torch.arange(heads, device=device).view(1, heads, 1, 1)
+    r = torch.arange(max_lq, device=device).view(1, 1, max_lq, 1)
+    j = torch.arange(max_lk, device=device).view(1, 1, 1, max_lk)
+    lane = (r % 8) * 4 + (j % 8) // 2
+    tile = ((b * heads + h) * nMT + r // 16) * nNT + j // 8
+    return (tile * 32 + lane) * 4 + 2 * (j % 2) + (r % 16) // 8
+
+
+def mha_fwd_h16(q, k, v, heads, q_pack=None, k_pack=None, max_lq=None, max_lk=None, key_pad=None, drop=None, drop_scale=1.0,
+                out_half=True):
+    """Forward-only attention on fp16 q / k / v (dasa_mha_fwd_h16). q: [Nq, Hd] packed (q_pack = (off, len)) or dense
+    [B, Lq, Hd]; k, v likewise (slices of a fused fp16 QKV buffer are fine). drop: uint8 keep mask [B, heads, max_lq, max_lk],
+    an ops.DropStream (flags drawn in the kernel) or None. Returns the context laid out like q (fp16, or fp32)."""
+    assert q.dtype == torch.float16 and k.dtype == torch.float16 and v.dtype == torch.float16
+    Hd = q.shape[-1]
+    dh = Hd // heads
+    odt = torch.float16 if out_half else torch.float32
+    if q_pack is not None:
+        B = q_pack[0].numel()
+        out = torch.empty(q.shape[0], Hd, device=q.device, dtype=odt)
+        ldq, ldo, sq, so = q.stride(0), Hd, 0, 0
+    else:
+        B, max_lq = q.shape[0], q.shape[1]
+        out = torch.empty(B, max_lq, Hd, device=q.device, dtype=odt)
+        ldq, ldo, sq, so = q.stride(1), Hd, q.stride(0), max_lq * Hd
+    if k_pack is not None:
+        ldk, ldv, skv = k.stride(0), v.stride(0), 0
+    else:
+        max_lk = k.shape[1]
+        ldk, ldv, skv = k.stride(1), v.stride(1), k.stride(0)
+        assert v.stride(0) == k.stride(0)
+    if key_pad is not None and key_pad.dtype != torch.uint8:
+        key_pad = key_pad.to(torch.uint8)
+    mp, sp, seed, base, p = _drop_args(drop)
+    call("dasa_mha_fwd_h16", _p(q), ldq, sq, _p(q_pack[0]) if q_pack else None, _p(q_pack[1]) if q_pack else None, _p(k), ldk,
+         _p(v), ldv, skv, _p(k_pack[0]) if k_pack else None, _p(k_pack[1]) if k_pack else None, _p(key_pad),
+         key_pad.stride(0) if key_pad is not None else 0, mp, sp, seed, base, p, float(drop_scale), _p(out), ldo, so,
+         int(out_half), B, heads, int(max_lq), int(max_lk), dh, _stream())
+    return out
+
+
+def dropout_residual_layernorm_fwd(x, resid, gamma, beta, eps, drop=None, scale=1.0, half_copy=False):
+    """Forward-only dropout -> + resid -> LayerNorm (dasa_dropout_residual_layernorm_fwd): x fp32 or fp16 (the c_half output of
+    the fp16 GEMM), drop = uint8 keep mask shaped like x, an ops.DropStream or None. Returns out fp32 (and its fp16 copy)."""
+    x2, R, Hd, ldx = _rows(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    out16 = torch.empty(x.shape, device=x.device, dtype=torch.float16) if half_copy else None
+    o2, _, _, ldo = _rows_out(out)
+    r2, ldr = None, 0
+    if resid is not None:
+        r2, _, _, ldr = _rows(resid)
+    mp, sp, seed, base, p = _drop_args(drop)
+    call("dasa_dropout_residual_layernorm_fwd", _p(x2), int(x.dtype == torch.float16), ldx, mp, sp, seed, base, p, float(scale),
+         _p(r2), ldr, _p(gamma), _p(beta), float(eps), _p(o2), ldo, _p(out16), R, Hd, _stream())
+    return (out, out16) if half_copy else out
 
 
 def gather_rows(src2d, idx_i32, out=None):

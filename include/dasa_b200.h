@@ -400,6 +400,30 @@ int dasa_mha_fwd_varlen(const float* q, int64_t ldq, const int32_t* q_off, const
                         int64_t dense_q_stride, int64_t dense_kv_stride, const uint8_t* drop_mask, float drop_scale,
                         float* out, int64_t ldo, int B, int heads, int max_Lq, int max_Lk, int dh, int precision,
                         int out_half, void* stream);
+/* The same attention on fp16 operands for the frozen (forward-only) stack, dh = 64 (vilmodel.py:203-236, 479-506, outputs
+ * detached at :1377-1410): q / k / v are IEEE halves as written by dasa_gemm_f16 with c_half = 1 (leading dimensions and sample
+ * strides in halves, multiples of 8; fused QKV buffers are addressed in place), packed (off / len) or dense (NULL) per operand
+ * like dasa_mha_fwd_varlen. Persistent CTAs, 2-stage cp.async ring over the (sample, head) units, mma.sync m16n8k16, fp32
+ * softmax. Probability dropout: `drop_mask` (uint8 keep mask [B, heads, max_Lq, max_Lk], tests) or, when it is NULL and
+ * drop_p > 0, keep flags drawn in place from the counter-hash stream (seed read from drop_seed_dev when non-NULL, else
+ * drop_seed; hash index base drop_base): the flags of probability [b, h, r, j] are stream byte
+ *   ((((b*heads + h)*nMT + r/16)*nNT + j/8)*32 + (r%8)*4 + (j%8)/2)*4 + 2*(j%2) + (r%16)/8,  nMT = ceil(max_Lq/16),
+ *   nNT = 2*ceil(max_Lk/16), i.e. byte i of dasa_dropout_mask(mask, n, p, seed, drop_base). out: fp16 (out_half) or fp32.        */
+int dasa_mha_fwd_h16(const dasa_half_t* q, int64_t ldq, int64_t sq, const int32_t* q_off, const int32_t* q_len,
+                     const dasa_half_t* k, int64_t ldk, const dasa_half_t* v, int64_t ldv, int64_t skv,
+                     const int32_t* k_off, const int32_t* k_len, const uint8_t* key_pad, int64_t ld_pad,
+                     const uint8_t* drop_mask, const uint64_t* drop_seed_dev, uint64_t drop_seed, uint64_t drop_base,
+                     float drop_p, float drop_scale, void* out, int64_t ldo, int64_t so, int out_half, int B, int heads,
+                     int max_Lq, int max_Lk, int dh, void* stream);
+/* Forward-only dropout -> + resid -> LayerNorm of the frozen stack (vilmodel.py:246-250, 305-309): like
+ * dasa_dropout_residual_layernorm without the backward outputs, x optionally fp16 (x_half: halves, ldx in halves - the
+ * c_half output of dasa_gemm_f16) and the keep flags either from `drop_mask` or, when it is NULL and drop_p > 0, drawn in
+ * place: element [row, c] = stream byte row*Hd + c of (seed, drop_base) (see dasa_mha_fwd_h16). */
+int dasa_dropout_residual_layernorm_fwd(const void* x, int x_half, int64_t ldx, const uint8_t* drop_mask,
+                                        const uint64_t* drop_seed_dev, uint64_t drop_seed, uint64_t drop_base,
+                                        float drop_p, float drop_scale, const float* resid, int64_t ldr,
+                                        const float* gamma, const float* beta, float eps, float* out, int64_t ldo,
+                                        dasa_half_t* out_half, int R, int Hd, void* stream);
 /* dst[r,:] = src[idx[r],:] for r < R (C % 4 == 0): packs the valid tokens of a padded [B*L, C] activation             */
 int dasa_gather_rows(const float* src, int64_t ld_src, const int32_t* idx, float* dst, int64_t ld_dst, int R, int C,
                      void* stream);

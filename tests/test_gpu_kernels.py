@@ -957,3 +957,114 @@ def test_gemm_f16_pair(M, N, K, epi, half_out):
         ref = 0.5 * ref * (1.0 + torch.erf(ref / math.sqrt(2.0)))
     e = rel_err(y, ref)
     assert e <= (1e-3 if half_out else 1e-5), e
+
+
+# ------------------------------------------------------------------------- fp16 attention + in-place dropout (frozen stack)
+def _round16(n):
+    return (n + 15) // 16 * 16
+
+
+@pytest.mark.parametrize("stream", [False, True])
+def test_mha_h16_matches_fp32_kernel(stream):
+    """dasa_mha_fwd_h16 (fp16 q/k/v, persistent cp.async ring, m16n8k16) against the exact-fp32 attention kernel on the SAME
+    fp16-representable inputs: packed self-attention, packed q over dense views, dense q over packed keys, dense with key_pad.
+    stream=True: the kernel draws its own keep flags; the reference gets the mask materialised from the same stream through
+    the documented index map. Bound 3e-3 (P rounded to fp16 before P.V; everything else fp32)."""
+    gen = g(91)
+    B, L, V, heads, dh = 7, 45, 36, 12, 64
+    Hd = heads * dh
+    lens = torch.randint(3, L + 1, (B,), generator=gen)
+    lens[0], lens[1] = L, 1
+    pad = (torch.arange(L)[None, :] >= lens[:, None]).to(DEV)
+    x = torch.randn(B, L, 3 * Hd, generator=gen).half()
+    vis = torch.randn(B, V, 3 * Hd, generator=gen).half()
+    rows = torch.cat([torch.arange(n) + b * L for b, n in enumerate(lens.tolist())]).to(DEV)
+    off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)[:-1]]).int().to(DEV)
+    len32 = lens.int().to(DEV)
+    xh, vh = x.to(DEV), vis.to(DEV)
+    xf, vf = xh.float(), vh.float()
+    xp = xh.view(B * L, -1)[rows].contiguous()
+    p, seed, base = 0.1, 4242, 1000
+
+    def drop(Lq, Lk):
+        n = ops.mha_h16_stream_bytes(B, heads, Lq, Lk)
+        assert n % 16 == 0
+        flat = ops.dropout_mask((n,), p, seed, base)
+        km = flat[ops.mha_h16_stream_index(B, heads, Lq, Lk, DEV)].contiguous()
+        assert 0.85 < float(km.float().mean()) < 0.95
+        return km, (ops.DropStream(None, seed, base, p) if stream else km)
+
+    ops.set_precision("fp32")
+    km, d = drop(L, L)
+    ref = ops.mha_fwd(xf[..., :Hd], xf[..., Hd:2 * Hd], xf[..., 2 * Hd:], heads, pad, km, 1 / 0.9)
+    got = ops.mha_fwd_h16(xp[:, :Hd], xp[:, Hd:2 * Hd], xp[:, 2 * Hd:], heads, (off, len32), (off, len32), L, L, None, d, 1 / 0.9)
+    assert got.dtype == torch.float16
+    assert_close(got.float(), ref.view(B * L, Hd)[rows], 3e-3, "packed q and k")
+    got32 = ops.mha_fwd_h16(xp[:, :Hd], xp[:, Hd:2 * Hd], xp[:, 2 * Hd:], heads, (off, len32), (off, len32), L, L, None, d, 1 / 0.9,
+                            out_half=False)
+    assert_close(got32, ref.view(B * L, Hd)[rows], 3e-3, "packed q and k, fp32 out")
+    km, d = drop(L, V)
+    ref = ops.mha_fwd(xf[..., :Hd], vf[..., Hd:2 * Hd], vf[..., 2 * Hd:], heads, None, km, 1 / 0.9)
+    got = ops.mha_fwd_h16(xp[:, :Hd], vh[..., Hd:2 * Hd], vh[..., 2 * Hd:], heads, (off, len32), None, L, V, None, d, 1 / 0.9)
+    assert_close(got.float(), ref.view(B * L, Hd)[rows], 3e-3, "packed q, dense k")
+    km, d = drop(V, L)
+    ref = ops.mha_fwd(vf[..., :Hd], xf[..., Hd:2 * Hd], xf[..., 2 * Hd:], heads, pad, km, 1 / 0.9)
+    got = ops.mha_fwd_h16(vh[..., :Hd], xp[:, Hd:2 * Hd], xp[:, 2 * Hd:], heads, None, (off, len32), V, L, None, d, 1 / 0.9)
+    assert_close(got.float(), ref, 3e-3, "dense q, packed k")
+    got = ops.mha_fwd_h16(vh[..., :Hd], xh[..., Hd:2 * Hd], xh[..., 2 * Hd:], heads, key_pad=pad, drop=d, drop_scale=1 / 0.9)
+    assert_close(got.float(), ref, 3e-3, "dense q, dense k + key_pad")
+    # no dropout (eval)
+    ref = ops.mha_fwd(vf[..., :Hd], vf[..., Hd:2 * Hd], vf[..., 2 * Hd:], heads)
+    got = ops.mha_fwd_h16(vh[..., :Hd], vh[..., Hd:2 * Hd], vh[..., 2 * Hd:], heads)
+    assert_close(got.float(), ref, 3e-3, "views, eval")
+
+
+def test_mha_h16_many_units_and_long_keys():
+    """More (sample, head) units than resident CTAs (the ring wraps, prefetch of the next unit under the current one) and 80-key
+    instructions (5 key blocks)."""
+    gen = g(92)
+    B, L, heads, dh = 300, 80, 12, 64
+    Hd = heads * dh
+    lens = torch.randint(8, L + 1, (B,), generator=gen)
+    lens[5] = L
+    rows = torch.cat([torch.arange(n) + b * L for b, n in enumerate(lens.tolist())]).to(DEV)
+    off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)[:-1]]).int().to(DEV)
+    len32 = lens.int().to(DEV)
+    xp = (torch.randn(int(lens.sum()), 3 * Hd, generator=gen) * 0.7).half().to(DEV)
+    xpad = torch.zeros(B * L, 3 * Hd, device=DEV)
+    xpad[rows] = xp.float()
+    xpad = xpad.view(B, L, 3 * Hd)
+    pad = (torch.arange(L)[None, :] >= lens[:, None]).to(DEV)
+    ops.set_precision("fp32")
+    ref = ops.mha_fwd(xpad[..., :Hd], xpad[..., Hd:2 * Hd], xpad[..., 2 * Hd:], heads, pad)
+    got = ops.mha_fwd_h16(xp[:, :Hd], xp[:, Hd:2 * Hd], xp[:, 2 * Hd:], heads, (off, len32), (off, len32), L, L)
+    assert_close(got.float(), ref.view(B * L, Hd)[rows], 3e-3, "300 x 12 units")
+
+
+@pytest.mark.parametrize("x_half", [False, True])
+@pytest.mark.parametrize("Hd", [768, 256])
+def test_layernorm_fwd_stream_dropout_bit_equal_to_mask(x_half, Hd):
+    """dasa_dropout_residual_layernorm_fwd: in-place draws == the materialised mask of the same stream, bit for bit; fp16 x; and
+    both equal the training-path kernel (dasa_dropout_residual_layernorm) on the same mask."""
+    gen = g(93)
+    R = 1037
+    x = torch.randn(R, Hd, generator=gen).to(DEV)
+    if x_half:
+        x = x.half()
+    resid = torch.randn(R, Hd, generator=gen).to(DEV)
+    gamma, beta = torch.rand(Hd, generator=gen).to(DEV) + 0.5, torch.randn(Hd, generator=gen).to(DEV)
+    p, seed, base = 0.1, 99, 77
+    n = (R * Hd + 15) // 16 * 16
+    km = ops.dropout_mask((n,), p, seed, base)[:R * Hd].view(R, Hd)
+    a, a16 = ops.dropout_residual_layernorm_fwd(x, resid, gamma, beta, 1e-12, ops.DropStream(None, seed, base, p), 1 / 0.9, True)
+    b, b16 = ops.dropout_residual_layernorm_fwd(x, resid, gamma, beta, 1e-12, km.contiguous(), 1 / 0.9, True)
+    assert torch.equal(a, b) and torch.equal(a16, b16)
+    c = ops.dropout_residual_layernorm(x.float(), resid, gamma, beta, 1e-12, km.contiguous(), 1 / 0.9)
+    assert_close(a, c, 2e-6, "forward-only kernel (fused multiply-adds) vs the training-path kernel")
+    seed_dev = torch.tensor([seed], dtype=torch.int64, device=DEV)
+    d = ops.dropout_residual_layernorm_fwd(x, resid, gamma, beta, 1e-12, ops.DropStream(seed_dev, 0, base, p), 1 / 0.9)
+    assert torch.equal(a, d)
+    z = x.float() * km.float() / 0.9 + resid
+    ref = torch.nn.functional.layer_norm(z.double(), (Hd,), gamma.double(), beta.double(), 1e-12)
+    assert_close(a, ref, 2e-5, "LN")
+    assert_close(a16.float(), ref, 1e-3, "LN fp16 copy")
