@@ -109,9 +109,13 @@ __host__ __device__ __forceinline__ int dp_chunk_pitch(int D, int S) { return (i
 // wrow[i] (i < 2*RT) = this lane's W row for local row g + 8*i, already offset by 4*t halves. K % 32 == 0.
 // red: DP_WARPS*RT*MT*128 floats, res: 16*RT*8*MT floats (shared memory). Ends with a __syncthreads: res is complete.
 typedef __half wt_t;
-__device__ __forceinline__ uint2 ldg_w4(const wt_t* p) {          // 4 consecutive fp16 weights, read-only path, no L1 allocation
+// 4 consecutive fp16 weights, read-only path, no L1 allocation, L2 evict_last: the 46 MB weight stream is re-read by every action
+// of the rollout and should stay resident in the 126 MB L2 against the read-once panorama / instruction tiles (evict_first) -
+// without the hints the weights were fetched from DRAM again in every action (ncu: 59 MB of DRAM reads per action, L2 hit 52 %)
+__device__ __forceinline__ uint2 ldg_w4(const wt_t* p) {
   uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(l2_policy_evict_last()));
   return r;
 }
 // component j of 4 packed halves as a TF32 operand (the fp16 -> fp32 conversion is exact and already TF32-representable)
@@ -270,7 +274,7 @@ __device__ __forceinline__ void dp_issue_tile(float* tile, int pitch, uint64_t* 
     if (cn > 0)
       for (int r = lane; r < rows; r += 32)
         if (mask_b == nullptr || mask_b[r] == 0)
-          bulk_g2s(tile + (size_t)r * pitch, src_b + (int64_t)r * ld_row + c0, (uint32_t)cn * 4u, bar);
+          bulk_g2s_hint(tile + (size_t)r * pitch, src_b + (int64_t)r * ld_row + c0, (uint32_t)cn * 4u, bar, l2_policy_evict_first());
   }
 }
 

@@ -21,7 +21,28 @@ static inline EpiParams make_epi(const dasa_epilogue_t* e) {
   return p;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+// gelu(x) = x * 0.5 * (1 + erf(x / sqrt(2)))  (vilmodel.gelu, vilmodel.py:125-131) with erf from Abramowitz & Stegun 7.1.26:
+// erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1 / (1 + p z), |error| <= 1.5e-7 (fp32 rounding level). Branch-free, two
+// MUFU ops (rcp, ex2) + ~12 FMA-pipe instructions instead of erff's ~35 with a divergent branch: the erf epilogue of the
+// 256 x 256 GELU tiles took three times as long as their fp16 main loop (166 us for 20300 x 3072 x 768; profiles/r02_*).
+// With q = 0.5 * poly * exp(-z^2): x >= 0 -> x - x q, x < 0 -> x q (no cancellation in either tail) = max(x, 0) - |x| q.
+__device__ __forceinline__ float gelu_erf(float x) {
+#ifdef DASA_GELU_EXACT                                   // the exact-fp32 FFMA kernels (DASA_PREC_FP32) keep libm's erff
+  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+#endif
+  // raw MUFU approximations (rcp: the denominator is >= 1; ex2: the argument is <= 0 and a flushed denormal is an exact-enough
+  // zero) - the libm-conforming exp2f / division wrap each in a denormal rescue (3 + 4 more instructions per element)
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164190f, ax, 1.0f)));          // p / sqrt(2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * -0.72134752044448170f));      // exp(-x^2 / 2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float q = (0.5f * t) * poly * e;
+  return fmaf(-ax, q, fmaxf(x, 0.f));                       // x >= 0: x - x q;  x < 0: x q
+}
 
 // v = alpha*acc + beta*C already applied by the caller. Compile-time epilogue kind: each kernel instantiation carries
 // exactly one variant (a runtime switch inside the fully unrolled accumulator loops made the kernels instruction-fetch bound).

@@ -2,6 +2,7 @@
 // projection takes when its operands do not satisfy the TMA alignment rules of the tcgen05 kernel (gemm_tc.cu).
 // Register-tiled, double-buffered through registers, split-K with a deterministic two-pass reduction.
 #include "common.cuh"
+#define DASA_GELU_EXACT 1
 #include "gemm_common.cuh"
 
 namespace {

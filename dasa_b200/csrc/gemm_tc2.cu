@@ -140,8 +140,11 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // F16: both operands are IEEE fp16 in HBM (K-major, 64 elements = one 128-byte swizzle row per stage row), tcgen05 kind::f16 at
 // twice the TF32 rate, fp32 accumulate. fp16 carries TF32's 10 mantissa bits, so for operands inside fp16's normal range the
 // products equal the TF32 kernel's: used for the frozen, forward-only transformer stack, whose activations are O(1..100).
-template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+// EW: epilogue warps per CTA (8, or 16 = four per TMEM lane quarter, each draining a quarter of the tile's columns: the erf-GELU
+// epilogue is FMA-pipe work - ~10 fma-pipe instructions per element - that two warps per scheduler cannot overlap with their own
+// TMEM / shared-memory round trips; with four the tile's epilogue drops under its fp16 main loop).
+template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false, int EW = P_EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, PairParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -149,7 +152,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers of BN fp32 columns
   unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* stage_all = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_all + P_EPI_WARPS * 32 * P_EPI_LD);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_all + EW * 32 * P_EPI_LD);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;              // [2]
   uint64_t* tmem_empty = tmem_full + 2;                  // [2], the leader's copy is the one that counts
@@ -167,7 +170,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * P_EPI_WARPS); }   // every epilogue warp of both CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * EW); }   // every epilogue warp of both CTAs
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -253,10 +256,10 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue warps 2..9 (both CTAs)
+    // ---------------------------------------------------------------- epilogue warps 2 .. 2 + EW - 1 (both CTAs)
     const int q = warp & 3;                                // TMEM lane quarter this warp may read
-    const int chalf = (warp - 2) >> 2;                     // which half of the tile's columns
-    constexpr int CW = BN / 2;                             // columns per epilogue warp
+    const int chalf = (warp - 2) >> 2;                     // which slice of the tile's columns
+    constexpr int CW = BN / (EW / 4);                      // columns per epilogue warp
     float* stg = stage_all + (warp - 2) * 32 * P_EPI_LD;
     const int col4 = lane & 7, rsub = lane >> 3;           // read-back: 8 lanes x float4 per row, 4 rows per instruction
     const float alpha = p.alpha, beta = p.beta;
@@ -425,18 +428,18 @@ bool pair_make_map_mn(CUtensorMap* map, const float* base, int64_t cols, int64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false>
+template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false, int EW = P_EPI_WARPS>
 int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + P_EPI_WARPS * 32 * P_EPI_LD * 4 + 256 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + EW * 32 * P_EPI_LD * 4 + 256 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
-  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI, AMN, BMN, F16>;
+  auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI, AMN, BMN, F16, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { dasa_set_error("gemm_tf32_pair attr", e); return DASA_ERR_CUDA; }
     attr_set = true;
   }
-  kern<<<dim3(2u * (unsigned)p.num_pairs), P_THREADS, smem, st>>>(ta[0], tb[0], ta[1], tb[1], p);     // __cluster_dims__(2,1,1): one pair per TPC
+  kern<<<dim3(2u * (unsigned)p.num_pairs), 64 + 32 * EW, smem, st>>>(ta[0], tb[0], ta[1], tb[1], p);     // __cluster_dims__(2,1,1): one pair per TPC
   return dasa_check_launch("gemm_tf32_pair_kernel");
 }
 
@@ -532,7 +535,7 @@ int dasa_gemm_tc_pair_f16(int M, int N, int K, const void* A, int64_t lda, const
   switch (epilogue) {
     case DASA_EPI_NONE: return launch_pair_e<256, 5, DASA_EPI_NONE, false, false, true>(ta, tb, p, st);
     case DASA_EPI_BIAS: return launch_pair_e<256, 5, DASA_EPI_BIAS, false, false, true>(ta, tb, p, st);
-    case DASA_EPI_BIAS_GELU: return launch_pair_e<256, 5, DASA_EPI_BIAS_GELU, false, false, true>(ta, tb, p, st);
+    case DASA_EPI_BIAS_GELU: return launch_pair_e<256, 4, DASA_EPI_BIAS_GELU, false, false, true, 16>(ta, tb, p, st);
     default: return DASA_ERR_UNSUPPORTED;
   }
 }
