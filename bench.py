@@ -193,7 +193,7 @@ def micro_rooflines(peak_gbs):
 
     def add(name, bytes_, secs):
         out[name] = {"bound": "hbm", "achieved": bytes_ / secs / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": bytes_ / secs / 1e9 / peak_gbs, "batch": B}
+                     "frac": bytes_ / secs / 1e9 / peak_gbs, "frac_vs_8tbs_nominal": bytes_ / secs / 1e9 / 8000.0, "batch": B}
     t = timeit(lambda: ops.gate_modulate(g, f[..., :C], o[..., :C]))
     add("adain_gate_modulate", 4 * 3 * B * V * C, t)
     t = timeit(lambda: ops.adain_rows(f[..., :C], d[..., :C], 1e-5, o[..., :C]))
@@ -207,7 +207,7 @@ def micro_rooflines(peak_gbs):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         peaks = {}
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0)) / 2.0     # a kernel timed alone: the BURST bf16 figure / 2 (tf32)
     prec = ops.get_precision()
     ops.set_precision("tf32")
     W = torch.randn(C, C, device=dev) / C ** 0.5
@@ -221,6 +221,7 @@ def micro_rooflines(peak_gbs):
     ops.set_precision(prec)
     out["adain_gate_gemm_fused"] = {"bound": "tensor", "achieved": 2.0 * R * C * C / t / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                                     "frac": 2.0 * R * C * C / t / 1e12 / peak_tf, "batch": B,
+                                    "peak_source": "%s bf16_tflops (burst) / 2" % ("measured" if "bf16_tflops" in peaks else "fallback"),
                                     "what": "tcgen05 TF32 GEMM %d x %d x %d with the sigmoid-gate epilogue (f strided in place, keep mask, gate "
                                             "saved)" % (R, C, C)}
     del g, o, d, sgate, keep, W
@@ -288,7 +289,7 @@ def run_ours(args):
     state = {"graph_error": None}
 
     # e2e: every rollout's inputs come from pinned host memory. The copy of rollout i+1 runs on a side stream into a staging
-    # set while rollout i computes (one device-to-device hand-over per step); the first upload of a timed region is exposed.
+    # set while rollout i computes (one device-to-device hand-over per step).
     up = {"stream": None, "stage": None, "ready": None, "free": None, "pending": False}
 
     def start_upload():
@@ -321,8 +322,11 @@ def run_ours(args):
         return loss
 
     def timed(read_back, upload, steps, warmup):
+        # e2e (upload=True) is the steady state of the double-buffered pipeline: every step - warm-up steps included - starts the
+        # upload of its successor's inputs on the copy stream before it computes, so each timed step consumes an upload started one
+        # step earlier; the timed region starts `steps` uploads of its own and closes only after the last of them has landed.
         for _ in range(warmup):
-            one_step(ep_res, read_back, upload)
+            one_step(ep_res, read_back, upload, prefetch_next=upload)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -331,7 +335,9 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            one_step(ep_res, read_back, upload, prefetch_next=upload and i + 1 < steps)
+            one_step(ep_res, read_back, upload, prefetch_next=upload)
+        if upload:
+            torch.cuda.current_stream().wait_event(up["ready"])
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -759,23 +765,30 @@ def config3_arm(args, cfg, T, dev, world, rank, pol, tr_main, peaks):
 
 
 def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
-    """Event-time every dasa_gemm launch of one training rollout. The dominant kernel of the step is the persistent CTA-pair
-    tcgen05 TF32 GEMM (gemm_tf32_pair_kernel<256,5,*>, gemm_tc2.cu) on the token-major shapes of the transformer stack, the AdaIN
-    gate and the bi-LSTM input projections (M >= 2048 rows; ~40 % of the step in profiles/r01_ncu_launches_step3_summary.txt):
-    its tensor roofline = algorithmic FLOPs (2*M*N*K per launch) / summed duration. The M = batch (20-row) decoder GEMMs stream
-    their weights once per action and are reported against the HBM roofline."""
+    """Event-time every GEMM launch and the two decoder-rollout launches of one training rollout (eager launches, warm caches).
+    Dominant kernel of the step by device time (profiles/r02_ncu_launches_step_*_summary.txt): the persistent CTA-pair tcgen05 GEMM
+    gemm_tf32_pair_kernel<256,*> (gemm_tc2.cu) - its kind::f16 instantiations run the 78 forward GEMMs of the frozen transformer
+    stack, its kind::tf32 instantiations the trainable token-major GEMMs (AdaIN gate, bi-LSTM projections / recurrence, weight
+    gradients). Tensor roofline per family = algorithmic FLOPs (2*M*N*K per launch) / summed launch duration against the
+    measured sustained cuBLAS bf16 rate (fp16 operands) or half of it (tf32). The decoder's M = 20-row projections live inside
+    the persistent rollout kernels and are reported as a weight-stream (HBM / L2) figure."""
     from dasa_b200 import lib, modules as M
-    events = []
+    events, dec = [], []
     orig = lib.call
 
     def hooked(name, *a):
-        if name != "dasa_gemm":
+        if name not in ("dasa_gemm", "dasa_gemm_f16", "dasa_decoder_rollout_fwd", "dasa_decoder_rollout_bwd"):
             return orig(name, *a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = orig(name, *a)
         e1.record()
-        events.append((e0, e1, int(a[2]), int(a[3]), int(a[4])))
+        if name == "dasa_gemm":
+            events.append((e0, e1, int(a[2]), int(a[3]), int(a[4]), "tf32"))
+        elif name == "dasa_gemm_f16":
+            events.append((e0, e1, int(a[0]), int(a[1]), int(a[2]), "f16"))
+        else:
+            dec.append((e0, e1, name))
         return rc
     import dasa_b200.ops as ops_mod
     ops_mod.call = hooked
@@ -789,27 +802,56 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
         torch.cuda.synchronize()
     finally:
         ops_mod.call = orig
-    big = [(a.elapsed_time(b) * 1e-3, m, n, k) for a, b, m, n, k in events if m >= 2048]
-    small = [(a.elapsed_time(b) * 1e-3, m, n, k) for a, b, m, n, k in events if m < 2048]
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0       # TF32 dense peak = half the bf16 figure
-    secs = sum(t for t, _, _, _ in big)
-    flops = sum(2.0 * m * n * k for _, m, n, k in big)
-    ach = flops / max(secs, 1e-12) / 1e12
+    timed = [(a.elapsed_time(b) * 1e-3, m, n, k, kind) for a, b, m, n, k, kind in events]
+    f16 = [x for x in timed if x[4] == "f16"]
+    big = [x for x in timed if x[4] == "tf32" and x[1] >= 2048]
+    small = [x for x in timed if x[4] == "tf32" and x[1] < 2048]
+    peak16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    s_secs = sum(t for t, _, _, _ in small)
-    s_bytes = sum(4.0 * (n * k + m * k + m * n) for _, m, n, k in small)
-    return {"bound": "tensor", "kernel": "gemm_tf32_pair_kernel<256,5,*> (persistent CTA pair, tcgen05.mma cta_group::2 kind::tf32 256x256x8, "
-                                         "TMA 128B-swizzle operands, double-buffered TMEM accumulator), token-major GEMMs with M >= 2048",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            # ncu --set full, one launch M=20300 N=3072 K=768 GELU epilogue (profiles/r01_gemm_tf32_pair_ncu_full.txt):
-            # dram__bytes_read.sum + dram__bytes_write.sum; algorithmic bytes of that launch = 4*(M*K + N*K + M*N) = 321e6
-            "traffic": 267.2e6, "traffic_launch": "M=20300 N=3072 K=768 (algorithmic 321e6 B, 95.8 GFLOP)",
-            "launches_timed": len(big), "device_seconds": secs,
-            "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src,
-            "small_m_gemms": {"bound": "hbm", "what": "decoder / critic GEMMs with M = batch rows: weights streamed once per action",
-                              "achieved": s_bytes / max(s_secs, 1e-12) / 1e9, "peak": hbm, "unit": "GB/s",
-                              "frac": s_bytes / max(s_secs, 1e-12) / 1e9 / hbm, "launches_timed": len(small),
-                              "device_seconds": s_secs, "note": "eager launches, event-bracketed: includes launch gaps"}}
+
+    def fam(rows, peak, what):
+        secs = sum(t for t, _, _, _, _ in rows)
+        flops = sum(2.0 * m * n * k for _, m, n, k, _ in rows)
+        ach = flops / max(secs, 1e-12) / 1e12
+        return {"bound": "tensor", "what": what, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "launches_timed": len(rows), "device_seconds": secs}
+    fam16 = fam(f16, peak16, "kind::f16 instantiations: forward GEMMs of the frozen language / cross-modal stack (fp16 operands, fp32 accumulate)")
+    fam32 = fam(big, peak16 / 2.0, "kind::tf32 instantiations, token-major GEMMs with M >= 2048 (AdaIN gate, bi-LSTM, weight gradients)")
+    s_secs = sum(t for t, _, _, _, _ in small)
+    s_bytes = sum(4.0 * (n * k + m * k + m * n) for _, m, n, k, _ in small)
+    # decoder rollout kernels: per action the fp16 weight stream [linear_in ; linear_shift], [W_ih | W_hh], att.linear_in,
+    # att.linear_out (forward: as stored, backward: transposed copies) + the fp32 view / instruction-context tiles
+    cfg, B = pol.cfg, ep.B
+    H, E, F, D, V = cfg.hidden, cfg.action_emb, cfg.feat, cfg.ctx_dim, cfg.views
+    w_bytes = 2.0 * ((F + cfg.shift_kernel) * H + 4 * H * (E + F + H) + D * H + H * (D + H))
+    tile_bytes = 4.0 * (B * V * F + sum(ep.seq_lengths_host) * D)         # views + the valid instruction tokens of the B episodes
+    dec_out = {}
+    for e0, e1, name in dec:
+        secs = e0.elapsed_time(e1) * 1e-3
+        byt = (w_bytes + tile_bytes * (2.0 if name.endswith("bwd") else 1.0)) * T
+        dec_out[name.replace("dasa_", "")] = {"bound": "hbm", "achieved": byt / secs / 1e9, "peak": hbm, "unit": "GB/s",
+                                               "frac": byt / secs / 1e9 / hbm, "us_per_action": secs * 1e6 / T,
+                                               "bytes_per_action": byt / T}
+    # top-level = the family with the larger share of the step
+    top, other, top_name, other_name = (fam16, fam32, "f16", "tf32") if fam16["device_seconds"] >= fam32["device_seconds"] else \
+        (fam32, fam16, "tf32", "f16")
+    out = dict(top)
+    out.update({
+        "kernel": "gemm_tf32_pair_kernel<256,*> (persistent CTA pair, tcgen05.mma cta_group::2 256x256 tiles, TMA 128B-swizzle operands, "
+                  "double-buffered TMEM accumulator): %s family" % top_name,
+        # one `ncu --set full` capture of ONE launch of this kernel (profiles/r02_gemm_f16_gelu_ncu_full.txt: M=20300 N=3072 K=768, fp16
+        # operands and output, GELU epilogue): dram__bytes_read.sum + dram__bytes_write.sum. Not measured in this run.
+        "traffic": 110.8e6, "traffic_launch": "M=20300 N=3072 K=768 fp16 in/out (algorithmic 160.6e6 B, 95.8 GFLOP; the output is still "
+                                              "partly L2-resident when the kernel ends)",
+        "traffic_source": "profiles/r02_gemm_f16_gelu_ncu_full.txt (ncu --set full, one launch), not measured in this run",
+        "peak_source": "%s bf16_tflops_sustained%s" % (peak_src, "" if top_name == "f16" else " / 2 (tf32)"),
+        "%s_family" % other_name: other,
+        "decoder_rollout": dec_out,
+        "small_m_gemms": {"bound": "hbm", "what": "remaining dasa_gemm calls with M < 2048 (critic, init-state linears, skinny shapes)",
+                          "achieved": s_bytes / max(s_secs, 1e-12) / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": s_bytes / max(s_secs, 1e-12) / 1e9 / hbm, "launches_timed": len(small),
+                          "device_seconds": s_secs, "note": "eager launches, event-bracketed: includes launch gaps"}})
+    return out
 
 
 def main():
