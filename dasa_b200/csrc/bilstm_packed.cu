@@ -15,8 +15,29 @@
 // summation order per gate as bilstm_gemm.cu.
 #include "common.cuh"
 #include "gemm_common.cuh"
+#include "rng.cuh"
 
 namespace {
+
+// Dropout on the layer output (r2rmodel.py:2357 `ctx = self.drop(ctx)`), fused into the only kernel that writes / reads `out`:
+// keep flag of out[seq, l, c] from a mask tensor [R, L, 2H] or drawn in place (rng.cuh: stream byte (seq * L + l) * 2H + c).
+// Saves a 292 MB read + write pass in each direction (and the 73 MB mask) at the benchmark geometry.
+struct PkDrop { const uint8_t* mask; const unsigned long long* seed_dev; unsigned long long seed, base; uint32_t thr; int stream; float scale; };
+
+__device__ __forceinline__ float4 pk_drop4(const PkDrop& dr, int64_t e, float4 v) {   // e: element index of v.x (multiple of 4)
+  if (dr.mask != nullptr) {
+    const uint32_t m = *reinterpret_cast<const uint32_t*>(dr.mask + e);
+    v.x *= (m & 0xFFu) ? dr.scale : 0.f; v.y *= (m & 0xFF00u) ? dr.scale : 0.f;
+    v.z *= (m & 0xFF0000u) ? dr.scale : 0.f; v.w *= (m & 0xFF000000u) ? dr.scale : 0.f;
+  } else if (dr.stream) {
+    DropStream ds;
+    ds.mixed = mix_seed(dr.seed_dev ? dr.seed_dev[0] : dr.seed); ds.base = dr.base; ds.thr = dr.thr;
+    const uint32_t k4 = stream_keep4(ds, (uint64_t)e >> 2);
+    v.x *= (k4 & 1u) ? dr.scale : 0.f; v.y *= (k4 & 2u) ? dr.scale : 0.f;
+    v.z *= (k4 & 4u) ? dr.scale : 0.f; v.w *= (k4 & 8u) ? dr.scale : 0.f;
+  }
+  return v;
+}
 
 struct PkFwd {
   const float* xp[2]; const float* gh[2]; const float* b_ih[2]; const float* b_hh[2];
@@ -26,6 +47,7 @@ struct PkFwd {
   float* out; const int32_t* perm;
   int pos[2], n[2], n_next[2];
   int L, H;
+  PkDrop drop;
 };
 
 // thread = 4 consecutive hidden units of one (direction, rank); all global accesses are 128-bit
@@ -75,8 +97,8 @@ __global__ void __launch_bounds__(256) bilstm_packed_pointwise_fwd_kernel(PkFwd 
       *reinterpret_cast<float4*>(p.h_fin[d] + sb) = h4;
       *reinterpret_cast<float4*>(p.c_fin[d] + sb) = c4;
     }
-    float* orow = p.out + ((int64_t)__ldg(p.perm + r) * p.L + l) * 2 * H + (int64_t)d * H + j;
-    *reinterpret_cast<float4*>(orow) = h4;
+    const int64_t oe = ((int64_t)__ldg(p.perm + r) * p.L + l) * 2 * H + (int64_t)d * H + j;
+    *reinterpret_cast<float4*>(p.out + oe) = pk_drop4(p.drop, oe, h4);
     float* arow = p.acts[d] + (int64_t)r * 4 * H + j;
     *reinterpret_cast<float4*>(arow) = make_float4(ig[0], ig[1], ig[2], ig[3]);
     *reinterpret_cast<float4*>(arow + H) = make_float4(fg[0], fg[1], fg[2], fg[3]);
@@ -94,6 +116,7 @@ struct PkBwd {
   const float* dout; const int32_t* perm;
   int pos[2], n[2], n_carried[2];                          // rows < n_carried continue a gradient; the others start from d*_fin
   int L, H;
+  PkDrop drop;
 };
 
 __global__ void __launch_bounds__(256) bilstm_packed_pointwise_bwd_kernel(PkBwd p) {
@@ -123,7 +146,8 @@ __global__ void __launch_bounds__(256) bilstm_packed_pointwise_bwd_kernel(PkBwd 
         dc[0] = v.x; dc[1] = v.y; dc[2] = v.z; dc[3] = v.w;
       }
     }
-    const float4 go = ldg_stream4(p.dout + ((int64_t)__ldg(p.perm + r) * p.L + l) * 2 * H + (int64_t)d * H + j);
+    const int64_t oe = ((int64_t)__ldg(p.perm + r) * p.L + l) * 2 * H + (int64_t)d * H + j;
+    const float4 go = pk_drop4(p.drop, oe, ldg_stream4(p.dout + oe));
     dh[0] += go.x; dh[1] += go.y; dh[2] += go.z; dh[3] += go.w;
     const float* a = p.acts[d] + (int64_t)r * 4 * H + j;
     const float4 i4 = ldg_stream4(a), f4 = ldg_stream4(a + H), g4 = ldg_stream4(a + 2 * H), o4 = ldg_stream4(a + 3 * H);
@@ -168,6 +192,14 @@ int pk_check(int R, int L, int H, const int32_t* n_rows, const int64_t* off) {
     if (n_rows[p] < 0 || (p > 0 && n_rows[p] > n_rows[p - 1]) || off[p + 1] != off[p] + n_rows[p]) return DASA_ERR_BAD_SHAPE;
   }
   return DASA_OK;
+}
+
+inline PkDrop pk_drop(const uint8_t* mask, const uint64_t* seed_dev, uint64_t seed, uint64_t base, float p, float scale) {
+  PkDrop d;
+  d.mask = mask; d.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev); d.seed = seed; d.base = base;
+  d.thr = (uint32_t)(p * 65536.0f); d.stream = (mask == nullptr && p > 0.f) ? 1 : 0;
+  d.scale = (mask != nullptr || d.stream) ? scale : 1.f;
+  return d;
 }
 
 }  // namespace
@@ -218,6 +250,7 @@ extern "C" int dasa_bilstm_packed_fwd(const dasa_bilstm_packed_fwd_t* a, void* w
     p.n_next[1] = (p1 >= 1) ? n[p1 - 1] : 0;
     p.h_next[1] = (p1 >= 1) ? a->hprev[1] + off[p1 - 1] * H : nullptr;
     p.out = a->out; p.perm = a->perm; p.L = L; p.H = H;
+    p.drop = pk_drop(a->out_mask, a->drop_seed_dev, a->drop_seed, a->drop_base, a->drop_p, a->drop_scale);
     const int rows = p.n[0] > p.n_next[1] ? p.n[0] : p.n_next[1];
     bilstm_packed_pointwise_fwd_kernel<<<pk_grid(rows > p.n[1] ? rows : p.n[1], H), 256, 0, st>>>(p);
   }
@@ -260,6 +293,7 @@ extern "C" int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* a, void* w
     p.n_carried[1] = (s == Le - 1) ? 0 : n[p1];
     p.nparts = nparts; p.part_stride = (int64_t)RH;
     p.dout = a->dout; p.perm = a->perm; p.L = L; p.H = H;
+    p.drop = pk_drop(a->out_mask, a->drop_seed_dev, a->drop_seed, a->drop_base, a->drop_p, a->drop_scale);
     bilstm_packed_pointwise_bwd_kernel<<<pk_grid(p.n[0] > p.n[1] ? p.n[0] : p.n[1], H), 256, 0, st>>>(p);
     if (s > 0) {                                              // dh of the states that fed step s (the gradient before step 0 is unused)
       const float* A[2] = {p.dgates[0], p.dgates[1]};

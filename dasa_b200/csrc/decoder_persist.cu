@@ -131,11 +131,15 @@ struct GemmFrag {
   float4 x[MT][2];
 };
 
+// half_last: the block has 16 * RT - 8 weight rows - the upper 8 rows of the last 16-row tile are neither loaded nor multiplied
+// (their A fragments are zero). Lets a phase with N outputs use row blocks of 8 / 24 rows, so that all 148 CTAs stream weights
+// (N = 1024: 64 blocks of 16 rows left 84 SMs idle; N = 3072: 192 blocks of 16 rows took two rounds on 44 of them).
 template <int MT, int RT>
 __device__ __forceinline__ void dp_load(GemmFrag<MT, RT>& f, const wt_t* (&wrow)[2 * RT], const float* (&xrow)[MT],
-                                        const bool (&xok)[MT], int kc) {
+                                        const bool (&xok)[MT], int kc, const bool half_last) {
 #pragma unroll
   for (int i = 0; i < 2 * RT; ++i) {
+    if (half_last && i == 2 * RT - 1) continue;
     f.w[i][0] = ldg_w4(wrow[i] + kc);
     f.w[i][1] = ldg_w4(wrow[i] + kc + 16);
   }
@@ -152,7 +156,7 @@ __device__ __forceinline__ void dp_load(GemmFrag<MT, RT>& f, const wt_t* (&wrow)
 }
 
 template <int MT, int RT>
-__device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFrag<MT, RT>& f) {
+__device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFrag<MT, RT>& f, const bool half_last) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t bf[MT][2];
@@ -164,10 +168,11 @@ __device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFr
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       uint32_t af[4];
-      af[0] = h4_tf32(f.w[2 * h][0], j);       // (row g,     k = t)
-      af[1] = h4_tf32(f.w[2 * h + 1][0], j);   // (row g + 8, k = t)
-      af[2] = h4_tf32(f.w[2 * h][1], j);       // (row g,     k = t + 4)
-      af[3] = h4_tf32(f.w[2 * h + 1][1], j);   // (row g + 8, k = t + 4)
+      const bool off = half_last && h == RT - 1;
+      af[0] = h4_tf32(f.w[2 * h][0], j);                     // (row g,     k = t)
+      af[1] = off ? 0u : h4_tf32(f.w[2 * h + 1][0], j);      // (row g + 8, k = t)
+      af[2] = h4_tf32(f.w[2 * h][1], j);                     // (row g,     k = t + 4)
+      af[3] = off ? 0u : h4_tf32(f.w[2 * h + 1][1], j);      // (row g + 8, k = t + 4)
 #pragma unroll
       for (int i = 0; i < MT; ++i) dp_mma(acc[h][i], af, bf[i][0], bf[i][1]);
     }
@@ -177,7 +182,7 @@ __device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFr
 // NST chunks of W / X in flight per warp (registers; the ring is fully unrolled so every fragment index is a constant)
 template <int MT, int RT, int NST>
 __device__ __forceinline__ void dp_gemm_block(const wt_t* (&wrow)[2 * RT], const float* X, int64_t ldx, int M, int K,
-                                              float* red, float* res) {
+                                              float* red, float* res, const bool half_last = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const float* xrow[MT];
@@ -202,14 +207,14 @@ __device__ __forceinline__ void dp_gemm_block(const wt_t* (&wrow)[2 * RT], const
   int c = warp;
 #pragma unroll
   for (int s = 0; s < NST - 1; ++s)
-    if (c + s * DP_WARPS < nchunks) dp_load<MT, RT>(f[s], wrow, xrow, xok, (c + s * DP_WARPS) * DP_CHUNK);
+    if (c + s * DP_WARPS < nchunks) dp_load<MT, RT>(f[s], wrow, xrow, xok, (c + s * DP_WARPS) * DP_CHUNK, half_last);
 #pragma unroll 1
   for (; c < nchunks; c += NST * DP_WARPS) {
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
       const int cl = c + (s + NST - 1) * DP_WARPS;
-      if (cl < nchunks) dp_load<MT, RT>(f[(s + NST - 1) % NST], wrow, xrow, xok, cl * DP_CHUNK);
-      if (c + s * DP_WARPS < nchunks) dp_compute<MT, RT>(acc, f[s]);
+      if (cl < nchunks) dp_load<MT, RT>(f[(s + NST - 1) % NST], wrow, xrow, xok, cl * DP_CHUNK, half_last);
+      if (c + s * DP_WARPS < nchunks) dp_compute<MT, RT>(acc, f[s], half_last);
     }
   }
 
@@ -234,12 +239,13 @@ __device__ __forceinline__ void dp_gemm_block(const wt_t* (&wrow)[2 * RT], const
   __syncthreads();
 }
 
-// plain row block: rows n0 .. n0+15 of W (clamped to N-1; the caller never stores rows >= N)
-__device__ __forceinline__ void dp_rows16(const wt_t* (&wrow)[2], const wt_t* W, int64_t ldw, int n0, int N) {
+// plain row block: rows n0 .. n0+15 (n0 .. n0+7 with rows8: the upper half is never loaded) of W, clamped to N-1; the caller
+// never stores rows >= N
+__device__ __forceinline__ void dp_rows16(const wt_t* (&wrow)[2], const wt_t* W, int64_t ldw, int n0, int N, const bool rows8 = false) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    int n = n0 + g + 8 * i;
+    int n = n0 + g + ((rows8 || i == 0) ? 0 : 8);
     n = n < N ? n : N - 1;
     wrow[i] = W + (int64_t)n * ldw + 4 * t;
   }
@@ -459,14 +465,16 @@ __device__ __forceinline__ void fwd_gemm16(const dasa_decoder_fwd_t& a, const in
   else if (ph == 4) { W = reinterpret_cast<const wt_t*>(a.w_att_in);  ldw = H;  N = D;  K = H;  X = a.cat + tb * DC + D;   ldx = DC; }   // P4: t2 = W_att_in drop(h_1)
   else              { W = reinterpret_cast<const wt_t*>(a.w_att_out); ldw = DC; N = H;  K = DC; X = a.cat + tb * DC;       ldx = DC; }   // P6: h~ = tanh(W_att_out [wc ; drop(h_1)])
   W = dp_opaque(W);
-  const int nitems = (N + 15) / 16;
+  const bool rows8 = N <= 8 * (int)gridDim.x;                  // P6 (N = H = 1024): 128 blocks of 8 rows, one per CTA
+  const int rb = rows8 ? 8 : 16;
+  const int nitems = (N + rb - 1) / rb;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const wt_t* wrow[2];
-    dp_rows16(wrow, W, ldw, item * 16, N);
-    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res);
+    dp_rows16(wrow, W, ldw, item * rb, N, rows8);
+    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res, rows8);
     for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
-      const int m = o >> 4, n = item * 16 + (o & 15);
-      if (m >= B || n >= N) continue;
+      const int m = o >> 4, n = item * rb + (o & 15);
+      if (m >= B || n >= N || (o & 15) >= rb) continue;
       if (ph == 0) {
         a.tk[(tb + m) * NK + n] = res[o] + __ldg(a.b_feat + n);
       } else if (ph == 4) {
@@ -696,14 +704,16 @@ __device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const in
   else if (ph == 3) { W = reinterpret_cast<const wt_t*>(a.w_att_in_t);  ldw = a.ld_w_att_in_t;  N = H;  K = D;  X = a.dt2 + tb * D;  ldx = D; }    // B4: dh1d, LSTM cell backward
   else              { W = reinterpret_cast<const wt_t*>(a.w_feat_t);    ldw = a.ld_w_feat_t;    N = H;  K = NK; X = a.dtk + tb * NK; ldx = NK; }   // B1: dh~_{t-1}, du_{t-1}
   W = dp_opaque(W);
-  const int nitems = (N + 15) / 16;
+  const bool rows8 = N <= 8 * (int)gridDim.x;                  // B4 / B1 (N = H = 1024): 128 blocks of 8 rows, one per CTA
+  const int rb = rows8 ? 8 : 16;
+  const int nitems = (N + rb - 1) / rb;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const wt_t* wrow[2];
-    dp_rows16(wrow, W, ldw, item * 16, N);
-    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res);
+    dp_rows16(wrow, W, ldw, item * rb, N, rows8);
+    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res, rows8);
     for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
-      const int m = o >> 4, n = item * 16 + (o & 15);
-      if (m >= B || n >= N) continue;
+      const int m = o >> 4, n = item * rb + (o & 15);
+      if (m >= B || n >= N || (o & 15) >= rb) continue;
       if (ph == 0) {
         a.dcat[(int64_t)m * DC + n] = res[o];
       } else if (ph == 3) {
@@ -741,37 +751,47 @@ __device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const in
   }
 }
 
+// The 32-row GEMM phases of the backward pass share ONE inlined K loop: B3 (ph 4, d[x ; h] = dgates [W_ih | W_hh], 134 blocks of
+// 32 rows) and, when DC outputs need more than one round of 16-row blocks but fit one round of 24-row blocks (DC = 3072 on 148
+// CTAs: 128 blocks), B6 (ph 0, dcat = du W_att_out).
+__device__ __forceinline__ bool bwd_b6_rows24(const dasa_decoder_bwd_t& a) {
+  const int DC = a.D + a.H;
+  return DC > 16 * (int)gridDim.x && DC <= 24 * (int)gridDim.x;
+}
 template <int MT>
-__device__ __forceinline__ void bwd_b3(const dasa_decoder_bwd_t& a, const int t, float* red, float* res) {
-  const int T = a.T, B = a.B, H = a.H, E = a.E, F = a.F, D = a.D, NK = a.NK;
+__device__ __forceinline__ void bwd_gemm32(const dasa_decoder_bwd_t& a, const int t, const int ph, float* red, float* res) {
+  const int B = a.B, H = a.H, E = a.E, F = a.F, D = a.D;
   const int KX = E + F + H, DC = D + H;
   const int tid = threadIdx.x;
   const int64_t tb = (int64_t)t * B;
-  const float scale = a.drop_scale;
-  (void)T; (void)NK; (void)KX; (void)DC; (void)scale; (void)tb; (void)tid;
-    {
-      const float* X = a.dgates + tb * 4 * H;
-      const int nitems = (KX + 31) / 32;
-      const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const wt_t* wrow[4];
+  const bool b6 = ph == 0;
+  const wt_t* W = b6 ? reinterpret_cast<const wt_t*>(a.w_att_out_t) : reinterpret_cast<const wt_t*>(a.w_lstm_t);
+  const int64_t ldw = b6 ? a.ld_w_att_out_t : a.ld_w_lstm_t;
+  const float* X = b6 ? a.du + tb * H : a.dgates + tb * 4 * H;
+  const int K = b6 ? H : 4 * H, N = b6 ? DC : KX;
+  const int rb = b6 ? 24 : 32;
+  W = dp_opaque(W);
+  const int nitems = (N + rb - 1) / rb;
+  const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const wt_t* wrow[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int n = item * 32 + g + 8 * i;
-          n = n < KX ? n : KX - 1;
-          wrow[i] = dp_opaque(reinterpret_cast<const wt_t*>(a.w_lstm_t)) + (int64_t)n * a.ld_w_lstm_t + 4 * tq;
-        }
-        dp_gemm_block<MT, 2, DP_NST2>(wrow, X, 4 * H, B, 4 * H, red, res);
-        for (int o = tid; o < 32 * 8 * MT; o += DP_THREADS) {
-          const int m = o >> 5, n = item * 32 + (o & 31);
-          if (m >= B || n >= KX) continue;
-          const float v = res[o];
-          if (n < E) a.demb[(tb + m) * E + n] = v;
-          else if (n < E + F) a.dattn[(int64_t)m * F + (n - E)] = v;
-          else a.dhdir[(int64_t)m * H + (n - E - F)] = v;
-        }
-      }
+    for (int i = 0; i < 4; ++i) {
+      int n = item * rb + g + 8 * ((b6 && i == 3) ? 2 : i);
+      n = n < N ? n : N - 1;
+      wrow[i] = W + (int64_t)n * ldw + 4 * tq;
     }
+    dp_gemm_block<MT, 2, DP_NST2>(wrow, X, K, B, K, red, res, b6);
+    for (int o = tid; o < 32 * 8 * MT; o += DP_THREADS) {
+      const int m = o >> 5, nl = o & 31, n = item * rb + nl;
+      if (m >= B || n >= N || nl >= rb) continue;
+      const float v = res[o];
+      if (b6) a.dcat[(int64_t)m * DC + n] = v;
+      else if (n < E) a.demb[(tb + m) * E + n] = v;
+      else if (n < E + F) a.dattn[(int64_t)m * F + (n - E)] = v;
+      else a.dhdir[(int64_t)m * H + (n - E - F)] = v;
+    }
+  }
 }
 
 __device__ __noinline__ void bwd_issue_feat(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
@@ -976,10 +996,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
       switch (ph) {
         case 1: bwd_b5a(a, pl, smem_raw, S, t, par); break;
         case 2: bwd_b5b(a, pl, smem_raw, S, t); break;
-        case 4: bwd_b3<MT>(a, t, red, res); break;          // d[x ; h] = dgates [W_ih | W_hh]
         case 5: bwd_b2a(a, pl, smem_raw, S, t, par); break;
         case 6: bwd_b2b(a, pl, smem_raw, S, t); break;
-        default: bwd_gemm16<MT>(a, t, ph, red, res); break;   // B6 (ph 0), B4 (ph 3), B1 (ph 7): ONE inlined copy
+        default:                                              // GEMM phases: ONE inlined copy of each K loop
+          if (ph == 4 || (ph == 0 && bwd_b6_rows24(a))) bwd_gemm32<MT>(a, t, ph, red, res);   // B3, B6 in 24-row blocks
+          else bwd_gemm16<MT>(a, t, ph, red, res);                                            // B6 (other shapes), B4 (ph 3), B1 (ph 7)
+          break;
       }
       grid_sync(gb);
       dp_stamp(1 + 8 * it + ph);

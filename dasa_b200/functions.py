@@ -74,10 +74,18 @@ def flush_weight_grads(owner=None):
     for key, (weight, bias, dys, xs, bias2) in _queue.items():
         if owner is not None and not _inside(weight.grad, owner):
             continue
-        dY = dys[0] if len(dys) == 1 else torch.cat(dys, 0)
-        X = xs[0] if len(xs) == 1 else torch.cat(xs, 0)
-        ops.linear_bwd_weight(dY, X, _zeros_like_grad(weight), True)
-        _bias_grads(dY, bias, bias2)
+        # pieces with thousands of rows (the AdaIN gate sees the 25 200 view rows and the 8 400 candidate rows of a rollout) each
+        # get their own accumulating long-K GEMM: concatenating them copied 550 MB per step; the many 20-row pieces of a
+        # per-action path are still stacked into one operand first
+        big = [i for i, d in enumerate(dys) if d.shape[0] >= 2048]
+        small = [i for i in range(len(dys)) if i not in big]
+        pieces = [(dys[i], xs[i]) for i in big]
+        if small:
+            pieces.append((dys[small[0]], xs[small[0]]) if len(small) == 1 else
+                          (torch.cat([dys[i] for i in small], 0), torch.cat([xs[i] for i in small], 0)))
+        for dY, X in pieces:
+            ops.linear_bwd_weight(dY, X, _zeros_like_grad(weight), True)
+            _bias_grads(dY, bias, bias2)
         done.append(key)
     for key in done:
         del _queue[key]
@@ -518,7 +526,9 @@ class PackedBiLSTMFn(torch.autograd.Function):
     past each length), h_fin [2, R, H], c_fin [2, R, H] in original sequence order, like BiLSTMFn."""
 
     @staticmethod
-    def forward(ctx, x_packed, plan, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+    def forward(ctx, x_packed, plan, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, drop=None, drop_scale=1.0):
+        """drop: dropout on the returned ctx (r2rmodel.py:2357) fused into the kernels that write it / read its gradient: a uint8
+        keep mask [R, L, 2H], an ops.DropStream (flags drawn in the kernel, forward and backward draw the same ones) or None."""
         R, L, N = plan.R, plan.L, plan.N
         H = w_hh_f.shape[1]
         dev = x_packed.device
@@ -537,12 +547,13 @@ class PackedBiLSTMFn(torch.autograd.Function):
                                     P2(b_ih_f.data_ptr(), b_ih_r.data_ptr()), P2(b_hh_f.data_ptr(), b_hh_r.data_ptr()),
                                     P2(hprev[0].data_ptr(), hprev[1].data_ptr()), P2(cs[0].data_ptr(), cs[1].data_ptr()),
                                     P2(acts[0].data_ptr(), acts[1].data_ptr()), out.data_ptr(),
-                                    P2(fin[0, 0].data_ptr(), fin[0, 1].data_ptr()), P2(fin[1, 0].data_ptr(), fin[1, 1].data_ptr()))
+                                    P2(fin[0, 0].data_ptr(), fin[0, 1].data_ptr()), P2(fin[1, 0].data_ptr(), fin[1, 1].data_ptr()),
+                                    *_drop_fields(drop, drop_scale, (R, L, 2 * H)))
         ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 0))
         ops.call("dasa_bilstm_packed_fwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         h_fin = fin[0].index_select(1, plan.rank_of)
         c_fin = fin[1].index_select(1, plan.rank_of)
-        ctx.plan = plan
+        ctx.plan, ctx.drop, ctx.drop_scale = plan, drop, drop_scale
         ctx.save_for_backward(xc, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hprev, cs, acts)
         return out, h_fin, c_fin
 
@@ -569,7 +580,7 @@ class PackedBiLSTMFn(torch.autograd.Function):
                                     P2(wt[0].data_ptr(), wt[1].data_ptr()), P2(acts[0].data_ptr(), acts[1].data_ptr()),
                                     P2(cs[0].data_ptr(), cs[1].data_ptr()), dout.data_ptr(), P2(pp(dhf, 0), pp(dhf, 1)),
                                     P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates[0].data_ptr(), dgates[1].data_ptr()),
-                                    P2(work[0].data_ptr(), work[1].data_ptr()))
+                                    P2(work[0].data_ptr(), work[1].data_ptr()), *_drop_fields(ctx.drop, ctx.drop_scale, (R, L, 2 * H)))
         ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 1))
         ops.call("dasa_bilstm_packed_bwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         dxc = None
@@ -583,7 +594,15 @@ class PackedBiLSTMFn(torch.autograd.Function):
         if dxc is not None:
             dx = torch.empty_like(dxc)
             dx[plan.src] = dxc                                                 # the gather index is a bijection of the N tokens
-        return (dx, None) + (None,) * 8
+        return (dx, None) + (None,) * 10
+
+
+def _drop_fields(drop, scale, shape):
+    """(out_mask, drop_seed_dev, drop_seed, drop_base, drop_p, drop_scale) of the fused-output-dropout ABI structs."""
+    if drop is not None and not isinstance(drop, ops.DropStream):
+        assert tuple(drop.shape) == tuple(shape) and drop.dtype == torch.uint8 and drop.is_contiguous(), (drop.shape, shape)
+    mp, sp, seed, base, p = ops._drop_args(drop)
+    return mp, sp, seed, base, p, float(scale)
 
 
 class MaskedCEFn(torch.autograd.Function):

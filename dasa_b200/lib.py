@@ -36,13 +36,15 @@ class BiLstmBwd(ctypes.Structure):
 class BiLstmPackedFwd(ctypes.Structure):
     """dasa_bilstm_packed_fwd_t"""
     _fields_ = [("R", I), ("L", I), ("H", I), ("n_rows", P), ("off", P), ("perm", P), ("xp", P * 2), ("w_hh", P * 2), ("b_ih", P * 2),
-                ("b_hh", P * 2), ("hprev", P * 2), ("cs", P * 2), ("acts", P * 2), ("out", P), ("h_fin", P * 2), ("c_fin", P * 2)]
+                ("b_hh", P * 2), ("hprev", P * 2), ("cs", P * 2), ("acts", P * 2), ("out", P), ("h_fin", P * 2), ("c_fin", P * 2),
+                ("out_mask", P), ("drop_seed_dev", P), ("drop_seed", U), ("drop_base", U), ("drop_p", F), ("drop_scale", F)]
 
 
 class BiLstmPackedBwd(ctypes.Structure):
     """dasa_bilstm_packed_bwd_t"""
     _fields_ = [("R", I), ("L", I), ("H", I), ("n_rows", P), ("off", P), ("perm", P), ("w_hh_t", P * 2), ("acts", P * 2), ("cs", P * 2),
-                ("dout", P), ("dh_fin", P * 2), ("dc_fin", P * 2), ("dgates", P * 2), ("dc_work", P * 2)]
+                ("dout", P), ("dh_fin", P * 2), ("dc_fin", P * 2), ("dgates", P * 2), ("dc_work", P * 2),
+                ("out_mask", P), ("drop_seed_dev", P), ("drop_seed", U), ("drop_base", U), ("drop_p", F), ("drop_scale", F)]
 
 
 class DecoderFwd(ctypes.Structure):

@@ -929,16 +929,26 @@ class DicEncoder(nn.Module):
         l = self.lstm
         lstm_args = (l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0, l.weight_ih_l0_reverse, l.weight_hh_l0_reverse,
                      l.bias_ih_l0_reverse, l.bias_hh_l0_reverse)
+        ctx_dropped = False
         if rev is None:      # padding-free recurrence straight from the packed tokens (reversal folded into its gather index)
-            ctx, h_fin, c_fin = Fn.PackedBiLSTMFn.apply(lang, pack.bilstm_plan(), *lstm_args)
+            # `ctx = self.drop(ctx)` (r2rmodel.py:2357) rides on the kernels that write ctx / read its gradient: flags drawn in
+            # place unless a test injects masks
+            shape = (steps * B, L, 2 * self.hidden_size)
+            if _source.injected is None and ops.stream_dropout:
+                m, sc = _source.stream(shape[0] * shape[1] * shape[2], self.dropout_ratio, tr)
+            else:
+                m, sc = _source.mask_steps("enc.ctx", (B,) + shape[1:], self.dropout_ratio, tr, lang.device, steps)
+            ctx, h_fin, c_fin = Fn.PackedBiLSTMFn.apply(lang, pack.bilstm_plan(), *lstm_args, m, sc)
+            ctx_dropped = True
         else:
             ctx, h_fin, c_fin = Fn.BiLSTMFn.apply(rev, len32, *lstm_args)
         h_cat = torch.cat((h_fin[1, :B], h_fin[0, :B]), 1)
         c_cat = torch.cat((c_fin[1, :B], c_fin[0, :B]), 1)
         decoder_init = Fn.linear(h_cat, self.encoder_lstm2decoder_ht.weight, self.encoder_lstm2decoder_ht.bias, "tanh")
         c_t = Fn.linear(c_cat, self.encoder_lstm2decoder_ct.weight, self.encoder_lstm2decoder_ct.bias)
-        m, sc = _source.mask_steps("enc.ctx", (B,) + tuple(ctx.shape[1:]), self.dropout_ratio, tr, ctx.device, steps)
-        ctx = Fn.dropout(ctx, m, sc)
+        if not ctx_dropped:
+            m, sc = _source.mask_steps("enc.ctx", (B,) + tuple(ctx.shape[1:]), self.dropout_ratio, tr, ctx.device, steps)
+            ctx = Fn.dropout(ctx, m, sc)
         return ctx, decoder_init, c_t
 
     def forward(self, inputs, mask, lengths, f_t_all=None, lang_out=None, lengths_host=None):

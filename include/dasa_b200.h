@@ -255,6 +255,10 @@ typedef struct {
   float* hprev[2]; float* cs[2]; float* acts[2];
   float* out;
   float* h_fin[2]; float* c_fin[2];
+  /* dropout on the layer output (r2rmodel.py:2357), fused into the write of `out`: out_mask = uint8 keep mask [R, L, 2H] (original
+   * order), or NULL with drop_p > 0: flags drawn in place, out[seq, l, c] = stream byte (seq*L + l)*2H + c of (seed, drop_base)
+   * (see dasa_mha_fwd_h16); NULL and drop_p == 0: no dropout. The backward struct takes the same fields and masks dout.          */
+  const uint8_t* out_mask; const uint64_t* drop_seed_dev; uint64_t drop_seed; uint64_t drop_base; float drop_p; float drop_scale;
 } dasa_bilstm_packed_fwd_t;
 /* Backward: dout [R, L, 2H] (original order), dh_fin / dc_fin [R, H] rank order (may be NULL), w_hh_t[d] = W_hh[d]^T [H, 4H].
  * Writes dgates[d] [N, 4H] (compact token order: the dY of dW_ih = dgates^T x, dW_hh = dgates^T hprev, dX = dgates W_ih).
@@ -265,6 +269,7 @@ typedef struct {
   const float* w_hh_t[2]; const float* acts[2]; const float* cs[2];
   const float* dout; const float* dh_fin[2]; const float* dc_fin[2];
   float* dgates[2]; float* dc_work[2];
+  const uint8_t* out_mask; const uint64_t* drop_seed_dev; uint64_t drop_seed; uint64_t drop_base; float drop_p; float drop_scale;
 } dasa_bilstm_packed_bwd_t;
 size_t dasa_bilstm_packed_workspace(int R, int H, int backward);
 int dasa_bilstm_packed_fwd(const dasa_bilstm_packed_fwd_t* args, void* workspace, size_t workspace_bytes, void* stream);

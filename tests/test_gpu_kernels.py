@@ -1068,3 +1068,44 @@ def test_layernorm_fwd_stream_dropout_bit_equal_to_mask(x_half, Hd):
     ref = torch.nn.functional.layer_norm(z.double(), (Hd,), gamma.double(), beta.double(), 1e-12)
     assert_close(a, ref, 2e-5, "LN")
     assert_close(a16.float(), ref, 1e-3, "LN fp16 copy")
+
+
+@pytest.mark.parametrize("stream", [False, True])
+def test_packed_bilstm_fused_output_dropout(stream):
+    """`ctx = drop(ctx)` (r2rmodel.py:2357) fused into the packed recurrence's output write and gradient read: identical (bit for
+    bit) to the unfused PackedBiLSTMFn followed by Fn.dropout with the same keep mask - a mask tensor, or the flags the kernels
+    draw in place (materialised here from the same stream)."""
+    R, L, In, H, seed = 90, 14, 64, 64, 5
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, L + 1, (R,), generator=g).tolist()
+    lens[0] = L
+    pack = M.PackInfo(lens, L, 1, DEV)
+    plan = pack.bilstm_plan()
+    x = (torch.randn(pack.ntok, In, generator=g) * 0.5).to(DEV)
+
+    def weights():
+        gg = torch.Generator().manual_seed(seed + 100)
+        return [(torch.randn(*s, generator=gg) * sc).to(DEV).requires_grad_(True)
+                for s, sc in (((4 * H, In), In ** -0.5), ((4 * H, H), H ** -0.5), ((4 * H,), 0.1), ((4 * H,), 0.1)) * 2]
+    gout = torch.randn(R, L, 2 * H, generator=g).to(DEV)
+    p, sd, base = 0.5, 31, 64
+    n = R * L * 2 * H
+    assert n % 16 == 0
+    km = ops.dropout_mask((n,), p, sd, base).view(R, L, 2 * H)
+    drop = ops.DropStream(None, sd, base, p) if stream else km
+    ops.set_precision("tf32")
+    try:
+        w0, x0 = weights(), x.clone().requires_grad_(True)
+        o0, _, _ = Fn.PackedBiLSTMFn.apply(x0, plan, *w0)
+        o0 = Fn.dropout(o0, km, 2.0)
+        (o0 * gout).sum().backward()
+        w1, x1 = weights(), x.clone().requires_grad_(True)
+        o1, _, _ = Fn.PackedBiLSTMFn.apply(x1, plan, *w1, drop, 2.0)
+        (o1 * gout).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision("fp32")
+    assert 0.4 < float((o1 == 0).float().mean()) and torch.equal(o0, o1)
+    assert torch.equal(x0.grad, x1.grad)
+    for a, b in zip(w0, w1):
+        assert torch.equal(a.grad, b.grad)
