@@ -59,6 +59,10 @@ struct RowAttnArgs {
   float* wc; int64_t ld_wc; float* attn_out; float* q_out; float* kappa_out;
   int chunk;
   int nbox, boxw;        // the channel slice is staged as nbox TMA boxes of [rows x boxw] floats (boxw <= 256, chunk = nbox*boxw)
+  // fused DGAdaChannel gate (K1 epilogue -> K3, agent_dg.py:1544-1547 feeding model.py:327-345): the staged tile holds the RAW
+  // features f; channels c < gate_C are multiplied in place by sigmoid(gate[b, r, c]) (* chan_scale[c]: the shared drop_env noise,
+  // agent_dg.py:656) before the attention runs on it, so the modulated features df_t are never written to HBM
+  const float* gate; int64_t ld_grow, ld_gsample; int gate_C; const float* chan_scale;
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -147,7 +151,9 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // LOCAL smem, (3) ONE full cluster barrier, (4) pull the peers' partials through DSMEM (fixed rank order => identical sums
 // everywhere), (5) arrive on the exit barrier (peers may still read our partials), softmax / shift, weighted sum from the
 // resident tile, (6) wait on the exit barrier. Only step (3) sits on the critical path.
-template <int CS, bool SHIFT>
+constexpr int RA_GATE_REGS = 12;   // float4 gate fragments a thread requests BEFORE it waits for the feature tile
+
+template <int CS, bool SHIFT, bool GATE = false>
 __global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap, RowAttnArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -177,7 +183,56 @@ __global__ void __launch_bounds__(RA_THREADS) row_attention_fwd_kernel(const __g
     for (int c = threadIdx.x; c < cn; c += RA_THREADS) s.tv[c] = t_b[c];
     __syncthreads();
   }
-  mbar_wait(s.bar, 0);
+  if (GATE) {
+    // gate pre-activations of this slice: streamed once from HBM, requested before the tile wait so both streams are in flight
+    const int b4g = boxw >> 2, per_box = rows * b4g, total4 = nbox * per_box;
+    const float* g_b = a.gate + (int64_t)b * a.ld_gsample;
+    auto locate = [&](int idx, int& c, float4*& tp) {
+      const int sb = idx / per_box, rem = idx - sb * per_box, r = rem / b4g, cin = rem - r * b4g;
+      c = c0 + sb * boxw + 4 * cin;
+      tp = reinterpret_cast<float4*>(s.tile + ((size_t)sb * rows + r) * boxw) + cin;
+      return r;
+    };
+    auto apply = [&](float4* tp, int c, const float4& g) {
+      float4 sg = make_float4(sigmoidf_(g.x), sigmoidf_(g.y), sigmoidf_(g.z), sigmoidf_(g.w));
+      if (a.chan_scale != nullptr) {
+        const float4 cs4 = __ldg(reinterpret_cast<const float4*>(a.chan_scale + c));
+        sg.x *= cs4.x; sg.y *= cs4.y; sg.z *= cs4.z; sg.w *= cs4.w;
+      }
+      float4 v = *tp;
+      v.x *= sg.x; v.y *= sg.y; v.z *= sg.z; v.w *= sg.w;
+      *tp = v;
+    };
+    float4 gr[RA_GATE_REGS];
+#pragma unroll
+    for (int i = 0; i < RA_GATE_REGS; ++i) {
+      const int idx = threadIdx.x + i * RA_THREADS;
+      gr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total4) {
+        int c; float4* tp;
+        const int r = locate(idx, c, tp);
+        if (c < a.gate_C) gr[i] = ldg_stream4(g_b + (int64_t)r * a.ld_grow + c);
+      }
+    }
+    mbar_wait(s.bar, 0);
+#pragma unroll
+    for (int i = 0; i < RA_GATE_REGS; ++i) {
+      const int idx = threadIdx.x + i * RA_THREADS;
+      if (idx < total4) {
+        int c; float4* tp;
+        locate(idx, c, tp);
+        if (c < a.gate_C) apply(tp, c, gr[i]);
+      }
+    }
+    for (int idx = threadIdx.x + RA_GATE_REGS * RA_THREADS; idx < total4; idx += RA_THREADS) {
+      int c; float4* tp;
+      const int r = locate(idx, c, tp);
+      if (c < a.gate_C) apply(tp, c, ldg_stream4(g_b + (int64_t)r * a.ld_grow + c));
+    }
+    __syncthreads();
+  } else {
+    mbar_wait(s.bar, 0);
+  }
 
   // partial dots of this channel slice -> local smem (aux doubles as the local partial array)
   {
@@ -531,22 +586,23 @@ int launch_cluster(Kern kern, int B, int cs, size_t smem, cudaStream_t st, const
 
 }  // namespace
 
-extern "C" int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
-                                      const float* t, int64_t ld_t, const uint8_t* mask, int64_t ld_mask, int shift_k,
-                                      int headings, const float* kappa_logits, int64_t ld_kappa, float* wc, int64_t ld_wc,
-                                      float* attn_out, float* q_out, float* kappa_out, void* stream) {
+static int row_attention_fwd_impl(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
+                                  const float* t, int64_t ld_t, const uint8_t* mask, int64_t ld_mask, int shift_k,
+                                  int headings, const float* kappa_logits, int64_t ld_kappa, float* wc, int64_t ld_wc,
+                                  float* attn_out, float* q_out, float* kappa_out, const float* gate, int64_t ld_grow,
+                                  int64_t ld_gsample, int gate_C, const float* chan_scale, void* stream) {
   if (B <= 0) return DASA_OK;
   if (rows <= 0 || rows > RA_MAX_ROWS || D <= 0 || D % 4 != 0) return DASA_ERR_BAD_SHAPE;
   if (shift_k < 0 || shift_k > RA_MAX_K || (shift_k > 0 && (headings <= 0 || rows % headings != 0 || kappa_logits == nullptr)))
     return DASA_ERR_BAD_SHAPE;
   if (!dasa_aligned16(ctx) || ld_row % 4 != 0 || ld_sample % 4 != 0) return DASA_ERR_BAD_ALIGN;
-  if (mask == nullptr && B >= ra_pipe_min_batch()) {
+  if (gate == nullptr && mask == nullptr && B >= ra_pipe_min_batch()) {
     const int rc = dasa_row_attention_fwd_pipelined(ctx, ld_row, ld_sample, B, rows, D, t, ld_t, shift_k, headings, kappa_logits,
                                                     ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out, (cudaStream_t)stream);
     if (rc != DASA_ERR_UNSUPPORTED) return rc;
   }
   RowAttnArgs a{ctx, ld_row, ld_sample, B, rows, D, t, ld_t, mask, ld_mask, shift_k, headings, kappa_logits, ld_kappa,
-                wc, ld_wc, attn_out, q_out, kappa_out, 0, 1, 0};
+                wc, ld_wc, attn_out, q_out, kappa_out, 0, 1, 0, gate, ld_grow, ld_gsample, gate_C, chan_scale};
   const int cs = pick_cluster(B, rows, D, &a.chunk);
   // TMA boxes: inner extent <= 256 elements; widen the slice so that it is a whole number of equal boxes
   a.nbox = (int)dasa_cdiv(a.chunk, 256);
@@ -578,7 +634,8 @@ extern "C" int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t 
   }
   cudaStream_t st = (cudaStream_t)stream;
 #define DASA_RA_FWD(CSV)                                                                                                  \
-  (shift_k > 0 ? launch_cluster(row_attention_fwd_kernel<CSV, true>, B, CSV, smem, st, "row_attention_fwd<shift>", tmap, a) \
+  (gate != nullptr ? launch_cluster(row_attention_fwd_kernel<CSV, true, true>, B, CSV, smem, st, "row_attention_fwd<gate,shift>", tmap, a) \
+   : shift_k > 0 ? launch_cluster(row_attention_fwd_kernel<CSV, true>, B, CSV, smem, st, "row_attention_fwd<shift>", tmap, a) \
                : launch_cluster(row_attention_fwd_kernel<CSV, false>, B, CSV, smem, st, "row_attention_fwd<softdot>", tmap, a))
   switch (cs) {
     case 1: return DASA_RA_FWD(1);
@@ -587,6 +644,27 @@ extern "C" int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t 
     default: return DASA_RA_FWD(8);
   }
 #undef DASA_RA_FWD
+}
+
+extern "C" int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
+                                      const float* t, int64_t ld_t, const uint8_t* mask, int64_t ld_mask, int shift_k,
+                                      int headings, const float* kappa_logits, int64_t ld_kappa, float* wc, int64_t ld_wc,
+                                      float* attn_out, float* q_out, float* kappa_out, void* stream) {
+  return row_attention_fwd_impl(ctx, ld_row, ld_sample, B, rows, D, t, ld_t, mask, ld_mask, shift_k, headings, kappa_logits, ld_kappa,
+                                wc, ld_wc, attn_out, q_out, kappa_out, nullptr, 0, 0, 0, nullptr, stream);
+}
+
+extern "C" int dasa_gate_shift_attention_fwd(const float* f, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
+                                             const float* gate_pre, int64_t ld_grow, int64_t ld_gsample, int gate_C,
+                                             const float* chan_scale, const float* t, int64_t ld_t, int shift_k, int headings,
+                                             const float* kappa_logits, int64_t ld_kappa, float* wc, int64_t ld_wc,
+                                             float* attn_out, float* q_out, float* kappa_out, void* stream) {
+  if (gate_pre == nullptr || shift_k <= 0) return DASA_ERR_BAD_SHAPE;
+  if (gate_C <= 0 || gate_C > D || gate_C % 4 != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(gate_pre) || ld_grow % 4 != 0 || ld_gsample % 4 != 0 || (chan_scale && !dasa_aligned16(chan_scale)))
+    return DASA_ERR_BAD_ALIGN;
+  return row_attention_fwd_impl(f, ld_row, ld_sample, B, rows, D, t, ld_t, nullptr, 0, shift_k, headings, kappa_logits, ld_kappa,
+                                wc, ld_wc, attn_out, q_out, kappa_out, gate_pre, ld_grow, ld_gsample, gate_C, chan_scale, stream);
 }
 
 extern "C" int dasa_row_attention_bwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,

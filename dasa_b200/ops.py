@@ -416,6 +416,24 @@ def row_attention_fwd(ctx, t, mask=None, shift_k=0, headings=12, kappa_logits=No
     return wc, attn, q, kappa
 
 
+def gate_shift_attention_fwd(f, gate_pre, t, kappa_logits, shift_k=5, headings=12, chan_scale=None):
+    """Fused DGAdaChannel gate -> ShiftSoftDotAttention (dasa_gate_shift_attention_fwd): f [B, rows, D] raw features, gate_pre
+    [B, rows, C] = a_fc(d) pre-activations (C <= D gated channels), t [B, D] = linear_in(h), kappa_logits [B, k]. Returns
+    (weighted context [B, D], pre-shift softmax [B, rows], shifted weights q, kappa) of the MODULATED features, which are never
+    written to HBM. Forward only."""
+    B, rows, D = f.shape
+    C = gate_pre.shape[2]
+    assert f.stride(2) == 1 and gate_pre.stride(2) == 1 and tuple(gate_pre.shape[:2]) == (B, rows)
+    wc = torch.empty(B, D, device=f.device, dtype=torch.float32)
+    attn = torch.empty(B, rows, device=f.device, dtype=torch.float32)
+    q = torch.empty(B, rows, device=f.device, dtype=torch.float32)
+    kappa = torch.empty(B, shift_k, device=f.device, dtype=torch.float32)
+    call("dasa_gate_shift_attention_fwd", _p(f), f.stride(1), f.stride(0), B, rows, D, _p(gate_pre), gate_pre.stride(1),
+         gate_pre.stride(0), C, _p(chan_scale), _p(t), t.stride(0), shift_k, headings, _p(kappa_logits), kappa_logits.stride(0),
+         _p(wc), wc.stride(0), _p(attn), _p(q), _p(kappa), _stream())
+    return wc, attn, q, kappa
+
+
 def row_attention_bwd(ctx, t, attn, q, kappa, dwc, shift_k=0, headings=12, need_dctx=True, dctx=None, accumulate=False,
                       dt=None, dkl=None):
     """dt / dkl (optional): caller-owned output views (e.g. column ranges of one buffer that feeds a single stacked GEMM)."""

@@ -165,6 +165,18 @@ int dasa_row_attention_fwd(const float* ctx, int64_t ld_row, int64_t ld_sample, 
  * Pass NULL to switch it off. Not used by the product path. */
 int dasa_debug_row_attention_trace(void* buf);
 
+/* Fused K1 -> K3: DGAdaChannel's gate epilogue (agent_dg.py:1544-1547: df = sigmoid(g) * f on the first
+ * gate_C channels, given the pre-activations g = a_fc(d); the remaining D - gate_C angle channels pass through; chan_scale
+ * (optional, [gate_C]) = the drop_env noise shared by batch and views, agent_dg.py:656) feeding ShiftSoftDotAttention
+ * (model.py:327-345) WITHOUT materialising df_t: the raw feature slice is staged in shared memory by TMA, modulated in place by
+ * the gate streamed from HBM, and the attention (logits, softmax over the views, circular heading shift, weighted sum) runs on
+ * the resident tile. Algorithmic bytes 4*B*rows*(D + gate_C) + 4*(2*B*D + B*rows) instead of an extra write + read of df_t.
+ * Forward only (the training rollout needs df_t for the candidate logits and the backward pass). Outputs as dasa_row_attention_fwd. */
+int dasa_gate_shift_attention_fwd(const float* f, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,
+                                  const float* gate_pre, int64_t ld_grow, int64_t ld_gsample, int gate_C,
+                                  const float* chan_scale, const float* t, int64_t ld_t, int shift_k, int headings,
+                                  const float* kappa_logits, int64_t ld_kappa, float* wc, int64_t ld_wc,
+                                  float* attn_out, float* q_out, float* kappa_out, void* stream);
 /* backward (Appendix A, K3 / K4): given dwc -> dctx (may be NULL), dt, dkappa_logits (shift only).
  * dctx_accumulate != 0 adds into dctx instead of overwriting it.                                                  */
 int dasa_row_attention_bwd(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D,

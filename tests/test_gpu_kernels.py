@@ -1109,3 +1109,38 @@ def test_packed_bilstm_fused_output_dropout(stream):
     assert torch.equal(x0.grad, x1.grad)
     for a, b in zip(w0, w1):
         assert torch.equal(a.grad, b.grad)
+
+
+@pytest.mark.parametrize("B,C", [(5, 2048), (20, 2048), (300, 2048), (9, 3072)])
+@pytest.mark.parametrize("noise", [False, True])
+def test_fused_gate_shift_attention_matches_unfused(B, C, noise):
+    """dasa_gate_shift_attention_fwd (K1 epilogue -> K3 without materialising df_t) against gate_modulate followed by the shift
+    attention on the materialised df_t, and against an fp64 restatement (agent_dg.py:1544-1547, model.py:327-345)."""
+    gen = g(B + C)
+    V, A, k, Hn = 36, 128, 5, 12
+    F = C + A
+    f = torch.rand(B, V, F, generator=gen).to(DEV)
+    gp = torch.randn(B, V, C, generator=gen).to(DEV)
+    t = (torch.randn(B, F, generator=gen) * 0.05).to(DEV)
+    kl = torch.randn(B, k, generator=gen).to(DEV)
+    cs = (torch.rand(C, generator=gen) > 0.4).float().div(0.6).to(DEV) if noise else None
+    wc, attn, q, kap = ops.gate_shift_attention_fwd(f, gp, t, kl, k, Hn, cs)
+    df = f.clone()
+    ops.gate_modulate(gp.view(B * V, C), f[..., :C], df[..., :C])
+    if noise:
+        df[..., :C] *= cs
+    wc0, attn0, q0, kap0 = ops.row_attention_fwd(df, t, None, k, Hn, kl)
+    for name, a, b in (("wc", wc, wc0), ("attn", attn, attn0), ("q", q, q0), ("kappa", kap, kap0)):
+        assert_close(a, b, 2e-6, "fused vs unfused " + name)
+    # fp64 restatement
+    d64 = f.double().clone()
+    d64[..., :C] = torch.sigmoid(gp.double()) * f[..., :C].double() * (cs.double() if noise else 1.0)
+    p = torch.softmax(torch.einsum("bvf,bf->bv", d64, t.double()), 1)
+    kp = torch.softmax(kl.double(), 1)
+    pe = p.view(B, V // Hn, Hn)
+    qq = torch.zeros_like(pe)
+    for j in range(k):
+        qq += kp[:, j].view(B, 1, 1) * torch.roll(pe, shifts=-(j - k // 2), dims=2)
+    ref = torch.einsum("bv,bvf->bf", qq.view(B, V), d64)
+    assert_close(attn, p, 1e-4, "softmax over the views")
+    assert_close(wc, ref, 1e-4, "weighted context")
