@@ -15,7 +15,9 @@ void* dasa_tensormap_encoder();
 // persistent pipelined forward of the (shift) view attention for large batches (row_attention_pipe.cu)
 int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D, const float* t,
                                      int64_t ld_t, int shift_k, int headings, const float* kappa_logits, int64_t ld_kappa,
-                                     float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, cudaStream_t st);
+                                     float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, cudaStream_t st,
+                                     const float* gate = nullptr, int64_t ld_grow = 0, int64_t ld_gsample = 0, int gate_C = 0,
+                                     const float* chan_scale = nullptr);
 
 static inline int dasa_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -596,9 +596,10 @@ static int row_attention_fwd_impl(const float* ctx, int64_t ld_row, int64_t ld_s
   if (shift_k < 0 || shift_k > RA_MAX_K || (shift_k > 0 && (headings <= 0 || rows % headings != 0 || kappa_logits == nullptr)))
     return DASA_ERR_BAD_SHAPE;
   if (!dasa_aligned16(ctx) || ld_row % 4 != 0 || ld_sample % 4 != 0) return DASA_ERR_BAD_ALIGN;
-  if (gate == nullptr && mask == nullptr && B >= ra_pipe_min_batch()) {
+  if (mask == nullptr && B >= ra_pipe_min_batch()) {
     const int rc = dasa_row_attention_fwd_pipelined(ctx, ld_row, ld_sample, B, rows, D, t, ld_t, shift_k, headings, kappa_logits,
-                                                    ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out, (cudaStream_t)stream);
+                                                    ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out, (cudaStream_t)stream,
+                                                    gate, ld_grow, ld_gsample, gate_C, chan_scale);
     if (rc != DASA_ERR_UNSUPPORTED) return rc;
   }
   RowAttnArgs a{ctx, ld_row, ld_sample, B, rows, D, t, ld_t, mask, ld_mask, shift_k, headings, kappa_logits, ld_kappa,

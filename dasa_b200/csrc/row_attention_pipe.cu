@@ -15,6 +15,11 @@
 //                     weights, arrive `wready[stage]`;
 //   * weighted-sum warps: warp = box, lane = float4 column: sum_r w_r * slice[r, :] from the still-resident stage, store,
 //                     arrive `empty[stage]`.
+//
+// GATE variant (fused DGAdaChannel epilogue -> shift attention, agent_dg.py:1544-1547 feeding model.py:327-345): the staged slice
+// holds the RAW features; the gate pre-activations of the same slice arrive through a second TMA ring (NG stages, released as
+// soon as they are consumed), 8 extra `gate warps` multiply the resident slice in place by sigmoid(g) (* chan_scale) for the
+// channels below gate_C and hand the stage to the dot warps through `gated[stage]`. The modulated features never reach HBM.
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include "common.cuh"
@@ -28,6 +33,7 @@ constexpr int RP_MAX_BOX = 4;         // boxes per slice = weighted-sum warps
 constexpr int RP_SWARPS = 4;          // softmax warps
 constexpr int RP_WARPS = RP_DWARPS + RP_MAX_BOX + RP_SWARPS + 1;
 constexpr int RP_THREADS = RP_WARPS * 32;
+constexpr int RP_GWARPS = 8;          // gate warps (GATE variant only), placed after the producer warp
 constexpr int RP_MAX_ROWS = 64;       // two rows per lane in a softmax warp
 constexpr int RP_MAX_K = 15;
 
@@ -37,6 +43,8 @@ struct PipeArgs {
   float* wc; int64_t ld_wc; float* attn_out; float* q_out; float* kappa_out;
   int B, rows, D, chunk, nbox, boxw, box_stride, shift_k, headings, nstages, nclusters;   // box_stride in floats
   long long* trace;      // debug: [CTA][sample][8] SM-clock stamps of the pipeline hand-offs (nullptr in production)
+  int gate_C, ngstages;  // GATE: channels [0, gate_C) are modulated; depth of the gate ring
+  const float* chan_scale;   // GATE: optional per-channel factor [gate_C] (drop_env noise, agent_dg.py:656)
 };
 
 // Shared memory of one CTA. NS stages; the partial-dot exchange ring is 2*NS deep: a peer can push sample j only after this
@@ -53,17 +61,23 @@ struct PipeSmem {
   uint64_t* empty;  // [NS]   weighted-sum warps are done with the stage
   uint64_t* wready; // [NS]   weights published
   uint64_t* zfull;  // [2*NS] all partial dots of a sample arrived
+  float* gtile;     // [NG][nbox][box_stride] GATE: gate pre-activations of the slice
+  float* cscale;    // [chunk]                GATE: chan_scale slice (1 where absent)
+  uint64_t* gfull;  // [NG]   gate slice landed
+  uint64_t* gempty; // [NG]   gate warps are done with the gate slice
+  uint64_t* gated;  // [NS]   the stage holds the modulated features
   size_t stage_floats;
 };
 
 __host__ __device__ inline int rp_rpad(int rows) { return (rows + 3) & ~3; }
 
-__host__ __device__ inline size_t rp_smem_bytes(int rows, int chunk, int nbox, int box_stride, int cs, int ns, int k) {
+__host__ __device__ inline size_t rp_smem_bytes(int rows, int chunk, int nbox, int box_stride, int cs, int ns, int k, int ng = 0) {
   const size_t rp = (size_t)rp_rpad(rows);
   size_t b = 4 * ((size_t)ns * nbox * box_stride + (size_t)ns * chunk + (size_t)ns * rp + (size_t)2 * ns * cs * rp +
                   (size_t)RP_SWARPS * (rp + 16));
   b += (((size_t)rows * (k > 0 ? k : 1)) + 15) & ~(size_t)15;
   b += 8 * (size_t)(5 * ns) + 128;
+  if (ng > 0) b += 4 * ((size_t)ng * nbox * box_stride + (size_t)chunk) + 8 * (size_t)(2 * ng + ns) + 128;
   return b;
 }
 
@@ -83,6 +97,17 @@ __device__ inline PipeSmem rp_carve(unsigned char* raw, const PipeArgs& a, int c
   s.empty = s.full + ns;
   s.wready = s.empty + ns;
   s.zfull = s.wready + ns;
+  s.gtile = nullptr; s.cscale = nullptr; s.gfull = s.gempty = s.gated = nullptr;
+  if (a.ngstages > 0) {                                         // GATE: appended after the barriers, 128-byte aligned
+    // byte offset from `raw` (not a uintptr_t round trip): keeps the shared-memory address space visible to the compiler (LDS/STS)
+    size_t off = (size_t)(reinterpret_cast<unsigned char*>(s.zfull + 2 * ns) - raw);
+    off = (off + 127) & ~size_t(127);
+    s.gtile = reinterpret_cast<float*>(raw + off);
+    s.cscale = s.gtile + (size_t)a.ngstages * s.stage_floats;
+    s.gfull = reinterpret_cast<uint64_t*>(s.cscale + a.chunk);
+    s.gempty = s.gfull + a.ngstages;
+    s.gated = s.gempty + a.ngstages;
+  }
   return s;
 }
 
@@ -101,7 +126,8 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
 }
 // Waiting warps back off with nanosleep: a bare try_wait loop retried ~35 times per wait (measured) and took a third of the
-// SM's issue slots away from the warps that had work.
+// SM's issue slots away from the warps that had work. (try_wait with a 10 ms suspend-time hint instead of the sleep: no polling
+// instructions at all, but the wake-up is ~80 cycles slower per hand-off and the kernels measure the same or 3 % slower.)
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -128,8 +154,10 @@ __device__ __forceinline__ float warp_max_f32(float v) {       // sm_100a: one R
 
 // ROWS / B4W (float4 columns per box row) > 0: compile-time shape (fully unrolled inner loops); 0: taken from the arguments
 // KT > 0: compile-time shift taps (source rows hoisted into registers, fully unrolled); 0: runtime k through the table
-template <int CS, int ROWS, int B4W, int KT>
-__global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap, PipeArgs a) {
+template <int CS, int ROWS, int B4W, int KT, bool GATE>
+__global__ void __launch_bounds__(RP_THREADS + (GATE ? RP_GWARPS * 32 : 0), 1)
+row_attention_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap gmap, PipeArgs a) {
+  constexpr int NTHREADS = RP_THREADS + (GATE ? RP_GWARPS * 32 : 0);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -155,13 +183,24 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       mbar_init(&s.wready[i], 1);
     }
     for (int i = 0; i < NZ; ++i) mbar_init(&s.zfull[i], 1);
+    if (GATE) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&gmap) : "memory");
+      for (int i = 0; i < a.ngstages; ++i) {
+        mbar_init(&s.gfull[i], 1);
+        mbar_init(&s.gempty[i], RP_GWARPS);
+      }
+      for (int i = 0; i < NS; ++i) mbar_init(&s.gated[i], RP_GWARPS);
+    }
     mbar_fence_init();
     for (int i = 0; i < NZ; ++i) mbar_expect_tx(&s.zfull[i], z_tx);
   }
   // target-slice tails past D stay zero for the whole kernel (the tile tail is zero-filled by TMA); weight padding too
-  for (int i = threadIdx.x; i < NS * chunk; i += RP_THREADS) s.tv[i] = 0.f;
-  for (int i = threadIdx.x; i < NS * rp; i += RP_THREADS) s.wts[i] = 0.f;
-  for (int i = threadIdx.x; i < rows * k; i += RP_THREADS) {          // circular shift along the heading axis (model.py:333-349)
+  for (int i = threadIdx.x; i < NS * chunk; i += NTHREADS) s.tv[i] = 0.f;
+  for (int i = threadIdx.x; i < NS * rp; i += NTHREADS) s.wts[i] = 0.f;
+  if (GATE)
+    for (int i = threadIdx.x; i < chunk; i += NTHREADS)
+      s.cscale[i] = (a.chan_scale != nullptr && c0 + i < a.gate_C) ? a.chan_scale[c0 + i] : 1.f;
+  for (int i = threadIdx.x; i < rows * k; i += NTHREADS) {          // circular shift along the heading axis (model.py:333-349)
     const int r = i / k, jj = i % k;
     const int e = r / Hn, l = r % Hn;
     int src = (l + jj - k / 2) % Hn;
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       const int offA = min(rA, rows - 1) * boxw, offB = min(rB, rows - 1) * boxw;
       for (int i = 0; i < n; ++i) {
         const int st = i % NS, zs = i % NZ;
-        mbar_wait_sleep(&s.full[st], (uint32_t)(i / NS) & 1u);
+        mbar_wait_sleep(GATE ? &s.gated[st] : &s.full[st], (uint32_t)(i / NS) & 1u);
         if (wid == 0) RP_STAMP(i, 1);
         const float* tile = s.tile + (size_t)st * s.stage_floats + (box_ok ? bl * a.box_stride : 0);
         const float4* tv4 = reinterpret_cast<const float4*>(s.tv + (size_t)st * chunk + (box_ok ? bl * boxw : 0));
@@ -247,6 +286,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
         const int st = i % NS;
         const int b = cid + i * a.nclusters;
         mbar_wait_sleep(&s.wready[st], (uint32_t)(i / NS) & 1u);
+        if (GATE) mbar_wait_sleep(&s.gated[st], (uint32_t)(i / NS) & 1u);   // direct acquire of the gate warps' writes (long complete)
         if (box == 0) RP_STAMP(i, 5);
         const float* tile = s.tile + (size_t)st * s.stage_floats + (size_t)box * a.box_stride;
         const float4* w4 = reinterpret_cast<const float4*>(s.wts + (size_t)st * rp);
@@ -372,9 +412,112 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       }
       __syncwarp();                              // pw / kw are rewritten by the next sample of this warp
     }
-  } else if (lane == 0) {
+  } else if (GATE && wid >= RP_WARPS) {
+    // ------------- gate warps: slice *= sigmoid(g) (* chan_scale) in place for the channels below gate_C (agent_dg.py:1544-1547).
+    // sigmoid on raw MUFU ex2 / rcp: relative error <= ~4e-7 for |g| <= 16 (2-ulp ex2, 1-ulp rcp, argument rounding |g|*2^-24)
+    constexpr int GT = RP_GWARPS * 32;
+    const int gt = (int)threadIdx.x - RP_THREADS;
+    const int NG = a.ngstages;
+    const int b4w = boxw >> 2, per_box4 = rows * b4w;
+    int ngb = 0;                                                   // boxes of this CTA that hold gated channels
+    while (ngb < nbox && c0 + ngb * boxw < a.gate_C) ++ngb;
+    const bool has_scale = a.chan_scale != nullptr;
+    const int col0 = gt % b4w, dcol = GT % b4w;
+    // sigmoid on bare MUFU: e = ex2(min(-g*log2(e), 60)) (the clamp bounds 1+e by 2^60 so that the product of two of them stays
+    // finite; sigmoid(g) for g < -41.6 then reads 8.7e-19 instead of a smaller positive number), ONE rcp per channel pair:
+    // 1/a = b * rcp(a*b), 1/b = a * rcp(a*b). Relative error <= ~5e-7 for |g| <= 16 (2-ulp ex2, 1-ulp rcp, argument rounding).
+    auto ex2n = [](float g) {
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(g * -1.4426950408889634f, 60.f)));
+      return 1.f + e;
+    };
+    auto rcpa = [](float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; };
+    auto modulate = [&](float4& v, const float4& gv) {
+      const float a0 = ex2n(gv.x), a1 = ex2n(gv.y), a2 = ex2n(gv.z), a3 = ex2n(gv.w);
+      const float r01 = rcpa(a0 * a1), r23 = rcpa(a2 * a3);
+      v.x *= a1 * r01; v.y *= a0 * r01; v.z *= a3 * r23; v.w *= a2 * r23;
+    };
+    // compile-time shape: IT float4 per thread and box, all loads of a box issued before the first MUFU
+    constexpr int IT = (ROWS && B4W) ? (ROWS * B4W + GT - 1) / GT : 1;
+    int cols[IT];
+#pragma unroll
+    for (int m = 0; m < IT; ++m) cols[m] = (gt + m * GT) % b4w;
+    for (int i = 0; i < n; ++i) {
+      const int st = i % NS, gs = i % NG;
+      mbar_wait_sleep(&s.full[st], (uint32_t)(i / NS) & 1u);
+      if (ngb > 0) mbar_wait_sleep(&s.gfull[gs], (uint32_t)(i / NG) & 1u);
+      float4* tile_st = reinterpret_cast<float4*>(s.tile + (size_t)st * s.stage_floats);
+      const float4* gate_st = reinterpret_cast<const float4*>(s.gtile + (size_t)gs * s.stage_floats);
+      const int bs4 = a.box_stride >> 2;
+      if (ROWS && B4W) {
+        // all loads of a box are issued before its first MUFU. (A ping-pong prefetch of the next box was tried: slower under
+        // the 80-register cap of the 672-thread block, 719 vs 530 us at B=4096.)
+        float4 gv[1][IT], fv[1][IT];
+        bool on[1][IT];
+        auto fetch = [&](int sb, float4 (&g_)[IT], float4 (&f_)[IT], bool (&on_)[IT]) {
+          const int climit = (a.gate_C - (c0 + sb * boxw)) >> 2;   // float4 columns of this box below gate_C
+#pragma unroll
+          for (int m = 0; m < IT; ++m) {
+            const int idx = gt + m * GT;
+            on_[m] = idx < per_box4 && cols[m] < climit;
+            if (on_[m]) { g_[m] = gate_st[sb * bs4 + idx]; f_[m] = tile_st[sb * bs4 + idx]; }
+          }
+        };
+        auto finish = [&](int sb, float4 (&g_)[IT], float4 (&f_)[IT], bool (&on_)[IT]) {
+          const float4* cs4 = reinterpret_cast<const float4*>(s.cscale + sb * boxw);
+#pragma unroll
+          for (int m = 0; m < IT; ++m) {
+            if (on_[m]) {
+              modulate(f_[m], g_[m]);
+              if (has_scale) {
+                const float4 sc = cs4[cols[m]];
+                f_[m].x *= sc.x; f_[m].y *= sc.y; f_[m].z *= sc.z; f_[m].w *= sc.w;
+              }
+              tile_st[sb * bs4 + gt + m * GT] = f_[m];
+            }
+          }
+        };
+        for (int sb = 0; sb < ngb; ++sb) {
+          fetch(sb, gv[0], fv[0], on[0]);
+          finish(sb, gv[0], fv[0], on[0]);
+        }
+      } else {
+        for (int sb = 0; sb < ngb; ++sb) {
+          float4* tile4 = tile_st + sb * bs4;
+          const float4* g4 = gate_st + sb * bs4;
+          const float4* cs4 = reinterpret_cast<const float4*>(s.cscale + sb * boxw);
+          const int climit = (a.gate_C - (c0 + sb * boxw)) >> 2;
+          int col = col0;
+          for (int idx = gt; idx < per_box4; idx += GT) {
+            if (col < climit) {
+              const float4 gv = g4[idx];
+              float4 v = tile4[idx];
+              modulate(v, gv);
+              if (has_scale) {
+                const float4 sc = cs4[col];
+                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+              }
+              tile4[idx] = v;
+            }
+            col += dcol;
+            if (col >= b4w) col -= b4w;
+          }
+        }
+      }
+      __syncwarp();
+      if (gt == 0) RP_STAMP(i, 7);
+      if (lane == 0) {
+        mbar_arrive(&s.gated[st]);                                 // release: the modulated slice is visible to the dot warps
+        if (ngb > 0) mbar_arrive(&s.gempty[gs]);
+      }
+    }
+  } else if (wid == RP_WARPS - 1 && lane == 0) {
     // ------------------------------------------------------------------------- producer: TMA loads into the stage ring
     const uint32_t stage_tx = (uint32_t)nbox * (uint32_t)rows * (uint32_t)boxw * 4u + (uint32_t)cn * 4u;
+    int ngb = 0;
+    if (GATE) while (ngb < nbox && c0 + ngb * boxw < a.gate_C) ++ngb;
+    const uint32_t gate_tx = (uint32_t)ngb * (uint32_t)rows * (uint32_t)boxw * 4u;
+    const int NG = GATE ? a.ngstages : 1;
     for (int j = 0; j < n; ++j) {
       const int st = j % NS;
       const int b = cid + j * a.nclusters;
@@ -384,6 +527,13 @@ __global__ void __launch_bounds__(RP_THREADS, 1) row_attention_fwd_pipe_kernel(c
       float* dst = s.tile + (size_t)st * s.stage_floats;
       for (int sb = 0; sb < nbox; ++sb) tma_box_3d(dst + (size_t)sb * a.box_stride, &tmap, c0 + sb * boxw, 0, b, &s.full[st]);
       if (cn > 0) bulk_g2s(s.tv + (size_t)st * chunk, a.t + (int64_t)b * a.ld_t + c0, (uint32_t)cn * 4u, &s.full[st]);
+      if (GATE && ngb > 0) {
+        const int gs = j % NG;
+        if (j >= NG) mbar_wait_sleep(&s.gempty[gs], (uint32_t)(j / NG - 1) & 1u);
+        mbar_expect_tx(&s.gfull[gs], gate_tx);
+        float* gdst = s.gtile + (size_t)gs * s.stage_floats;
+        for (int sb = 0; sb < ngb; ++sb) tma_box_3d(gdst + (size_t)sb * a.box_stride, &gmap, c0 + sb * boxw, 0, b, &s.gfull[gs]);
+      }
     }
   }
 #undef RP_STAMP
@@ -397,9 +547,9 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int CS, int ROWS, int B4W, int KT>
-int launch_pipe(const CUtensorMap& tmap, PipeArgs a, size_t smem, cudaStream_t st) {
-  auto kern = row_attention_fwd_pipe_kernel<CS, ROWS, B4W, KT>;
+template <int CS, int ROWS, int B4W, int KT, bool GATE = false>
+int launch_pipe(const CUtensorMap& tmap, const CUtensorMap& gmap, PipeArgs a, size_t smem, cudaStream_t st) {
+  auto kern = row_attention_fwd_pipe_kernel<CS, ROWS, B4W, KT, GATE>;
   static int max_clusters = -1;                  // per (CS) instantiation; the smem request below is the worst case
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe attr", e); return DASA_ERR_CUDA; }
@@ -408,7 +558,7 @@ int launch_pipe(const CUtensorMap& tmap, PipeArgs a, size_t smem, cudaStream_t s
     if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe cluster attr", e); return DASA_ERR_CUDA; }
   }
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(RP_THREADS);
+  cfg.blockDim = dim3(RP_THREADS + (GATE ? RP_GWARPS * 32 : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -429,21 +579,29 @@ int launch_pipe(const CUtensorMap& tmap, PipeArgs a, size_t smem, cudaStream_t s
   }
   a.nclusters = a.B < max_clusters ? a.B : max_clusters;
   cfg.gridDim = dim3((unsigned)(a.nclusters * CS));
-  e = cudaLaunchKernelEx(&cfg, kern, tmap, a);
-  if (e != cudaSuccess) { dasa_set_error("row_attention_fwd_pipe", e); return DASA_ERR_CUDA; }
+  e = cudaLaunchKernelEx(&cfg, kern, tmap, gmap, a);
+  if (e != cudaSuccess) { dasa_set_error(GATE ? "row_attention_fwd_pipe<gate>" : "row_attention_fwd_pipe", e); return DASA_ERR_CUDA; }
   return DASA_OK;
 }
 
 }  // namespace
 
 // Returns DASA_ERR_UNSUPPORTED when the shape does not fit this kernel (the caller then uses the one-shot cluster kernel).
+// gate != nullptr: fused DGAdaChannel epilogue (GATE variant; requires shift_k > 0 only because that is the only caller).
 int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t ld_sample, int B, int rows, int D, const float* t,
                                      int64_t ld_t, int shift_k, int headings, const float* kappa_logits, int64_t ld_kappa,
-                                     float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, cudaStream_t st) {
+                                     float* wc, int64_t ld_wc, float* attn_out, float* q_out, float* kappa_out, cudaStream_t st,
+                                     const float* gate, int64_t ld_grow, int64_t ld_gsample, int gate_C, const float* chan_scale) {
   if (rows > RP_MAX_ROWS || shift_k > RP_MAX_K || D % 4 != 0) return DASA_ERR_UNSUPPORTED;
   if (!dasa_aligned16(t) || ld_t % 4 != 0 || !dasa_aligned16(wc) || ld_wc % 4 != 0) return DASA_ERR_UNSUPPORTED;
-  // channel slice per CTA, split into <= 4 TMA boxes of equal width (<= 256 floats); prefer an odd number of float4 per box row
-  int best_cs = 0, best_ns = 0, best_nbox = 0, best_boxw = 0, best_stride = 0;
+  const bool gated = gate != nullptr;
+  if (gated && (gate_C <= 0 || gate_C > D || gate_C % 4 != 0 || !dasa_aligned16(gate) || ld_grow % 4 != 0 || ld_gsample % 4 != 0))
+    return DASA_ERR_UNSUPPORTED;
+  // channel slice per CTA, split into <= 4 TMA boxes of equal width (<= 256 floats); prefer an odd number of float4 per box row.
+  // Ring depths: plain = the deepest NS in [3, 8] that fits; gated = (NS, NG) from the list below (the gate ring is released
+  // right after the modulation, so it can be shallower than the feature ring).
+  static const int gate_rings[][2] = {{4, 3}, {4, 2}, {3, 2}};
+  int best_cs = 0, best_ns = 0, best_ng = 0, best_nbox = 0, best_boxw = 0, best_stride = 0;
   for (int cs = 8; cs <= 16 && best_cs == 0; cs *= 2) {
     const int c4 = (int)dasa_cdiv(D / 4, cs);                        // float4 columns per CTA
     if ((int64_t)(cs - 1) * c4 * 4 >= D) continue;                   // every rank owns >= 1 column
@@ -454,10 +612,17 @@ int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t l
         if ((int64_t)b4 * nbox != c4) continue;                      // equal boxes tile the slice exactly (no overlap with the peer)
         const int boxw = b4 * 4;
         const int stride = (int)(dasa_cdiv((int64_t)rows * boxw, 32) * 32);   // floats; 128-byte aligned box bases
-        int ns = 8;
-        while (ns >= 3 && rp_smem_bytes(rows, nbox * boxw, nbox, stride, cs, ns, shift_k) > 227 * 1024) --ns;
-        if (ns < 3) continue;
-        best_cs = cs; best_ns = ns; best_nbox = nbox; best_boxw = boxw; best_stride = stride;
+        int ns = 0, ng = 0;
+        if (!gated) {
+          ns = 8;
+          while (ns >= 3 && rp_smem_bytes(rows, nbox * boxw, nbox, stride, cs, ns, shift_k) > 227 * 1024) --ns;
+          if (ns < 3) continue;
+        } else {
+          for (const auto& r : gate_rings)
+            if (rp_smem_bytes(rows, nbox * boxw, nbox, stride, cs, r[0], shift_k, r[1]) <= 227 * 1024) { ns = r[0]; ng = r[1]; break; }
+          if (ns == 0) continue;
+        }
+        best_cs = cs; best_ns = ns; best_ng = ng; best_nbox = nbox; best_boxw = boxw; best_stride = stride;
         break;
       }
     }
@@ -466,7 +631,7 @@ int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t l
   const int cs = best_cs, ns = best_ns, nbox = best_nbox, boxw = best_boxw, chunk = best_nbox * best_boxw;
   EncodeFn enc = reinterpret_cast<EncodeFn>(dasa_tensormap_encoder());
   if (enc == nullptr) return DASA_ERR_UNSUPPORTED;
-  CUtensorMap tmap;
+  CUtensorMap tmap, gmap;
   cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld_row * 4, (cuuint64_t)ld_sample * 4};
   cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)rows, 1};
@@ -474,13 +639,27 @@ int dasa_row_attention_fwd_pipelined(const float* ctx, int64_t ld_row, int64_t l
   if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ctx), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DASA_ERR_UNSUPPORTED;
+  gmap = tmap;
+  if (gated) {
+    cuuint64_t gdims[3] = {(cuuint64_t)gate_C, (cuuint64_t)rows, (cuuint64_t)B};
+    cuuint64_t gstrides[2] = {(cuuint64_t)ld_grow * 4, (cuuint64_t)ld_gsample * 4};
+    if (enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(gate), gdims, gstrides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DASA_ERR_UNSUPPORTED;
+  }
   PipeArgs a{t, ld_t, kappa_logits, ld_kappa, wc, ld_wc, attn_out, q_out, kappa_out,
-             B, rows, D, chunk, nbox, boxw, best_stride, shift_k, headings, ns, 0, g_trace};
-  const size_t smem = rp_smem_bytes(rows, chunk, nbox, best_stride, cs, ns, shift_k);
+             B, rows, D, chunk, nbox, boxw, best_stride, shift_k, headings, ns, 0, g_trace, gate_C, best_ng, chan_scale};
+  const size_t smem = rp_smem_bytes(rows, chunk, nbox, best_stride, cs, ns, shift_k, best_ng);
   const int b4 = boxw / 4;
-  if (cs == 8 && rows == 36 && b4 == 17 && shift_k == 5) return launch_pipe<8, 36, 17, 5>(tmap, a, smem, st);     // 36 x (2048+128), k=5
-  if (cs == 16 && rows == 36 && b4 == 33 && shift_k == 5) return launch_pipe<16, 36, 33, 5>(tmap, a, smem, st);   // 36 x (4096+128), k=5
-  return cs == 8 ? launch_pipe<8, 0, 0, 0>(tmap, a, smem, st) : launch_pipe<16, 0, 0, 0>(tmap, a, smem, st);
+  if (gated) {
+    if (cs == 8 && rows == 36 && b4 == 17 && shift_k == 5) return launch_pipe<8, 36, 17, 5, true>(tmap, gmap, a, smem, st);
+    if (cs == 16 && rows == 36 && b4 == 33 && shift_k == 5) return launch_pipe<16, 36, 33, 5, true>(tmap, gmap, a, smem, st);
+    return cs == 8 ? launch_pipe<8, 0, 0, 0, true>(tmap, gmap, a, smem, st) : launch_pipe<16, 0, 0, 0, true>(tmap, gmap, a, smem, st);
+  }
+  if (cs == 8 && rows == 36 && b4 == 17 && shift_k == 5) return launch_pipe<8, 36, 17, 5>(tmap, gmap, a, smem, st);     // 36 x (2048+128), k=5
+  if (cs == 16 && rows == 36 && b4 == 33 && shift_k == 5) return launch_pipe<16, 36, 33, 5>(tmap, gmap, a, smem, st);   // 36 x (4096+128), k=5
+  return cs == 8 ? launch_pipe<8, 0, 0, 0>(tmap, gmap, a, smem, st) : launch_pipe<16, 0, 0, 0>(tmap, gmap, a, smem, st);
 }
 
 // Debug hook for scripts/: stamps of the pipeline hand-offs go to `buf` ([CTAs][ceil(B/clusters)][8] int64); nullptr = off.

@@ -26,9 +26,17 @@ def timeit(fn, reps=7):
 
 V, A = 36, 128
 batches = [1, 4, 16, 64, 256, 512, 1024, 2048, 4096, 8192]
+channels = (2048, 3072, 4096)
+only = None
+if len(sys.argv) > 1:      # quick runs: micro_sweep.py "2048,4096" "512,4096" ["K3,fused"]
+    channels = tuple(int(x) for x in sys.argv[1].split(","))
+    if len(sys.argv) > 2:
+        batches = [int(x) for x in sys.argv[2].split(",")]
+    if len(sys.argv) > 3:
+        only = sys.argv[3].split(",")
 rows = []
 print("# kernel, C, B, us, GB/s, %% of measured HBM peak (%.0f GB/s), %% of the nominal 8 TB/s" % peak)
-for C in (2048, 3072, 4096):
+for C in channels:
     F = C + A
     for B in batches:
         if B * V * F * 4 * 3 > 60e9:
@@ -51,6 +59,8 @@ for C in (2048, 3072, 4096):
              lambda: (ops.gate_modulate(g, f[..., :C], o[..., :C]), ops.row_attention_fwd(o, t_, None, 5, 12, kl))),
         ]
         for name, byt, fn in cases:
+            if only and not any(o in name for o in only):
+                continue
             s = timeit(fn)
             gbs = byt / s / 1e9
             rows.append((name, C, B, s * 1e6, gbs, gbs / peak))
