@@ -135,7 +135,41 @@ __global__ void env_step_kernel(const int64_t* __restrict__ action, int ignore_i
   if (traj_view != nullptr) traj_view[b] = w;
 }
 
+// --submit (agent_dg.py:834-840, "avoiding cyclic path"): the current viewpoint joins the episode's visited set (a bitmap over
+// the viewpoints), every candidate whose viewpoint is in the set is masked: blocked[b, k] = 1 and logit[b, k] = -inf. The END
+// slot (k == deg) is not an entry of ob['candidate'] and is never masked. One thread per episode (B x dmax table reads).
+__global__ void env_visited_mask_kernel(const int32_t* __restrict__ vp, const int32_t* __restrict__ nbr,
+                                        const int32_t* __restrict__ deg, int dmax, uint32_t* __restrict__ visited, int words,
+                                        uint8_t* __restrict__ blocked, int nc, float* __restrict__ logit, int64_t ld_logit, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int v = vp[b];
+  uint32_t* vis = visited + (int64_t)b * words;
+  vis[v >> 5] |= 1u << (v & 31);
+  const int dg = deg[v];
+  for (int k = 0; k < nc; ++k) {
+    bool hit = false;
+    if (k < dg && k < dmax) {
+      const int u = nbr[(int64_t)v * dmax + k];
+      hit = (vis[u >> 5] >> (u & 31)) & 1u;
+    }
+    if (blocked != nullptr) blocked[(int64_t)b * nc + k] = hit ? 1 : 0;
+    if (hit && logit != nullptr) logit[(int64_t)b * ld_logit + k] = -INFINITY;
+  }
+}
+
 }  // namespace
+
+extern "C" int dasa_env_visited_mask(const int32_t* vp, const int32_t* nbr, const int32_t* deg, int dmax, int n_vp,
+                                     uint32_t* visited, int words, uint8_t* blocked, int nc, float* logit, int64_t ld_logit,
+                                     int B, void* stream) {
+  if (B <= 0) return DASA_OK;
+  if (n_vp <= 0 || dmax <= 0 || nc <= 0 || visited == nullptr || words * 32 < n_vp || (logit != nullptr && ld_logit < nc))
+    return DASA_ERR_BAD_SHAPE;
+  env_visited_mask_kernel<<<(unsigned)dasa_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(vp, nbr, deg, dmax, visited, words, blocked,
+                                                                                       nc, logit, ld_logit, B);
+  return dasa_check_launch("env_visited_mask_kernel");
+}
 
 extern "C" int dasa_env_observe(const float* rgb_bank, const float* dep_bank, const int32_t* nbr, const int32_t* nbr_point,
                                 const int32_t* deg, const float* cand_angle, const float* view_angle, const float* agent_angle,

@@ -54,6 +54,7 @@ class DeviceEnv:
         self.goal.copy_(torch.as_tensor(goal, dtype=torch.int32), non_blocking=True)
         self.ended.zero_()
         self.err.zero_()
+        self.visited = None                                     # --submit: allocated (zeroed) by the first visited_mask()
         # last_dist = the start's distance to the goal (agent_dg.py:693-695): one gather on the device
         torch.index_select(self.t_dist.view(-1), 0, self.vp.long() * self.n_vp + self.goal.long(), out=self.last_dist)
         return self
@@ -86,6 +87,19 @@ class DeviceEnv:
         ops.call("dasa_env_step", p(action), self.cfg.ignore_id, p(self.t_nbr), p(self.t_nbr_point), p(self.t_deg), self.dmax,
                  p(self.t_dist), self.n_vp, p(self.vp), p(self.view), p(self.goal), p(self.ended), p(self.last_dist), p(reward),
                  p(mask), p(traj_vp), p(traj_view), p(self.err), self.B, ops._stream())
+
+    def visited_mask(self, logit=None, want_mask=False):
+        """--submit (agent_dg.py:834-840): the current viewpoints join the per-episode visited sets; candidates leading back to
+        a visited viewpoint get logit = -inf (in place). Returns the uint8 [B, nc] mask when `want_mask`."""
+        words = (self.n_vp + 31) // 32
+        if self.visited is None:
+            self.visited = torch.zeros(self.B, words, dtype=torch.int32, device=self.device)
+        blocked = torch.empty(self.B, self.nc, dtype=torch.uint8, device=self.device) if want_mask else None
+        p = ops._p
+        assert logit is None or (logit.dtype == torch.float32 and logit.stride(1) == 1 and logit.shape[1] >= self.nc)
+        ops.call("dasa_env_visited_mask", p(self.vp), p(self.t_nbr), p(self.t_deg), self.dmax, self.n_vp, p(self.visited), words,
+                 p(blocked), self.nc, p(logit), 0 if logit is None else logit.stride(0), self.B, ops._stream())
+        return blocked
 
     def check(self):
         """Host-side check of the device error word (one sync; call it after a rollout, not inside)."""

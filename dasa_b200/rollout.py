@@ -271,12 +271,18 @@ class NavPolicy:
         Fn.flush_weight_grads()
 
     @torch.no_grad()
-    def greedy_rollout(self, ep, T=None):
-        """feedback='argmax' decode (agent_dg.py:871-875) over pre-generated observations: per-step greedy actions."""
+    def greedy_rollout(self, ep, T=None, submit=False):
+        """feedback='argmax' decode (agent_dg.py:871-875) over pre-generated observations: per-step greedy actions.
+        submit=True (args.submit, agent_dg.py:834-840; live environment episodes only): candidates that lead back to an already
+        visited viewpoint are masked before the argmax."""
         T = ep.T if T is None else T
         carry, actions, logits = None, [], []
+        if submit and not getattr(ep, "live", False):
+            raise ValueError("submit=True needs live environment episodes (the visited sets follow the agent's own actions)")
         for t in range(T):
             logit, h_t, carry = self.step(ep, t, carry)
+            if submit:
+                ep.env.visited_mask(logit)
             _, a_t, _, _ = ops.masked_ce(logit, None, self.cfg.ignore_id, 0.0, None, want_grad=False)
             if getattr(ep, "live", False):
                 ep.advance(t, a_t)

@@ -550,6 +550,13 @@ int dasa_env_step(const int64_t* action, int ignore_id, const int32_t* nbr, cons
                   uint8_t* ended, float* last_dist, float* reward, float* mask, int32_t* traj_vp, int32_t* traj_view,
                   int32_t* err, int B, void* stream);
 
+/* --submit "avoiding cyclic path" (agent_dg.py:834-840): add the current viewpoint of every episode to its visited set
+ * (`visited`: [B, words] uint32 bitmap over the viewpoints, words*32 >= n_vp, zeroed at reset), then mask every candidate whose
+ * viewpoint was visited: blocked[b, k] = 1 (uint8 [B, nc], may be NULL) and logit[b, k] = -inf (fp32 [B, ld_logit], may be NULL).
+ * The END slot is never masked (it is not an entry of ob['candidate']). */
+int dasa_env_visited_mask(const int32_t* vp, const int32_t* nbr, const int32_t* deg, int dmax, int n_vp, uint32_t* visited,
+                          int words, uint8_t* blocked, int nc, float* logit, int64_t ld_logit, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,18 @@ def teacher_action(obs, ended, ignoreid=-100):
     return a
 
 
+def submit_candidate_mask(obs, visited, max_cand):
+    """agent_dg.py:834-840 (args.submit, "avoiding cyclic path"): the current viewpoint joins visited[ob_id]; a candidate whose
+    viewpointId was visited is masked. `visited`: list of python sets, mutated like the reference's. Returns bool [B, max_cand]."""
+    mask = np.zeros((len(obs), max_cand), dtype=bool)
+    for ob_id, ob in enumerate(obs):
+        visited[ob_id].add(ob["viewpoint"])
+        for c_id, c in enumerate(ob["candidate"]):
+            if c["viewpointId"] in visited[ob_id]:
+                mask[ob_id][c_id] = True
+    return mask
+
+
 def env_action(a_t, cand_leng, ignoreid=-100):
     """agent_dg.py:890-893: <end> and ignore become -1."""
     cpu_a_t = np.array(a_t, dtype=np.int64).copy()

@@ -84,3 +84,25 @@ def test_union_of_scans():
     assert (h[:14, 14:] == -1).all() and np.array_equal(h[14:, 14:], g2.hops())
     s, v, goal = u.sample_episodes(12, 0, min_hops=2, max_hops=5)
     assert ((s < 14) == (goal < 14)).all()                      # start and goal always in the same scan
+
+
+def test_oracle_submit_mask_blocks_the_way_back():
+    """agent_dg.py:834-840 as restated in the oracle: after moving a -> b the candidate leading back to a is masked at b, the
+    END slot never is, and the sets only grow."""
+    g, rgb, dep, start, view, goal = scenario(n=24, B=4, seed=2)
+    env = E.RefStyleEnv("s", features=rgb, dfeatures=dep, **lists(g))
+    env.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+    nc = g.dmax + 1
+    visited = [set() for _ in start]
+    obs = env.get_obs()
+    m0 = E.submit_candidate_mask(obs, visited, nc)
+    assert not m0.any()                                   # nothing visited yet except the current viewpoints
+    first = [ob["viewpoint"] for ob in obs]
+    env.make_equiv_action(np.zeros(len(start), np.int64), obs)          # everybody takes candidate 0
+    obs = env.get_obs()
+    m1 = E.submit_candidate_mask(obs, visited, nc)
+    for i, ob in enumerate(obs):
+        back = [k for k, c in enumerate(ob["candidate"]) if c["viewpointId"] == first[i]]
+        assert back and all(m1[i, k] for k in back)
+        assert not m1[i, len(ob["candidate"]):].any()     # END slot and padding
+        assert visited[i] == {first[i], ob["viewpoint"]}

@@ -304,3 +304,71 @@ def test_env_on_a_union_of_scans():
     env, buf, reward, mask, ended, vps, views = _device_rollout(g, rgb, dep, start, view, goal, T, None, cfg)
     _compare(steps, g, buf, reward, mask, ended, vps, views, T)
     env.check()
+
+
+@pytest.mark.parametrize("seed,n,B", [(0, 24, 5), (3, 40, 11)])
+def test_submit_visited_mask_matches_oracle(seed, n, B):
+    """--submit "avoiding cyclic path" (agent_dg.py:834-840): the device bitmap + mask kernel against the oracle's python sets on a
+    random closed-loop walk; masked logits are -inf exactly where the oracle masks, untouched elsewhere."""
+    from dasa_b200.env import DeviceEnv
+    T, C = 9, 32
+    g, rgb, dep, start, view, goal = scenario(n, B, T, C, seed)
+    cfg = _cfg(C)
+    acts = random_actions(g, start, T, seed, stop_prob=0.1)
+    env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+    ref = E.RefStyleEnv("scan0", **lists(g), features=rgb, dfeatures=dep, angle_size=cfg.angle_size)
+    ref.new_episodes([g.names[i] for i in start], view, [g.names[i] for i in goal])
+    visited = [set() for _ in range(B)]
+    gen = torch.Generator().manual_seed(seed)
+    for t in range(T):
+        obs = ref.get_obs()
+        want = E.submit_candidate_mask(obs, visited, env.nc)
+        logit = torch.randn(B, env.nc, generator=gen).to(DEV)
+        before = logit.clone()
+        got = env.visited_mask(logit, want_mask=True)
+        assert np.array_equal(got.cpu().numpy().astype(bool), want), "step %d mask" % t
+        w = torch.from_numpy(want).to(DEV)
+        assert torch.isneginf(logit[w]).all() and torch.equal(logit[~w], before[~w]), "step %d logits" % t
+        a = np.asarray(acts[t])
+        leng = [len(ob["candidate"]) + 1 for ob in obs]
+        ref.make_equiv_action(E.env_action(a, leng), obs)
+        env.step(torch.as_tensor(a).to(DEV))
+    torch.cuda.synchronize()
+    if t > 2:
+        assert any(len(v) > 2 for v in visited)
+
+
+def test_greedy_rollout_submit_never_revisits():
+    """feedback='argmax' with args.submit (agent_dg.py:834-840, 871-875) in closed loop on the device environment: with the visited
+    mask no episode ever steps onto a viewpoint it has been to (it may only stop), and the masked logits are -inf exactly for the
+    candidates leading to its own past trajectory; without the mask the same policy does revisit (so the property is not vacuous)."""
+    from dasa_b200.env import DeviceEnv
+    from dasa_b200.rollout import NavPolicy
+    cfg, B, T = SMALL, 8, 8
+    g, rgb, dep, start, view, goal = scenario(n=12, B=B, T=T, C=cfg.rgb_size, seed=4)
+    instr = synth.instructions(B, cfg, 4)
+    pol = NavPolicy(cfg, synth.policy_state(cfg, 3), DEV).eval()
+    revisits = {}
+    for submit in (False, True):
+        env = DeviceEnv(g, rgb, dep, cfg, DEV).reset(start, view, goal)
+        ep = env.live_episodes(T, instr)
+        actions, logits = pol.greedy_rollout(ep, T, submit=submit)
+        torch.cuda.synchronize()
+        env.check()
+        traj = ep.traj[:T + 1].cpu().numpy()                  # [T + 1, B] viewpoints, traj[0] = start
+        n_rev = 0
+        for b in range(B):
+            seen = {int(traj[0, b])}
+            for t in range(T):
+                a, v = int(actions[t][b]), int(traj[t, b])
+                moved = a != int(g.deg[v])
+                if submit:                                    # mask check against the trajectory so far
+                    blocked = torch.isneginf(logits[t][b, :int(g.deg[v])]).cpu().numpy()
+                    want = np.array([int(g.nbr[v, k]) in seen for k in range(int(g.deg[v]))])
+                    assert np.array_equal(blocked, want), (b, t)
+                if moved:
+                    n_rev += int(traj[t + 1, b]) in seen
+                    seen.add(int(traj[t + 1, b]))
+        revisits[submit] = n_rev
+    assert revisits[True] == 0
+    assert revisits[False] > 0
