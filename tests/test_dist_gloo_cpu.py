@@ -79,3 +79,91 @@ def test_two_rank_gradients_equal_global_batch(tmp_path):
     loss.backward()
     want = torch.cat([train[k].grad.reshape(-1) for k in got["names"]])
     torch.testing.assert_close(got["flat"], want, rtol=1e-4, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The PRODUCT data-parallel loop (dasa_b200/trainer.py RolloutTrainer: per-rank ML scaling, batch-global A2C `total`,
+# per-group all-reduce, optimizer hand-off) over gloo with a stand-in policy: the rollouts are small differentiable torch
+# functions of the flat parameter buffers, so the test isolates exactly the host logic that has no GPU dependency. The same loop
+# with the real NavPolicy on two GPUs is tests/test_gpu_dist.py.
+class _StubPolicy:
+    """Quacks like rollout.NavPolicy for RolloutTrainer: two optimizer groups with flat parameter / gradient buffers."""
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(5)
+        self._flat = []
+        for name, n in (("decoder", 7), ("critic", 3)):
+            p = torch.randn(n, generator=g, dtype=torch.float64).requires_grad_(True)
+            p.grad = torch.zeros(n, dtype=torch.float64)
+            self._flat.append({"name": name, "params": [p], "clip": None, "flat_p": p.data, "flat_g": p.grad,
+                               "flat_sq": torch.zeros(n, dtype=torch.float64)})
+        self.iteration, self.steps_taken = 0, 0
+
+    def zero_grad(self):
+        for grp in self._flat:
+            grp["flat_g"].zero_()
+
+    def _features(self, ep):
+        return ep["x"] @ self._flat[0]["params"][0], ep["x"][:, :3] @ self._flat[1]["params"][0]
+
+    def teacher_rollout(self, ep, T, ml_weight, tag_steps=False):
+        # sum over the episodes * ml_weight / B_local, the shape of agent_dg.py:850, 1024
+        a, c = self._features(ep)
+        return ((a ** 2).sum() + c.sum()) * ml_weight / ep["x"].shape[0], None, None
+
+    def sample_rollout(self, ep, T, tag_steps=False, gamma=0.9, ent_coef=0.01, normalize="total", actions_in=None):
+        a, c = self._features(ep)
+        live = ep["live"]                                      # 0/1 per episode: the A2C mask; `total` = number of live pairs
+        rl = (live * (a * c)).sum()
+        total = live.sum().reshape(1)
+        if normalize == "total":
+            rl = rl / total.clamp(min=1.0)
+        elif normalize == "batch":
+            rl = rl / ep["x"].shape[0]
+        return rl, {"total": total}
+
+    def optim_step(self, lr, use_lr_scheduler=None):
+        self.steps_taken += 1
+
+
+def _stub_episodes(lo, hi):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(6, 7, generator=g, dtype=torch.float64)
+    live = torch.tensor([1., 0., 0., 1., 1., 1.], dtype=torch.float64)       # 1 vs 3 live pairs on the two shards
+    return {"x": x[lo:hi], "live": live[lo:hi]}
+
+
+def _trainer_worker(rank, world, port, out, feedback):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from dasa_b200 import modules as M
+    from dasa_b200.trainer import RolloutTrainer
+    ddist.init("gloo")
+    pol = _StubPolicy()
+    lo, hi = ddist.shard(6, rank, world)
+    tr = RolloutTrainer(pol, T=2, feedback=feedback, world=world, dropout_source=M.DropoutSource(seed=1, device="cpu"))
+    tr.broadcast_parameters()
+    tr.step(_stub_episodes(lo, hi))
+    assert pol.steps_taken == 1
+    if rank == 0:
+        torch.save([g["flat_g"].clone() for g in pol._flat], out)
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("feedback", ["teacher", "sample"])
+def test_rollout_trainer_two_ranks_equal_one_process(tmp_path, feedback):
+    """RolloutTrainer on 2 gloo ranks (episodes 0-2 / 3-5 with 1 vs 3 live pairs) leaves in every flat gradient buffer
+    exactly the gradient of ONE process running all 6 episodes: ML loss / global batch (agent_dg.py:1024), A2C loss / the
+    batch-global `total` (agent_dg.py:988-994) - the normaliser the round-1 loop got wrong."""
+    from dasa_b200 import modules as M
+    from dasa_b200.trainer import RolloutTrainer
+    out = str(tmp_path / "g.pt")
+    mp.start_processes(_trainer_worker, args=(2, _free_port(), out, feedback), nprocs=2, join=True, start_method="spawn")
+    got = torch.load(out)
+    pol = _StubPolicy()
+    tr = RolloutTrainer(pol, T=2, feedback=feedback, world=1, dropout_source=M.DropoutSource(seed=1, device="cpu"))
+    tr.step(_stub_episodes(0, 6))
+    for g, w in zip(got, pol._flat):
+        torch.testing.assert_close(g, w["flat_g"], rtol=1e-12, atol=1e-14)
+        assert float(w["flat_g"].abs().max()) > 0
