@@ -16,28 +16,9 @@
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "rng.cuh"
+#include "lstm_epi.cuh"
 
 namespace {
-
-// Dropout on the layer output (r2rmodel.py:2357 `ctx = self.drop(ctx)`), fused into the only kernel that writes / reads `out`:
-// keep flag of out[seq, l, c] from a mask tensor [R, L, 2H] or drawn in place (rng.cuh: stream byte (seq * L + l) * 2H + c).
-// Saves a 292 MB read + write pass in each direction (and the 73 MB mask) at the benchmark geometry.
-struct PkDrop { const uint8_t* mask; const unsigned long long* seed_dev; unsigned long long seed, base; uint32_t thr; int stream; float scale; };
-
-__device__ __forceinline__ float4 pk_drop4(const PkDrop& dr, int64_t e, float4 v) {   // e: element index of v.x (multiple of 4)
-  if (dr.mask != nullptr) {
-    const uint32_t m = *reinterpret_cast<const uint32_t*>(dr.mask + e);
-    v.x *= (m & 0xFFu) ? dr.scale : 0.f; v.y *= (m & 0xFF00u) ? dr.scale : 0.f;
-    v.z *= (m & 0xFF0000u) ? dr.scale : 0.f; v.w *= (m & 0xFF000000u) ? dr.scale : 0.f;
-  } else if (dr.stream) {
-    DropStream ds;
-    ds.mixed = mix_seed(dr.seed_dev ? dr.seed_dev[0] : dr.seed); ds.base = dr.base; ds.thr = dr.thr;
-    const uint32_t k4 = stream_keep4(ds, (uint64_t)e >> 2);
-    v.x *= (k4 & 1u) ? dr.scale : 0.f; v.y *= (k4 & 2u) ? dr.scale : 0.f;
-    v.z *= (k4 & 4u) ? dr.scale : 0.f; v.w *= (k4 & 8u) ? dr.scale : 0.f;
-  }
-  return v;
-}
 
 struct PkFwd {
   const float* xp[2]; const float* gh[2]; const float* b_ih[2]; const float* b_hh[2];
@@ -202,7 +183,29 @@ inline PkDrop pk_drop(const uint8_t* mask, const uint64_t* seed_dev, uint64_t se
   return d;
 }
 
+// out[c][k] = fp16(W_hh[gate * H + u][k]) with c = nt * 256 + ch * 128 + gate * 32 + ul, u = nt * 64 + ch * 32 + ul (lstm_epi.cuh)
+__global__ void __launch_bounds__(256) lstm_whh_interleave_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int H) {
+  const int64_t total = (int64_t)4 * H * (H >> 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / (H >> 2)), k = (int)(i % (H >> 2)) * 4;
+    const int nt = c >> 8, ch = (c >> 7) & 1, gate = (c >> 5) & 3, ul = c & 31;
+    const int u = nt * 64 + ch * 32 + ul;
+    const float4 v = *reinterpret_cast<const float4*>(w + ((int64_t)gate * H + u) * H + k);
+    __half2 h[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
+    *reinterpret_cast<uint2*>(out + (int64_t)c * H + k) = *reinterpret_cast<uint2*>(h);
+  }
+}
+
 }  // namespace
+
+extern "C" int dasa_lstm_whh_interleave_f16(const float* w_hh, dasa_half_t* out, int H, void* stream) {
+  if (w_hh == nullptr || out == nullptr || H < 64 || (H % 64) != 0) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(w_hh) || !dasa_aligned16(out)) return DASA_ERR_BAD_ALIGN;
+  const int64_t work = (int64_t)H * H;
+  const unsigned grid = (unsigned)(dasa_cdiv(work, 256) < (int64_t)DASA_NUM_SMS * 8 ? dasa_cdiv(work, 256) : (int64_t)DASA_NUM_SMS * 8);
+  lstm_whh_interleave_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_hh, reinterpret_cast<__half*>(out), H);
+  return dasa_check_launch("lstm_whh_interleave_f16_kernel");
+}
 
 extern "C" size_t dasa_bilstm_packed_workspace(int R, int H, int backward) {
   if (R <= 0 || H <= 0) return 0;
@@ -223,6 +226,44 @@ extern "C" int dasa_bilstm_packed_fwd(const dasa_bilstm_packed_fwd_t* a, void* w
   float* gh[2] = {static_cast<float*>(workspace), static_cast<float*>(workspace) + (size_t)R * 4 * H};
   const float* Bw[2] = {a->w_hh[0], a->w_hh[1]};
   const size_t RH = (size_t)R * H;
+  // fused form (lstm_epi.cuh): fp16 state rows x interleaved fp16 W_hh on tcgen05 kind::f16, LSTM cell on the accumulator:
+  // ONE launch per time step, gh never written. h in (-1, 1) and fp16 carries TF32's 10 mantissa bits, so the recurrent
+  // products are the TF32 kernel's (below 2^-14 the absolute rounding step stays 6e-8).
+  const bool fused = a->w_hh16[0] != nullptr && a->w_hh16[1] != nullptr && a->h16[0] != nullptr && a->h16[1] != nullptr &&
+                     H >= 64 && (H % 64) == 0;
+  if (fused) {
+    __half* h16[2] = {reinterpret_cast<__half*>(a->h16[0]), reinterpret_cast<__half*>(a->h16[1])};
+    const __half* W16[2] = {reinterpret_cast<const __half*>(a->w_hh16[0]), reinterpret_cast<const __half*>(a->w_hh16[1])};
+    cudaMemsetAsync(a->hprev[0], 0, (size_t)n[0] * H * sizeof(float), st);
+    cudaMemsetAsync(h16[0], 0, (size_t)n[0] * H * sizeof(__half), st);
+    cudaMemsetAsync(a->cs[0], 0, (size_t)n[0] * H * sizeof(float), st);
+    cudaMemsetAsync(a->hprev[1] + off[Le - 1] * H, 0, (size_t)n[Le - 1] * H * sizeof(float), st);
+    cudaMemsetAsync(h16[1] + off[Le - 1] * H, 0, (size_t)n[Le - 1] * H * sizeof(__half), st);
+    cudaMemsetAsync(a->cs[1], 0, (size_t)n[Le - 1] * H * sizeof(float), st);
+    for (int s = 0; s < Le; ++s) {
+      const int pos[2] = {s, Le - 1 - s};
+      LstmEpi le;
+      const __half* A16[2];
+      for (int d = 0; d < 2; ++d) {
+        const int pp = pos[d];
+        const int nx = d == 0 ? pp + 1 : pp - 1;               // block the next step of this direction reads
+        const bool has_next = nx >= 0 && nx < Le;
+        A16[d] = h16[d] + off[pp] * H;
+        le.xp[d] = a->xp[d] + off[pp] * 4 * H; le.b_ih[d] = a->b_ih[d]; le.b_hh[d] = a->b_hh[d];
+        le.c_prev[d] = a->cs[d] + s * RH; le.c_out[d] = a->cs[d] + (s + 1) * RH;
+        le.acts[d] = a->acts[d] + off[pp] * 4 * H;
+        le.h_next[d] = has_next ? a->hprev[d] + off[nx] * H : nullptr;
+        le.h16_next[d] = has_next ? h16[d] + off[nx] * H : nullptr;
+        le.h_fin[d] = a->h_fin[d]; le.c_fin[d] = a->c_fin[d];
+        le.pos[d] = pp; le.n[d] = n[pp]; le.n_next[d] = has_next ? n[nx] : 0;
+      }
+      le.out = a->out; le.perm = a->perm; le.L = L; le.H = H;
+      le.drop = pk_drop(a->out_mask, a->drop_seed_dev, a->drop_seed, a->drop_base, a->drop_p, a->drop_scale);
+      rc = dasa_gemm_tc_pair_lstm(A16, W16, le, st);
+      if (rc != DASA_OK) return rc;
+    }
+    return DASA_OK;
+  }
   // zero initial state: forward direction block 0 (every sequence), reverse direction block Le-1 (the longest sequences)
   cudaMemsetAsync(a->hprev[0], 0, (size_t)n[0] * H * sizeof(float), st);
   cudaMemsetAsync(a->cs[0], 0, (size_t)n[0] * H * sizeof(float), st);

@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "gemm_common.cuh"
+#include "lstm_epi.cuh"
 
 namespace {
 
@@ -39,6 +40,11 @@ struct PairParams {
   int64_t split_stride;
   int tiles_total, num_pairs;
 };
+
+// Internal epilogue id (not part of the C ABI): the LSTM cell of the packed bi-LSTM recurrence on the accumulator (lstm_epi.cuh)
+constexpr int P_EPI_LSTM = 100;
+template <int EPI> struct PairExt {};                       // per-launch extra parameters of an epilogue kind (none by default)
+template <> struct PairExt<P_EPI_LSTM> { LstmEpi le; };
 
 struct PairTile { int g, ks, mt, nt; };
 __device__ __forceinline__ PairTile pair_decode(const PairParams& p, int w) {
@@ -135,6 +141,155 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Fused LSTM cell (P_EPI_LSTM): the calling epilogue warp owns rows row0 .. row0+31 and the 128 accumulator columns at t_addr =
+// gates i, f, g, o of hidden units unit0 .. unit0+31 (lstm_epi.cuh). The 32 x 128 accumulator block goes through `stg` (a
+// [32][P_LSTM_LD] fp32 staging area in the - by then idle - operand ring: the launch gives every CTA pair exactly ONE tile) so
+// that every global access is coalesced: a lane owns 4 consecutive units, 8 lanes cover the 32 units of one row (128 contiguous
+// bytes of xp / acts / c / h / out per gate), a warp instruction covers 4 rows. (Thread = row straight out of TMEM touched 32
+// different lines per instruction: 62 us per step instead of 35 for the two-launch form.) The summation order per gate is the
+// pointwise kernel's: ((x + gh) + b_ih) + b_hh. `release()` hands the accumulator buffer back after the last TMEM read.
+// Fused LSTM cell (P_EPI_LSTM): the calling epilogue warp owns rows row0 .. row0+31 and the 128 accumulator columns at t_addr =
+// gates i, f, g, o of hidden units unit0 .. unit0+31 (lstm_epi.cuh). The 32 x 128 accumulator block goes through `stg` (a
+// [32][P_LSTM_LD] fp32 staging area in the - by then idle - operand ring: the launch gives every CTA pair exactly ONE tile) so
+// that every global access is coalesced: a lane owns 4 consecutive units, 8 lanes cover the 32 units of one row (128 contiguous
+// bytes of xp / acts / c / h / out per gate), a warp instruction covers 4 rows. (Thread = row straight out of TMEM touched 32
+// different lines per instruction: 62 us per step instead of 35 for the two-launch form.) Rows go in batches of 2 row groups whose
+// xp / c_prev loads are issued one batch AHEAD of the cell update that uses them - the first batch and the bias columns before the
+// warp even waits for the accumulator (none of it depends on the GEMM). The summation order per gate is the pointwise kernel's:
+// ((x + gh) + b_ih) + b_hh.
+constexpr int P_LSTM_LD = 132;       // staging row stride in floats: conflict-free 128-bit rows for both access patterns
+constexpr int P_LSTM_NB = 2;         // row groups (of 4 rows) per batch
+struct LstmBatch { float4 x[P_LSTM_NB][4]; float4 cp[P_LSTM_NB]; int pr[P_LSTM_NB]; };
+// per-lane constants of a tile: the direction's pointers already offset to this lane's 4 units (indexing the kernel parameter
+// with the run-time direction costs a constant-bank indirection per access), bias columns, the dropout stream
+struct LstmLane {
+  float4 bi[4], bh[4];
+  const float* xp; const float* c_prev; float* c_out; float* acts; float* h_next; __half* h16_next; float* h_fin; float* c_fin;
+  float* out; const int32_t* perm;
+  int n, n_next, H, L, col4, rsub;
+  int64_t out_off;               // (pos * 2 + d) * H + u: offset of this lane's units inside an output row block
+  DropStream ds; const uint8_t* mask; float scale; int drop_mode;    // 0 none, 1 mask tensor, 2 in-place draws
+};
+
+__device__ __forceinline__ void p_lstm_lane(LstmLane& ln, const LstmEpi& le, const int d, const int unit0) {
+  const int lane = threadIdx.x & 31;
+  ln.col4 = lane & 7; ln.rsub = lane >> 3;
+  const int u = unit0 + 4 * ln.col4, H = le.H;
+  ln.H = H; ln.L = le.L; ln.n = le.n[d]; ln.n_next = le.n_next[d];
+  ln.xp = le.xp[d] + u; ln.c_prev = le.c_prev[d] + u; ln.c_out = le.c_out[d] + u; ln.acts = le.acts[d] + u;
+  ln.h_next = le.h_next[d] + u; ln.h16_next = le.h16_next[d] + u; ln.h_fin = le.h_fin[d] + u; ln.c_fin = le.c_fin[d] + u;
+  ln.out = le.out; ln.perm = le.perm;
+  ln.out_off = ((int64_t)le.pos[d] * 2 + d) * H + u;
+  ln.mask = le.drop.mask; ln.scale = le.drop.scale;
+  ln.drop_mode = le.drop.mask != nullptr ? 1 : (le.drop.stream ? 2 : 0);
+  if (ln.drop_mode == 2) {
+    ln.ds.mixed = mix_seed(le.drop.seed_dev ? le.drop.seed_dev[0] : le.drop.seed); ln.ds.base = le.drop.base; ln.ds.thr = le.drop.thr;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {          // this lane's 4 units keep their bias columns for every row of the tile
+    ln.bi[q] = __ldg(reinterpret_cast<const float4*>(le.b_ih[d] + q * H + u));
+    ln.bh[q] = __ldg(reinterpret_cast<const float4*>(le.b_hh[d] + q * H + u));
+  }
+}
+// Pulls the xp / c_prev lines of the warp's 32 rows x 32 units into L2 while the tensor cores work (no registers held): the
+// epilogue's loads then are L2 hits - its registers cannot keep the ~100 KB per SM in flight that DRAM latency would need.
+__device__ __forceinline__ void p_lstm_prefetch(const LstmEpi& le, const int d, const int row0, const int unit0) {
+  const int lane = threadIdx.x & 31;
+  const int H = le.H, n = le.n[d];
+  const int q = lane & 3;
+#pragma unroll
+  for (int rr = 0; rr < 32; rr += 8) {
+    const int r = row0 + rr + (lane >> 2);
+    if (r < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(le.xp[d] + (int64_t)r * 4 * H + q * H + unit0));
+  }
+  if (row0 + lane < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(le.c_prev[d] + (int64_t)(row0 + lane) * H + unit0));
+}
+__device__ __forceinline__ void p_lstm_load(LstmBatch& b, const LstmLane& ln, const int row0, const int rb) {
+  const int H = ln.H;
+#pragma unroll
+  for (int i = 0; i < P_LSTM_NB; ++i) {
+    const int r = row0 + rb + 4 * i + ln.rsub;
+    const int rc = r < ln.n ? r : ln.n - 1;                   // clamped: the loads are unconditional, dead rows discard them
+    const float* xrow = ln.xp + (int64_t)rc * 4 * H;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b.x[i][q] = ldg_stream4(xrow + q * H);
+    b.cp[i] = *reinterpret_cast<const float4*>(ln.c_prev + (int64_t)rc * H);
+    b.pr[i] = __ldg(ln.perm + rc);
+  }
+}
+__device__ __forceinline__ void p_lstm_cell(const LstmBatch& b, const LstmLane& ln, const int row0, const int rb, const float* stg) {
+  const int H = ln.H;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < P_LSTM_NB; ++i) {
+    const int rl = rb + 4 * i + ln.rsub, r = row0 + rl;
+    const bool live = r < ln.n, fresh = !live && r < ln.n_next;
+    const int64_t rH = (int64_t)r * H;
+    if (live) {
+      float g[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * P_LSTM_LD + q * 32 + 4 * ln.col4);
+        g[q][0] = ((b.x[i][q].x + a4.x) + ln.bi[q].x) + ln.bh[q].x; g[q][1] = ((b.x[i][q].y + a4.y) + ln.bi[q].y) + ln.bh[q].y;
+        g[q][2] = ((b.x[i][q].z + a4.z) + ln.bi[q].z) + ln.bh[q].z; g[q][3] = ((b.x[i][q].w + a4.w) + ln.bi[q].w) + ln.bh[q].w;
+      }
+      const float cp[4] = {b.cp[i].x, b.cp[i].y, b.cp[i].z, b.cp[i].w};
+      float c1[4], h1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[0][e] = lstm_sigmoid(g[0][e]); g[1][e] = lstm_sigmoid(g[1][e]); g[2][e] = lstm_tanh(g[2][e]); g[3][e] = lstm_sigmoid(g[3][e]);
+        c1[e] = g[1][e] * cp[e] + g[0][e] * g[2][e];
+        h1[e] = g[3][e] * lstm_tanh(c1[e]);
+      }
+      float* arow = ln.acts + (int64_t)r * 4 * H;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(arow + q * H) = make_float4(g[q][0], g[q][1], g[q][2], g[q][3]);
+      const float4 c4 = make_float4(c1[0], c1[1], c1[2], c1[3]);
+      float4 h4 = make_float4(h1[0], h1[1], h1[2], h1[3]);
+      *reinterpret_cast<float4*>(ln.c_out + rH) = c4;
+      if (r < ln.n_next) {
+        *reinterpret_cast<float4*>(ln.h_next + rH) = h4;
+        __half2 hh[2] = {__floats2half2_rn(h1[0], h1[1]), __floats2half2_rn(h1[2], h1[3])};
+        *reinterpret_cast<uint2*>(ln.h16_next + rH) = *reinterpret_cast<uint2*>(hh);
+      } else {        // last token of this sequence in this direction
+        *reinterpret_cast<float4*>(ln.h_fin + rH) = h4;
+        *reinterpret_cast<float4*>(ln.c_fin + rH) = c4;
+      }
+      const int64_t oe = (int64_t)b.pr[i] * ln.L * 2 * H + ln.out_off;      // out[perm[r], pos, d * H + u]
+      if (ln.drop_mode == 1) {
+        const uint32_t m = *reinterpret_cast<const uint32_t*>(ln.mask + oe);
+        h4.x *= (m & 0xFFu) ? ln.scale : 0.f; h4.y *= (m & 0xFF00u) ? ln.scale : 0.f;
+        h4.z *= (m & 0xFF0000u) ? ln.scale : 0.f; h4.w *= (m & 0xFF000000u) ? ln.scale : 0.f;
+      } else if (ln.drop_mode == 2) {
+        const uint32_t k4 = stream_keep4(ln.ds, (uint64_t)oe >> 2);
+        h4.x *= (k4 & 1u) ? ln.scale : 0.f; h4.y *= (k4 & 2u) ? ln.scale : 0.f;
+        h4.z *= (k4 & 4u) ? ln.scale : 0.f; h4.w *= (k4 & 8u) ? ln.scale : 0.f;
+      }
+      *reinterpret_cast<float4*>(ln.out + oe) = h4;
+    } else if (fresh) {   // reverse direction: this sequence joins at the NEXT step with a zero state
+      *reinterpret_cast<float4*>(ln.h_next + rH) = z4;
+      *reinterpret_cast<uint2*>(ln.h16_next + rH) = make_uint2(0u, 0u);
+      *reinterpret_cast<float4*>(ln.c_out + rH) = z4;
+    }
+  }
+}
+// accumulator block -> staging (thread = row = TMEM lane); `release()` hands the TMEM buffer back after the last read
+template <typename Release>
+__device__ __forceinline__ void p_lstm_stage(const uint32_t t_addr, float* stg, Release release) {
+  float* srow = stg + (threadIdx.x & 31) * P_LSTM_LD;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[32];
+    p_tmem_ld32(t_addr + (uint32_t)(q * 32), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(srow + q * 32 + 4 * j) =
+          make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  }
+  release();
+  __syncwarp();
+}
+
 // AMN / BMN: the operand is MN-major in HBM (A stored [K][M], B stored [K][N]): dX = dY.W and dW = dY^T.X run without any
 // transposed copy of the activations / weights.
 // F16: both operands are IEEE fp16 in HBM (K-major, 64 elements = one 128-byte swizzle row per stage row), tcgen05 kind::f16 at
@@ -146,7 +301,8 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false, int EW = P_EPI_WARPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, PairParams p) {
+                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, PairParams p,
+                      const __grid_constant__ PairExt<EPI> ext) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int A_BYTES = P_BM * P_BK * 4, B_BYTES = (BN / 2) * P_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers of BN fp32 columns
@@ -284,11 +440,37 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int n_base = t.nt * BN + chalf * CW;
       float* const Cg = p.C[t.g] + (int64_t)t.ks * p.split_stride;
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      LstmLane lln;
+      LstmBatch lb[2];
+      if constexpr (EPI == P_EPI_LSTM) {                   // nothing here depends on the GEMM: in flight while the tensor cores work
+        p_lstm_prefetch(ext.le, t.g, m_base, t.nt * 64 + chalf * 32);
+        p_lstm_lane(lln, ext.le, t.g, t.nt * 64 + chalf * 32);
+        p_lstm_load(lb[0], lln, m_base, 0);
+      }
       mbar_wait(&tmem_full[a], aph);
       p_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + chalf * CW;
       const int Mg = t.g ? p.M2 : p.M;
       const bool interior = plain && (m_base + 32 <= Mg) && (n_base + CW <= p.N);   // warp-uniform: no edge checks at all
+      if constexpr (EPI == P_EPI_LSTM) {
+        static_assert(EPI != P_EPI_LSTM || (BN == 256 && EW == 8), "the LSTM epilogue assumes 128 accumulator columns per epilogue warp");
+        (void)interior; (void)Cg;
+        static_assert(EPI != P_EPI_LSTM || 8 * 32 * P_LSTM_LD * 4 <= STAGES * STAGE_BYTES, "LSTM staging must fit the operand ring");
+        // one tile per pair (host: num_pairs == tiles_total): once tmem_full has fired every operand stage is idle for good
+        float* stg = reinterpret_cast<float*>(tiles) + (warp - 2) * 32 * P_LSTM_LD;
+        p_lstm_stage(t_addr, stg, [&]() {
+          p_fence_before();
+          __syncwarp();
+          if (lane == 0) p_remote_arrive(a ? empty_remote1 : empty_remote0);
+        });
+        constexpr int NBATCH = 32 / (4 * P_LSTM_NB);
+#pragma unroll
+        for (int bi = 0; bi < NBATCH; ++bi) {
+          if (bi + 1 < NBATCH) p_lstm_load(lb[(bi + 1) & 1], lln, m_base, (bi + 1) * 4 * P_LSTM_NB);
+          p_lstm_cell(lb[bi & 1], lln, m_base, bi * 4 * P_LSTM_NB, stg);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
         float4 gsrc[8];
@@ -429,7 +611,8 @@ bool pair_make_map_mn(CUtensorMap* map, const float* base, int64_t cols, int64_t
 }
 
 template <int BN, int STAGES, int EPI, bool AMN = false, bool BMN = false, bool F16 = false, int EW = P_EPI_WARPS>
-int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, cudaStream_t st) {
+int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams& p, cudaStream_t st,
+                  const PairExt<EPI>& ext = PairExt<EPI>{}) {
   constexpr size_t smem = (size_t)STAGES * (P_BM * P_BK * 4 + (BN / 2) * P_BK * 4) + EW * 32 * P_EPI_LD * 4 + 256 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
   auto kern = gemm_tf32_pair_kernel<BN, STAGES, EPI, AMN, BMN, F16, EW>;
@@ -439,7 +622,7 @@ int launch_pair_e(const CUtensorMap* ta, const CUtensorMap* tb, const PairParams
     if (e != cudaSuccess) { dasa_set_error("gemm_tf32_pair attr", e); return DASA_ERR_CUDA; }
     attr_set = true;
   }
-  kern<<<dim3(2u * (unsigned)p.num_pairs), 64 + 32 * EW, smem, st>>>(ta[0], tb[0], ta[1], tb[1], p);     // __cluster_dims__(2,1,1): one pair per TPC
+  kern<<<dim3(2u * (unsigned)p.num_pairs), 64 + 32 * EW, smem, st>>>(ta[0], tb[0], ta[1], tb[1], p, ext);     // __cluster_dims__(2,1,1): one pair per TPC
   return dasa_check_launch("gemm_tf32_pair_kernel");
 }
 
@@ -665,4 +848,39 @@ int dasa_gemm_tc_pair_grouped2(int M0, int M1, int N, int K, const float* const 
   if (M0 == 0) { ta[0] = ta[1]; tb[0] = tb[1]; }            // an absent group has no tiles: its maps are never fetched
   if (M1 == 0) { ta[1] = ta[0]; tb[1] = tb[0]; }
   return launch_pair_e<256, 5, DASA_EPI_NONE>(ta, tb, p, st) == DASA_OK ? p.splits : DASA_ERR_CUDA;
+}
+
+// One recurrence step of the packed bi-LSTM, both directions, GEMM + cell update in ONE launch (lstm_epi.cuh). Tiles cover
+// max(n, n_next) rows per direction (rows that join at the next step get their zero state from the epilogue); the operand maps
+// cover the n live rows only, so the rest of a tile's A rows are zero-filled by TMA.
+int dasa_gemm_tc_pair_lstm(const __half* const A16[2], const __half* const W16[2], const LstmEpi& le, cudaStream_t st) {
+  const int H = le.H, N = 4 * le.H, K = le.H;
+  if (H < 64 || (H % 64) != 0) return DASA_ERR_UNSUPPORTED;
+  int cover[2];
+  for (int g = 0; g < 2; ++g) cover[g] = le.n[g] > le.n_next[g] ? le.n[g] : le.n_next[g];
+  if (le.n[0] < 0 || le.n[1] < 0 || cover[0] + cover[1] <= 0) return DASA_ERR_BAD_SHAPE;
+  ++g_gemm_routes[DASA_ROUTE_PAIR_GROUPED];
+  PairParams p{};
+  p.M = cover[0]; p.M2 = cover[1]; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.ldc = N;
+  p.tiles_n = N / 256;
+  p.tiles_mn = (int)(dasa_cdiv(cover[0], 2 * P_BM) * p.tiles_n);
+  p.tiles_mn2 = (int)(dasa_cdiv(cover[1], 2 * P_BM) * p.tiles_n);
+  p.splits = 1; p.kb_per_split = K / (2 * P_BK); p.split_stride = 0;
+  p.tiles_total = p.tiles_mn + p.tiles_mn2;
+  p.num_pairs = p.tiles_total;                                // ONE tile per CTA pair: the epilogue stages through the idle operand ring
+  CUtensorMap ta[2], tb[2];
+  bool have[2] = {false, false};
+  for (int g = 0; g < 2; ++g) {
+    if (cover[g] == 0) continue;
+    if (!dasa_aligned16(A16[g]) || !dasa_aligned16(W16[g])) return DASA_ERR_BAD_ALIGN;
+    // a direction with tiles but no live row (cannot happen for a valid plan) would need a 0-row map: refuse it
+    if (le.n[g] <= 0) return DASA_ERR_BAD_SHAPE;
+    if (!pair_make_map_f16(&ta[g], A16[g], le.n[g], K, K, P_BM) || !pair_make_map_f16(&tb[g], W16[g], N, K, K, 128)) return DASA_ERR_UNSUPPORTED;
+    have[g] = true;
+  }
+  if (!have[0]) { ta[0] = ta[1]; tb[0] = tb[1]; }            // an absent group has no tiles: its maps are never fetched
+  if (!have[1]) { ta[1] = ta[0]; tb[1] = tb[0]; }
+  PairExt<P_EPI_LSTM> ext;
+  ext.le = le;
+  return launch_pair_e<256, 5, P_EPI_LSTM, false, false, true>(ta, tb, p, st, ext);
 }

@@ -542,13 +542,19 @@ class PackedBiLSTMFn(torch.autograd.Function):
         fin = torch.empty(2, 2, R, H, device=dev, dtype=torch.float32)         # [h | c][direction] in rank order
         P2 = ops.lib.P * 2
         cast = ops.ctypes.cast
+        if ops.fused_lstm_cell and H >= 64 and H % 64 == 0:                    # cell update in the recurrent GEMM's epilogue
+            w16 = (ops.lstm_whh_interleaved(w_hh_f), ops.lstm_whh_interleaved(w_hh_r))
+            h16 = torch.empty(2, N, H, device=dev, dtype=torch.float16)
+            fused = (P2(w16[0].data_ptr(), w16[1].data_ptr()), P2(h16[0].data_ptr(), h16[1].data_ptr()))
+        else:
+            fused = (P2(None, None), P2(None, None))
         a = ops.lib.BiLstmPackedFwd(R, L, H, cast(plan.n_rows, ops.lib.P), cast(plan.off, ops.lib.P), plan.perm.data_ptr(),
                                     P2(xp[0].data_ptr(), xp[1].data_ptr()), P2(w_hh_f.data_ptr(), w_hh_r.data_ptr()),
                                     P2(b_ih_f.data_ptr(), b_ih_r.data_ptr()), P2(b_hh_f.data_ptr(), b_hh_r.data_ptr()),
                                     P2(hprev[0].data_ptr(), hprev[1].data_ptr()), P2(cs[0].data_ptr(), cs[1].data_ptr()),
                                     P2(acts[0].data_ptr(), acts[1].data_ptr()), out.data_ptr(),
                                     P2(fin[0, 0].data_ptr(), fin[0, 1].data_ptr()), P2(fin[1, 0].data_ptr(), fin[1, 1].data_ptr()),
-                                    *_drop_fields(drop, drop_scale, (R, L, 2 * H)))
+                                    *_drop_fields(drop, drop_scale, (R, L, 2 * H)), *fused)
         ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 0))
         ops.call("dasa_bilstm_packed_fwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         h_fin = fin[0].index_select(1, plan.rank_of)

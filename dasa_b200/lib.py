@@ -37,7 +37,8 @@ class BiLstmPackedFwd(ctypes.Structure):
     """dasa_bilstm_packed_fwd_t"""
     _fields_ = [("R", I), ("L", I), ("H", I), ("n_rows", P), ("off", P), ("perm", P), ("xp", P * 2), ("w_hh", P * 2), ("b_ih", P * 2),
                 ("b_hh", P * 2), ("hprev", P * 2), ("cs", P * 2), ("acts", P * 2), ("out", P), ("h_fin", P * 2), ("c_fin", P * 2),
-                ("out_mask", P), ("drop_seed_dev", P), ("drop_seed", U), ("drop_base", U), ("drop_p", F), ("drop_scale", F)]
+                ("out_mask", P), ("drop_seed_dev", P), ("drop_seed", U), ("drop_base", U), ("drop_p", F), ("drop_scale", F),
+                ("w_hh16", P * 2), ("h16", P * 2)]
 
 
 class BiLstmPackedBwd(ctypes.Structure):

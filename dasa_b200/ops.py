@@ -195,6 +195,24 @@ def half_weight(w):
     return out
 
 
+def lstm_whh_interleaved(w_hh):
+    """fp16 copy of a recurrent LSTM weight [4H, H] with its rows interleaved for the fused cell epilogue of the packed bi-LSTM
+    (dasa_lstm_whh_interleave_f16), cached like half_weight (rebuilt after every optimizer step for a trainable weight)."""
+    key = ("whh16", id(w_hh))
+    tag = (w_hh._version, weights_epoch if w_hh.requires_grad else -1, w_hh.data_ptr())
+    hit = _half_cache.get(key)
+    if hit is not None and hit[0] == tag and hit[2]() is w_hh:
+        return hit[1]
+    src = w_hh.detach()
+    src = src if src.is_contiguous() else src.contiguous()
+    out = torch.empty(src.shape, device=src.device, dtype=torch.float16)
+    call("dasa_lstm_whh_interleave_f16", _p(src), _p(out), src.shape[1], _stream())
+    _half_cache[key] = (tag, out, weakref.ref(w_hh))
+    return out
+
+
+fused_lstm_cell = True      # packed bi-LSTM forward: cell update in the recurrent GEMM's epilogue (one launch per time step)
+
 _stack_cache = {}
 
 

@@ -271,7 +271,15 @@ typedef struct {
    * order), or NULL with drop_p > 0: flags drawn in place, out[seq, l, c] = stream byte (seq*L + l)*2H + c of (seed, drop_base)
    * (see dasa_mha_fwd_h16); NULL and drop_p == 0: no dropout. The backward struct takes the same fields and masks dout.          */
   const uint8_t* out_mask; const uint64_t* drop_seed_dev; uint64_t drop_seed; uint64_t drop_base; float drop_p; float drop_scale;
+  /* Fused recurrence (all four non-NULL and H % 64 == 0; else the two-launch form): w_hh16[d] = dasa_lstm_whh_interleave_f16 of
+   * W_hh[d], h16[d] [N, H] fp16 scratch (the state rows as the fp16 A operand). One launch per time step: tcgen05 kind::f16
+   * GEMM of both directions with the LSTM cell applied to the accumulator (gates never reach memory as pre-activations).       */
+  const dasa_half_t* w_hh16[2]; dasa_half_t* h16[2];
 } dasa_bilstm_packed_fwd_t;
+/* out [4H, H] fp16 = the rows of W_hh ([4H, H] fp32, gate-major i, f, g, o) interleaved so that every 128 consecutive output
+ * columns of h W_hh^T are the four gates of 32 consecutive hidden units: row nt*256 + ch*128 + gate*32 + ul <- gate*H + nt*64 +
+ * ch*32 + ul. H % 64 == 0.                                                                                                       */
+int dasa_lstm_whh_interleave_f16(const float* w_hh, dasa_half_t* out, int H, void* stream);
 /* Backward: dout [R, L, 2H] (original order), dh_fin / dc_fin [R, H] rank order (may be NULL), w_hh_t[d] = W_hh[d]^T [H, 4H].
  * Writes dgates[d] [N, 4H] (compact token order: the dY of dW_ih = dgates^T x, dW_hh = dgates^T hprev, dX = dgates W_ih).
  * dc_work[d]: scratch [2, R, H].                                                                                               */

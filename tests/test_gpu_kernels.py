@@ -736,7 +736,6 @@ def test_gemm_pair_plan_routes_big_token_major_shapes():
     try:
         for mode in (0, 1):
             L.dasa_debug_gemm_pair(mode)
-            n0 = lib.launches
             C = torch.empty(M, N, device=DEV)
             ops.gemm(A, K, 1, W, K, 1, C, N, M, N, K, epilogue=ops.EPI_BIAS, bias=b, precision=ops.PREC_TF32)
             outs.append(C)
@@ -900,6 +899,53 @@ def test_packed_bilstm_matches_padded_path(R, L, In, H, seed):
         assert rel_err(a, b) <= 5e-3, "%s: %.3e" % (name, rel_err(a, b))
     for i, nm in enumerate(("w_ih_f", "w_hh_f", "b_ih_f", "b_hh_f", "w_ih_r", "w_hh_r", "b_ih_r", "b_hh_r")):
         assert rel_err(w_pk[i].grad, w_ref[i].grad) <= 5e-3, "grad %s: %.3e" % (nm, rel_err(w_pk[i].grad, w_ref[i].grad))
+
+
+@pytest.mark.parametrize("R,L,In,H,seed", [(70, 12, 64, 64, 0), (600, 23, 96, 128, 1), (300, 9, 64, 256, 2)])
+def test_packed_bilstm_fused_cell_matches_two_launch_form(R, L, In, H, seed):
+    """Forward recurrence with the LSTM cell in the GEMM epilogue (fp16 state rows x interleaved fp16 W_hh, tcgen05 kind::f16, one
+    launch per step) against the two-launch form (TF32 grouped GEMM + pointwise kernel): outputs, final states, the saved gate
+    activations through every gradient. Both carry 11-bit operands, so they agree far inside the TF32 bound; rows past a length stay
+    exactly zero. R = 600 crosses the 256-row tile boundary in both directions (rows joining / leaving inside a tile)."""
+    from dasa_b200 import functions as Fn
+    from dasa_b200 import modules as M
+    from dasa_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, L + 1, (R,), generator=g).tolist()
+    lens[3] = L
+    lens[5] = 1
+    pack = M.PackInfo(lens, L, 1, DEV)
+    plan = pack.bilstm_plan()
+    x = (torch.randn(pack.ntok, In, generator=g) * 0.5).to(DEV)
+
+    def weights():
+        gg = torch.Generator().manual_seed(seed + 100)
+        return [(torch.randn(*s, generator=gg) * sc).to(DEV).requires_grad_(True)
+                for s, sc in (((4 * H, In), In ** -0.5), ((4 * H, H), H ** -0.5), ((4 * H,), 0.1), ((4 * H,), 0.1)) * 2]
+    gout = torch.randn(R, L, 2 * H, generator=g).to(DEV)
+    ghf = torch.randn(2, R, H, generator=g).to(DEV)
+    gcf = torch.randn(2, R, H, generator=g).to(DEV)
+    res = []
+    ops.set_precision("tf32")
+    try:
+        for fused in (False, True):
+            ops.fused_lstm_cell = fused
+            w = weights()
+            xx = x.clone().requires_grad_(True)
+            out, h, c = Fn.PackedBiLSTMFn.apply(xx, plan, *w)
+            ((out * gout).sum() + (h * ghf).sum() + (c * gcf).sum()).backward()
+            torch.cuda.synchronize()
+            res.append((out, h, c, xx.grad, [t.grad for t in w]))
+    finally:
+        ops.fused_lstm_cell = True
+        ops.set_precision("fp32")
+    (o0, h0, c0, dx0, gw0), (o1, h1, c1, dx1, gw1) = res
+    valid = torch.arange(L, device=DEV).view(1, L) < pack.len.view(R, 1)
+    assert float(o1[~valid].abs().max()) == 0.0
+    for name, a, b in (("out", o1, o0), ("h_fin", h1, h0), ("c_fin", c1, c0), ("dx", dx1, dx0)):
+        assert rel_err(a, b) <= 2e-3, "%s: %.3e" % (name, rel_err(a, b))
+    for i, (a, b) in enumerate(zip(gw1, gw0)):
+        assert rel_err(a, b) <= 2e-3, "grad %d: %.3e" % (i, rel_err(a, b))
 
 
 class ReversePackedFn(torch.autograd.Function):
