@@ -31,6 +31,7 @@ constexpr int DP_WARPS = 8;
 constexpr int DP_CHUNK = 32;         // k per chunk
 constexpr int DP_MAXROWS = 128;      // attention rows (views / tokens)
 constexpr int DP_MAXK = 15;          // shift kernel taps
+constexpr int DP_NST2_H = 3;         // the same for the fp16-X block (its X fragments are half the registers)
 constexpr int DP_NST2 = 2;           // chunks in flight per warp in the 32-row GEMM phases (register budget: 3 spill at 24 episodes); 3 in the 16-row ones
 
 // ------------------------------------------------------------------------------------------------ device-wide barrier
@@ -90,6 +91,18 @@ __device__ __forceinline__ T* dp_opaque(T* p) {
 }
 // component j of a float4 with j a compile-time constant after unrolling (no address-of: the fragments must stay in registers)
 __device__ __forceinline__ float f4_get(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+
+// fp16 with saturation to +-65504 instead of inf (the backward pass's scaled gradient copies: a clipped value, never a NaN)
+__device__ __forceinline__ __half dp_half_sat(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return __ushort_as_half(r);
+}
+__device__ __forceinline__ __half2 dp_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
 
 struct Slice { int c0, cn; };
 // channel slice s of S over D channels, float4-granular
@@ -179,6 +192,31 @@ __device__ __forceinline__ void dp_compute(float (&acc)[RT][MT][4], const GemmFr
   }
 }
 
+// fold the K slices of the 8 warps in warp order (deterministic): red[warp][h][i][e][lane] -> res[m * 16 RT + nl]. Ends with a
+// __syncthreads: res is complete.
+template <int MT, int RT>
+__device__ __forceinline__ void dp_fold(const float (&acc)[RT][MT][4], float* red, float* res) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 0; h < RT; ++h)
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[(((warp * RT + h) * MT + i) * 4 + e) * 32 + lane] = acc[h][i][e];
+  __syncthreads();
+  constexpr int NL = 16 * RT, OUTS = NL * 8 * MT;
+  for (int o = threadIdx.x; o < OUTS; o += DP_THREADS) {
+    const int nl = o % NL, m = o / NL;
+    const int h = nl >> 4, r16 = nl & 15, i = m >> 3, mm = m & 7;
+    const int e = (mm & 1) + (r16 >= 8 ? 2 : 0), ln = (r16 & 7) * 4 + (mm >> 1);
+    float s = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < DP_WARPS; ++w2) s += red[(((w2 * RT + h) * MT + i) * 4 + e) * 32 + ln];
+    res[o] = s;                      // res[m * NL + nl]
+  }
+  __syncthreads();
+}
+
 // NST chunks of W / X in flight per warp (registers; the ring is fully unrolled so every fragment index is a constant)
 template <int MT, int RT, int NST>
 __device__ __forceinline__ void dp_gemm_block(const wt_t* (&wrow)[2 * RT], const float* X, int64_t ldx, int M, int K,
@@ -218,36 +256,113 @@ __device__ __forceinline__ void dp_gemm_block(const wt_t* (&wrow)[2 * RT], const
     }
   }
 
-  // fold the K slices of the 8 warps in warp order (deterministic)
+  dp_fold<MT, RT>(acc, red, res);
+}
+
+// ---- the same product with X stored as fp16 (forward pass: every GEMM operand of the decoder is O(1) - tanh / sigmoid outputs,
+// dropout-scaled states, attention-weighted features - so its fp16 copy carries exactly the 11 significant bits the TF32 tensor
+// core would have kept, at half the bytes). X is read by EVERY CTA in every GEMM phase (148 x 20 x K x 4 B: 99 MB per action against
+// 42 MB of weights), so halving it is the larger part of the phase's L2 traffic. mma.sync.m16n8k16 f16 x f16 -> f32: a lane
+// loads 8 consecutive k (one 128-bit access) of each of its W rows and of its X row per 32-wide chunk and feeds halves
+// (4j, 4j+1) / (4j+2, 4j+3) to k slots (2t, 2t+1) / (2t+8, 2t+9) of MMA step j for BOTH operands (any bijection of the reduction
+// index is a valid GEMM). wrow[i] / X rows are offset by 8 * t halves.
+typedef __half xh_t;
+__device__ __forceinline__ uint4 ldg_w8(const wt_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(l2_policy_evict_last()));
+  return r;
+}
+__device__ __forceinline__ uint32_t u4_get(const uint4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void dp_mma_h(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int MT, int RT>
+struct GemmFragH {
+  uint4 w[2 * RT];
+  uint4 x[MT];
+};
+template <int MT, int RT>
+__device__ __forceinline__ void dp_load_h(GemmFragH<MT, RT>& f, const wt_t* (&wrow)[2 * RT], const xh_t* (&xrow)[MT],
+                                          const bool (&xok)[MT], int kc, const bool half_last) {
+#pragma unroll
+  for (int i = 0; i < 2 * RT; ++i) {
+    if (half_last && i == 2 * RT - 1) continue;
+    f.w[i] = ldg_w8(wrow[i] + kc);
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+    f.x[i] = xok[i] ? __ldcg(reinterpret_cast<const uint4*>(xrow[i] + kc)) : make_uint4(0u, 0u, 0u, 0u);
+}
+template <int MT, int RT>
+__device__ __forceinline__ void dp_compute_h(float (&acc)[RT][MT][4], const GemmFragH<MT, RT>& f, const bool half_last) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int h = 0; h < RT; ++h) {
+      uint32_t af[4];
+      const bool off = half_last && h == RT - 1;
+      af[0] = u4_get(f.w[2 * h], 2 * j);
+      af[1] = off ? 0u : u4_get(f.w[2 * h + 1], 2 * j);
+      af[2] = u4_get(f.w[2 * h], 2 * j + 1);
+      af[3] = off ? 0u : u4_get(f.w[2 * h + 1], 2 * j + 1);
+#pragma unroll
+      for (int i = 0; i < MT; ++i) dp_mma_h(acc[h][i], af, u4_get(f.x[i], 2 * j), u4_get(f.x[i], 2 * j + 1));
+    }
+  }
+}
+template <int MT, int RT, int NST>
+__device__ __forceinline__ void dp_gemm_block_h(const wt_t* (&wrow)[2 * RT], const xh_t* X, int64_t ldx, int M, int K,
+                                                float* red, float* res, const bool half_last = false) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const xh_t* xrow[MT];
+  bool xok[MT];
+  X = dp_opaque(X);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int m = 8 * i + g;
+    xok[i] = m < M;
+    xrow[i] = X + (int64_t)(xok[i] ? m : 0) * ldx + 8 * t;
+  }
+  float acc[RT][MT][4];
 #pragma unroll
   for (int h = 0; h < RT; ++h)
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) red[(((warp * RT + h) * MT + i) * 4 + e) * 32 + lane] = acc[h][i][e];
-  __syncthreads();
-  constexpr int NL = 16 * RT, OUTS = NL * 8 * MT;
-  for (int o = threadIdx.x; o < OUTS; o += DP_THREADS) {
-    const int nl = o % NL, m = o / NL;
-    const int h = nl >> 4, r16 = nl & 15, i = m >> 3, mm = m & 7;
-    const int e = (mm & 1) + (r16 >= 8 ? 2 : 0), ln = (r16 & 7) * 4 + (mm >> 1);
-    float s = 0.f;
+      for (int e = 0; e < 4; ++e) acc[h][i][e] = 0.f;
+
+  const int nchunks = K / DP_CHUNK;
+  GemmFragH<MT, RT> f[NST];
+  int c = warp;
 #pragma unroll
-    for (int w2 = 0; w2 < DP_WARPS; ++w2) s += red[(((w2 * RT + h) * MT + i) * 4 + e) * 32 + ln];
-    res[o] = s;                      // res[m * NL + nl]
+  for (int s = 0; s < NST - 1; ++s)
+    if (c + s * DP_WARPS < nchunks) dp_load_h<MT, RT>(f[s], wrow, xrow, xok, (c + s * DP_WARPS) * DP_CHUNK, half_last);
+#pragma unroll 1
+  for (; c < nchunks; c += NST * DP_WARPS) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      const int cl = c + (s + NST - 1) * DP_WARPS;
+      if (cl < nchunks) dp_load_h<MT, RT>(f[(s + NST - 1) % NST], wrow, xrow, xok, cl * DP_CHUNK, half_last);
+      if (c + s * DP_WARPS < nchunks) dp_compute_h<MT, RT>(acc, f[s], half_last);
+    }
   }
-  __syncthreads();
+  dp_fold<MT, RT>(acc, red, res);
 }
 
 // plain row block: rows n0 .. n0+15 (n0 .. n0+7 with rows8: the upper half is never loaded) of W, clamped to N-1; the caller
 // never stores rows >= N
-__device__ __forceinline__ void dp_rows16(const wt_t* (&wrow)[2], const wt_t* W, int64_t ldw, int n0, int N, const bool rows8 = false) {
+// kper: consecutive k a lane owns per chunk (4: fp32-X block, two 64-bit accesses per row and chunk; 8: fp16-X block, one 128-bit)
+__device__ __forceinline__ void dp_rows16(const wt_t* (&wrow)[2], const wt_t* W, int64_t ldw, int n0, int N, const bool rows8 = false,
+                                          const int kper = 4) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     int n = n0 + g + ((rows8 || i == 0) ? 0 : 8);
     n = n < N ? n : N - 1;
-    wrow[i] = W + (int64_t)n * ldw + 4 * t;
+    wrow[i] = W + (int64_t)n * ldw + kper * t;
   }
 }
 
@@ -305,8 +420,9 @@ __device__ __forceinline__ void dp_partial_dots(const float* tile, int pitch, co
 }
 
 // out[c0 + 4*col ..] = sum_r w[r] * tile[r, col]  over unmasked rows (w in shared memory); out may be any global row
+// out16 (optional): the same values as fp16 at the same element offsets (the forward pass's GEMM operand copies)
 __device__ __forceinline__ void dp_weighted_sum(const AttnSmem& s, int pitch, int rows, int cn, const uint8_t* mask_b, const float* w,
-                                                float* out) {
+                                                float* out, __half* out16 = nullptr, const float s16 = 1.f) {
   const int n4 = cn >> 2;
   if (n4 <= 0) return;
   const int G = n4 >= DP_THREADS ? 1 : min(DP_THREADS / n4, 8);
@@ -336,7 +452,13 @@ __device__ __forceinline__ void dp_weighted_sum(const AttnSmem& s, int pitch, in
           acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
         }
     }
-    if (act && grp == 0) *reinterpret_cast<float4*>(out + 4 * col) = acc;
+    if (act && grp == 0) {
+      *reinterpret_cast<float4*>(out + 4 * col) = acc;
+      if (out16 != nullptr) {
+        __half2 h[2] = {dp_half2_sat(acc.x * s16, acc.y * s16), dp_half2_sat(acc.z * s16, acc.w * s16)};
+        *reinterpret_cast<uint2*>(out16 + 4 * col) = *reinterpret_cast<uint2*>(h);
+      }
+    }
   }
 }
 
@@ -446,6 +568,18 @@ __device__ __forceinline__ const uint8_t* dp_mask_smem(unsigned char* raw, const
   return mask != nullptr ? dp_attn_smem(raw, pl, false).mk : nullptr;
 }
 
+// fp16 copies of the forward GEMM operands inside the caller's x16 scratch: drop(h~_{t-1}) [T,B,H] | [emb ; attn ; h~] [T,B,KX] |
+// [wc ; drop(h_1)] [T,B,DC]
+struct FwdX16 { __half* hp; __half* xh; __half* cat; };
+__device__ __forceinline__ FwdX16 fwd_x16(const dasa_decoder_fwd_t& a) {
+  FwdX16 x;
+  const int64_t TB = (int64_t)a.T * a.B;
+  x.hp = reinterpret_cast<__half*>(a.x16);
+  x.xh = x.hp + TB * a.H;
+  x.cat = x.xh + TB * (a.E + a.F + a.H);
+  return x;
+}
+
 // ---- the GEMM phases (one function each)
 
 // The three 16-row GEMM phases of an action share ONE instance of the K loop (the phase picks operands and epilogue at run
@@ -458,20 +592,21 @@ __device__ __forceinline__ void fwd_gemm16(const dasa_decoder_fwd_t& a, const in
   const int tid = threadIdx.x;
   const int64_t tb = (int64_t)t * B;
   const float scale = a.drop_scale;
-  const wt_t* W; const float* X;
+  const wt_t* W; const xh_t* X;
   int64_t ldw, ldx;
   int N, K;
-  if (ph == 0)      { W = reinterpret_cast<const wt_t*>(a.w_feat);    ldw = H;  N = NK; K = H;  X = a.hprev_drop + tb * H; ldx = H; }    // P1: tk = W_feat drop(h~) + b
-  else if (ph == 4) { W = reinterpret_cast<const wt_t*>(a.w_att_in);  ldw = H;  N = D;  K = H;  X = a.cat + tb * DC + D;   ldx = DC; }   // P4: t2 = W_att_in drop(h_1)
-  else              { W = reinterpret_cast<const wt_t*>(a.w_att_out); ldw = DC; N = H;  K = DC; X = a.cat + tb * DC;       ldx = DC; }   // P6: h~ = tanh(W_att_out [wc ; drop(h_1)])
+  const FwdX16 x16 = fwd_x16(a);
+  if (ph == 0)      { W = reinterpret_cast<const wt_t*>(a.w_feat);    ldw = H;  N = NK; K = H;  X = x16.hp + tb * H;        ldx = H; }    // P1: tk = W_feat drop(h~) + b
+  else if (ph == 4) { W = reinterpret_cast<const wt_t*>(a.w_att_in);  ldw = H;  N = D;  K = H;  X = x16.cat + tb * DC + D;  ldx = DC; }   // P4: t2 = W_att_in drop(h_1)
+  else              { W = reinterpret_cast<const wt_t*>(a.w_att_out); ldw = DC; N = H;  K = DC; X = x16.cat + tb * DC;      ldx = DC; }   // P6: h~ = tanh(W_att_out [wc ; drop(h_1)])
   W = dp_opaque(W);
   const bool rows8 = N <= 8 * (int)gridDim.x;                  // P6 (N = H = 1024): 128 blocks of 8 rows, one per CTA
   const int rb = rows8 ? 8 : 16;
   const int nitems = (N + rb - 1) / rb;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const wt_t* wrow[2];
-    dp_rows16(wrow, W, ldw, item * rb, N, rows8);
-    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res, rows8);
+    dp_rows16(wrow, W, ldw, item * rb, N, rows8, 8);
+    dp_gemm_block_h<MT, 1, 3>(wrow, X, ldx, B, K, red, res, rows8);
     for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
       const int m = o >> 4, n = item * rb + (o & 15);
       if (m >= B || n >= N || (o & 15) >= rb) continue;
@@ -484,8 +619,11 @@ __device__ __forceinline__ void fwd_gemm16(const dasa_decoder_fwd_t& a, const in
         a.htilde[(tb + m) * H + n] = v;
         if (t + 1 < T) {
           a.xh[(tb + B + m) * KX + E + F + n] = v;
+          x16.xh[(tb + B + m) * KX + E + F + n] = __float2half_rn(v);
           const int64_t mi = (tb + B + m) * H + n;
-          a.hprev_drop[mi] = a.m_hprev ? (a.m_hprev[mi] ? v * scale : 0.f) : v;
+          const float vd = a.m_hprev ? (a.m_hprev[mi] ? v * scale : 0.f) : v;
+          a.hprev_drop[mi] = vd;
+          x16.hp[mi] = __float2half_rn(vd);
         }
       }
     }
@@ -501,14 +639,15 @@ __device__ __forceinline__ void fwd_p3(const dasa_decoder_fwd_t& a, const int t,
   const float scale = a.drop_scale;
   (void)T; (void)NK; (void)KX; (void)DC; (void)scale; (void)tb; (void)tid;
     {
-      const float* X = a.xh + tb * KX;
+      const FwdX16 x16 = fwd_x16(a);
+      const xh_t* X = x16.xh + tb * KX;
       const int nitems = H / 8;
       const int lane = tid & 31, g = lane >> 2, tq = lane & 3;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const wt_t* wrow[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wrow[i] = dp_opaque(reinterpret_cast<const wt_t*>(a.w_lstm)) + (int64_t)(i * H + item * 8 + g) * KX + 4 * tq;
-        dp_gemm_block<MT, 2, DP_NST2>(wrow, X, KX, B, KX, red, res);
+        for (int i = 0; i < 4; ++i) wrow[i] = dp_opaque(reinterpret_cast<const wt_t*>(a.w_lstm)) + (int64_t)(i * H + item * 8 + g) * KX + 8 * tq;
+        dp_gemm_block_h<MT, 2, DP_NST2_H>(wrow, X, KX, B, KX, red, res);
         for (int o = tid; o < 8 * MT * 8; o += DP_THREADS) {
           const int m = o >> 3, j = o & 7, u = item * 8 + j;
           if (m >= B) continue;
@@ -524,7 +663,9 @@ __device__ __forceinline__ void fwd_p3(const dasa_decoder_fwd_t& a, const int t,
           a.c[(tb + B + m) * H + u] = c1;
           a.h1[(tb + m) * H + u] = h1;
           const int64_t mi = (tb + m) * H + u;
-          a.cat[(tb + m) * DC + D + u] = a.m_h1 ? (a.m_h1[mi] ? h1 * scale : 0.f) : h1;
+          const float h1d = a.m_h1 ? (a.m_h1[mi] ? h1 * scale : 0.f) : h1;
+          a.cat[(tb + m) * DC + D + u] = h1d;
+          x16.cat[(tb + m) * DC + D + u] = __float2half_rn(h1d);
         }
       }
     }
@@ -598,7 +739,8 @@ __device__ __noinline__ void fwd_p2b(const dasa_decoder_fwd_t& a, const SmemPlan
     }
   }
   __syncthreads();
-  dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.wrow, a.xh + (tb + o.b) * KX + E + o.sl.c0);
+  dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.wrow, a.xh + (tb + o.b) * KX + E + o.sl.c0,
+                  fwd_x16(a).xh + (tb + o.b) * KX + E + o.sl.c0);
   // the next action's tile is prefetched at the top of the NEXT phase (after the barrier): every thread is done with this one
 }
 
@@ -627,24 +769,32 @@ __device__ __noinline__ void fwd_p5b(const dasa_decoder_fwd_t& a, const SmemPlan
   __syncthreads();
   if (o.s == 0)
     for (int r = tid; r < L; r += DP_THREADS) a.alpha[(tb + o.b) * L + r] = sc.prow[r];
-  dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.prow, a.cat + (tb + o.b) * DC + o.sl.c0);
+  dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.prow, a.cat + (tb + o.b) * DC + o.sl.c0,
+                  fwd_x16(a).cat + (tb + o.b) * DC + o.sl.c0);
 }
 
 __device__ __noinline__ void fwd_prologue(const dasa_decoder_fwd_t& a) {
   const int B = a.B, H = a.H, E = a.E, KX = a.E + a.F + a.H;
   const int gtid = blockIdx.x * DP_THREADS + threadIdx.x, gthreads = gridDim.x * DP_THREADS;
   const float scale = a.drop_scale;
-  // recurrent state of action 0, action embeddings of every action into the [x ; h] rows
+  const FwdX16 x16 = fwd_x16(a);
+  // recurrent state of action 0, action embeddings of every action into the [x ; h] rows (fp32 for the backward pass, fp16 for
+  // the GEMM phases)
   for (int i = gtid; i < B * H; i += gthreads) {
     const int b = i / H, n = i % H;
     const float h = __ldg(a.h0 + i);
     a.xh[(int64_t)b * KX + E + a.F + n] = h;
-    a.hprev_drop[i] = a.m_hprev ? (a.m_hprev[i] ? h * scale : 0.f) : h;
+    x16.xh[(int64_t)b * KX + E + a.F + n] = __float2half_rn(h);
+    const float hd = a.m_hprev ? (a.m_hprev[i] ? h * scale : 0.f) : h;
+    a.hprev_drop[i] = hd;
+    x16.hp[i] = __float2half_rn(hd);
     a.c[i] = __ldg(a.c0 + i);
   }
   for (int i = gtid; i < a.T * B * E; i += gthreads) {
     const int r = i / E, e = i % E;
-    a.xh[(int64_t)r * KX + e] = __ldg(a.emb + i);
+    const float v = __ldg(a.emb + i);
+    a.xh[(int64_t)r * KX + e] = v;
+    x16.xh[(int64_t)r * KX + e] = __float2half_rn(v);
   }
 }
 
@@ -690,6 +840,21 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_fwd_kernel(cons
   }
 }
 
+// fp16 copies of the backward GEMM operands (the gradients du, dt2, dgates, dtk) inside the caller's g16 scratch, multiplied by
+// DP_GSCALE = 2^8 so that fp16's normal range covers |g| in [2.4e-7, 256) with TF32's 11 significant bits (smaller values keep an
+// absolute step of 2.3e-10, larger ones saturate instead of overflowing); the folded sums are multiplied by 2^-8 (exact).
+constexpr float DP_GSCALE = 256.f, DP_GUNSCALE = 1.f / 256.f;
+struct BwdX16 { __half* du; __half* dt2; __half* dgates; __half* dtk; };
+__device__ __forceinline__ BwdX16 bwd_x16(const dasa_decoder_bwd_t& a) {
+  BwdX16 x;
+  const int64_t TB = (int64_t)a.T * a.B;
+  x.du = reinterpret_cast<__half*>(a.g16);
+  x.dt2 = x.du + TB * a.H;
+  x.dgates = x.dt2 + TB * a.D;
+  x.dtk = x.dgates + TB * 4 * a.H;
+  return x;
+}
+
 template <int MT>
 __device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const int t, const int ph, float* red, float* res) {
   const int B = a.B, H = a.H, D = a.D, NK = a.NK;
@@ -697,29 +862,30 @@ __device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const in
   const int tid = threadIdx.x;
   const int64_t tb = (int64_t)t * B;
   const float scale = a.drop_scale;
-  const wt_t* W; const float* X;
+  const wt_t* W; const xh_t* X;
   int64_t ldw, ldx;
   int N, K;
-  if (ph == 0)      { W = reinterpret_cast<const wt_t*>(a.w_att_out_t); ldw = a.ld_w_att_out_t; N = DC; K = H;  X = a.du + tb * H;   ldx = H; }    // B6: dcat = du W_att_out
-  else if (ph == 3) { W = reinterpret_cast<const wt_t*>(a.w_att_in_t);  ldw = a.ld_w_att_in_t;  N = H;  K = D;  X = a.dt2 + tb * D;  ldx = D; }    // B4: dh1d, LSTM cell backward
-  else              { W = reinterpret_cast<const wt_t*>(a.w_feat_t);    ldw = a.ld_w_feat_t;    N = H;  K = NK; X = a.dtk + tb * NK; ldx = NK; }   // B1: dh~_{t-1}, du_{t-1}
+  const BwdX16 x16 = bwd_x16(a);
+  if (ph == 0)      { W = reinterpret_cast<const wt_t*>(a.w_att_out_t); ldw = a.ld_w_att_out_t; N = DC; K = H;  X = x16.du + tb * H;   ldx = H; }    // B6: dcat = du W_att_out
+  else if (ph == 3) { W = reinterpret_cast<const wt_t*>(a.w_att_in_t);  ldw = a.ld_w_att_in_t;  N = H;  K = D;  X = x16.dt2 + tb * D;  ldx = D; }    // B4: dh1d, LSTM cell backward
+  else              { W = reinterpret_cast<const wt_t*>(a.w_feat_t);    ldw = a.ld_w_feat_t;    N = H;  K = NK; X = x16.dtk + tb * NK; ldx = NK; }   // B1: dh~_{t-1}, du_{t-1}
   W = dp_opaque(W);
   const bool rows8 = N <= 8 * (int)gridDim.x;                  // B4 / B1 (N = H = 1024): 128 blocks of 8 rows, one per CTA
   const int rb = rows8 ? 8 : 16;
   const int nitems = (N + rb - 1) / rb;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const wt_t* wrow[2];
-    dp_rows16(wrow, W, ldw, item * rb, N, rows8);
-    dp_gemm_block<MT, 1, 3>(wrow, X, ldx, B, K, red, res, rows8);
+    dp_rows16(wrow, W, ldw, item * rb, N, rows8, 8);
+    dp_gemm_block_h<MT, 1, 3>(wrow, X, ldx, B, K, red, res, rows8);
     for (int o = tid; o < 16 * 8 * MT; o += DP_THREADS) {
       const int m = o >> 4, n = item * rb + (o & 15);
       if (m >= B || n >= N || (o & 15) >= rb) continue;
       if (ph == 0) {
-        a.dcat[(int64_t)m * DC + n] = res[o];
+        a.dcat[(int64_t)m * DC + n] = res[o] * DP_GUNSCALE;
       } else if (ph == 3) {
         const int u = n;
         const int64_t mi = (tb + m) * H + u;
-        const float dh1d = res[o] + ld_cg(a.dcat + (int64_t)m * DC + D + u);
+        const float dh1d = res[o] * DP_GUNSCALE + ld_cg(a.dcat + (int64_t)m * DC + D + u);
         float dhv = a.m_h1 ? (a.m_h1[mi] ? dh1d * scale : 0.f) : dh1d;
         if (a.d_h1) dhv += __ldg(a.d_h1 + mi);
         const float* ac = a.acts + (tb + m) * 4 * H;
@@ -729,20 +895,24 @@ __device__ __forceinline__ void bwd_gemm16(const dasa_decoder_bwd_t& a, const in
         const float dcv = ld_cg(a.dc_carry + (int64_t)m * H + u);
         const float dct = dcv + dhv * og * (1.f - tc * tc);
         float* dg = a.dgates + (tb + m) * 4 * H;
-        dg[u] = dct * gg * ig * (1.f - ig);
-        dg[H + u] = dct * cp * fg * (1.f - fg);
-        dg[2 * H + u] = dct * ig * (1.f - gg * gg);
-        dg[3 * H + u] = dhv * tc * og * (1.f - og);
+        __half* dg16 = x16.dgates + (tb + m) * 4 * H;
+        const float d0 = dct * gg * ig * (1.f - ig), d1 = dct * cp * fg * (1.f - fg), d2 = dct * ig * (1.f - gg * gg),
+                    d3 = dhv * tc * og * (1.f - og);
+        dg[u] = d0; dg[H + u] = d1; dg[2 * H + u] = d2; dg[3 * H + u] = d3;
+        dg16[u] = dp_half_sat(d0 * DP_GSCALE); dg16[H + u] = dp_half_sat(d1 * DP_GSCALE);
+        dg16[2 * H + u] = dp_half_sat(d2 * DP_GSCALE); dg16[3 * H + u] = dp_half_sat(d3 * DP_GSCALE);
         a.dc_carry[(int64_t)m * H + u] = dct * fg;
       } else {
         const int64_t mi = (tb + m) * H + n;
-        float v = res[o];
+        float v = res[o] * DP_GUNSCALE;
         v = a.m_hprev ? (a.m_hprev[mi] ? v * scale : 0.f) : v;
         v += ld_cg(a.dhdir + (int64_t)m * H + n);
         if (t > 0) {
           const int64_t pj = mi - (int64_t)B * H;
           const float ht = __ldg(a.htilde + pj);
-          a.du[pj] = (__ldg(a.d_htilde + pj) + v) * (1.f - ht * ht);
+          const float duv = (__ldg(a.d_htilde + pj) + v) * (1.f - ht * ht);
+          a.du[pj] = duv;
+          x16.du[pj] = dp_half_sat(duv * DP_GSCALE);
         } else {
           a.dh0[(int64_t)m * H + n] = v;
         }
@@ -767,7 +937,8 @@ __device__ __forceinline__ void bwd_gemm32(const dasa_decoder_bwd_t& a, const in
   const bool b6 = ph == 0;
   const wt_t* W = b6 ? reinterpret_cast<const wt_t*>(a.w_att_out_t) : reinterpret_cast<const wt_t*>(a.w_lstm_t);
   const int64_t ldw = b6 ? a.ld_w_att_out_t : a.ld_w_lstm_t;
-  const float* X = b6 ? a.du + tb * H : a.dgates + tb * 4 * H;
+  const BwdX16 x16 = bwd_x16(a);
+  const xh_t* X = b6 ? x16.du + tb * H : x16.dgates + tb * 4 * H;
   const int K = b6 ? H : 4 * H, N = b6 ? DC : KX;
   const int rb = b6 ? 24 : 32;
   W = dp_opaque(W);
@@ -779,13 +950,13 @@ __device__ __forceinline__ void bwd_gemm32(const dasa_decoder_bwd_t& a, const in
     for (int i = 0; i < 4; ++i) {
       int n = item * rb + g + 8 * ((b6 && i == 3) ? 2 : i);
       n = n < N ? n : N - 1;
-      wrow[i] = W + (int64_t)n * ldw + 4 * tq;
+      wrow[i] = W + (int64_t)n * ldw + 8 * tq;
     }
-    dp_gemm_block<MT, 2, DP_NST2>(wrow, X, K, B, K, red, res, b6);
+    dp_gemm_block_h<MT, 2, DP_NST2_H>(wrow, X, K, B, K, red, res, b6);
     for (int o = tid; o < 32 * 8 * MT; o += DP_THREADS) {
       const int m = o >> 5, nl = o & 31, n = item * rb + nl;
       if (m >= B || n >= N || nl >= rb) continue;
-      const float v = res[o];
+      const float v = res[o] * DP_GUNSCALE;
       if (b6) a.dcat[(int64_t)m * DC + n] = v;
       else if (n < E) a.demb[(tb + m) * E + n] = v;
       else if (n < E + F) a.dattn[(int64_t)m * F + (n - E)] = v;
@@ -850,7 +1021,8 @@ __device__ __noinline__ void bwd_b5b(const dasa_decoder_bwd_t& a, const SmemPlan
     for (int r = lane; r < L; r += 32) sc.aux[r] = sc.prow[r] * (sc.zrow[r] - pd);
   }
   __syncthreads();
-  dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.aux, a.dt2 + (tb + o.b) * D + o.sl.c0);      // dt2[c] = sum_l dz_l ctx[l, c]
+  dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.aux, a.dt2 + (tb + o.b) * D + o.sl.c0,      // dt2[c] = sum_l dz_l ctx[l, c]
+                  bwd_x16(a).dt2 + (tb + o.b) * D + o.sl.c0, DP_GSCALE);
   {                                                     // dctx[l, c] = alpha_l dwc[c] + dz_l t2[c]   (zero rows where masked)
     const int n4 = o.sl.cn >> 2;
     float* dst_b = a.dctx + ((tb + o.b) * L) * (int64_t)D + o.sl.c0;
@@ -891,6 +1063,7 @@ __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan
   const int64_t tb = (int64_t)t * a.B;
   const float* zp = a.zpart + (size_t)o.b * S * DP_MAXROWS;
   float* dtk_b = a.dtk + (tb + o.b) * NK;
+  __half* dtk16_b = bwd_x16(a).dtk + (tb + o.b) * NK;
   if (tid < 32) {
     const int lane = tid, k = a.shift_k, half = k / 2, Hn = a.headings;
     float* dq = sf.zrow;
@@ -929,8 +1102,15 @@ __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan
       if (lane == j) dk_mine = part;
     }
     if (o.s == 0) {
-      if (lane < k) dtk_b[F + lane] = sf.kap[lane] * (dk_mine - dot);
-      for (int c = F + k + lane; c < NK; c += 32) dtk_b[c] = 0.f;       // padding columns of the stacked projection
+      if (lane < k) {
+        const float dkl = sf.kap[lane] * (dk_mine - dot);
+        dtk_b[F + lane] = dkl;
+        dtk16_b[F + lane] = dp_half_sat(dkl * DP_GSCALE);
+      }
+      for (int c = F + k + lane; c < NK; c += 32) {       // padding columns of the stacked projection
+        dtk_b[c] = 0.f;
+        dtk16_b[c] = __float2half_rn(0.f);
+      }
     }
     __syncwarp();
     float pd = 0.f;
@@ -939,7 +1119,7 @@ __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan
     for (int r = lane; r < V; r += 32) sf.aux[r] = sf.prow[r] * (dp[r] - pd);
   }
   __syncthreads();
-  dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.aux, dtk_b + o.sl.c0);     // dt[c] = sum_v dz_v feat[v, c]
+  dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.aux, dtk_b + o.sl.c0, dtk16_b + o.sl.c0, DP_GSCALE);   // dt[c] = sum_v dz_v feat[v, c]
   {                                                     // dfeat[v, c] = q_v dattn[c] + dz_v t[c]
     const int n4 = o.sl.cn >> 2;
     float* dst_b = a.dfeat + (int64_t)t * a.dfeat_ld_t + (int64_t)o.b * a.dfeat_ld_b + o.sl.c0;
@@ -961,7 +1141,9 @@ __device__ __noinline__ void bwd_prologue(const dasa_decoder_bwd_t& a) {
   for (int i = gtid; i < B * H; i += gthreads) {      // du of the last action, zero cell-state gradient
     const int64_t j = (int64_t)(a.T - 1) * B * H + i;
     const float ht = __ldg(a.htilde + j);
-    a.du[j] = __ldg(a.d_htilde + j) * (1.f - ht * ht);
+    const float duv = __ldg(a.d_htilde + j) * (1.f - ht * ht);
+    a.du[j] = duv;
+    bwd_x16(a).du[j] = dp_half_sat(duv * DP_GSCALE);
     a.dc_carry[i] = a.d_c_last ? __ldg(a.d_c_last + i) : 0.f;
   }
 }
@@ -1147,6 +1329,16 @@ extern "C" int dasa_debug_decoder_phase_clocks(long long* out, int n) {
   return m;
 }
 
+extern "C" size_t dasa_decoder_rollout_x16_halves(int T, int B, int H, int E, int F, int D) {
+  if (T < 1 || B < 1) return 0;
+  return (size_t)T * B * ((size_t)H + (size_t)(E + F + H) + (size_t)(D + H));
+}
+
+extern "C" size_t dasa_decoder_rollout_g16_halves(int T, int B, int H, int D, int NK) {
+  if (T < 1 || B < 1) return 0;
+  return (size_t)T * B * ((size_t)H + (size_t)D + (size_t)4 * H + (size_t)NK);
+}
+
 extern "C" size_t dasa_decoder_rollout_scratch_floats(int B) { return (size_t)(B < 1 ? 1 : B) * 8 * DP_MAXROWS; }
 
 extern "C" int dasa_decoder_rollout_fwd(const dasa_decoder_fwd_t* a, void* stream) {
@@ -1157,7 +1349,8 @@ extern "C" int dasa_decoder_rollout_fwd(const dasa_decoder_fwd_t* a, void* strea
   if (!dasa_aligned16(a->feat) || !dasa_aligned16(a->ctx) || (a->feat_ld_row & 3) || (a->feat_ld_b & 3) || (a->feat_ld_t & 3) ||
       (a->ctx_ld_row & 3) || (a->ctx_ld_b & 3) || (a->ctx_ld_t & 3))
     return DASA_ERR_BAD_ALIGN;
-  const void* w[] = {a->w_feat, a->w_lstm, a->w_att_in, a->w_att_out, a->hprev_drop, a->xh, a->cat, a->tk, a->t2};
+  if ((a->H & 7) || ((a->E + a->F + a->H) & 7) || ((a->D + a->H) & 7) || (a->D & 7) || ((a->E + a->F) & 7)) return DASA_ERR_BAD_ALIGN;
+  const void* w[] = {a->w_feat, a->w_lstm, a->w_att_in, a->w_att_out, a->hprev_drop, a->xh, a->cat, a->tk, a->t2, a->x16};
   for (const void* p : w)
     if (p == nullptr || !dasa_aligned16(p)) return DASA_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1176,10 +1369,11 @@ extern "C" int dasa_decoder_rollout_bwd(const dasa_decoder_bwd_t* a, void* strea
   if (a->headings <= 0 || (a->V % a->headings) != 0) return DASA_ERR_BAD_SHAPE;
   if (!dasa_aligned16(a->feat) || !dasa_aligned16(a->ctx) || (a->feat_ld_row & 3) || (a->feat_ld_b & 3) || (a->feat_ld_t & 3) ||
       (a->ctx_ld_row & 3) || (a->ctx_ld_b & 3) || (a->ctx_ld_t & 3) || (a->dfeat_ld_row & 3) || (a->dfeat_ld_b & 3) ||
-      (a->dfeat_ld_t & 3) || (a->ld_w_feat_t & 3) || (a->ld_w_lstm_t & 3) || (a->ld_w_att_in_t & 3) || (a->ld_w_att_out_t & 3))
+      (a->dfeat_ld_t & 3) || (a->ld_w_feat_t & 7) || (a->ld_w_lstm_t & 7) || (a->ld_w_att_in_t & 7) || (a->ld_w_att_out_t & 7) ||
+      (a->H & 7) || (a->D & 7) || (a->NK & 7))
     return DASA_ERR_BAD_ALIGN;
   const void* w[] = {a->w_feat_t, a->w_lstm_t, a->w_att_in_t, a->w_att_out_t, a->du, a->dt2, a->dgates, a->dtk, a->dfeat, a->dctx,
-                     a->dcat, a->dattn};
+                     a->dcat, a->dattn, a->g16};
   for (const void* p : w)
     if (p == nullptr || !dasa_aligned16(p)) return DASA_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;

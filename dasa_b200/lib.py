@@ -56,7 +56,7 @@ class DecoderFwd(ctypes.Structure):
                  ("h0", P), ("c0", P), ("m_hprev", P), ("m_h1", P), ("drop_scale", F),
                  ("w_feat", P), ("b_feat", P), ("w_lstm", P), ("b_ih", P), ("b_hh", P), ("w_att_in", P), ("w_att_out", P)] +
                 [(k, P) for k in ("hprev_drop", "tk", "p", "q", "kappa", "xh", "acts", "c", "h1", "cat", "t2", "alpha", "htilde",
-                                  "zpart", "barrier")])
+                                  "zpart", "barrier", "x16")])
 
 
 class DecoderBwd(ctypes.Structure):
@@ -70,7 +70,7 @@ class DecoderBwd(ctypes.Structure):
                 [(k, P) for k in ("tk", "p", "q", "kappa", "acts", "c", "cat", "t2", "alpha", "htilde", "d_htilde", "d_h1",
                                   "d_c_last", "du", "dt2", "dgates", "dtk", "demb")] +
                 [("dfeat", P), ("dfeat_ld_row", L), ("dfeat_ld_b", L), ("dfeat_ld_t", L)] +
-                [(k, P) for k in ("dctx", "dh0", "dc0", "dcat", "dattn", "dhdir", "dc_carry", "zpart", "barrier")])
+                [(k, P) for k in ("dctx", "dh0", "dc0", "dcat", "dattn", "dhdir", "dc_carry", "zpart", "barrier", "g16")])
 
 
 class Epilogue(ctypes.Structure):

@@ -849,8 +849,9 @@ def decoder_rollout_fwd(emb, feat, ctx, ctx_mask, h0, c0, m_hprev, m_h1, scale, 
     a.w_att_in, a.w_att_out = _p(hw[2]), _p(hw[3])
     for k, v in o.items():
         setattr(a, k, _p(v))
-    a.zpart, a.barrier = _p(zpart), _p(barrier)
-    keep = (emb, feat, ctx, ctx_mask, h0, c0, zpart, barrier, hw)      # referenced until the launch is enqueued
+    x16 = torch.empty(lib.load().dasa_decoder_rollout_x16_halves(T, B, H, E, F, D), device=dev, dtype=torch.float16)
+    a.zpart, a.barrier, a.x16 = _p(zpart), _p(barrier), _p(x16)
+    keep = (emb, feat, ctx, ctx_mask, h0, c0, zpart, barrier, hw, x16)      # referenced until the launch is enqueued
     call("dasa_decoder_rollout_fwd", ctypes.byref(a), _stream())
     del keep
     return o
@@ -900,8 +901,9 @@ def decoder_rollout_bwd(saved, feat, ctx, ctx_mask, m_hprev, m_h1, scale, w_feat
     a.dfeat_ld_row, a.dfeat_ld_b, a.dfeat_ld_t = _ld3(g["dfeat"])
     for k, v in scratch.items():
         setattr(a, k, _p(v))
-    a.zpart, a.barrier = _p(zpart), _p(barrier)
-    keep = (d_htilde, d_h1, d_c_last, ctx_mask, scratch, zpart, barrier, hw)
+    g16 = torch.empty(lib.load().dasa_decoder_rollout_g16_halves(T, B, H, D, NK), device=dev, dtype=torch.float16)
+    a.zpart, a.barrier, a.g16 = _p(zpart), _p(barrier), _p(g16)
+    keep = (d_htilde, d_h1, d_c_last, ctx_mask, scratch, zpart, barrier, hw, g16)
     call("dasa_decoder_rollout_bwd", ctypes.byref(a), _stream())
     del keep
     return g

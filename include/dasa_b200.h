@@ -340,7 +340,12 @@ typedef struct {
   float* htilde;                                      /* [T, B, H]                                                         */
   float* zpart;                                       /* scratch, dasa_decoder_rollout_scratch_floats(B) floats            */
   unsigned int* barrier;                              /* scratch, 4 bytes, zeroed by the call                              */
+  /* scratch, dasa_decoder_rollout_x16_halves(T, B, H, E, F, D) halves, 16-byte aligned: fp16 copies of the GEMM operands
+   * (drop(h~), [emb ; attn ; h~], [wc ; drop(h_1)]). Every CTA re-reads the whole operand in every GEMM phase, so their bytes - not
+   * the weights' - dominate the L2 traffic of an action; the operands are O(1), so fp16 keeps the 11 significant bits TF32 uses.  */
+  dasa_half_t* x16;
 } dasa_decoder_fwd_t;
+size_t dasa_decoder_rollout_x16_halves(int T, int B, int H, int E, int F, int D);
 /* Backward of the same T actions (reverse order) in one cooperative launch. Weight operands are the TRANSPOSED weights
  * ([in, out] rows with leading dimension ld_*): dX = dY.W then streams K-major rows like the forward. Weight gradients are NOT
  * formed here: du, dt2, dgates, dtk (the dY of the four projections) are left in [T, B, .] buffers for one long-K GEMM each.
@@ -367,7 +372,11 @@ typedef struct {
   float* dh0; float* dc0;                             /* [B, H]                                                            */
   float* dcat; float* dattn; float* dhdir; float* dc_carry;   /* scratch [B, D+H], [B, F], [B, H], [B, H]                  */
   float* zpart; unsigned int* barrier;
+  /* scratch, dasa_decoder_rollout_g16_halves(T, B, H, D, NK) halves, 16-byte aligned: fp16 copies of the gradient operands du,
+   * dt2, dgates, dtk scaled by 2^8 (saturating), the X operand of the four dX projections; the sums are rescaled by 2^-8.       */
+  dasa_half_t* g16;
 } dasa_decoder_bwd_t;
+size_t dasa_decoder_rollout_g16_halves(int T, int B, int H, int D, int NK);
 int dasa_decoder_rollout_supported(int B, int H, int E, int F, int V, int L, int D, int NK, int shift_k);
 size_t dasa_decoder_rollout_scratch_floats(int B);
 /* Profiling aid: SM-clock timestamps of CTA 0 at the phase barriers of the first 4 actions of the LAST rollout launch (forward or
