@@ -98,7 +98,20 @@ struct PkBwd {
   int pos[2], n[2], n_carried[2];                          // rows < n_carried continue a gradient; the others start from d*_fin
   int L, H;
   PkDrop drop;
+  // fp16 recurrence (optional): dgates also as fp16 scaled by PK_GSCALE (saturating) = the A operand of the next dh GEMM on
+  // tcgen05 kind::f16; the partial sums then carry the same factor and are multiplied by part_scale = 1 / PK_GSCALE (exact)
+  __half* dg16[2];
+  float part_scale;
 };
+// 2^8: fp16's normal range then covers |dgate| in [2.4e-7, 256) with the 11 significant bits TF32 keeps; smaller values keep an
+// absolute step of 2.3e-10, larger ones saturate
+constexpr float PK_GSCALE = 256.f;
+__device__ __forceinline__ uint2 pk_half4_sat(float a, float b, float c, float d) {
+  uint2 r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(d), "f"(c));
+  return r;
+}
 
 __global__ void __launch_bounds__(256) bilstm_packed_pointwise_bwd_kernel(PkBwd p) {
   const int d = blockIdx.y;
@@ -115,6 +128,8 @@ __global__ void __launch_bounds__(256) bilstm_packed_pointwise_bwd_kernel(PkBwd 
         const float4 v = ldg_stream4(p.part[d] + (int64_t)k * p.part_stride + sb);
         dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dh[e] *= p.part_scale;
       const float4 v = *reinterpret_cast<const float4*>(p.dc_in[d] + sb);
       dc[0] = v.x; dc[1] = v.y; dc[2] = v.z; dc[3] = v.w;
     } else {                                                  // the step that produced this sequence's final state
@@ -152,6 +167,14 @@ __global__ void __launch_bounds__(256) bilstm_packed_pointwise_bwd_kernel(PkBwd 
     *reinterpret_cast<float4*>(dg + H) = make_float4(df[0], df[1], df[2], df[3]);
     *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(dgg[0], dgg[1], dgg[2], dgg[3]);
     *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+    if (p.dg16[d] != nullptr) {
+      __half* dh16 = p.dg16[d] + (int64_t)r * 4 * H + j;
+      const float s = PK_GSCALE;
+      *reinterpret_cast<uint2*>(dh16) = pk_half4_sat(di[0] * s, di[1] * s, di[2] * s, di[3] * s);
+      *reinterpret_cast<uint2*>(dh16 + H) = pk_half4_sat(df[0] * s, df[1] * s, df[2] * s, df[3] * s);
+      *reinterpret_cast<uint2*>(dh16 + 2 * H) = pk_half4_sat(dgg[0] * s, dgg[1] * s, dgg[2] * s, dgg[3] * s);
+      *reinterpret_cast<uint2*>(dh16 + 3 * H) = pk_half4_sat(dO[0] * s, dO[1] * s, dO[2] * s, dO[3] * s);
+    }
     *reinterpret_cast<float4*>(p.dc_out[d] + sb) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
   }
 }
@@ -312,6 +335,11 @@ extern "C" int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* a, void* w
   const size_t RH = (size_t)R * H;
   float* part[2] = {static_cast<float*>(workspace), static_cast<float*>(workspace) + (size_t)PK_BWD_SPLITS * RH};
   const float* Bw[2] = {a->w_hh_t[0], a->w_hh_t[1]};          // [H, 4H]: K-major B operand of dh = dgates * W_hh
+  // fp16 form of the recurrent GEMM (dgates scaled by 2^8 as the fp16 A operand, W_hh^T as fp16): twice the tensor rate on the
+  // 2 x L dependent launches; the fp32 dgates (weight gradients, dX) are written as before
+  const bool f16 = a->w_hh_t16[0] != nullptr && a->w_hh_t16[1] != nullptr && a->dg16[0] != nullptr && a->dg16[1] != nullptr &&
+                   (H % 64) == 0;
+  const __half* Bw16[2] = {reinterpret_cast<const __half*>(a->w_hh_t16[0]), reinterpret_cast<const __half*>(a->w_hh_t16[1])};
   int nparts = 0;
   for (int s = Le - 1; s >= 0; --s) {
     const int cur = (Le - 1 - s) & 1, prv = cur ^ 1;           // ping-pong halves of dc_work
@@ -326,8 +354,10 @@ extern "C" int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* a, void* w
       p.acts[d] = a->acts[d] + off[pp] * 4 * H;
       p.c_prev[d] = a->cs[d] + s * RH; p.c_new[d] = a->cs[d] + (s + 1) * RH;
       p.dgates[d] = a->dgates[d] + off[pp] * 4 * H;
+      p.dg16[d] = f16 ? reinterpret_cast<__half*>(a->dg16[d]) + off[pp] * 4 * H : nullptr;
       p.pos[d] = pp; p.n[d] = n[pp];
     }
+    p.part_scale = f16 ? 1.f / PK_GSCALE : 1.f;
     // rows that continue a gradient from step s + 1: forward direction the sequences still alive at p0 + 1; reverse direction
     // everything alive now except at the very first backward step (position 0 produced every final state)
     p.n_carried[0] = (p0 + 1 < Le) ? n[p0 + 1] : 0;
@@ -337,8 +367,13 @@ extern "C" int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* a, void* w
     p.drop = pk_drop(a->out_mask, a->drop_seed_dev, a->drop_seed, a->drop_base, a->drop_p, a->drop_scale);
     bilstm_packed_pointwise_bwd_kernel<<<pk_grid(p.n[0] > p.n[1] ? p.n[0] : p.n[1], H), 256, 0, st>>>(p);
     if (s > 0) {                                              // dh of the states that fed step s (the gradient before step 0 is unused)
-      const float* A[2] = {p.dgates[0], p.dgates[1]};
-      nparts = dasa_gemm_tc_pair_grouped2(n[p0], n[p1], H, 4 * H, A, 4 * H, Bw, 4 * H, part, H, PK_BWD_SPLITS, (int64_t)RH, st);
+      if (f16) {
+        const __half* A16[2] = {p.dg16[0], p.dg16[1]};
+        nparts = dasa_gemm_tc_pair_grouped2_f16(n[p0], n[p1], H, 4 * H, A16, 4 * H, Bw16, 4 * H, part, H, PK_BWD_SPLITS, (int64_t)RH, st);
+      } else {
+        const float* A[2] = {p.dgates[0], p.dgates[1]};
+        nparts = dasa_gemm_tc_pair_grouped2(n[p0], n[p1], H, 4 * H, A, 4 * H, Bw, 4 * H, part, H, PK_BWD_SPLITS, (int64_t)RH, st);
+      }
       if (nparts < 0) return nparts;
     }
   }

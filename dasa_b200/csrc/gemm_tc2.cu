@@ -850,6 +850,37 @@ int dasa_gemm_tc_pair_grouped2(int M0, int M1, int N, int K, const float* const 
   return launch_pair_e<256, 5, DASA_EPI_NONE>(ta, tb, p, st) == DASA_OK ? p.splits : DASA_ERR_CUDA;
 }
 
+// The grouped / split-K launch with fp16 operands (tcgen05 kind::f16, fp32 partial sums): the backward recurrence of the packed
+// bi-LSTM, dh = dgates W_hh over scaled fp16 copies of dgates (bilstm_packed.cu). K % 8 == 0, lda / ldb in halves.
+int dasa_gemm_tc_pair_grouped2_f16(int M0, int M1, int N, int K, const __half* const A[2], int64_t lda, const __half* const B[2],
+                                   int64_t ldb, float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st) {
+  if (M0 < 0 || M1 < 0 || M0 + M1 <= 0 || N <= 0 || K < 2 * P_BK || (K & 7) || splits < 1) return DASA_ERR_BAD_SHAPE;
+  if ((lda & 7) || (ldb & 7)) return DASA_ERR_BAD_ALIGN;
+  ++g_gemm_routes[DASA_ROUTE_PAIR_GROUPED];
+  PairParams p{};
+  p.M = M0; p.M2 = M1; p.N = N; p.K = K; p.alpha = 1.f; p.beta = 0.f; p.C[0] = C[0]; p.C[1] = C[1]; p.ldc = ldc;
+  p.tiles_n = (int)dasa_cdiv(N, 256);
+  p.tiles_mn = (int)(dasa_cdiv(M0, 2 * P_BM) * p.tiles_n);
+  p.tiles_mn2 = (int)(dasa_cdiv(M1, 2 * P_BM) * p.tiles_n);
+  const int nkb = (int)dasa_cdiv(K, 2 * P_BK);
+  if (splits > nkb) splits = nkb;
+  p.kb_per_split = (int)dasa_cdiv(nkb, splits);
+  p.splits = (int)dasa_cdiv(nkb, p.kb_per_split);
+  p.split_stride = split_stride;
+  p.tiles_total = (p.tiles_mn + p.tiles_mn2) * p.splits;
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta[2], tb[2];
+  for (int g = 0; g < 2; ++g) {
+    const int Mg = g ? M1 : M0;
+    if (Mg == 0) continue;
+    if (!dasa_aligned16(A[g]) || !dasa_aligned16(B[g])) return DASA_ERR_BAD_ALIGN;
+    if (!pair_make_map_f16(&ta[g], A[g], Mg, K, lda, P_BM) || !pair_make_map_f16(&tb[g], B[g], N, K, ldb, 128)) return DASA_ERR_UNSUPPORTED;
+  }
+  if (M0 == 0) { ta[0] = ta[1]; tb[0] = tb[1]; }
+  if (M1 == 0) { ta[1] = ta[0]; tb[1] = tb[0]; }
+  return launch_pair_e<256, 5, DASA_EPI_NONE, false, false, true>(ta, tb, p, st) == DASA_OK ? p.splits : DASA_ERR_CUDA;
+}
+
 // One recurrence step of the packed bi-LSTM, both directions, GEMM + cell update in ONE launch (lstm_epi.cuh). Tiles cover
 // max(n, n_next) rows per direction (rows that join at the next step get their zero state from the epilogue); the operand maps
 // cover the n live rows only, so the rest of a tile's A rows are zero-filled by TMA.

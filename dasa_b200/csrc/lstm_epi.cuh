@@ -63,3 +63,6 @@ struct LstmEpi {
 // gemm_tc2.cu: one launch = the recurrent GEMMs of both directions (fp16 operands, tcgen05 kind::f16) + the cell update.
 // A16[d]: [n[d], H] fp16 state rows, W16[d]: [4H, H] fp16 interleaved recurrent weights. H % 64 == 0.
 int dasa_gemm_tc_pair_lstm(const __half* const A16[2], const __half* const W16[2], const LstmEpi& le, cudaStream_t st);
+// gemm_tc2.cu: grouped (two directions) split-K GEMM on fp16 operands, fp32 partial sums; returns the number of K splits used.
+int dasa_gemm_tc_pair_grouped2_f16(int M0, int M1, int N, int K, const __half* const A[2], int64_t lda, const __half* const B[2],
+                                   int64_t ldb, float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st);

@@ -582,11 +582,18 @@ class PackedBiLSTMFn(torch.autograd.Function):
 
         def pp(t, d):
             return None if t is None else t[d].data_ptr()
+        if ops.fused_lstm_cell and H >= 64 and H % 64 == 0:       # dh = dgates W_hh on fp16 operands (scaled dgates copy)
+            wt16 = (ops.half_weight(wt[0]), ops.half_weight(wt[1]))
+            dg16 = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float16)
+            half = (P2(wt16[0].data_ptr(), wt16[1].data_ptr()), P2(dg16[0].data_ptr(), dg16[1].data_ptr()))
+        else:
+            half = (P2(None, None), P2(None, None))
         a = ops.lib.BiLstmPackedBwd(R, L, H, cast(plan.n_rows, ops.lib.P), cast(plan.off, ops.lib.P), plan.perm.data_ptr(),
                                     P2(wt[0].data_ptr(), wt[1].data_ptr()), P2(acts[0].data_ptr(), acts[1].data_ptr()),
                                     P2(cs[0].data_ptr(), cs[1].data_ptr()), dout.data_ptr(), P2(pp(dhf, 0), pp(dhf, 1)),
                                     P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates[0].data_ptr(), dgates[1].data_ptr()),
-                                    P2(work[0].data_ptr(), work[1].data_ptr()), *_drop_fields(ctx.drop, ctx.drop_scale, (R, L, 2 * H)))
+                                    P2(work[0].data_ptr(), work[1].data_ptr()), *_drop_fields(ctx.drop, ctx.drop_scale, (R, L, 2 * H)),
+                                    *half)
         ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 1))
         ops.call("dasa_bilstm_packed_bwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         dxc = None

@@ -45,7 +45,8 @@ class BiLstmPackedBwd(ctypes.Structure):
     """dasa_bilstm_packed_bwd_t"""
     _fields_ = [("R", I), ("L", I), ("H", I), ("n_rows", P), ("off", P), ("perm", P), ("w_hh_t", P * 2), ("acts", P * 2), ("cs", P * 2),
                 ("dout", P), ("dh_fin", P * 2), ("dc_fin", P * 2), ("dgates", P * 2), ("dc_work", P * 2),
-                ("out_mask", P), ("drop_seed_dev", P), ("drop_seed", U), ("drop_base", U), ("drop_p", F), ("drop_scale", F)]
+                ("out_mask", P), ("drop_seed_dev", P), ("drop_seed", U), ("drop_base", U), ("drop_p", F), ("drop_scale", F),
+                ("w_hh_t16", P * 2), ("dg16", P * 2)]
 
 
 class DecoderFwd(ctypes.Structure):

@@ -290,6 +290,10 @@ typedef struct {
   const float* dout; const float* dh_fin[2]; const float* dc_fin[2];
   float* dgates[2]; float* dc_work[2];
   const uint8_t* out_mask; const uint64_t* drop_seed_dev; uint64_t drop_seed; uint64_t drop_base; float drop_p; float drop_scale;
+  /* fp16 recurrence (all four non-NULL and H % 64 == 0; else TF32): w_hh_t16[d] = fp16 copy of w_hh_t[d], dg16[d] [N, 4H] fp16
+   * scratch receiving dgates * 2^8 (saturating) = the A operand of dh = dgates W_hh on tcgen05 kind::f16 (the sums are rescaled
+   * by 2^-8; fp16 keeps TF32's 11 significant bits for |dgate| in [2.4e-7, 256)).                                               */
+  const dasa_half_t* w_hh_t16[2]; dasa_half_t* dg16[2];
 } dasa_bilstm_packed_bwd_t;
 size_t dasa_bilstm_packed_workspace(int R, int H, int backward);
 int dasa_bilstm_packed_fwd(const dasa_bilstm_packed_fwd_t* args, void* workspace, size_t workspace_bytes, void* stream);
