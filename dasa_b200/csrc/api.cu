@@ -65,6 +65,12 @@ extern "C" int dasa_gemm_f16(int M, int N, int K, const dasa_half_t* A, int64_t 
   return dasa_gemm_tc_pair_f16(M, N, K, A, lda, B, ldb, C, ldc, c_half, epilogue, ep, (cudaStream_t)stream);
 }
 
+extern "C" int dasa_gemm_f16_mn(int M, int N, int K, float alpha, const dasa_half_t* A, int64_t lda, const dasa_half_t* B, int64_t ldb,
+                                float beta, float* C, int64_t ldc, void* workspace, size_t workspace_bytes, void* stream) {
+  if (A == nullptr || B == nullptr || C == nullptr) return DASA_ERR_BAD_SHAPE;
+  return dasa_gemm_tc_pair_mn_f16(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, const float* A, int64_t lda,
                          const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int epilogue,
                          const dasa_epilogue_t* epi, int precision, void* workspace, size_t workspace_bytes,

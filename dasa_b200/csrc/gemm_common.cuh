@@ -121,6 +121,9 @@ int dasa_gemm_tc_pair_mn(int a_kmajor, int b_kmajor, int M, int N, int K, float 
 int dasa_gemm_tc_pair_grouped(int M, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,
                               float* const C[2], int64_t ldc, int splits, int64_t split_stride, cudaStream_t st);
 bool dasa_gemm_f16_pair_supported(int M, int N, int K);
+// C = alpha * A^T B + beta * C, A [K][lda], B [K][ldb] fp16 (both MN-major), split-K through the workspace like dasa_gemm_tc_pair_mn
+int dasa_gemm_tc_pair_mn_f16(int M, int N, int K, float alpha, const void* A, int64_t lda, const void* B, int64_t ldb, float beta,
+                             float* C, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int dasa_gemm_tc_pair_f16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_half,
                           int epilogue, const EpiParams& ep, cudaStream_t st);
 int dasa_gemm_tc_pair_grouped2(int M0, int M1, int N, int K, const float* const A[2], int64_t lda, const float* const B[2], int64_t ldb,

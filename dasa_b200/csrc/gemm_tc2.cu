@@ -129,6 +129,20 @@ __device__ __forceinline__ uint64_t p_desc_sw128_mn(const void* smem_ptr) {
   d |= (uint64_t)1 << 61;
   return d;
 }
+// MN-major 16-bit operand: the ordinary 128-byte swizzle (16-byte atoms, descriptor layout type 2). A TMA box {64 mn, BKE k}
+// written with CU_TENSOR_MAP_SWIZZLE_128B gives, per 64-wide chunk of the M/N extent, BKE rows (one per k) of 128 bytes swizzled in
+// groups of 8 rows (1024 B). Canonical form ((8,8,n),(8,k)):((1,8,LBO),(64,SBO)) in elements: LBO = distance between 64-wide M/N
+// chunks (BKE * 128 B), SBO = distance between groups of 8 k rows (1024 B). One UMMA (K = 16) consumes two groups of every chunk.
+__device__ __forceinline__ uint64_t p_desc_sw128_mn16(const void* smem_ptr, int bke) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((bke * 128) >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -357,15 +371,16 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // both CTAs' boxes complete on the leader's barrier
           const uint32_t fb = p_mapa(smem_u32(&full_bar[s]), 0);
           unsigned char* dst = tiles + s * STAGE_BYTES;
+          constexpr int MNC = F16 ? 64 : 32;             // M/N elements per 128-byte row of an MN-major chunk
           if constexpr (AMN) {
 #pragma unroll
-            for (int c = 0; c < P_BM / 32; ++c) p_tma_load_2sm(dst + c * (P_BK * 128), ma, m0 + 32 * c, kb * P_BK, fb);
+            for (int c = 0; c < P_BM / MNC; ++c) p_tma_load_2sm(dst + c * (BKE * 128), ma, m0 + MNC * c, kb * BKE, fb);
           } else {
             p_tma_load_2sm(dst, ma, kb * BKE, m0, fb);
           }
           if constexpr (BMN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) p_tma_load_2sm(dst + A_BYTES + c * (P_BK * 128), mb, nb0 + 32 * c, kb * P_BK, fb);
+            for (int c = 0; c < (BN / 2) / MNC; ++c) p_tma_load_2sm(dst + A_BYTES + c * (BKE * 128), mb, nb0 + MNC * c, kb * BKE, fb);
           } else {
             p_tma_load_2sm(dst + A_BYTES, mb, kb * BKE, nb0, fb);
           }
@@ -397,10 +412,10 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&full_bar[s], ph);
           p_fence_after();
           unsigned char* src = tiles + s * STAGE_BYTES;
-          const uint64_t da = AMN ? p_desc_sw128_mn(src) : p_desc_sw128(src);
-          const uint64_t db = BMN ? p_desc_sw128_mn(src + A_BYTES) : p_desc_sw128(src + A_BYTES);
-          // K-major: 8 tf32 = 32 B further along the swizzled row; MN-major: the next group of 8 k rows (1024 B)
-          constexpr uint64_t ka = AMN ? 64 : 2, kbs = BMN ? 64 : 2;
+          const uint64_t da = AMN ? (F16 ? p_desc_sw128_mn16(src, BKE) : p_desc_sw128_mn(src)) : p_desc_sw128(src);
+          const uint64_t db = BMN ? (F16 ? p_desc_sw128_mn16(src + A_BYTES, BKE) : p_desc_sw128_mn(src + A_BYTES)) : p_desc_sw128(src + A_BYTES);
+          // K-major: 8 tf32 / 16 fp16 = 32 B further along the swizzled row; MN-major: the next 8 (tf32) / 16 (fp16) k rows
+          constexpr uint64_t ka = AMN ? (F16 ? 128 : 64) : 2, kbs = BMN ? (F16 ? 128 : 64) : 2;
 #pragma unroll
           for (int k = 0; k < P_BK / 8; ++k) {             // 4 UMMAs of 32 bytes of K each (8 tf32 / 16 fp16)
             if constexpr (F16) p_umma_f16_pair(d_tmem, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
@@ -848,6 +863,60 @@ int dasa_gemm_tc_pair_grouped2(int M0, int M1, int N, int K, const float* const 
   if (M0 == 0) { ta[0] = ta[1]; tb[0] = tb[1]; }            // an absent group has no tiles: its maps are never fetched
   if (M1 == 0) { ta[1] = ta[0]; tb[1] = tb[0]; }
   return launch_pair_e<256, 5, DASA_EPI_NONE>(ta, tb, p, st) == DASA_OK ? p.splits : DASA_ERR_CUDA;
+}
+
+// dW-shaped products on fp16 operands: C[M, N] = alpha * A^T B + beta * C with A stored [K][M] and B stored [K][N] as IEEE fp16
+// (both MN-major: the row index of both arrays is the reduction index), tcgen05 kind::f16, fp32 accumulate, K split like the
+// TF32 MN-major path. The bi-LSTM weight gradients dW_ih = dgates^T x, dW_hh = dgates^T h_prev use it with the fp16 copies the
+// recurrence already keeps (dgates * 2^8, the state rows): twice the tensor rate and half the operand bytes of the TF32 form.
+namespace {
+bool pair_make_map_mn16(CUtensorMap* map, const void* base, int64_t cols, int64_t K, int64_t ld) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(dasa_tensormap_encoder());
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)(2 * P_BK)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+int dasa_gemm_tc_pair_mn_f16(int M, int N, int K, float alpha, const void* A, int64_t lda, const void* B, int64_t ldb, float beta,
+                             float* C, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K < 2 * P_BK) return DASA_ERR_BAD_SHAPE;
+  if (!dasa_aligned16(A) || !dasa_aligned16(B) || (lda & 7) || (ldb & 7)) return DASA_ERR_BAD_ALIGN;
+  ++g_gemm_routes[DASA_ROUTE_PAIR_F16];
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C[0] = C; p.C[1] = C; p.ldc = ldc;
+  p.tiles_n = (int)dasa_cdiv(N, 256);
+  p.tiles_mn = (int)(dasa_cdiv(M, 2 * P_BM) * p.tiles_n);
+  const int nkb = (int)dasa_cdiv(K, 2 * P_BK);
+  p.splits = 1; p.kb_per_split = nkb; p.split_stride = 0;
+  p.tiles_total = p.tiles_mn;
+  int splits = dasa_gemm_pair_mn_splits(M, N, K);
+  if ((N & 3) != 0 || workspace == nullptr || workspace_bytes < (size_t)splits * M * N * sizeof(float) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+    splits = 1;
+  if (splits > 1) {
+    p.kb_per_split = (int)dasa_cdiv(nkb, splits);
+    p.splits = (int)dasa_cdiv(nkb, p.kb_per_split);
+    p.split_stride = (int64_t)M * N;
+    p.C[0] = p.C[1] = static_cast<float*>(workspace);
+    p.ldc = N; p.alpha = 1.f; p.beta = 0.f;
+    p.tiles_total = p.tiles_mn * p.splits;
+  }
+  p.num_pairs = p.tiles_total < DASA_NUM_SMS / 2 ? p.tiles_total : DASA_NUM_SMS / 2;
+  CUtensorMap ta[2], tb[2];
+  if (!pair_make_map_mn16(&ta[0], A, M, K, lda) || !pair_make_map_mn16(&tb[0], B, N, K, ldb)) return DASA_ERR_UNSUPPORTED;
+  ta[1] = ta[0]; tb[1] = tb[0];
+  int rc = launch_pair_e<256, 5, DASA_EPI_NONE, true, true, true>(ta, tb, p, st);
+  if (rc != DASA_OK || p.splits <= 1) return rc;
+  const int64_t work = (int64_t)M * (N >> 2);
+  const unsigned grid = (unsigned)(dasa_cdiv(work, 256) < (int64_t)DASA_NUM_SMS * 8 ? dasa_cdiv(work, 256) : (int64_t)DASA_NUM_SMS * 8);
+  pair_split_reduce_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(workspace), p.splits, p.split_stride, alpha, beta, C, ldc, M, N);
+  return dasa_check_launch("pair_split_reduce_kernel");
 }
 
 // The grouped / split-K launch with fp16 operands (tcgen05 kind::f16, fp32 partial sums): the backward recurrence of the packed

@@ -105,6 +105,13 @@ int dasa_debug_gemm_route_counts(int64_t* out, int n, int reset);
 int dasa_gemm_f16_supported(int M, int N, int K);
 int dasa_gemm_f16(int M, int N, int K, const dasa_half_t* A, int64_t lda, const dasa_half_t* B, int64_t ldb, void* C, int64_t ldc,
                   int c_half, int epilogue, const dasa_epilogue_t* epi, void* stream);
+/* C[M, N] = alpha * A^T B + beta * C with A stored [K][lda] and B stored [K][ldb] as IEEE fp16 (both MN-major: the rows of both
+ * arrays run over the reduction index - the shape of a weight gradient dW = dY^T X), tcgen05 kind::f16, fp32 accumulate, K split
+ * through the workspace (dasa_gemm_workspace_bytes(M, N, K, DASA_PREC_TF32) bytes) with a deterministic fold. lda / ldb in
+ * elements, multiples of 8; K >= 64. The packed bi-LSTM's dW_ih / dW_hh (r2rmodel.py:2339-2357 backward) use it with the fp16
+ * operand copies its recurrence keeps (alpha = 2^-8 undoes the gradient copy's scale).                                        */
+int dasa_gemm_f16_mn(int M, int N, int K, float alpha, const dasa_half_t* A, int64_t lda, const dasa_half_t* B, int64_t ldb,
+                     float beta, float* C, int64_t ldc, void* workspace, size_t workspace_bytes, void* stream);
 size_t dasa_gemm_workspace_bytes(int M, int N, int K, int precision);
 /* 1 when dasa_gemm(DASA_PREC_TF32) runs this operand-layout combination on the tensor cores directly: always for two K-major
  * operands; for an MN-major A ([K][M] in memory) and / or B ([K][N]) when the problem is large enough for the persistent CTA-pair
