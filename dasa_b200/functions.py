@@ -59,6 +59,21 @@ def _wgrad(weight, dy, x, bias=None, bias2=None):
     ent[3].append(x2)
 
 
+def _wgrad16(weight, dy16, x16, alpha, dy, bias=None, bias2=None):
+    """dW += alpha * dy16^T x16 on the fp16-operand tensor-core kernel (operand copies the producer already keeps: the bi-LSTM's
+    scaled dgates and state rows); db += colsum(dy) from the fp32 gradient. Immediately, or queued like _wgrad."""
+    if not weight.requires_grad:
+        return
+    if not _defer:
+        ops.linear_bwd_weight_f16(dy16, x16, _zeros_like_grad(weight), alpha, True)
+        _bias_grads(dy, bias, bias2)
+        return
+    _queue16.append((weight, dy16, x16, alpha, dy, bias, bias2))
+
+
+_queue16 = []
+
+
 def _inside(t, owner):
     """True when tensor t lives inside the flat buffer `owner`."""
     if t is None:
@@ -89,6 +104,15 @@ def flush_weight_grads(owner=None):
         done.append(key)
     for key in done:
         del _queue[key]
+    keep = []
+    for ent in _queue16:
+        weight, dy16, x16, alpha, dy, bias, bias2 = ent
+        if owner is not None and not _inside(weight.grad, owner):
+            keep.append(ent)
+            continue
+        ops.linear_bwd_weight_f16(dy16, x16, _zeros_like_grad(weight), alpha, True)
+        _bias_grads(dy, bias, bias2)
+    _queue16[:] = keep
 
 
 def _rowmajor(t):
@@ -534,7 +558,12 @@ class PackedBiLSTMFn(torch.autograd.Function):
         dev = x_packed.device
         xc = x_packed.detach().index_select(0, plan.src)                       # [N, In] position-block order
         params = ((w_ih_f, w_hh_f, b_ih_f, b_hh_f), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))
-        xp = [ops.linear_fwd(xc, w_ih) for (w_ih, _, _, _) in params]          # [N, 4H]: valid tokens only
+        use16 = ops.fused_lstm_cell and H >= 64 and H % 64 == 0 and xc.shape[1] % 8 == 0 and xc.shape[1] >= 64
+        xc16 = ops.to_half(xc) if use16 else None                              # LayerNorm output, O(1): fp16 keeps TF32's 11 bits
+        if use16 and ops.gemm_f16_supported(N, 4 * H, xc.shape[1]):
+            xp = [ops.linear_f16(xc16, ops.half_weight(w_ih)) for (w_ih, _, _, _) in params]
+        else:
+            xp = [ops.linear_fwd(xc, w_ih) for (w_ih, _, _, _) in params]      # [N, 4H]: valid tokens only
         hprev = torch.empty(2, N, H, device=dev, dtype=torch.float32)
         cs = torch.empty(2, L + 1, R, H, device=dev, dtype=torch.float32)
         acts = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float32)
@@ -542,6 +571,7 @@ class PackedBiLSTMFn(torch.autograd.Function):
         fin = torch.empty(2, 2, R, H, device=dev, dtype=torch.float32)         # [h | c][direction] in rank order
         P2 = ops.lib.P * 2
         cast = ops.ctypes.cast
+        h16 = None
         if ops.fused_lstm_cell and H >= 64 and H % 64 == 0:                    # cell update in the recurrent GEMM's epilogue
             w16 = (ops.lstm_whh_interleaved(w_hh_f), ops.lstm_whh_interleaved(w_hh_r))
             h16 = torch.empty(2, N, H, device=dev, dtype=torch.float16)
@@ -560,6 +590,7 @@ class PackedBiLSTMFn(torch.autograd.Function):
         h_fin = fin[0].index_select(1, plan.rank_of)
         c_fin = fin[1].index_select(1, plan.rank_of)
         ctx.plan, ctx.drop, ctx.drop_scale = plan, drop, drop_scale
+        ctx.half = (xc16, h16) if (use16 and h16 is not None) else None        # fp16 operand copies for the weight gradients
         ctx.save_for_backward(xc, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hprev, cs, acts)
         return out, h_fin, c_fin
 
@@ -582,6 +613,7 @@ class PackedBiLSTMFn(torch.autograd.Function):
 
         def pp(t, d):
             return None if t is None else t[d].data_ptr()
+        dg16 = None
         if ops.fused_lstm_cell and H >= 64 and H % 64 == 0:       # dh = dgates W_hh on fp16 operands (scaled dgates copy)
             wt16 = (ops.half_weight(wt[0]), ops.half_weight(wt[1]))
             dg16 = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float16)
@@ -597,9 +629,14 @@ class PackedBiLSTMFn(torch.autograd.Function):
         ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 1))
         ops.call("dasa_bilstm_packed_bwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         dxc = None
+        half16 = ctx.half if (dg16 is not None and ctx.half is not None and N >= 64) else None
         for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
-            _wgrad(w_ih, dgates[d], xc, b_ih, b_hh)                            # db_ih == db_hh: one column sum
-            _wgrad(w_hh, dgates[d], hprev[d])
+            if half16 is not None:      # dW = 2^-8 (dgates * 2^8)^T x on kind::f16 with the copies the recurrence keeps
+                _wgrad16(w_ih, dg16[d], half16[0], 1.0 / 256.0, dgates[d], b_ih, b_hh)
+                _wgrad16(w_hh, dg16[d], half16[1][d], 1.0 / 256.0, None)
+            else:
+                _wgrad(w_ih, dgates[d], xc, b_ih, b_hh)                        # db_ih == db_hh: one column sum
+                _wgrad(w_hh, dgates[d], hprev[d])
             if ctx.needs_input_grad[0]:
                 g = ops.linear_bwd_input(dgates[d], w_ih)
                 dxc = g if dxc is None else dxc + g

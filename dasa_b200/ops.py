@@ -292,6 +292,20 @@ def linear_bwd_weight(dy, x, dw, accumulate=True, precision=None):
     return dw
 
 
+def linear_bwd_weight_f16(dy16, x16, dw, alpha=1.0, accumulate=True):
+    """dw[N, K] (+)= alpha * dy16[M, N]^T @ x16[M, K] with fp16 operands read where they lie (both MN-major: dasa_gemm_f16_mn)."""
+    assert dy16.dtype == torch.float16 and x16.dtype == torch.float16 and dy16.dim() == 2 and x16.dim() == 2
+    assert dy16.stride(1) == 1 and x16.stride(1) == 1 and dy16.shape[0] == x16.shape[0]
+    M, N = dy16.shape
+    K = x16.shape[1]
+    assert dw.shape == (N, K) and dw.is_contiguous() and dw.dtype == torch.float32
+    nbytes = lib.load().dasa_gemm_workspace_bytes(N, K, M, PREC_TF32)
+    ws = workspace(nbytes) if nbytes else None
+    call("dasa_gemm_f16_mn", N, K, M, float(alpha), _p(dy16), dy16.stride(0), _p(x16), x16.stride(0), 1.0 if accumulate else 0.0,
+         _p(dw), K, _p(ws), ws.numel() if ws is not None else 0, _stream())
+    return dw
+
+
 def colsum(x, out, accumulate=True):
     x2, M, N, ld = _rows(x)
     call("dasa_colsum", _p(x2), ld, M, N, _p(out), int(accumulate), _stream())

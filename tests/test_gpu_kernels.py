@@ -852,6 +852,30 @@ def test_linear_backward_helpers_tf32_mn_major():
         ops.set_precision("fp32")
 
 
+@pytest.mark.parametrize("rows,N,K", [(3000, 512, 768), (19810, 4096, 1024), (1000, 304, 200), (4100, 1024, 768)])
+def test_gemm_f16_mn_major_weight_gradient(rows, N, K):
+    """dasa_gemm_f16_mn: dW[N, K] = alpha * dY^T X (+ beta dW) with fp16 operands stored row-per-reduction-index (both MN-major),
+    tcgen05 kind::f16, split-K with a deterministic fold, against fp64 on the same fp16 values: only fp32 accumulation error."""
+    from dasa_b200 import ops
+    g = torch.Generator().manual_seed(rows + N)
+    dy = (torch.randn(rows, N, generator=g) * 0.3).half().to(DEV)
+    x = (torch.randn(rows, K, generator=g) * 0.5).half().to(DEV)
+    dw0 = torch.randn(N, K, generator=g).to(DEV)
+    ref = 0.25 * (dy.double().t() @ x.double())
+    dw = dw0.clone()
+    ops.linear_bwd_weight_f16(dy, x, dw, alpha=0.25, accumulate=True)
+    assert rel_err(dw.double(), ref + dw0.double()) <= 1e-4, rel_err(dw.double(), ref + dw0.double())
+    dw2 = torch.full_like(dw0, float("nan"))
+    ops.linear_bwd_weight_f16(dy, x, dw2, alpha=0.25, accumulate=False)
+    assert rel_err(dw2.double(), ref) <= 1e-4
+    # strided operands (column slices of wider buffers), deterministic
+    wide = torch.zeros(rows, N + 64, dtype=torch.float16, device=DEV)
+    wide[:, 8:8 + N] = dy
+    dw3 = torch.zeros_like(dw0)
+    ops.linear_bwd_weight_f16(wide[:, 8:8 + N], x, dw3, alpha=0.25, accumulate=False)
+    assert torch.equal(dw3, dw2)
+
+
 # ------------------------------------------------------------------------------ padding-free bi-LSTM (bilstm_packed.cu)
 @pytest.mark.parametrize("R,L,In,H,seed", [(70, 12, 64, 64, 0), (300, 21, 96, 128, 1), (45, 9, 64, 32, 2)])
 def test_packed_bilstm_matches_padded_path(R, L, In, H, seed):
