@@ -3,6 +3,7 @@
 //   view_stats + channel_modulate : DGAdaStatChannel / DGAdaMeanChannel (stats over the 36 views per channel)
 //   adain_rows                    : adaptive_instance_normalization (stats over channels per view), one pass
 // All loads/stores are 128-bit and streaming (L1::no_allocate); grids are sized in multiples of the SM count.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256) gate_backward_kernel(const float* __restr
                                                             const float* __restrict__ f, int64_t ldf,
                                                             const float* __restrict__ s, int64_t lds,
                                                             const uint8_t* __restrict__ mask, float scale,
-                                                            float* __restrict__ dg, int64_t lddg, int R, int C, int vec) {
+                                                            float* __restrict__ dg, int64_t lddg, int R, int C, int vec,
+                                                            __half* __restrict__ dg16, float scale16) {
   if (vec) {
     const int c4 = C >> 2;
     const int64_t total = (int64_t)R * c4;
@@ -64,6 +66,12 @@ __global__ void __launch_bounds__(256) gate_backward_kernel(const float* __restr
         o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
       }
       stg_stream4(dg + (int64_t)r * lddg + c, o);
+      if (dg16 != nullptr) {                  // scaled, saturating fp16 copy: the dY operand of dW = dg^T d on kind::f16
+        uint2 h;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y * scale16), "f"(o.x * scale16));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w * scale16), "f"(o.z * scale16));
+        *reinterpret_cast<uint2*>(dg16 + (int64_t)r * C + c) = h;
+      }
     }
   } else {
     const int64_t total = (int64_t)R * C;
@@ -264,7 +272,19 @@ extern "C" int dasa_gate_backward(const float* dout, int64_t lddo, const float* 
   const bool vec = (C % 4 == 0) && vec_ok(dout, lddo) && vec_ok(f, ldf) && vec_ok(s, lds) && vec_ok(dg, lddg) &&
                    (drop_mask == nullptr || (reinterpret_cast<uintptr_t>(drop_mask) % 4 == 0));
   gate_backward_kernel<<<stream_grid((int64_t)R * C / (vec ? 4 : 1), 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      dout, lddo, f, ldf, s, lds, drop_mask, drop_scale, dg, lddg, R, C, vec ? 1 : 0);
+      dout, lddo, f, ldf, s, lds, drop_mask, drop_scale, dg, lddg, R, C, vec ? 1 : 0, nullptr, 1.f);
+  return dasa_check_launch("gate_backward_kernel");
+}
+
+extern "C" int dasa_gate_backward_h(const float* dout, int64_t lddo, const float* f, int64_t ldf, const float* s, int64_t lds,
+                                    const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, dasa_half_t* dg16,
+                                    float scale16, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return DASA_OK;
+  const bool vec = (C % 4 == 0) && vec_ok(dout, lddo) && vec_ok(f, ldf) && vec_ok(s, lds) && vec_ok(dg, lddg) &&
+                   (drop_mask == nullptr || (reinterpret_cast<uintptr_t>(drop_mask) % 4 == 0));
+  if (dg16 != nullptr && (!vec || (reinterpret_cast<uintptr_t>(dg16) & 7))) return DASA_ERR_BAD_ALIGN;
+  gate_backward_kernel<<<stream_grid((int64_t)R * C / (vec ? 4 : 1), 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      dout, lddo, f, ldf, s, lds, drop_mask, drop_scale, dg, lddg, R, C, vec ? 1 : 0, reinterpret_cast<__half*>(dg16), scale16);
   return dasa_check_launch("gate_backward_kernel");
 }
 

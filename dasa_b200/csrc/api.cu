@@ -60,7 +60,11 @@ extern "C" int dasa_gemm_f16_supported(int M, int N, int K) { return dasa_gemm_f
 extern "C" int dasa_gemm_f16(int M, int N, int K, const dasa_half_t* A, int64_t lda, const dasa_half_t* B, int64_t ldb, void* C,
                              int64_t ldc, int c_half, int epilogue, const dasa_epilogue_t* epi, void* stream) {
   if (A == nullptr || B == nullptr || C == nullptr) return DASA_ERR_BAD_SHAPE;
-  if (epi != nullptr && (epi->drop_mask != nullptr || epi->gate_src != nullptr)) return DASA_ERR_UNSUPPORTED;
+  if (epilogue == DASA_EPI_GATE) {
+    if (epi == nullptr || epi->gate_src == nullptr || c_half) return DASA_ERR_BAD_SHAPE;
+  } else if (epi != nullptr && (epi->drop_mask != nullptr || epi->gate_src != nullptr)) {
+    return DASA_ERR_UNSUPPORTED;
+  }
   const EpiParams ep = make_epi(epi);
   return dasa_gemm_tc_pair_f16(M, N, K, A, lda, B, ldb, C, ldc, c_half, epilogue, ep, (cudaStream_t)stream);
 }

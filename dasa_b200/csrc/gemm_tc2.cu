@@ -734,6 +734,7 @@ int dasa_gemm_tc_pair_f16(int M, int N, int K, const void* A, int64_t lda, const
     case DASA_EPI_NONE: return launch_pair_e<256, 5, DASA_EPI_NONE, false, false, true>(ta, tb, p, st);
     case DASA_EPI_BIAS: return launch_pair_e<256, 5, DASA_EPI_BIAS, false, false, true>(ta, tb, p, st);
     case DASA_EPI_BIAS_GELU: return launch_pair_e<256, 4, DASA_EPI_BIAS_GELU, false, false, true, 16>(ta, tb, p, st);
+    case DASA_EPI_GATE: return c_half ? DASA_ERR_UNSUPPORTED : launch_pair_e<256, 5, DASA_EPI_GATE, false, false, true>(ta, tb, p, st);
     default: return DASA_ERR_UNSUPPORTED;
   }
 }

@@ -287,6 +287,27 @@ __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict
     out[i] = __float2half_rn(in[i]);
 }
 
+// the same over the leading C columns of R strided rows (C % 8 == 0): out[r, c] = fp16(in[r * ld_in + c])
+__global__ void __launch_bounds__(256) f32_to_f16_rows_kernel(const float* __restrict__ in, int64_t ld_in, __half* __restrict__ out,
+                                                              int64_t ld_out, int R, int C) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)R * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c8), c = (int)(i % c8) << 3;
+    const float4 a = ldg_stream4(in + (int64_t)r * ld_in + c), b = ldg_stream4(in + (int64_t)r * ld_in + c + 4);
+    __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(out + (int64_t)r * ld_out + c) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+extern "C" int dasa_f32_to_f16_rows(const float* in, int64_t ld_in, dasa_half_t* out, int64_t ld_out, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return DASA_OK;
+  if ((C & 7) || (ld_in & 3) || (ld_out & 7)) return DASA_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return DASA_ERR_BAD_ALIGN;
+  f32_to_f16_rows_kernel<<<ew_grid((int64_t)R * (C >> 3)), 256, 0, (cudaStream_t)stream>>>(in, ld_in, reinterpret_cast<__half*>(out), ld_out, R, C);
+  return dasa_check_launch("f32_to_f16_rows_kernel");
+}
+
 extern "C" int dasa_f32_to_f16(const float* in, dasa_half_t* out, int64_t n, void* stream) {
   if (n <= 0) return DASA_OK;
   if (n >= 8 && (!dasa_aligned16(in) || !dasa_aligned16(out))) return DASA_ERR_BAD_ALIGN;

@@ -180,8 +180,16 @@ class AdaINGateFn(torch.autograd.Function):
         d2, _, _, ldd = ops._rows(d)
         o2, _, _, ldo = ops._rows_out(out)
         s = torch.empty(R, C, device=f.device, dtype=torch.float32)
-        ops.gemm(d2, ldd, 1, weight, C, 1, o2, ldo, R, C, C, epilogue=EPI_GATE, bias=bias, gate_src=f2, ld_gate=ldf,
-                 gate_out=s, ld_gate_out=C, drop_mask=mask, drop_scale=scale)
+        d16 = None
+        if ops.half_gate and C % 8 == 0 and ops.gemm_f16_supported(R, C, C):
+            # depth features are O(1..10): their fp16 copy keeps the 11 significant bits the TF32 kernel would use; the GEMM runs
+            # at the fp16 tensor rate and the copy is the X operand of the weight gradient as well
+            d16 = ops.to_half_rows(d2, ldd, R, C)
+            ops.linear_f16_gate(d16, ops.half_weight(weight), bias, o2, ldo, f2, ldf, s, mask, scale)
+        else:
+            ops.gemm(d2, ldd, 1, weight, C, 1, o2, ldo, R, C, C, epilogue=EPI_GATE, bias=bias, gate_src=f2, ld_gate=ldf,
+                     gate_out=s, ld_gate_out=C, drop_mask=mask, drop_scale=scale)
+        ctx.d16 = d16
         if F_all > C:
             ops.axpy2d(1.0, f2[:, C:], o2[:, C:], accumulate=False)
         ctx.C, ctx.scale = C, scale
@@ -198,9 +206,16 @@ class AdaINGateFn(torch.autograd.Function):
         d2, _, _, ldd = ops._rows(d)
         g2, _, _, ldg = ops._rows(dout)
         dg = torch.empty(R, C, device=f.device, dtype=torch.float32)
-        ops.call("dasa_gate_backward", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
-                 None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, R, C, ops._stream())
-        _wgrad(weight, dg, d2[:, :C], bias)        # dW[C,C] += dg^T d ; db += colsum(dg)
+        if ctx.d16 is not None and R >= 64:
+            dg16 = torch.empty(R, C, device=f.device, dtype=torch.float16)
+            ops.call("dasa_gate_backward_h", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
+                     None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, dg16.data_ptr(), 256.0, R, C,
+                     ops._stream())
+            _wgrad16(weight, dg16, ctx.d16, 1.0 / 256.0, dg, bias)      # dW[C,C] += 2^-8 dg16^T d16 ; db += colsum(dg)
+        else:
+            ops.call("dasa_gate_backward", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
+                     None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, R, C, ops._stream())
+            _wgrad(weight, dg, d2[:, :C], bias)        # dW[C,C] += dg^T d ; db += colsum(dg)
         return None, None, None, None, None, None, None
 
 

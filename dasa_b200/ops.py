@@ -171,6 +171,25 @@ def to_half(x):
     return out
 
 
+def to_half_rows(x2, ld, R, C):
+    """fp16 copy [R, C] of the leading C columns of R rows with row stride ld (dasa_f32_to_f16_rows)."""
+    out = torch.empty(R, C, device=x2.device, dtype=torch.float16)
+    call("dasa_f32_to_f16_rows", _p(x2), ld, _p(out), C, R, C, _stream())
+    return out
+
+
+half_gate = True        # AdaIN gate GEMM (and its weight gradient) on fp16 operands in the tensor-core precision mode
+
+
+def linear_f16_gate(d16, w16, bias, out2, ldo, f2, ldf, gate_out, mask, scale):
+    """out2[r, :N] = sigmoid(d16 w16^T + bias) * f2[r, :N] (* mask * scale) on the fp16-operand kernel, fp32 in-place rows."""
+    M, K = d16.shape
+    N = w16.shape[0]
+    e = Epilogue(_p(bias), _p(f2), ldf, _p(gate_out), gate_out.stride(0) if gate_out is not None else 0, _p(mask), float(scale))
+    call("dasa_gemm_f16", M, N, K, _p(d16), d16.stride(0), _p(w16), w16.stride(0), _p(out2), ldo, 0, EPI_GATE, ctypes.byref(e),
+         _stream())
+
+
 _half_cache = {}
 
 

@@ -98,7 +98,9 @@ int dasa_debug_gemm_route_counts(int64_t* out, int n, int reset);
 
 /* C[M, N] = epilogue(A[M, K] B[N, K]^T (+ bias)) with IEEE fp16 operands (both K-major, leading dimensions in elements, multiples of
  * 8) on the persistent CTA-pair tcgen05 kernel with kind::f16 (twice the TF32 rate), fp32 accumulation. c_half = 0: C is float
- * [M, ldc]; 1: C is fp16 [M, ldc] (N % 4 == 0) - the activation of the next fp16 GEMM. epilogue: DASA_EPI_NONE / _BIAS / _BIAS_GELU.
+ * [M, ldc]; 1: C is fp16 [M, ldc] (N % 4 == 0) - the activation of the next fp16 GEMM. epilogue: DASA_EPI_NONE / _BIAS / _BIAS_GELU,
+ * or DASA_EPI_GATE with fp32 output (the DGAdaChannel gate over an fp16 copy of the depth features; gate operand, saved gate and
+ * keep mask as in dasa_gemm).
  * Used for the forward-only GEMMs of the frozen transformer stack (vilmodel.py:1370-1410: 9 language + 3 cross-modal layers,
  * detached in the train configuration): fp16 keeps TF32's 10 mantissa bits, so inside fp16's normal range the products are the
  * TF32 kernel's. dasa_gemm_f16_supported: 1 when the shape has enough 256 x 256 tiles for this kernel (else use dasa_gemm).     */
@@ -134,6 +136,11 @@ int dasa_gate_modulate(const float* g, int64_t ldg, const float* f, int64_t ldf,
 /* backward of the gate: dg[r,c] = dout[r,c] * mask*scale * f[r,c] * s(1-s), s = saved sigmoid (Appendix A, K1) */
 int dasa_gate_backward(const float* dout, int64_t lddo, const float* f, int64_t ldf, const float* s, int64_t lds,
                        const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, int R, int C, void* stream);
+/* the same, also writing dg16[r, c] = fp16(dg[r, c] * scale16) (saturating; [R, C] contiguous, C % 4 == 0): the dY operand of
+ * the gate's weight gradient on dasa_gemm_f16_mn.                                                                       */
+int dasa_gate_backward_h(const float* dout, int64_t lddo, const float* f, int64_t ldf, const float* s, int64_t lds,
+                         const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, dasa_half_t* dg16, float scale16,
+                         int R, int C, void* stream);
 
 /* a2: per-channel statistics over the views of one panorama (agent_dg.py:1651-1656):
  *     stats[n, 0:C]=mean, [C:2C]=unbiased std, [2C:3C]=max, [3C:4C]=min of d[n, :, c] over V views.            */
@@ -324,6 +331,9 @@ int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* args, void* workspace
  * dasa_decoder_rollout_supported() says whether the shared-memory plan fits (else use the per-op entry points).      */
 /* out[i] = fp16(in[i]) (round to nearest even), n elements; in 16-byte aligned when n >= 8. Used for the decoder kernel's weights. */
 int dasa_f32_to_f16(const float* in, dasa_half_t* out, int64_t n, void* stream);
+/* out[r, c] = fp16(in[r * ld_in + c]) for c < C (C % 8 == 0, ld_in % 4 == 0, ld_out % 8 == 0): a column slice of strided rows
+ * (the RGB part of the depth features, the K-major A operand of the AdaIN gate GEMM on dasa_gemm_f16).                    */
+int dasa_f32_to_f16_rows(const float* in, int64_t ld_in, dasa_half_t* out, int64_t ld_out, int R, int C, void* stream);
 typedef struct {
   int T, B, H, E, F, V, L, D, headings, shift_k, NK;
   const float* emb;                                   /* [T, B, E] drop(tanh(embedding(action)))  (model.py:504-505)        */

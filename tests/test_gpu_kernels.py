@@ -876,6 +876,46 @@ def test_gemm_f16_mn_major_weight_gradient(rows, N, K):
     assert torch.equal(dw3, dw2)
 
 
+def test_adain_gate_on_fp16_operands_matches_tf32_path():
+    """AdaINGateFn in the tensor-core mode: the gate GEMM over an fp16 copy of the depth features (dasa_gemm_f16, GATE epilogue) and
+    its weight gradient over the scaled fp16 gradient copy (dasa_gate_backward_h + dasa_gemm_f16_mn) against the TF32 operand path
+    and against fp64: output, saved gate, dW, db. Depth features O(1..10) stay inside fp16's range, so both carry 11-bit operands."""
+    from dasa_b200 import functions as Fn
+    from dasa_b200 import ops
+    R, C, F_all = 36 * 128, 2048, 2176
+    g = torch.Generator().manual_seed(11)
+    f = torch.randn(R, F_all, generator=g).abs().to(DEV)
+    d = (torch.randn(R, F_all, generator=g).abs() * 2.0).to(DEV)
+    w0 = (torch.randn(C, C, generator=g) * C ** -0.5)
+    b0 = torch.randn(C, generator=g) * 0.1
+    gout = (torch.randn(R, F_all, generator=g) * 0.01).to(DEV)
+    mask = (torch.rand(R, C, generator=g) > 0.3).to(torch.uint8).to(DEV)
+    res = []
+    ops.set_precision("tf32")
+    try:
+        for half in (False, True):
+            ops.half_gate = half
+            w = w0.clone().to(DEV).requires_grad_(True)
+            b = b0.clone().to(DEV).requires_grad_(True)
+            out = Fn.AdaINGateFn.apply(f, d, w, b, mask, 1.0 / 0.7, C)
+            (out * gout).sum().backward()
+            torch.cuda.synchronize()
+            res.append((out, w.grad.clone(), b.grad.clone()))
+    finally:
+        ops.half_gate = True
+        ops.set_precision("fp32")
+    # fp64 reference
+    wd, bd = w0.double().to(DEV).requires_grad_(True), b0.double().to(DEV).requires_grad_(True)
+    gate = torch.sigmoid(d[:, :C].double() @ wd.t() + bd)
+    ref = torch.cat([gate * f[:, :C].double() * mask.double() / 0.7, f[:, C:].double()], 1)
+    (ref * gout.double()).sum().backward()
+    for name, (out, dw, db) in zip(("tf32", "fp16"), res):
+        assert rel_err(out.double(), ref) <= 3e-3, (name, rel_err(out.double(), ref))
+        assert rel_err(dw.double(), wd.grad) <= 3e-3, (name, rel_err(dw.double(), wd.grad))
+        assert rel_err(db.double(), bd.grad) <= 3e-3, (name, rel_err(db.double(), bd.grad))
+    assert rel_err(res[1][0], res[0][0]) <= 2e-3 and rel_err(res[1][1], res[0][1]) <= 2e-3
+
+
 # ------------------------------------------------------------------------------ padding-free bi-LSTM (bilstm_packed.cu)
 @pytest.mark.parametrize("R,L,In,H,seed", [(70, 12, 64, 64, 0), (300, 21, 96, 128, 1), (45, 9, 64, 32, 2)])
 def test_packed_bilstm_matches_padded_path(R, L, In, H, seed):
