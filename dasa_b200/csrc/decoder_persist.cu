@@ -399,23 +399,29 @@ __device__ __forceinline__ void dp_issue_tile(float* tile, int pitch, uint64_t* 
   }
 }
 
-// partial row dots of the resident slice against vec (shared memory): zp[r] = tile[r, :cn] . vec ; masked rows -> 0
+// partial row dots of the resident slice against vec (shared memory): zp[r] = tile[r, :cn] . vec ; masked rows -> 0.
+// A warp works on 4 rows at once (8 lanes per row, 3 shuffle steps): with one row per warp iteration the 5-step shuffle chains of
+// the 10 rows a warp owns (80 tokens) ran back to back, ~1.5 us of pure latency per attention.
 __device__ __forceinline__ void dp_partial_dots(const float* tile, int pitch, const float* vec, int rows, int cn,
                                                 const uint8_t* mask_b, float* zp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rq = lane >> 3, cl = lane & 7;
   const int n4 = cn >> 2;
-  for (int r = wid; r < rows; r += DP_WARPS) {
+  const float4* v4 = reinterpret_cast<const float4*>(vec);
+  for (int r0 = wid * 4; r0 < rows; r0 += DP_WARPS * 4) {
+    const int r = r0 + rq;
     float acc = 0.f;
-    if (mask_b == nullptr || mask_b[r] == 0) {
+    if (r < rows && (mask_b == nullptr || mask_b[r] == 0)) {
       const float4* row = reinterpret_cast<const float4*>(tile + (size_t)r * pitch);
-      const float4* v4 = reinterpret_cast<const float4*>(vec);
-      for (int j = lane; j < n4; j += 32) {
+      for (int j = cl; j < n4; j += 8) {
         const float4 a = row[j], b = v4[j];
         acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
       }
-      acc = warp_sum(acc);
     }
-    if (lane == 0) zp[r] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (cl == 0 && r < rows) zp[r] = acc;
   }
 }
 
@@ -462,15 +468,26 @@ __device__ __forceinline__ void dp_weighted_sum(const AttnSmem& s, int pitch, in
   }
 }
 
+// Sum of the S (<= 8) slice partials of row r in slice order (deterministic). All S loads are issued before the first add: written
+// as `v += ld_cg(..)` in a loop over the run-time S the compiler serialised them - 7 dependent L2 round trips (~5 us) per row, which
+// was most of the softmax phases and 10 of the 16 us of B2b.
+__device__ __forceinline__ float dp_sum_partials(const float* zp, int S, int r) {
+  float t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t[k] = (k < S) ? ld_cg(zp + (size_t)k * DP_MAXROWS + r) : 0.f;
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < S) v += t[k];
+  return v;
+}
+
 // z[r] = sum over the S slice partials (fixed order; one row per thread), then warp 0: masked softmax -> s.prow (0 for masked
 // rows). Ends with the softmax visible to warp 0 only: callers __syncthreads() before other warps read s.prow.
 __device__ __forceinline__ void dp_softmax_rows(const AttnSmem& s, const float* zpart_b, int S, int rows, const uint8_t* mask_b) {
   for (int r = threadIdx.x; r < DP_MAXROWS; r += DP_THREADS) {
     float v = -INFINITY;
-    if (r < rows && (mask_b == nullptr || mask_b[r] == 0)) {
-      v = 0.f;
-      for (int k = 0; k < S; ++k) v += ld_cg(zpart_b + (size_t)k * DP_MAXROWS + r);
-    }
+    if (r < rows && (mask_b == nullptr || mask_b[r] == 0)) v = dp_sum_partials(zpart_b, S, r);
     s.zrow[r] = v;
   }
   __syncthreads();
@@ -1004,20 +1021,17 @@ __device__ __noinline__ void bwd_b5b(const dasa_decoder_bwd_t& a, const SmemPlan
   const int tid = threadIdx.x, L = a.L, D = a.D;
   const int64_t tb = (int64_t)t * a.B;
   const float* zp = a.zpart + (size_t)o.b * S * DP_MAXROWS;
+  for (int r = tid; r < L; r += DP_THREADS) {               // one row per thread: partial sums + saved alpha in one round trip
+    const bool ok = o.mask_b == nullptr || o.mask_b[r] == 0;
+    sc.zrow[r] = ok ? dp_sum_partials(zp, S, r) : 0.f;
+    sc.prow[r] = ok ? __ldg(a.alpha + (tb + o.b) * L + r) : 0.f;
+  }
+  __syncthreads();
   if (tid < 32) {
     const int lane = tid;
     float pd = 0.f;
-    for (int r = lane; r < L; r += 32) {
-      const bool ok = o.mask_b == nullptr || o.mask_b[r] == 0;
-      float v = 0.f;
-      if (ok) for (int k = 0; k < S; ++k) v += ld_cg(zp + (size_t)k * DP_MAXROWS + r);
-      const float al = ok ? __ldg(a.alpha + (tb + o.b) * L + r) : 0.f;
-      sc.zrow[r] = v;
-      sc.prow[r] = al;
-      pd = fmaf(al, v, pd);
-    }
+    for (int r = lane; r < L; r += 32) pd = fmaf(sc.prow[r], sc.zrow[r], pd);
     pd = warp_sum(pd);
-    __syncwarp();
     for (int r = lane; r < L; r += 32) sc.aux[r] = sc.prow[r] * (sc.zrow[r] - pd);
   }
   __syncthreads();
@@ -1064,19 +1078,17 @@ __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan
   const float* zp = a.zpart + (size_t)o.b * S * DP_MAXROWS;
   float* dtk_b = a.dtk + (tb + o.b) * NK;
   __half* dtk16_b = bwd_x16(a).dtk + (tb + o.b) * NK;
+  for (int r = tid; r < V; r += DP_THREADS) {               // one row per thread: partial sums + saved p, q in one round trip
+    sf.zrow[r] = dp_sum_partials(zp, S, r);
+    sf.prow[r] = __ldg(a.p + (tb + o.b) * V + r);
+    sf.wrow[r] = __ldg(a.q + (tb + o.b) * V + r);
+  }
+  if (tid >= DP_THREADS - 32 && (tid & 31) < a.shift_k) sf.kap[tid & 31] = __ldg(a.kappa + (tb + o.b) * a.shift_k + (tid & 31));
+  __syncthreads();
   if (tid < 32) {
     const int lane = tid, k = a.shift_k, half = k / 2, Hn = a.headings;
     float* dq = sf.zrow;
     float* dp = sf.aux2;
-    for (int r = lane; r < V; r += 32) {
-      float v = 0.f;
-      for (int kk = 0; kk < S; ++kk) v += ld_cg(zp + (size_t)kk * DP_MAXROWS + r);
-      dq[r] = v;
-      sf.prow[r] = __ldg(a.p + (tb + o.b) * V + r);
-      sf.wrow[r] = __ldg(a.q + (tb + o.b) * V + r);
-    }
-    if (lane < k) sf.kap[lane] = __ldg(a.kappa + (tb + o.b) * k + lane);
-    __syncwarp();
     for (int r = lane; r < V; r += 32) {
       const int e = r / Hn, m = r % Hn;
       float v = 0.f;
