@@ -797,7 +797,9 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
     """Event-time every GEMM launch and the two decoder-rollout launches of one training rollout (eager launches, warm caches).
     Dominant kernel of the step by device time (profiles/r02_ncu_launches_step_*_summary.txt): the persistent CTA-pair tcgen05 GEMM
     gemm_tf32_pair_kernel<256,*> (gemm_tc2.cu) - its kind::f16 instantiations run the 78 forward GEMMs of the frozen transformer
-    stack, its kind::tf32 instantiations the trainable token-major GEMMs (AdaIN gate, bi-LSTM projections / recurrence, weight
+    stack and, on fp16 operand copies, the AdaIN gate, the bi-LSTM input projections and the MN-major weight gradients of both
+    (dasa_gemm_f16 / dasa_gemm_f16_mn; the bi-LSTM's recurrent GEMMs run inside dasa_bilstm_packed_fwd / _bwd and are not timed
+    one by one); its kind::tf32 instantiations keep the remaining token-major GEMMs (vision projection, decoder weight
     gradients). Tensor roofline per family = algorithmic FLOPs (2*M*N*K per launch) / summed launch duration against the
     measured sustained cuBLAS bf16 rate (fp16 operands) or half of it (tf32). The decoder's M = 20-row projections live inside
     the persistent rollout kernels and are reported as a weight-stream (HBM / L2) figure."""
@@ -806,7 +808,7 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
     orig = lib.call
 
     def hooked(name, *a):
-        if name not in ("dasa_gemm", "dasa_gemm_f16", "dasa_decoder_rollout_fwd", "dasa_decoder_rollout_bwd"):
+        if name not in ("dasa_gemm", "dasa_gemm_f16", "dasa_gemm_f16_mn", "dasa_decoder_rollout_fwd", "dasa_decoder_rollout_bwd"):
             return orig(name, *a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -814,7 +816,7 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
         e1.record()
         if name == "dasa_gemm":
             events.append((e0, e1, int(a[2]), int(a[3]), int(a[4]), "tf32"))
-        elif name == "dasa_gemm_f16":
+        elif name in ("dasa_gemm_f16", "dasa_gemm_f16_mn"):
             events.append((e0, e1, int(a[0]), int(a[1]), int(a[2]), "f16"))
         else:
             dec.append((e0, e1, name))
@@ -844,8 +846,9 @@ def dominant_kernel_roofline(pol, ep, src, peaks, peak_src):
         ach = flops / max(secs, 1e-12) / 1e12
         return {"bound": "tensor", "what": what, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "launches_timed": len(rows), "device_seconds": secs}
-    fam16 = fam(f16, peak16, "kind::f16 instantiations: forward GEMMs of the frozen language / cross-modal stack (fp16 operands, fp32 accumulate)")
-    fam32 = fam(big, peak16 / 2.0, "kind::tf32 instantiations, token-major GEMMs with M >= 2048 (AdaIN gate, bi-LSTM, weight gradients)")
+    fam16 = fam(f16, peak16, "kind::f16 instantiations (fp16 operands, fp32 accumulate): forward GEMMs of the frozen language / cross-modal stack, AdaIN gate, "
+                "bi-LSTM input projections, MN-major weight gradients of the bi-LSTM and the gate")
+    fam32 = fam(big, peak16 / 2.0, "kind::tf32 instantiations, token-major GEMMs with M >= 2048 (vision projection, decoder weight gradients)")
     s_secs = sum(t for t, _, _, _, _ in small)
     s_bytes = sum(4.0 * (n * k + m * k + m * n) for _, m, n, k, _ in small)
     # decoder rollout kernels: per action the fp16 weight stream [linear_in ; linear_shift], [W_ih | W_hh], att.linear_in,
