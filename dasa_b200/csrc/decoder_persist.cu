@@ -335,17 +335,24 @@ __device__ __forceinline__ void dp_gemm_block_h(const wt_t* (&wrow)[2 * RT], con
       for (int e = 0; e < 4; ++e) acc[h][i][e] = 0.f;
 
   const int nchunks = K / DP_CHUNK;
+  // Every CTA reads the WHOLE X operand; started at chunk 0 everywhere, all 148 CTAs asked the same few L2 lines for the same
+  // chunk at the same moment. Each CTA walks the reduction index from its own rotation instead (any bijection of k is the same
+  // sum up to fp32 ordering, and the order is a fixed function of the CTA index: deterministic). Staging X through shared memory
+  // with bulk copies (2 x 512-k pieces in flight, all that fits next to the attention tiles) was tried and is slower: 10 -> 17 us
+  // for P3, the copies' latency is exposed once per piece.
+  const int rot = (int)((blockIdx.x * 11u) % (unsigned)nchunks);
+  auto kc_of = [&](int ci) { int q = ci + rot; q = q >= nchunks ? q - nchunks : q; return q * DP_CHUNK; };
   GemmFragH<MT, RT> f[NST];
   int c = warp;
 #pragma unroll
   for (int s = 0; s < NST - 1; ++s)
-    if (c + s * DP_WARPS < nchunks) dp_load_h<MT, RT>(f[s], wrow, xrow, xok, (c + s * DP_WARPS) * DP_CHUNK, half_last);
+    if (c + s * DP_WARPS < nchunks) dp_load_h<MT, RT>(f[s], wrow, xrow, xok, kc_of(c + s * DP_WARPS), half_last);
 #pragma unroll 1
   for (; c < nchunks; c += NST * DP_WARPS) {
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
       const int cl = c + (s + NST - 1) * DP_WARPS;
-      if (cl < nchunks) dp_load_h<MT, RT>(f[(s + NST - 1) % NST], wrow, xrow, xok, cl * DP_CHUNK, half_last);
+      if (cl < nchunks) dp_load_h<MT, RT>(f[(s + NST - 1) % NST], wrow, xrow, xok, kc_of(cl), half_last);
       if (c + s * DP_WARPS < nchunks) dp_compute_h<MT, RT>(acc, f[s], half_last);
     }
   }

@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 
 // NKB = 16-key blocks the launch can hold (max_Lk <= 16 * NKB)
 template <int NKB>
-__global__ void __launch_bounds__(H16_THREADS, 6) mha_fwd_h16_kernel(MhaH16Args a) {
+__global__ void __launch_bounds__(H16_THREADS, 8) mha_fwd_h16_kernel(MhaH16Args a) {
   extern __shared__ __align__(16) __half smem_h[];
   const int LqM = (a.Lq + 15) & ~15, LkM = (a.Lk + 15) & ~15;
   const int stage_halves = (LqM + 2 * LkM) * H16_STRIDE;
@@ -310,7 +310,7 @@ extern "C" int dasa_mha_fwd_h16(const dasa_half_t* q, int64_t ldq, int64_t sq, c
   const int LqM = (max_Lq + 15) & ~15, LkM = (max_Lk + 15) & ~15;
   const size_t stage_bytes = (size_t)(LqM + 2 * LkM) * H16_STRIDE * sizeof(__half);
   if (stage_bytes > 227 * 1024) return DASA_ERR_BAD_SHAPE;
-  const int stages = (6 * (2 * stage_bytes + 1024) <= 227 * 1024) ? 2 : 1;
+  const int stages = (8 * (2 * stage_bytes + 1024) <= 227 * 1024) ? 2 : 1;
   const size_t smem = stages * stage_bytes;
   const bool use_stream = drop_mask == nullptr && drop_p > 0.f;
   MhaH16Args a{reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(k), reinterpret_cast<const __half*>(v),
