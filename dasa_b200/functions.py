@@ -73,6 +73,17 @@ def _wgrad16(weight, dy16, x16, alpha, dy, bias=None, bias2=None):
 
 _queue16 = []
 
+# Called (once, then cleared by the caller) when the backward pass reaches the encoder's packed bi-LSTM: in the batched
+# teacher-forced rollout every decoder / critic node was created after the encoder, so autograd has finished all of them by then.
+# trainer.RolloutTrainer uses it to flush + all-reduce the decoder group under the bi-LSTM's latency-bound backward chain.
+pre_encoder_backward = None
+
+
+def pending_weight_grads(owner):
+    """Number of queued weight-gradient reductions whose target lives inside the flat buffer `owner`."""
+    n = sum(1 for (weight, _, _, _, _) in _queue.values() if _inside(weight.grad, owner))
+    return n + sum(1 for ent in _queue16 if _inside(ent[0].grad, owner))
+
 
 def _inside(t, owner):
     """True when tensor t lives inside the flat buffer `owner`."""
@@ -612,6 +623,10 @@ class PackedBiLSTMFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, dh_fin, dc_fin):
         (xc, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, hprev, cs, acts) = ctx.saved_tensors
+        global pre_encoder_backward
+        if pre_encoder_backward is not None:
+            hook, pre_encoder_backward = pre_encoder_backward, None
+            hook()
         plan = ctx.plan
         R, L, N = plan.R, plan.L, plan.N
         H = w_hh_f.shape[1]

@@ -42,6 +42,7 @@ class RolloutTrainer:
         self.gamma, self.ent_coef, self.normalize = gamma, ent_coef, normalize
         self.graph, self.graph_loss, self.graph_launches = None, None, 0
         self._works = []
+        self._early = set()             # names of the optimizer groups already flushed + reduced during the backward pass
         if policy._flat is None:
             policy.flatten_parameters()
 
@@ -72,13 +73,28 @@ class RolloutTrainer:
         else:
             dist.all_reduce(g["flat_g"], op=dist.ReduceOp.SUM)
 
+    def _early_reduce(self):
+        """Hook at the start of the encoder's bi-LSTM backward (batched teacher-forced rollout, last backward pass of the step):
+        every decoder / critic node has run, so those groups' weight-gradient GEMMs are flushed and their all-reduce (120 of the
+        232 MB) starts now, under the bi-LSTM's latency-bound recurrence instead of after it."""
+        for g in sorted(self.pol._flat, key=lambda g: -g["flat_g"].numel()):
+            if g["name"] in ("decoder", "critic"):
+                Fn.flush_weight_grads(owner=g["flat_g"])
+                self._reduce_group(g)
+                self._early.add(g["name"])
+
     def _flush_and_reduce(self):
         """Deferred weight-gradient GEMMs group by group (largest flat buffer first), each group's all-reduce started as soon as
         its gradients are complete."""
         groups = sorted(self.pol._flat, key=lambda g: -g["flat_g"].numel())
         for g in groups:
+            if g["name"] in self._early:
+                if Fn.pending_weight_grads(g["flat_g"]):
+                    raise RuntimeError("a %s gradient arrived after the group's early all-reduce had started" % g["name"])
+                continue
             Fn.flush_weight_grads(owner=g["flat_g"])
             self._reduce_group(g)
+        self._early = set()
         Fn.flush_weight_grads()                               # anything outside the flat buffers (none in practice)
 
     def _wait_reductions(self):
@@ -96,7 +112,7 @@ class RolloutTrainer:
         self.src.advance()
         losses = []
         with M.use_dropout_source(self.src):
-            for w in self.ml_weights:
+            for wi, w in enumerate(self.ml_weights):
                 loss, _, _ = pol.teacher_rollout(ep, T, w / world, tag_steps=False)
                 if self.feedback == "sample":
                     # The IL rollout is back-propagated as soon as it ends: same accumulated gradients as summing the two
@@ -115,7 +131,13 @@ class RolloutTrainer:
                     rl.backward()
                     losses.append(rl.detach())
                 else:
-                    loss.backward()
+                    last = wi == len(self.ml_weights) - 1
+                    if world > 1 and self.overlap and last and getattr(pol, "schedule", None) == "batched":
+                        Fn.pre_encoder_backward = self._early_reduce
+                    try:
+                        loss.backward()
+                    finally:
+                        Fn.pre_encoder_backward = None
                     losses.append(loss.detach())
         total = losses[0].reshape(1)
         for x in losses[1:]:
