@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) gate_backward_kernel(const float* __restr
         const float4 m = mask4(mask + (int64_t)r * C + c, scale);
         o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
       }
-      stg_stream4(dg + (int64_t)r * lddg + c, o);
+      if (dg != nullptr) stg_stream4(dg + (int64_t)r * lddg + c, o);
       if (dg16 != nullptr) {                  // scaled, saturating fp16 copy: the dY operand of dW = dg^T d on kind::f16
         uint2 h;
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y * scale16), "f"(o.x * scale16));
@@ -280,9 +280,10 @@ extern "C" int dasa_gate_backward_h(const float* dout, int64_t lddo, const float
                                     const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, dasa_half_t* dg16,
                                     float scale16, int R, int C, void* stream) {
   if (R <= 0 || C <= 0) return DASA_OK;
-  const bool vec = (C % 4 == 0) && vec_ok(dout, lddo) && vec_ok(f, ldf) && vec_ok(s, lds) && vec_ok(dg, lddg) &&
+  const bool vec = (C % 4 == 0) && vec_ok(dout, lddo) && vec_ok(f, ldf) && vec_ok(s, lds) && (dg == nullptr || vec_ok(dg, lddg)) &&
                    (drop_mask == nullptr || (reinterpret_cast<uintptr_t>(drop_mask) % 4 == 0));
   if (dg16 != nullptr && (!vec || (reinterpret_cast<uintptr_t>(dg16) & 7))) return DASA_ERR_BAD_ALIGN;
+  if (dg == nullptr && (dg16 == nullptr || !vec)) return DASA_ERR_BAD_SHAPE;
   gate_backward_kernel<<<stream_grid((int64_t)R * C / (vec ? 4 : 1), 256, 8), 256, 0, (cudaStream_t)stream>>>(
       dout, lddo, f, ldf, s, lds, drop_mask, drop_scale, dg, lddg, R, C, vec ? 1 : 0, reinterpret_cast<__half*>(dg16), scale16);
   return dasa_check_launch("gate_backward_kernel");

@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(256) bilstm_packed_pointwise_bwd_kernel(PkBwd 
       dO[e] = dh[e] * tc * og[e] * (1.f - og[e]);
       dcp[e] = dct * fg[e];
     }
-    float* dg = p.dgates[d] + (int64_t)r * 4 * H + j;
-    *reinterpret_cast<float4*>(dg) = make_float4(di[0], di[1], di[2], di[3]);
-    *reinterpret_cast<float4*>(dg + H) = make_float4(df[0], df[1], df[2], df[3]);
-    *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(dgg[0], dgg[1], dgg[2], dgg[3]);
-    *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+    if (p.dgates[d] != nullptr) {          // fp32 copy: only when somebody reads it (dX in the finetune configuration, TF32 path)
+      float* dg = p.dgates[d] + (int64_t)r * 4 * H + j;
+      *reinterpret_cast<float4*>(dg) = make_float4(di[0], di[1], di[2], di[3]);
+      *reinterpret_cast<float4*>(dg + H) = make_float4(df[0], df[1], df[2], df[3]);
+      *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(dgg[0], dgg[1], dgg[2], dgg[3]);
+      *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+    }
     if (p.dg16[d] != nullptr) {
       __half* dh16 = p.dg16[d] + (int64_t)r * 4 * H + j;
       const float s = PK_GSCALE;
@@ -340,6 +342,7 @@ extern "C" int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* a, void* w
   const bool f16 = a->w_hh_t16[0] != nullptr && a->w_hh_t16[1] != nullptr && a->dg16[0] != nullptr && a->dg16[1] != nullptr &&
                    (H % 64) == 0;
   const __half* Bw16[2] = {reinterpret_cast<const __half*>(a->w_hh_t16[0]), reinterpret_cast<const __half*>(a->w_hh_t16[1])};
+  if (!f16 && (a->dgates[0] == nullptr || a->dgates[1] == nullptr)) return DASA_ERR_BAD_SHAPE;   // the TF32 recurrence reads them
   int nparts = 0;
   for (int s = Le - 1; s >= 0; --s) {
     const int cur = (Le - 1 - s) & 1, prv = cur ^ 1;           // ping-pong halves of dc_work
@@ -353,7 +356,7 @@ extern "C" int dasa_bilstm_packed_bwd(const dasa_bilstm_packed_bwd_t* a, void* w
       p.dc_in[d] = a->dc_work[d] + prv * RH; p.dc_out[d] = a->dc_work[d] + cur * RH;
       p.acts[d] = a->acts[d] + off[pp] * 4 * H;
       p.c_prev[d] = a->cs[d] + s * RH; p.c_new[d] = a->cs[d] + (s + 1) * RH;
-      p.dgates[d] = a->dgates[d] + off[pp] * 4 * H;
+      p.dgates[d] = a->dgates[d] != nullptr ? a->dgates[d] + off[pp] * 4 * H : nullptr;
       p.dg16[d] = f16 ? reinterpret_cast<__half*>(a->dg16[d]) + off[pp] * 4 * H : nullptr;
       p.pos[d] = pp; p.n[d] = n[pp];
     }

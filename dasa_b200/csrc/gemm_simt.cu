@@ -1,6 +1,7 @@
 // FP32 (FFMA) GEMM with fused epilogues — the exact-fp32 precision mode of dasa_gemm, and the path every
 // projection takes when its operands do not satisfy the TMA alignment rules of the tcgen05 kernel (gemm_tc.cu).
 // Register-tiled, double-buffered through registers, split-K with a deterministic two-pass reduction.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #define DASA_GELU_EXACT 1
 #include "gemm_common.cuh"
@@ -151,14 +152,20 @@ constexpr int COLSUM_MAX_GROUPS = 1 << 12;
 __device__ float g_colsum_part[COLSUM_PART_FLOATS];
 __device__ unsigned int g_colsum_ticket[COLSUM_MAX_GROUPS];
 
-__global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out, int rows_per_slab) {
+__device__ __forceinline__ float colsum_ld(const float* p) { return *p; }
+__device__ __forceinline__ float colsum_ld(const __half* p) { return __half2float(*p); }
+
+// T = float, or __half with `scale` applied to the sums (the scaled fp16 gradient copies of the fp16-operand weight-gradient path:
+// half the bytes of this read-once, HBM-bound pass)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out, int rows_per_slab, float scale) {
   __shared__ float red[8][33];
   __shared__ bool last;
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int m0 = blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
   float s = 0.f;
   if (n < N)
-    for (int m = m0 + threadIdx.y; m < m1; m += 8) s += X[(int64_t)m * ldx + n];
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) s += colsum_ld(X + (int64_t)m * ldx + n);
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   float t = 0.f;
@@ -167,7 +174,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, i
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
   }
   if (gridDim.y == 1) {
-    if (threadIdx.y == 0 && n < N) out[n] += t;
+    if (threadIdx.y == 0 && n < N) out[n] += t * scale;
     return;
   }
   const int ngrp = gridDim.x * 32;
@@ -181,7 +188,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, i
   if (threadIdx.y == 0) {
     float v = 0.f;
     for (int z = 0; z < (int)gridDim.y; ++z) v += __ldcg(g_colsum_part + (size_t)z * ngrp + blockIdx.x * 32 + threadIdx.x);
-    if (n < N) out[n] += v;
+    if (n < N) out[n] += v * scale;
     if (threadIdx.x == 0) g_colsum_ticket[blockIdx.x] = 0;
   }
 }
@@ -270,9 +277,9 @@ int dasa_gemm_simt(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha,
   return rc;
 }
 
-extern "C" int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out, int accumulate, void* stream) {
+template <typename T>
+static int colsum_launch(const T* X, int64_t ldx, int M, int N, float scale, float* out, int accumulate, cudaStream_t st) {
   if (N <= 0) return DASA_OK;
-  cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) {
     zero_kernel<<<(unsigned)dasa_cdiv(N, 256), 256, 0, st>>>(out, N);
     if (dasa_check_launch("zero_kernel") != DASA_OK) return DASA_ERR_CUDA;
@@ -287,6 +294,81 @@ extern "C" int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out
   while (slabs > 1 && (int64_t)slabs * col_groups * 32 > COLSUM_PART_FLOATS) --slabs;
   const int rows_per_slab = (int)dasa_cdiv(M, slabs);
   dim3 grid((unsigned)col_groups, (unsigned)dasa_cdiv(M, rows_per_slab));
-  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(X, ldx, M, N, out, rows_per_slab);
+  colsum_kernel<T><<<grid, dim3(32, 8), 0, st>>>(X, ldx, M, N, out, rows_per_slab, scale);
   return dasa_check_launch("colsum_kernel");
+}
+
+extern "C" int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out, int accumulate, void* stream) {
+  return colsum_launch<float>(X, ldx, M, N, 1.f, out, accumulate, (cudaStream_t)stream);
+}
+
+// fp16 input, 8 columns (one 128-bit load) per thread: a warp row covers 256 columns. Same slab / ticket scheme as colsum_kernel
+// (bit-reproducible). N % 8 == 0, ldx % 8 == 0.
+__global__ void __launch_bounds__(256) colsum_h8_kernel(const __half* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out,
+                                                        int rows_per_slab, float scale) {
+  __shared__ float red[8][32 * 8 + 8];
+  __shared__ bool last;
+  const int n0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int m0 = blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (n0 < N)
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) {
+      uint4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(X + (int64_t)m * ldx + n0));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+      }
+    }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.y][threadIdx.x * 8 + e] = acc[e];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;            // 256 threads = the 256 columns of this group
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][tid];
+  const int n = blockIdx.x * 256 + tid;
+  if (gridDim.y == 1) {
+    if (n < N) out[n] += t * scale;
+    return;
+  }
+  const int ngrp = gridDim.x * 256;
+  g_colsum_part[(size_t)blockIdx.y * ngrp + blockIdx.x * 256 + tid] = t;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(&g_colsum_ticket[blockIdx.x], 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float v = 0.f;
+  for (int z = 0; z < (int)gridDim.y; ++z) v += __ldcg(g_colsum_part + (size_t)z * ngrp + blockIdx.x * 256 + tid);
+  if (n < N) out[n] += v * scale;
+  if (tid == 0) g_colsum_ticket[blockIdx.x] = 0;
+}
+
+extern "C" int dasa_colsum_h(const dasa_half_t* X, int64_t ldx, int M, int N, float scale, float* out, int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half* Xh = reinterpret_cast<const __half*>(X);
+  if ((N & 7) || (ldx & 7) || (reinterpret_cast<uintptr_t>(X) & 15)) return colsum_launch<__half>(Xh, ldx, M, N, scale, out, accumulate, st);
+  if (N <= 0) return DASA_OK;
+  if (!accumulate) {
+    zero_kernel<<<(unsigned)dasa_cdiv(N, 256), 256, 0, st>>>(out, N);
+    if (dasa_check_launch("zero_kernel") != DASA_OK) return DASA_ERR_CUDA;
+  }
+  if (M <= 0) return DASA_OK;
+  const int col_groups = (int)dasa_cdiv(N, 256);
+  int slabs = (int)dasa_cdiv(4 * DASA_NUM_SMS, col_groups);
+  const int max_slabs = (int)dasa_cdiv(M, 64);
+  slabs = slabs < 1 ? 1 : (slabs > max_slabs ? max_slabs : slabs);
+  if (col_groups > COLSUM_MAX_GROUPS) slabs = 1;
+  while (slabs > 1 && (int64_t)slabs * col_groups * 256 > COLSUM_PART_FLOATS) --slabs;
+  const int rows_per_slab = (int)dasa_cdiv(M, slabs);
+  dim3 grid((unsigned)col_groups, (unsigned)dasa_cdiv(M, rows_per_slab));
+  colsum_h8_kernel<<<grid, dim3(32, 8), 0, st>>>(Xh, ldx, M, N, out, rows_per_slab, scale);
+  return dasa_check_launch("colsum_h8_kernel");
 }

@@ -27,18 +27,24 @@ def defer_weight_grads(flag=True):
     _defer = bool(flag)
 
 
-def _bias_grads(dY, bias, bias2):
+def _bias_grads(dY, bias, bias2, half=None):
     """db += colsum(dY); a second bias fed by the same dY (nn.LSTM's b_ih / b_hh) reuses the column sums instead of a second
-    pass over dY."""
+    pass over dY. half = (dY16, alpha): take the sums from the scaled fp16 copy instead (dY may then be None)."""
     if bias is None or not bias.requires_grad:
         bias, bias2 = bias2, None
     if bias is None or not bias.requires_grad:
         return
+
+    def csum(out, acc):
+        if dY is not None:
+            ops.colsum(dY, out, acc)
+        else:
+            ops.colsum_h(half[0], half[1], out, acc)
     if bias2 is None or not bias2.requires_grad:
-        ops.colsum(dY, _zeros_like_grad(bias), True)
+        csum(_zeros_like_grad(bias), True)
         return
     s = torch.empty_like(bias)
-    ops.colsum(dY, s, False)
+    csum(s, False)
     ops.axpy2d(1.0, s, _zeros_like_grad(bias), accumulate=True)
     ops.axpy2d(1.0, s, _zeros_like_grad(bias2), accumulate=True)
 
@@ -66,7 +72,7 @@ def _wgrad16(weight, dy16, x16, alpha, dy, bias=None, bias2=None):
         return
     if not _defer:
         ops.linear_bwd_weight_f16(dy16, x16, _zeros_like_grad(weight), alpha, True)
-        _bias_grads(dy, bias, bias2)
+        _bias_grads(dy, bias, bias2, (dy16, alpha))
         return
     _queue16.append((weight, dy16, x16, alpha, dy, bias, bias2))
 
@@ -122,7 +128,7 @@ def flush_weight_grads(owner=None):
             keep.append(ent)
             continue
         ops.linear_bwd_weight_f16(dy16, x16, _zeros_like_grad(weight), alpha, True)
-        _bias_grads(dy, bias, bias2)
+        _bias_grads(dy, bias, bias2, (dy16, alpha))
     _queue16[:] = keep
 
 
@@ -216,14 +222,14 @@ class AdaINGateFn(torch.autograd.Function):
         f2, R, _, ldf = ops._rows(f)
         d2, _, _, ldd = ops._rows(d)
         g2, _, _, ldg = ops._rows(dout)
-        dg = torch.empty(R, C, device=f.device, dtype=torch.float32)
         if ctx.d16 is not None and R >= 64:
-            dg16 = torch.empty(R, C, device=f.device, dtype=torch.float16)
+            dg16 = torch.empty(R, C, device=f.device, dtype=torch.float16)     # only the scaled fp16 gradient is materialised
             ops.call("dasa_gate_backward_h", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
-                     None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, dg16.data_ptr(), 256.0, R, C,
+                     None if mask is None else mask.data_ptr(), float(ctx.scale), None, C, dg16.data_ptr(), 256.0, R, C,
                      ops._stream())
-            _wgrad16(weight, dg16, ctx.d16, 1.0 / 256.0, dg, bias)      # dW[C,C] += 2^-8 dg16^T d16 ; db += colsum(dg)
+            _wgrad16(weight, dg16, ctx.d16, 1.0 / 256.0, None, bias)    # dW[C,C] += 2^-8 dg16^T d16 ; db += 2^-8 colsum(dg16)
         else:
+            dg = torch.empty(R, C, device=f.device, dtype=torch.float32)
             ops.call("dasa_gate_backward", g2.data_ptr(), ldg, f2.data_ptr(), ldf, s.data_ptr(), C,
                      None if mask is None else mask.data_ptr(), float(ctx.scale), dg.data_ptr(), C, R, C, ops._stream())
             _wgrad(weight, dg, d2[:, :C], bias)        # dW[C,C] += dg^T d ; db += colsum(dg)
@@ -636,7 +642,6 @@ class PackedBiLSTMFn(torch.autograd.Function):
         dhf = dh_fin.index_select(1, plan.perm64).contiguous() if dh_fin is not None else None      # rank order
         dcf = dc_fin.index_select(1, plan.perm64).contiguous() if dc_fin is not None else None
         wt = (_transposed(w_hh_f), _transposed(w_hh_r))
-        dgates = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float32)
         work = torch.empty(2, 2, R, H, device=dev, dtype=torch.float32)
         P2 = ops.lib.P * 2
         cast = ops.ctypes.cast
@@ -650,19 +655,22 @@ class PackedBiLSTMFn(torch.autograd.Function):
             half = (P2(wt16[0].data_ptr(), wt16[1].data_ptr()), P2(dg16[0].data_ptr(), dg16[1].data_ptr()))
         else:
             half = (P2(None, None), P2(None, None))
+        half16 = ctx.half if (dg16 is not None and ctx.half is not None and N >= 64) else None
+        # the fp32 dgates are only read by dX (finetune configuration) and by the TF32 weight-gradient path
+        need32 = half16 is None or ctx.needs_input_grad[0]
+        dgates = torch.empty(2, N, 4 * H, device=dev, dtype=torch.float32) if need32 else None
         a = ops.lib.BiLstmPackedBwd(R, L, H, cast(plan.n_rows, ops.lib.P), cast(plan.off, ops.lib.P), plan.perm.data_ptr(),
                                     P2(wt[0].data_ptr(), wt[1].data_ptr()), P2(acts[0].data_ptr(), acts[1].data_ptr()),
                                     P2(cs[0].data_ptr(), cs[1].data_ptr()), dout.data_ptr(), P2(pp(dhf, 0), pp(dhf, 1)),
-                                    P2(pp(dcf, 0), pp(dcf, 1)), P2(dgates[0].data_ptr(), dgates[1].data_ptr()),
+                                    P2(pp(dcf, 0), pp(dcf, 1)), P2(pp(dgates, 0), pp(dgates, 1)),
                                     P2(work[0].data_ptr(), work[1].data_ptr()), *_drop_fields(ctx.drop, ctx.drop_scale, (R, L, 2 * H)),
                                     *half)
         ws = ops.workspace(ops.lib.load().dasa_bilstm_packed_workspace(R, H, 1))
         ops.call("dasa_bilstm_packed_bwd", ops.ctypes.byref(a), ops._p(ws), ws.numel(), ops._stream())
         dxc = None
-        half16 = ctx.half if (dg16 is not None and ctx.half is not None and N >= 64) else None
         for d, (w_ih, w_hh, b_ih, b_hh) in enumerate(params):
             if half16 is not None:      # dW = 2^-8 (dgates * 2^8)^T x on kind::f16 with the copies the recurrence keeps
-                _wgrad16(w_ih, dg16[d], half16[0], 1.0 / 256.0, dgates[d], b_ih, b_hh)
+                _wgrad16(w_ih, dg16[d], half16[0], 1.0 / 256.0, None, b_ih, b_hh)
                 _wgrad16(w_hh, dg16[d], half16[1][d], 1.0 / 256.0, None)
             else:
                 _wgrad(w_ih, dgates[d], xc, b_ih, b_hh)                        # db_ih == db_hh: one column sum

@@ -331,6 +331,13 @@ def colsum(x, out, accumulate=True):
     return out
 
 
+def colsum_h(x16, scale, out, accumulate=True):
+    """out[n] (+)= scale * sum_m x16[m, n] over an fp16 matrix (dasa_colsum_h)."""
+    assert x16.dtype == torch.float16 and x16.dim() == 2 and x16.stride(1) == 1
+    call("dasa_colsum_h", _p(x16), x16.stride(0), x16.shape[0], x16.shape[1], float(scale), _p(out), int(accumulate), _stream())
+    return out
+
+
 def _acc_grad(param, fn_new):
     """Accumulate a parameter gradient in place (param.grad is created zero-filled on first use)."""
     if param.grad is None:

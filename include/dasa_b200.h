@@ -126,6 +126,9 @@ int dasa_gemm(int a_kmajor, int b_kmajor, int M, int N, int K, float alpha, cons
 
 /* column sums: out[n] (+)= sum_m X[m*ldx + n]   (bias gradients) */
 int dasa_colsum(const float* X, int64_t ldx, int M, int N, float* out, int accumulate, void* stream);
+/* the same over an fp16 matrix, out[n] (+)= scale * sum_m X[m, n]: bias gradients from the scaled fp16 gradient copies the
+ * fp16-operand weight-gradient path keeps (scale = the inverse of the copy's factor).                                  */
+int dasa_colsum_h(const dasa_half_t* X, int64_t ldx, int M, int N, float scale, float* out, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------ AdaIN family
  * a1: DGAdaChannel ab_type=a, a_type=sigmoid (agent_dg.py:1534-1547) = dasa_gemm(..., DASA_EPI_GATE) for the fused
@@ -137,7 +140,7 @@ int dasa_gate_modulate(const float* g, int64_t ldg, const float* f, int64_t ldf,
 int dasa_gate_backward(const float* dout, int64_t lddo, const float* f, int64_t ldf, const float* s, int64_t lds,
                        const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, int R, int C, void* stream);
 /* the same, also writing dg16[r, c] = fp16(dg[r, c] * scale16) (saturating; [R, C] contiguous, C % 4 == 0): the dY operand of
- * the gate's weight gradient on dasa_gemm_f16_mn.                                                                       */
+ * the gate's weight gradient on dasa_gemm_f16_mn. dg may be NULL (only the fp16 copy is written).                      */
 int dasa_gate_backward_h(const float* dout, int64_t lddo, const float* f, int64_t ldf, const float* s, int64_t lds,
                          const uint8_t* drop_mask, float drop_scale, float* dg, int64_t lddg, dasa_half_t* dg16, float scale16,
                          int R, int C, void* stream);
@@ -307,6 +310,7 @@ typedef struct {
   /* fp16 recurrence (all four non-NULL and H % 64 == 0; else TF32): w_hh_t16[d] = fp16 copy of w_hh_t[d], dg16[d] [N, 4H] fp16
    * scratch receiving dgates * 2^8 (saturating) = the A operand of dh = dgates W_hh on tcgen05 kind::f16 (the sums are rescaled
    * by 2^-8; fp16 keeps TF32's 11 significant bits for |dgate| in [2.4e-7, 256)).                                               */
+  /* With the fp16 recurrence dgates[d] may be NULL: only the scaled fp16 copy is written (the weight / bias gradients read it).  */
   const dasa_half_t* w_hh_t16[2]; dasa_half_t* dg16[2];
 } dasa_bilstm_packed_bwd_t;
 size_t dasa_bilstm_packed_workspace(int R, int H, int backward);

@@ -916,6 +916,24 @@ def test_adain_gate_on_fp16_operands_matches_tf32_path():
     assert rel_err(res[1][0], res[0][0]) <= 2e-3 and rel_err(res[1][1], res[0][1]) <= 2e-3
 
 
+@pytest.mark.parametrize("M,N,ld", [(19810, 4096, 4096), (700, 2048, 2112), (333, 40, 40), (64, 1000, 1000)])
+def test_colsum_fp16_scaled(M, N, ld):
+    """dasa_colsum_h: out[n] (+)= scale * sum_m x16[m, n] (vectorised 8-column path and the scalar fallback) vs fp64; run twice for
+    bit-reproducibility."""
+    from dasa_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    wide = (torch.randn(M, ld, generator=g) * 3.0).half().to(DEV)
+    x = wide[:, :N]
+    out0 = torch.randn(N, generator=g).to(DEV)
+    ref = out0.double() + x.double().sum(0) / 256.0
+    a = ops.colsum_h(x, 1.0 / 256.0, out0.clone(), True)
+    b = ops.colsum_h(x, 1.0 / 256.0, out0.clone(), True)
+    assert torch.equal(a, b)
+    assert rel_err(a.double(), ref) <= 1e-5, rel_err(a.double(), ref)
+    c = ops.colsum_h(x, 1.0 / 256.0, torch.full((N,), float("nan"), device=DEV), False)
+    assert rel_err(c.double(), ref - out0.double()) <= 1e-5
+
+
 # ------------------------------------------------------------------------------ padding-free bi-LSTM (bilstm_packed.cu)
 @pytest.mark.parametrize("R,L,In,H,seed", [(70, 12, 64, 64, 0), (300, 21, 96, 128, 1), (45, 9, 64, 32, 2)])
 def test_packed_bilstm_matches_padded_path(R, L, In, H, seed):
