@@ -150,6 +150,7 @@ def test_train_rollout_gradients_match_reference_fixture():
         for k, prm in mod.named_parameters():
             named[grp + "." + k] = prm
     worst, checked = ("", 0.0), 0
+    errs = []
     for name, d in g["grads"].items():
         want_norm = float(d["norm"])
         prm = named[name]
@@ -162,6 +163,7 @@ def test_train_rollout_gradients_match_reference_fixture():
         if want_norm < 1e-7:          # attention key biases etc.: the gradient is round-off in the reference too
             continue
         checked += 1
+        errs.append((e_l2, name))
         if e_l2 > worst[1]:
             worst = (name, e_l2)
         # Bias vectors of a handful of elements (linear_shift.bias: 5) are column sums of mixed-sign per-row terms (the rows of a
@@ -170,6 +172,7 @@ def test_train_rollout_gradients_match_reference_fixture():
         assert e_norm <= tol, "gradient %s: norm differs by %.3e" % (name, e_norm)
         assert e_l2 <= tol, "gradient %s: L2 error of the strided sample %.3e" % (name, e_l2)
     print("train: %d gradients checked, worst L2 rel err %.2e (%s)" % (checked, worst[1], worst[0]))
+    print("train: L2 rel err per gradient: " + ", ".join("%s %.1e" % (n, e) for e, n in sorted(errs, reverse=True)))
     assert checked >= 20
 
 
