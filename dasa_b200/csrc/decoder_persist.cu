@@ -1234,6 +1234,26 @@ __device__ __forceinline__ void grid_sync_variant(GridBar& gb) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
         if (++it > (1u << 22)) __trap();
       } while ((int)(v - gb.target) < 0);
+    } else if (VARIANT == 3) {              // release-add, RELAXED polls (no L1 invalidate per iteration), one acquire fence at the end
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+      unsigned int v, it = 0;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+        if (++it > (1u << 22)) __trap();
+      } while ((int)(v - gb.target) < 0);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    } else if (VARIANT == 4) {              // the same with two polls in flight (detection delay = half a round trip)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+      unsigned int v0, v1, it = 0;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(gb.ctr) : "memory");
+      for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(gb.ctr) : "memory");
+        if ((int)(v0 - gb.target) >= 0) break;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(gb.ctr) : "memory");
+        if ((int)(v1 - gb.target) >= 0) break;
+        if (++it > (1u << 22)) __trap();
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     } else {                                // VARIANT 2: fence + relaxed atomic + volatile poll + fence (cooperative-groups style)
       __threadfence();
       atomicAdd(gb.ctr, 1u);
@@ -1335,6 +1355,8 @@ extern "C" int dasa_debug_barrier_bench(int variant, int iters, unsigned int* ct
   cudaError_t e;
   if (variant == 0) e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<0>, ctr, iters, out, junk);
   else if (variant == 1) e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<1>, ctr, iters, out, junk);
+  else if (variant == 3) e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<3>, ctr, iters, out, junk);
+  else if (variant == 4) e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<4>, ctr, iters, out, junk);
   else e = cudaLaunchKernelEx(&cfg, barrier_bench_kernel<2>, ctr, iters, out, junk);
   if (e != cudaSuccess) { dasa_set_error("barrier_bench_kernel", e); return DASA_ERR_CUDA; }
   return DASA_OK;
