@@ -85,6 +85,12 @@ _queue16 = []
 pre_encoder_backward = None
 
 
+def discard_weight_grads():
+    """Drop every queued weight-gradient reduction (profiling helpers that run a backward pass without an optimizer step)."""
+    _queue.clear()
+    _queue16.clear()
+
+
 def pending_weight_grads(owner):
     """Number of queued weight-gradient reductions whose target lives inside the flat buffer `owner`."""
     n = sum(1 for (weight, _, _, _, _) in _queue.values() if _inside(weight.grad, owner))
