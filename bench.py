@@ -383,6 +383,11 @@ def run_ours(args):
     def try_capture(trainer, ep):
         if args.no_graph or args.profile_step:
             return
+        if sample:
+            # the closed-loop sampled rollout draws from torch's generator and is launched eagerly; a FAILED capture attempt would
+            # also leave that generator in its capture state ("Offset increment outside graph capture") for the eager steps
+            state["graph_error"] = "sampled feedback: closed-loop rollout, eager launches"
+            return
         try:
             trainer.capture(ep)
         except Exception as e:                              # stay on eager launches, say so in the JSON line
