@@ -4,6 +4,8 @@
 // (256 KB, L2-resident across the 80 steps) with 128-bit loads, and applies the LSTM pointwise math for its units in the
 // same kernel. Exact fp32 (FFMA). The whole sequence loop is issued from one C call, so the host cost is one call per
 // encoder pass instead of ~320.
+#include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -473,6 +475,343 @@ __global__ void __launch_bounds__(THREADS) bilstm_step_bwd_tc_kernel(SeqBwd p, i
   }
 }
 
+// ================================================================================================ persistent form (TF32 mode)
+// The whole time loop in ONE cooperative launch each way (B <= 20, H % 128 == 0, H <= 1024): the same 2 x H/16 CTAs stay
+// resident, keep their 64 recurrent-weight rows (forward) / their 16 rows of W_hh^T (backward) in SHARED MEMORY as fp16 for all L
+// steps (128 KB; streamed from L2 as 256 KB of fp32 in every step before), exchange the state / the gate gradients of a step as
+// fp16 rows through L2 (h in (-1, 1); gate gradients scaled by 2^8, saturating: fp16 keeps TF32's 11 significant bits) and
+// separate the steps with a device-wide barrier instead of a kernel boundary (11.5 / 16.6 us per step -> see DESIGN.md).
+// Products on mma.sync.m16n8k16 f16 x f16 -> f32; pointwise math, state and every saved tensor in fp32 exactly as the per-step
+// kernels write them.
+constexpr int PS_MAXH = 1024;
+__device__ __half g_ps_x16[2][2][NB][PS_MAXH];            // forward: state rows [ping-pong][direction][b][H]
+__device__ __half g_ps_g16[2][2][NB][4 * PS_MAXH];        // backward: scaled gate gradients [ping-pong][direction][b][4H]
+__device__ unsigned int g_ps_bar[2];                      // barrier counters (forward, backward), zeroed before each launch
+constexpr float PS_GSCALE = 256.f;
+
+struct PsBar { unsigned int* ctr; unsigned int target, nblk; };
+__device__ __forceinline__ void ps_grid_sync(PsBar& gb) {
+  gb.target += gb.nblk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+    unsigned int v, it = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      if (++it > (1u << 22)) __trap();                   // a protocol bug traps instead of hanging the device
+    } while ((int)(v - gb.target) < 0);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void ps_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ps_u4(const uint4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+__device__ __forceinline__ uint4 ps_ldcg16(const __half* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
+// Forward. Shared memory: Ws[64][H + 32] halves (row pitch = 64 B mod 128 B: the 8 lanes of a quarter warp hit 32 distinct banks),
+// part[8][64][NB + 1] floats. Lane (g, t) owns 8 consecutive k of its rows per 32-wide chunk (k slots of the MMA are a fixed
+// bijection of the reduction index, the same for both operands).
+__global__ void __launch_bounds__(THREADS, 1) bilstm_persist_fwd_kernel(SeqFwd p) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  const int B = p.B, L = p.L, H = p.H;
+  const int pitch = H + 32;
+  __half* Ws = reinterpret_cast<__half*>(ps_smem);
+  float (*part)[64][NB + 1] = reinterpret_cast<float (*)[64][NB + 1]>(ps_smem + (size_t)64 * pitch * sizeof(__half));
+  float (*gbuf)[NB + 1] = part[0];
+  const int d = blockIdx.y, j0 = blockIdx.x * UNITS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  PsBar gb{&g_ps_bar[0], 0u, gridDim.x * gridDim.y};
+  // weights: local row r = unit * 4 + gate <- W_hh row gate * H + j0 + unit, fp32 -> fp16 once
+  for (int i = threadIdx.x; i < 64 * (H >> 2); i += THREADS) {
+    const int r = i / (H >> 2), k = (i % (H >> 2)) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.w_hh[d] + ((size_t)(r & 3) * H + j0 + (r >> 2)) * H + k));
+    __half2 h2[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
+    *reinterpret_cast<uint2*>(Ws + (size_t)r * pitch + k) = *reinterpret_cast<uint2*>(h2);
+  }
+  // the state before step 0 is zero (hs / cs index 0 are zero-filled by the caller): its fp16 rows for this CTA's units
+  for (int i = threadIdx.x; i < UNITS * NB; i += THREADS) g_ps_x16[0][d][i / UNITS][j0 + i % UNITS] = __float2half_rn(0.f);
+  ps_grid_sync(gb);
+  const int kspan = H >> 3, kw0 = warp * kspan, nch = kspan >> 5;       // this warp's slice of the reduction: nch chunks of 32
+  for (int s = 0; s < L; ++s) {
+    const int l = d == 0 ? s : L - 1 - s;
+    const __half* x16 = &g_ps_x16[s & 1][d][0][0];
+    __half* x16n = &g_ps_x16[(s + 1) & 1][d][0][0];
+    // the pointwise operands of this thread's (unit, episode) items do not depend on the GEMM: requested now (xp and the cell
+    // state come from DRAM), consumed after the fold
+    float pre_x[2][4], pre_c[2], pre_h[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int tt = threadIdx.x + it * THREADS;
+      pre_c[it] = 0.f; pre_h[it] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre_x[it][q] = 0.f;
+      if (tt < UNITS * B) {
+        const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+        pre_c[it] = p.cs[d][(size_t)s * B * H + (size_t)b * H + j];
+        if (l < p.lengths[b]) {
+          const float* xrow = p.xp[d] + ((size_t)b * L + l) * 4 * H;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pre_x[it][q] = __ldg(xrow + q * H + j);
+        } else {
+          pre_h[it] = p.hs[d][(size_t)s * B * H + (size_t)b * H + j];
+        }
+      }
+    }
+    float acc[4][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= nch) break;
+      const int k = kw0 + 32 * c + 8 * t;
+      uint4 xf[3];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) xf[nt] = (8 * nt + g < B) ? ps_ldcg16(x16 + (size_t)(8 * nt + g) * PS_MAXH + k) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const uint4 wa = *reinterpret_cast<const uint4*>(Ws + (size_t)(16 * mt + g) * pitch + k);
+        const uint4 wb = *reinterpret_cast<const uint4*>(Ws + (size_t)(16 * mt + g + 8) * pitch + k);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t af[4] = {ps_u4(wa, 2 * j), ps_u4(wb, 2 * j), ps_u4(wa, 2 * j + 1), ps_u4(wb, 2 * j + 1)};
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) ps_mma(acc[mt][nt], af, ps_u4(xf[nt], 2 * j), ps_u4(xf[nt], 2 * j + 1));
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        part[warp][16 * mt + g][8 * nt + 2 * t] = acc[mt][nt][0];
+        part[warp][16 * mt + g][8 * nt + 2 * t + 1] = acc[mt][nt][1];
+        part[warp][16 * mt + g + 8][8 * nt + 2 * t] = acc[mt][nt][2];
+        part[warp][16 * mt + g + 8][8 * nt + 2 * t + 1] = acc[mt][nt][3];
+      }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 64 * NB; o += THREADS) {
+      const int r = o / NB, c = o % NB;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][r][c];
+      gbuf[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int tt = threadIdx.x + it * THREADS;
+      if (tt >= UNITS * B) break;
+      const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+      const size_t sb = (size_t)b * H + j;
+      const float cp = pre_c[it];
+      float* hn = p.hs[d] + (size_t)(s + 1) * B * H;
+      float* cn = p.cs[d] + (size_t)(s + 1) * B * H;
+      float* a = p.acts[d] + ((size_t)s * B + b) * 4 * H;
+      float* o = p.out + ((size_t)b * L + l) * 2 * H + (size_t)d * H + j;
+      if (l >= p.lengths[b]) {                       // packed-sequence semantics: carry state, zero output row
+        const float hp = pre_h[it];
+        hn[sb] = hp;
+        cn[sb] = cp;
+        x16n[(size_t)b * PS_MAXH + j] = __float2half_rn(hp);
+        *o = 0.f;
+        a[j] = 0.f; a[H + j] = 0.f; a[2 * H + j] = 0.f; a[3 * H + j] = 0.f;
+        continue;
+      }
+      float gt[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        gt[q] = gbuf[u * 4 + q][b] + pre_x[it][q] + __ldg(p.b_ih[d] + q * H + j) + __ldg(p.b_hh[d] + q * H + j);
+      const float ig = sigmoidf_(gt[0]), fg = sigmoidf_(gt[1]), gg = tanhf(gt[2]), og = sigmoidf_(gt[3]);
+      const float c1 = fg * cp + ig * gg;
+      const float h1 = og * tanhf(c1);
+      hn[sb] = h1;
+      cn[sb] = c1;
+      x16n[(size_t)b * PS_MAXH + j] = __float2half_rn(h1);
+      *o = h1;
+      a[j] = ig; a[H + j] = fg; a[2 * H + j] = gg; a[3 * H + j] = og;
+    }
+    if (s + 1 < L) ps_grid_sync(gb);
+  }
+}
+
+// Backward. Shared memory: Wt[16][4H + 32] halves = this CTA's 16 rows of W_hh^T, part[8][16][NB + 1] + red[16][NB] floats.
+__global__ void __launch_bounds__(THREADS, 1) bilstm_persist_bwd_kernel(SeqBwd p) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  const int B = p.B, L = p.L, H = p.H, G = 4 * H;
+  const int pitch = G + 32;
+  __half* Wt = reinterpret_cast<__half*>(ps_smem);
+  float (*part)[UNITS][NB + 1] = reinterpret_cast<float (*)[UNITS][NB + 1]>(ps_smem + (size_t)UNITS * pitch * sizeof(__half));
+  float (*red)[NB] = reinterpret_cast<float (*)[NB]>(reinterpret_cast<float*>(part) + 8 * UNITS * (NB + 1));
+  const int d = blockIdx.y, j0 = blockIdx.x * UNITS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  PsBar gb{&g_ps_bar[1], 0u, gridDim.x * gridDim.y};
+  for (int i = threadIdx.x; i < UNITS * (G >> 2); i += THREADS) {
+    const int r = i / (G >> 2), k = (i % (G >> 2)) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.w_hh_t[d] + (size_t)(j0 + r) * G + k));
+    __half2 h2[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
+    *reinterpret_cast<uint2*>(Wt + (size_t)r * pitch + k) = *reinterpret_cast<uint2*>(h2);
+  }
+  __syncthreads();
+  const int kspan = G >> 3, kw0 = warp * kspan, nch = kspan >> 5;
+  for (int s = L - 1; s >= 0; --s) {
+    const int l = d == 0 ? s : L - 1 - s;
+    const bool last = (s == L - 1);
+    const int par = s & 1;
+    // pointwise operands of this thread's (unit, episode) items (saved activations / cell states / output gradient come from
+    // DRAM): requested before the GEMM
+    float q_a[2][4], q_cp[2], q_cn[2], q_do[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int tt = threadIdx.x + it * THREADS;
+      q_cp[it] = q_cn[it] = q_do[it] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) q_a[it][q] = 0.f;
+      if (tt < UNITS * B) {
+        const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+        if (l < p.lengths[b]) {
+          const size_t sb = (size_t)b * H + j;
+          const float* a = p.acts[d] + ((size_t)s * B + b) * G;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) q_a[it][q] = __ldg(a + q * H + j);
+          q_cp[it] = __ldg(p.cs[d] + (size_t)s * B * H + sb);
+          q_cn[it] = __ldg(p.cs[d] + (size_t)(s + 1) * B * H + sb);
+          q_do[it] = __ldg(p.dout + ((size_t)b * L + l) * 2 * H + (size_t)d * H + j);
+        }
+      }
+    }
+    if (!last) {
+      // rec[unit, b] = dgates_{s+1}[b, :] . W_hh^T[unit, :] over the scaled fp16 copies every CTA published in the previous step
+      const __half* x16 = &g_ps_g16[par ^ 1][d][0][0];
+      float acc[3][4];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < nch; ++c) {
+        const int k = kw0 + 32 * c + 8 * t;
+        uint4 xf[3];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+          xf[nt] = (8 * nt + g < B) ? ps_ldcg16(x16 + (size_t)(8 * nt + g) * (4 * PS_MAXH) + k) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 wa = *reinterpret_cast<const uint4*>(Wt + (size_t)g * pitch + k);
+        const uint4 wb = *reinterpret_cast<const uint4*>(Wt + (size_t)(g + 8) * pitch + k);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t af[4] = {ps_u4(wa, 2 * j), ps_u4(wb, 2 * j), ps_u4(wa, 2 * j + 1), ps_u4(wb, 2 * j + 1)};
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) ps_mma(acc[nt], af, ps_u4(xf[nt], 2 * j), ps_u4(xf[nt], 2 * j + 1));
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        part[warp][g][8 * nt + 2 * t] = acc[nt][0];
+        part[warp][g][8 * nt + 2 * t + 1] = acc[nt][1];
+        part[warp][g + 8][8 * nt + 2 * t] = acc[nt][2];
+        part[warp][g + 8][8 * nt + 2 * t + 1] = acc[nt][3];
+      }
+      __syncthreads();
+      for (int o = threadIdx.x; o < UNITS * NB; o += THREADS) {
+        const int r = o / NB, c = o % NB;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += part[w][r][c];
+        red[r][c] = v * (1.f / PS_GSCALE);
+      }
+    }
+    __syncthreads();
+    __half* g16 = &g_ps_g16[par][d][0][0];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int tt = threadIdx.x + it * THREADS;
+      if (tt >= UNITS * B) break;
+      const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+      const size_t sb = (size_t)b * H + j;
+      float dh, dc;
+      if (last) {
+        dh = p.dh_fin[d] ? p.dh_fin[d][sb] : 0.f;
+        dc = p.dc_fin[d] ? p.dc_fin[d][sb] : 0.f;
+      } else {
+        dh = red[u][b] + p.dh_pass[d][(size_t)(par ^ 1) * B * H + sb];
+        dc = p.dc_work[d][(size_t)(par ^ 1) * B * H + sb];
+      }
+      float* dg = p.dgates[d] + ((size_t)s * B + b) * G;
+      float* dh_pass = p.dh_pass[d] + (size_t)par * B * H;
+      float* dc_out = p.dc_work[d] + (size_t)par * B * H;
+      __half* gh = g16 + (size_t)b * (4 * PS_MAXH);
+      if (l >= p.lengths[b]) {
+        dg[j] = 0.f; dg[H + j] = 0.f; dg[2 * H + j] = 0.f; dg[3 * H + j] = 0.f;
+        const __half z = __float2half_rn(0.f);
+        gh[j] = z; gh[H + j] = z; gh[2 * H + j] = z; gh[3 * H + j] = z;
+        dh_pass[sb] = dh;
+        dc_out[sb] = dc;
+        continue;
+      }
+      dh += q_do[it];
+      const float ig = q_a[it][0], fg = q_a[it][1], gg = q_a[it][2], og = q_a[it][3];
+      const float cp = q_cp[it];
+      const float tc = tanhf(q_cn[it]);
+      const float dct = dc + dh * og * (1.f - tc * tc);
+      const float d0 = dct * gg * ig * (1.f - ig), d1 = dct * cp * fg * (1.f - fg), d2 = dct * ig * (1.f - gg * gg),
+                  d3 = dh * tc * og * (1.f - og);
+      dg[j] = d0; dg[H + j] = d1; dg[2 * H + j] = d2; dg[3 * H + j] = d3;
+      unsigned short q0, q1, q2, q3;
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q0) : "f"(d0 * PS_GSCALE));
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q1) : "f"(d1 * PS_GSCALE));
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q2) : "f"(d2 * PS_GSCALE));
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q3) : "f"(d3 * PS_GSCALE));
+      gh[j] = __ushort_as_half(q0); gh[H + j] = __ushort_as_half(q1); gh[2 * H + j] = __ushort_as_half(q2); gh[3 * H + j] = __ushort_as_half(q3);
+      dh_pass[sb] = 0.f;
+      dc_out[sb] = dct * fg;
+    }
+    if (s > 0) ps_grid_sync(gb);
+  }
+}
+
+int g_ps_mode = -1;      // -1: read DASA_BILSTM_PERSIST (default 1); 0 = per-step launches; 1 = persistent kernels when they apply
+
+bool ps_enabled(int B, int H) {
+  if (g_ps_mode < 0) { const char* e = getenv("DASA_BILSTM_PERSIST"); g_ps_mode = e ? atoi(e) : 1; }
+  return g_ps_mode != 0 && B <= 20 && H % 256 == 0 && H <= PS_MAXH;     // each of the 8 warps owns whole 32-wide chunks of H
+}
+
+template <typename Kern, typename Args>
+int ps_launch(Kern kern, const Args& p, size_t smem, int which, cudaStream_t st, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
+  static unsigned int* bar = nullptr;
+  if (bar == nullptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&bar), g_ps_bar) != cudaSuccess) return DASA_ERR_CUDA;
+  if (cudaMemsetAsync(bar + which, 0, sizeof(unsigned int), st) != cudaSuccess) return DASA_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.H / UNITS), 2);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;         // all 2 x H/16 CTAs co-resident, or the launch fails (never a deadlock)
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) { dasa_set_error(name, e); return DASA_ERR_CUDA; }
+  return DASA_OK;
+}
+
+int run_fwd_persist(const SeqFwd& p, cudaStream_t st) {
+  const size_t smem = (size_t)64 * (p.H + 32) * sizeof(__half) + sizeof(float) * 8 * 64 * (NB + 1);
+  return ps_launch(bilstm_persist_fwd_kernel, p, smem, 0, st, "bilstm_persist_fwd_kernel");
+}
+int run_bwd_persist(const SeqBwd& p, cudaStream_t st) {
+  const size_t smem = (size_t)UNITS * (4 * p.H + 32) * sizeof(__half) + sizeof(float) * (8 * UNITS * (NB + 1) + UNITS * NB);
+  return ps_launch(bilstm_persist_bwd_kernel, p, smem, 1, st, "bilstm_persist_bwd_kernel");
+}
+
 int run_fwd_tc(const SeqFwd& p, cudaStream_t st) {
   dim3 grid((unsigned)(p.H / UNITS), 2);
   constexpr size_t smem = sizeof(float) * 8 * 64 * (NB + 1);
@@ -517,6 +856,11 @@ int run_bwd(const SeqBwd& p, cudaStream_t st) {
 
 extern "C" int dasa_bilstm_max_batch(void) { return 20; }
 
+extern "C" int dasa_debug_bilstm_persist(int mode) {
+  g_ps_mode = mode;
+  return DASA_OK;
+}
+
 extern "C" int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* a, int precision, void* stream) {
   if (a == nullptr || a->B <= 0 || a->L <= 0) return DASA_ERR_BAD_SHAPE;
   if (a->B > 20 || a->H % 64 != 0) return DASA_ERR_UNSUPPORTED;
@@ -528,6 +872,7 @@ extern "C" int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* a, int precision, vo
   }
   p.out = a->out; p.lengths = a->lengths; p.B = a->B; p.L = a->L; p.H = a->H;
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DASA_PREC_TF32 && ps_enabled(p.B, p.H)) return run_fwd_persist(p, st);
   if (precision == DASA_PREC_TF32 && p.H % 128 == 0) return run_fwd_tc(p, st);
   if (p.B <= 4) return run_fwd<4>(p, st);
   if (p.B <= 8) return run_fwd<8>(p, st);
@@ -548,6 +893,7 @@ extern "C" int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* a, int precision, vo
   }
   p.dout = a->dout; p.lengths = a->lengths; p.B = a->B; p.L = a->L; p.H = a->H;
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == DASA_PREC_TF32 && ps_enabled(p.B, p.H)) return run_bwd_persist(p, st);
   if (precision == DASA_PREC_TF32 && p.H % 128 == 0) return run_bwd_tc(p, st);
   if (p.B <= 4) return run_bwd<4>(p, st);
   if (p.B <= 8) return run_bwd<8>(p, st);

@@ -256,6 +256,10 @@ typedef struct {
 } dasa_bilstm_bwd_t;
 int dasa_bilstm_max_batch(void);
 /* precision: DASA_PREC_FP32 = FFMA kernels (exact fp32); DASA_PREC_TF32 = mma.sync TF32 tensor-core kernels (H % 128 == 0) */
+/* In the TF32 mode with H % 256 == 0 and H <= 1024 both calls run ONE cooperative launch for the whole time loop (recurrent weights
+ * resident in shared memory as fp16, fp16 state / scaled gate-gradient exchange through L2, device-wide barrier per step) instead
+ * of one launch per step; dasa_debug_bilstm_persist(0) selects the per-step kernels (1 = default, also env DASA_BILSTM_PERSIST). */
+int dasa_debug_bilstm_persist(int mode);
 int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* args, int precision, void* stream);
 int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, int precision, void* stream);
 /* Large-batch form of the same recurrence (the batched teacher-forced schedule runs all T x B instruction copies at once):

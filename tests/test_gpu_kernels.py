@@ -421,6 +421,47 @@ def test_bilstm_tf32_tensor_core_path(B, L, In, H):
     assert max(errs.values()) <= 1e-2, errs
 
 
+@pytest.mark.parametrize("B,L,H", [(20, 45, 1024), (7, 13, 1024), (1, 5, 512), (20, 80, 256)])
+def test_bilstm_persistent_kernels_match_per_step_kernels(B, L, H):
+    """Small-batch bi-LSTM in the tensor-core mode: the persistent cooperative kernels (whole time loop in one launch, fp16 weights
+    resident in shared memory, fp16 state / scaled gate-gradient exchange) against the per-step TF32 kernels they replace
+    (dasa_debug_bilstm_persist): outputs, final states and every gradient, ragged lengths incl. length 1. Both carry 11-bit operands."""
+    from dasa_b200 import lib
+    In = 64
+    gen = g(77 + B + L)
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    base = {}
+    for sfx in ("", "_reverse"):
+        base["weight_ih_l0" + sfx] = torch.randn(4 * H, In, generator=gen) / math.sqrt(In)
+        base["weight_hh_l0" + sfx] = torch.randn(4 * H, H, generator=gen) / math.sqrt(H)
+        base["bias_ih_l0" + sfx] = torch.randn(4 * H, generator=gen) * 0.1
+        base["bias_hh_l0" + sfx] = torch.randn(4 * H, generator=gen) * 0.1
+    lengths = torch.randint(1, L + 1, (B,), generator=gen).sort(descending=True).values
+    lengths[0] = L
+    lengths[-1] = 1
+    x = torch.randn(B, L, In, generator=gen)
+    wts = [torch.randn(B, L, 2 * H, generator=gen), torch.randn(2, B, H, generator=gen), torch.randn(2, B, H, generator=gen)]
+    l32 = lengths.to(DEV).to(torch.int32)
+    res = []
+    ops.set_precision("tf32")
+    try:
+        for mode in (0, 1):
+            lib.load().dasa_debug_bilstm_persist(mode)
+            P = {k: v.clone().to(DEV).requires_grad_(True) for k, v in base.items()}
+            xd = x.clone().to(DEV).requires_grad_(True)
+            o2, hfin, cfin = Fn.BiLSTMFn.apply(xd, l32, *[P[n] for n in names], *[P[n + "_reverse"] for n in names])
+            torch.autograd.backward([o2, hfin, cfin], [w.to(DEV) for w in wts])
+            torch.cuda.synchronize()
+            res.append([o2, hfin, cfin, xd.grad] + [P[k].grad for k in sorted(P)])
+    finally:
+        lib.load().dasa_debug_bilstm_persist(1)
+        ops.set_precision("fp32")
+    for i, (a, b) in enumerate(zip(res[1], res[0])):
+        assert rel_err(a, b) <= 2e-3, (i, rel_err(a, b))
+    valid = torch.arange(L, device=DEV).view(1, L) < l32.view(B, 1)
+    assert float(res[1][0][~valid].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 3e-3)])
 @pytest.mark.parametrize("B,Lq,Lk", [(3, 45, 45), (2, 80, 36), (4, 36, 80), (2, 23, 23)])
 def test_mha_forward_both_precisions(prec, tol, B, Lq, Lk):
