@@ -258,7 +258,9 @@ int dasa_bilstm_max_batch(void);
 /* precision: DASA_PREC_FP32 = FFMA kernels (exact fp32); DASA_PREC_TF32 = mma.sync TF32 tensor-core kernels (H % 128 == 0) */
 /* In the TF32 mode with H % 256 == 0 and H <= 1024 both calls run ONE cooperative launch for the whole time loop (recurrent weights
  * resident in shared memory as fp16, fp16 state / scaled gate-gradient exchange through L2, device-wide barrier per step) instead
- * of one launch per step; dasa_debug_bilstm_persist(0) selects the per-step kernels (1 = default, also env DASA_BILSTM_PERSIST). */
+ * of one launch per step; dasa_debug_bilstm_persist(0) selects the per-step kernels (1 = default, also env DASA_BILSTM_PERSIST).
+ * The exchange rows and the barrier word live in a static device scratch: calls on ONE stream at a time per device (like
+ * dasa_colsum's slab scratch); the launch is cooperative, so it fails instead of deadlocking if the grid cannot be co-resident. */
 int dasa_debug_bilstm_persist(int mode);
 int dasa_bilstm_seq_fwd(const dasa_bilstm_fwd_t* args, int precision, void* stream);
 int dasa_bilstm_seq_bwd(const dasa_bilstm_bwd_t* args, int precision, void* stream);
