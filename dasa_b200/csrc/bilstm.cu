@@ -503,6 +503,23 @@ __device__ __forceinline__ void ps_grid_sync(PsBar& gb) {
   }
   __syncthreads();
 }
+// The same barrier in two halves: everything a CTA stores BEFORE ps_arrive is visible to the others after their ps_wait; stores
+// issued between the two halves (tensors nobody reads inside the launch) drain under the wait instead of in front of the arrive.
+__device__ __forceinline__ void ps_arrive(PsBar& gb) {
+  gb.target += gb.nblk;
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+}
+__device__ __forceinline__ void ps_wait(PsBar& gb) {
+  if (threadIdx.x == 0) {
+    unsigned int v, it = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      if (++it > (1u << 22)) __trap();
+    } while ((int)(v - gb.target) < 0);
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ void ps_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -603,40 +620,47 @@ __global__ void __launch_bounds__(THREADS, 1) bilstm_persist_fwd_kernel(SeqFwd p
       gbuf[r][c] = v;
     }
     __syncthreads();
+    float r_h[2], r_c[2], r_g[2][4];
+    bool r_live[2];
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < 2; ++it) {                 // phase 1: the cell update; only the fp16 state row other CTAs read is stored
+      const int tt = threadIdx.x + it * THREADS;
+      r_h[it] = r_c[it] = 0.f; r_live[it] = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r_g[it][q] = 0.f;
+      if (tt >= UNITS * B) break;
+      const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+      const float cp = pre_c[it];
+      if (l >= p.lengths[b]) {                       // packed-sequence semantics: carry state, zero output row
+        r_h[it] = pre_h[it];
+        r_c[it] = cp;
+      } else {
+        float gt[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          gt[q] = gbuf[u * 4 + q][b] + pre_x[it][q] + __ldg(p.b_ih[d] + q * H + j) + __ldg(p.b_hh[d] + q * H + j);
+        const float ig = sigmoidf_(gt[0]), fg = sigmoidf_(gt[1]), gg = tanhf(gt[2]), og = sigmoidf_(gt[3]);
+        r_c[it] = fg * cp + ig * gg;
+        r_h[it] = og * tanhf(r_c[it]);
+        r_g[it][0] = ig; r_g[it][1] = fg; r_g[it][2] = gg; r_g[it][3] = og;
+        r_live[it] = true;
+      }
+      x16n[(size_t)b * PS_MAXH + j] = __float2half_rn(r_h[it]);
+    }
+    if (s + 1 < L) ps_arrive(gb);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {                 // phase 2: everything only later kernels (or this thread) read
       const int tt = threadIdx.x + it * THREADS;
       if (tt >= UNITS * B) break;
       const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
       const size_t sb = (size_t)b * H + j;
-      const float cp = pre_c[it];
-      float* hn = p.hs[d] + (size_t)(s + 1) * B * H;
-      float* cn = p.cs[d] + (size_t)(s + 1) * B * H;
+      p.hs[d][(size_t)(s + 1) * B * H + sb] = r_h[it];
+      p.cs[d][(size_t)(s + 1) * B * H + sb] = r_c[it];
       float* a = p.acts[d] + ((size_t)s * B + b) * 4 * H;
-      float* o = p.out + ((size_t)b * L + l) * 2 * H + (size_t)d * H + j;
-      if (l >= p.lengths[b]) {                       // packed-sequence semantics: carry state, zero output row
-        const float hp = pre_h[it];
-        hn[sb] = hp;
-        cn[sb] = cp;
-        x16n[(size_t)b * PS_MAXH + j] = __float2half_rn(hp);
-        *o = 0.f;
-        a[j] = 0.f; a[H + j] = 0.f; a[2 * H + j] = 0.f; a[3 * H + j] = 0.f;
-        continue;
-      }
-      float gt[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        gt[q] = gbuf[u * 4 + q][b] + pre_x[it][q] + __ldg(p.b_ih[d] + q * H + j) + __ldg(p.b_hh[d] + q * H + j);
-      const float ig = sigmoidf_(gt[0]), fg = sigmoidf_(gt[1]), gg = tanhf(gt[2]), og = sigmoidf_(gt[3]);
-      const float c1 = fg * cp + ig * gg;
-      const float h1 = og * tanhf(c1);
-      hn[sb] = h1;
-      cn[sb] = c1;
-      x16n[(size_t)b * PS_MAXH + j] = __float2half_rn(h1);
-      *o = h1;
-      a[j] = ig; a[H + j] = fg; a[2 * H + j] = gg; a[3 * H + j] = og;
+      p.out[((size_t)b * L + l) * 2 * H + (size_t)d * H + j] = r_live[it] ? r_h[it] : 0.f;
+      a[j] = r_g[it][0]; a[H + j] = r_g[it][1]; a[2 * H + j] = r_g[it][2]; a[3 * H + j] = r_g[it][3];
     }
-    if (s + 1 < L) ps_grid_sync(gb);
+    if (s + 1 < L) ps_wait(gb);
   }
 }
 
@@ -727,9 +751,13 @@ __global__ void __launch_bounds__(THREADS, 1) bilstm_persist_bwd_kernel(SeqBwd p
     }
     __syncthreads();
     __half* g16 = &g_ps_g16[par][d][0][0];
+    float r_d[2][4], r_dh[2], r_dc[2];
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < 2; ++it) {                 // phase 1: gate gradients; only the scaled fp16 rows other CTAs read are stored
       const int tt = threadIdx.x + it * THREADS;
+      r_dh[it] = r_dc[it] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r_d[it][q] = 0.f;
       if (tt >= UNITS * B) break;
       const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
       const size_t sb = (size_t)b * H + j;
@@ -741,16 +769,12 @@ __global__ void __launch_bounds__(THREADS, 1) bilstm_persist_bwd_kernel(SeqBwd p
         dh = red[u][b] + p.dh_pass[d][(size_t)(par ^ 1) * B * H + sb];
         dc = p.dc_work[d][(size_t)(par ^ 1) * B * H + sb];
       }
-      float* dg = p.dgates[d] + ((size_t)s * B + b) * G;
-      float* dh_pass = p.dh_pass[d] + (size_t)par * B * H;
-      float* dc_out = p.dc_work[d] + (size_t)par * B * H;
       __half* gh = g16 + (size_t)b * (4 * PS_MAXH);
-      if (l >= p.lengths[b]) {
-        dg[j] = 0.f; dg[H + j] = 0.f; dg[2 * H + j] = 0.f; dg[3 * H + j] = 0.f;
+      if (l >= p.lengths[b]) {                       // inactive: state was carried, pass gradients straight through
         const __half z = __float2half_rn(0.f);
         gh[j] = z; gh[H + j] = z; gh[2 * H + j] = z; gh[3 * H + j] = z;
-        dh_pass[sb] = dh;
-        dc_out[sb] = dc;
+        r_dh[it] = dh;
+        r_dc[it] = dc;
         continue;
       }
       dh += q_do[it];
@@ -758,19 +782,32 @@ __global__ void __launch_bounds__(THREADS, 1) bilstm_persist_bwd_kernel(SeqBwd p
       const float cp = q_cp[it];
       const float tc = tanhf(q_cn[it]);
       const float dct = dc + dh * og * (1.f - tc * tc);
-      const float d0 = dct * gg * ig * (1.f - ig), d1 = dct * cp * fg * (1.f - fg), d2 = dct * ig * (1.f - gg * gg),
-                  d3 = dh * tc * og * (1.f - og);
-      dg[j] = d0; dg[H + j] = d1; dg[2 * H + j] = d2; dg[3 * H + j] = d3;
-      unsigned short q0, q1, q2, q3;
-      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q0) : "f"(d0 * PS_GSCALE));
-      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q1) : "f"(d1 * PS_GSCALE));
-      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q2) : "f"(d2 * PS_GSCALE));
-      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(q3) : "f"(d3 * PS_GSCALE));
-      gh[j] = __ushort_as_half(q0); gh[H + j] = __ushort_as_half(q1); gh[2 * H + j] = __ushort_as_half(q2); gh[3 * H + j] = __ushort_as_half(q3);
-      dh_pass[sb] = 0.f;
-      dc_out[sb] = dct * fg;
+      r_d[it][0] = dct * gg * ig * (1.f - ig);
+      r_d[it][1] = dct * cp * fg * (1.f - fg);
+      r_d[it][2] = dct * ig * (1.f - gg * gg);
+      r_d[it][3] = dh * tc * og * (1.f - og);
+      r_dh[it] = 0.f;
+      r_dc[it] = dct * fg;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unsigned short hq;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hq) : "f"(r_d[it][q] * PS_GSCALE));
+        gh[q * H + j] = __ushort_as_half(hq);
+      }
     }
-    if (s > 0) ps_grid_sync(gb);
+    if (s > 0) ps_arrive(gb);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {                 // phase 2: fp32 gate gradients (weight gradients, later) and this thread's carries
+      const int tt = threadIdx.x + it * THREADS;
+      if (tt >= UNITS * B) break;
+      const int u = tt % UNITS, b = tt / UNITS, j = j0 + u;
+      const size_t sb = (size_t)b * H + j;
+      float* dg = p.dgates[d] + ((size_t)s * B + b) * G;
+      dg[j] = r_d[it][0]; dg[H + j] = r_d[it][1]; dg[2 * H + j] = r_d[it][2]; dg[3 * H + j] = r_d[it][3];
+      p.dh_pass[d][(size_t)par * B * H + sb] = r_dh[it];
+      p.dc_work[d][(size_t)par * B * H + sb] = r_dc[it];
+    }
+    if (s > 0) ps_wait(gb);
   }
 }
 
