@@ -60,6 +60,24 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
   __syncthreads();
 }
 
+// The barrier in two halves: stores issued BEFORE grid_arrive are visible to every CTA after its grid_wait; stores issued between the
+// halves (output rows nothing in this launch reads: dctx, dfeat) drain under the wait instead of in front of the arrive.
+__device__ __forceinline__ void grid_arrive(GridBar& gb) {
+  gb.target += gb.nblk;
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+}
+__device__ __forceinline__ void grid_wait(GridBar& gb) {
+  if (threadIdx.x == 0) {
+    unsigned int v, it = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      if (++it > (1u << 22)) __trap();
+    } while ((int)(v - gb.target) < 0);
+  }
+  __syncthreads();
+}
+
 // Phase timestamps of CTA 0 (SM clock) for the LAST launch: [0] = after the prologue barrier, then one per phase barrier of the
 // first DP_TIMED_ACTIONS actions. Read with dasa_debug_decoder_phase_clocks (profiling only; ~20 clock reads per action).
 constexpr int DP_TIMED_ACTIONS = 4;
@@ -1044,18 +1062,27 @@ __device__ __noinline__ void bwd_b5b(const dasa_decoder_bwd_t& a, const SmemPlan
   __syncthreads();
   dp_weighted_sum(sc, pl.pitchC, L, o.sl.cn, o.mask_b, sc.aux, a.dt2 + (tb + o.b) * D + o.sl.c0,      // dt2[c] = sum_l dz_l ctx[l, c]
                   bwd_x16(a).dt2 + (tb + o.b) * D + o.sl.c0, DP_GSCALE);
-  {                                                     // dctx[l, c] = alpha_l dwc[c] + dz_l t2[c]   (zero rows where masked)
-    const int n4 = o.sl.cn >> 2;
-    float* dst_b = a.dctx + ((tb + o.b) * L) * (int64_t)D + o.sl.c0;
-    for (int i = tid; i < L * n4; i += DP_THREADS) {
-      const int r = i / n4, col = i % n4;
-      const float wr = sc.prow[r], dz = sc.aux[r];
-      const float4 dw = reinterpret_cast<const float4*>(sc.dv)[col];
-      const float4 tv = reinterpret_cast<const float4*>(sc.tv)[col];
-      const float4 ov = make_float4(fmaf(wr, dw.x, dz * tv.x), fmaf(wr, dw.y, dz * tv.y), fmaf(wr, dw.z, dz * tv.z),
-                                    fmaf(wr, dw.w, dz * tv.w));
-      stg_stream4(dst_b + (int64_t)r * D + 4 * col, ov);
-    }
+  // the dctx rows are written by bwd_b5c between the two halves of this phase's barrier
+}
+
+// dctx[l, c] = alpha_l dwc[c] + dz_l t2[c] (zero rows where masked) from the vectors B5b left in shared memory; nothing in this
+// launch reads dctx, so the 95 KB of stores per CTA go out AFTER the CTA has arrived at the barrier
+__device__ __noinline__ void bwd_b5c(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.D, dp_mask_smem(raw, pl, a.ctx_mask));
+  if (!o.on) return;
+  const AttnSmem sc = dp_attn_smem(raw, pl, false);
+  const int tid = threadIdx.x, L = a.L, D = a.D;
+  const int64_t tb = (int64_t)t * a.B;
+  const int n4 = o.sl.cn >> 2;
+  float* dst_b = a.dctx + ((tb + o.b) * L) * (int64_t)D + o.sl.c0;
+  for (int i = tid; i < L * n4; i += DP_THREADS) {
+    const int r = i / n4, col = i % n4;
+    const float wr = sc.prow[r], dz = sc.aux[r];
+    const float4 dw = reinterpret_cast<const float4*>(sc.dv)[col];
+    const float4 tv = reinterpret_cast<const float4*>(sc.tv)[col];
+    const float4 ov = make_float4(fmaf(wr, dw.x, dz * tv.x), fmaf(wr, dw.y, dz * tv.y), fmaf(wr, dw.z, dz * tv.z),
+                                  fmaf(wr, dw.w, dz * tv.w));
+    stg_stream4(dst_b + (int64_t)r * D + 4 * col, ov);
   }
 }
 
@@ -1139,18 +1166,25 @@ __device__ __noinline__ void bwd_b2b(const dasa_decoder_bwd_t& a, const SmemPlan
   }
   __syncthreads();
   dp_weighted_sum(sf, pl.pitchF, V, o.sl.cn, nullptr, sf.aux, dtk_b + o.sl.c0, dtk16_b + o.sl.c0, DP_GSCALE);   // dt[c] = sum_v dz_v feat[v, c]
-  {                                                     // dfeat[v, c] = q_v dattn[c] + dz_v t[c]
-    const int n4 = o.sl.cn >> 2;
-    float* dst_b = a.dfeat + (int64_t)t * a.dfeat_ld_t + (int64_t)o.b * a.dfeat_ld_b + o.sl.c0;
-    for (int i = tid; i < V * n4; i += DP_THREADS) {
-      const int r = i / n4, col = i % n4;
-      const float wr = sf.wrow[r], dz = sf.aux[r];
-      const float4 dw = reinterpret_cast<const float4*>(sf.dv)[col];
-      const float4 tv = reinterpret_cast<const float4*>(sf.tv)[col];
-      const float4 ov = make_float4(fmaf(wr, dw.x, dz * tv.x), fmaf(wr, dw.y, dz * tv.y), fmaf(wr, dw.z, dz * tv.z),
-                                    fmaf(wr, dw.w, dz * tv.w));
-      stg_stream4(dst_b + (int64_t)r * a.dfeat_ld_row + 4 * col, ov);
-    }
+  // dfeat is written by bwd_b2c between the two halves of this phase's barrier
+}
+
+// dfeat[v, c] = q_v dattn[c] + dz_v t[c] from the vectors B2b left in shared memory (an output only, like dctx)
+__device__ __noinline__ void bwd_b2c(const dasa_decoder_bwd_t& a, const SmemPlan& pl, unsigned char* raw, int S, int t) {
+  const AttnOwner o = dp_owner(a.B, S, a.F, nullptr);
+  if (!o.on) return;
+  const AttnSmem sf = dp_attn_smem(raw, pl, true);
+  const int tid = threadIdx.x, V = a.V;
+  const int n4 = o.sl.cn >> 2;
+  float* dst_b = a.dfeat + (int64_t)t * a.dfeat_ld_t + (int64_t)o.b * a.dfeat_ld_b + o.sl.c0;
+  for (int i = tid; i < V * n4; i += DP_THREADS) {
+    const int r = i / n4, col = i % n4;
+    const float wr = sf.wrow[r], dz = sf.aux[r];
+    const float4 dw = reinterpret_cast<const float4*>(sf.dv)[col];
+    const float4 tv = reinterpret_cast<const float4*>(sf.tv)[col];
+    const float4 ov = make_float4(fmaf(wr, dw.x, dz * tv.x), fmaf(wr, dw.y, dz * tv.y), fmaf(wr, dw.z, dz * tv.z),
+                                  fmaf(wr, dw.w, dz * tv.w));
+    stg_stream4(dst_b + (int64_t)r * a.dfeat_ld_row + 4 * col, ov);
   }
 }
 
@@ -1204,7 +1238,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decoder_rollout_bwd_kernel(cons
           else bwd_gemm16<MT>(a, t, ph, red, res);                                            // B6 (other shapes), B4 (ph 3), B1 (ph 7)
           break;
       }
-      grid_sync(gb);
+      if (ph == 2 || ph == 6) {                             // big output-only rows leave between the halves of the barrier
+        grid_arrive(gb);
+        if (ph == 2) bwd_b5c(a, pl, smem_raw, S, t);
+        else bwd_b2c(a, pl, smem_raw, S, t);
+        grid_wait(gb);
+      } else {
+        grid_sync(gb);
+      }
       dp_stamp(1 + 8 * it + ph);
     }
   }
